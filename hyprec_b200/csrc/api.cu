@@ -1,0 +1,754 @@
+// C ABI of libhyprec_b200.so (declared in include/hyprec_b200.h): owns device memory, launches
+// the kernels of gram.cuh / als_solve.cuh / score.cuh / topk.cuh on one stream, reports errors
+// by code + message.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/hyprec_b200.h"
+#include "als_solve.cuh"
+#include "common.cuh"
+#include "gram.cuh"
+#include "score.cuh"
+#include "topk.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? HYPREC_E_NOMEM : HYPREC_E_CUDA,         \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+#define HY_TRY(expr)            \
+    do {                        \
+        int rc_ = (expr);       \
+        if (rc_ != HYPREC_OK) return rc_; \
+    } while (0)
+
+// Device buffer that only grows.
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want) {
+        if (want <= bytes) return HYPREC_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        CU_TRY(cudaMalloc(&ptr, want));
+        bytes = want;
+        return HYPREC_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    template <typename U>
+    U* as() const { return reinterpret_cast<U*>(ptr); }
+};
+
+struct Csr {
+    int64_t rows = 0, nnz = 0;
+    DevBuf indptr, indices, values;   // int64, int32, T
+    std::vector<int64_t> h_indptr;    // host copy of the row pointers (sharding, flag offsets)
+    void release() { indptr.release(); indices.release(); values.release(); }
+};
+
+constexpr int kNumTimers = 7;
+
+struct EngineBase {
+    virtual ~EngineBase() {}
+    virtual int set_train(int64_t m, int64_t n, const int64_t* indptr, const int32_t* indices, const double* values) = 0;
+    virtual int set_eval(const int64_t* fp, const int32_t* fi, const double* fv, const int64_t* tp,
+                         const int32_t* ti, const double* tv) = 0;
+    virtual int set_factors(const double* u, const double* v, int k) = 0;
+    virtual int get_factors(double* u, double* v) = 0;
+    virtual int set_prior(const double* theta) = 0;
+    virtual int half_step(int side, double lambda) = 0;
+    virtual int rmse(double* out) = 0;
+    virtual int predict_dense(double* out) = 0;
+    virtual int eval_topk(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci, int cap, double* thr,
+                          int64_t* ones, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) = 0;
+    virtual int device_factors(void** u, void** v, int* elem) = 0;
+};
+
+}  // namespace
+
+struct hyprec_ctx {
+    int device = 0;
+    int precision = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    int max_smem = 0;
+    int64_t launches = 0;
+    int64_t user_lo = 0, user_hi = -1, item_lo = 0, item_hi = -1;   // shard; hi < 0 => all
+    cudaEvent_t ev_begin[kNumTimers], ev_end[kNumTimers];
+    bool ev_used[kNumTimers];
+    EngineBase* engine = nullptr;
+};
+
+namespace {
+
+struct Timer {
+    hyprec_ctx* h;
+    int which;
+    Timer(hyprec_ctx* ctx, int w) : h(ctx), which(w) { cudaEventRecord(h->ev_begin[w], h->stream); }
+    ~Timer() {
+        cudaEventRecord(h->ev_end[which], h->stream);
+        h->ev_used[which] = true;
+    }
+};
+
+template <typename T>
+struct Engine : EngineBase {
+    hyprec_ctx* h;
+    int64_t m = 0, n = 0;
+    int k = 0;
+    Csr csr, csc, full, test;
+    DevBuf U, V, prior;
+    bool has_prior = false;
+    bool gram_ok[2] = {false, false};   // [0] = U^T U, [1] = V^T V match the current factors
+    DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
+    DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
+    DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk;
+
+    explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
+    ~Engine() override {
+        DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
+                         &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
+                         &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk};
+        for (DevBuf* b : all) b->release();
+        csr.release(); csc.release(); full.release(); test.release();
+    }
+
+    // ---------------------------------------------------------------- uploads
+    int upload_csr(Csr& dst, int64_t rows, int64_t cols, const int64_t* indptr, const int32_t* indices,
+                   const double* values, const char* what) {
+        if (!indptr || rows < 0) return fail(HYPREC_E_INVALID, std::string(what) + ": null indptr");
+        if (indptr[0] != 0) return fail(HYPREC_E_INVALID, std::string(what) + ": indptr[0] != 0");
+        const int64_t nnz = indptr[rows];
+        if (nnz > 0 && !indices) return fail(HYPREC_E_INVALID, std::string(what) + ": null indices");
+        for (int64_t r = 0; r < rows; ++r) {
+            if (indptr[r + 1] < indptr[r]) return fail(HYPREC_E_INVALID, std::string(what) + ": indptr not monotone");
+            for (int64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+                if (indices[e] < 0 || indices[e] >= cols)
+                    return fail(HYPREC_E_INVALID, std::string(what) + ": column id out of range");
+                if (e > indptr[r] && indices[e] <= indices[e - 1])
+                    return fail(HYPREC_E_INVALID, std::string(what) + ": column ids must be strictly increasing in a row");
+            }
+        }
+        dst.rows = rows;
+        dst.nnz = nnz;
+        dst.h_indptr.assign(indptr, indptr + rows + 1);
+        HY_TRY(dst.indptr.reserve(sizeof(int64_t) * (rows + 1)));
+        HY_TRY(dst.indices.reserve(sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+        HY_TRY(dst.values.reserve(sizeof(T) * std::max<int64_t>(nnz, 1)));
+        CU_TRY(cudaMemcpyAsync(dst.indptr.ptr, indptr, sizeof(int64_t) * (rows + 1), cudaMemcpyHostToDevice, h->stream));
+        if (nnz > 0) {
+            CU_TRY(cudaMemcpyAsync(dst.indices.ptr, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
+            std::vector<T> vals(nnz);
+            for (int64_t e = 0; e < nnz; ++e) vals[e] = values ? (T)values[e] : T(1);
+            CU_TRY(cudaMemcpyAsync(dst.values.ptr, vals.data(), sizeof(T) * nnz, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));   // vals goes out of scope
+        }
+        return HYPREC_OK;
+    }
+
+    int set_train(int64_t m_, int64_t n_, const int64_t* indptr, const int32_t* indices, const double* values) override {
+        if (m_ <= 0 || n_ <= 0) return fail(HYPREC_E_INVALID, "set_train_csr: empty matrix");
+        if (m_ != m || n_ != n) { k = 0; gram_ok[0] = gram_ok[1] = false; }
+        m = m_;
+        n = n_;
+        HY_TRY(upload_csr(csr, m, n, indptr, indices, values, "train"));
+        // item-major copy (counting sort keeps user ids increasing inside an item's list)
+        const int64_t nnz = indptr[m];
+        std::vector<int64_t> cptr(n + 1, 0);
+        for (int64_t e = 0; e < nnz; ++e) ++cptr[indices[e] + 1];
+        for (int64_t j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
+        std::vector<int32_t> cidx(std::max<int64_t>(nnz, 1));
+        std::vector<double> cval(std::max<int64_t>(nnz, 1));
+        std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
+        for (int64_t r = 0; r < m; ++r)
+            for (int64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+                const int64_t at = fill[indices[e]]++;
+                cidx[at] = (int32_t)r;
+                cval[at] = values ? values[e] : 1.0;
+            }
+        HY_TRY(upload_csr(csc, n, m, cptr.data(), cidx.data(), cval.data(), "train^T"));
+        return HYPREC_OK;
+    }
+
+    int set_eval(const int64_t* fp, const int32_t* fi, const double* fv, const int64_t* tp, const int32_t* ti,
+                 const double* tv) override {
+        if (m == 0) return fail(HYPREC_E_INVALID, "set_eval_csr before set_train_csr");
+        HY_TRY(upload_csr(full, m, n, fp, fi, fv, "ratings"));
+        // hit values are float64 in every mode (evaluator.py:287 multiplies the stored rating)
+        if (full.nnz > 0) {
+            HY_TRY(full.values.reserve(sizeof(double) * full.nnz));
+            std::vector<double> vals(full.nnz);
+            for (int64_t e = 0; e < full.nnz; ++e) vals[e] = fv ? fv[e] : 1.0;
+            CU_TRY(cudaMemcpyAsync(full.values.ptr, vals.data(), sizeof(double) * full.nnz, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+        }
+        HY_TRY(upload_csr(test, m, n, tp, ti, tv, "test"));
+        return HYPREC_OK;
+    }
+
+    int upload_matrix(DevBuf& dst, const double* src, int64_t rows) {
+        const size_t count = (size_t)rows * k;
+        HY_TRY(dst.reserve(sizeof(T) * count));
+        if (sizeof(T) == sizeof(double)) {
+            CU_TRY(cudaMemcpyAsync(dst.ptr, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+        } else {
+            std::vector<T> tmp(count);
+            for (size_t i = 0; i < count; ++i) tmp[i] = (T)src[i];
+            CU_TRY(cudaMemcpyAsync(dst.ptr, tmp.data(), sizeof(T) * count, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+        }
+        return HYPREC_OK;
+    }
+
+    int download_matrix(const DevBuf& src, double* dst, int64_t rows) {
+        const size_t count = (size_t)rows * k;
+        if (sizeof(T) == sizeof(double)) {
+            CU_TRY(cudaMemcpyAsync(dst, src.ptr, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+        } else {
+            std::vector<T> tmp(count);
+            CU_TRY(cudaMemcpyAsync(tmp.data(), src.ptr, sizeof(T) * count, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            for (size_t i = 0; i < count; ++i) dst[i] = (double)tmp[i];
+        }
+        return HYPREC_OK;
+    }
+
+    int set_factors(const double* u, const double* v, int k_) override {
+        if (m == 0) return fail(HYPREC_E_INVALID, "set_factors before set_train_csr");
+        if (k_ <= 0 || k_ > 2000) return fail(HYPREC_E_UNSUPPORTED, "n_factors must be in [1, 2000]");
+        if (!u || !v) return fail(HYPREC_E_INVALID, "set_factors: null matrix");
+        if (k_ != k) { has_prior = false; }
+        k = k_;
+        HY_TRY(upload_matrix(U, u, m));
+        HY_TRY(upload_matrix(V, v, n));
+        gram_ok[0] = gram_ok[1] = false;
+        return HYPREC_OK;
+    }
+
+    int get_factors(double* u, double* v) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "get_factors before set_factors");
+        if (u) HY_TRY(download_matrix(U, u, m));
+        if (v) HY_TRY(download_matrix(V, v, n));
+        return HYPREC_OK;
+    }
+
+    int set_prior(const double* theta) override {
+        if (!theta) { has_prior = false; return HYPREC_OK; }
+        if (k == 0) return fail(HYPREC_E_INVALID, "set_item_prior before set_factors");
+        HY_TRY(upload_matrix(prior, theta, n));
+        has_prior = true;
+        return HYPREC_OK;
+    }
+
+    int device_factors(void** u, void** v, int* elem) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "device_factors before set_factors");
+        if (u) *u = U.ptr;
+        if (v) *v = V.ptr;
+        if (elem) *elem = (int)sizeof(T);
+        gram_ok[0] = gram_ok[1] = false;   // the caller may write through these pointers
+        return HYPREC_OK;
+    }
+
+    // ---------------------------------------------------------------- Gram / column sums
+    int compute_gram(int which) {   // 0: U, 1: V
+        if (gram_ok[which]) return HYPREC_OK;
+        const T* y = which == 0 ? U.as<T>() : V.as<T>();
+        const int64_t rows = which == 0 ? m : n;
+        const int ntile = (k + hyprec::kGramTile - 1) / hyprec::kGramTile;
+        const int tiles = hyprec::tri(ntile);
+        int nsplit = (int)std::min<int64_t>((rows + 255) / 256, std::max(1, (4 * h->num_sms) / tiles));
+        nsplit = std::max(nsplit, 1);
+        int64_t per = (rows + nsplit - 1) / nsplit;
+        per = (per + hyprec::kGramRows - 1) / hyprec::kGramRows * hyprec::kGramRows;
+        nsplit = (int)((rows + per - 1) / per);
+        HY_TRY(gram_partial.reserve(sizeof(T) * (size_t)nsplit * k * k));
+        HY_TRY(gram[which].reserve(sizeof(T) * (size_t)k * k));
+        Timer t(h, HYPREC_T_GRAM);
+        hyprec::gram_partial_kernel<T><<<dim3(tiles, nsplit), hyprec::kGramThreads, 0, h->stream>>>(
+            y, rows, k, per, gram_partial.as<T>());
+        hyprec::gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, h->stream>>>(
+            gram_partial.as<T>(), nsplit, k, gram[which].as<T>());
+        h->launches += 2;
+        CU_TRY(cudaGetLastError());
+        gram_ok[which] = true;
+        return HYPREC_OK;
+    }
+
+    int compute_colsum_v() {
+        int nsplit = (int)std::min<int64_t>(std::max<int64_t>(n / 64, 1), 4 * h->num_sms);
+        const int64_t per = (n + nsplit - 1) / nsplit;
+        nsplit = (int)((n + per - 1) / per);
+        HY_TRY(colsum_partial.reserve(sizeof(double) * (size_t)nsplit * k));
+        HY_TRY(colsum.reserve(sizeof(double) * k));
+        hyprec::colsum_partial_kernel<T><<<nsplit, 256, 0, h->stream>>>(V.as<T>(), n, k, per, colsum_partial.as<double>());
+        hyprec::colsum_reduce_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(colsum_partial.as<double>(), nsplit, k,
+                                                                               colsum.as<double>());
+        h->launches += 2;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
+    // ---------------------------------------------------------------- ALS half-step
+    int half_step(int side, double lambda) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "als_half_step before set_factors");
+        if (side != HYPREC_SIDE_USER && side != HYPREC_SIDE_ITEM) return fail(HYPREC_E_INVALID, "side must be 0 or 1");
+        const bool user = side == HYPREC_SIDE_USER;
+        const Csr& rows_csr = user ? csr : csc;
+        const int64_t total = user ? m : n;
+        int64_t lo = user ? h->user_lo : h->item_lo, hi = user ? h->user_hi : h->item_hi;
+        if (hi < 0) { lo = 0; hi = total; }
+        if (lo < 0 || hi > total || lo > hi) return fail(HYPREC_E_INVALID, "shard outside the matrix");
+
+        HY_TRY(compute_gram(user ? 1 : 0));   // Gram of the FIXED side
+        const int nb = hyprec::aug_blocks(k), n_tiles = hyprec::tri(nb);
+        HY_TRY(base.reserve(sizeof(T) * (size_t)hyprec::kTileElems * n_tiles));
+        {
+            const int total_e = hyprec::kTileElems * n_tiles;
+            hyprec::build_base_tiles_kernel<T><<<(total_e + 255) / 256, 256, 0, h->stream>>>(
+                gram[user ? 1 : 0].as<T>(), k, (T)lambda, base.as<T>());
+            h->launches += 1;
+        }
+        if (hi == lo) return HYPREC_OK;
+
+        // shared-memory plan: tiles in shared memory when they fit, else per-CTA global scratch
+        int chunk = 32;
+        hyprec::SolveLayout lay = hyprec::solve_layout(k, chunk, true, sizeof(T));
+        while (lay.total > (size_t)h->max_smem && chunk > 4) {
+            chunk /= 2;
+            lay = hyprec::solve_layout(k, chunk, true, sizeof(T));
+        }
+        const bool in_smem = lay.total <= (size_t)h->max_smem;
+        if (!in_smem) {
+            chunk = 16;
+            lay = hyprec::solve_layout(k, chunk, false, sizeof(T));
+            if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "n_factors too large for the solve kernel");
+        }
+        auto kern = hyprec::als_solve_rows_kernel<T>;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+        int per_sm = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, hyprec::kSolveThreads, lay.total));
+        if (per_sm < 1) return fail(HYPREC_E_UNSUPPORTED, "solve kernel does not fit on an SM");
+        const int grid = (int)std::min<int64_t>(hi - lo, (int64_t)per_sm * h->num_sms);
+        if (!in_smem) HY_TRY(a_scratch.reserve(sizeof(T) * (size_t)grid * hyprec::kTileElems * n_tiles));
+        HY_TRY(counter.reserve(2 * sizeof(int)));
+        CU_TRY(cudaMemsetAsync(counter.ptr, 0, 2 * sizeof(int), h->stream));
+
+        hyprec::SolveArgs<T> a;
+        a.indptr = rows_csr.indptr.template as<int64_t>();
+        a.indices = rows_csr.indices.template as<int32_t>();
+        a.values = rows_csr.values.template as<T>();
+        a.fixed = user ? V.as<T>() : U.as<T>();
+        a.latent = user ? U.as<T>() : V.as<T>();
+        a.base = base.as<T>();
+        a.prior = (!user && has_prior) ? prior.as<T>() : nullptr;
+        a.a_scratch = in_smem ? nullptr : a_scratch.as<T>();
+        a.work_counter = counter.as<int>();
+        a.status = counter.as<int>() + 1;
+        a.lambda = (T)lambda;
+        a.k = k;
+        a.row_lo = lo;
+        a.row_hi = hi;
+        a.chunk_rows = chunk;
+        {
+            Timer t(h, HYPREC_T_SOLVE);
+            kern<<<grid, hyprec::kSolveThreads, lay.total, h->stream>>>(a);
+            h->launches += 1;
+        }
+        CU_TRY(cudaGetLastError());
+        gram_ok[user ? 0 : 1] = false;
+        int status[2] = {0, 0};
+        CU_TRY(cudaMemcpyAsync(status, counter.ptr, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (status[1] != 0)
+            return fail(HYPREC_E_SINGULAR, "als_half_step: non-finite solution (singular normal matrix; lambda == 0?)");
+        return HYPREC_OK;
+    }
+
+    // ---------------------------------------------------------------- RMSE
+    int rmse(double* out) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "rmse before set_factors");
+        HY_TRY(compute_gram(0));
+        HY_TRY(compute_gram(1));
+        HY_TRY(row_s1.reserve(sizeof(double) * m));
+        HY_TRY(row_s2.reserve(sizeof(double) * m));
+        HY_TRY(scalars.reserve(sizeof(double) * 4));
+        {
+            Timer t(h, HYPREC_T_RMSE);
+            hyprec::frob_inner_kernel<T><<<1, 256, 0, h->stream>>>(gram[0].as<T>(), gram[1].as<T>(), k * k,
+                                                                     scalars.as<double>());
+            const int wpb = 8;
+            hyprec::sddmm_row_kernel<T><<<(unsigned)((m + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
+                csr.indptr.template as<int64_t>(), csr.indices.template as<int32_t>(), csr.values.template as<T>(),
+                U.as<T>(), V.as<T>(), k, m, row_s1.as<double>(), row_s2.as<double>());
+            hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s1.as<double>(), m, scalars.as<double>() + 1);
+            hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s2.as<double>(), m, scalars.as<double>() + 2);
+            h->launches += 4;
+        }
+        CU_TRY(cudaGetLastError());
+        double s[3];
+        CU_TRY(cudaMemcpyAsync(s, scalars.ptr, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        double rss = s[0] - 2.0 * s[1] + s[2];
+        if (rss < 0.0) rss = 0.0;
+        *out = sqrt(rss / ((double)m * (double)n));
+        return HYPREC_OK;
+    }
+
+    // ---------------------------------------------------------------- dense prediction
+    int predict_dense(double* out) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "predict_dense before set_factors");
+        if (!out) return fail(HYPREC_E_INVALID, "predict_dense: null output");
+        int64_t blk = std::max<int64_t>(hyprec::kSweepTile, ((int64_t)256 << 20) / (8 * n) / hyprec::kSweepTile * hyprec::kSweepTile);
+        blk = std::min(blk, (m + hyprec::kSweepTile - 1) / hyprec::kSweepTile * hyprec::kSweepTile);
+        HY_TRY(dense_blk.reserve(sizeof(double) * (size_t)blk * n));
+        for (int64_t lo = 0; lo < m; lo += blk) {
+            const int64_t hi = std::min(m, lo + blk);
+            hyprec::SweepArgs<T> a;
+            a.user_vecs = U.as<T>();
+            a.item_vecs = V.as<T>();
+            a.k = k;
+            a.user_lo = lo;
+            a.user_hi = hi;
+            a.n_items = n;
+            a.dense_out = dense_blk.as<double>();
+            a.thresholds = nullptr;
+            a.counts = nullptr;
+            dim3 grid((unsigned)((n + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
+                      (unsigned)((hi - lo + hyprec::kSweepTile - 1) / hyprec::kSweepTile));
+            {
+                Timer t(h, HYPREC_T_SWEEP);
+                hyprec::score_sweep_kernel<T, hyprec::kSweepStore><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(a);
+                h->launches += 1;
+            }
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(out + lo * n, dense_blk.ptr, sizeof(double) * (size_t)(hi - lo) * n,
+                                   cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+        }
+        return HYPREC_OK;
+    }
+
+    // ---------------------------------------------------------------- evaluation
+    int eval_topk(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci, int cap, double* thr_out,
+                  int64_t* ones_out, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "eval_topk before set_factors");
+        if (lo < 0 || hi > m || lo > hi) return fail(HYPREC_E_INVALID, "eval_topk: user range outside the matrix");
+        const int64_t nu = hi - lo;
+        const bool want_topk = tidx || tval || thit;
+        if (want_topk && (cap <= 0 || cap > 4096)) return fail(HYPREC_E_UNSUPPORTED, "capacity must be in [1, 4096]");
+        if (ci && !cp) return fail(HYPREC_E_INVALID, "eval_topk: candidate ids without indptr");
+        if ((trf || tef || thit) && full.rows != m) return fail(HYPREC_E_INVALID, "eval_topk: set_eval_csr first");
+
+        // thresholds for every user (cheap), float64
+        HY_TRY(compute_colsum_v());
+        HY_TRY(thresholds.reserve(sizeof(double) * m));
+        {
+            const int wpb = 8;
+            hyprec::row_threshold_kernel<T><<<(unsigned)((m + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
+                U.as<T>(), colsum.as<double>(), k, m, n, thresholds.as<double>());
+            h->launches += 1;
+            CU_TRY(cudaGetLastError());
+        }
+        if (nu == 0) return HYPREC_OK;
+        if (thr_out)
+            CU_TRY(cudaMemcpyAsync(thr_out, thresholds.as<double>() + lo, sizeof(double) * nu, cudaMemcpyDeviceToHost, h->stream));
+
+        if (ones_out) {
+            HY_TRY(counts.reserve(sizeof(unsigned long long) * nu));
+            CU_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(unsigned long long) * nu, h->stream));
+            hyprec::SweepArgs<T> a;
+            a.user_vecs = U.as<T>();
+            a.item_vecs = V.as<T>();
+            a.k = k;
+            a.user_lo = lo;
+            a.user_hi = hi;
+            a.n_items = n;
+            a.dense_out = nullptr;
+            a.thresholds = thresholds.as<double>();
+            a.counts = counts.as<unsigned long long>();
+            dim3 grid((unsigned)((n + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
+                      (unsigned)((nu + hyprec::kSweepTile - 1) / hyprec::kSweepTile));
+            {
+                Timer t(h, HYPREC_T_COUNT);
+                hyprec::score_sweep_kernel<T, hyprec::kSweepCount><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(a);
+                h->launches += 1;
+            }
+            CU_TRY(cudaGetLastError());
+            static_assert(sizeof(unsigned long long) == sizeof(int64_t), "count width");
+            CU_TRY(cudaMemcpyAsync(ones_out, counts.ptr, sizeof(int64_t) * nu, cudaMemcpyDeviceToHost, h->stream));
+        }
+
+        if (want_topk) {
+            int64_t max_cand = n;
+            if (ci) {
+                max_cand = 0;
+                if (cp[0] != 0) return fail(HYPREC_E_INVALID, "eval_topk: cand_indptr[0] != 0");
+                for (int64_t u = 0; u < nu; ++u) {
+                    if (cp[u + 1] < cp[u]) return fail(HYPREC_E_INVALID, "eval_topk: cand_indptr not monotone");
+                    max_cand = std::max(max_cand, cp[u + 1] - cp[u]);
+                }
+                const int64_t total = cp[nu];
+                for (int64_t e = 0; e < total; ++e)
+                    if (ci[e] < 0 || ci[e] >= n) return fail(HYPREC_E_INVALID, "eval_topk: candidate id out of range");
+                HY_TRY(cand_ptr.reserve(sizeof(int64_t) * (nu + 1)));
+                HY_TRY(cand_ids.reserve(sizeof(int32_t) * std::max<int64_t>(total, 1)));
+                CU_TRY(cudaMemcpyAsync(cand_ptr.ptr, cp, sizeof(int64_t) * (nu + 1), cudaMemcpyHostToDevice, h->stream));
+                if (total > 0)
+                    CU_TRY(cudaMemcpyAsync(cand_ids.ptr, ci, sizeof(int32_t) * total, cudaMemcpyHostToDevice, h->stream));
+            }
+            int sort_size = 2;
+            while (sort_size < cap) sort_size <<= 1;
+            max_cand = std::max<int64_t>(max_cand, 1);
+            const hyprec::TopkLayout lay = hyprec::topk_layout((int)max_cand, k, sort_size);
+            if (lay.total > (size_t)h->max_smem)
+                return fail(HYPREC_E_UNSUPPORTED, "eval_topk: candidate list too long for one CTA's shared memory");
+            auto kern = hyprec::eval_topk_kernel<T>;
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+            int per_sm = 0;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, hyprec::kTopkThreads, lay.total));
+            per_sm = std::max(per_sm, 1);
+            const int grid = (int)std::min<int64_t>(nu, (int64_t)per_sm * h->num_sms);
+            HY_TRY(out_idx.reserve(sizeof(int32_t) * (size_t)nu * cap));
+            HY_TRY(out_val.reserve(sizeof(double) * (size_t)nu * cap));
+            HY_TRY(out_hit.reserve(sizeof(double) * (size_t)nu * cap));
+            hyprec::TopkArgs<T> a;
+            a.user_vecs = U.as<T>();
+            a.item_vecs = V.as<T>();
+            a.k = k;
+            a.n_items = n;
+            a.user_lo = lo;
+            a.user_hi = hi;
+            a.cand_indptr = ci ? cand_ptr.as<int64_t>() : nullptr;
+            a.cand_ids = ci ? cand_ids.as<int32_t>() : nullptr;
+            a.thresholds = thresholds.as<double>();
+            const bool have_full = full.rows == m;
+            a.full_indptr = have_full ? full.indptr.template as<int64_t>() : nullptr;
+            a.full_indices = have_full ? full.indices.template as<int32_t>() : nullptr;
+            a.full_values = have_full ? full.values.template as<double>() : nullptr;
+            a.capacity = cap;
+            a.sort_size = sort_size;
+            a.max_cand = (int)max_cand;
+            a.topk_idx = out_idx.as<int32_t>();
+            a.topk_val = out_val.as<double>();
+            a.topk_hit = out_hit.as<double>();
+            {
+                Timer t(h, HYPREC_T_TOPK);
+                kern<<<grid, hyprec::kTopkThreads, lay.total, h->stream>>>(a);
+                h->launches += 1;
+            }
+            CU_TRY(cudaGetLastError());
+            if (tidx) CU_TRY(cudaMemcpyAsync(tidx, out_idx.ptr, sizeof(int32_t) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
+            if (tval) CU_TRY(cudaMemcpyAsync(tval, out_val.ptr, sizeof(double) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
+            if (thit) CU_TRY(cudaMemcpyAsync(thit, out_hit.ptr, sizeof(double) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
+        }
+
+        // rounded predictions at train / test non-zeros
+        const Csr* which[2] = {&csr, &test};
+        uint8_t* outs[2] = {trf, tef};
+        for (int s = 0; s < 2; ++s) {
+            if (!outs[s]) continue;
+            const Csr& c = *which[s];
+            if (c.rows != m) return fail(HYPREC_E_INVALID, "eval_topk: test matrix missing (set_eval_csr)");
+            const int64_t e0 = c.h_indptr[lo], e1 = c.h_indptr[hi];
+            if (e1 == e0) continue;
+            HY_TRY(flags.reserve((size_t)(e1 - e0)));
+            const int wpb = 8;
+            {
+                Timer t(h, HYPREC_T_FLAGS);
+                hyprec::nz_flags_kernel<T><<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
+                    c.indptr.template as<int64_t>(), c.indices.template as<int32_t>(), U.as<T>(), V.as<T>(), k,
+                    thresholds.as<double>(), lo, hi, flags.as<uint8_t>());
+                h->launches += 1;
+            }
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(outs[s], flags.ptr, (size_t)(e1 - e0), cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));   // flags buffer is reused for the next matrix
+        }
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        return HYPREC_OK;
+    }
+};
+
+int check(hyprec_t* h) {
+    if (!h || !h->engine) return fail(HYPREC_E_INVALID, "null handle");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(HYPREC_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return HYPREC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hyprec_abi_version(void) { return 1; }
+
+const char* hyprec_last_error(void) { return g_error.c_str(); }
+
+int hyprec_create(hyprec_t** out, int device_id, int precision) {
+    if (!out) return fail(HYPREC_E_INVALID, "hyprec_create: null output");
+    *out = nullptr;
+    if (precision != HYPREC_F64 && precision != HYPREC_F32) return fail(HYPREC_E_INVALID, "precision must be 0 (f64) or 1 (f32)");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(HYPREC_E_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                       " (hyprec_b200 has no CPU fallback)");
+    if (device_id < 0 || device_id >= count) return fail(HYPREC_E_INVALID, "device id out of range");
+    CU_TRY(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device_id));
+    hyprec_ctx* h = new hyprec_ctx();
+    h->device = device_id;
+    h->precision = precision;
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kNumTimers; ++i) {
+        CU_TRY(cudaEventCreate(&h->ev_begin[i]));
+        CU_TRY(cudaEventCreate(&h->ev_end[i]));
+        h->ev_used[i] = false;
+    }
+    if (precision == HYPREC_F64) h->engine = new Engine<double>(h);
+    else h->engine = new Engine<float>(h);
+    *out = h;
+    return HYPREC_OK;
+}
+
+int hyprec_destroy(hyprec_t* h) {
+    if (!h) return HYPREC_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    delete h->engine;
+    for (int i = 0; i < kNumTimers; ++i) {
+        cudaEventDestroy(h->ev_begin[i]);
+        cudaEventDestroy(h->ev_end[i]);
+    }
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return HYPREC_OK;
+}
+
+int64_t hyprec_launch_count(const hyprec_t* h) { return h ? h->launches : 0; }
+
+int hyprec_set_train_csr(hyprec_t* h, int64_t m, int64_t n, const int64_t* indptr, const int32_t* indices,
+                         const double* values) {
+    HY_TRY(check(h));
+    return h->engine->set_train(m, n, indptr, indices, values);
+}
+
+int hyprec_set_shard(hyprec_t* h, int64_t user_lo, int64_t user_hi, int64_t item_lo, int64_t item_hi) {
+    HY_TRY(check(h));
+    h->user_lo = user_lo; h->user_hi = user_hi; h->item_lo = item_lo; h->item_hi = item_hi;
+    return HYPREC_OK;
+}
+
+int hyprec_set_factors(hyprec_t* h, const double* u, const double* v, int k) {
+    HY_TRY(check(h));
+    return h->engine->set_factors(u, v, k);
+}
+
+int hyprec_get_factors(hyprec_t* h, double* u, double* v) {
+    HY_TRY(check(h));
+    return h->engine->get_factors(u, v);
+}
+
+int hyprec_device_factors(hyprec_t* h, void** u, void** v, int* elem) {
+    HY_TRY(check(h));
+    return h->engine->device_factors(u, v, elem);
+}
+
+int hyprec_set_item_prior(hyprec_t* h, const double* theta) {
+    HY_TRY(check(h));
+    return h->engine->set_prior(theta);
+}
+
+int hyprec_als_half_step(hyprec_t* h, int side, double lambda) {
+    HY_TRY(check(h));
+    return h->engine->half_step(side, lambda);
+}
+
+int hyprec_rmse(hyprec_t* h, double* out) {
+    HY_TRY(check(h));
+    if (!out) return fail(HYPREC_E_INVALID, "hyprec_rmse: null output");
+    return h->engine->rmse(out);
+}
+
+int hyprec_train(hyprec_t* h, int n_iter, double lambda, double start_error, hyprec_epoch_cb cb, void* user,
+                 int* epochs_run, double* last_rmse) {
+    HY_TRY(check(h));
+    if (h->user_hi >= 0 || h->item_hi >= 0)
+        return fail(HYPREC_E_INVALID, "hyprec_train with a shard set: loop hyprec_als_half_step and exchange shards instead");
+    double error = start_error;
+    int done = 0;
+    for (int epoch = 1; epoch <= n_iter; ++epoch) {
+        const double old_error = error;
+        const auto t0 = std::chrono::steady_clock::now();
+        HY_TRY(h->engine->half_step(HYPREC_SIDE_USER, lambda));
+        HY_TRY(h->engine->half_step(HYPREC_SIDE_ITEM, lambda));
+        const auto t1 = std::chrono::steady_clock::now();
+        HY_TRY(h->engine->rmse(&error));
+        done = epoch;
+        if (cb) cb(epoch, error, std::chrono::duration<double>(t1 - t0).count(), user);
+        if (error >= old_error) break;   // collaborative_filtering.py:256
+    }
+    if (epochs_run) *epochs_run = done;
+    if (last_rmse) *last_rmse = error;
+    return HYPREC_OK;
+}
+
+int hyprec_predict_dense(hyprec_t* h, double* out) {
+    HY_TRY(check(h));
+    return h->engine->predict_dense(out);
+}
+
+int hyprec_set_eval_csr(hyprec_t* h, const int64_t* fp, const int32_t* fi, const double* fv, const int64_t* tp,
+                        const int32_t* ti, const double* tv) {
+    HY_TRY(check(h));
+    return h->engine->set_eval(fp, fi, fv, tp, ti, tv);
+}
+
+int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
+                     const int32_t* cand_ids, int capacity, double* thresholds, int64_t* ones_per_row,
+                     int32_t* topk_idx, double* topk_val, double* topk_hit, uint8_t* train_flags,
+                     uint8_t* test_flags) {
+    HY_TRY(check(h));
+    return h->engine->eval_topk(user_lo, user_hi, cand_indptr, cand_ids, capacity, thresholds, ones_per_row,
+                                topk_idx, topk_val, topk_hit, train_flags, test_flags);
+}
+
+int hyprec_last_kernel_ms(hyprec_t* h, int which, float* ms) {
+    HY_TRY(check(h));
+    if (which < 0 || which >= kNumTimers || !ms) return fail(HYPREC_E_INVALID, "hyprec_last_kernel_ms: bad argument");
+    if (!h->ev_used[which]) { *ms = 0.f; return HYPREC_OK; }
+    CU_TRY(cudaEventSynchronize(h->ev_end[which]));
+    CU_TRY(cudaEventElapsedTime(ms, h->ev_begin[which], h->ev_end[which]));
+    return HYPREC_OK;
+}
+
+}  // extern "C"

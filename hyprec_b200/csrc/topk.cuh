@@ -1,0 +1,249 @@
+// Fused candidate scoring + top-k + hit flags, one CTA per user; the scores of a user's
+// candidates live only in shared memory.
+//
+// Replaces /root/reference/lib/evaluator.py:215-234 (load_top_recommendations) together with the
+// container it streams into, /root/reference/util/top_recommendations.py:23-40, and the hit
+// product of evaluator.py:287-288 / :309 / :333 (`self.ratings[user][idx] * rounded[user][idx]`).
+//
+// Order contract: the reference keeps an ascending list with bisect_right
+// insertion and a STRICT `<` admission test, then reverses it.  Result: score descending, equal
+// scores later-streamed first; everything strictly above the capacity-th largest score is kept;
+// elements EQUAL to that cut-off form a FIFO (admitted while the list is not full, rejected when
+// it is, oldest evicted when a strictly larger element finds the list full).  The kernel finds
+// the cut-off with an 8-pass radix select over order-preserving 64-bit keys, replays the FIFO
+// only over elements >= cut-off, and bitonic-sorts the <= capacity survivors by
+// (key desc, stream position desc).
+#pragma once
+#include "common.cuh"
+#include "score.cuh"
+
+namespace hyprec {
+
+constexpr int kTopkThreads = 256;
+
+struct TopkLayout {
+    size_t off_keys, off_u, off_selkey, off_selpos, off_fifo, off_hist, total;
+};
+
+HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size) {
+    TopkLayout l;
+    size_t o = 0;
+    l.off_keys = o;
+    o += 8 * (size_t)max_cand;
+    l.off_u = o;
+    o += 8 * (size_t)k;
+    l.off_selkey = o;
+    o += 8 * (size_t)sort_size;
+    l.off_selpos = o;
+    o += 4 * (size_t)sort_size;
+    l.off_fifo = o;
+    o += 4 * (size_t)sort_size;
+    l.off_hist = o;
+    o += 4 * 256;
+    l.total = (o + 15) & ~(size_t)15;
+    return l;
+}
+
+template <typename T>
+struct TopkArgs {
+    const T* user_vecs;
+    const T* item_vecs;
+    int k;
+    int64_t n_items;
+    int64_t user_lo, user_hi;
+    const int64_t* cand_indptr;   // relative to user_lo, or null => all items
+    const int32_t* cand_ids;      // or null => all items in index order
+    const double* thresholds;     // [n_users]
+    const int64_t* full_indptr;   // full ratings CSR (global user ids); may be null => hit = 0
+    const int32_t* full_indices;
+    const double* full_values;
+    int capacity;                 // n_recommendations
+    int sort_size;                // power of two >= capacity
+    int max_cand;                 // shared-memory capacity for keys
+    int32_t* topk_idx;            // [n_local_users][capacity], -1 padded
+    double* topk_val;
+    double* topk_hit;
+};
+
+// order-preserving map double -> uint64 (larger score <=> larger key)
+__device__ __forceinline__ unsigned long long score_key(double s) {
+    s = s + 0.0;   // -0.0 -> +0.0: the reference compares floats, where they are equal
+    unsigned long long b = (unsigned long long)__double_as_longlong(s);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_score(unsigned long long key) {
+    unsigned long long b = (key & 0x8000000000000000ull) ? (key & 0x7fffffffffffffffull) : ~key;
+    return __longlong_as_double((long long)b);
+}
+// a is listed before b
+__device__ __forceinline__ bool topk_before(unsigned long long ka, int pa, unsigned long long kb, int pb) {
+    return ka > kb || (ka == kb && pa > pb);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) {
+    HYPREC_DYN_SMEM(smem_raw);
+    __shared__ int s_digit, s_need, s_count, s_nsel;
+    const TopkLayout lay = topk_layout(p.max_cand, p.k, p.sort_size);
+    unsigned long long* keys = (unsigned long long*)(smem_raw + lay.off_keys);
+    double* uvec = (double*)(smem_raw + lay.off_u);
+    unsigned long long* selkey = (unsigned long long*)(smem_raw + lay.off_selkey);
+    int* selpos = (int*)(smem_raw + lay.off_selpos);
+    int* fifo = (int*)(smem_raw + lay.off_fifo);
+    unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int k = p.k, cap = p.capacity, P = p.sort_size;
+
+    for (int64_t u = p.user_lo + blockIdx.x; u < p.user_hi; u += gridDim.x) {
+        const int64_t ul = u - p.user_lo;
+        const int64_t cbase = p.cand_ids ? p.cand_indptr[ul] : 0;
+        const int ncand = p.cand_ids ? (int)(p.cand_indptr[ul + 1] - cbase) : (int)p.n_items;
+        __syncthreads();   // previous user's shared state is dead
+        for (int c = tid; c < k; c += kTopkThreads) uvec[c] = (double)p.user_vecs[u * k + c];
+        if (tid == 0) s_nsel = 0;
+        __syncthreads();
+
+        // ---- scores: one warp per candidate, coalesced read of the item's factor row ---------
+        for (int c = warp; c < ncand; c += kTopkThreads / 32) {
+            const int64_t item = p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c;
+            const double s = warp_dot(uvec, p.item_vecs + item * k, k, lane);
+            if (lane == 0) keys[c] = score_key(s);
+        }
+        __syncthreads();
+
+        // ---- cut-off = capacity-th largest key (radix select, 8 bits per pass) ---------------
+        unsigned long long prefix = 0, mask = 0;
+        int need = cap;          // how many elements equal to the cut-off are kept
+        int n_equal = 0;         // how many elements equal the cut-off
+        const bool select = ncand > cap;
+        if (select) {
+            for (int pass = 0; pass < 8; ++pass) {
+                const int shift = 56 - 8 * pass;
+                hist[tid] = 0;
+                __syncthreads();
+                for (int i = tid; i < ncand; i += kTopkThreads) {
+                    const unsigned long long key = keys[i];
+                    if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned loc[8], tot = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        loc[b] = hist[8 * lane + b];
+                        tot += loc[b];
+                    }
+                    unsigned suf = tot;   // suffix sum over lanes >= lane (bins from the top)
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned o = __shfl_down_sync(0xffffffffu, suf, d);
+                        if (lane + d < 32) suf += o;
+                    }
+                    unsigned above = __shfl_down_sync(0xffffffffu, suf, 1);
+                    if (lane == 31) above = 0;
+                    if (suf >= (unsigned)need && above < (unsigned)need) {
+                        unsigned cum = above;
+                        for (int b = 7; b >= 0; --b) {
+                            if (cum + loc[b] >= (unsigned)need) {
+                                s_digit = 8 * lane + b;
+                                s_need = need - (int)cum;
+                                s_count = (int)loc[b];
+                                break;
+                            }
+                            cum += loc[b];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= (unsigned long long)s_digit << shift;
+                mask |= 0xffull << shift;
+                need = s_need;
+                n_equal = s_count;
+            }
+        }
+
+        // ---- survivors -------------------------------------------------------------------------
+        const bool replay = select && n_equal != need;   // tie straddles the cut-off
+        for (int i = tid; i < ncand; i += kTopkThreads) {
+            const unsigned long long key = keys[i];
+            if (!select || key > prefix || (!replay && key == prefix)) {
+                const int slot = atomicAdd(&s_nsel, 1);
+                selkey[slot] = key;
+                selpos[slot] = i;
+            }
+        }
+        __syncthreads();
+        if (replay && tid == 0) {
+            // stream order matters only among elements >= cut-off
+            int held = 0, head = 0, tail = 0;
+            for (int i = 0; i < ncand; ++i) {
+                const unsigned long long key = keys[i];
+                if (key > prefix) {
+                    if (held == cap) ++head; else ++held;
+                } else if (key == prefix && held < cap) {
+                    fifo[tail % P] = i;
+                    ++tail;
+                    ++held;
+                }
+            }
+            int slot = s_nsel;
+            for (int q = head; q < tail; ++q) {
+                selkey[slot] = prefix;
+                selpos[slot] = fifo[q % P];
+                ++slot;
+            }
+            s_nsel = slot;
+        }
+        __syncthreads();
+        const int nsel = s_nsel;
+        for (int i = nsel + tid; i < P; i += kTopkThreads) {
+            selkey[i] = 0;     // below every finite score's key
+            selpos[i] = -1;
+        }
+        __syncthreads();
+
+        // ---- bitonic sort of the survivors: (key desc, stream position desc) -----------------
+        for (int size = 2; size <= P; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = tid; i < P / 2; i += kTopkThreads) {
+                    const int lo = 2 * i - (i & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const unsigned long long kl = selkey[lo], kh = selkey[hi];
+                    const int pl = selpos[lo], ph = selpos[hi];
+                    const bool swap = up ? topk_before(kh, ph, kl, pl) : topk_before(kl, pl, kh, ph);
+                    if (swap) {
+                        selkey[lo] = kh; selkey[hi] = kl;
+                        selpos[lo] = ph; selpos[hi] = pl;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- outputs ---------------------------------------------------------------------------
+        const double thr = p.thresholds[u];
+        for (int r = tid; r < cap; r += kTopkThreads) {
+            int32_t item = -1;
+            double val = 0.0, hit = 0.0;
+            if (r < nsel) {
+                const int pos = selpos[r];
+                item = p.cand_ids ? p.cand_ids[cbase + pos] : (int32_t)pos;
+                val = key_score(selkey[r]);
+                if (p.full_indptr != nullptr && val >= thr) {
+                    int64_t a = p.full_indptr[u], b = p.full_indptr[u + 1];
+                    while (a < b) {   // lower bound of item in the sorted row
+                        const int64_t mid = (a + b) >> 1;
+                        if (p.full_indices[mid] < item) a = mid + 1; else b = mid;
+                    }
+                    if (a < p.full_indptr[u + 1] && p.full_indices[a] == item) hit = p.full_values[a];
+                }
+            }
+            if (p.topk_idx) p.topk_idx[ul * cap + r] = item;
+            if (p.topk_val) p.topk_val[ul * cap + r] = val;
+            if (p.topk_hit) p.topk_hit[ul * cap + r] = hit;
+        }
+    }
+}
+
+}  // namespace hyprec

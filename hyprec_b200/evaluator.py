@@ -1,0 +1,220 @@
+"""
+Host-side mirror of the reference ``Evaluator`` (/root/reference/lib/evaluator.py:10-341): same
+constructor, attributes and method names, so the reference's callers (RecommenderSystem,
+GridSearch, runnables.py) and its tests can use either class.
+
+What differs is how the work is done, not what comes out:
+
+* the k-fold / naive splits consume the global ``numpy.random`` stream exactly as the reference
+  does (seed 42 unless ``random_seed``; one ``shuffle(rated)`` then one ``shuffle(non_rated)`` per
+  user in user order, evaluator.py:144-171; one ``choice`` per user, :92-93) so the splits are
+  bit-identical, but fold matrices are assembled with array indexing instead of per-user
+  Python ``set`` arithmetic (evaluator.py:206-213 costs ~20 s per fold at citeulike-a size);
+* CSR views of ratings / train / test are kept next to the dense matrices the API exposes;
+* the metric methods compute each per-user value with the reference's own arithmetic and hand
+  the list to the same ``numpy.mean(..., dtype=numpy.float16)`` call (evaluator.py:292, 315, 341),
+  which keeps the reported scalars bit-identical;
+* ``load_top_recommendations`` and everything that needs scores is normally driven by
+  ``hyprec_b200.CollaborativeFiltering.get_evaluation_report`` from device results
+  (``set_device_results``); the dense-matrix entry points remain for API compatibility.
+"""
+import numpy
+import scipy.sparse as sp
+
+from hyprec_b200.top_recommendations import TopRecommendations, top_k_stream_order
+
+
+class Evaluator(object):
+    def __init__(self, ratings, abstracts_preprocessor=None, random_seed=False, verbose=False):
+        self.ratings = ratings
+        self.n_users, self.n_items = ratings.shape
+        if abstracts_preprocessor:
+            self.abstracts_preprocessor = abstracts_preprocessor
+        self.random_seed = random_seed
+        self._verbose = verbose
+        self.k_folds = None
+        if self._verbose:
+            print('%d users and %d items' % (self.n_users, self.n_items))
+        self.recommendation_indices = [[] for _ in range(self.n_users)]
+        self.recs_loaded = False
+        self._ratings_csr = None
+        # per-user hit flags (ratings * rounded along recommendation_indices) and test likes,
+        # filled by set_device_results(); None => metric methods fall back to dense inputs.
+        self._device_hits = None
+
+    # ------------------------------------------------------------------ plumbing
+    def get_abstracts_preprocessor(self):
+        return self.abstracts_preprocessor
+
+    def get_ratings(self):
+        return self.ratings
+
+    def ratings_csr(self):
+        if self._ratings_csr is None:
+            csr = sp.csr_matrix(self.ratings, dtype=numpy.float64)
+            csr.eliminate_zeros()
+            csr.sort_indices()
+            self._ratings_csr = csr
+        return self._ratings_csr
+
+    def set_kfolds(self, kfolds):
+        self.k_folds = kfolds
+        self.test_percentage = 1.0 / self.k_folds
+
+    # ------------------------------------------------------------------ naive split (:67-118)
+    def naive_split(self, type='user'):
+        if type == 'user':
+            return self.naive_split_users()
+        return self.naive_split_items()
+
+    def naive_split_users(self):
+        if self.random_seed is False:
+            numpy.random.seed(42)
+        csr = self.ratings_csr()
+        test = numpy.zeros(self.ratings.shape)
+        train = self.ratings.copy()
+        for user in range(self.n_users):
+            non_zeros = csr.indices[csr.indptr[user]:csr.indptr[user + 1]]
+            # sampling WITH replacement, evaluator.py:92-93
+            picked = numpy.random.choice(non_zeros, size=int(self.test_percentage * len(non_zeros)))
+            train[user, picked] = 0.
+            test[user, picked] = self.ratings[user, picked]
+        self.test_indices = test
+        return train, test
+
+    def naive_split_items(self):
+        if self.random_seed is False:
+            numpy.random.seed(42)
+        columns = numpy.random.choice(list(range(self.n_items)),
+                                      size=int(self.test_percentage * self.n_items))
+        train = self.ratings.copy()
+        test = numpy.zeros(self.ratings.shape)
+        train[:, columns] = 0
+        test[:, columns] = self.ratings[:, columns]
+        return train, test
+
+    # ------------------------------------------------------------------ k-fold (:120-213)
+    def get_kfold_indices(self):
+        """Flat list of n_users * k_folds int64 arrays; slot ``u * k_folds + f`` holds user u's
+        fold-f candidates: its share of shuffled positives followed by shuffled non-rated items,
+        int(n_items / k_folds) long (evaluator.py:176-192)."""
+        if self.random_seed is False:
+            numpy.random.seed(42)
+        csr = self.ratings_csr()
+        n, k = self.n_items, self.k_folds
+        all_items = numpy.arange(n)
+        out = []
+        for user in range(self.n_users):
+            rated = csr.indices[csr.indptr[user]:csr.indptr[user + 1]].astype(numpy.int64)
+            mask = numpy.ones(n, dtype=bool)
+            mask[rated] = False
+            non_rated = all_items[mask]
+            numpy.random.shuffle(rated)                       # :162
+            share = round((1.0 / k) * len(rated))             # :165 (banker's rounding)
+            numpy.random.shuffle(non_rated)                   # :171
+            fills = []
+            start = 0
+            for f in range(k):
+                positives = rated[start:] if f == k - 1 else rated[start:start + share]
+                start += share
+                fills.append(int((n / k) - len(positives)))   # :184
+                if f > 0 and fills[f] != fills[f - 1]:        # :185-187
+                    extra = non_rated[f * fills[f - 1]:(fills[f - 1] * f) + fills[f]]
+                else:                                         # :189
+                    extra = non_rated[f * fills[f]:fills[f] * (f + 1)]
+                out.append(numpy.append(numpy.array(positives), extra))
+        self.test_indices = out
+        return out
+
+    def get_fold(self, fold_num, fold_test_indices):
+        picked = [fold_test_indices[fold_num + user * self.k_folds] for user in range(self.n_users)]
+        return self.generate_kfold_matrix(picked)
+
+    def generate_kfold_matrix(self, test_indices):
+        """train = ratings with the listed cells zeroed, test = ratings on the listed cells
+        (evaluator.py:206-213)."""
+        train = numpy.array(self.ratings, dtype=numpy.float64)
+        test = numpy.zeros(self.ratings.shape)
+        for user in range(self.n_users):
+            cols = numpy.asarray(test_indices[user], dtype=numpy.int64)
+            test[user, cols] = self.ratings[user, cols]
+            train[user, cols] = 0
+        return train, test
+
+    # ------------------------------------------------------------------ top-k (:215-234)
+    def candidate_lists(self, fold):
+        """The per-user candidate streams ``load_top_recommendations`` walks (evaluator.py:225),
+        including the reference's ``user * (1 + fold)`` slot arithmetic and,
+        for the naive split, the dense test rows whose 0./1. values are cast to item ids
+        (App. A Q7).  Returns (indptr int64[m+1], ids int32[total])."""
+        rows = [numpy.asarray(self.test_indices[user * (1 + fold)]).astype(numpy.int64)
+                for user in range(self.n_users)]
+        indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
+        numpy.cumsum([len(r) for r in rows], out=indptr[1:])
+        ids = numpy.concatenate(rows).astype(numpy.int32) if rows else numpy.zeros(0, numpy.int32)
+        return indptr, ids
+
+    def load_top_recommendations(self, n_recommendations, predictions, test_data, fold):
+        for user in range(self.n_users):
+            cand = numpy.asarray(self.test_indices[user * (1 + fold)]).astype(numpy.int64)
+            ids, _ = top_k_stream_order(cand, numpy.asarray(predictions[user])[cand], n_recommendations)
+            self.recommendation_indices[user] = ids
+        self.recs_loaded = True
+        self._device_hits = None
+        return self.recommendation_indices
+
+    def set_device_results(self, recommendation_indices, hits):
+        """Install top-k lists and hit flags computed on the device."""
+        self.recommendation_indices = recommendation_indices
+        self._device_hits = hits
+        self.recs_loaded = True
+
+    # ------------------------------------------------------------------ metrics (:236-341)
+    def get_rmse(self, predicted, actual=None):
+        if actual is None:
+            actual = self.ratings
+        rss = 0
+        for i in range(predicted.shape[0]):
+            rss += numpy.sum((predicted[i] - actual[i]) ** 2)
+        return numpy.sqrt(float(rss) / numpy.size(predicted))
+
+    def calculate_recall(self, ratings, predictions):
+        denom = sum(sum(ratings))
+        return sum(predictions[ratings.nonzero()]) / denom
+
+    def _hits(self, rounded_predictions):
+        if self._device_hits is not None and rounded_predictions is None:
+            return self._device_hits
+        return [numpy.asarray(self.ratings[user])[numpy.asarray(recs, dtype=numpy.int64)] *
+                numpy.asarray(rounded_predictions[user])[numpy.asarray(recs, dtype=numpy.int64)]
+                for user, recs in enumerate(self.recommendation_indices)]
+
+    def recall_at_x(self, x, predictions, ratings, rounded_predictions):
+        hits = self._hits(rounded_predictions)
+        likes = numpy.asarray(ratings.sum(axis=1)).ravel()
+        recalls = [numpy.sum(hits[u][:x]) / (min(x, likes[u]) * 1.0)
+                   for u in range(len(hits)) if likes[u] != 0]
+        return numpy.mean(recalls, dtype=numpy.float16)
+
+    def calculate_ndcg(self, n_recommendations, predictions, test_data, rounded_predictions):
+        hits = self._hits(rounded_predictions)
+        logs = numpy.log2(numpy.arange(max(n_recommendations, 1)) + 2)
+        ndcgs = []
+        for h in hits:
+            top = min(len(h), n_recommendations)
+            if top == 0:
+                continue
+            # sequential accumulation, as the reference's += loop (:308-312)
+            dcg = numpy.cumsum(numpy.asarray(h[:top], dtype=numpy.float64) / logs[:top])[-1]
+            idcg = numpy.cumsum(1 / logs[:top])[-1]
+            if idcg != 0:
+                ndcgs.append(dcg / idcg)
+        return numpy.mean(ndcgs, dtype=numpy.float16)
+
+    def calculate_mrr(self, n_recommendations, predictions, test_data, rounded_predictions):
+        hits = self._hits(rounded_predictions)
+        mrr_list = []
+        for h in hits:
+            first = numpy.nonzero(numpy.asarray(h[:n_recommendations]) == 1)[0]
+            mrr_list.append(1.0 / (first[0] + 1) if len(first) else 0)
+        return numpy.mean(mrr_list, dtype=numpy.float16)

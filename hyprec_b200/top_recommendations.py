@@ -1,0 +1,88 @@
+"""
+Host-side mirror of /root/reference/util/top_recommendations.py (TopRecommendations, :8-95) plus
+the order rule the device top-k kernel reproduces.
+
+Semantics that matter (util/top_recommendations.py:31-40): values are kept
+ascending; a new value goes to the right of equal values (``bisect`` == bisect_right); when the
+list is full a candidate is admitted only if it is STRICTLY greater than the current minimum,
+and the minimum that leaves is the earliest-inserted of the minimal values.  After
+``reversed()`` (evaluator.py:230) the list is: score descending, equal scores later-inserted
+first.
+"""
+import bisect
+
+import numpy
+
+
+class TopRecommendations(object):
+    def __init__(self, n_recommendations):
+        self.recommendations_values = []
+        self.recommendations_indices = []
+        self.n_recommendations = n_recommendations
+
+    def insert(self, index, value):
+        values = self.recommendations_values
+        if self.n_recommendations > len(values):
+            self._place(index, value)
+        elif len(values) != 0 and values[0] < value:
+            values.pop(0)
+            self.recommendations_indices.pop(0)
+            self._place(index, value)
+
+    def _place(self, index, value):
+        at = bisect.bisect(self.recommendations_values, value)
+        self.recommendations_values.insert(at, value)
+        self.recommendations_indices.insert(at, index)
+
+    def get_indices(self):
+        return self.recommendations_indices
+
+    def get_values(self):
+        return self.recommendations_values
+
+    def get_recommendations_count(self):
+        return len(self.recommendations_values)
+
+
+def resolve_cutoff_ties(scores, capacity):
+    """Positions (ascending) of the elements the stream keeps, for one candidate stream.
+
+    Everything strictly above the capacity-th largest value is always kept.  Elements EQUAL to
+    that cut-off behave as a FIFO: one is admitted while the list is not full, rejected when it
+    is (strict ``<``), and every later strictly-larger arrival that finds the list full evicts
+    the oldest of them.  Elements below the cut-off never influence which of the others stay.
+    """
+    scores = numpy.asarray(scores, dtype=numpy.float64)
+    total = len(scores)
+    if total <= capacity:
+        return numpy.arange(total)
+    cut = numpy.partition(scores, total - capacity)[total - capacity]
+    above = scores > cut
+    equal = scores == cut
+    need = capacity - int(above.sum())
+    if int(equal.sum()) == need:
+        return numpy.nonzero(above | equal)[0]
+    held = 0          # elements >= cut currently in the list
+    fifo = []         # positions of cut-valued elements in the list, oldest first
+    for pos in numpy.nonzero(above | equal)[0]:
+        if above[pos]:
+            if held == capacity:
+                fifo.pop(0)
+            else:
+                held += 1
+        elif held < capacity:
+            fifo.append(pos)
+            held += 1
+    return numpy.sort(numpy.concatenate((numpy.nonzero(above)[0], numpy.asarray(fifo, dtype=numpy.int64))))
+
+
+def top_k_stream_order(ids, scores, capacity):
+    """(ids, scores) of the reference's streamed top-``capacity`` in final (descending) order."""
+    ids = numpy.asarray(ids)
+    scores = numpy.asarray(scores, dtype=numpy.float64)
+    if len(ids) == 0 or capacity <= 0:
+        return [], []
+    kept = resolve_cutoff_ties(scores, capacity)
+    order = numpy.lexsort((-kept, -scores[kept]))
+    sel = kept[order]
+    return [int(i) for i in ids[sel]], [float(v) for v in scores[sel]]

@@ -1,0 +1,138 @@
+/*
+ * hyprec_b200.h -- C ABI of the B200-native HyPRec hot path.
+ *
+ * The reference (mostafa-mahmoud/HyPRec) is pure Python and has no FFI of its own; its only
+ * replaceable seam is the Python class lib/collaborative_filtering.py:13 CollaborativeFiltering
+ * (SURVEY.md section 8b).  hyprec_b200/collaborative_filtering.py keeps that class surface and
+ * binds the functions below with ctypes; each entry point names the reference arithmetic it
+ * replaces.  Plain pointers and sizes only: no torch / numpy types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative HYPREC_E_* code; the message is
+ *     available from hyprec_last_error() (thread-local, valid until the next failing call);
+ *   - one handle owns one GPU (one process per GPU; multi-GPU runs create one handle per rank);
+ *     a handle is not thread-safe;
+ *   - host buffers are caller-owned and may be pageable or pinned; device memory is owned by
+ *     the library until hyprec_destroy();
+ *   - users x items matrices are row-major; factor matrices are rows x k row-major float64 on
+ *     the host regardless of the device precision;
+ *   - confidence weights are fixed at 1.0 on train non-zeros and 0.1 elsewhere, as in
+ *     lib/collaborative_filtering.py:120-144 (build_confidence_matrix).
+ */
+#ifndef HYPREC_B200_H
+#define HYPREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYPREC_OK 0
+#define HYPREC_E_INVALID (-1)   /* bad argument / call order                                   */
+#define HYPREC_E_CUDA (-2)      /* CUDA runtime error (message has the CUDA string)             */
+#define HYPREC_E_NOMEM (-3)     /* host or device allocation failed                             */
+#define HYPREC_E_UNSUPPORTED (-4) /* shape outside what the kernels handle (message says which) */
+#define HYPREC_E_SINGULAR (-5)  /* non-finite solution: the reference raises LinAlgError here    */
+
+#define HYPREC_F64 0            /* float64 storage and arithmetic (parity with numpy float64)   */
+#define HYPREC_F32 1            /* float32 factor storage / solve, float64 reductions           */
+
+#define HYPREC_SIDE_USER 0
+#define HYPREC_SIDE_ITEM 1
+
+typedef struct hyprec_ctx hyprec_t;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int hyprec_create(hyprec_t** out, int device_id, int precision);
+int hyprec_destroy(hyprec_t* h);
+const char* hyprec_last_error(void);
+int hyprec_abi_version(void);
+/* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
+int64_t hyprec_launch_count(const hyprec_t* h);
+
+/* ---- data ------------------------------------------------------------------------------ */
+/* Train matrix as CSR (users x items).  Replaces the dense self.train_data the reference
+ * scans in build_confidence_matrix (collaborative_filtering.py:120-144) and the ratings
+ * argument of als_step (:69).  indices must be sorted within a row; values NULL => all 1.0.
+ * The item-major (CSC) copy is built here. */
+int hyprec_set_train_csr(hyprec_t* h, int64_t n_users, int64_t n_items, const int64_t* indptr,
+                         const int32_t* indices, const double* values);
+
+/* Rows this handle solves in a half-step (multi-GPU sharding).  Default:
+ * all rows.  Rows outside the range are left untouched in the local replica; the caller
+ * exchanges shards (all-gather over the pointers hyprec_device_factors returns). */
+int hyprec_set_shard(hyprec_t* h, int64_t user_lo, int64_t user_hi, int64_t item_lo, int64_t item_hi);
+
+/* self.user_vecs / self.item_vecs (collaborative_filtering.py:173-178); k = n_factors. */
+int hyprec_set_factors(hyprec_t* h, const double* user_vecs, const double* item_vecs, int k);
+int hyprec_get_factors(hyprec_t* h, double* user_vecs, double* item_vecs);
+/* Device addresses and element size (8 or 4) of the replicated factor matrices, for the
+ * caller's collective (torch.distributed / NCCL all-gather of the solved shard). */
+int hyprec_device_factors(hyprec_t* h, void** user_vecs_dev, void** item_vecs_dev, int* elem_size);
+
+/* self.document_distribution for the update_with_items rule (:93-96); NULL clears it. */
+int hyprec_set_item_prior(hyprec_t* h, const double* theta);
+
+/* ---- ALS ------------------------------------------------------------------------------- */
+/* One half-step == als_step(latent, fixed, train, _lambda, type) (collaborative_filtering.py
+ * :69-99) for the handle's shard: Gram of the fixed side, per-row CSR gather of
+ * sum y y^T and sum r y, k x k Cholesky solve, row written back. */
+int hyprec_als_half_step(hyprec_t* h, int side, double lambda);
+
+/* evaluator.get_rmse(U.dot(V.T), train) (evaluator.py:236-252, called at
+ * collaborative_filtering.py:247) without forming U.V^T; float64 accumulation in every mode. */
+int hyprec_rmse(hyprec_t* h, double* out);
+
+/* partial_train() (collaborative_filtering.py:224-259): epochs of user half-step, item
+ * half-step, RMSE; stops after the epoch whose error >= the previous one (:256).
+ * start_error is the initial `error` (inf, or the epoch-0 RMSE when verbose, :228-234).
+ * The callback (may be NULL) sees every epoch: (epoch starting at 1, rmse, seconds of the two
+ * half-steps).  Single-GPU only: with a shard set the caller loops half-steps itself. */
+typedef void (*hyprec_epoch_cb)(int epoch, double rmse, double seconds, void* user);
+int hyprec_train(hyprec_t* h, int n_iter, double lambda, double start_error, hyprec_epoch_cb cb,
+                 void* user, int* epochs_run, double* last_rmse);
+
+/* ---- prediction / evaluation ------------------------------------------------------------ */
+/* get_predictions(): U.dot(V.T) (collaborative_filtering.py:270), n_users x n_items float64
+ * written to host memory.  Meant for the API's dense return value at small shapes. */
+int hyprec_predict_dense(hyprec_t* h, double* out);
+
+/* The matrices the report needs besides train: full ratings (evaluator.ratings) and test.
+ * Same CSR conventions as hyprec_set_train_csr. */
+int hyprec_set_eval_csr(hyprec_t* h, const int64_t* full_indptr, const int32_t* full_indices,
+                        const double* full_values, const int64_t* test_indptr,
+                        const int32_t* test_indices, const double* test_values);
+
+/* Everything get_evaluation_report() (abstract_recommender.py:100-131) derives from scores,
+ * for users [user_lo, user_hi) (0, n_users for a single GPU); output arrays are indexed
+ * relative to user_lo:
+ *   thresholds[u]        row average of the prediction row (abstract_recommender.py:183)
+ *   ones_per_row[u]      #items with score >= threshold  (rounded_predictions, :184-186)
+ *   topk_idx/val/hit     top-`capacity` of the user's candidate stream in the order
+ *                        load_top_recommendations leaves it (evaluator.py:215-234 +
+ *                        util/top_recommendations.py:23-40), -1 padded; hit = full rating of
+ *                        that cell times its rounded prediction (evaluator.py:287-288)
+ *   train_flags/test_flags  rounded prediction at every train / test non-zero of these users,
+ *                        in CSR order (calculate_recall, evaluator.py:254-266)
+ * cand_indptr is relative to user_lo (cand_indptr[0] == 0); cand_ids NULL => every item in
+ * index order (recommend_items, abstract_recommender.py:200-203).  Any output may be NULL. */
+int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
+                     const int32_t* cand_ids, int capacity, double* thresholds,
+                     int64_t* ones_per_row, int32_t* topk_idx, double* topk_val, double* topk_hit,
+                     uint8_t* train_flags, uint8_t* test_flags);
+
+/* Device time (ms, CUDA events) of the most recent call of each kind; for bench.py's roofline. */
+#define HYPREC_T_GRAM 0
+#define HYPREC_T_SOLVE 1
+#define HYPREC_T_RMSE 2
+#define HYPREC_T_SWEEP 3
+#define HYPREC_T_TOPK 4
+#define HYPREC_T_FLAGS 5
+#define HYPREC_T_COUNT 6
+int hyprec_last_kernel_ms(hyprec_t* h, int which, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPREC_B200_H */

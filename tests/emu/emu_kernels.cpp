@@ -1,0 +1,143 @@
+// TEST INFRASTRUCTURE: runs the SIMT kernels of hyprec_b200/csrc/*.cuh on the CPU through
+// emu_cuda.h so tests/test_emu_kernels.py can check their indexing and synchronisation against
+// the oracle without a GPU.  Built by tests/emu/build.py into tests/emu/libhyprec_emu.so.
+#define HYPREC_EMU 1
+#include "emu_cuda.h"
+
+namespace emu {
+thread_local emu_dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+thread_local Block* t_block = nullptr;
+}  // namespace emu
+
+#include "../../hyprec_b200/csrc/als_solve.cuh"
+#include "../../hyprec_b200/csrc/gram.cuh"
+#include "../../hyprec_b200/csrc/score.cuh"
+#include "../../hyprec_b200/csrc/topk.cuh"
+
+using namespace hyprec;
+
+template <typename T>
+static void gram_impl(const T* y, int64_t rows, int k, int nsplit, T* g) {
+    const int ntile = (k + kGramTile - 1) / kGramTile, tiles = tri(ntile);
+    int64_t per = (rows + nsplit - 1) / nsplit;
+    per = (per + kGramRows - 1) / kGramRows * kGramRows;
+    nsplit = (int)((rows + per - 1) / per);
+    std::vector<T> partial((size_t)nsplit * k * k, T(0));
+    emu::launch(dim3(tiles, nsplit), dim3(kGramThreads), 0,
+                [&]() { gram_partial_kernel<T>(y, rows, k, per, partial.data()); });
+    emu::launch(dim3((k * k + 255) / 256), dim3(256), 0,
+                [&]() { gram_reduce_kernel<T>(partial.data(), nsplit, k, g); });
+}
+
+template <typename T>
+static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T* values, const T* fixed,
+                          int64_t n_fixed, T* latent, int64_t row_lo, int64_t row_hi, int k, T lambda,
+                          const T* prior, int chunk_rows, int grid, int a_in_smem) {
+    std::vector<T> g((size_t)k * k);
+    gram_impl<T>(fixed, n_fixed, k, 3, g.data());
+    const int nb = aug_blocks(k), n_tiles = tri(nb);
+    std::vector<T> base((size_t)kTileElems * n_tiles);
+    emu::launch(dim3((kTileElems * n_tiles + 255) / 256), dim3(256), 0,
+                [&]() { build_base_tiles_kernel<T>(g.data(), k, lambda, base.data()); });
+    SolveLayout lay = solve_layout(k, chunk_rows, a_in_smem != 0, sizeof(T));
+    std::vector<T> scratch(a_in_smem ? 1 : (size_t)grid * kTileElems * n_tiles);
+    int counter[2] = {0, 0};
+    SolveArgs<T> a;
+    a.indptr = indptr; a.indices = indices; a.values = values; a.fixed = fixed; a.latent = latent;
+    a.base = base.data(); a.prior = prior; a.a_scratch = a_in_smem ? nullptr : scratch.data();
+    a.work_counter = counter; a.status = counter + 1; a.lambda = lambda; a.k = k;
+    a.row_lo = row_lo; a.row_hi = row_hi; a.chunk_rows = chunk_rows;
+    emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T>(a); });
+    return counter[1];
+}
+
+template <typename T>
+static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
+                      const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
+                      const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
+                      int grid) {
+    std::vector<double> part(2 * (size_t)k), colsum(k);
+    const int64_t per = (n + 1) / 2;
+    emu::launch(dim3(2), dim3(64), 0, [&]() { colsum_partial_kernel<T>(V, n, k, per, part.data()); });
+    emu::launch(dim3((k + 255) / 256), dim3(256), 0, [&]() { colsum_reduce_kernel(part.data(), 2, k, colsum.data()); });
+    emu::launch(dim3((unsigned)((m + 1) / 2)), dim3(64), 0,
+                [&]() { row_threshold_kernel<T>(U, colsum.data(), k, m, n, thr); });
+    const int64_t nu = hi - lo;
+    if (ones) {
+        std::vector<unsigned long long> counts(nu, 0);
+        SweepArgs<T> a;
+        a.user_vecs = U; a.item_vecs = V; a.k = k; a.user_lo = lo; a.user_hi = hi; a.n_items = n;
+        a.dense_out = nullptr; a.thresholds = thr; a.counts = counts.data();
+        emu::launch(dim3((unsigned)((n + kSweepTile - 1) / kSweepTile), (unsigned)((nu + kSweepTile - 1) / kSweepTile)),
+                    dim3(kSweepThreads), 0, [&]() { score_sweep_kernel<T, kSweepCount>(a); });
+        for (int64_t u = 0; u < nu; ++u) ones[u] = (int64_t)counts[u];
+    }
+    int64_t max_cand = n;
+    if (ci) {
+        max_cand = 1;
+        for (int64_t u = 0; u < nu; ++u) max_cand = std::max(max_cand, cp[u + 1] - cp[u]);
+    }
+    int sort_size = 2;
+    while (sort_size < cap) sort_size <<= 1;
+    TopkLayout lay = topk_layout((int)max_cand, k, sort_size);
+    TopkArgs<T> a;
+    a.user_vecs = U; a.item_vecs = V; a.k = k; a.n_items = n; a.user_lo = lo; a.user_hi = hi;
+    a.cand_indptr = ci ? cp : nullptr; a.cand_ids = ci; a.thresholds = thr;
+    a.full_indptr = fp; a.full_indices = fi; a.full_values = fv;
+    a.capacity = cap; a.sort_size = sort_size; a.max_cand = (int)max_cand;
+    a.topk_idx = tidx; a.topk_val = tval; a.topk_hit = thit;
+    emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T>(a); });
+}
+
+extern "C" {
+
+void emu_gram_f64(const double* y, int64_t rows, int k, int nsplit, double* g) { gram_impl<double>(y, rows, k, nsplit, g); }
+void emu_gram_f32(const float* y, int64_t rows, int k, int nsplit, float* g) { gram_impl<float>(y, rows, k, nsplit, g); }
+
+int emu_half_step_f64(const int64_t* indptr, const int32_t* indices, const double* values, const double* fixed,
+                      int64_t n_fixed, double* latent, int64_t row_lo, int64_t row_hi, int k, double lambda,
+                      const double* prior, int chunk_rows, int grid, int a_in_smem) {
+    return half_step_impl<double>(indptr, indices, values, fixed, n_fixed, latent, row_lo, row_hi, k, lambda, prior,
+                                  chunk_rows, grid, a_in_smem);
+}
+int emu_half_step_f32(const int64_t* indptr, const int32_t* indices, const float* values, const float* fixed,
+                      int64_t n_fixed, float* latent, int64_t row_lo, int64_t row_hi, int k, float lambda,
+                      const float* prior, int chunk_rows, int grid, int a_in_smem) {
+    return half_step_impl<float>(indptr, indices, values, fixed, n_fixed, latent, row_lo, row_hi, k, lambda, prior,
+                                 chunk_rows, grid, a_in_smem);
+}
+
+void emu_eval_f64(const double* U, const double* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
+                  const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
+                  const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit, int grid) {
+    eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid);
+}
+
+void emu_predict_f64(const double* U, const double* V, int64_t m, int64_t n, int k, double* out) {
+    SweepArgs<double> a;
+    a.user_vecs = U; a.item_vecs = V; a.k = k; a.user_lo = 0; a.user_hi = m; a.n_items = n;
+    a.dense_out = out; a.thresholds = nullptr; a.counts = nullptr;
+    emu::launch(dim3((unsigned)((n + kSweepTile - 1) / kSweepTile), (unsigned)((m + kSweepTile - 1) / kSweepTile)),
+                dim3(kSweepThreads), 0, [&]() { score_sweep_kernel<double, kSweepStore>(a); });
+}
+
+// sum_nz r (u.v), sum r^2, <U^T U, V^T V>
+void emu_rmse_terms_f64(const int64_t* indptr, const int32_t* indices, const double* values, const double* U,
+                        const double* V, int64_t m, int64_t n, int k, double* out3) {
+    std::vector<double> gu((size_t)k * k), gv((size_t)k * k), s1(m), s2(m);
+    gram_impl<double>(U, m, k, 2, gu.data());
+    gram_impl<double>(V, n, k, 2, gv.data());
+    emu::launch(dim3(1), dim3(256), 0, [&]() { frob_inner_kernel<double>(gu.data(), gv.data(), k * k, out3); });
+    emu::launch(dim3((unsigned)((m + 1) / 2)), dim3(64), 0,
+                [&]() { sddmm_row_kernel<double>(indptr, indices, values, U, V, k, m, s1.data(), s2.data()); });
+    emu::launch(dim3(1), dim3(1024), 0, [&]() { reduce_sum_kernel(s1.data(), m, out3 + 1); });
+    emu::launch(dim3(1), dim3(1024), 0, [&]() { reduce_sum_kernel(s2.data(), m, out3 + 2); });
+}
+
+void emu_nz_flags_f64(const int64_t* indptr, const int32_t* indices, const double* U, const double* V, int k,
+                      const double* thr, int64_t lo, int64_t hi, uint8_t* flags) {
+    emu::launch(dim3((unsigned)((hi - lo + 1) / 2)), dim3(64), 0,
+                [&]() { nz_flags_kernel<double>(indptr, indices, U, V, k, thr, lo, hi, flags); });
+}
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""
+bench.py -- the measurement contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload citeulike-a|citeulike-t|small] [--precision fp64|fp32]
+
+One "step" = one pass of the hot path over the workload: one weighted-ALS epoch (user half-step,
+item half-step, RMSE -- /root/reference/lib/collaborative_filtering.py:241-247) followed by one
+evaluation report's device work (row thresholds, rounded counts, streamed top-200 per user, hit and
+recall flags -- lib/abstract_recommender.py:100-131).
+
+Workload at N=1 (BASELINE.json configs[1]): citeulike-a shape (5551 x 16980, 204986 positives),
+reference 5-fold split (seed 42) fold 0, n_factors=200, lambda=0.01, item factors initialised from a
+synthetic LDA theta (Dirichlet rows), candidate lists exactly as load_top_recommendations reads them.
+
+Printed JSON (one line, rank 0):
+  metric/value   als_epoch_ms: device time (CUDA events on the launching stream) of one epoch's
+                 kernels with every input resident in HBM
+  e2e            the same epoch through the C ABI with HOST buffers: factors host->device, epoch,
+                 factors device->host; eval through hyprec_eval_topk with host candidate lists
+  roofline       dominant kernel (the fused gather+Cholesky row solve): algorithmic FLOPs / event time
+                 against the FMA rate measured on this GPU by hyprec_probe_fma_tflops
+  cpu_baseline   the oracle's restatement of the reference arithmetic timed on a bounded row sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (synth shape, n_factors, lambda, k_folds)
+    "citeulike-a": ("citeulike-a", 200, 0.01, 5),
+    "citeulike-t": ("citeulike-t", 300, 0.01, 5),
+    "small": ("small", 50, 0.01, 5),
+}
+
+
+# --------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------
+def build_workload(name):
+    """Synthetic ratings, the reference's 5-fold split (fold 0), theta-initialised item factors."""
+    from hyprec_b200 import synth
+    from hyprec_b200.evaluator import Evaluator
+    shape, k, lam, folds = WORKLOADS[name]
+    t0 = time.time()
+    ratings_csr = synth.ratings_csr(shape)
+    ratings = numpy.asarray(ratings_csr.todense(), dtype=numpy.float64)
+    evaluator = Evaluator(ratings)
+    evaluator.set_kfolds(folds)
+    lists = evaluator.get_kfold_indices()
+    train, test = evaluator.get_fold(0, lists)
+    cand_indptr, cand_ids = evaluator.candidate_lists(0)
+    m, n = ratings.shape
+    user_vecs = numpy.random.random((m, k))                  # drawn right after the split (App. A Q4)
+    theta = synth.dirichlet_theta(n, k, seed=7)
+    import scipy.sparse as sp
+    wl = dict(name=name, m=m, n=n, k=k, lam=lam, folds=folds, ratings=ratings, train=train, test=test,
+              train_csr=sp.csr_matrix(train), test_csr=sp.csr_matrix(test), full_csr=ratings_csr,
+              cand_indptr=cand_indptr, cand_ids=cand_ids, u0=user_vecs, v0=theta.copy(),
+              setup_s=time.time() - t0)
+    for key in ("train_csr", "test_csr", "full_csr"):
+        wl[key].sort_indices()
+    return wl
+
+
+def algorithmic_work(wl):
+    """FLOPs / bytes per epoch and per launch of the solve kernel (SURVEY.md section 8d formulas)."""
+    m, n, k = wl["m"], wl["n"], wl["k"]
+    nnz = wl["train_csr"].nnz
+    solve_flops = 2 * (2.0 * nnz * k * k) + (m + n) * (k ** 3 / 3.0 + 2.0 * k * k) + 2 * (2.0 * nnz * k)
+    return dict(nnz=nnz, solve_flops_per_epoch=solve_flops,
+                solve_bytes_per_epoch=lambda s: 2.0 * nnz * (k * s + 4) + 2.0 * (m + n) * k * s + 8.0 * (m + n + 2),
+                eval_flops=2.0 * m * n * k)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) < 9:
+                continue
+            try:
+                sm.append(float(s[1]))
+                mx.append(float(s[2]))
+                power.append(float(s[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, s[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(numpy.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline (the oracle timed on the host: the only place bench.py executes oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_epoch_sample(wl, n_rows, literal, seed=0):
+    """Time the reference arithmetic on a row sample and extrapolate to one epoch (ms).
+
+    literal=True : oracle.als.als_step_literal -- the reference's per-row dense
+                   (k x n)(n x k) product + LAPACK solve (collaborative_filtering.py:82-98), with the
+                   pure-Python confidence loop replaced by numpy.where (favours the reference).
+    literal=False: the sparse-identity restatement (batched numpy solves)."""
+    from oracle import als as oals
+    rs = numpy.random.RandomState(seed)
+    m, n, k, lam = wl["m"], wl["n"], wl["k"], wl["lam"]
+    users = numpy.sort(rs.choice(m, min(n_rows, m), replace=False))
+    items = numpy.sort(rs.choice(n, min(n_rows, n), replace=False))
+    u, v = wl["u0"].copy(), wl["v0"].copy()
+    if literal:
+        train = wl["train"]
+        t0 = time.perf_counter()
+        oals.als_step_literal(u[users], v, train[users], lam, "user")
+        t_user = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oals.als_step_literal(v[items], u, train[:, items], lam, "item")
+        t_item = time.perf_counter() - t0
+    else:
+        csr = wl["train_csr"]
+        csc = csr.T.tocsr()
+        t0 = time.perf_counter()
+        oals.als_half_step(u, v, csr, lam, rows=users)
+        t_user = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oals.als_half_step(v, u, csc, lam, rows=items)
+        t_item = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oals.rmse_gram(u, v, wl["train_csr"])
+    t_rmse = time.perf_counter() - t0
+    epoch_ms = 1e3 * (t_user * m / len(users) + t_item * n / len(items) + t_rmse)
+    return epoch_ms, dict(users=len(users), items=len(items), t_user_s=t_user, t_item_s=t_item, t_rmse_s=t_rmse)
+
+
+def cpu_eval_sample(wl, n_users, seed=0):
+    """Users/s of the literal streamed top-k + thresholds on a user sample (oracle, pure Python)."""
+    from oracle import evaluation as oev
+    rs = numpy.random.RandomState(seed)
+    users = numpy.sort(rs.choice(wl["m"], min(n_users, wl["m"]), replace=False))
+    u, v = wl["u0"], wl["v0"]
+    t0 = time.perf_counter()
+    for uid in users:
+        row = u[uid].dot(v.T)
+        thr = sum(row) / row.shape[0]                                   # abstract_recommender.py:183
+        cand = wl["cand_ids"][wl["cand_indptr"][uid]:wl["cand_indptr"][uid + 1]]
+        oev.top_recommendations_stream(cand, row[cand], 200)            # evaluator.py:226-230
+        _ = row >= thr
+    return len(users) / (time.perf_counter() - t0)
+
+
+def reference_arm(args, wl):
+    """--impl reference: the reference's CPU arithmetic for the same metric/config, bounded sample."""
+    cores = os.cpu_count()
+    per_step = []
+    for step in range(args.warmup + args.steps):
+        ms, detail = cpu_epoch_sample(wl, args.cpu_rows, literal=True, seed=step)
+        if step >= args.warmup:
+            per_step.append(ms)
+    value = float(numpy.mean(per_step))
+    eval_rate = cpu_eval_sample(wl, 24)
+    sample = ("%d users + %d items (random rows, full width) through the literal per-row arithmetic, "
+              "extrapolated x m/%d and x n/%d, + full Gram-identity RMSE; per step" %
+              (detail["users"], detail["items"], detail["users"], detail["items"]))
+    line = dict(impl="reference", metric="als_epoch_ms", value=value, unit="ms", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=value, higher_is_better=False, scaling="strong", vs_baseline=None,
+                dtype="f64", data="synthetic", config=config_block(wl, args),
+                eval_users_per_s=eval_rate,
+                cpu_baseline=dict(value=value, unit="ms", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def config_block(wl, args):
+    return dict(workload="%s shape %dx%d, %d train positives (5-fold split, fold 0), n_factors=%d, lambda=%g, "
+                         "theta-initialised item factors, top-200 over %d candidates/user" %
+                         (wl["name"], wl["m"], wl["n"], wl["train_csr"].nnz, wl["k"], wl["lam"],
+                          int(wl["cand_indptr"][1] - wl["cand_indptr"][0])),
+                users=wl["m"], items=wl["n"], n_factors=wl["k"], train_nnz=int(wl["train_csr"].nnz),
+                precision=args.precision, l2="flushed between timed steps (384 MiB memset)",
+                parallelism="rows sharded over %d GPU(s), factor all-gather per half-step" % args.gpus)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def our_arm(args, wl):
+    from hyprec_b200 import _native
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        return our_arm_distributed(args, wl, rank, world, local)
+
+    precision = _native.F64 if args.precision == "fp64" else _native.F32
+    h = _native.Handle(local, precision)
+    m, n, k, lam = wl["m"], wl["n"], wl["k"], wl["lam"]
+    tr, te, fu = wl["train_csr"], wl["test_csr"], wl["full_csr"]
+    h.set_train_csr(m, n, tr.indptr, tr.indices, tr.data)
+    h.set_eval_csr((fu.indptr, fu.indices, fu.data), (te.indptr, te.indices, te.data))
+    h.set_factors(wl["u0"], wl["v0"])
+    classes = dict(gram=_native.T_GRAM, solve=_native.T_SOLVE, rmse=_native.T_RMSE, count=_native.T_COUNT,
+                   topk=_native.T_TOPK, flags=_native.T_FLAGS)
+
+    def epoch():
+        h.als_half_step(_native.SIDE_USER, lam)
+        h.als_half_step(_native.SIDE_ITEM, lam)
+        return h.rmse()
+
+    def evaluate():
+        return h.eval_topk(200, wl["cand_indptr"], wl["cand_ids"], n_train_nz=tr.nnz, n_test_nz=te.nnz)
+
+    for _ in range(args.warmup):
+        h.flush_l2()
+        epoch()
+        h.flush_l2()
+        evaluate()
+    h.reset_kernel_ms()
+    launches0 = h.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    wall_epoch = wall_eval = 0.0
+    rmse = None
+    for _ in range(args.steps):
+        h.flush_l2()
+        t0 = time.perf_counter()
+        rmse = epoch()
+        wall_epoch += time.perf_counter() - t0
+        h.flush_l2()
+        t0 = time.perf_counter()
+        out = evaluate()
+        wall_eval += time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = h.launch_count - launches0
+    dev = {name: h.kernel_ms(t) for name, t in classes.items()}      # (total ms, regions, last)
+    per_step = {name: dev[name][0] / args.steps for name in dev}
+    epoch_ms = per_step["gram"] + per_step["solve"] + per_step["rmse"]
+    eval_ms = per_step["count"] + per_step["topk"] + per_step["flags"]
+
+    # ---- e2e: host buffers in, host buffers out, every step
+    u_host, v_host = h.get_factors()
+    e2e_epoch = e2e_eval = 0.0
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        h.set_factors(u_host, v_host)
+        epoch()
+        h.get_factors(u_host, v_host)
+        t1 = time.perf_counter()
+        evaluate()
+        t2 = time.perf_counter()
+        if step >= args.warmup:
+            e2e_epoch += t1 - t0
+            e2e_eval += t2 - t1
+    e2e_epoch_ms = 1e3 * e2e_epoch / args.steps
+    e2e_eval_ms = 1e3 * e2e_eval / args.steps
+    factor_bytes = (m + n) * k * 8
+    eval_h2d = wl["cand_ids"].nbytes + wl["cand_indptr"].nbytes
+    eval_d2h = m * 200 * (4 + 8 + 8) + m * 16 + tr.nnz + te.nnz
+
+    # ---- metrics of the final model (reported, not timed)
+    from hyprec_b200 import metrics as hm
+    lengths = (out["topk_idx"] >= 0).sum(axis=1)
+    test_likes = numpy.asarray(te.sum(axis=1)).ravel()
+    recall200 = float(hm.recall_at_x(200, out["topk_hit"], test_likes))
+
+    # ---- roofline of the dominant kernel
+    work = algorithmic_work(wl)
+    elem = 8 if args.precision == "fp64" else 4
+    solve_ms = per_step["solve"]
+    peak = h.probe_fma_tflops(precision)
+    achieved = work["solve_flops_per_epoch"] / (solve_ms * 1e-3) / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_file):
+        hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured"
+    solve_gbs = work["solve_bytes_per_epoch"](elem) / (solve_ms * 1e-3) / 1e9
+    roofline = dict(kernel="als_solve_rows_kernel (2 launches per epoch)", bound="%s_fma" % args.precision,
+                    achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak if peak else None,
+                    peak_source="hyprec_probe_fma_tflops on this GPU (FMA chains, best of 4)", traffic=None,
+                    flops_per_epoch=work["solve_flops_per_epoch"],
+                    hbm=dict(achieved=solve_gbs, peak=hbm_peak, unit="GB/s", frac=solve_gbs / hbm_peak,
+                             peak_source=hbm_src + " MEASURED_PEAKS.json", algorithmic_bytes=work["solve_bytes_per_epoch"](elem)))
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu_ms, cpu_detail = cpu_epoch_sample(wl, args.cpu_rows, literal=True)
+    cpu_vec_ms, _ = cpu_epoch_sample(wl, 8 * args.cpu_rows, literal=False)
+    cpu_eval = cpu_eval_sample(wl, 16)
+    cpu_baseline = dict(value=cpu_ms, unit="ms", cores=os.cpu_count(), kind="port",
+                        sample="%d users + %d items at full width through the reference's per-row dense arithmetic "
+                               "(oracle.als.als_step_literal), extrapolated to %d + %d rows, + RMSE" %
+                               (cpu_detail["users"], cpu_detail["items"], m, n),
+                        vectorised_value=cpu_vec_ms, eval_users_per_s=cpu_eval)
+
+    line = dict(metric="als_epoch_ms", value=epoch_ms, unit="ms", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * (wall_epoch + wall_eval) / args.steps, higher_is_better=False, scaling="strong",
+                vs_baseline=None, dtype="f64" if args.precision == "fp64" else "f32", data="synthetic",
+                config=config_block(wl, args), clocks=clocks,
+                e2e=dict(value=e2e_epoch_ms, unit="ms", h2d_bytes_per_step=factor_bytes + eval_h2d,
+                         d2h_bytes_per_step=factor_bytes + eval_d2h, eval_ms=e2e_eval_ms,
+                         eval_users_per_s=m / (e2e_eval_ms * 1e-3)),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
+                eval_ms=eval_ms, eval_users_per_s=m / (eval_ms * 1e-3), wall_epoch_ms=1e3 * wall_epoch / args.steps,
+                wall_eval_ms=1e3 * wall_eval / args.steps, kernel_ms_per_step=per_step, rmse=rmse,
+                recall_at_200=recall200, setup_s=wl["setup_s"])
+    print(json.dumps(line))
+    h.close()
+
+
+def our_arm_distributed(args, wl, rank, world, local):
+    from hyprec_b200 import distributed
+    line = distributed.bench_sharded(args, wl, rank, world, local, config_block(wl, args))
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="citeulike-a", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("HYPREC_PRECISION", "fp64"), choices=["fp64", "fp32"])
+    ap.add_argument("--cpu-rows", type=int, default=16, help="rows per side in the CPU baseline sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        reference_arm(args, build_workload(args.workload))
+        return
+    our_arm(args, build_workload(args.workload))
+
+
+if __name__ == "__main__":
+    main()

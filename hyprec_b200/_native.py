@@ -1,0 +1,221 @@
+"""
+ctypes binding of libhyprec_b200.so (include/hyprec_b200.h).  There is no CPU fallback: if the
+library is missing, or no CUDA device is visible, creating a handle raises.
+"""
+import ctypes
+import os
+
+import numpy
+
+from hyprec_b200 import build as _build
+
+F64, F32 = 0, 1
+SIDE_USER, SIDE_ITEM = 0, 1
+T_GRAM, T_SOLVE, T_RMSE, T_SWEEP, T_TOPK, T_FLAGS, T_COUNT = range(7)
+
+EXPORTS = [
+    "hyprec_create", "hyprec_destroy", "hyprec_last_error", "hyprec_abi_version", "hyprec_launch_count",
+    "hyprec_set_train_csr", "hyprec_set_shard", "hyprec_set_factors", "hyprec_get_factors",
+    "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_train",
+    "hyprec_predict_dense", "hyprec_set_eval_csr", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
+    "hyprec_flush_l2", "hyprec_probe_fma_tflops",
+]
+
+EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
+
+_lib = None
+
+
+class HyprecError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "hyprec_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def load_library(rebuild=False):
+    """Load (building first when stale and nvcc is present) the C-ABI library."""
+    global _lib
+    if _lib is not None and not rebuild:
+        return _lib
+    path = _build.LIB_PATH
+    if rebuild or _build.is_stale():
+        try:
+            _build.build(force=rebuild)
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise RuntimeError("libhyprec_b200.so is missing (run `python -m hyprec_b200.build`); "
+                           "hyprec_b200 has no CPU fallback")
+    lib = ctypes.CDLL(path)
+    c_i64, c_int, c_dbl, vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+    lib.hyprec_create.argtypes = [ctypes.POINTER(vp), c_int, c_int]
+    lib.hyprec_destroy.argtypes = [vp]
+    lib.hyprec_last_error.restype = ctypes.c_char_p
+    lib.hyprec_launch_count.argtypes = [vp]
+    lib.hyprec_launch_count.restype = c_i64
+    lib.hyprec_set_train_csr.argtypes = [vp, c_i64, c_i64, vp, vp, vp]
+    lib.hyprec_set_shard.argtypes = [vp, c_i64, c_i64, c_i64, c_i64]
+    lib.hyprec_set_factors.argtypes = [vp, vp, vp, c_int]
+    lib.hyprec_get_factors.argtypes = [vp, vp, vp]
+    lib.hyprec_device_factors.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(c_int)]
+    lib.hyprec_set_item_prior.argtypes = [vp, vp]
+    lib.hyprec_als_half_step.argtypes = [vp, c_int, c_dbl]
+    lib.hyprec_rmse.argtypes = [vp, ctypes.POINTER(c_dbl)]
+    lib.hyprec_train.argtypes = [vp, c_int, c_dbl, c_dbl, EPOCH_CB, vp, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]
+    lib.hyprec_predict_dense.argtypes = [vp, vp]
+    lib.hyprec_set_eval_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.hyprec_eval_topk.argtypes = [vp, c_i64, c_i64, vp, vp, c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.hyprec_kernel_ms.argtypes = [vp, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]
+    lib.hyprec_reset_kernel_ms.argtypes = [vp]
+    lib.hyprec_flush_l2.argtypes = [vp]
+    lib.hyprec_probe_fma_tflops.argtypes = [vp, c_int, ctypes.POINTER(c_dbl)]
+    _lib = lib
+    return lib
+
+
+def _ptr(array):
+    return None if array is None else array.ctypes.data_as(ctypes.c_void_p)
+
+
+def _as(array, dtype):
+    if array is None:
+        return None
+    return numpy.ascontiguousarray(array, dtype=dtype)
+
+
+class Handle(object):
+    """One GPU's worth of device state behind the C ABI."""
+
+    def __init__(self, device=0, precision=F64):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        self.precision = precision
+        self.m = self.n = self.k = 0
+        self._check(self._lib.hyprec_create(ctypes.byref(self._h), int(device), int(precision)))
+
+    def _check(self, code):
+        if code != 0:
+            raise HyprecError(code, self._lib.hyprec_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.hyprec_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self._lib.hyprec_launch_count(self._h))
+
+    # ---- data
+    def set_train_csr(self, m, n, indptr, indices, values=None):
+        indptr, indices, values = _as(indptr, numpy.int64), _as(indices, numpy.int32), _as(values, numpy.float64)
+        self._check(self._lib.hyprec_set_train_csr(self._h, m, n, _ptr(indptr), _ptr(indices), _ptr(values)))
+        self.m, self.n = int(m), int(n)
+
+    def set_eval_csr(self, full, test):
+        """full / test: (indptr, indices, values-or-None) triples."""
+        arrs = []
+        for indptr, indices, values in (full, test):
+            arrs += [_as(indptr, numpy.int64), _as(indices, numpy.int32), _as(values, numpy.float64)]
+        self._check(self._lib.hyprec_set_eval_csr(self._h, *[_ptr(a) for a in arrs]))
+
+    def set_shard(self, user_lo, user_hi, item_lo, item_hi):
+        self._check(self._lib.hyprec_set_shard(self._h, user_lo, user_hi, item_lo, item_hi))
+
+    def set_factors(self, user_vecs, item_vecs):
+        u, v = _as(user_vecs, numpy.float64), _as(item_vecs, numpy.float64)
+        if u.shape[0] != self.m or v.shape[0] != self.n or u.shape[1] != v.shape[1]:
+            raise ValueError("factor shapes %s / %s do not match a %d x %d problem" % (u.shape, v.shape, self.m, self.n))
+        self.k = int(u.shape[1])
+        self._check(self._lib.hyprec_set_factors(self._h, _ptr(u), _ptr(v), self.k))
+
+    def get_factors(self, user_out=None, item_out=None):
+        """Copy the factors into the given float64 C-contiguous arrays (allocated when None)."""
+        if user_out is None:
+            user_out = numpy.empty((self.m, self.k))
+        if item_out is None:
+            item_out = numpy.empty((self.n, self.k))
+        for arr in (user_out, item_out):
+            if arr is not False and not (arr.dtype == numpy.float64 and arr.flags.c_contiguous):
+                raise ValueError("factor outputs must be C-contiguous float64")
+        self._check(self._lib.hyprec_get_factors(self._h, _ptr(user_out) if user_out is not False else None,
+                                                 _ptr(item_out) if item_out is not False else None))
+        return user_out, item_out
+
+    def device_factors(self):
+        u, v, e = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
+        self._check(self._lib.hyprec_device_factors(self._h, ctypes.byref(u), ctypes.byref(v), ctypes.byref(e)))
+        return u.value, v.value, e.value
+
+    def set_item_prior(self, theta):
+        theta = _as(theta, numpy.float64)
+        self._check(self._lib.hyprec_set_item_prior(self._h, _ptr(theta)))
+
+    # ---- compute
+    def als_half_step(self, side, lam):
+        self._check(self._lib.hyprec_als_half_step(self._h, side, float(lam)))
+
+    def rmse(self):
+        out = ctypes.c_double()
+        self._check(self._lib.hyprec_rmse(self._h, ctypes.byref(out)))
+        return out.value
+
+    def train(self, n_iter, lam, start_error=numpy.inf, callback=None):
+        """Returns (epochs_run, last_rmse); callback(epoch, rmse, seconds)."""
+        cb = EPOCH_CB(lambda e, r, s, _u: callback(e, r, s)) if callback else ctypes.cast(None, EPOCH_CB)
+        epochs, last = ctypes.c_int(), ctypes.c_double()
+        self._check(self._lib.hyprec_train(self._h, int(n_iter), float(lam), float(start_error), cb, None,
+                                           ctypes.byref(epochs), ctypes.byref(last)))
+        return epochs.value, last.value
+
+    def predict_dense(self):
+        out = numpy.empty((self.m, self.n))
+        self._check(self._lib.hyprec_predict_dense(self._h, _ptr(out)))
+        return out
+
+    def eval_topk(self, capacity, cand_indptr=None, cand_ids=None, user_lo=0, user_hi=None, want_counts=True,
+                  want_topk=True, n_train_nz=None, n_test_nz=None):
+        """Returns dict(thresholds, ones_per_row, topk_idx, topk_val, topk_hit, train_flags, test_flags)."""
+        user_hi = self.m if user_hi is None else user_hi
+        nu = user_hi - user_lo
+        cand_indptr, cand_ids = _as(cand_indptr, numpy.int64), _as(cand_ids, numpy.int32)
+        out = dict(thresholds=numpy.empty(nu))
+        out["ones_per_row"] = numpy.zeros(nu, dtype=numpy.int64) if want_counts else None
+        if want_topk:
+            out["topk_idx"] = numpy.empty((nu, capacity), dtype=numpy.int32)
+            out["topk_val"] = numpy.empty((nu, capacity))
+            out["topk_hit"] = numpy.empty((nu, capacity))
+        else:
+            out["topk_idx"] = out["topk_val"] = out["topk_hit"] = None
+        out["train_flags"] = numpy.zeros(n_train_nz, dtype=numpy.uint8) if n_train_nz is not None else None
+        out["test_flags"] = numpy.zeros(n_test_nz, dtype=numpy.uint8) if n_test_nz is not None else None
+        self._check(self._lib.hyprec_eval_topk(
+            self._h, user_lo, user_hi, _ptr(cand_indptr), _ptr(cand_ids), int(capacity), _ptr(out["thresholds"]),
+            _ptr(out["ones_per_row"]), _ptr(out["topk_idx"]), _ptr(out["topk_val"]), _ptr(out["topk_hit"]),
+            _ptr(out["train_flags"]), _ptr(out["test_flags"])))
+        return out
+
+    def kernel_ms(self, which):
+        """(total ms, timed regions, ms of the latest API call) of one kernel class."""
+        total, calls, last = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+        self._check(self._lib.hyprec_kernel_ms(self._h, which, ctypes.byref(total), ctypes.byref(calls),
+                                               ctypes.byref(last)))
+        return total.value, calls.value, last.value
+
+    def reset_kernel_ms(self):
+        self._check(self._lib.hyprec_reset_kernel_ms(self._h))
+
+    def probe_fma_tflops(self, precision):
+        out = ctypes.c_double()
+        self._check(self._lib.hyprec_probe_fma_tflops(self._h, int(precision), ctypes.byref(out)))
+        return out.value
+
+    def flush_l2(self):
+        self._check(self._lib.hyprec_flush_l2(self._h))

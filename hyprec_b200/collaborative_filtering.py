@@ -1,0 +1,394 @@
+"""
+Drop-in replacement for the reference's ``CollaborativeFiltering``
+(/root/reference/lib/collaborative_filtering.py:13-302) whose heavy lifting runs on a B200
+through the C ABI of include/hyprec_b200.h.
+
+Same constructor (positional order of collaborative_filtering.py:18-20), attributes
+(``user_vecs``, ``item_vecs``, ``train_data``, ``test_data``, ``n_factors``, ``hyperparameters``,
+``predictions``, ``document_distribution`` ...) and methods, so ``RecommenderSystem``
+(lib/recommender_system.py:97-101), ``GridSearch`` (lib/grid_search.py:63-75) and ``runnables.py``
+(:115-118) can use it unchanged; ``hyprec_b200.install()`` rebinds the reference's module
+attribute to this class.
+
+What runs where:
+  * ``partial_train`` / ``als_step``      -> hyprec_train / hyprec_als_half_step (device)
+  * ``get_predictions``                   -> hyprec_predict_dense (device GEMM, dense result on host)
+  * ``get_evaluation_report``             -> hyprec_eval_topk + hyprec_rmse (device); the float16 means
+                                             are taken on the host with the reference's numpy call
+  * splits, configuration, checkpoints    -> host (evaluator / initializer objects passed in)
+There is no CPU fallback: without the CUDA library or a GPU the first device call raises.
+
+Environment knobs (the JSON config surface is unchanged): ``HYPREC_PRECISION`` = fp64 (default,
+parity with numpy float64) | fp32; ``HYPREC_DEVICE`` = CUDA device index (default: LOCAL_RANK or 0).
+"""
+import os
+import time
+
+import numpy
+import scipy.sparse as sp
+
+from hyprec_b200 import _native, metrics
+from hyprec_b200.abstract_recommender import AbstractRecommender, REPORT_FORMAT
+
+
+def _precision_from_env():
+    name = os.environ.get("HYPREC_PRECISION", "fp64").lower()
+    if name in ("fp64", "f64", "float64", "0"):
+        return _native.F64
+    if name in ("fp32", "f32", "float32", "1"):
+        return _native.F32
+    raise ValueError("HYPREC_PRECISION must be fp64 or fp32, got %r" % name)
+
+
+def _csr_triplet(matrix):
+    """(indptr int64, indices int32, values float64) of a dense or scipy-sparse matrix, zeros
+    dropped, column ids sorted."""
+    csr = matrix if sp.issparse(matrix) else sp.csr_matrix(numpy.asarray(matrix, dtype=numpy.float64))
+    csr = sp.csr_matrix(csr, dtype=numpy.float64)
+    csr.eliminate_zeros()
+    csr.sort_indices()
+    return csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
+
+
+class CollaborativeFiltering(AbstractRecommender):
+    n_recommendations = 200          # abstract_recommender.py:111
+    recall_cutoff = 200              # abstract_recommender.py:114
+
+    def __init__(self, initializer, evaluator, hyperparameters, options,
+                 verbose=False, load_matrices=True, dump_matrices=True, train_more=True,
+                 is_hybrid=False, update_with_items=False, init_with_content=True):
+        self.initializer = initializer
+        self.evaluator = evaluator
+        self.ratings = evaluator.get_ratings()
+        self.n_users, self.n_items = self.ratings.shape
+        self.k_folds = None
+        self.prediction_fold = -1
+
+        self._verbose = verbose
+        self._load_matrices = load_matrices
+        self._dump_matrices = dump_matrices
+        self._train_more = train_more
+        self._is_hybrid = is_hybrid
+        self._update_with_items = update_with_items
+        self._split_type = 'user'
+        self._init_with_content = init_with_content
+
+        self.document_distribution = None
+        self._handle = None
+        self._precision = _precision_from_env()
+        self._train_uploaded = None      # the train_data object the device CSR was built from
+        self._eval_uploaded = None       # (ratings, test_data) objects of the uploaded eval CSRs
+        self._train_nnz = 0
+        self._test_nnz = 0
+        self._sync_token = None
+        self.last_report_details = None  # per-user device outputs of the latest report
+
+        self.set_hyperparameters(hyperparameters)
+        self.set_options(options)
+
+    # ------------------------------------------------------------------ configuration
+    def set_hyperparameters(self, hyperparameters):
+        self.n_factors = hyperparameters['n_factors']
+        self._lambda = hyperparameters['_lambda']
+        self.predictions = None
+        self.hyperparameters = hyperparameters.copy()
+
+    def set_item_based_recommender(self, recommender):
+        self.item_based_recommender = recommender
+
+    def _get_options_suffix(self):
+        suffix = ('i' if self._init_with_content else '') + ('u' if self._update_with_items else '')
+        return '_' + suffix if suffix else ''
+
+    # ------------------------------------------------------------------ device state
+    def device(self):
+        """The C-ABI handle (created on first use; raises without the CUDA library / a GPU)."""
+        if self._handle is None:
+            index = int(os.environ.get("HYPREC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            self._handle = _native.Handle(index, self._precision)
+        return self._handle
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+            self._train_uploaded = self._eval_uploaded = self._sync_token = None
+
+    def set_data(self, train_data, test_data):
+        AbstractRecommender.set_data(self, train_data, test_data)
+        self._sync_token = None
+
+    def _upload_train(self):
+        h = self.device()
+        if self._train_uploaded is not self.train_data:
+            indptr, indices, values = _csr_triplet(self.train_data)
+            h.set_train_csr(self.n_users, self.n_items, indptr, indices, values)
+            self._train_nnz = len(indices)
+            self._train_uploaded = self.train_data
+            self._eval_uploaded = None
+            self._sync_token = None
+        return h
+
+    def _upload_eval(self):
+        h = self._upload_train()
+        key = (self.ratings, self.test_data)
+        if self._eval_uploaded is None or self._eval_uploaded[0] is not key[0] or self._eval_uploaded[1] is not key[1]:
+            full = _csr_triplet(self.ratings)
+            test = _csr_triplet(self.test_data)
+            h.set_eval_csr(full, test)
+            self._test_nnz = len(test[1])
+            self._eval_uploaded = key
+        return h
+
+    @staticmethod
+    def _fingerprint(user_vecs, item_vecs):
+        """Cheap witness that the host factor arrays still hold what the device holds."""
+        def sample(a):
+            flat = a.reshape(-1)
+            step = max(1, flat.shape[0] // 509)
+            return float(flat[::step].sum()), float(flat[-1]), a.shape, a.__array_interface__['data'][0]
+        return sample(user_vecs), sample(item_vecs)
+
+    def _upload_factors(self, force=False):
+        h = self._upload_train()
+        token = self._fingerprint(self.user_vecs, self.item_vecs)
+        if force or token != self._sync_token:
+            h.set_factors(self.user_vecs, self.item_vecs)
+            self._sync_token = token
+        return h
+
+    def _download_factors(self, h):
+        """Write the device factors INTO the existing host arrays: ``item_vecs`` may alias the
+        caller's theta, which the reference overwrites in place."""
+        def target(arr):
+            ok = arr.dtype == numpy.float64 and arr.flags.c_contiguous and arr.flags.writeable
+            return arr if ok else numpy.empty(arr.shape)
+        u_out, v_out = target(self.user_vecs), target(self.item_vecs)
+        h.get_factors(u_out, v_out)
+        if u_out is not self.user_vecs:
+            self.user_vecs[...] = u_out
+        if v_out is not self.item_vecs:
+            self.item_vecs[...] = v_out
+        self._sync_token = self._fingerprint(self.user_vecs, self.item_vecs)
+
+    # ------------------------------------------------------------------ ALS
+    def build_confidence_matrix(self, index, type='user'):
+        """collaborative_filtering.py:120-144: 1.0 on train non-zeros of the row/column, else 0.1."""
+        train = self.train_data
+        line = train[index] if type == 'user' else train[:, index]
+        if sp.issparse(line):
+            line = numpy.asarray(line.todense()).ravel()
+        return numpy.where(numpy.asarray(line) != 0, 1.0, 0.1)
+
+    def als_step(self, latent_vectors, fixed_vecs, ratings, _lambda, type='user'):
+        """One half-step (collaborative_filtering.py:69-99): ``latent_vectors`` is overwritten in
+        place and returned.  As in the reference the confidence pattern comes from
+        ``self.train_data``; ``ratings`` must be that same matrix (the only way the reference and
+        SDAE.py:218-219 call it)."""
+        if ratings is not self.train_data:
+            same = ratings.shape == self.train_data.shape and (
+                (ratings != self.train_data).nnz == 0 if sp.issparse(ratings) or sp.issparse(self.train_data)
+                else numpy.array_equal(ratings, self.train_data))
+            if not same:
+                raise NotImplementedError("als_step: ratings other than self.train_data are not supported "
+                                          "on the device path")
+        if type not in ('user', 'item'):
+            return latent_vectors       # the reference does nothing for other values (:79-99)
+        h = self._upload_train()
+        if type == 'user':
+            h.set_factors(latent_vectors, fixed_vecs)
+            h.set_item_prior(None)
+            h.als_half_step(_native.SIDE_USER, _lambda)
+            solved, _ = h.get_factors(None, False)
+        else:
+            h.set_factors(fixed_vecs, latent_vectors)
+            prior = self.document_distribution if self._update_with_items else None
+            h.set_item_prior(prior)
+            h.als_half_step(_native.SIDE_ITEM, _lambda)
+            _, solved = h.get_factors(False, None)
+        latent_vectors[...] = solved
+        self._sync_token = None
+        return latent_vectors
+
+    def train(self, item_vecs=None):
+        """collaborative_filtering.py:102-118."""
+        self.document_distribution = item_vecs.copy() if item_vecs is not None else None
+        if self.splitting_method == 'naive':
+            self.set_data(*self.evaluator.naive_split(self._split_type))
+            self.hyperparameters['fold'] = 0
+            return self.train_one_fold(item_vecs)
+        self.fold_test_indices = self.evaluator.get_kfold_indices()
+        return self.train_k_fold(item_vecs)
+
+    def train_k_fold(self, item_vecs=None):
+        """collaborative_filtering.py:147-161."""
+        all_errors = []
+        for current_k in range(self.k_folds):
+            self.set_data(*self.evaluator.get_fold(current_k, self.fold_test_indices))
+            self.hyperparameters['fold'] = current_k
+            all_errors.append(self.train_one_fold(item_vecs))
+            self.predictions = None
+        return numpy.mean(all_errors, axis=0)
+
+    def train_one_fold(self, item_vecs=None):
+        """collaborative_filtering.py:164-212: initialise (random / theta / checkpoint), train,
+        optionally save, report.  The order of the ``numpy.random`` draws is the reference's
+        (user matrix first)."""
+        user_shape, item_shape = (self.n_users, self.n_factors), (self.n_items, self.n_factors)
+        matrices_found = False
+        if self._load_matrices is False:
+            self.user_vecs = numpy.random.random(user_shape)
+            use_content = item_vecs is not None and self._init_with_content and item_vecs.shape == item_shape
+            self.item_vecs = item_vecs if use_content else numpy.random.random(item_shape)
+        else:
+            suffix = self._get_options_suffix()
+            users_found, self.user_vecs = self.initializer.load_matrix(self.hyperparameters, 'user_vecs' + suffix,
+                                                                       user_shape)
+            if self._verbose and users_found:
+                print("User distributions files were found.")
+            items_found, self.item_vecs = self.initializer.load_matrix(self.hyperparameters, 'item_vecs' + suffix,
+                                                                       item_shape)
+            if self._verbose and items_found:
+                print("Document distributions files were found.")
+            if not items_found and item_vecs is not None:
+                items_found = True
+                self.item_vecs = item_vecs
+            matrices_found = users_found and items_found
+        self._sync_token = None
+        if not matrices_found:
+            if self._verbose and self._load_matrices:
+                print("User and Document distributions files were not found, will train collaborative.")
+            self.partial_train()
+        elif self._train_more:
+            if self._verbose and self._load_matrices:
+                print("User and Document distributions files found, will train model further.")
+            self.partial_train()
+        elif self._verbose and self._load_matrices:
+            print("User and Document distributions files found, will not train the model further.")
+
+        if self._dump_matrices:
+            self.initializer.set_config(self.hyperparameters, self.n_iter)
+            self.initializer.save_matrix(self.user_vecs, 'user_vecs' + self._get_options_suffix())
+            self.initializer.save_matrix(self.item_vecs, 'item_vecs' + self._get_options_suffix())
+        return self.get_evaluation_report()
+
+    def partial_train(self):
+        """collaborative_filtering.py:224-259, device-resident: factors go up once, the epochs
+        (user half-step, item half-step, RMSE, ``error >= old_error`` break) run inside
+        hyprec_train, and the result is written back into the host arrays."""
+        h = self._upload_factors(force=True)
+        use_prior = self._update_with_items and self.document_distribution is not None
+        h.set_item_prior(self.document_distribution if use_prior else None)
+        fold = self.hyperparameters['fold'] + 1 if 'fold' in self.hyperparameters else 0
+        prefix = 'Fold:{:02d} '.format(fold) if fold != 0 else ''
+        line = prefix + 'Epoch:{epoch:02d} Loss:{loss:1.4e} Time:{time:.3f}s'
+        error = numpy.inf
+        if self._verbose:
+            error = h.rmse()
+            print(line.format(epoch=0, loss=error, time=0))
+        state = {'previous': error, 'stalled': False}
+
+        def on_epoch(epoch, rmse, seconds):
+            if self._verbose:
+                print(line.format(epoch=epoch, loss=rmse, time=seconds))
+            state['stalled'] = rmse >= state['previous']
+            state['previous'] = rmse
+
+        h.train(self.n_iter, self._lambda, error, on_epoch)
+        if self._verbose and state['stalled']:
+            print("Local Optimum was found in the last iteration, breaking.")
+        self._download_factors(h)
+
+    # ------------------------------------------------------------------ prediction
+    def get_predictions(self):
+        """collaborative_filtering.py:262-284; the dense product is computed on the device."""
+        if self.predictions is None or not self.prediction_fold == self.hyperparameters['fold']:
+            h = self._upload_factors()
+            collaborative_predictions = h.predict_dense()
+            if self._is_hybrid:
+                try:
+                    from lib.linear_regression import LinearRegression
+                except ImportError:
+                    raise NotImplementedError("the hybrid linear-regression blend (lib/linear_regression.py) is "
+                                              "outside the B200 hot path; run inside the reference tree to use it")
+                self.item_based_recommender.set_data(self.train_data, self.test_data)
+                regr = LinearRegression(self.train_data, self.test_data,
+                                        self.item_based_recommender.get_predictions(), collaborative_predictions)
+                self.predictions = regr.train()
+                if self._verbose:
+                    print("returned linear regression ratings")
+            else:
+                self.predictions = collaborative_predictions
+            self.prediction_fold = self.hyperparameters['fold']
+        return self.predictions
+
+    def predict(self, user, item):
+        return self.user_vecs[user, :].dot(self.item_vecs[item, :].T)
+
+    def recommend_items(self, user_id, num_recommendations=10):
+        """abstract_recommender.py:189-204 without the dense matrix: full-catalogue top-N of one user
+        on the device, returned ascending like TopRecommendations' lists."""
+        if self._is_hybrid:
+            return AbstractRecommender.recommend_items(self, user_id, num_recommendations)
+        h = self._upload_factors()
+        out = h.eval_topk(num_recommendations, None, None, user_id, user_id + 1, want_counts=False)
+        keep = out["topk_idx"][0] >= 0
+        ids = [int(i) for i in out["topk_idx"][0][keep]]
+        vals = [float(v) for v in out["topk_val"][0][keep]]
+        return zip(reversed(ids), reversed(vals))
+
+    # ------------------------------------------------------------------ evaluation
+    def candidate_lists(self, fold):
+        """The candidate stream of every user exactly as load_top_recommendations reads it:
+        ``evaluator.test_indices[user * (1 + fold)]`` cast to int (evaluator.py:225-228; SURVEY.md
+        App. A Q6 / Q7 describe what that slot holds for k-fold and naive splits)."""
+        rows = [numpy.asarray(self.evaluator.test_indices[user * (1 + fold)]).astype(numpy.int64)
+                for user in range(self.n_users)]
+        indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
+        numpy.cumsum([len(r) for r in rows], out=indptr[1:])
+        ids = numpy.concatenate(rows).astype(numpy.int32) if len(rows) else numpy.zeros(0, numpy.int32)
+        return indptr, ids
+
+    def get_evaluation_report(self):
+        """abstract_recommender.py:100-131.  Scores never leave the GPU: the device returns row
+        thresholds, per-row counts of rounded ones, the streamed top-200 of every user's candidate
+        list with hit flags, and the rounded prediction at every train / test positive; the metric
+        arithmetic is then the reference's."""
+        if self._is_hybrid:
+            return AbstractRecommender.get_evaluation_report(self)
+        fold = self.hyperparameters['fold']
+        h = self._upload_eval()
+        self._upload_factors()
+        cand_indptr, cand_ids = self.candidate_lists(fold)
+        out = h.eval_topk(self.n_recommendations, cand_indptr, cand_ids, 0, self.n_users,
+                          n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
+        rmse = h.rmse()
+
+        lengths = (out["topk_idx"] >= 0).sum(axis=1)
+        recs = [[int(i) for i in row[:n]] for row, n in zip(out["topk_idx"], lengths)]
+        hits = out["topk_hit"]
+        self.evaluator.recommendation_indices = recs
+        self.evaluator.recs_loaded = True
+        if hasattr(self.evaluator, "set_device_results"):
+            self.evaluator.set_device_results(recs, [hits[u][:lengths[u]] for u in range(self.n_users)])
+
+        test_sum = self.test_data.sum()
+        train_sum = self.train_data.sum()
+        with numpy.errstate(divide='ignore', invalid='ignore'):
+            # sum(rounded[ratings.nonzero()]) / sum(sum(ratings))  (evaluator.py:263-266)
+            train_recall = numpy.float64(out["train_flags"].sum(dtype=numpy.int64)) / numpy.float64(train_sum)
+            test_recall = numpy.float64(out["test_flags"].sum(dtype=numpy.int64)) / numpy.float64(test_sum)
+            ratio = numpy.float64(out["ones_per_row"].sum()) / sum(sum(self.ratings))
+        test_likes = numpy.asarray(self.test_data.sum(axis=1)).ravel()
+        recall_at_x = metrics.recall_at_x(self.recall_cutoff, hits, test_likes)
+        mrr_at_five = metrics.mrr_at(5, hits, lengths)
+        ndcg_at_five = metrics.ndcg_at(5, hits, lengths)
+        mrr_at_ten = metrics.mrr_at(10, hits, lengths)
+        ndcg_at_ten = metrics.ndcg_at(10, hits, lengths)
+        out["lengths"] = lengths
+        self.last_report_details = out
+        report = (test_sum, train_sum, rmse, train_recall, test_recall, recall_at_x, ratio, mrr_at_five,
+                  ndcg_at_five, mrr_at_ten, ndcg_at_ten)
+        if self._verbose:
+            print(REPORT_FORMAT.format(*report))
+        return report

@@ -98,20 +98,59 @@ struct hyprec_ctx {
     int max_smem = 0;
     int64_t launches = 0;
     int64_t user_lo = 0, user_hi = -1, item_lo = 0, item_hi = -1;   // shard; hi < 0 => all
-    cudaEvent_t ev_begin[kNumTimers], ev_end[kNumTimers];
-    bool ev_used[kNumTimers];
+    // kernel timing: (begin, end) event pairs taken from a pool, harvested into per-class
+    // totals after the stream has been synchronised
+    std::vector<cudaEvent_t> ev_pool;
+    struct Pending { cudaEvent_t b, e; int which; };
+    std::vector<Pending> pending;
+    double ms_total[kNumTimers] = {0};
+    double ms_last[kNumTimers] = {0};
+    int64_t ms_calls[kNumTimers] = {0};
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
     EngineBase* engine = nullptr;
+
+    cudaEvent_t take_event() {
+        if (ev_pool.empty()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            return e;
+        }
+        cudaEvent_t e = ev_pool.back();
+        ev_pool.pop_back();
+        return e;
+    }
+    void harvest() {   // call only when the stream is idle
+        bool seen[kNumTimers] = {false};
+        for (const Pending& p : pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.b, p.e) == cudaSuccess) {
+                ms_total[p.which] += ms;
+                ms_calls[p.which] += 1;
+                ms_last[p.which] = seen[p.which] ? ms_last[p.which] + ms : ms;
+                seen[p.which] = true;
+            }
+            ev_pool.push_back(p.b);
+            ev_pool.push_back(p.e);
+        }
+        pending.clear();
+    }
 };
 
 namespace {
 
 struct Timer {
     hyprec_ctx* h;
-    int which;
-    Timer(hyprec_ctx* ctx, int w) : h(ctx), which(w) { cudaEventRecord(h->ev_begin[w], h->stream); }
+    hyprec_ctx::Pending p;
+    Timer(hyprec_ctx* ctx, int w) : h(ctx) {
+        p.which = w;
+        p.b = h->take_event();
+        p.e = h->take_event();
+        cudaEventRecord(p.b, h->stream);
+    }
     ~Timer() {
-        cudaEventRecord(h->ev_end[which], h->stream);
-        h->ev_used[which] = true;
+        cudaEventRecord(p.e, h->stream);
+        h->pending.push_back(p);
     }
 };
 
@@ -595,6 +634,50 @@ struct Engine : EngineBase {
     }
 };
 
+// Peak-rate probe: 16 independent FMA chains per thread, enough CTAs to fill every SM.
+template <typename T>
+__global__ void fma_probe_kernel(T* out, int iters, T seed) {
+    T acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = seed + T(i) + T(threadIdx.x);
+    const T a = T(1.0000001), b = T(1e-9);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + b;
+    }
+    T s = T(0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == T(-1)) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the loop alive
+}
+
+template <typename T>
+int run_fma_probe(hyprec_ctx* h, double* tflops) {
+    const int iters = 4096, threads = 256, blocks = h->num_sms * 16;
+    T* out = nullptr;
+    CU_TRY(cudaMalloc(&out, sizeof(T) * (size_t)threads * blocks));
+    cudaEvent_t b, e;
+    CU_TRY(cudaEventCreate(&b));
+    CU_TRY(cudaEventCreate(&e));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(b, h->stream));
+        fma_probe_kernel<T><<<blocks, threads, 0, h->stream>>>(out, iters, T(rep));
+        CU_TRY(cudaEventRecord(e, h->stream));
+        CU_TRY(cudaEventSynchronize(e));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, b, e));
+        const double flops = 2.0 * 16.0 * iters * (double)threads * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        h->launches += 1;
+    }
+    cudaEventDestroy(b);
+    cudaEventDestroy(e);
+    cudaFree(out);
+    *tflops = best;
+    return HYPREC_OK;
+}
+
 int check(hyprec_t* h) {
     if (!h || !h->engine) return fail(HYPREC_E_INVALID, "null handle");
     cudaError_t e = cudaSetDevice(h->device);
@@ -629,11 +712,6 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < kNumTimers; ++i) {
-        CU_TRY(cudaEventCreate(&h->ev_begin[i]));
-        CU_TRY(cudaEventCreate(&h->ev_end[i]));
-        h->ev_used[i] = false;
-    }
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);
     else h->engine = new Engine<float>(h);
     *out = h;
@@ -645,10 +723,9 @@ int hyprec_destroy(hyprec_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     delete h->engine;
-    for (int i = 0; i < kNumTimers; ++i) {
-        cudaEventDestroy(h->ev_begin[i]);
-        cudaEventDestroy(h->ev_end[i]);
-    }
+    h->harvest();
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->flush_buf) cudaFree(h->flush_buf);
     cudaStreamDestroy(h->stream);
     delete h;
     return HYPREC_OK;
@@ -742,12 +819,46 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
                                 topk_idx, topk_val, topk_hit, train_flags, test_flags);
 }
 
-int hyprec_last_kernel_ms(hyprec_t* h, int which, float* ms) {
+int hyprec_kernel_ms(hyprec_t* h, int which, double* total_ms, int64_t* calls, double* last_ms) {
     HY_TRY(check(h));
-    if (which < 0 || which >= kNumTimers || !ms) return fail(HYPREC_E_INVALID, "hyprec_last_kernel_ms: bad argument");
-    if (!h->ev_used[which]) { *ms = 0.f; return HYPREC_OK; }
-    CU_TRY(cudaEventSynchronize(h->ev_end[which]));
-    CU_TRY(cudaEventElapsedTime(ms, h->ev_begin[which], h->ev_end[which]));
+    if (which < 0 || which >= kNumTimers) return fail(HYPREC_E_INVALID, "hyprec_kernel_ms: bad timer id");
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    h->harvest();
+    if (total_ms) *total_ms = h->ms_total[which];
+    if (calls) *calls = h->ms_calls[which];
+    if (last_ms) *last_ms = h->ms_last[which];
+    return HYPREC_OK;
+}
+
+int hyprec_reset_kernel_ms(hyprec_t* h) {
+    HY_TRY(check(h));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    h->harvest();
+    for (int i = 0; i < kNumTimers; ++i) {
+        h->ms_total[i] = 0;
+        h->ms_last[i] = 0;
+        h->ms_calls[i] = 0;
+    }
+    return HYPREC_OK;
+}
+
+int hyprec_probe_fma_tflops(hyprec_t* h, int precision, double* tflops) {
+    HY_TRY(check(h));
+    if (!tflops) return fail(HYPREC_E_INVALID, "hyprec_probe_fma_tflops: null output");
+    if (precision == HYPREC_F64) return run_fma_probe<double>(h, tflops);
+    if (precision == HYPREC_F32) return run_fma_probe<float>(h, tflops);
+    return fail(HYPREC_E_INVALID, "precision must be 0 (f64) or 1 (f32)");
+}
+
+int hyprec_flush_l2(hyprec_t* h) {
+    HY_TRY(check(h));
+    const size_t want = (size_t)384 << 20;   // 3x the 126 MB L2
+    if (!h->flush_buf) {
+        CU_TRY(cudaMalloc(&h->flush_buf, want));
+        h->flush_bytes = want;
+    }
+    CU_TRY(cudaMemsetAsync(h->flush_buf, 0x5a, h->flush_bytes, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
     return HYPREC_OK;
 }
 

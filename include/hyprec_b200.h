@@ -122,7 +122,9 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
                      int64_t* ones_per_row, int32_t* topk_idx, double* topk_val, double* topk_hit,
                      uint8_t* train_flags, uint8_t* test_flags);
 
-/* Device time (ms, CUDA events) of the most recent call of each kind; for bench.py's roofline. */
+/* Device time of the library's kernels, measured with CUDA events on the launching stream and
+ * accumulated per class since creation / the last reset: total ms, number of timed regions, and
+ * the ms of the regions of the most recent API call.  For bench.py's roofline. */
 #define HYPREC_T_GRAM 0
 #define HYPREC_T_SOLVE 1
 #define HYPREC_T_RMSE 2
@@ -130,7 +132,13 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
 #define HYPREC_T_TOPK 4
 #define HYPREC_T_FLAGS 5
 #define HYPREC_T_COUNT 6
-int hyprec_last_kernel_ms(hyprec_t* h, int which, float* ms);
+int hyprec_kernel_ms(hyprec_t* h, int which, double* total_ms, int64_t* calls, double* last_ms);
+int hyprec_reset_kernel_ms(hyprec_t* h);
+/* Measured FMA rate of this GPU (TFLOP/s, best of 4 after a warm-up) in the given precision:
+ * the roofline denominator for the SIMT solve kernel, which MEASURED_PEAKS.json does not hold. */
+int hyprec_probe_fma_tflops(hyprec_t* h, int precision, double* tflops);
+/* Overwrite a buffer 3x the size of L2 so the next kernel starts cold (benchmark hygiene). */
+int hyprec_flush_l2(hyprec_t* h);
 
 #ifdef __cplusplus
 }

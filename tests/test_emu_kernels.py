@@ -1,0 +1,180 @@
+"""The SIMT kernels (hyprec_b200/csrc/*.cuh) executed on the CPU through the pthread CUDA shim of
+tests/emu/ and compared with the oracle: indexing, tiling, padding, synchronisation and the tie
+rules are checked here without a GPU.  The GPU parity tests proper are tests/test_gpu_parity.py."""
+import ctypes
+import importlib.util
+import os
+
+import numpy
+import pytest
+
+from conftest import golden_folds, split_lists
+from oracle import als as oals
+from oracle import evaluation as oev
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+I64, DBL = ctypes.c_int64, ctypes.c_double
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    spec = importlib.util.spec_from_file_location("emu_build", os.path.join(HERE, "emu", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return ctypes.CDLL(mod.build())
+
+
+def half_step(emu, csr, fixed, latent, lam, prior=None, chunk=4, grid=2, smem=1, lo=0, hi=None, f32=False):
+    dt = numpy.float32 if f32 else numpy.float64
+    out = numpy.ascontiguousarray(latent, dtype=dt).copy()
+    fixed = numpy.ascontiguousarray(fixed, dtype=dt)
+    prior = None if prior is None else numpy.ascontiguousarray(prior, dtype=dt)
+    ip, ix, vals = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(dt)
+    hi = out.shape[0] if hi is None else hi
+    fn = emu.emu_half_step_f32 if f32 else emu.emu_half_step_f64
+    lam_c = ctypes.c_float(lam) if f32 else DBL(lam)
+    status = fn(_ptr(ip), _ptr(ix), _ptr(vals), _ptr(fixed), I64(fixed.shape[0]), _ptr(out), I64(lo), I64(hi),
+                out.shape[1], lam_c, _ptr(prior), chunk, grid, smem)
+    return out, status
+
+
+@pytest.mark.parametrize("k", [1, 5, 7, 8, 9, 16, 23])
+def test_solve_kernel_all_paddings(emu, k):
+    """k covers: single tile, rhs row inside the last diagonal tile (k % 8 != 0), rhs row in its
+    own tile (k % 8 == 0), several panels."""
+    rs = numpy.random.RandomState(k)
+    m, n = 6, 40
+    train = (rs.rand(m, n) < 0.4).astype(numpy.float64) * rs.randint(1, 3, size=(m, n))
+    train[2, :] = 0
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    want = oals.als_half_step(u0.copy(), v0, oals.to_csr(train), 0.01)
+    got, status = half_step(emu, oals.to_csr(train), v0, u0, 0.01, chunk=4, grid=3)
+    assert status == 0
+    assert numpy.allclose(got, want, rtol=1e-10, atol=1e-12)
+    assert numpy.all(got[2] == 0)          # empty row -> exact zeros (App. A Q10)
+
+
+def test_solve_kernel_golden_epoch(emu, als_cases):
+    g = als_cases["als_theta_toy"]
+    fold = golden_folds(g)[0]
+    lam, train = float(g["lam"]), fold["train"]
+    csr, csc = oals.to_csr(train), oals.to_csr(train.T)
+    u, _ = half_step(emu, csr, fold["v0"], fold["u0"], lam, chunk=8, grid=4)
+    v, _ = half_step(emu, csc, u, fold["v0"], lam, prior=g["theta"], chunk=8, grid=4)
+    u_ref = oals.als_half_step(fold["u0"].copy(), fold["v0"], csr, lam)
+    v_ref = oals.als_half_step(fold["v0"].copy(), u_ref, csc, lam, prior=g["theta"])
+    assert numpy.allclose(u, u_ref, rtol=1e-9, atol=1e-11)
+    assert numpy.allclose(v, v_ref, rtol=1e-9, atol=1e-11)
+
+
+def test_solve_kernel_shard_scratch_and_f32(emu):
+    rs = numpy.random.RandomState(2)
+    m, n, k = 9, 50, 12
+    train = (rs.rand(m, n) < 0.5).astype(numpy.float64)
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    want = oals.als_half_step(u0.copy(), v0, oals.to_csr(train), 0.05)
+    got, _ = half_step(emu, oals.to_csr(train), v0, u0, 0.05, chunk=16, grid=2, smem=0, lo=3, hi=7)
+    assert numpy.allclose(got[3:7], want[3:7], rtol=1e-10, atol=1e-12)
+    assert numpy.array_equal(got[:3], u0[:3]) and numpy.array_equal(got[7:], u0[7:])   # outside the shard
+    got32, _ = half_step(emu, oals.to_csr(train), v0, u0, 0.05, chunk=4, grid=2, f32=True)
+    assert numpy.allclose(got32, want, rtol=2e-3, atol=2e-4)
+
+
+def test_singular_system_sets_status(emu):
+    train = numpy.zeros((3, 4))
+    train[0, 1] = 1
+    u0, v0 = numpy.ones((3, 2)), numpy.zeros((4, 2))      # G = 0, lambda = 0 -> singular
+    _, status = half_step(emu, oals.to_csr(train), v0, u0, 0.0)
+    assert status == 1
+
+
+def test_gram_kernel(emu):
+    rs = numpy.random.RandomState(3)
+    for rows, k in ((70, 5), (130, 64), (33, 70)):
+        y = rs.rand(rows, k)
+        g = numpy.empty((k, k))
+        emu.emu_gram_f64(_ptr(y), I64(rows), k, 3, _ptr(g))
+        assert numpy.allclose(g, y.T.dot(y), rtol=1e-12)
+        assert numpy.array_equal(g, g.T)
+
+
+def test_rmse_terms_and_dense_prediction(emu, als_cases):
+    fold = golden_folds(als_cases["als_kfold_toy"])[2]
+    u, v, train = fold["u"], fold["v"], fold["train"]
+    csr = oals.to_csr(train)
+    out = numpy.zeros(3)
+    m, n = train.shape
+    emu.emu_rmse_terms_f64(_ptr(csr.indptr.astype(numpy.int64)), _ptr(csr.indices.astype(numpy.int32)),
+                           _ptr(csr.data), _ptr(u), _ptr(v), I64(m), I64(n), u.shape[1], _ptr(out))
+    rmse = numpy.sqrt((out[0] - 2 * out[1] + out[2]) / (m * n))
+    assert abs(rmse - fold["report"][2]) < 1e-13
+    pred = numpy.empty((m, n))
+    emu.emu_predict_f64(_ptr(u), _ptr(v), I64(m), I64(n), u.shape[1], _ptr(pred))
+    assert numpy.allclose(pred, u.dot(v.T), rtol=1e-13, atol=1e-15)
+
+
+def run_eval(emu, u, v, full, cands, cap, grid=3):
+    m, n = full.shape
+    csr = oals.to_csr(full)
+    fp, fi, fv = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
+    if cands is None:
+        cp = ci = None
+    else:
+        cp = numpy.zeros(m + 1, numpy.int64)
+        cp[1:] = numpy.cumsum([len(c) for c in cands])
+        ci = numpy.concatenate(cands).astype(numpy.int32)
+    thr, ones = numpy.zeros(m), numpy.zeros(m, numpy.int64)
+    tidx = numpy.zeros((m, cap), numpy.int32)
+    tval, thit = numpy.zeros((m, cap)), numpy.zeros((m, cap))
+    emu.emu_eval_f64(_ptr(u), _ptr(v), I64(m), I64(n), u.shape[1], I64(0), I64(m), _ptr(cp), _ptr(ci), cap,
+                     _ptr(fp), _ptr(fi), _ptr(fv), _ptr(thr), _ptr(ones), _ptr(tidx), _ptr(tval), _ptr(thit), grid)
+    return thr, ones, tidx, tval, thit
+
+
+@pytest.mark.parametrize("name", ["als_kfold_toy", "als_naive_toy"])
+def test_eval_kernels_golden(emu, als_cases, name):
+    """Top-200 lists, rounded counts and hits against the unmodified reference, including the
+    all-tied zero user and (naive split) candidate lists made of duplicated ids 0/1."""
+    g = als_cases[name]
+    for fold in golden_folds(g)[:2]:
+        cands = split_lists(fold["cand_ids"], fold["cand_len"])
+        thr, ones, tidx, tval, thit = run_eval(emu, fold["u"], fold["v"], g["ratings"], cands, 200)
+        want = split_lists(fold["rec_ids"], fold["rec_len"])
+        for u_id, w in enumerate(want):
+            assert list(tidx[u_id][:len(w)]) == list(w)
+            assert numpy.all(tidx[u_id][len(w):] == -1)
+        assert numpy.array_equal(ones, fold["rounded_ones"])
+        ref = oev.evaluation_report(fold["u"], fold["v"], g["ratings"], fold["train"], fold["test"], cands)
+        for u_id in range(len(want)):
+            assert numpy.array_equal(thit[u_id][:len(want[u_id])], ref["hits"][u_id])
+
+
+def test_eval_kernel_ties_and_full_catalogue(emu):
+    rs = numpy.random.RandomState(9)
+    m, n, k = 5, 260, 6
+    u = numpy.round((rs.rand(m, k) - 0.3) * 2) / 2
+    v = numpy.round((rs.rand(n, k) - 0.3) * 2) / 2           # quantised: many exactly tied scores
+    full = (rs.rand(m, n) < 0.3).astype(numpy.float64)
+    for cap, cands in ((7, None), (16, [rs.randint(0, n, size=150) for _ in range(m)]), (300, None)):
+        _, _, tidx, _, _ = run_eval(emu, u, v, full, cands, cap)
+        for u_id in range(m):
+            ids = numpy.arange(n) if cands is None else cands[u_id]
+            want, _ = oev.top_recommendations_stream(ids, u[u_id].dot(v[ids].T), cap)
+            assert list(tidx[u_id][:len(want)]) == want
+
+
+def test_nz_flags_kernel(emu, als_cases):
+    fold = golden_folds(als_cases["als_kfold_toy"])[0]
+    u, v, test = fold["u"], fold["v"], fold["test"]
+    csr = oals.to_csr(test)
+    pred = u.dot(v.T)
+    thr = numpy.array([oev.row_threshold(r) for r in pred])
+    flags = numpy.zeros(csr.nnz, dtype=numpy.uint8)
+    emu.emu_nz_flags_f64(_ptr(csr.indptr.astype(numpy.int64)), _ptr(csr.indices.astype(numpy.int32)), _ptr(u), _ptr(v),
+                         u.shape[1], _ptr(thr), I64(0), I64(u.shape[0]), _ptr(flags))
+    rows = numpy.repeat(numpy.arange(u.shape[0]), numpy.diff(csr.indptr))
+    assert numpy.array_equal(flags, (pred[rows, csr.indices] >= thr[rows]).astype(numpy.uint8))

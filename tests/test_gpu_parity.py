@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (hyprec_b200._native.Handle) and
+through the reference-facing class, against (a) golden outputs of the unmodified reference and
+(b) the oracle on the same seeded inputs.
+
+Tolerances (the reference computes in float64 with LAPACK LU; the device uses Cholesky):
+  fp64 mode  factors / predictions  rtol 1e-8 (observed ~1e-13)    top-k ids, counts, flags, metrics: exact
+  fp32 mode  factors / predictions  relative Frobenius error <= 2e-4 (observed ~1e-5)
+"""
+import numpy
+import pytest
+import scipy.sparse as sp
+
+from conftest import golden_folds, split_lists
+from oracle import als as oals
+from oracle import evaluation as oev
+
+pytestmark = pytest.mark.gpu
+
+F64_RTOL = 1e-8
+F32_FROB = 2e-4
+
+
+@pytest.fixture(scope="module")
+def native():
+    from hyprec_b200 import _native
+    return _native
+
+
+def make_handle(native, train, precision=0):
+    h = native.Handle(0, precision)
+    csr = oals.to_csr(train)
+    h.set_train_csr(csr.shape[0], csr.shape[1], csr.indptr, csr.indices, csr.data)
+    return h, csr
+
+
+def rel_frob(a, b):
+    return numpy.linalg.norm(a - b) / max(numpy.linalg.norm(b), 1e-300)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden cases through the reference-facing class
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["als_kfold_4x30", "als_kfold_toy", "als_theta_toy", "als_naive_toy"])
+def test_class_reproduces_reference_run(als_cases, name):
+    """Whole train() flow: identical split (numpy.random seed 42), identical initial draws, device
+    training with early stopping, device evaluation -> the reference's averaged 11-tuple."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
+    g = als_cases[name]
+    hyper = {'n_factors': int(g["k"]), '_lambda': float(g["lam"])}
+    options = {'k_folds': int(g["k_folds"]), 'n_iterations': int(g["n_iter"])}
+    evaluator = Evaluator(g["ratings"])
+    cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), options['n_iterations']), evaluator, hyper, options,
+                                load_matrices=False, dump_matrices=False,
+                                update_with_items=bool(int(g["update_with_items"])))
+    theta = g["theta"].copy() if "theta" in g else None
+    report = numpy.asarray(cf.train(theta), dtype=numpy.float64)
+    want = g["mean_report"]
+    both_nan = numpy.isnan(report) & numpy.isnan(want)
+    assert numpy.all(both_nan | (numpy.abs(report - want) <= 1e-9 * numpy.maximum(1, numpy.abs(want)))), (report, want)
+    last = golden_folds(g)[-1]
+    assert numpy.allclose(cf.user_vecs, last["u"], rtol=F64_RTOL, atol=1e-11)
+    assert numpy.allclose(cf.item_vecs, last["v"], rtol=F64_RTOL, atol=1e-11)
+    recs = [list(r) for r in split_lists(last["rec_ids"], last["rec_len"])]
+    assert cf.evaluator.recommendation_indices == recs
+    assert isinstance(cf.predict(0, 1), numpy.float64)           # collaborative_tests.py:55-56
+    assert cf.get_predictions().shape == g["ratings"].shape
+    assert numpy.allclose(cf.get_predictions(), last["u"].dot(last["v"].T), rtol=1e-7, atol=1e-10)
+    rounded = cf.rounded_predictions()
+    assert set(numpy.unique(rounded)) <= {0.0, 1.0}
+    cf.close()
+
+
+def test_theta_is_overwritten_in_place(als_cases):
+    """train(item_vecs) aliases theta as item_vecs and trains it in place (App. A Q5)."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
+    g = als_cases["als_theta_toy"]
+    hyper = {'n_factors': int(g["k"]), '_lambda': float(g["lam"])}
+    options = {'k_folds': 5, 'n_iterations': int(g["n_iter"])}
+    cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), 4), Evaluator(g["ratings"]), hyper, options,
+                                load_matrices=False, dump_matrices=False, update_with_items=True)
+    theta = g["theta"].copy()
+    cf.train(theta)
+    assert cf.item_vecs is theta
+    assert numpy.allclose(theta, golden_folds(g)[-1]["v"], rtol=F64_RTOL, atol=1e-11)
+    assert numpy.array_equal(cf.document_distribution, g["theta"])
+    cf.close()
+
+
+def test_als_step_signature_in_place(als_cases):
+    """als_step(latent, fixed, ratings, _lambda, type) mutates and returns latent (:85, :99)."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
+    g = als_cases["als_kfold_toy"]
+    fold = golden_folds(g)[0]
+    hyper = {'n_factors': int(g["k"]), '_lambda': 0.01}
+    cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), 1), Evaluator(g["ratings"]), hyper,
+                                {'k_folds': 5, 'n_iterations': 1}, load_matrices=False, dump_matrices=False)
+    cf.set_data(fold["train"], fold["test"])
+    cf.hyperparameters['fold'] = 0
+    u, v = fold["u0"].copy(), fold["v0"].copy()
+    cf.user_vecs, cf.item_vecs = u, v
+    back = cf.als_step(u, v, cf.train_data, 0.01, type='user')
+    assert back is u
+    want_u = oals.als_half_step(fold["u0"].copy(), fold["v0"], oals.to_csr(fold["train"]), 0.01)
+    assert numpy.allclose(u, want_u, rtol=F64_RTOL, atol=1e-12)
+    back = cf.als_step(v, u, cf.train_data, 0.01, type='item')
+    assert back is v
+    want_v = oals.als_half_step(fold["v0"].copy(), want_u, oals.to_csr(fold["train"].T), 0.01)
+    assert numpy.allclose(v, want_v, rtol=F64_RTOL, atol=1e-12)
+    conf = cf.build_confidence_matrix(1, 'user')
+    assert numpy.array_equal(conf, numpy.where(fold["train"][1] != 0, 1.0, 0.1))
+    ids_vals = list(cf.recommend_items(2, 7))
+    want_ids, _ = oev.top_recommendations_stream(numpy.arange(v.shape[0]), u[2].dot(v.T), 7)
+    assert [i for i, _ in ids_vals] == list(reversed(want_ids))
+    cf.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# C ABI against the oracle on synthetic problems
+# ------------------------------------------------------------------------------------------------
+def synthetic(m, n, k, nnz, seed, empty=True):
+    from hyprec_b200 import synth
+    full = synth.ratings_csr("toy", n_users=m, n_items=n, positives=nnz, min_degree=2, seed=seed)
+    rs = numpy.random.RandomState(seed + 1)
+    keep = rs.rand(full.nnz) < 0.8
+    coo = full.tocoo()
+    train = sp.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=full.shape)
+    test = sp.csr_matrix((coo.data[~keep], (coo.row[~keep], coo.col[~keep])), shape=full.shape)
+    if empty:
+        lil = train.tolil()
+        lil[1, :] = 0
+        lil[:, 2] = 0
+        train = lil.tocsr()
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    cands = [rs.permutation(n)[:max(1, n // 5)] for _ in range(m)]
+    return full, oals.to_csr(train), oals.to_csr(test), u0, v0, cands
+
+
+@pytest.mark.parametrize("m,n,k,nnz", [(60, 200, 5, 1200), (300, 900, 50, 9000), (120, 400, 200, 4000),
+                                       (64, 300, 33, 2500)])
+def test_epochs_match_oracle_fp64(native, m, n, k, nnz):
+    full, train, test, u0, v0, cands = synthetic(m, n, k, nnz, seed=k)
+    h, csr = make_handle(native, train)
+    h.set_factors(u0, v0)
+    u, v = u0.copy(), v0.copy()
+    csc = oals.to_csr(train.T)
+    for epoch in range(2):
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        oals.als_half_step(u, v, csr, 0.01)
+        oals.als_half_step(v, u, csc, 0.01)
+        assert abs(h.rmse() - oals.rmse_gram(u, v, csr)) < 1e-12
+    du, dv = h.get_factors()
+    assert numpy.allclose(du, u, rtol=F64_RTOL, atol=1e-12)
+    assert numpy.allclose(dv, v, rtol=F64_RTOL, atol=1e-12)
+    assert numpy.all(du[1] == 0) and numpy.all(dv[2] == 0)       # empty user / item rows
+    assert numpy.allclose(h.predict_dense(), du.dot(dv.T), rtol=1e-10, atol=1e-13)
+    h.close()
+
+
+def check_eval(native, h, full, train, test, u, v, cands, cap):
+    ftr = (full.indptr, full.indices, full.data)
+    ttr = (test.indptr, test.indices, test.data)
+    h.set_eval_csr(ftr, ttr)
+    m = full.shape[0]
+    if cands is None:
+        cp = ci = None
+    else:
+        cp = numpy.zeros(m + 1, numpy.int64)
+        cp[1:] = numpy.cumsum([len(c) for c in cands])
+        ci = numpy.concatenate(cands)
+    out = h.eval_topk(cap, cp, ci, n_train_nz=train.nnz, n_test_nz=test.nnz)
+    ref = oev.evaluation_report(u, v, full, train, test, cands, n_recommendations=cap)
+    assert numpy.allclose(out["thresholds"], ref["thresholds"], rtol=1e-10, atol=1e-14)
+    assert numpy.array_equal(out["ones_per_row"], ref["ones_per_row"])
+    for uid in range(m):
+        want = ref["rec_ids"][uid]
+        assert list(out["topk_idx"][uid][:len(want)]) == want, uid
+        assert numpy.all(out["topk_idx"][uid][len(want):] == -1)
+        assert numpy.allclose(out["topk_val"][uid][:len(want)], ref["rec_vals"][uid], rtol=1e-10, atol=1e-14)
+        assert numpy.array_equal(out["topk_hit"][uid][:len(want)], ref["hits"][uid])
+    pred = u.dot(v.T)
+    for name, mat in (("train_flags", train), ("test_flags", test)):
+        rows = numpy.repeat(numpy.arange(m), numpy.diff(mat.indptr))
+        assert numpy.array_equal(out[name], (pred[rows, mat.indices] >= ref["thresholds"][rows]).astype(numpy.uint8))
+    return out, ref
+
+
+@pytest.mark.parametrize("m,n,k,nnz,cap", [(60, 200, 5, 1200, 200), (300, 900, 50, 9000, 200), (64, 300, 33, 2500, 300)])
+def test_eval_matches_oracle_fp64(native, m, n, k, nnz, cap):
+    full, train, test, u0, v0, cands = synthetic(m, n, k, nnz, seed=100 + k)
+    h, csr = make_handle(native, train)
+    h.set_factors(u0, v0)
+    h.als_half_step(native.SIDE_USER, 0.01)
+    h.als_half_step(native.SIDE_ITEM, 0.01)
+    u, v = h.get_factors()
+    check_eval(native, h, full, train, test, u, v, cands, cap)
+    check_eval(native, h, full, train, test, u, v, None, 50)        # full catalogue (recommend_items)
+    h.close()
+
+
+def test_eval_ties_replay(native):
+    """Quantised factors: exactly tied scores across the cut-off, duplicated candidates."""
+    rs = numpy.random.RandomState(5)
+    m, n, k = 40, 500, 6
+    full = sp.csr_matrix((rs.rand(m, n) < 0.2).astype(numpy.float64))
+    train = oals.to_csr(full.multiply(rs.rand(m, n) < 0.7))
+    test = oals.to_csr(full - train)
+    full = oals.to_csr(full)
+    u = numpy.round((rs.rand(m, k) - 0.3) * 2) / 2
+    v = numpy.round((rs.rand(n, k) - 0.3) * 2) / 2
+    u[3] = 0
+    h, _ = make_handle(native, train)
+    h.set_factors(u, v)
+    cands = [rs.randint(0, n, size=300) for _ in range(m)]
+    check_eval(native, h, full, train, test, u, v, cands, 200)
+    check_eval(native, h, full, train, test, u, v, None, 64)
+    h.close()
+
+
+def test_fp32_mode_within_stated_tolerance(native):
+    full, train, test, u0, v0, cands = synthetic(300, 900, 50, 9000, seed=7)
+    h, csr = make_handle(native, train, precision=native.F32)
+    h.set_factors(u0, v0)
+    u, v = u0.copy(), v0.copy()
+    csc = oals.to_csr(train.T)
+    for _ in range(3):
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        oals.als_half_step(u, v, csr, 0.01)
+        oals.als_half_step(v, u, csc, 0.01)
+    du, dv = h.get_factors()
+    print("fp32 rel frob U %.2e V %.2e" % (rel_frob(du, u), rel_frob(dv, v)))
+    assert rel_frob(du, u) < F32_FROB and rel_frob(dv, v) < F32_FROB
+    assert abs(h.rmse() - oals.rmse_gram(u, v, csr)) < 1e-5
+    h.close()
+
+
+@pytest.mark.parametrize("k", [256, 300])
+def test_large_k_paths(native, k):
+    """k = 256 / 300: float64 tiles do not fit in shared memory (per-CTA scratch path); float32 do."""
+    full, train, test, u0, v0, cands = synthetic(40, 500, k, 3000, seed=k, empty=False)
+    csc = oals.to_csr(train.T)
+    u = oals.als_half_step(u0.copy(), v0, train, 0.01)
+    for precision, check in ((native.F64, lambda a: numpy.allclose(a, u, rtol=F64_RTOL, atol=1e-12)),
+                             (native.F32, lambda a: rel_frob(a, u) < F32_FROB)):
+        h, _ = make_handle(native, train, precision)
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        du, _ = h.get_factors()
+        assert check(du), rel_frob(du, u)
+        h.close()
+
+
+def test_errors_are_loud(native):
+    full, train, test, u0, v0, cands = synthetic(30, 90, 4, 300, seed=1)
+    h, _ = make_handle(native, train)
+    with pytest.raises(native.HyprecError):
+        h.als_half_step(native.SIDE_USER, 0.01)                    # no factors yet
+    h.set_factors(numpy.ones((30, 4)), numpy.zeros((90, 4)))
+    with pytest.raises(native.HyprecError) as err:                   # G = 0 and lambda = 0: singular
+        h.als_half_step(native.SIDE_USER, 0.0)
+    assert err.value.code == -5
+    bad = train.indices.copy()
+    bad[0] = 10 ** 6
+    with pytest.raises(native.HyprecError):
+        h.set_train_csr(30, 90, train.indptr, bad, train.data)
+    h.close()
+
+
+def test_sharded_half_steps_compose(native):
+    """Two handles solving complementary row ranges == one handle solving all rows (the multi-GPU
+    decomposition of SURVEY.md section 8e, exercised on one device)."""
+    full, train, test, u0, v0, cands = synthetic(90, 250, 12, 2000, seed=3)
+    whole, _ = make_handle(native, train)
+    whole.set_factors(u0, v0)
+    whole.als_half_step(native.SIDE_USER, 0.01)
+    want, _ = whole.get_factors()
+    parts = []
+    for lo, hi in ((0, 40), (40, 90)):
+        h, _ = make_handle(native, train)
+        h.set_shard(lo, hi, 0, 250)
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        got, _ = h.get_factors()
+        assert numpy.array_equal(got[:lo], u0[:lo]) and numpy.array_equal(got[hi:], u0[hi:])
+        parts.append(got[lo:hi])
+        h.close()
+    assert numpy.array_equal(numpy.vstack(parts), want)
+    whole.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# full citeulike-a shape: sampled oracle rows + size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_citeulike_a_shape_epoch_and_eval(native):
+    from hyprec_b200 import synth
+    full = synth.ratings_csr("citeulike-a")
+    m, n, k, cap = full.shape[0], full.shape[1], 200, 200
+    rs = numpy.random.RandomState(42)
+    keep = rs.rand(full.nnz) < 0.8
+    coo = full.tocoo()
+    train = oals.to_csr(sp.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=full.shape))
+    test = oals.to_csr(sp.csr_matrix((coo.data[~keep], (coo.row[~keep], coo.col[~keep])), shape=full.shape))
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    h, _ = make_handle(native, train)
+    h.set_factors(u0, v0)
+    h.als_half_step(native.SIDE_USER, 0.01)
+    du, _ = h.get_factors()
+    sample_u = rs.choice(m, 48, replace=False)
+    want_u = oals.als_half_step(u0.copy(), v0, train, 0.01, rows=sample_u)
+    assert numpy.allclose(du[sample_u], want_u[sample_u], rtol=F64_RTOL, atol=1e-12)
+    h.als_half_step(native.SIDE_ITEM, 0.01)
+    _, dv = h.get_factors()
+    sample_i = rs.choice(n, 48, replace=False)
+    want_v = oals.als_half_step(v0.copy(), du, oals.to_csr(train.T), 0.01, rows=sample_i)
+    assert numpy.allclose(dv[sample_i], want_v[sample_i], rtol=F64_RTOL, atol=1e-12)
+    assert numpy.all(numpy.isfinite(du)) and numpy.all(numpy.isfinite(dv))
+    assert abs(h.rmse() - oals.rmse_gram(du, dv, train)) < 1e-11
+
+    h.set_eval_csr((full.indptr, full.indices, full.data), (test.indptr, test.indices, test.data))
+    n_cand = n // 5
+    cands = numpy.stack([rs.permutation(n)[:n_cand] for _ in range(m)]).astype(numpy.int32)
+    cp = numpy.arange(m + 1, dtype=numpy.int64) * n_cand
+    out = h.eval_topk(cap, cp, cands.ravel(), n_train_nz=train.nnz, n_test_nz=test.nnz)
+    # properties that hold at any size
+    vals, idx = out["topk_val"], out["topk_idx"]
+    assert numpy.all(idx >= 0) and numpy.all(vals[:, :-1] >= vals[:, 1:])
+    assert numpy.all(out["ones_per_row"] >= 0) and numpy.all(out["ones_per_row"] <= n)
+    for uid in rs.choice(m, 24, replace=False):
+        scores = du[uid].dot(dv[cands[uid]].T)
+        want, want_vals = oev.top_recommendations_fast(cands[uid], scores, cap)
+        assert list(idx[uid]) == want
+        row = du[uid].dot(dv.T)
+        thr = oev.row_threshold(row)
+        assert abs(out["thresholds"][uid] - thr) <= 1e-12 * max(1.0, abs(thr))
+        # cells within a few ulps of the threshold may round differently (documented tie)
+        near = int(numpy.sum(numpy.abs(row - thr) <= 1e-12 * numpy.abs(thr)))
+        assert abs(int(out["ones_per_row"][uid]) - int(numpy.sum(row >= thr))) <= near
+    h.close()

@@ -1,0 +1,128 @@
+"""Host-side mirrors (Evaluator, TopRecommendations, ModelInitializer, metrics) against the golden
+outputs of the unmodified reference, plus the reference's own invariants
+(/root/reference/tests/evaluator_tests.py:42-100, top_recommendations_tests.py:18-46,
+util_tests.py:110-124)."""
+import numpy
+import pytest
+
+from conftest import golden_folds, load_golden, split_lists
+from hyprec_b200 import metrics
+from hyprec_b200.evaluator import Evaluator
+from hyprec_b200.model_initializer import ModelInitializer
+from hyprec_b200.top_recommendations import TopRecommendations, top_k_stream_order
+
+
+@pytest.mark.parametrize("name", ["als_kfold_4x30", "als_kfold_toy"])
+def test_kfold_split_is_bit_identical(als_cases, name):
+    g = als_cases[name]
+    ev = Evaluator(g["ratings"])
+    ev.set_kfolds(int(g["k_folds"]))
+    lists = ev.get_kfold_indices()
+    want = split_lists(g["kfold_ids"], g["kfold_len"])
+    assert len(lists) == len(want)
+    for a, b in zip(lists, want):
+        assert numpy.array_equal(numpy.asarray(a).astype(numpy.int64), b)
+    for f, fold in enumerate(golden_folds(g)):
+        train, test = ev.get_fold(f, lists)
+        assert numpy.array_equal(train, fold["train"])
+        assert numpy.array_equal(test, fold["test"])
+        indptr, ids = ev.candidate_lists(f)
+        assert numpy.array_equal(numpy.diff(indptr), fold["cand_len"])
+        assert numpy.array_equal(ids, fold["cand_ids"])
+
+
+def test_naive_split_is_bit_identical(als_cases):
+    g = als_cases["als_naive_toy"]
+    fold = golden_folds(g)[0]
+    ev = Evaluator(g["ratings"])
+    ev.set_kfolds(1)
+    train, test = ev.naive_split()
+    assert numpy.array_equal(train, fold["train"])
+    assert numpy.array_equal(test, fold["test"])
+    assert numpy.all(train * test == 0)
+    indptr, ids = ev.candidate_lists(0)
+    assert numpy.array_equal(ids, fold["cand_ids"])
+
+
+def test_kfold_invariants():
+    """evaluator_tests.py:50-74: folds are disjoint, cover every rating once, train/test disjoint."""
+    ratings = numpy.array([[int(not bool((a + u) % 3)) for a in range(18)] for u in range(10)])
+    ev = Evaluator(ratings)
+    ev.set_kfolds(3)
+    lists = ev.get_kfold_indices()
+    seen = numpy.zeros(ratings.shape)
+    for f in range(3):
+        train, test = ev.get_fold(f, lists)
+        assert numpy.all(train * test == 0)
+        assert numpy.array_equal(train + test, ratings)
+        seen += test
+    assert numpy.array_equal(seen, ratings)
+
+
+def test_rmse_matches_definition():
+    rs = numpy.random.RandomState(5)
+    a, b = rs.rand(7, 9), rs.rand(7, 9)
+    ev = Evaluator(b)
+    assert abs(ev.get_rmse(a, b) - numpy.sqrt(numpy.mean((a - b) ** 2))) < 1e-12
+    assert abs(ev.get_rmse(a) - numpy.sqrt(numpy.mean((a - b) ** 2))) < 1e-12
+
+
+def test_top_recommendations_golden_and_invariants():
+    g = load_golden("top_recommendations")
+    for c in range(int(g["n_cases"])):
+        cap, stream, want = int(g["c%d_cap" % c]), g["c%d_stream" % c], list(g["c%d_result" % c])
+        top = TopRecommendations(cap)
+        for idx, val in enumerate(stream):
+            top.insert(idx, float(val))
+        assert list(reversed(top.get_indices())) == want
+        vals = top.get_values()
+        assert all(vals[i] <= vals[i + 1] for i in range(len(vals) - 1))
+        assert top.get_recommendations_count() == min(cap, len(stream)) == len(top.get_indices())
+        assert top_k_stream_order(numpy.arange(len(stream)), stream, cap)[0] == want
+
+
+def test_metrics_golden():
+    g = load_golden("metrics")
+    ratings, expected = g["ratings"], g["expected"]
+    recs = [list(r) for r in split_lists(g["rec_ids"], g["rec_len"])]
+    ev = Evaluator(ratings)
+    ev.recs_loaded = True
+    ev.recommendation_indices = recs
+    hits = [ratings[u][numpy.asarray(r, dtype=int)] * expected[u][numpy.asarray(r, dtype=int)] for u, r in enumerate(recs)]
+    lengths = [len(r) for r in recs]
+    for n in (1, 4, 5):
+        assert ev.calculate_mrr(n, None, ratings, expected) == numpy.float16(g["mrr_%d" % n])
+        assert ev.calculate_ndcg(n, None, ratings, expected) == numpy.float16(g["ndcg_%d" % n])
+        assert metrics.mrr_at(n, hits, lengths) == numpy.float16(g["mrr_%d" % n])
+        assert metrics.ndcg_at(n, hits, lengths) == numpy.float16(g["ndcg_%d" % n])
+    assert ev.recall_at_x(3, None, ratings, expected) == numpy.float16(g["recall_3"])
+    assert metrics.recall_at_x(3, hits, ratings.sum(axis=1)) == numpy.float16(g["recall_3"])
+    # evaluator_tests.py:94-100: deleting top hits cannot raise MRR
+    before = ev.calculate_mrr(5, None, ratings, expected)
+    ev.recommendation_indices = [r[1:] for r in recs]
+    assert ev.calculate_mrr(5, None, ratings, expected) <= before
+
+
+def test_load_top_recommendations_matches_reference(als_cases):
+    g = als_cases["als_kfold_toy"]
+    ev = Evaluator(g["ratings"])
+    ev.set_kfolds(int(g["k_folds"]))
+    ev.get_kfold_indices()
+    for f, fold in enumerate(golden_folds(g)):
+        pred = fold["u"].dot(fold["v"].T)
+        recs = ev.load_top_recommendations(200, pred, fold["test"], f)
+        want = [list(w) for w in split_lists(fold["rec_ids"], fold["rec_len"])]
+        assert [list(r) for r in recs] == want
+
+
+def test_model_initializer_roundtrip(tmp_path):
+    """util_tests.py:110-124: file name and save/load equality."""
+    init = ModelInitializer({'n_factors': 3, '_lambda': 0.01}, 1, folder=str(tmp_path))
+    path = init._create_path('user_v', (10, 3), {'n_iterations': 1})
+    assert path.endswith('n_factors-3,n_iterations-1,n_rows-10user_v.dat')
+    matrix = numpy.random.RandomState(0).rand(10, 3)
+    init.save_matrix(matrix, 'user_v')
+    found, loaded = init.load_matrix({'n_factors': 3, '_lambda': 0.01}, 'user_v', (10, 3))
+    assert found and numpy.array_equal(loaded, matrix)
+    found, fresh = init.load_matrix({'n_factors': 3, '_lambda': 0.01}, 'missing', (4, 3))
+    assert not found and fresh.shape == (4, 3)

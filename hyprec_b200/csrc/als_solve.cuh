@@ -11,6 +11,11 @@
 // b = sum_{j in R_r} r_rj y_j (confidence is 1.0 on R_r and 0.1 elsewhere, and the rating is 0
 // outside R_r).  `base` holds 0.1 * Y^T Y + lambda * I, shared by all rows (gram.cuh).
 //
+// During the factorisation the first 8 rows of the gather staging buffer hold the current
+// panel (the 8 freshly solved columns of L for all rows below the diagonal tile) in the same
+// interleaved order as gathered factor rows, so the trailing update reads its operands with
+// broadcast / consecutive-word accesses exactly like the rank-1 accumulation.
+//
 // Layout: the (k+1) x (k+1) augmented matrix [A b; b^T .] is kept as 8x8 tiles of its lower
 // triangle, element (r, c) of tile t at [(r*8+c) * n_tiles + t] (common.cuh).  Carrying b as
 // row k makes the forward substitution part of the factorisation: after the last panel, row k
@@ -69,8 +74,8 @@ struct SolveArgs {
     int chunk_rows;
 };
 
-__device__ __forceinline__ double inv_sqrt(double x) { return 1.0 / sqrt(x); }
-__device__ __forceinline__ float inv_sqrt(float x) { return 1.0f / sqrtf(x); }
+__device__ __forceinline__ double inv_sqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ float inv_sqrt(float x) { return rsqrtf(x); }
 
 // Cholesky of the leading nvalid x nvalid block of an 8x8 tile held in registers (lower
 // triangle); the rows below it are carried along as in a panel factorisation (that is where the
@@ -113,13 +118,25 @@ __device__ __forceinline__ void chol8_invert(T (&a)[kTile][kTile], int nvalid) {
     }
 }
 
-// Factor diagonal tile `p` (block column p) in registers; if the right-hand-side row sits in
-// this tile (k not a multiple of 8 and p == k / 8) publish its z entries first.
+// Factor diagonal tile `p` (tile id `t` of the tiled matrix A) in place: Cholesky of its leading
+// block, then that block's inverse.  If the right-hand-side row sits in this tile (k not a
+// multiple of 8 and p == k / 8) its z entries are published first.  Runs in ONE thread; kept out
+// of line so that its register needs do not spill the callers' accumulator tiles.
+#ifndef HYPREC_EMU
 template <typename T>
-__device__ __forceinline__ void factor_diag_tile(T (&a)[kTile][kTile], int p, int k, T* zvec) {
+__device__ __noinline__ void factor_diag_tile(T* A, int NT, int t, int p, int k, T* zvec) {
+#else
+template <typename T>
+void factor_diag_tile(T* A, int NT, int t, int p, int k, T* zvec) {
+#endif
     int nvalid = k - p * kTile;
     if (nvalid > kTile) nvalid = kTile;
     if (nvalid <= 0) return;
+    T a[kTile][kTile];
+#pragma unroll
+    for (int r = 0; r < kTile; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = A[(size_t)(r * kTile + c) * NT + t];
     chol8_factor(a, nvalid);
     if (nvalid < kTile) {
 #pragma unroll
@@ -130,6 +147,10 @@ __device__ __forceinline__ void factor_diag_tile(T (&a)[kTile][kTile], int p, in
             }
     }
     chol8_invert(a, nvalid);
+#pragma unroll
+    for (int r = 0; r < kTile; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) A[(size_t)(r * kTile + c) * NT + t] = a[r][c];
 }
 
 template <typename T>
@@ -192,6 +213,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
             }
             __syncthreads();
             const bool last = (ch == nchunks - 1);
+#pragma unroll 1
             for (int q = tid; q < NT; q += kSolveThreads) {
                 const int bi = tmap[2 * q], bj = tmap[2 * q + 1];
                 T acc[kTile][kTile];
@@ -206,6 +228,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
 #pragma unroll
                         for (int c = 0; c < kTile; ++c) acc[r][c] = A[(size_t)(r * kTile + c) * NT + q];
                 }
+#pragma unroll 2
                 for (int t = 0; t < cr; ++t) {
                     const T* yrow = ybuf + (size_t)t * kpad;
                     T vi[kTile], vj[kTile];
@@ -238,12 +261,12 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                             acc[r][c] = v;
                         }
                     }
-                    if (q == 0) factor_diag_tile(acc, 0, k, zvec);
                 }
 #pragma unroll
                 for (int r = 0; r < kTile; ++r)
 #pragma unroll
                     for (int c = 0; c < kTile; ++c) A[(size_t)(r * kTile + c) * NT + q] = acc[r][c];
+                if (last && q == 0) factor_diag_tile(A, NT, 0, 0, k, zvec);
             }
             __syncthreads();
         }
@@ -267,7 +290,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                     y[c] = s;
                 }
 #pragma unroll
-                for (int c = 0; c < kTile; ++c) A[(size_t)(r * kTile + c) * NT + t] = y[c];
+                for (int c = 0; c < kTile; ++c) {
+                    A[(size_t)(r * kTile + c) * NT + t] = y[c];
+                    ybuf[(size_t)c * kpad + r * nb + i / kTile] = y[c];   // panel, row 8*b+r at [r*nb+b]
+                }
                 if (i == k) {
 #pragma unroll
                     for (int c = 0; c < kTile; ++c) zvec[pnl * kTile + c] = y[c];
@@ -277,31 +303,33 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
             // trailing update; the owner of the next diagonal tile factors it straight away
             const int ntr = nb - 1 - pnl;
             const int ntiles = tri(ntr);
+#pragma unroll 1
             for (int q = tid; q < ntiles; q += kSolveThreads) {
                 const int bi = pnl + 1 + tmap[2 * q], bj = pnl + 1 + tmap[2 * q + 1];
-                const int t = tile_id(bi, bj), ti = tile_id(bi, pnl), tj = tile_id(bj, pnl);
+                const int t = tile_id(bi, bj);
                 T acc[kTile][kTile];
 #pragma unroll
                 for (int r = 0; r < kTile; ++r)
 #pragma unroll
                     for (int c = 0; c < kTile; ++c) acc[r][c] = A[(size_t)(r * kTile + c) * NT + t];
-#pragma unroll
+#pragma unroll 2
                 for (int kk = 0; kk < kTile; ++kk) {
+                    const T* prow = ybuf + (size_t)kk * kpad;
                     T li[kTile], lj[kTile];
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r) li[r] = A[(size_t)(r * kTile + kk) * NT + ti];
+                    for (int r = 0; r < kTile; ++r) li[r] = prow[r * nb + bi];
 #pragma unroll
-                    for (int c = 0; c < kTile; ++c) lj[c] = A[(size_t)(c * kTile + kk) * NT + tj];
+                    for (int c = 0; c < kTile; ++c) lj[c] = prow[c * nb + bj];
 #pragma unroll
                     for (int r = 0; r < kTile; ++r)
 #pragma unroll
                         for (int c = 0; c < kTile; ++c) acc[r][c] -= li[r] * lj[c];
                 }
-                if (q == 0) factor_diag_tile(acc, pnl + 1, k, zvec);
 #pragma unroll
                 for (int r = 0; r < kTile; ++r)
 #pragma unroll
                     for (int c = 0; c < kTile; ++c) A[(size_t)(r * kTile + c) * NT + t] = acc[r][c];
+                if (q == 0) factor_diag_tile(A, NT, t, pnl + 1, k, zvec);
             }
             __syncthreads();
         }

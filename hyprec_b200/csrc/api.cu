@@ -378,7 +378,7 @@ struct Engine : EngineBase {
         // shared-memory plan: tiles in shared memory when they fit, else per-CTA global scratch
         int chunk = 32;
         hyprec::SolveLayout lay = hyprec::solve_layout(k, chunk, true, sizeof(T));
-        while (lay.total > (size_t)h->max_smem && chunk > 4) {
+        while (lay.total > (size_t)h->max_smem && chunk > 8) {
             chunk /= 2;
             lay = hyprec::solve_layout(k, chunk, true, sizeof(T));
         }
@@ -502,7 +502,7 @@ struct Engine : EngineBase {
         const bool want_topk = tidx || tval || thit;
         if (want_topk && (cap <= 0 || cap > 4096)) return fail(HYPREC_E_UNSUPPORTED, "capacity must be in [1, 4096]");
         if (ci && !cp) return fail(HYPREC_E_INVALID, "eval_topk: candidate ids without indptr");
-        if ((trf || tef || thit) && full.rows != m) return fail(HYPREC_E_INVALID, "eval_topk: set_eval_csr first");
+        if (tef && test.rows != m) return fail(HYPREC_E_INVALID, "eval_topk: test flags need set_eval_csr first");
 
         // thresholds for every user (cheap), float64
         HY_TRY(compute_colsum_v());

@@ -28,7 +28,7 @@ def emu():
     return ctypes.CDLL(mod.build())
 
 
-def half_step(emu, csr, fixed, latent, lam, prior=None, chunk=4, grid=2, smem=1, lo=0, hi=None, f32=False):
+def half_step(emu, csr, fixed, latent, lam, prior=None, chunk=8, grid=2, smem=1, lo=0, hi=None, f32=False):
     dt = numpy.float32 if f32 else numpy.float64
     out = numpy.ascontiguousarray(latent, dtype=dt).copy()
     fixed = numpy.ascontiguousarray(fixed, dtype=dt)
@@ -52,7 +52,7 @@ def test_solve_kernel_all_paddings(emu, k):
     train[2, :] = 0
     u0, v0 = rs.rand(m, k), rs.rand(n, k)
     want = oals.als_half_step(u0.copy(), v0, oals.to_csr(train), 0.01)
-    got, status = half_step(emu, oals.to_csr(train), v0, u0, 0.01, chunk=4, grid=3)
+    got, status = half_step(emu, oals.to_csr(train), v0, u0, 0.01, chunk=8, grid=3)
     assert status == 0
     assert numpy.allclose(got, want, rtol=1e-10, atol=1e-12)
     assert numpy.all(got[2] == 0)          # empty row -> exact zeros (App. A Q10)
@@ -80,7 +80,7 @@ def test_solve_kernel_shard_scratch_and_f32(emu):
     got, _ = half_step(emu, oals.to_csr(train), v0, u0, 0.05, chunk=16, grid=2, smem=0, lo=3, hi=7)
     assert numpy.allclose(got[3:7], want[3:7], rtol=1e-10, atol=1e-12)
     assert numpy.array_equal(got[:3], u0[:3]) and numpy.array_equal(got[7:], u0[7:])   # outside the shard
-    got32, _ = half_step(emu, oals.to_csr(train), v0, u0, 0.05, chunk=4, grid=2, f32=True)
+    got32, _ = half_step(emu, oals.to_csr(train), v0, u0, 0.05, chunk=8, grid=2, f32=True)
     assert numpy.allclose(got32, want, rtol=2e-3, atol=2e-4)
 
 

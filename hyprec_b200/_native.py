@@ -16,7 +16,7 @@ T_GRAM, T_SOLVE, T_RMSE, T_SWEEP, T_TOPK, T_FLAGS, T_COUNT = range(7)
 EXPORTS = [
     "hyprec_create", "hyprec_destroy", "hyprec_last_error", "hyprec_abi_version", "hyprec_launch_count",
     "hyprec_set_train_csr", "hyprec_set_shard", "hyprec_set_factors", "hyprec_get_factors",
-    "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_train",
+    "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_rmse_terms", "hyprec_train",
     "hyprec_predict_dense", "hyprec_set_eval_csr", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
     "hyprec_flush_l2", "hyprec_probe_fma_tflops",
 ]
@@ -62,6 +62,7 @@ def load_library(rebuild=False):
     lib.hyprec_set_item_prior.argtypes = [vp, vp]
     lib.hyprec_als_half_step.argtypes = [vp, c_int, c_dbl]
     lib.hyprec_rmse.argtypes = [vp, ctypes.POINTER(c_dbl)]
+    lib.hyprec_rmse_terms.argtypes = [vp, ctypes.POINTER(c_dbl)]
     lib.hyprec_train.argtypes = [vp, c_int, c_dbl, c_dbl, EPOCH_CB, vp, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]
     lib.hyprec_predict_dense.argtypes = [vp, vp]
     lib.hyprec_set_eval_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -166,6 +167,12 @@ class Handle(object):
         out = ctypes.c_double()
         self._check(self._lib.hyprec_rmse(self._h, ctypes.byref(out)))
         return out.value
+
+    def rmse_terms(self):
+        """(<U^T U, V^T V>, sum_nz r u.v, sum_nz r^2); sparse sums over this handle's user shard."""
+        out = (ctypes.c_double * 3)()
+        self._check(self._lib.hyprec_rmse_terms(self._h, out))
+        return out[0], out[1], out[2]
 
     def train(self, n_iter, lam, start_error=numpy.inf, callback=None):
         """Returns (epochs_run, last_rmse); callback(epoch, rmse, seconds)."""

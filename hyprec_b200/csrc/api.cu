@@ -82,6 +82,7 @@ struct EngineBase {
     virtual int set_prior(const double* theta) = 0;
     virtual int half_step(int side, double lambda) = 0;
     virtual int rmse(double* out) = 0;
+    virtual int rmse_terms(double* out3, bool shard_only) = 0;
     virtual int predict_dense(double* out) = 0;
     virtual int eval_topk(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci, int cap, double* thr,
                           int64_t* ones, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) = 0;
@@ -430,29 +431,44 @@ struct Engine : EngineBase {
     }
 
     // ---------------------------------------------------------------- RMSE
-    int rmse(double* out) override {
+    // out3 = { <U^T U, V^T V>_F, sum_nz r (u.v), sum_nz r^2 }; the two sparse sums cover the
+    // handle's user shard only when shard_only (the caller all-reduces them across ranks).
+    int rmse_terms(double* out3, bool shard_only) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "rmse before set_factors");
+        int64_t lo = 0, hi = m;
+        if (shard_only && h->user_hi >= 0) { lo = h->user_lo; hi = h->user_hi; }
         HY_TRY(compute_gram(0));
         HY_TRY(compute_gram(1));
         HY_TRY(row_s1.reserve(sizeof(double) * m));
         HY_TRY(row_s2.reserve(sizeof(double) * m));
         HY_TRY(scalars.reserve(sizeof(double) * 4));
+        CU_TRY(cudaMemsetAsync(scalars.ptr, 0, sizeof(double) * 4, h->stream));
         {
             Timer t(h, HYPREC_T_RMSE);
             hyprec::frob_inner_kernel<T><<<1, 256, 0, h->stream>>>(gram[0].as<T>(), gram[1].as<T>(), k * k,
                                                                      scalars.as<double>());
-            const int wpb = 8;
-            hyprec::sddmm_row_kernel<T><<<(unsigned)((m + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
-                csr.indptr.template as<int64_t>(), csr.indices.template as<int32_t>(), csr.values.template as<T>(),
-                U.as<T>(), V.as<T>(), k, m, row_s1.as<double>(), row_s2.as<double>());
-            hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s1.as<double>(), m, scalars.as<double>() + 1);
-            hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s2.as<double>(), m, scalars.as<double>() + 2);
-            h->launches += 4;
+            h->launches += 1;
+            if (hi > lo) {
+                const int wpb = 8;
+                const int64_t rows = hi - lo;
+                hyprec::sddmm_row_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
+                    csr.indptr.template as<int64_t>() + lo, csr.indices.template as<int32_t>(),
+                    csr.values.template as<T>(), U.as<T>() + lo * k, V.as<T>(), k, rows, row_s1.as<double>(),
+                    row_s2.as<double>());
+                hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s1.as<double>(), rows, scalars.as<double>() + 1);
+                hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s2.as<double>(), rows, scalars.as<double>() + 2);
+                h->launches += 3;
+            }
         }
         CU_TRY(cudaGetLastError());
-        double s[3];
-        CU_TRY(cudaMemcpyAsync(s, scalars.ptr, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaMemcpyAsync(out3, scalars.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
+        return HYPREC_OK;
+    }
+
+    int rmse(double* out) override {
+        double s[3];
+        HY_TRY(rmse_terms(s, false));
         double rss = s[0] - 2.0 * s[1] + s[2];
         if (rss < 0.0) rss = 0.0;
         *out = sqrt(rss / ((double)m * (double)n));
@@ -774,6 +790,12 @@ int hyprec_rmse(hyprec_t* h, double* out) {
     HY_TRY(check(h));
     if (!out) return fail(HYPREC_E_INVALID, "hyprec_rmse: null output");
     return h->engine->rmse(out);
+}
+
+int hyprec_rmse_terms(hyprec_t* h, double* out3) {
+    HY_TRY(check(h));
+    if (!out3) return fail(HYPREC_E_INVALID, "hyprec_rmse_terms: null output");
+    return h->engine->rmse_terms(out3, true);
 }
 
 int hyprec_train(hyprec_t* h, int n_iter, double lambda, double start_error, hyprec_epoch_cb cb, void* user,

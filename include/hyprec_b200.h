@@ -84,6 +84,11 @@ int hyprec_als_half_step(hyprec_t* h, int side, double lambda);
  * collaborative_filtering.py:247) without forming U.V^T; float64 accumulation in every mode. */
 int hyprec_rmse(hyprec_t* h, double* out);
 
+/* The three sums the RMSE is made of, for sharded runs: out3 = { <U^T U, V^T V>_F,
+ * sum_nz r (u.v), sum_nz r^2 } where the two sparse sums cover only the handle's user shard.
+ * rmse = sqrt((out3[0] - 2 * SUM_ranks out3[1] + SUM_ranks out3[2]) / (n_users * n_items)). */
+int hyprec_rmse_terms(hyprec_t* h, double* out3);
+
 /* partial_train() (collaborative_filtering.py:224-259): epochs of user half-step, item
  * half-step, RMSE; stops after the epoch whose error >= the previous one (:256).
  * start_error is the initial `error` (inf, or the epoch-0 RMSE when verbose, :228-234).

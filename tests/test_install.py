@@ -1,0 +1,29 @@
+"""hyprec_b200.install() rebinds the reference's class names (only where /root/reference exists:
+the build container; skipped on the GPU box)."""
+import pytest
+
+from oracle import reference_loader
+
+
+@pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not present")
+def test_install_rebinds_reference_modules():
+    import sys
+    ref = reference_loader.load_reference(heavy=True)
+    import hyprec_b200
+    original = sys.modules["lib.collaborative_filtering"].CollaborativeFiltering
+    try:
+        patched = hyprec_b200.install()
+        assert "lib.collaborative_filtering" in patched and "lib.recommender_system" in patched
+        assert sys.modules["lib.recommender_system"].CollaborativeFiltering is hyprec_b200.CollaborativeFiltering
+        # same constructor surface as the reference class (collaborative_filtering.py:18-20)
+        import inspect
+        assert list(inspect.signature(original.__init__).parameters) == \
+            list(inspect.signature(hyprec_b200.CollaborativeFiltering.__init__).parameters)
+        for name in ("train", "train_k_fold", "train_one_fold", "partial_train", "als_step", "get_predictions",
+                     "predict", "set_hyperparameters", "set_options", "set_data", "get_evaluation_report",
+                     "rounded_predictions", "recommend_items", "dump_recommendations", "get_ratings",
+                     "build_confidence_matrix", "set_item_based_recommender", "_get_options_suffix"):
+            assert callable(getattr(hyprec_b200.CollaborativeFiltering, name)), name
+    finally:
+        for name in ("lib.collaborative_filtering", "lib.recommender_system"):
+            sys.modules[name].CollaborativeFiltering = original

@@ -11,7 +11,7 @@ from hyprec_b200 import build as _build
 
 F64, F32 = 0, 1
 SIDE_USER, SIDE_ITEM = 0, 1
-T_GRAM, T_SOLVE, T_RMSE, T_SWEEP, T_TOPK, T_FLAGS, T_COUNT = range(7)
+T_GRAM, T_SOLVE, T_RMSE, T_SWEEP, T_TOPK, T_FLAGS, T_COUNT, T_PREP = range(8)
 
 EXPORTS = [
     "hyprec_create", "hyprec_destroy", "hyprec_last_error", "hyprec_abi_version", "hyprec_launch_count",

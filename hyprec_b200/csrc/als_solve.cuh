@@ -23,6 +23,17 @@
 // the panel solve and the back substitution are small mat-vecs instead of dependent chains.
 //
 // One CTA = one row at a time; CTAs pull rows from an atomic counter (rows differ in degree).
+//
+// Low-rank mode (rows with deg << k).  With B = 0.1 G + lambda I = L L^T and the whitened factors
+// Q = Y L^-T, the same normal matrix is A = L (I_k + 0.9 Q_r^T Q_r) L^T (Q_r = the deg gathered
+// rows of Q), and by the Woodbury identity
+//     x = L^-T y,   y = Q_r^T S^-1 (r - 0.9 Q_r p) + p,   S = I_deg + 0.9 Q_r Q_r^T,   p = lambda L^-1 theta_r
+// (`prior` then holds the rows of theta L^-T; lambda is applied here)
+// so only a deg x deg SPD system is factorised.  The kernel below is reused as is: the system
+// dimension becomes deg, the rank-1 vectors are the k columns of Q_r, the base matrix is the
+// identity, the right-hand side is r - 0.9 Q_r p, and the epilogue forms y; the caller turns the
+// y rows into x with one small GEMM against L^-1.  Mathematically identical to the direct path,
+// ~k/deg times fewer serial factorisation steps.
 #pragma once
 #include "common.cuh"
 
@@ -31,25 +42,32 @@ namespace hyprec {
 constexpr int kSolveThreads = 256;
 
 struct SolveLayout {
-    int nb, n_tiles, kpad, chunk_rows;
-    size_t off_a, off_y, off_z, off_x, off_map, total;
+    int nb, n_tiles, kpad, ystride, chunk_rows;
+    size_t off_a, off_y, off_z, off_x, off_idx, off_map, total;
 };
 
-HYPREC_HD SolveLayout solve_layout(int k, int chunk_rows, bool a_in_smem, size_t elem) {
+// Shared-memory plan for systems of dimension <= max_dim (k in direct mode, the largest row
+// degree of the launch in low-rank mode).  chunk_rows (>= 8: the buffer doubles as the panel
+// buffer) rank-1 vectors are staged at a time; rows of the staging buffer are ystride apart
+// (odd, so the low-rank gather's column-wise stores spread over banks).
+HYPREC_HD SolveLayout solve_layout(int max_dim, int chunk_rows, bool a_in_smem, size_t elem) {
     SolveLayout l;
-    l.nb = aug_blocks(k);
+    l.nb = aug_blocks(max_dim);
     l.n_tiles = tri(l.nb);
     l.kpad = l.nb * kTile;
+    l.ystride = l.kpad + 1;
     l.chunk_rows = chunk_rows;
     size_t o = 0;
     l.off_a = o;
     if (a_in_smem) o += elem * (size_t)kTileElems * l.n_tiles;
     l.off_y = o;
-    o += elem * (size_t)chunk_rows * l.kpad;
+    o += elem * (size_t)chunk_rows * l.ystride;
     l.off_z = o;
     o += elem * (size_t)l.kpad;
     l.off_x = o;
     o += elem * (size_t)l.kpad;
+    l.off_idx = (o + 7) & ~(size_t)7;
+    o = l.off_idx + 4 * (size_t)l.kpad;
     l.off_map = o;
     o += 2 * (size_t)l.n_tiles;
     l.total = (o + 15) & ~(size_t)15;
@@ -72,7 +90,24 @@ struct SolveArgs {
     int k;
     int64_t row_lo, row_hi;
     int chunk_rows;
+    // ---- work list / modes --------------------------------------------------------------------
+    const int32_t* row_list;  // optional: row ids to process instead of [row_lo, row_hi)
+    int64_t n_list;
+    int max_dim;              // system dimension the shared-memory layout is sized for
+    int lowrank;              // 0: direct k x k systems; 1: deg x deg systems on whitened factors
+    T* ymat;                  // low-rank output [n_rows][k]
+    T* export_tiles;          // direct mode: factored tiles of the processed row (single-row launch)
 };
+
+// float64 dot product of two k-vectors by one warp (lane-strided partial sums, xor-shuffle tree)
+template <typename TA, typename TB>
+__device__ __forceinline__ double warp_dot_t(const TA* __restrict__ a, const TB* __restrict__ b, int k, int lane) {
+    double s = 0.0;
+    for (int l = lane; l < k; l += 32) s += (double)a[l] * (double)b[l];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    return s;
+}
 
 __device__ __forceinline__ double inv_sqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ float inv_sqrt(float x) { return rsqrtf(x); }
@@ -157,20 +192,22 @@ template <typename T>
 __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveArgs<T> p) {
     HYPREC_DYN_SMEM(smem_raw);
     __shared__ long long s_row;
-    const int tid = threadIdx.x;
-    const int lane = tid % 32, warp = tid / 32;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid % 32, warp = tid / 32, nwarps = nthreads / 32;
     const int k = p.k;
-    const SolveLayout lay = solve_layout(k, p.chunk_rows, p.a_scratch == nullptr, sizeof(T));
-    const int nb = lay.nb, NT = lay.n_tiles, kpad = lay.kpad, CH = lay.chunk_rows;
-    T* A = p.a_scratch ? p.a_scratch + (size_t)blockIdx.x * kTileElems * NT : (T*)(smem_raw + lay.off_a);
+    const bool lowrank = p.lowrank != 0;
+    const SolveLayout lay = solve_layout(p.max_dim, p.chunk_rows, p.a_scratch == nullptr, sizeof(T));
+    const int CH = lay.chunk_rows, ystride = lay.ystride;
+    T* A = p.a_scratch ? p.a_scratch + (size_t)blockIdx.x * kTileElems * lay.n_tiles : (T*)(smem_raw + lay.off_a);
     T* ybuf = (T*)(smem_raw + lay.off_y);
     T* zvec = (T*)(smem_raw + lay.off_z);
     T* xvec = (T*)(smem_raw + lay.off_x);
+    int* idxs = (int*)(smem_raw + lay.off_idx);
     unsigned char* tmap = smem_raw + lay.off_map;
-    const int nbk = (k + kTile - 1) / kTile;   // block columns that hold factor columns
     const T pos_scale = T(kConfPos - kConfNeg);
+    const int64_t n_work = p.row_list ? p.n_list : p.row_hi - p.row_lo;
 
-    for (int t = tid; t < NT; t += kSolveThreads) {
+    for (int t = tid; t < lay.n_tiles; t += nthreads) {
         int bi, bj;
         tri_coords(t, &bi, &bj);
         tmap[2 * t] = (unsigned char)bi;
@@ -178,43 +215,78 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
     }
 
     while (true) {
-        __syncthreads();   // previous row finished with A / zvec / xvec / s_row; tmap visible
-        if (tid == 0) s_row = p.row_lo + (long long)atomicAdd(p.work_counter, 1);
+        __syncthreads();   // previous row finished with A / zvec / xvec / idxs / s_row; tmap visible
+        if (tid == 0) s_row = (long long)atomicAdd(p.work_counter, 1);
         __syncthreads();
-        const int64_t row = s_row;
-        if (row >= p.row_hi) break;
+        if (s_row >= n_work) break;
+        const int64_t row = p.row_list ? (int64_t)p.row_list[s_row] : p.row_lo + s_row;
         const int64_t lo = p.indptr[row];
         const int deg = (int)(p.indptr[row + 1] - lo);
-        T* out = p.latent + row * k;
-        if (deg == 0 && p.prior == nullptr) {
-            // b == 0 => the solve returns exactly 0
-            for (int c = tid; c < k; c += kSolveThreads) out[c] = T(0);
+        T* out = lowrank ? p.ymat + row * k : p.latent + row * k;
+        const T* prior_row = p.prior ? p.prior + row * k : nullptr;
+        if (deg == 0 && (lowrank || (p.prior == nullptr && p.export_tiles == nullptr))) {
+            // direct: b == 0 => the solve returns exactly 0; low-rank: y = p
+            for (int c = tid; c < k; c += nthreads) out[c] = (lowrank && prior_row) ? p.lambda * prior_row[c] : T(0);
             continue;
         }
+        // dimension of this row's system, number of rank-1 vectors that build it
+        const int dim = lowrank ? deg : k;
+        const int nvec = lowrank ? k : deg;
+        const int nb = aug_blocks(dim), NT = tri(nb), kpad = nb * kTile;
+        const int nbk = (dim + kTile - 1) / kTile;   // block columns that hold system columns
 
-        // ---- gather + rank-1 accumulation, CH gathered rows at a time ------------------------
-        const int nchunks = deg == 0 ? 1 : (deg + CH - 1) / CH;
+        if (lowrank) {
+            // positives' ids; right-hand side r - 0.9 * Q_r p kept in xvec until the finalize step
+            for (int i = tid; i < dim; i += nthreads) idxs[i] = p.indices[lo + i];
+            __syncthreads();
+            for (int i = warp; i < dim; i += nwarps) {
+                T v = p.values[lo + i];
+                if (prior_row) {
+                    const double d = warp_dot_t(p.fixed + (int64_t)idxs[i] * k, prior_row, k, lane);
+                    v -= pos_scale * p.lambda * (T)d;
+                }
+                if (lane == 0) xvec[i] = v;
+            }
+        }
+
+        // ---- gather + rank-1 accumulation, CH vectors at a time --------------------------------
+        const int nchunks = nvec == 0 ? 1 : (nvec + CH - 1) / CH;
         for (int ch = 0; ch < nchunks; ++ch) {
             const int c0 = ch * CH;
-            int cr = deg - c0;
+            int cr = nvec - c0;
             if (cr > CH) cr = CH;
-            // one warp per gathered row: coalesced read of the factor row, stored with column
-            // 8*b+c at [c * nb + b] so tile owners read consecutive words
-            for (int t = warp; t < cr; t += kSolveThreads / 32) {
-                const int64_t src = (int64_t)p.indices[lo + c0 + t] * k;
-                const T rating = p.values[lo + c0 + t];
-                T* dst = ybuf + (size_t)t * kpad;
-                for (int col = lane; col < kpad; col += 32) {
-                    T v = T(0);
-                    if (col < k) v = p.fixed[src + col];
-                    else if (col == k) v = rating;
-                    dst[(col % kTile) * nb + col / kTile] = v;
+            if (!lowrank) {
+                // one warp per gathered row: coalesced read of the factor row, stored with
+                // column 8*b+c at [c * nb + b] so tile owners read consecutive words
+                for (int t = warp; t < cr; t += nwarps) {
+                    const int64_t src = (int64_t)p.indices[lo + c0 + t] * k;
+                    const T rating = p.values[lo + c0 + t];
+                    T* dst = ybuf + (size_t)t * ystride;
+                    for (int col = lane; col < kpad; col += 32) {
+                        T v = T(0);
+                        if (col < k) v = p.fixed[src + col];
+                        else if (col == k) v = rating;
+                        dst[(col % kTile) * nb + col / kTile] = v;
+                    }
+                }
+            } else {
+                // vector t = column c0+t of Q restricted to this row's positives: one warp per
+                // positive reads cr consecutive values of its Q row
+                for (int i = warp; i < dim; i += nwarps) {
+                    const T* src = p.fixed + (int64_t)idxs[i] * k + c0;
+                    const int pos = (i % kTile) * nb + i / kTile;
+                    for (int t = lane; t < cr; t += 32) ybuf[(size_t)t * ystride + pos] = src[t];
+                }
+                const int npad = kpad - dim;   // augmented slot + padding carry zeros
+                for (int e = tid; e < cr * npad; e += nthreads) {
+                    const int t = e / npad, i = dim + e % npad;
+                    ybuf[(size_t)t * ystride + (i % kTile) * nb + i / kTile] = T(0);
                 }
             }
             __syncthreads();
             const bool last = (ch == nchunks - 1);
 #pragma unroll 1
-            for (int q = tid; q < NT; q += kSolveThreads) {
+            for (int q = tid; q < NT; q += nthreads) {
                 const int bi = tmap[2 * q], bj = tmap[2 * q + 1];
                 T acc[kTile][kTile];
                 if (ch == 0) {
@@ -230,7 +302,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                 }
 #pragma unroll 2
                 for (int t = 0; t < cr; ++t) {
-                    const T* yrow = ybuf + (size_t)t * kpad;
+                    const T* yrow = ybuf + (size_t)t * ystride;
                     T vi[kTile], vj[kTile];
 #pragma unroll
                     for (int r = 0; r < kTile; ++r) vi[r] = yrow[r * nb + bi];
@@ -242,7 +314,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                         for (int c = 0; c < kTile; ++c) acc[r][c] += vi[r] * vj[c];
                 }
                 if (last) {
-                    // A = base + 0.9 * sum y y^T on factor rows; the rhs row keeps sum r y
+                    // direct:   A = base + 0.9 * sum y y^T, rhs row = sum r y (+ lambda theta)
+                    // low-rank: S = I + 0.9 * Q_r Q_r^T,    rhs row = r - 0.9 Q_r p
 #pragma unroll
                     for (int r = 0; r < kTile; ++r) {
                         const int i = bi * kTile + r;
@@ -250,11 +323,17 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                         for (int c = 0; c < kTile; ++c) {
                             const int j = bj * kTile + c;
                             T v;
-                            if (i < k) {
-                                v = p.base[(size_t)(r * kTile + c) * NT + q] + pos_scale * acc[r][c];
-                            } else if (i == k) {
-                                v = acc[r][c];
-                                if (p.prior != nullptr && j < k) v += p.lambda * p.prior[row * k + j];
+                            if (i < dim) {
+                                const T base = lowrank ? (i == j ? T(1) : T(0))
+                                                       : p.base[(size_t)(r * kTile + c) * NT + q];
+                                v = base + pos_scale * acc[r][c];
+                            } else if (i == dim) {
+                                if (lowrank) {
+                                    v = j < dim ? xvec[j] : T(0);
+                                } else {
+                                    v = acc[r][c];
+                                    if (prior_row != nullptr && j < k) v += p.lambda * prior_row[j];
+                                }
                             } else {
                                 v = T(0);
                             }
@@ -266,17 +345,17 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                 for (int r = 0; r < kTile; ++r)
 #pragma unroll
                     for (int c = 0; c < kTile; ++c) A[(size_t)(r * kTile + c) * NT + q] = acc[r][c];
-                if (last && q == 0) factor_diag_tile(A, NT, 0, 0, k, zvec);
+                if (last && q == 0) factor_diag_tile(A, NT, 0, 0, dim, zvec);
             }
             __syncthreads();
         }
 
         // ---- right-looking blocked Cholesky, 8-column panels ---------------------------------
         for (int pnl = 0; pnl < nbk; ++pnl) {
-            // panel solve: rows below the diagonal tile (factor rows and the rhs row k) times
+            // panel solve: rows below the diagonal tile (system rows and the rhs row `dim`) times
             // the transposed inverse of the diagonal tile's factor
             const int tdiag = tile_id(pnl, pnl);
-            for (int i = kTile * (pnl + 1) + tid; i <= k; i += kSolveThreads) {
+            for (int i = kTile * (pnl + 1) + tid; i <= dim; i += nthreads) {
                 const int r = i % kTile;
                 const int t = tile_id(i / kTile, pnl);
                 T x[kTile], y[kTile];
@@ -292,9 +371,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
 #pragma unroll
                 for (int c = 0; c < kTile; ++c) {
                     A[(size_t)(r * kTile + c) * NT + t] = y[c];
-                    ybuf[(size_t)c * kpad + r * nb + i / kTile] = y[c];   // panel, row 8*b+r at [r*nb+b]
+                    ybuf[(size_t)c * ystride + r * nb + i / kTile] = y[c];   // panel, row 8*b+r at [r*nb+b]
                 }
-                if (i == k) {
+                if (i == dim) {
 #pragma unroll
                     for (int c = 0; c < kTile; ++c) zvec[pnl * kTile + c] = y[c];
                 }
@@ -304,7 +383,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
             const int ntr = nb - 1 - pnl;
             const int ntiles = tri(ntr);
 #pragma unroll 1
-            for (int q = tid; q < ntiles; q += kSolveThreads) {
+            for (int q = tid; q < ntiles; q += nthreads) {
                 const int bi = pnl + 1 + tmap[2 * q], bj = pnl + 1 + tmap[2 * q + 1];
                 const int t = tile_id(bi, bj);
                 T acc[kTile][kTile];
@@ -314,7 +393,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                     for (int c = 0; c < kTile; ++c) acc[r][c] = A[(size_t)(r * kTile + c) * NT + t];
 #pragma unroll 2
                 for (int kk = 0; kk < kTile; ++kk) {
-                    const T* prow = ybuf + (size_t)kk * kpad;
+                    const T* prow = ybuf + (size_t)kk * ystride;
                     T li[kTile], lj[kTile];
 #pragma unroll
                     for (int r = 0; r < kTile; ++r) li[r] = prow[r * nb + bi];
@@ -329,14 +408,18 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                 for (int r = 0; r < kTile; ++r)
 #pragma unroll
                     for (int c = 0; c < kTile; ++c) A[(size_t)(r * kTile + c) * NT + t] = acc[r][c];
-                if (q == 0) factor_diag_tile(A, NT, t, pnl + 1, k, zvec);
+                if (q == 0) factor_diag_tile(A, NT, t, pnl + 1, dim, zvec);
             }
             __syncthreads();
         }
 
+        if (!lowrank && p.export_tiles != nullptr) {
+            for (int e = tid; e < kTileElems * NT; e += nthreads) p.export_tiles[e] = A[e];
+        }
+
         // ---- back substitution L^T x = z, one block column at a time -------------------------
         for (int bj = nbk - 1; bj >= 0; --bj) {
-            int nv = k - kTile * bj;
+            int nv = dim - kTile * bj;
             if (nv > kTile) nv = kTile;
             const int td = tile_id(bj, bj);
             if (tid < nv) {
@@ -345,7 +428,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                 xvec[kTile * bj + tid] = s;
             }
             __syncthreads();
-            for (int jp = tid; jp < kTile * bj; jp += kSolveThreads) {
+            for (int jp = tid; jp < kTile * bj; jp += nthreads) {
                 const int t = tile_id(bj, jp / kTile), c = jp % kTile;
                 T s = zvec[jp];
                 for (int i = 0; i < nv; ++i) s -= A[(size_t)(i * kTile + c) * NT + t] * xvec[kTile * bj + i];
@@ -353,10 +436,87 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
             }
             __syncthreads();
         }
-        for (int c = tid; c < k; c += kSolveThreads) {
-            const T v = xvec[c];
-            if (!(v - v == T(0))) *p.status = 1;   // inf or nan: singular system (lambda == 0)
-            out[c] = v;
+        if (!lowrank) {
+            for (int c = tid; c < k; c += nthreads) {
+                const T v = xvec[c];
+                if (!(v - v == T(0))) *p.status = 1;   // inf or nan: singular system (lambda == 0)
+                out[c] = v;
+            }
+        } else {
+            // y = Q_r^T t + p  (second, L2-resident pass over the row's Q rows; coalesced along a)
+            for (int a = tid; a < k; a += nthreads) {
+                T s = prior_row ? p.lambda * prior_row[a] : T(0);
+                for (int i = 0; i < dim; ++i) s += p.fixed[(int64_t)idxs[i] * k + a] * xvec[i];
+                if (!(s - s == T(0))) *p.status = 1;
+                out[a] = s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L^-1 (dense, lower triangular) and its transpose from the factored tiles of a k x k matrix
+// (als_solve_rows_kernel with export_tiles: off-diagonal tiles hold L, diagonal tiles hold the
+// inverse of their 8x8 factor).  Block column J of X = L^-1:
+//     X_JJ = D_J^-1,   X_IJ = -D_I^-1 * sum_{Q=J}^{I-1} L_IQ X_QJ   (I > J)
+// grid = block columns, 64 threads = the 8x8 elements of the tile being formed; the exported
+// tiles are staged in shared memory when they fit (tiles_in_smem), else read through L2.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(64) tri_inverse_kernel(const T* __restrict__ tiles, int k, int tiles_in_smem,
+                                                         T* __restrict__ linv, T* __restrict__ linv_t) {
+    HYPREC_DYN_SMEM(smem_raw);
+    const int nb_src = aug_blocks(k), NT = tri(nb_src);
+    const int nbk = (k + kTile - 1) / kTile;
+    const int J = blockIdx.x;
+    const int tid = threadIdx.x, r = tid / kTile, c = tid % kTile;
+    T* xcol = (T*)smem_raw;                       // [nbk][64] tiles of block column J
+    T* sbuf = xcol + (size_t)nbk * kTileElems;    // [64]
+    T* ls = sbuf + kTileElems;                    // [64 * NT] optional copy of the tiles
+    const T* L = tiles;
+    if (tiles_in_smem) {
+        for (int e = tid; e < kTileElems * NT; e += 64) ls[e] = tiles[e];
+        L = ls;
+    }
+    __syncthreads();
+    for (int I = J; I < nbk; ++I) {
+        T v;
+        if (I == J) {
+            v = (c <= r) ? L[(size_t)(r * kTile + c) * NT + tile_id(J, J)] : T(0);
+        } else {
+            T s = T(0);
+            for (int Q = J; Q < I; ++Q) {
+                const int t = tile_id(I, Q);
+#pragma unroll
+                for (int kk = 0; kk < kTile; ++kk)
+                    s += L[(size_t)(r * kTile + kk) * NT + t] * xcol[(size_t)Q * kTileElems + kk * kTile + c];
+            }
+            sbuf[r * kTile + c] = s;
+            __syncthreads();
+            const int td = tile_id(I, I);
+            T acc = T(0);
+            for (int rr = 0; rr <= r; ++rr) acc += L[(size_t)(r * kTile + rr) * NT + td] * sbuf[rr * kTile + c];
+            v = -acc;
+        }
+        const int gi = I * kTile + r, gj = J * kTile + c;
+        if (gi >= k || gj >= k) v = T(0);
+        xcol[(size_t)I * kTileElems + r * kTile + c] = v;
+        if (gi < k && gj < k) {
+            linv[(size_t)gi * k + gj] = v;
+            linv_t[(size_t)gj * k + gi] = v;
+            if (I == J && c > r) {   // strictly upper part of the diagonal block is zero in L^-1
+                linv[(size_t)gi * k + gj] = T(0);
+                linv_t[(size_t)gj * k + gi] = T(0);
+            }
+        }
+        __syncthreads();
+    }
+    // zero the strictly upper block triangle (tiles with I < J) of linv / lower of linv_t
+    for (int I = 0; I < J; ++I) {
+        const int gi = I * kTile + r, gj = J * kTile + c;
+        if (gi < k && gj < k) {
+            linv[(size_t)gi * k + gj] = T(0);
+            linv_t[(size_t)gj * k + gi] = T(0);
         }
     }
 }

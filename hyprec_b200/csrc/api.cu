@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -70,7 +71,7 @@ struct Csr {
     void release() { indptr.release(); indices.release(); values.release(); }
 };
 
-constexpr int kNumTimers = 7;
+constexpr int kNumTimers = 8;
 
 struct EngineBase {
     virtual ~EngineBase() {}
@@ -98,6 +99,7 @@ struct hyprec_ctx {
     int num_sms = 0;
     int max_smem = 0;
     int64_t launches = 0;
+    bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
     int64_t user_lo = 0, user_hi = -1, item_lo = 0, item_hi = -1;   // shard; hi < 0 => all
     // kernel timing: (begin, end) event pairs taken from a pool, harvested into per-class
     // totals after the stream has been synchronised
@@ -166,13 +168,16 @@ struct Engine : EngineBase {
     bool gram_ok[2] = {false, false};   // [0] = U^T U, [1] = V^T V match the current factors
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
     DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
+    DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr;
+    int solve_smem_attr = 0;
     DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk;
 
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
     ~Engine() override {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
-                         &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk};
+                         &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &plan[0].lists, &plan[1].lists};
         for (DevBuf* b : all) b->release();
         csr.release(); csc.release(); full.release(); test.release();
     }
@@ -213,6 +218,7 @@ struct Engine : EngineBase {
     int set_train(int64_t m_, int64_t n_, const int64_t* indptr, const int32_t* indices, const double* values) override {
         if (m_ <= 0 || n_ <= 0) return fail(HYPREC_E_INVALID, "set_train_csr: empty matrix");
         if (m_ != m || n_ != n) { k = 0; gram_ok[0] = gram_ok[1] = false; }
+        plan[0].lo = plan[1].lo = -1;
         m = m_;
         n = n_;
         HY_TRY(upload_csr(csr, m, n, indptr, indices, values, "train"));
@@ -355,12 +361,139 @@ struct Engine : EngineBase {
     }
 
     // ---------------------------------------------------------------- ALS half-step
+    // Launch the row kernel over a contiguous range or a row list, in direct or low-rank mode.
+    int launch_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
+                    bool lowrank, int max_dim, int threads, const T* fixed_ptr, const T* prior_ptr, T* export_ptr,
+                    const int64_t* indptr_override, int64_t work) {
+        const Csr& rows_csr = user ? csr : csc;
+        // shared-memory plan: tiles in shared memory when they fit, else per-CTA global scratch
+        int chunk = lowrank ? 16 : 32;
+        hyprec::SolveLayout lay = hyprec::solve_layout(max_dim, chunk, true, sizeof(T));
+        while (lay.total > (size_t)h->max_smem && chunk > 8) {
+            chunk /= 2;
+            lay = hyprec::solve_layout(max_dim, chunk, true, sizeof(T));
+        }
+        const bool in_smem = lay.total <= (size_t)h->max_smem;
+        if (!in_smem) {
+            chunk = 16;
+            lay = hyprec::solve_layout(max_dim, chunk, false, sizeof(T));
+            if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "n_factors too large for the solve kernel");
+        }
+        auto kern = hyprec::als_solve_rows_kernel<T>;
+        if ((int)lay.total > solve_smem_attr) {
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+            solve_smem_attr = (int)lay.total;
+        }
+        int per_sm = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));
+        if (per_sm < 1) return fail(HYPREC_E_UNSUPPORTED, "solve kernel does not fit on an SM");
+        const int grid = (int)std::min<int64_t>(work, (int64_t)per_sm * h->num_sms);
+        if (!in_smem) HY_TRY(a_scratch.reserve(sizeof(T) * (size_t)grid * hyprec::kTileElems * lay.n_tiles));
+        CU_TRY(cudaMemsetAsync(counter.ptr, 0, sizeof(int), h->stream));   // work counter only; status accumulates
+
+        hyprec::SolveArgs<T> a;
+        a.indptr = indptr_override ? indptr_override : rows_csr.indptr.template as<int64_t>();
+        a.indices = rows_csr.indices.template as<int32_t>();
+        a.values = rows_csr.values.template as<T>();
+        a.fixed = fixed_ptr;
+        a.latent = user ? U.as<T>() : V.as<T>();
+        a.base = base.as<T>();
+        a.prior = prior_ptr;
+        a.a_scratch = in_smem ? nullptr : a_scratch.as<T>();
+        a.work_counter = counter.as<int>();
+        a.status = counter.as<int>() + 1;
+        a.lambda = (T)lambda;
+        a.k = k;
+        a.row_lo = lo;
+        a.row_hi = hi;
+        a.chunk_rows = chunk;
+        a.row_list = list;
+        a.n_list = n_list;
+        a.max_dim = max_dim;
+        a.lowrank = lowrank ? 1 : 0;
+        a.ymat = ymat.as<T>();
+        a.export_tiles = export_ptr;
+        kern<<<grid, threads, lay.total, h->stream>>>(a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
+    // C[ra x rb] = A[ra x k] B[rb x k]^T through the sweep kernel (float64 path only)
+    int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, double* c) {
+        hyprec::SweepArgs<T> s;
+        s.user_vecs = a;
+        s.item_vecs = b;
+        s.k = k;
+        s.user_lo = 0;
+        s.user_hi = ra;
+        s.n_items = rb;
+        s.dense_out = c;
+        s.thresholds = nullptr;
+        s.counts = nullptr;
+        dim3 grid((unsigned)((rb + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
+                  (unsigned)((ra + hyprec::kSweepTile - 1) / hyprec::kSweepTile));
+        hyprec::score_sweep_kernel<T, hyprec::kSweepStore><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(s);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
+    // Rows of [lo, hi) grouped for the low-rank path: bucket b holds rows with
+    // deg <= kBucketDim[b] (sorted by degree, heaviest first), `heavy` the rest.
+    struct RowPlan {
+        int64_t lo = -1, hi = -1;
+        int cap = -1;
+        std::vector<int64_t> bucket_off;   // offsets into `lists`, size n_buckets + 2 (last = heavy)
+        std::vector<int> bucket_dim;
+        DevBuf lists;
+    };
+    RowPlan plan[2];
+
+    int build_plan(bool user, int64_t lo, int64_t hi, int cap) {
+        RowPlan& pl = plan[user ? 0 : 1];
+        if (pl.lo == lo && pl.hi == hi && pl.cap == cap) return HYPREC_OK;
+        const std::vector<int64_t>& ptr = (user ? csr : csc).h_indptr;
+        static const int dims[4] = {31, 63, 127, 191};
+        std::vector<std::vector<int32_t>> groups(5);
+        for (int64_t r = lo; r < hi; ++r) {
+            const int64_t deg = ptr[r + 1] - ptr[r];
+            int b = 4;
+            if (deg <= cap)
+                for (int i = 0; i < 4; ++i)
+                    if (deg <= dims[i]) { b = i; break; }
+            groups[b].push_back((int32_t)r);
+        }
+        std::vector<int32_t> flat;
+        pl.bucket_off.assign(1, 0);
+        pl.bucket_dim.clear();
+        for (int b = 0; b < 5; ++b) {
+            std::stable_sort(groups[b].begin(), groups[b].end(), [&](int32_t x, int32_t y) {
+                return ptr[x + 1] - ptr[x] > ptr[y + 1] - ptr[y];
+            });
+            int maxdeg = 1;
+            if (!groups[b].empty()) maxdeg = (int)std::max<int64_t>(1, ptr[groups[b][0] + 1] - ptr[groups[b][0]]);
+            pl.bucket_dim.push_back(b < 4 ? std::min(maxdeg, dims[b]) : k);
+            flat.insert(flat.end(), groups[b].begin(), groups[b].end());
+            pl.bucket_off.push_back((int64_t)flat.size());
+        }
+        HY_TRY(pl.lists.reserve(sizeof(int32_t) * std::max<size_t>(flat.size(), 1)));
+        if (!flat.empty()) {
+            CU_TRY(cudaMemcpyAsync(pl.lists.ptr, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+        }
+        pl.lo = lo;
+        pl.hi = hi;
+        pl.cap = cap;
+        return HYPREC_OK;
+    }
+
     int half_step(int side, double lambda) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "als_half_step before set_factors");
         if (side != HYPREC_SIDE_USER && side != HYPREC_SIDE_ITEM) return fail(HYPREC_E_INVALID, "side must be 0 or 1");
         const bool user = side == HYPREC_SIDE_USER;
-        const Csr& rows_csr = user ? csr : csc;
         const int64_t total = user ? m : n;
+        const int64_t n_fixed = user ? n : m;
         int64_t lo = user ? h->user_lo : h->item_lo, hi = user ? h->user_hi : h->item_hi;
         if (hi < 0) { lo = 0; hi = total; }
         if (lo < 0 || hi > total || lo > hi) return fail(HYPREC_E_INVALID, "shard outside the matrix");
@@ -375,52 +508,80 @@ struct Engine : EngineBase {
             h->launches += 1;
         }
         if (hi == lo) return HYPREC_OK;
-
-        // shared-memory plan: tiles in shared memory when they fit, else per-CTA global scratch
-        int chunk = 32;
-        hyprec::SolveLayout lay = hyprec::solve_layout(k, chunk, true, sizeof(T));
-        while (lay.total > (size_t)h->max_smem && chunk > 8) {
-            chunk /= 2;
-            lay = hyprec::solve_layout(k, chunk, true, sizeof(T));
-        }
-        const bool in_smem = lay.total <= (size_t)h->max_smem;
-        if (!in_smem) {
-            chunk = 16;
-            lay = hyprec::solve_layout(k, chunk, false, sizeof(T));
-            if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "n_factors too large for the solve kernel");
-        }
-        auto kern = hyprec::als_solve_rows_kernel<T>;
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-        int per_sm = 0;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, hyprec::kSolveThreads, lay.total));
-        if (per_sm < 1) return fail(HYPREC_E_UNSUPPORTED, "solve kernel does not fit on an SM");
-        const int grid = (int)std::min<int64_t>(hi - lo, (int64_t)per_sm * h->num_sms);
-        if (!in_smem) HY_TRY(a_scratch.reserve(sizeof(T) * (size_t)grid * hyprec::kTileElems * n_tiles));
         HY_TRY(counter.reserve(2 * sizeof(int)));
         CU_TRY(cudaMemsetAsync(counter.ptr, 0, 2 * sizeof(int), h->stream));
+        const T* fixed_ptr = user ? V.as<T>() : U.as<T>();
+        const T* prior_ptr = (!user && has_prior) ? prior.as<T>() : nullptr;
+        HY_TRY(ymat.reserve(sizeof(T)));
 
-        hyprec::SolveArgs<T> a;
-        a.indptr = rows_csr.indptr.template as<int64_t>();
-        a.indices = rows_csr.indices.template as<int32_t>();
-        a.values = rows_csr.values.template as<T>();
-        a.fixed = user ? V.as<T>() : U.as<T>();
-        a.latent = user ? U.as<T>() : V.as<T>();
-        a.base = base.as<T>();
-        a.prior = (!user && has_prior) ? prior.as<T>() : nullptr;
-        a.a_scratch = in_smem ? nullptr : a_scratch.as<T>();
-        a.work_counter = counter.as<int>();
-        a.status = counter.as<int>() + 1;
-        a.lambda = (T)lambda;
-        a.k = k;
-        a.row_lo = lo;
-        a.row_hi = hi;
-        a.chunk_rows = chunk;
-        {
+        // The low-rank path needs float64 (it goes through L^-1 of 0.1 G + lambda I) and pays off
+        // when rows have far fewer positives than k.
+        const bool lowrank = sizeof(T) == sizeof(double) && h->lowrank_enabled && lambda > 0.0 && k >= 16;
+        if (!lowrank) {
             Timer t(h, HYPREC_T_SOLVE);
-            kern<<<grid, hyprec::kSolveThreads, lay.total, h->stream>>>(a);
-            h->launches += 1;
+            HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
+                               nullptr, nullptr, hi - lo));
+        } else {
+            const int cap = std::min(k, 191);
+            HY_TRY(build_plan(user, lo, hi, cap));
+            const RowPlan& pl = plan[user ? 0 : 1];
+            const int32_t* lists = pl.lists.template as<int32_t>();
+            {
+                Timer t(h, HYPREC_T_PREP);
+                // 1. factor B = 0.1 G + lambda I once (a row without positives), keep the tiles
+                HY_TRY(tiles.reserve(sizeof(T) * (size_t)hyprec::kTileElems * n_tiles));
+                HY_TRY(dummy_ptr.reserve(2 * sizeof(int64_t)));
+                CU_TRY(cudaMemsetAsync(dummy_ptr.ptr, 0, 2 * sizeof(int64_t), h->stream));
+                HY_TRY(launch_rows(user, lambda, 0, 1, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, nullptr,
+                                   tiles.as<T>(), dummy_ptr.as<int64_t>(), 1));
+                // 2. L^-1 and L^-T
+                HY_TRY(linv.reserve(sizeof(T) * (size_t)k * k));
+                HY_TRY(linv_t.reserve(sizeof(T) * (size_t)k * k));
+                const int nbk = (k + hyprec::kTile - 1) / hyprec::kTile;
+                size_t inv_smem = sizeof(T) * ((size_t)nbk * hyprec::kTileElems + hyprec::kTileElems);
+                const size_t with_tiles = inv_smem + sizeof(T) * (size_t)hyprec::kTileElems * n_tiles;
+                const int tis = with_tiles <= (size_t)h->max_smem ? 1 : 0;
+                if (tis) inv_smem = with_tiles;
+                auto inv_kern = hyprec::tri_inverse_kernel<T>;
+                CU_TRY(cudaFuncSetAttribute(inv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+                inv_kern<<<nbk, 64, inv_smem, h->stream>>>(tiles.as<T>(), k, tis, linv.as<T>(), linv_t.as<T>());
+                h->launches += 1;
+                CU_TRY(cudaGetLastError());
+                // 3. whitened factors Q = Y L^-T (and theta L^-T for the item prior)
+                HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
+                HY_TRY(gemm_nt(fixed_ptr, n_fixed, linv.as<T>(), k, qmat.as<double>()));
+                if (prior_ptr) {
+                    HY_TRY(pq.reserve(sizeof(T) * (size_t)total * k));
+                    HY_TRY(gemm_nt(prior_ptr, total, linv.as<T>(), k, pq.as<double>()));
+                }
+            }
+            HY_TRY(ymat.reserve(sizeof(T) * (size_t)total * k));
+            const int64_t n_light = pl.bucket_off[4];
+            {
+                Timer t(h, HYPREC_T_SOLVE);
+                static const int threads[4] = {32, 64, 128, 256};
+                if (n_light < hi - lo)   // heavy rows' y is never produced: keep the GEMM input finite
+                    CU_TRY(cudaMemsetAsync(ymat.as<T>() + lo * k, 0, sizeof(T) * (size_t)(hi - lo) * k, h->stream));
+                for (int b = 0; b < 4; ++b) {
+                    const int64_t cnt = pl.bucket_off[b + 1] - pl.bucket_off[b];
+                    if (cnt == 0) continue;
+                    HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
+                                       threads[b], qmat.as<T>(), prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt));
+                }
+            }
+            if (n_light > 0) {
+                // 4. x = L^-T y for every row of the shard: one GEMM straight into the factor matrix
+                Timer t(h, HYPREC_T_PREP);
+                T* latent = (user ? U.as<T>() : V.as<T>()) + lo * k;
+                HY_TRY(gemm_nt(ymat.as<T>() + lo * k, hi - lo, linv_t.as<T>(), k, (double*)latent));
+            }
+            const int64_t n_heavy = pl.bucket_off[5] - pl.bucket_off[4];
+            if (n_heavy > 0) {
+                Timer t(h, HYPREC_T_SOLVE);
+                HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[4], n_heavy, false, k,
+                                   hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy));
+            }
         }
-        CU_TRY(cudaGetLastError());
         gram_ok[user ? 0 : 1] = false;
         int status[2] = {0, 0};
         CU_TRY(cudaMemcpyAsync(status, counter.ptr, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
@@ -728,6 +889,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const char* lr = getenv("HYPREC_LOWRANK");
+    h->lowrank_enabled = !(lr && lr[0] == '0');
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);
     else h->engine = new Engine<float>(h);
     *out = h;

@@ -22,6 +22,8 @@ def user_degrees(rs, n_users, total, min_degree, max_degree):
     deg = min_degree + numpy.floor(raw * (spare / raw.sum())).astype(numpy.int64)
     deg = numpy.minimum(deg, max_degree)
     short = total - int(deg.sum())
+    if total > max_degree * n_users:
+        raise ValueError("%d positives do not fit %d users of at most %d positives" % (total, n_users, max_degree))
     order = rs.permutation(n_users)
     i = 0
     while short > 0:            # hand the remainder out one by one

@@ -137,6 +137,7 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
 #define HYPREC_T_TOPK 4
 #define HYPREC_T_FLAGS 5
 #define HYPREC_T_COUNT 6
+#define HYPREC_T_PREP 7   /* low-rank path: factor of 0.1 G + lambda I, L^-1, whitening / un-whitening GEMMs */
 int hyprec_kernel_ms(hyprec_t* h, int which, double* total_ms, int64_t* calls, double* last_ms);
 int hyprec_reset_kernel_ms(hyprec_t* h);
 /* Measured FMA rate of this GPU (TFLOP/s, best of 4 after a warm-up) in the given precision:

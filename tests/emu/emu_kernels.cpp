@@ -47,7 +47,88 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
     a.base = base.data(); a.prior = prior; a.a_scratch = a_in_smem ? nullptr : scratch.data();
     a.work_counter = counter; a.status = counter + 1; a.lambda = lambda; a.k = k;
     a.row_lo = row_lo; a.row_hi = row_hi; a.chunk_rows = chunk_rows;
+    a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = nullptr;
     emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T>(a); });
+    return counter[1];
+}
+
+// C = A B^T through the sweep kernel (A: ra x k, B: rb x k, C: ra x rb float64)
+static void gemm_nt(const double* a, int64_t ra, const double* b, int64_t rb, int k, double* c) {
+    SweepArgs<double> s;
+    s.user_vecs = a; s.item_vecs = b; s.k = k; s.user_lo = 0; s.user_hi = ra; s.n_items = rb;
+    s.dense_out = c; s.thresholds = nullptr; s.counts = nullptr;
+    emu::launch(dim3((unsigned)((rb + kSweepTile - 1) / kSweepTile), (unsigned)((ra + kSweepTile - 1) / kSweepTile)),
+                dim3(kSweepThreads), 0, [&]() { score_sweep_kernel<double, kSweepStore>(s); });
+}
+
+// Low-rank (Woodbury) half-step, the same pipeline hyprec_b200/csrc/api.cu runs on the device:
+// Gram -> base tiles -> factor B (one dummy row, tiles exported) -> L^-1 -> Q = Y L^-T ->
+// per-row deg x deg systems on Q (rows with deg <= dim_cap) -> X = Ymat L^-1; heavier rows go
+// through the direct kernel.
+static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices, const double* values,
+                                  const double* fixed, int64_t n_fixed, double* latent, int64_t n_rows, int k,
+                                  double lambda, const double* prior, int dim_cap, int threads, int grid,
+                                  int tiles_in_smem) {
+    typedef double T;
+    std::vector<T> g((size_t)k * k);
+    gram_impl<T>(fixed, n_fixed, k, 3, g.data());
+    const int nb = aug_blocks(k), n_tiles = tri(nb);
+    std::vector<T> base((size_t)kTileElems * n_tiles), tiles((size_t)kTileElems * n_tiles);
+    emu::launch(dim3((kTileElems * n_tiles + 255) / 256), dim3(256), 0,
+                [&]() { build_base_tiles_kernel<T>(g.data(), k, lambda, base.data()); });
+    int counter[2] = {0, 0};
+    // 1. factor B: a single row without positives
+    int64_t dummy_ptr[2] = {0, 0};
+    std::vector<T> dummy_out(k);
+    SolveArgs<T> a;
+    a.indptr = dummy_ptr; a.indices = indices; a.values = values; a.fixed = fixed; a.latent = dummy_out.data();
+    a.base = base.data(); a.prior = nullptr; a.a_scratch = nullptr; a.work_counter = counter; a.status = counter + 1;
+    a.lambda = lambda; a.k = k; a.row_lo = 0; a.row_hi = 1; a.chunk_rows = 8; a.row_list = nullptr; a.n_list = 0;
+    a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = tiles.data();
+    SolveLayout lay = solve_layout(k, 8, true, sizeof(T));
+    emu::launch(dim3(1), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T>(a); });
+    // 2. L^-1 and its transpose
+    std::vector<T> linv((size_t)k * k, -777.0), linv_t((size_t)k * k, -777.0);
+    const int nbk = (k + kTile - 1) / kTile;
+    size_t inv_smem = sizeof(T) * ((size_t)nbk * kTileElems + kTileElems + (tiles_in_smem ? (size_t)kTileElems * n_tiles : 0));
+    emu::launch(dim3(nbk), dim3(64), inv_smem,
+                [&]() { tri_inverse_kernel<T>(tiles.data(), k, tiles_in_smem, linv.data(), linv_t.data()); });
+    // 3. whitened factors Q = Y L^-T  (Q[i][a] = sum_b Y[i][b] Linv[a][b]) and prior rows p = lambda theta L^-T
+    std::vector<T> q((size_t)n_fixed * k), pq;
+    gemm_nt(fixed, n_fixed, linv.data(), k, k, q.data());
+    if (prior) {
+        pq.resize((size_t)n_rows * k);
+        gemm_nt(prior, n_rows, linv.data(), k, k, pq.data());
+    }
+    // 4. rows by degree
+    std::vector<int32_t> light, heavy;
+    int max_deg = 1;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int deg = (int)(indptr[r + 1] - indptr[r]);
+        if (deg <= dim_cap) { light.push_back((int32_t)r); max_deg = std::max(max_deg, deg); }
+        else heavy.push_back((int32_t)r);
+    }
+    std::vector<T> ymat((size_t)n_rows * k, 0.0);
+    if (!light.empty()) {
+        counter[0] = 0;
+        SolveArgs<T> b = a;
+        b.indptr = indptr; b.fixed = q.data(); b.prior = prior ? pq.data() : nullptr; b.latent = nullptr;
+        b.row_list = light.data(); b.n_list = (int64_t)light.size(); b.max_dim = max_deg; b.lowrank = 1;
+        b.ymat = ymat.data(); b.export_tiles = nullptr; b.chunk_rows = 16;
+        SolveLayout l2 = solve_layout(max_deg, 16, true, sizeof(T));
+        emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T>(b); });
+        // 5. X = Ymat L^-1  (X[i][c] = sum_a Ymat[i][a] LinvT[c][a]) -- light rows only are meaningful
+        std::vector<T> x((size_t)n_rows * k);
+        gemm_nt(ymat.data(), n_rows, linv_t.data(), k, k, x.data());
+        for (int32_t r : light) memcpy(latent + (size_t)r * k, x.data() + (size_t)r * k, sizeof(T) * k);
+    }
+    if (!heavy.empty()) {
+        counter[0] = 0;
+        SolveArgs<T> d = a;
+        d.indptr = indptr; d.latent = latent; d.prior = prior; d.row_list = heavy.data(); d.n_list = (int64_t)heavy.size();
+        d.export_tiles = nullptr; d.chunk_rows = 8;
+        emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T>(d); });
+    }
     return counter[1];
 }
 
@@ -105,6 +186,13 @@ int emu_half_step_f32(const int64_t* indptr, const int32_t* indices, const float
                       const float* prior, int chunk_rows, int grid, int a_in_smem) {
     return half_step_impl<float>(indptr, indices, values, fixed, n_fixed, latent, row_lo, row_hi, k, lambda, prior,
                                  chunk_rows, grid, a_in_smem);
+}
+
+int emu_half_step_lowrank_f64(const int64_t* indptr, const int32_t* indices, const double* values, const double* fixed,
+                              int64_t n_fixed, double* latent, int64_t n_rows, int k, double lambda, const double* prior,
+                              int dim_cap, int threads, int grid, int tiles_in_smem) {
+    return half_step_lowrank_impl(indptr, indices, values, fixed, n_fixed, latent, n_rows, k, lambda, prior, dim_cap,
+                                  threads, grid, tiles_in_smem);
 }
 
 void emu_eval_f64(const double* U, const double* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,

@@ -41,7 +41,7 @@ def rel_frob(a, b):
 # golden cases through the reference-facing class
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["als_kfold_4x30", "als_kfold_toy", "als_theta_toy", "als_naive_toy"])
-def test_class_reproduces_reference_run(als_cases, name):
+def test_class_reproduces_reference_run(als_cases, name, solve_path):
     """Whole train() flow: identical split (numpy.random seed 42), identical initial draws, device
     training with early stopping, device evaluation -> the reference's averaged 11-tuple."""
     from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
@@ -135,9 +135,17 @@ def synthetic(m, n, k, nnz, seed, empty=True):
     return full, oals.to_csr(train), oals.to_csr(test), u0, v0, cands
 
 
+@pytest.fixture(params=["lowrank", "direct"])
+def solve_path(request, monkeypatch):
+    """Both row-solve formulations: deg x deg systems on whitened factors (default for rows with
+    deg <= k) and the direct k x k Cholesky (HYPREC_LOWRANK=0); the switch is read at hyprec_create."""
+    monkeypatch.setenv("HYPREC_LOWRANK", "1" if request.param == "lowrank" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("m,n,k,nnz", [(60, 200, 5, 1200), (300, 900, 50, 9000), (120, 400, 200, 4000),
-                                       (64, 300, 33, 2500)])
-def test_epochs_match_oracle_fp64(native, m, n, k, nnz):
+                                       (64, 300, 33, 2500), (50, 120, 24, 1450)])
+def test_epochs_match_oracle_fp64(native, solve_path, m, n, k, nnz):
     full, train, test, u0, v0, cands = synthetic(m, n, k, nnz, seed=k)
     h, csr = make_handle(native, train)
     h.set_factors(u0, v0)

@@ -49,7 +49,7 @@ def main():
             h.eval_topk(200, cp, cands.ravel(), n_train_nz=train.nnz, n_test_nz=test.nnz)
         t2 = time.perf_counter()
         print("epoch %d rmse %.6f epoch %.2f ms eval %.2f ms" % (e, rmse, 1e3 * (t1 - t0), 1e3 * (t2 - t1)))
-    names = ["gram", "solve", "rmse", "sweep", "topk", "flags", "count"]
+    names = ["gram", "solve", "rmse", "sweep", "topk", "flags", "count", "prep"]
     for i, name in enumerate(names):
         total, calls, last = h.kernel_ms(i)
         print("%-6s total %.3f ms in %d regions" % (name, total, calls))

@@ -109,6 +109,8 @@ struct hyprec_ctx {
     double ms_total[kNumTimers] = {0};
     double ms_last[kNumTimers] = {0};
     int64_t ms_calls[kNumTimers] = {0};
+    cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // concurrent row-kernel launches
+    cudaEvent_t ev_fork = nullptr, ev_base = nullptr, ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     EngineBase* engine = nullptr;
@@ -168,7 +170,9 @@ struct Engine : EngineBase {
     bool gram_ok[2] = {false, false};   // [0] = U^T U, [1] = V^T V match the current factors
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
     DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
-    DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr;
+    DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out;
+    DevBuf a_scratch_slot[8];
+    static constexpr int kStatusSlot = 15;
     int solve_smem_attr = 0;
     DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk;
 
@@ -177,7 +181,9 @@ struct Engine : EngineBase {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
-                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &plan[0].lists, &plan[1].lists};
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &plan[0].lists, &plan[1].lists,
+                         &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
+                         &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7]};
         for (DevBuf* b : all) b->release();
         csr.release(); csc.release(); full.release(); test.release();
     }
@@ -364,7 +370,14 @@ struct Engine : EngineBase {
     // Launch the row kernel over a contiguous range or a row list, in direct or low-rank mode.
     int launch_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
                     bool lowrank, int max_dim, int threads, const T* fixed_ptr, const T* prior_ptr, T* export_ptr,
-                    const int64_t* indptr_override, int64_t work) {
+                    const int64_t* indptr_override, int64_t work, cudaStream_t st, int slot) {
+        // export_ptr != null: the single-row launch that only factors B -- its (zero) solution must
+        // not land in the factor matrix
+        T* latent_ptr = user ? U.as<T>() : V.as<T>();
+        if (export_ptr) {
+            if (dummy_out.reserve(sizeof(T) * (size_t)k) != HYPREC_OK) return HYPREC_E_NOMEM;
+            latent_ptr = dummy_out.as<T>();
+        }
         const Csr& rows_csr = user ? csr : csc;
         // shared-memory plan: tiles in shared memory when they fit, else per-CTA global scratch
         int chunk = lowrank ? 16 : 32;
@@ -388,20 +401,21 @@ struct Engine : EngineBase {
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));
         if (per_sm < 1) return fail(HYPREC_E_UNSUPPORTED, "solve kernel does not fit on an SM");
         const int grid = (int)std::min<int64_t>(work, (int64_t)per_sm * h->num_sms);
-        if (!in_smem) HY_TRY(a_scratch.reserve(sizeof(T) * (size_t)grid * hyprec::kTileElems * lay.n_tiles));
-        CU_TRY(cudaMemsetAsync(counter.ptr, 0, sizeof(int), h->stream));   // work counter only; status accumulates
+        // (work counters of all slots were zeroed at the start of the half-step)
+        DevBuf& scratch_buf = a_scratch_slot[slot];
+        if (!in_smem) HY_TRY(scratch_buf.reserve(sizeof(T) * (size_t)grid * hyprec::kTileElems * lay.n_tiles));
 
         hyprec::SolveArgs<T> a;
         a.indptr = indptr_override ? indptr_override : rows_csr.indptr.template as<int64_t>();
         a.indices = rows_csr.indices.template as<int32_t>();
         a.values = rows_csr.values.template as<T>();
         a.fixed = fixed_ptr;
-        a.latent = user ? U.as<T>() : V.as<T>();
+        a.latent = latent_ptr;
         a.base = base.as<T>();
         a.prior = prior_ptr;
-        a.a_scratch = in_smem ? nullptr : a_scratch.as<T>();
-        a.work_counter = counter.as<int>();
-        a.status = counter.as<int>() + 1;
+        a.a_scratch = in_smem ? nullptr : scratch_buf.template as<T>();
+        a.work_counter = counter.as<int>() + slot;
+        a.status = counter.as<int>() + kStatusSlot;
         a.lambda = (T)lambda;
         a.k = k;
         a.row_lo = lo;
@@ -413,14 +427,15 @@ struct Engine : EngineBase {
         a.lowrank = lowrank ? 1 : 0;
         a.ymat = ymat.as<T>();
         a.export_tiles = export_ptr;
-        kern<<<grid, threads, lay.total, h->stream>>>(a);
+        kern<<<grid, threads, lay.total, st>>>(a);
         h->launches += 1;
         CU_TRY(cudaGetLastError());
         return HYPREC_OK;
     }
 
-    // C[ra x rb] = A[ra x k] B[rb x k]^T through the sweep kernel (float64 path only)
-    int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, double* c) {
+    // C[ra x rb] = A[ra x k] B[rb x k]^T through the sweep kernel (float64 path only).  With a row
+    // list the product is taken over rows A[list[i]] and row i is stored at C[list[i]].
+    int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, double* c, const int32_t* list = nullptr) {
         hyprec::SweepArgs<T> s;
         s.user_vecs = a;
         s.item_vecs = b;
@@ -429,6 +444,7 @@ struct Engine : EngineBase {
         s.user_hi = ra;
         s.n_items = rb;
         s.dense_out = c;
+        s.row_list = list;
         s.thresholds = nullptr;
         s.counts = nullptr;
         dim3 grid((unsigned)((rb + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
@@ -508,8 +524,8 @@ struct Engine : EngineBase {
             h->launches += 1;
         }
         if (hi == lo) return HYPREC_OK;
-        HY_TRY(counter.reserve(2 * sizeof(int)));
-        CU_TRY(cudaMemsetAsync(counter.ptr, 0, 2 * sizeof(int), h->stream));
+        HY_TRY(counter.reserve(16 * sizeof(int)));
+        CU_TRY(cudaMemsetAsync(counter.ptr, 0, 16 * sizeof(int), h->stream));
         const T* fixed_ptr = user ? V.as<T>() : U.as<T>();
         const T* prior_ptr = (!user && has_prior) ? prior.as<T>() : nullptr;
         HY_TRY(ymat.reserve(sizeof(T)));
@@ -520,73 +536,87 @@ struct Engine : EngineBase {
         if (!lowrank) {
             Timer t(h, HYPREC_T_SOLVE);
             HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
-                               nullptr, nullptr, hi - lo));
+                               nullptr, nullptr, hi - lo, h->stream, 0));
         } else {
             const int cap = std::min(k, 191);
             HY_TRY(build_plan(user, lo, hi, cap));
             const RowPlan& pl = plan[user ? 0 : 1];
             const int32_t* lists = pl.lists.template as<int32_t>();
-            {
-                Timer t(h, HYPREC_T_PREP);
-                // 1. factor B = 0.1 G + lambda I once (a row without positives), keep the tiles
-                HY_TRY(tiles.reserve(sizeof(T) * (size_t)hyprec::kTileElems * n_tiles));
-                HY_TRY(dummy_ptr.reserve(2 * sizeof(int64_t)));
-                CU_TRY(cudaMemsetAsync(dummy_ptr.ptr, 0, 2 * sizeof(int64_t), h->stream));
-                HY_TRY(launch_rows(user, lambda, 0, 1, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, nullptr,
-                                   tiles.as<T>(), dummy_ptr.as<int64_t>(), 1));
-                // 2. L^-1 and L^-T
-                HY_TRY(linv.reserve(sizeof(T) * (size_t)k * k));
-                HY_TRY(linv_t.reserve(sizeof(T) * (size_t)k * k));
-                const int nbk = (k + hyprec::kTile - 1) / hyprec::kTile;
-                size_t inv_smem = sizeof(T) * ((size_t)nbk * hyprec::kTileElems + hyprec::kTileElems);
-                const size_t with_tiles = inv_smem + sizeof(T) * (size_t)hyprec::kTileElems * n_tiles;
-                const int tis = with_tiles <= (size_t)h->max_smem ? 1 : 0;
-                if (tis) inv_smem = with_tiles;
-                auto inv_kern = hyprec::tri_inverse_kernel<T>;
-                CU_TRY(cudaFuncSetAttribute(inv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
-                inv_kern<<<nbk, 64, inv_smem, h->stream>>>(tiles.as<T>(), k, tis, linv.as<T>(), linv_t.as<T>());
-                h->launches += 1;
-                CU_TRY(cudaGetLastError());
-                // 3. whitened factors Q = Y L^-T (and theta L^-T for the item prior)
-                HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
-                HY_TRY(gemm_nt(fixed_ptr, n_fixed, linv.as<T>(), k, qmat.as<double>()));
-                if (prior_ptr) {
-                    HY_TRY(pq.reserve(sizeof(T) * (size_t)total * k));
-                    HY_TRY(gemm_nt(prior_ptr, total, linv.as<T>(), k, pq.as<double>()));
-                }
-            }
-            HY_TRY(ymat.reserve(sizeof(T) * (size_t)total * k));
             const int64_t n_light = pl.bucket_off[4];
-            {
-                Timer t(h, HYPREC_T_SOLVE);
-                static const int threads[4] = {32, 64, 128, 256};
-                if (n_light < hi - lo)   // heavy rows' y is never produced: keep the GEMM input finite
-                    CU_TRY(cudaMemsetAsync(ymat.as<T>() + lo * k, 0, sizeof(T) * (size_t)(hi - lo) * k, h->stream));
-                for (int b = 0; b < 4; ++b) {
-                    const int64_t cnt = pl.bucket_off[b + 1] - pl.bucket_off[b];
-                    if (cnt == 0) continue;
-                    HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
-                                       threads[b], qmat.as<T>(), prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt));
-                }
+            const int64_t n_heavy = pl.bucket_off[5] - pl.bucket_off[4];
+            HY_TRY(ymat.reserve(sizeof(T) * (size_t)total * k));
+            // rows above the cap do not depend on the factor of B: start them right away on their
+            // own stream (base tiles and counters are ready on the main stream)
+            CU_TRY(cudaEventRecord(h->ev_base, h->stream));
+            if (n_heavy > 0) {
+                CU_TRY(cudaStreamWaitEvent(h->aux[4], h->ev_base, 0));
+                HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[4], n_heavy, false, k,
+                                   hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy, h->aux[4], 5));
+                CU_TRY(cudaEventRecord(h->ev_join[4], h->aux[4]));
             }
             if (n_light > 0) {
-                // 4. x = L^-T y for every row of the shard: one GEMM straight into the factor matrix
-                Timer t(h, HYPREC_T_PREP);
-                T* latent = (user ? U.as<T>() : V.as<T>()) + lo * k;
-                HY_TRY(gemm_nt(ymat.as<T>() + lo * k, hi - lo, linv_t.as<T>(), k, (double*)latent));
+                {
+                    Timer t(h, HYPREC_T_PREP);
+                    // 1. factor B = 0.1 G + lambda I once (a row without positives), keep the tiles
+                    HY_TRY(tiles.reserve(sizeof(T) * (size_t)hyprec::kTileElems * n_tiles));
+                    HY_TRY(dummy_ptr.reserve(2 * sizeof(int64_t)));
+                    CU_TRY(cudaMemsetAsync(dummy_ptr.ptr, 0, 2 * sizeof(int64_t), h->stream));
+                    HY_TRY(launch_rows(user, lambda, 0, 1, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, nullptr,
+                                       tiles.as<T>(), dummy_ptr.as<int64_t>(), 1, h->stream, 0));
+                    // 2. L^-1 and L^-T
+                    HY_TRY(linv.reserve(sizeof(T) * (size_t)k * k));
+                    HY_TRY(linv_t.reserve(sizeof(T) * (size_t)k * k));
+                    const int nbk = (k + hyprec::kTile - 1) / hyprec::kTile;
+                    size_t inv_smem = sizeof(T) * ((size_t)nbk * hyprec::kTileElems + hyprec::kTileElems);
+                    const size_t with_tiles = inv_smem + sizeof(T) * (size_t)hyprec::kTileElems * n_tiles;
+                    const int tis = with_tiles <= (size_t)h->max_smem ? 1 : 0;
+                    if (tis) inv_smem = with_tiles;
+                    auto inv_kern = hyprec::tri_inverse_kernel<T>;
+                    CU_TRY(cudaFuncSetAttribute(inv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+                    inv_kern<<<nbk, 64, inv_smem, h->stream>>>(tiles.as<T>(), k, tis, linv.as<T>(), linv_t.as<T>());
+                    h->launches += 1;
+                    CU_TRY(cudaGetLastError());
+                    // 3. whitened factors Q = Y L^-T (and theta L^-T for the item prior)
+                    HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
+                    HY_TRY(gemm_nt(fixed_ptr, n_fixed, linv.as<T>(), k, qmat.as<double>()));
+                    if (prior_ptr) {
+                        HY_TRY(pq.reserve(sizeof(T) * (size_t)total * k));
+                        HY_TRY(gemm_nt(prior_ptr, total, linv.as<T>(), k, pq.as<double>()));
+                    }
+                }
+                {
+                    // 4. deg x deg systems, one launch per degree bucket, all buckets concurrently
+                    Timer t(h, HYPREC_T_SOLVE);
+                    static const int threads[4] = {32, 64, 128, 256};
+                    CU_TRY(cudaEventRecord(h->ev_fork, h->stream));
+                    for (int b = 0; b < 4; ++b) {
+                        const int64_t cnt = pl.bucket_off[b + 1] - pl.bucket_off[b];
+                        if (cnt == 0) continue;
+                        CU_TRY(cudaStreamWaitEvent(h->aux[b], h->ev_fork, 0));
+                        HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
+                                           threads[b], qmat.as<T>(), prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr,
+                                           cnt, h->aux[b], 1 + b));
+                        CU_TRY(cudaEventRecord(h->ev_join[b], h->aux[b]));
+                        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
+                    }
+                }
+                {
+                    // 5. x = L^-T y for the low-rank rows: one GEMM straight into the factor matrix
+                    Timer t(h, HYPREC_T_PREP);
+                    T* latent = user ? U.as<T>() : V.as<T>();
+                    HY_TRY(gemm_nt(ymat.as<T>(), n_light, linv_t.as<T>(), k, (double*)latent, lists));
+                }
             }
-            const int64_t n_heavy = pl.bucket_off[5] - pl.bucket_off[4];
             if (n_heavy > 0) {
-                Timer t(h, HYPREC_T_SOLVE);
-                HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[4], n_heavy, false, k,
-                                   hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy));
+                Timer t(h, HYPREC_T_SOLVE);   // whatever of the heavy rows' launch is still running
+                CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[4], 0));
             }
         }
         gram_ok[user ? 0 : 1] = false;
-        int status[2] = {0, 0};
+        int status[16] = {0};
         CU_TRY(cudaMemcpyAsync(status, counter.ptr, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
-        if (status[1] != 0)
+        if (status[kStatusSlot] != 0)
             return fail(HYPREC_E_SINGULAR, "als_half_step: non-finite solution (singular normal matrix; lambda == 0?)");
         return HYPREC_OK;
     }
@@ -653,6 +683,7 @@ struct Engine : EngineBase {
             a.user_hi = hi;
             a.n_items = n;
             a.dense_out = dense_blk.as<double>();
+            a.row_list = nullptr;
             a.thresholds = nullptr;
             a.counts = nullptr;
             dim3 grid((unsigned)((n + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
@@ -706,6 +737,7 @@ struct Engine : EngineBase {
             a.user_hi = hi;
             a.n_items = n;
             a.dense_out = nullptr;
+            a.row_list = nullptr;
             a.thresholds = thresholds.as<double>();
             a.counts = counts.as<unsigned long long>();
             dim3 grid((unsigned)((n + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
@@ -889,6 +921,12 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 5; ++i) {
+        CU_TRY(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&h->ev_base, cudaEventDisableTiming));
     const char* lr = getenv("HYPREC_LOWRANK");
     h->lowrank_enabled = !(lr && lr[0] == '0');
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);
@@ -904,6 +942,12 @@ int hyprec_destroy(hyprec_t* h) {
     delete h->engine;
     h->harvest();
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 5; ++i) {
+        if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_base) cudaEventDestroy(h->ev_base);
     if (h->flush_buf) cudaFree(h->flush_buf);
     cudaStreamDestroy(h->stream);
     delete h;

@@ -26,6 +26,8 @@ struct SweepArgs {
     int k;
     int64_t user_lo, user_hi, n_items;
     double* dense_out;               // [user_hi-user_lo][n_items]          (kSweepStore)
+    const int32_t* row_list;         // optional (kSweepStore): the "user" rows are row_list[user_lo..user_hi)
+                                     // and row r of the product is stored at dense_out[row_list[r] * n_items]
     const double* thresholds;        // [n_users]                           (kSweepCount)
     unsigned long long* counts;      // [user_hi-user_lo], zeroed by caller (kSweepCount)
 };
@@ -53,7 +55,12 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
             const int rr = e / kSweepKC, cc = e % kSweepKC;
             const int col = c0 + cc;
             const int64_t ui = i0 + rr, vj = j0 + rr;
-            us[cc][rr] = (ui < p.user_hi && col < k) ? p.user_vecs[ui * k + col] : T(0);
+            T uval = T(0);
+            if (ui < p.user_hi && col < k) {
+                const int64_t src = (MODE == kSweepStore && p.row_list) ? (int64_t)p.row_list[ui] : ui;
+                uval = p.user_vecs[src * k + col];
+            }
+            us[cc][rr] = uval;
             vs[cc][rr] = (vj < p.n_items && col < k) ? p.item_vecs[vj * k + col] : T(0);
         }
         __syncthreads();
@@ -78,10 +85,11 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
         const bool row_ok = row < p.user_hi;
         if (MODE == kSweepStore) {
             if (row_ok) {
+                const int64_t dst = p.row_list ? (int64_t)p.row_list[row] : row - p.user_lo;
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
                     const int64_t col = j0 + tx + 16 * b;
-                    if (col < p.n_items) p.dense_out[(row - p.user_lo) * p.n_items + col] = (double)acc[a][b];
+                    if (col < p.n_items) p.dense_out[dst * p.n_items + col] = (double)acc[a][b];
                 }
             }
         } else {

@@ -80,6 +80,7 @@ class CollaborativeFiltering(AbstractRecommender):
         self._eval_uploaded = None       # (ratings, test_data) objects of the uploaded eval CSRs
         self._train_nnz = 0
         self._test_nnz = 0
+        self._cands_uploaded = None      # (test_indices object, fold) of the candidate lists on the device
         self._sync_token = None
         self.last_report_details = None  # per-user device outputs of the latest report
 
@@ -112,7 +113,7 @@ class CollaborativeFiltering(AbstractRecommender):
         if self._handle is not None:
             self._handle.close()
             self._handle = None
-            self._train_uploaded = self._eval_uploaded = self._sync_token = None
+            self._train_uploaded = self._eval_uploaded = self._sync_token = self._cands_uploaded = None
 
     def set_data(self, train_data, test_data):
         AbstractRecommender.set_data(self, train_data, test_data)
@@ -126,6 +127,7 @@ class CollaborativeFiltering(AbstractRecommender):
             self._train_nnz = len(indices)
             self._train_uploaded = self.train_data
             self._eval_uploaded = None
+            self._cands_uploaded = None
             self._sync_token = None
         return h
 
@@ -359,8 +361,11 @@ class CollaborativeFiltering(AbstractRecommender):
         fold = self.hyperparameters['fold']
         h = self._upload_eval()
         self._upload_factors()
-        cand_indptr, cand_ids = self.candidate_lists(fold)
-        out = h.eval_topk(self.n_recommendations, cand_indptr, cand_ids, 0, self.n_users,
+        key = (self.evaluator.test_indices, fold)
+        if self._cands_uploaded is None or self._cands_uploaded[0] is not key[0] or self._cands_uploaded[1] != fold:
+            h.set_candidates(*self.candidate_lists(fold))        # once per fold
+            self._cands_uploaded = key
+        out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users,
                           n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
         rmse = h.rmse()
 

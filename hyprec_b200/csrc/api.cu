@@ -88,6 +88,7 @@ struct EngineBase {
     virtual int eval_topk(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci, int cap, double* thr,
                           int64_t* ones, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) = 0;
     virtual int device_factors(void** u, void** v, int* elem) = 0;
+    virtual int set_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) = 0;
 };
 
 }  // namespace
@@ -225,6 +226,8 @@ struct Engine : EngineBase {
         if (m_ <= 0 || n_ <= 0) return fail(HYPREC_E_INVALID, "set_train_csr: empty matrix");
         if (m_ != m || n_ != n) { k = 0; gram_ok[0] = gram_ok[1] = false; }
         plan[0].lo = plan[1].lo = -1;
+        cand_lo = cand_hi = -1;
+        use_cached_cands = false;
         m = m_;
         n = n_;
         HY_TRY(upload_csr(csr, m, n, indptr, indices, values, "train"));
@@ -702,6 +705,48 @@ struct Engine : EngineBase {
     }
 
     // ---------------------------------------------------------------- evaluation
+    int64_t cand_lo = -1, cand_hi = -1, cand_max = 0;
+    bool use_cached_cands = false;
+
+    // Candidate streams of users [lo, hi): validated (one min/max pass), copied to the device and
+    // kept until replaced, so that a fold's lists cross PCIe once.
+    int upload_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) {
+        const int64_t nu = hi - lo;
+        if (!cp || !ci) return fail(HYPREC_E_INVALID, "candidates: null array");
+        if (cp[0] != 0) return fail(HYPREC_E_INVALID, "candidates: cand_indptr[0] != 0");
+        int64_t max_cand = 0;
+        for (int64_t u = 0; u < nu; ++u) {
+            if (cp[u + 1] < cp[u]) return fail(HYPREC_E_INVALID, "candidates: cand_indptr not monotone");
+            max_cand = std::max(max_cand, cp[u + 1] - cp[u]);
+        }
+        const int64_t total = cp[nu];
+        int32_t lo_id = 0, hi_id = 0;
+        for (int64_t e = 0; e < total; ++e) {   // branch-free: vectorises
+            lo_id = std::min(lo_id, ci[e]);
+            hi_id = std::max(hi_id, ci[e]);
+        }
+        if (lo_id < 0 || hi_id >= n) return fail(HYPREC_E_INVALID, "candidates: item id out of range");
+        HY_TRY(cand_ptr.reserve(sizeof(int64_t) * (nu + 1)));
+        HY_TRY(cand_ids.reserve(sizeof(int32_t) * std::max<int64_t>(total, 1)));
+        CU_TRY(cudaMemcpyAsync(cand_ptr.ptr, cp, sizeof(int64_t) * (nu + 1), cudaMemcpyHostToDevice, h->stream));
+        if (total > 0)
+            CU_TRY(cudaMemcpyAsync(cand_ids.ptr, ci, sizeof(int32_t) * total, cudaMemcpyHostToDevice, h->stream));
+        cand_lo = lo;
+        cand_hi = hi;
+        cand_max = std::max<int64_t>(max_cand, 1);
+        return HYPREC_OK;
+    }
+
+    int set_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) override {
+        if (m == 0) return fail(HYPREC_E_INVALID, "set_candidates before set_train_csr");
+        if (!cp && !ci) { use_cached_cands = false; cand_lo = cand_hi = -1; return HYPREC_OK; }
+        if (lo < 0 || hi > m || lo > hi) return fail(HYPREC_E_INVALID, "set_candidates: user range outside the matrix");
+        HY_TRY(upload_candidates(lo, hi, cp, ci));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        use_cached_cands = true;
+        return HYPREC_OK;
+    }
+
     int eval_topk(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci, int cap, double* thr_out,
                   int64_t* ones_out, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "eval_topk before set_factors");
@@ -710,6 +755,7 @@ struct Engine : EngineBase {
         const bool want_topk = tidx || tval || thit;
         if (want_topk && (cap <= 0 || cap > 4096)) return fail(HYPREC_E_UNSUPPORTED, "capacity must be in [1, 4096]");
         if (ci && !cp) return fail(HYPREC_E_INVALID, "eval_topk: candidate ids without indptr");
+        if (cp && !ci) return fail(HYPREC_E_INVALID, "eval_topk: candidate indptr without ids");
         if (tef && test.rows != m) return fail(HYPREC_E_INVALID, "eval_topk: test flags need set_eval_csr first");
 
         // thresholds for every user (cheap), float64
@@ -754,22 +800,14 @@ struct Engine : EngineBase {
 
         if (want_topk) {
             int64_t max_cand = n;
+            const bool cached = !ci && cp == nullptr && cand_lo == lo && cand_hi == hi && cand_max > 0 && use_cached_cands;
             if (ci) {
-                max_cand = 0;
-                if (cp[0] != 0) return fail(HYPREC_E_INVALID, "eval_topk: cand_indptr[0] != 0");
-                for (int64_t u = 0; u < nu; ++u) {
-                    if (cp[u + 1] < cp[u]) return fail(HYPREC_E_INVALID, "eval_topk: cand_indptr not monotone");
-                    max_cand = std::max(max_cand, cp[u + 1] - cp[u]);
-                }
-                const int64_t total = cp[nu];
-                for (int64_t e = 0; e < total; ++e)
-                    if (ci[e] < 0 || ci[e] >= n) return fail(HYPREC_E_INVALID, "eval_topk: candidate id out of range");
-                HY_TRY(cand_ptr.reserve(sizeof(int64_t) * (nu + 1)));
-                HY_TRY(cand_ids.reserve(sizeof(int32_t) * std::max<int64_t>(total, 1)));
-                CU_TRY(cudaMemcpyAsync(cand_ptr.ptr, cp, sizeof(int64_t) * (nu + 1), cudaMemcpyHostToDevice, h->stream));
-                if (total > 0)
-                    CU_TRY(cudaMemcpyAsync(cand_ids.ptr, ci, sizeof(int32_t) * total, cudaMemcpyHostToDevice, h->stream));
+                HY_TRY(upload_candidates(lo, hi, cp, ci));
+                max_cand = cand_max;
+            } else if (cached) {
+                max_cand = cand_max;
             }
+            const bool have_list = ci != nullptr || cached;
             int sort_size = 2;
             while (sort_size < cap) sort_size <<= 1;
             max_cand = std::max<int64_t>(max_cand, 1);
@@ -792,8 +830,8 @@ struct Engine : EngineBase {
             a.n_items = n;
             a.user_lo = lo;
             a.user_hi = hi;
-            a.cand_indptr = ci ? cand_ptr.as<int64_t>() : nullptr;
-            a.cand_ids = ci ? cand_ids.as<int32_t>() : nullptr;
+            a.cand_indptr = have_list ? cand_ptr.as<int64_t>() : nullptr;
+            a.cand_ids = have_list ? cand_ids.as<int32_t>() : nullptr;
             a.thresholds = thresholds.as<double>();
             const bool have_full = full.rows == m;
             a.full_indptr = have_full ? full.indptr.template as<int64_t>() : nullptr;
@@ -1037,6 +1075,12 @@ int hyprec_set_eval_csr(hyprec_t* h, const int64_t* fp, const int32_t* fi, const
                         const int32_t* ti, const double* tv) {
     HY_TRY(check(h));
     return h->engine->set_eval(fp, fi, fv, tp, ti, tv);
+}
+
+int hyprec_set_candidates(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
+                          const int32_t* cand_ids) {
+    HY_TRY(check(h));
+    return h->engine->set_candidates(user_lo, user_hi, cand_indptr, cand_ids);
 }
 
 int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,

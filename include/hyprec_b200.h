@@ -109,6 +109,13 @@ int hyprec_set_eval_csr(hyprec_t* h, const int64_t* full_indptr, const int32_t* 
                         const double* full_values, const int64_t* test_indptr,
                         const int32_t* test_indices, const double* test_values);
 
+/* Candidate streams of users [user_lo, user_hi) -- evaluator.test_indices[user * (1 + fold)] in
+ * stream order (evaluator.py:225) -- copied to the device once per fold and used by every later
+ * hyprec_eval_topk call over the same user range that passes cand_indptr = cand_ids = NULL.
+ * Passing NULL, NULL here drops them (eval_topk with NULL lists then means "all items"). */
+int hyprec_set_candidates(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
+                          const int32_t* cand_ids);
+
 /* Everything get_evaluation_report() (abstract_recommender.py:100-131) derives from scores,
  * for users [user_lo, user_hi) (0, n_users for a single GPU); output arrays are indexed
  * relative to user_lo:
@@ -120,8 +127,9 @@ int hyprec_set_eval_csr(hyprec_t* h, const int64_t* full_indptr, const int32_t* 
  *                        that cell times its rounded prediction (evaluator.py:287-288)
  *   train_flags/test_flags  rounded prediction at every train / test non-zero of these users,
  *                        in CSR order (calculate_recall, evaluator.py:254-266)
- * cand_indptr is relative to user_lo (cand_indptr[0] == 0); cand_ids NULL => every item in
- * index order (recommend_items, abstract_recommender.py:200-203).  Any output may be NULL. */
+ * cand_indptr is relative to user_lo (cand_indptr[0] == 0); cand_ids NULL => the lists installed by
+ * hyprec_set_candidates for this user range, or, without those, every item in index order
+ * (recommend_items, abstract_recommender.py:200-203).  Any output may be NULL. */
 int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
                      const int32_t* cand_ids, int capacity, double* thresholds,
                      int64_t* ones_per_row, int32_t* topk_idx, double* topk_val, double* topk_hit,

@@ -73,6 +73,42 @@ def build_workload(name):
     return wl
 
 
+def build_scaled_workload(scale):
+    """BASELINE.json configs[3] shape times `scale`: 1M x 2M users x items, 2e8 positives (mean 200 per
+    user, log-normal), Zipf(0.8) item popularity, n_factors=256, float32 uniform initial factors.
+    Built directly as CSR; a random 20 % of the positives is held out (5-fold-equivalent split).
+    No dense matrices and no per-user candidate lists exist at this size: epoch-only workload."""
+    import scipy.sparse as sp
+    t0 = time.time()
+    m, n, nnz = int(1e6 * scale), int(2e6 * scale), int(2e8 * scale)
+    k, lam = 256, 0.01
+    rs = numpy.random.RandomState(20170303)
+    raw = rs.lognormal(mean=numpy.log(200.0) - 0.32, sigma=0.8, size=m)
+    deg = numpy.clip(numpy.round(raw * (nnz / raw.sum())), 1, n // 4).astype(numpy.int64)
+    p = (numpy.arange(n) + 20.0) ** -0.8
+    cdf = numpy.cumsum(p[rs.permutation(n)])
+    cdf /= cdf[-1]
+    rows = numpy.repeat(numpy.arange(m, dtype=numpy.int64), deg)
+    items = numpy.searchsorted(cdf, rs.random_sample(rows.shape[0])).astype(numpy.int64)
+    numpy.minimum(items, n - 1, out=items)
+    keys = numpy.unique(rows * n + items)                 # drops the duplicates of sampling with replacement
+    rows, items = keys // n, (keys % n).astype(numpy.int32)
+    keep = rs.random_sample(keys.shape[0]) < 0.8
+    def csr_of(mask):
+        indptr = numpy.zeros(m + 1, dtype=numpy.int64)
+        numpy.cumsum(numpy.bincount(rows[mask], minlength=m), out=indptr[1:])
+        return sp.csr_matrix((numpy.ones(int(mask.sum())), items[mask], indptr), shape=(m, n))
+    train, test = csr_of(keep), csr_of(~keep)
+    full = sp.csr_matrix((numpy.ones(keys.shape[0]), items, numpy.concatenate(([0], numpy.cumsum(numpy.bincount(rows, minlength=m))))),
+                         shape=(m, n))
+    rs4 = numpy.random.RandomState(4)
+    u0 = rs4.random_sample((m, k)).astype(numpy.float32).astype(numpy.float64)
+    v0 = rs4.random_sample((n, k)).astype(numpy.float32).astype(numpy.float64)
+    return dict(name="scaled-%g" % scale, m=m, n=n, k=k, lam=lam, folds=5, ratings=None, train=None, test=None,
+                train_csr=train, test_csr=test, full_csr=full, cand_indptr=None, cand_ids=None, u0=u0, v0=v0,
+                setup_s=time.time() - t0)
+
+
 def algorithmic_work(wl):
     """FLOPs / bytes per epoch and per launch of the solve kernel (SURVEY.md section 8d formulas)."""
     m, n, k = wl["m"], wl["n"], wl["k"]
@@ -179,9 +215,11 @@ def cpu_epoch_sample(wl, n_rows, literal, seed=0):
         t0 = time.perf_counter()
         oals.als_half_step(v, u, csc, lam, rows=items)
         t_item = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    oals.rmse_gram(u, v, wl["train_csr"])
-    t_rmse = time.perf_counter() - t0
+    t_rmse = 0.0
+    if wl["train_csr"].nnz <= 2000000:       # the Gram-identity RMSE is a small term; skipped at scaled sizes
+        t0 = time.perf_counter()
+        oals.rmse_gram(u, v, wl["train_csr"])
+        t_rmse = time.perf_counter() - t0
     epoch_ms = 1e3 * (t_user * m / len(users) + t_item * n / len(items) + t_rmse)
     return epoch_ms, dict(users=len(users), items=len(items), t_user_s=t_user, t_item_s=t_item, t_rmse_s=t_rmse)
 
@@ -207,11 +245,11 @@ def reference_arm(args, wl):
     cores = os.cpu_count()
     per_step = []
     for step in range(args.warmup + args.steps):
-        ms, detail = cpu_epoch_sample(wl, args.cpu_rows, literal=True, seed=step)
+        ms, detail = cpu_epoch_sample(wl, args.cpu_rows, literal=wl["train"] is not None, seed=step)
         if step >= args.warmup:
             per_step.append(ms)
     value = float(numpy.mean(per_step))
-    eval_rate = cpu_eval_sample(wl, 24)
+    eval_rate = cpu_eval_sample(wl, 24) if wl["cand_ids"] is not None else None
     sample = ("%d users + %d items (random rows, full width) through the literal per-row arithmetic, "
               "extrapolated x m/%d and x n/%d, + full Gram-identity RMSE; per step" %
               (detail["users"], detail["items"], detail["users"], detail["items"]))
@@ -225,10 +263,16 @@ def reference_arm(args, wl):
 
 
 def config_block(wl, args):
-    return dict(workload="%s shape %dx%d, %d train positives (5-fold split, fold 0), n_factors=%d, lambda=%g, "
-                         "theta-initialised item factors, top-200 over %d candidates/user" %
-                         (wl["name"], wl["m"], wl["n"], wl["train_csr"].nnz, wl["k"], wl["lam"],
-                          int(wl["cand_indptr"][1] - wl["cand_indptr"][0])),
+    if wl["cand_ids"] is None:
+        what = ("%s: %dx%d, %d train positives (random 80/20 split), n_factors=%d, lambda=%g, uniform float32 "
+                "initial factors, ALS epochs only (no per-user candidate lists at this size)" %
+                (wl["name"], wl["m"], wl["n"], wl["train_csr"].nnz, wl["k"], wl["lam"]))
+    else:
+        what = ("%s shape %dx%d, %d train positives (5-fold split, fold 0), n_factors=%d, lambda=%g, "
+                "theta-initialised item factors, top-200 over %d candidates/user" %
+                (wl["name"], wl["m"], wl["n"], wl["train_csr"].nnz, wl["k"], wl["lam"],
+                 int(wl["cand_indptr"][1] - wl["cand_indptr"][0])))
+    return dict(workload=what,
                 users=wl["m"], items=wl["n"], n_factors=wl["k"], train_nnz=int(wl["train_csr"].nnz),
                 precision=args.precision, l2="flushed between timed steps (384 MiB memset)",
                 parallelism="rows sharded over %d GPU(s), factor all-gather per half-step" % args.gpus)
@@ -260,9 +304,13 @@ def our_arm(args, wl):
         h.als_half_step(_native.SIDE_ITEM, lam)
         return h.rmse()
 
-    h.set_candidates(wl["cand_indptr"], wl["cand_ids"])      # per fold, like the train CSR
+    has_eval = wl["cand_ids"] is not None
+    if has_eval:
+        h.set_candidates(wl["cand_indptr"], wl["cand_ids"])      # per fold, like the train CSR
 
     def evaluate():
+        if not has_eval:
+            return None
         return h.eval_topk(200, None, None, n_train_nz=tr.nnz, n_test_nz=te.nnz)
 
     sampler = ClockSampler(local)      # started before the warm-up (same load) so that short timed
@@ -315,9 +363,10 @@ def our_arm(args, wl):
 
     # ---- metrics of the final model (reported, not timed)
     from hyprec_b200 import metrics as hm
-    lengths = (out["topk_idx"] >= 0).sum(axis=1)
-    test_likes = numpy.asarray(te.sum(axis=1)).ravel()
-    recall200 = float(hm.recall_at_x(200, out["topk_hit"], test_likes))
+    recall200 = None
+    if has_eval:
+        test_likes = numpy.asarray(te.sum(axis=1)).ravel()
+        recall200 = float(hm.recall_at_x(200, out["topk_hit"], test_likes))
 
     # ---- roofline of the dominant kernels
     work = algorithmic_work(wl)
@@ -332,9 +381,9 @@ def our_arm(args, wl):
     if os.path.exists(peaks_file):
         hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured"
     solve_gbs = work["solve_bytes_per_epoch"](elem) / (solve_ms * 1e-3) / 1e9
-    sweep_tflops = work["eval_flops"] / (per_step["count"] * 1e-3) / 1e12
-    topk_bytes = float(wl["cand_ids"].shape[0]) * (k * elem + 4) + m * 200 * 20
-    topk_gbs = topk_bytes / (per_step["topk"] * 1e-3) / 1e9
+    sweep_tflops = work["eval_flops"] / (max(per_step["count"], 1e-9) * 1e-3) / 1e12
+    topk_bytes = (float(wl["cand_ids"].shape[0]) if has_eval else 0.0) * (k * elem + 4) + m * 200 * 20
+    topk_gbs = topk_bytes / (max(per_step["topk"], 1e-9) * 1e-3) / 1e9
     roofline = dict(kernel="als_solve_rows_kernel (row systems of one epoch; %s)" %
                            ("deg x deg low-rank systems in 4 concurrent degree buckets + direct k x k for heavy rows"
                             if lowrank else "direct k x k systems, 2 launches"),
@@ -355,9 +404,10 @@ def our_arm(args, wl):
                                        bytes=topk_bytes, note="bytes gathered through L2, against the HBM copy peak")))
 
     # ---- CPU baseline on this box's host cores (bounded sample)
-    cpu_ms, cpu_detail = cpu_epoch_sample(wl, args.cpu_rows, literal=True)
+    literal = wl["train"] is not None      # the literal arithmetic needs the dense train matrix
+    cpu_ms, cpu_detail = cpu_epoch_sample(wl, args.cpu_rows, literal=literal)
     cpu_vec_ms, _ = cpu_epoch_sample(wl, 8 * args.cpu_rows, literal=False)
-    cpu_eval = cpu_eval_sample(wl, 16)
+    cpu_eval = cpu_eval_sample(wl, 16) if has_eval else None
     cpu_baseline = dict(value=cpu_ms, unit="ms", cores=os.cpu_count(), kind="port",
                         sample="%d users + %d items at full width through the reference's per-row dense arithmetic "
                                "(oracle.als.als_step_literal), extrapolated to %d + %d rows, + RMSE" %
@@ -369,10 +419,10 @@ def our_arm(args, wl):
                 vs_baseline=None, dtype="f64" if args.precision == "fp64" else "f32", data="synthetic",
                 config=config_block(wl, args), clocks=clocks,
                 e2e=dict(value=e2e_epoch_ms, unit="ms", h2d_bytes_per_step=factor_bytes + eval_h2d,
-                         d2h_bytes_per_step=factor_bytes + eval_d2h, eval_ms=e2e_eval_ms,
-                         eval_users_per_s=m / (e2e_eval_ms * 1e-3)),
+                         d2h_bytes_per_step=factor_bytes + (eval_d2h if has_eval else 0), eval_ms=e2e_eval_ms,
+                         eval_users_per_s=(m / (e2e_eval_ms * 1e-3)) if has_eval else None),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
-                eval_ms=eval_ms, eval_users_per_s=m / (eval_ms * 1e-3), wall_epoch_ms=1e3 * wall_epoch / args.steps,
+                eval_ms=eval_ms, eval_users_per_s=(m / (eval_ms * 1e-3)) if has_eval else None, wall_epoch_ms=1e3 * wall_epoch / args.steps,
                 wall_eval_ms=1e3 * wall_eval / args.steps, kernel_ms_per_step=per_step, rmse=rmse,
                 recall_at_200=recall200, setup_s=wl["setup_s"])
     print(json.dumps(line))
@@ -392,7 +442,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="citeulike-a", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="citeulike-a", choices=sorted(WORKLOADS) + ["scaled"])
+    ap.add_argument("--scale", type=float, default=0.1, help="fraction of the 1M x 2M / 2e8 config (--workload scaled)")
     ap.add_argument("--precision", default=os.environ.get("HYPREC_PRECISION", "fp64"), choices=["fp64", "fp32"])
     ap.add_argument("--cpu-rows", type=int, default=16, help="rows per side in the CPU baseline sample")
     args = ap.parse_args()
@@ -400,9 +451,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        reference_arm(args, build_workload(args.workload))
+        reference_arm(args, make_workload(args))
         return
-    our_arm(args, build_workload(args.workload))
+    our_arm(args, make_workload(args))
+
+
+def make_workload(args):
+    if args.workload == "scaled":
+        if args.precision == "fp64" and "HYPREC_PRECISION" not in os.environ:
+            args.precision = "fp32"          # configs[3] is specified in float32
+        return build_scaled_workload(args.scale)
+    return build_workload(args.workload)
 
 
 if __name__ == "__main__":

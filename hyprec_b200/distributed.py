@@ -175,17 +175,22 @@ def bench_sharded(args, wl, rank, world, local, config):
     engine = NativeEngine(h, local)
     als = ShardedALS(engine, user_bounds, item_bounds, rank, m, n)
     ulo, uhi = user_bounds[rank], user_bounds[rank + 1]
-    cp = wl["cand_indptr"][ulo:uhi + 1] - wl["cand_indptr"][ulo]
-    ci = wl["cand_ids"][wl["cand_indptr"][ulo]:wl["cand_indptr"][uhi]]
+    has_eval = wl["cand_ids"] is not None
     n_tr = int(tr.indptr[uhi] - tr.indptr[ulo])
     n_te = int(te.indptr[uhi] - te.indptr[ulo])
+    if has_eval:
+        cp = wl["cand_indptr"][ulo:uhi + 1] - wl["cand_indptr"][ulo]
+        ci = wl["cand_ids"][wl["cand_indptr"][ulo]:wl["cand_indptr"][uhi]]
+        h.set_candidates(cp, ci, ulo, uhi)
 
-    h.set_candidates(cp, ci, ulo, uhi)
+    def evaluate():
+        if has_eval:
+            return h.eval_topk(200, None, None, ulo, uhi, n_train_nz=n_tr, n_test_nz=n_te)
+        return None
 
     def step():
         rmse = als.epoch(lam)
-        out = h.eval_topk(200, None, None, ulo, uhi, n_train_nz=n_tr, n_test_nz=n_te)
-        return rmse, out
+        return rmse, evaluate()
 
     for _ in range(args.warmup):
         h.flush_l2()
@@ -205,7 +210,7 @@ def bench_sharded(args, wl, rank, world, local, config):
         rmse = als.epoch(lam)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        out = h.eval_topk(200, None, None, ulo, uhi, n_train_nz=n_tr, n_test_nz=n_te)
+        out = evaluate()
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         epoch_wall += t1 - t0
@@ -222,7 +227,8 @@ def bench_sharded(args, wl, rank, world, local, config):
     line = dict(metric="als_epoch_ms", value=epoch_ms, unit="ms", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=step_ms, higher_is_better=False, scaling="strong", vs_baseline=None,
                 dtype="f64" if args.precision == "fp64" else "f32", data="synthetic", config=config,
-                gpu_launches=int(launches.item()), rmse=rmse, eval_users_per_s=m / ((step_ms - epoch_ms) * 1e-3),
+                gpu_launches=int(launches.item()), rmse=rmse,
+                eval_users_per_s=(m / ((step_ms - epoch_ms) * 1e-3)) if has_eval else None,
                 timing="wall clock around barrier + cuda synchronize on both sides, max over ranks "
                        "(the epoch mixes library-stream kernels and NCCL broadcasts)",
                 rank0_solve_kernel_ms=solve_ms,
@@ -231,4 +237,6 @@ def bench_sharded(args, wl, rank, world, local, config):
                          note="factors stay device-resident across sharded epochs; evaluation inputs/outputs "
                               "cross PCIe every step"))
     h.close()
+    dist.barrier()
+    dist.destroy_process_group()
     return line

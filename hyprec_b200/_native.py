@@ -17,7 +17,7 @@ EXPORTS = [
     "hyprec_create", "hyprec_destroy", "hyprec_last_error", "hyprec_abi_version", "hyprec_launch_count",
     "hyprec_set_train_csr", "hyprec_set_shard", "hyprec_set_factors", "hyprec_get_factors",
     "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_rmse_terms", "hyprec_train",
-    "hyprec_predict_dense", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
+    "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
     "hyprec_flush_l2", "hyprec_probe_fma_tflops",
 ]
 
@@ -65,6 +65,7 @@ def load_library(rebuild=False):
     lib.hyprec_rmse_terms.argtypes = [vp, ctypes.POINTER(c_dbl)]
     lib.hyprec_train.argtypes = [vp, c_int, c_dbl, c_dbl, EPOCH_CB, vp, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]
     lib.hyprec_predict_dense.argtypes = [vp, vp]
+    lib.hyprec_score_dense_f32.argtypes = [vp, vp]
     lib.hyprec_set_eval_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.hyprec_set_candidates.argtypes = [vp, c_i64, c_i64, vp, vp]
     lib.hyprec_eval_topk.argtypes = [vp, c_i64, c_i64, vp, vp, c_int, vp, vp, vp, vp, vp, vp, vp]
@@ -193,6 +194,12 @@ class Handle(object):
         user_hi = self.m if user_hi is None else user_hi
         cand_indptr, cand_ids = _as(cand_indptr, numpy.int64), _as(cand_ids, numpy.int32)
         self._check(self._lib.hyprec_set_candidates(self._h, user_lo, user_hi, _ptr(cand_indptr), _ptr(cand_ids)))
+
+    def score_dense_f32(self):
+        """Tensor-core (tcgen05, 3xTF32) approximation of U.V^T as float32."""
+        out = numpy.empty((self.m, self.n), dtype=numpy.float32)
+        self._check(self._lib.hyprec_score_dense_f32(self._h, _ptr(out)))
+        return out
 
     def eval_topk(self, capacity, cand_indptr=None, cand_ids=None, user_lo=0, user_hi=None, want_counts=True,
                   want_topk=True, n_train_nz=None, n_test_nz=None):

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gram.cuh"
 #include "score.cuh"
+#include "tc_score.cuh"
 #include "topk.cuh"
 
 namespace {
@@ -89,6 +90,7 @@ struct EngineBase {
                           int64_t* ones, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) = 0;
     virtual int device_factors(void** u, void** v, int* elem) = 0;
     virtual int set_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) = 0;
+    virtual int score_dense_f32(float* out) = 0;
 };
 
 }  // namespace
@@ -101,6 +103,8 @@ struct hyprec_ctx {
     int max_smem = 0;
     int64_t launches = 0;
     bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
+    bool tc_enabled = true;        // HYPREC_TC=0 keeps the score sweep on the SIMT kernel
+    void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
     int64_t user_lo = 0, user_hi = -1, item_lo = 0, item_hi = -1;   // shard; hi < 0 => all
     // kernel timing: (begin, end) event pairs taken from a pool, harvested into per-class
     // totals after the stream has been synchronised
@@ -184,7 +188,8 @@ struct Engine : EngineBase {
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
                          &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
-                         &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7]};
+                         &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
+                         &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32};
         for (DevBuf* b : all) b->release();
         csr.release(); csc.release(); full.release(); test.release();
     }
@@ -704,6 +709,105 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+    // ---------------------------------------------------------------- tensor-core score sweep
+    DevBuf u_hi, u_lo, v_hi, v_lo, unorm, vnorm, border_cells, border_count, dense_f32;
+    static constexpr unsigned int kBorderCapacity = 8u << 20;   // cells the exact re-check can take
+    unsigned int last_border_cells = 0;
+
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+    int make_map(CUtensorMap* map, float* base, int64_t rows) {
+        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)k * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)hyprec::tc::kBK, (cuuint32_t)hyprec::tc::kBM};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = ((EncodeTiledFn)h->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(HYPREC_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        return HYPREC_OK;
+    }
+
+    bool tc_usable() const { return h->tc_enabled && k % 4 == 0 && k >= 8; }
+
+    // S~ = U V^T on tcgen05 for users [0, m): per-row counts of score >= threshold (exact, through
+    // the margin + re-check scheme) and/or the dense float32 score matrix.
+    int tc_sweep(int64_t lo, int64_t hi, bool want_counts, bool want_dense, int64_t* dense_ld_out) {
+        namespace tcn = hyprec::tc;
+        const int64_t nu = hi - lo;
+        HY_TRY(u_hi.reserve(sizeof(float) * (size_t)m * k));
+        HY_TRY(u_lo.reserve(sizeof(float) * (size_t)m * k));
+        HY_TRY(v_hi.reserve(sizeof(float) * (size_t)n * k));
+        HY_TRY(v_lo.reserve(sizeof(float) * (size_t)n * k));
+        HY_TRY(unorm.reserve(sizeof(float) * (size_t)m));
+        HY_TRY(vnorm.reserve(sizeof(float) * (size_t)n));
+        HY_TRY(border_cells.reserve(sizeof(uint2) * (size_t)kBorderCapacity));
+        HY_TRY(border_count.reserve(sizeof(unsigned int)));
+        const int64_t tiles_n = (n + tcn::kBN - 1) / tcn::kBN;
+        const int64_t dense_ld = tiles_n * tcn::kBN;
+        if (want_dense) HY_TRY(dense_f32.reserve(sizeof(float) * (size_t)nu * dense_ld));
+        if (dense_ld_out) *dense_ld_out = dense_ld;
+        const int64_t cu = nu * k, cv = n * k;
+        tcn::split_tf32_kernel<T><<<(unsigned)((cu + 255) / 256), 256, 0, h->stream>>>(U.as<T>() + lo * k, cu, u_hi.as<float>(), u_lo.as<float>());
+        tcn::split_tf32_kernel<T><<<(unsigned)((cv + 255) / 256), 256, 0, h->stream>>>(V.as<T>(), cv, v_hi.as<float>(), v_lo.as<float>());
+        tcn::row_norm_kernel<T><<<(unsigned)((nu + 7) / 8), 256, 0, h->stream>>>(U.as<T>() + lo * k, nu, k, unorm.as<float>());
+        tcn::row_norm_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(V.as<T>(), n, k, vnorm.as<float>());
+        h->launches += 4;
+        CU_TRY(cudaGetLastError());
+        CUtensorMap mu_hi, mu_lo, mv_hi, mv_lo;
+        HY_TRY(make_map(&mu_hi, u_hi.as<float>(), nu));
+        HY_TRY(make_map(&mu_lo, u_lo.as<float>(), nu));
+        HY_TRY(make_map(&mv_hi, v_hi.as<float>(), n));
+        HY_TRY(make_map(&mv_lo, v_lo.as<float>(), n));
+        CU_TRY(cudaMemsetAsync(border_count.ptr, 0, sizeof(unsigned int), h->stream));
+        tcn::ScoreArgs a;
+        a.m = nu;
+        a.n = n;
+        a.k = k;
+        a.thresholds = thresholds.as<double>() + lo;
+        a.unorm = unorm.as<float>();
+        a.vnorm = vnorm.as<float>();
+        // split residual + float32 accumulation over 3 * ceil(k / 8) tensor-core adds, doubled
+        a.margin_coef = (float)((3.0 * ((k + 7) / 8) + 32.0) * 2.0 * 1.1920929e-7);
+        a.counts = want_counts ? counts.as<unsigned long long>() : nullptr;
+        a.border_count = border_count.as<unsigned int>();
+        a.border_cells = border_cells.as<uint2>();
+        a.border_capacity = kBorderCapacity;
+        a.dense = want_dense ? dense_f32.as<float>() : nullptr;
+        a.dense_ld = dense_ld;
+        auto kern = tcn::tc_score_kernel;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcn::kSmemBytes));
+        const int64_t n_tiles = ((nu + tcn::kBM - 1) / tcn::kBM) * tiles_n;
+        const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
+        kern<<<grid, tcn::kThreads, tcn::kSmemBytes, h->stream>>>(mu_hi, mu_lo, mv_hi, mv_lo, a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        if (want_counts) {
+            tcn::recheck_cells_kernel<T><<<h->num_sms * 4, 256, 0, h->stream>>>(
+                border_cells.as<uint2>(), border_count.as<unsigned int>(), kBorderCapacity, U.as<T>() + lo * k, V.as<T>(), k,
+                thresholds.as<double>() + lo, counts.as<unsigned long long>());
+            h->launches += 1;
+            CU_TRY(cudaGetLastError());
+        }
+        return HYPREC_OK;
+    }
+
+    int score_dense_f32(float* out) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "score_dense_f32 before set_factors");
+        if (!tc_usable()) return fail(HYPREC_E_UNSUPPORTED, "tensor-core score sweep unavailable (HYPREC_TC=0, not sm_100, or n_factors % 4 != 0)");
+        int64_t ld = 0;
+        {
+            Timer t(h, HYPREC_T_SWEEP);
+            HY_TRY(tc_sweep(0, m, false, true, &ld));
+        }
+        CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * n, dense_f32.ptr, sizeof(float) * ld, sizeof(float) * n, m,
+                                 cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        return HYPREC_OK;
+    }
+
     // ---------------------------------------------------------------- evaluation
     int64_t cand_lo = -1, cand_hi = -1, cand_max = 0;
     bool use_cached_cands = false;
@@ -775,20 +879,35 @@ struct Engine : EngineBase {
         if (ones_out) {
             HY_TRY(counts.reserve(sizeof(unsigned long long) * nu));
             CU_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(unsigned long long) * nu, h->stream));
-            hyprec::SweepArgs<T> a;
-            a.user_vecs = U.as<T>();
-            a.item_vecs = V.as<T>();
-            a.k = k;
-            a.user_lo = lo;
-            a.user_hi = hi;
-            a.n_items = n;
-            a.dense_out = nullptr;
-            a.row_list = nullptr;
-            a.thresholds = thresholds.as<double>();
-            a.counts = counts.as<unsigned long long>();
-            dim3 grid((unsigned)((n + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
-                      (unsigned)((nu + hyprec::kSweepTile - 1) / hyprec::kSweepTile));
-            {
+            bool done = false;
+            if (tc_usable()) {
+                // tcgen05 sweep decides every cell outside the error margin, the rest is re-checked
+                // in float64; falls back to the SIMT sweep if the border list overflowed
+                {
+                    Timer t(h, HYPREC_T_COUNT);
+                    HY_TRY(tc_sweep(lo, hi, true, false, nullptr));
+                }
+                unsigned int border = 0;
+                CU_TRY(cudaMemcpyAsync(&border, border_count.ptr, sizeof(border), cudaMemcpyDeviceToHost, h->stream));
+                CU_TRY(cudaStreamSynchronize(h->stream));
+                last_border_cells = border;
+                done = border <= kBorderCapacity;
+                if (!done) CU_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(unsigned long long) * nu, h->stream));
+            }
+            if (!done) {
+                hyprec::SweepArgs<T> a;
+                a.user_vecs = U.as<T>();
+                a.item_vecs = V.as<T>();
+                a.k = k;
+                a.user_lo = lo;
+                a.user_hi = hi;
+                a.n_items = n;
+                a.dense_out = nullptr;
+                a.row_list = nullptr;
+                a.thresholds = thresholds.as<double>();
+                a.counts = counts.as<unsigned long long>();
+                dim3 grid((unsigned)((n + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
+                          (unsigned)((nu + hyprec::kSweepTile - 1) / hyprec::kSweepTile));
                 Timer t(h, HYPREC_T_COUNT);
                 hyprec::score_sweep_kernel<T, hyprec::kSweepCount><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(a);
                 h->launches += 1;
@@ -965,6 +1084,16 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     }
     CU_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&h->ev_base, cudaEventDisableTiming));
+    const char* tcv = getenv("HYPREC_TC");
+    h->tc_enabled = !(tcv && tcv[0] == '0') && prop.major == 10;
+    if (h->tc_enabled) {
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->encode_tiled, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || !h->encode_tiled) {
+            h->tc_enabled = false;
+            cudaGetLastError();
+        }
+    }
     const char* lr = getenv("HYPREC_LOWRANK");
     h->lowrank_enabled = !(lr && lr[0] == '0');
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);
@@ -1075,6 +1204,12 @@ int hyprec_set_eval_csr(hyprec_t* h, const int64_t* fp, const int32_t* fi, const
                         const int32_t* ti, const double* tv) {
     HY_TRY(check(h));
     return h->engine->set_eval(fp, fi, fv, tp, ti, tv);
+}
+
+int hyprec_score_dense_f32(hyprec_t* h, float* out) {
+    HY_TRY(check(h));
+    if (!out) return fail(HYPREC_E_INVALID, "hyprec_score_dense_f32: null output");
+    return h->engine->score_dense_f32(out);
 }
 
 int hyprec_set_candidates(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,

@@ -103,6 +103,12 @@ int hyprec_train(hyprec_t* h, int n_iter, double lambda, double start_error, hyp
  * written to host memory.  Meant for the API's dense return value at small shapes. */
 int hyprec_predict_dense(hyprec_t* h, double* out);
 
+/* Approximate predictions from the tensor-core sweep (tcgen05, 3xTF32 split, float32 accumulate),
+ * n_users x n_items float32 on the host: |out - u.v| <= ~3e-5 * ||u|| * ||v||.
+ * The evaluation uses this pass to decide cells far from a threshold and to pre-filter top-k
+ * candidates; exposed for tests and diagnostics.  HYPREC_E_UNSUPPORTED when unavailable. */
+int hyprec_score_dense_f32(hyprec_t* h, float* out);
+
 /* The matrices the report needs besides train: full ratings (evaluator.ratings) and test.
  * Same CSR conventions as hyprec_set_train_csr. */
 int hyprec_set_eval_csr(hyprec_t* h, const int64_t* full_indptr, const int32_t* full_indices,

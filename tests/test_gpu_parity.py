@@ -223,6 +223,41 @@ def test_eval_matches_oracle_fp64(native, m, n, k, nnz, cap):
     h.close()
 
 
+@pytest.mark.parametrize("m,n,k", [(130, 257, 200), (300, 900, 48), (64, 100, 8)])
+def test_tensor_core_scores_within_margin(native, m, n, k):
+    """tcgen05 3xTF32 sweep: |s~ - u.v| stays far inside the margin the count path uses
+    (margin_coef = (3 ceil(k/8) + 32) * 2^-22 ~ 2.5e-5 at k = 200; observed ~1e-6)."""
+    rs = numpy.random.RandomState(k)
+    u, v = rs.rand(m, k) - 0.3, rs.rand(n, k) - 0.4
+    train = sp.csr_matrix((numpy.ones(m), (numpy.arange(m), numpy.arange(m) % n)), shape=(m, n))
+    h, _ = make_handle(native, train)
+    h.set_factors(u, v)
+    approx = h.score_dense_f32()
+    scale = numpy.linalg.norm(u, axis=1)[:, None] * numpy.linalg.norm(v, axis=1)[None, :]
+    ratio = numpy.abs(approx - u.dot(v.T)) / scale
+    coef = (3.0 * ((k + 7) // 8) + 32.0) * 2.0 * 1.1920929e-7
+    print("tc ratio max %.2e (margin coef %.2e)" % (ratio.max(), coef))
+    assert ratio.max() < 0.25 * coef
+    h.close()
+
+
+@pytest.mark.parametrize("use_tc", ["1", "0"])
+def test_counts_identical_with_and_without_tensor_cores(native, monkeypatch, use_tc):
+    """The tensor-core count path (margin + float64 re-check) returns exactly the float64 counts."""
+    monkeypatch.setenv("HYPREC_TC", use_tc)
+    full, train, test, u0, v0, cands = synthetic(200, 700, 64, 6000, seed=9)
+    h, csr = make_handle(native, train)
+    h.set_factors(u0 - 0.45, v0 - 0.5)           # mixed signs: many scores close to the row mean
+    u, v = h.get_factors()
+    out = h.eval_topk(10, want_topk=False)
+    pred = u.dot(v.T)
+    thr = numpy.array([oev.row_threshold(r) for r in pred])
+    want = (pred >= thr[:, None]).sum(axis=1)
+    near = (numpy.abs(pred - thr[:, None]) <= 1e-12 * numpy.abs(thr[:, None])).sum(axis=1)
+    assert numpy.all(numpy.abs(out["ones_per_row"] - want) <= near)
+    h.close()
+
+
 def test_eval_ties_replay(native):
     """Quantised factors: exactly tied scores across the cut-off, duplicated candidates."""
     rs = numpy.random.RandomState(5)

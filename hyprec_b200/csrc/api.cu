@@ -189,7 +189,7 @@ struct Engine : EngineBase {
                          &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
-                         &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32};
+                         &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
         for (DevBuf* b : all) b->release();
         csr.release(); csc.release(); full.release(); test.release();
     }
@@ -710,7 +710,7 @@ struct Engine : EngineBase {
     }
 
     // ---------------------------------------------------------------- tensor-core score sweep
-    DevBuf u_hi, u_lo, v_hi, v_lo, unorm, vnorm, border_cells, border_count, dense_f32;
+    DevBuf u_hi, u_lo, v_hi, v_lo, unorm, vnorm, border_cells, border_count, dense_f32, vmax_buf;
     static constexpr unsigned int kBorderCapacity = 8u << 20;   // cells the exact re-check can take
     unsigned int last_border_cells = 0;
 
@@ -731,6 +731,9 @@ struct Engine : EngineBase {
     }
 
     bool tc_usable() const { return h->tc_enabled && k % 4 == 0 && k >= 8; }
+    // |s~ - s| <= coef * ||u|| * ||v||: split residual + float32 accumulation over 3 * ceil(k / 8)
+    // tensor-core adds, doubled (observed maximum on B200: 1.2e-6 at k = 200)
+    float tc_margin_coef() const { return (float)((3.0 * ((k + 7) / 8) + 32.0) * 2.0 * 1.1920929e-7); }
 
     // S~ = U V^T on tcgen05 for users [0, m): per-row counts of score >= threshold (exact, through
     // the margin + re-check scheme) and/or the dense float32 score matrix.
@@ -769,8 +772,7 @@ struct Engine : EngineBase {
         a.thresholds = thresholds.as<double>() + lo;
         a.unorm = unorm.as<float>();
         a.vnorm = vnorm.as<float>();
-        // split residual + float32 accumulation over 3 * ceil(k / 8) tensor-core adds, doubled
-        a.margin_coef = (float)((3.0 * ((k + 7) / 8) + 32.0) * 2.0 * 1.1920929e-7);
+        a.margin_coef = tc_margin_coef();
         a.counts = want_counts ? counts.as<unsigned long long>() : nullptr;
         a.border_count = border_count.as<unsigned int>();
         a.border_cells = border_cells.as<uint2>();
@@ -876,25 +878,31 @@ struct Engine : EngineBase {
         if (thr_out)
             CU_TRY(cudaMemcpyAsync(thr_out, thresholds.as<double>() + lo, sizeof(double) * nu, cudaMemcpyDeviceToHost, h->stream));
 
+        // One tensor-core sweep serves both the rounded counts (margin + float64 re-check) and the
+        // float32 score matrix the top-k kernel pre-filters with.
+        const int64_t tc_ld = ((n + hyprec::tc::kBN - 1) / hyprec::tc::kBN) * hyprec::tc::kBN;
+        const bool tc_dense = tc_usable() && want_topk && (size_t)nu * (size_t)tc_ld * sizeof(float) <= ((size_t)4 << 30);
+        bool counts_done = false;
         if (ones_out) {
             HY_TRY(counts.reserve(sizeof(unsigned long long) * nu));
             CU_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(unsigned long long) * nu, h->stream));
-            bool done = false;
-            if (tc_usable()) {
-                // tcgen05 sweep decides every cell outside the error margin, the rest is re-checked
-                // in float64; falls back to the SIMT sweep if the border list overflowed
-                {
-                    Timer t(h, HYPREC_T_COUNT);
-                    HY_TRY(tc_sweep(lo, hi, true, false, nullptr));
-                }
+        }
+        if (tc_usable() && (ones_out || tc_dense)) {
+            {
+                Timer t(h, HYPREC_T_COUNT);
+                HY_TRY(tc_sweep(lo, hi, ones_out != nullptr, tc_dense, nullptr));
+            }
+            if (ones_out) {
                 unsigned int border = 0;
                 CU_TRY(cudaMemcpyAsync(&border, border_count.ptr, sizeof(border), cudaMemcpyDeviceToHost, h->stream));
                 CU_TRY(cudaStreamSynchronize(h->stream));
                 last_border_cells = border;
-                done = border <= kBorderCapacity;
-                if (!done) CU_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(unsigned long long) * nu, h->stream));
+                counts_done = border <= kBorderCapacity;   // else: list overflowed, redo on the SIMT kernel
+                if (!counts_done) CU_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(unsigned long long) * nu, h->stream));
             }
-            if (!done) {
+        }
+        if (ones_out) {
+            if (!counts_done) {
                 hyprec::SweepArgs<T> a;
                 a.user_vecs = U.as<T>();
                 a.item_vecs = V.as<T>();
@@ -930,7 +938,7 @@ struct Engine : EngineBase {
             int sort_size = 2;
             while (sort_size < cap) sort_size <<= 1;
             max_cand = std::max<int64_t>(max_cand, 1);
-            const hyprec::TopkLayout lay = hyprec::topk_layout((int)max_cand, k, sort_size);
+            const hyprec::TopkLayout lay = hyprec::topk_layout((int)max_cand, k, sort_size, tc_dense);
             if (lay.total > (size_t)h->max_smem)
                 return fail(HYPREC_E_UNSUPPORTED, "eval_topk: candidate list too long for one CTA's shared memory");
             auto kern = hyprec::eval_topk_kernel<T>;
@@ -962,6 +970,23 @@ struct Engine : EngineBase {
             a.topk_idx = out_idx.as<int32_t>();
             a.topk_val = out_val.as<double>();
             a.topk_hit = out_hit.as<double>();
+            a.approx = nullptr;
+            a.approx_ld = tc_ld;
+            a.unorm = nullptr;
+            a.err_coef = 0.f;
+            a.vmax = nullptr;
+            a.fallbacks = nullptr;
+            if (tc_dense) {
+                HY_TRY(vmax_buf.reserve(2 * sizeof(float)));
+                CU_TRY(cudaMemsetAsync(vmax_buf.ptr, 0, 2 * sizeof(float), h->stream));
+                hyprec::max_float_kernel<<<1, 256, 0, h->stream>>>(vnorm.as<float>(), n, vmax_buf.as<float>());
+                h->launches += 1;
+                a.approx = dense_f32.as<float>();
+                a.unorm = unorm.as<float>();
+                a.err_coef = tc_margin_coef();
+                a.vmax = vmax_buf.as<float>();
+                a.fallbacks = reinterpret_cast<unsigned int*>(vmax_buf.as<float>() + 1);
+            }
             {
                 Timer t(h, HYPREC_T_TOPK);
                 kern<<<grid, hyprec::kTopkThreads, lay.total, h->stream>>>(a);

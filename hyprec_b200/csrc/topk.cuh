@@ -13,6 +13,13 @@
 // the cut-off with an 8-pass radix select over order-preserving 64-bit keys, replays the FIFO
 // only over elements >= cut-off, and bitonic-sorts the <= capacity survivors by
 // (key desc, stream position desc).
+//
+// Pre-filter (when the tensor-core sweep of tc_score.cuh has produced float32 scores s~ with
+// |s~ - s| <= E for this user): the capacity-th largest s~ minus 2E bounds the exact cut-off from
+// below, so only candidates with s~ >= that bound can be in (or tie with) the exact top; those few
+// (capacity + a handful) are re-scored exactly in float64 and go through the same selection as
+// above, in stream order.  If too many candidates pass the bound the user falls back to exact
+// scoring of every candidate.  Results are identical either way.
 #pragma once
 #include "common.cuh"
 #include "score.cuh"
@@ -20,16 +27,22 @@
 namespace hyprec {
 
 constexpr int kTopkThreads = 256;
+constexpr int kTopkMaxShortlist = 1024;   // pre-filter survivors re-scored exactly; more => exact fallback
 
 struct TopkLayout {
-    size_t off_keys, off_u, off_selkey, off_selpos, off_fifo, off_hist, total;
+    size_t off_keys, off_pos, off_k32, off_u, off_selkey, off_selpos, off_fifo, off_hist, off_scan, total;
 };
 
-HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size) {
+HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size, bool prefilter) {
     TopkLayout l;
     size_t o = 0;
     l.off_keys = o;
     o += 8 * (size_t)max_cand;
+    l.off_pos = o;
+    o += prefilter ? 4 * (size_t)max_cand : 0;
+    l.off_k32 = o;
+    o += prefilter ? 4 * (size_t)max_cand : 0;
+    o = (o + 7) & ~(size_t)7;
     l.off_u = o;
     o += 8 * (size_t)k;
     l.off_selkey = o;
@@ -40,6 +53,8 @@ HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size) {
     o += 4 * (size_t)sort_size;
     l.off_hist = o;
     o += 4 * 256;
+    l.off_scan = o;
+    o += 4 * (kTopkThreads + 1);
     l.total = (o + 15) & ~(size_t)15;
     return l;
 }
@@ -63,6 +78,13 @@ struct TopkArgs {
     int32_t* topk_idx;            // [n_local_users][capacity], -1 padded
     double* topk_val;
     double* topk_hit;
+    // pre-filter inputs (null approx => exact scoring of every candidate)
+    const float* approx;          // [n_local_users][approx_ld] tensor-core scores
+    int64_t approx_ld;
+    const float* unorm;           // [n_local_users] ||u|| (rounded up)
+    float err_coef;               // E = err_coef * ||u|| * vmax
+    const float* vmax;            // max_i ||v_i||
+    unsigned int* fallbacks;      // users that fell back to exact scoring (diagnostic)
 };
 
 // order-preserving map double -> uint64 (larger score <=> larger key)
@@ -75,22 +97,94 @@ __device__ __forceinline__ double key_score(unsigned long long key) {
     unsigned long long b = (key & 0x8000000000000000ull) ? (key & 0x7fffffffffffffffull) : ~key;
     return __longlong_as_double((long long)b);
 }
+__device__ __forceinline__ unsigned int float_key(float s) {
+    s = s + 0.0f;
+    unsigned int b;
+    memcpy(&b, &s, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned int key) {
+    unsigned int b = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    float s;
+    memcpy(&s, &b, 4);
+    return s;
+}
 // a is listed before b
 __device__ __forceinline__ bool topk_before(unsigned long long ka, int pa, unsigned long long kb, int pb) {
     return ka > kb || (ka == kb && pa > pb);
+}
+
+// The kth largest of keys[0..count) by most-significant-digit radix select (8 bits per pass).
+// Returns the key; *need = how many elements equal to it belong to the top kth, *n_equal = how
+// many elements equal it.  All threads of the CTA call it; hist has 256 words; s_* are shared.
+template <typename KeyT>
+__device__ __forceinline__ KeyT radix_select(const KeyT* keys, int count, int kth, unsigned* hist, int* s_digit,
+                                            int* s_need, int* s_count, int* need_out, int* n_equal_out) {
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    KeyT prefix = 0, mask = 0;
+    int need = kth, n_equal = 0;
+    for (int shift = 8 * (int)sizeof(KeyT) - 8; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < count; i += kTopkThreads) {
+            const KeyT key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned loc[8], tot = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                loc[b] = hist[8 * lane + b];
+                tot += loc[b];
+            }
+            unsigned suf = tot;   // suffix sum over lanes >= lane (bins from the top)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_down_sync(0xffffffffu, suf, d);
+                if (lane + d < 32) suf += o;
+            }
+            unsigned above = __shfl_down_sync(0xffffffffu, suf, 1);
+            if (lane == 31) above = 0;
+            if (suf >= (unsigned)need && above < (unsigned)need) {
+                unsigned cum = above;
+                for (int b = 7; b >= 0; --b) {
+                    if (cum + loc[b] >= (unsigned)need) {
+                        *s_digit = 8 * lane + b;
+                        *s_need = need - (int)cum;
+                        *s_count = (int)loc[b];
+                        break;
+                    }
+                    cum += loc[b];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (KeyT)(*s_digit) << shift;
+        mask |= (KeyT)0xff << shift;
+        need = *s_need;
+        n_equal = *s_count;
+    }
+    *need_out = need;
+    *n_equal_out = n_equal;
+    return prefix;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) {
     HYPREC_DYN_SMEM(smem_raw);
     __shared__ int s_digit, s_need, s_count, s_nsel;
-    const TopkLayout lay = topk_layout(p.max_cand, p.k, p.sort_size);
+    const bool prefilter = p.approx != nullptr;
+    const TopkLayout lay = topk_layout(p.max_cand, p.k, p.sort_size, prefilter);
     unsigned long long* keys = (unsigned long long*)(smem_raw + lay.off_keys);
+    int* posarr = (int*)(smem_raw + lay.off_pos);
+    unsigned int* keys32 = (unsigned int*)(smem_raw + lay.off_k32);
     double* uvec = (double*)(smem_raw + lay.off_u);
     unsigned long long* selkey = (unsigned long long*)(smem_raw + lay.off_selkey);
     int* selpos = (int*)(smem_raw + lay.off_selpos);
     int* fifo = (int*)(smem_raw + lay.off_fifo);
     unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
+    int* scan = (int*)(smem_raw + lay.off_scan);
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int k = p.k, cap = p.capacity, P = p.sort_size;
 
@@ -103,92 +197,91 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
         if (tid == 0) s_nsel = 0;
         __syncthreads();
 
-        // ---- scores: one warp per candidate, coalesced read of the item's factor row ---------
-        for (int c = warp; c < ncand; c += kTopkThreads / 32) {
+        // ---- scores -------------------------------------------------------------------------------
+        // np elements end up in keys[] (exact float64 scores); element j is stream position
+        // (shortlist ? posarr[j] : j).  Both orders are ascending in stream position.
+        int np = ncand;
+        bool shortlist = false;
+        if (prefilter && ncand > cap) {
+            const float* arow = p.approx + ul * p.approx_ld;
+            for (int c = tid; c < ncand; c += kTopkThreads) {
+                const int64_t item = p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c;
+                keys32[c] = float_key(arow[item]);
+            }
+            __syncthreads();
+            int need32, equal32;
+            const unsigned int kth = radix_select<unsigned int>(keys32, ncand, cap, hist, &s_digit, &s_need, &s_count,
+                                                                &need32, &equal32);
+            // every exact top / cut-off-tied candidate has s~ >= (capacity-th largest s~) - 2E
+            const double err = (double)p.err_coef * (double)p.unorm[ul] * (double)(*p.vmax);
+            const double bound = (double)key_float(kth) - 2.0 * err;
+            // ordered compaction of the survivors (stream order is part of the tie rule)
+            const int chunk = (ncand + kTopkThreads - 1) / kTopkThreads;
+            const int c_lo = tid * chunk, c_hi = c_lo + chunk < ncand ? c_lo + chunk : ncand;
+            int mine = 0;
+            for (int c = c_lo; c < c_hi; ++c) mine += ((double)key_float(keys32[c]) >= bound) ? 1 : 0;
+            scan[tid + 1] = mine;
+            if (tid == 0) scan[0] = 0;
+            __syncthreads();
+            if (tid == 0)
+                for (int t = 1; t <= kTopkThreads; ++t) scan[t] += scan[t - 1];
+            __syncthreads();
+            const int total = scan[kTopkThreads];
+            if (total <= kTopkMaxShortlist && total <= p.max_cand) {
+                int at = scan[tid];
+                for (int c = c_lo; c < c_hi; ++c)
+                    if ((double)key_float(keys32[c]) >= bound) posarr[at++] = c;
+                np = total;
+                shortlist = true;
+            } else if (tid == 0 && p.fallbacks) {
+                atomicAdd(p.fallbacks, 1u);
+            }
+            __syncthreads();
+        }
+        // exact float64 scores: one warp per element, coalesced read of the item's factor row
+        for (int j = warp; j < np; j += kTopkThreads / 32) {
+            const int c = shortlist ? posarr[j] : j;
             const int64_t item = p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c;
             const double s = warp_dot(uvec, p.item_vecs + item * k, k, lane);
-            if (lane == 0) keys[c] = score_key(s);
+            if (lane == 0) keys[j] = score_key(s);
         }
         __syncthreads();
 
-        // ---- cut-off = capacity-th largest key (radix select, 8 bits per pass) ---------------
-        unsigned long long prefix = 0, mask = 0;
+        // ---- cut-off = capacity-th largest key ------------------------------------------------
+        unsigned long long cutoff = 0;
         int need = cap;          // how many elements equal to the cut-off are kept
         int n_equal = 0;         // how many elements equal the cut-off
-        const bool select = ncand > cap;
-        if (select) {
-            for (int pass = 0; pass < 8; ++pass) {
-                const int shift = 56 - 8 * pass;
-                hist[tid] = 0;
-                __syncthreads();
-                for (int i = tid; i < ncand; i += kTopkThreads) {
-                    const unsigned long long key = keys[i];
-                    if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    unsigned loc[8], tot = 0;
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        loc[b] = hist[8 * lane + b];
-                        tot += loc[b];
-                    }
-                    unsigned suf = tot;   // suffix sum over lanes >= lane (bins from the top)
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const unsigned o = __shfl_down_sync(0xffffffffu, suf, d);
-                        if (lane + d < 32) suf += o;
-                    }
-                    unsigned above = __shfl_down_sync(0xffffffffu, suf, 1);
-                    if (lane == 31) above = 0;
-                    if (suf >= (unsigned)need && above < (unsigned)need) {
-                        unsigned cum = above;
-                        for (int b = 7; b >= 0; --b) {
-                            if (cum + loc[b] >= (unsigned)need) {
-                                s_digit = 8 * lane + b;
-                                s_need = need - (int)cum;
-                                s_count = (int)loc[b];
-                                break;
-                            }
-                            cum += loc[b];
-                        }
-                    }
-                }
-                __syncthreads();
-                prefix |= (unsigned long long)s_digit << shift;
-                mask |= 0xffull << shift;
-                need = s_need;
-                n_equal = s_count;
-            }
-        }
+        const bool select = np > cap;
+        if (select)
+            cutoff = radix_select<unsigned long long>(keys, np, cap, hist, &s_digit, &s_need, &s_count, &need, &n_equal);
 
         // ---- survivors -------------------------------------------------------------------------
         const bool replay = select && n_equal != need;   // tie straddles the cut-off
-        for (int i = tid; i < ncand; i += kTopkThreads) {
+        for (int i = tid; i < np; i += kTopkThreads) {
             const unsigned long long key = keys[i];
-            if (!select || key > prefix || (!replay && key == prefix)) {
+            if (!select || key > cutoff || (!replay && key == cutoff)) {
                 const int slot = atomicAdd(&s_nsel, 1);
                 selkey[slot] = key;
-                selpos[slot] = i;
+                selpos[slot] = shortlist ? posarr[i] : i;
             }
         }
         __syncthreads();
         if (replay && tid == 0) {
             // stream order matters only among elements >= cut-off
             int held = 0, head = 0, tail = 0;
-            for (int i = 0; i < ncand; ++i) {
+            for (int i = 0; i < np; ++i) {
                 const unsigned long long key = keys[i];
-                if (key > prefix) {
+                if (key > cutoff) {
                     if (held == cap) ++head; else ++held;
-                } else if (key == prefix && held < cap) {
-                    fifo[tail % P] = i;
+                } else if (key == cutoff && held < cap) {
+                    fifo[tail % P] = shortlist ? posarr[i] : i;
                     ++tail;
                     ++held;
                 }
             }
             int slot = s_nsel;
             for (int q = head; q < tail; ++q) {
-                selkey[slot] = prefix;
+                selkey[slot] = cutoff;
                 selpos[slot] = fifo[q % P];
                 ++slot;
             }
@@ -244,6 +337,20 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
             if (p.topk_hit) p.topk_hit[ul * cap + r] = hit;
         }
     }
+}
+
+// max of a float array (single block), for the uniform error bound of the pre-filter
+__global__ void max_float_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
+    __shared__ float red[256];
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = in[i] > s ? in[i] : s;
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] = red[threadIdx.x + w] > red[threadIdx.x] ? red[threadIdx.x + w] : red[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
 }
 
 }  // namespace hyprec

@@ -136,7 +136,7 @@ template <typename T>
 static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
                       const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
                       const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
-                      int grid) {
+                      int grid, double prefilter_coef = 0.0) {
     std::vector<double> part(2 * (size_t)k), colsum(k);
     const int64_t per = (n + 1) / 2;
     emu::launch(dim3(2), dim3(64), 0, [&]() { colsum_partial_kernel<T>(V, n, k, per, part.data()); });
@@ -160,13 +160,39 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
     }
     int sort_size = 2;
     while (sort_size < cap) sort_size <<= 1;
-    TopkLayout lay = topk_layout((int)max_cand, k, sort_size);
+    // optional pre-filter: float32 scores as the tensor-core sweep would provide them (here: the
+    // float64 product rounded to float32 and perturbed inside the error bound)
+    std::vector<float> approx, unorm_v(nu, 0.f);
+    float vmax[2] = {0.f, 0.f};
+    const int64_t ld = n + 3;
+    if (prefilter_coef > 0.0) {
+        approx.assign((size_t)nu * ld, 0.f);
+        for (int64_t j = 0; j < n; ++j) {
+            double s = 0;
+            for (int c = 0; c < k; ++c) s += (double)V[j * k + c] * (double)V[j * k + c];
+            vmax[0] = std::max(vmax[0], (float)(std::sqrt(s) * 1.0001));
+        }
+        for (int64_t u = 0; u < nu; ++u) {
+            double s = 0;
+            for (int c = 0; c < k; ++c) s += (double)U[(lo + u) * k + c] * (double)U[(lo + u) * k + c];
+            unorm_v[u] = (float)(std::sqrt(s) * 1.0001);
+            for (int64_t j = 0; j < n; ++j) {
+                double d = 0;
+                for (int c = 0; c < k; ++c) d += (double)U[(lo + u) * k + c] * (double)V[j * k + c];
+                const double wiggle = 0.9 * prefilter_coef * unorm_v[u] * vmax[0] * (((u * 131 + j * 7) % 21) - 10) / 10.0;
+                approx[(size_t)u * ld + j] = (float)(d + wiggle);
+            }
+        }
+    }
+    TopkLayout lay = topk_layout((int)max_cand, k, sort_size, prefilter_coef > 0.0);
     TopkArgs<T> a;
     a.user_vecs = U; a.item_vecs = V; a.k = k; a.n_items = n; a.user_lo = lo; a.user_hi = hi;
     a.cand_indptr = ci ? cp : nullptr; a.cand_ids = ci; a.thresholds = thr;
     a.full_indptr = fp; a.full_indices = fi; a.full_values = fv;
     a.capacity = cap; a.sort_size = sort_size; a.max_cand = (int)max_cand;
     a.topk_idx = tidx; a.topk_val = tval; a.topk_hit = thit;
+    a.approx = prefilter_coef > 0.0 ? approx.data() : nullptr; a.approx_ld = ld; a.unorm = unorm_v.data();
+    a.err_coef = (float)prefilter_coef; a.vmax = vmax; a.fallbacks = reinterpret_cast<unsigned int*>(vmax + 1);
     emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T>(a); });
 }
 
@@ -199,6 +225,13 @@ void emu_eval_f64(const double* U, const double* V, int64_t m, int64_t n, int k,
                   const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
                   const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit, int grid) {
     eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid);
+}
+
+void emu_eval_prefilter_f64(const double* U, const double* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
+                            const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
+                            const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
+                            int grid, double prefilter_coef) {
+    eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid, prefilter_coef);
 }
 
 void emu_predict_f64(const double* U, const double* V, int64_t m, int64_t n, int k, double* out) {

@@ -188,6 +188,40 @@ def test_eval_kernel_ties_and_full_catalogue(emu):
             assert list(tidx[u_id][:len(want)]) == want
 
 
+@pytest.mark.parametrize("coef", [1e-6, 3e-3, 0.5])
+def test_eval_prefilter_is_exact(emu, coef):
+    """Top-k through the pre-filter (approximate float32 scores perturbed up to 0.9 E, shortlist,
+    exact float64 re-score) equals the streamed reference, for a tight bound, a loose bound (large
+    shortlist) and a useless bound (every user falls back to exact scoring of all candidates);
+    quantised factors give exactly tied scores across the cut-off."""
+    rs = numpy.random.RandomState(int(coef * 1e6) % 1000)
+    m, n, k, cap = 6, 1500, 6, 20
+    u = numpy.round((rs.rand(m, k) - 0.3) * 4) / 4
+    v = numpy.round((rs.rand(n, k) - 0.3) * 4) / 4
+    u[2] = 0
+    full = (rs.rand(m, n) < 0.2).astype(numpy.float64)
+    csr = oals.to_csr(full)
+    fp, fi, fv = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
+    for cands in (None, [rs.randint(0, n, size=1200) for _ in range(m)]):
+        if cands is None:
+            cp = ci = None
+        else:
+            cp = numpy.zeros(m + 1, numpy.int64)
+            cp[1:] = numpy.cumsum([len(c) for c in cands])
+            ci = numpy.concatenate(cands).astype(numpy.int32)
+        thr, ones = numpy.zeros(m), numpy.zeros(m, numpy.int64)
+        tidx = numpy.zeros((m, cap), numpy.int32)
+        tval, thit = numpy.zeros((m, cap)), numpy.zeros((m, cap))
+        emu.emu_eval_prefilter_f64(_ptr(u), _ptr(v), I64(m), I64(n), k, I64(0), I64(m), _ptr(cp), _ptr(ci), cap,
+                                   _ptr(fp), _ptr(fi), _ptr(fv), _ptr(thr), None, _ptr(tidx), _ptr(tval), _ptr(thit),
+                                   3, DBL(coef))
+        for u_id in range(m):
+            ids = numpy.arange(n) if cands is None else cands[u_id]
+            want, vals = oev.top_recommendations_stream(ids, u[u_id].dot(v[ids].T), cap)
+            assert list(tidx[u_id][:len(want)]) == want, (coef, u_id)
+            assert numpy.allclose(tval[u_id][:len(want)], vals, rtol=1e-12, atol=1e-15)
+
+
 def test_nz_flags_kernel(emu, als_cases):
     fold = golden_folds(als_cases["als_kfold_toy"])[0]
     u, v, test = fold["u"], fold["v"], fold["test"]

@@ -47,19 +47,23 @@ struct SolveLayout {
 };
 
 // Shared-memory plan for systems of dimension <= max_dim (k in direct mode, the largest row
-// degree of the launch in low-rank mode).  chunk_rows (>= 8: the buffer doubles as the panel
-// buffer) rank-1 vectors are staged at a time; rows of the staging buffer are ystride apart
+// degree of the launch in low-rank mode) held as ts x ts tiles (8 for the k x k systems; 4 for
+// the small low-rank systems, where 8 x 8 tiles would leave most threads without a tile and
+// serialise 64 FMAs per rank-1 vector in the few that have one).  chunk_rows (>= ts: the buffer
+// doubles as the panel buffer) rank-1 vectors are staged at a time; rows of the staging buffer are ystride apart
 // (odd, so the low-rank gather's column-wise stores spread over banks).
-HYPREC_HD SolveLayout solve_layout(int max_dim, int chunk_rows, bool a_in_smem, size_t elem) {
+HYPREC_HD int aug_blocks_ts(int dim, int ts) { return (dim + 1 + ts - 1) / ts; }
+
+HYPREC_HD SolveLayout solve_layout(int ts, int max_dim, int chunk_rows, bool a_in_smem, size_t elem) {
     SolveLayout l;
-    l.nb = aug_blocks(max_dim);
+    l.nb = aug_blocks_ts(max_dim, ts);
     l.n_tiles = tri(l.nb);
-    l.kpad = l.nb * kTile;
+    l.kpad = l.nb * ts;
     l.ystride = l.kpad + 1;
     l.chunk_rows = chunk_rows;
     size_t o = 0;
     l.off_a = o;
-    if (a_in_smem) o += elem * (size_t)kTileElems * l.n_tiles;
+    if (a_in_smem) o += elem * (size_t)(ts * ts) * l.n_tiles;
     l.off_y = o;
     o += elem * (size_t)chunk_rows * l.ystride;
     l.off_z = o;
@@ -115,33 +119,33 @@ __device__ __forceinline__ float inv_sqrt(float x) { return rsqrtf(x); }
 // Cholesky of the leading nvalid x nvalid block of an 8x8 tile held in registers (lower
 // triangle); the rows below it are carried along as in a panel factorisation (that is where the
 // right-hand-side row picks up its part of z).  The diagonal is left INVERTED.
-template <typename T>
-__device__ __forceinline__ void chol8_factor(T (&a)[kTile][kTile], int nvalid) {
+template <typename T, int TS>
+__device__ __forceinline__ void chol8_factor(T (&a)[TS][TS], int nvalid) {
 #pragma unroll
-    for (int j = 0; j < kTile; ++j) {
+    for (int j = 0; j < TS; ++j) {
         if (j < nvalid) {
             const T inv = inv_sqrt(a[j][j]);
             a[j][j] = inv;
 #pragma unroll
-            for (int i = j + 1; i < kTile; ++i) a[i][j] *= inv;
+            for (int i = j + 1; i < TS; ++i) a[i][j] *= inv;
 #pragma unroll
-            for (int l = j + 1; l < kTile; ++l)
+            for (int l = j + 1; l < TS; ++l)
 #pragma unroll
-                for (int i = l; i < kTile; ++i) a[i][l] -= a[i][j] * a[l][j];
+                for (int i = l; i < TS; ++i) a[i][l] -= a[i][j] * a[l][j];
         }
     }
 }
 
 // In-place inverse of the leading lower-triangular nvalid x nvalid block (diagonal already
 // inverted by chol8_factor): column j of L^-1 is -L22^-1 L[j+1:, j] / L[j][j].
-template <typename T>
-__device__ __forceinline__ void chol8_invert(T (&a)[kTile][kTile], int nvalid) {
+template <typename T, int TS>
+__device__ __forceinline__ void chol8_invert(T (&a)[TS][TS], int nvalid) {
 #pragma unroll
-    for (int j = kTile - 1; j >= 0; --j) {
+    for (int j = TS - 1; j >= 0; --j) {
         if (j < nvalid) {
             const T njj = -a[j][j];
 #pragma unroll
-            for (int i = kTile - 1; i > j; --i) {
+            for (int i = TS - 1; i > j; --i) {
                 if (i < nvalid) {
                     T s = T(0);
 #pragma unroll
@@ -158,47 +162,47 @@ __device__ __forceinline__ void chol8_invert(T (&a)[kTile][kTile], int nvalid) {
 // multiple of 8 and p == k / 8) its z entries are published first.  Runs in ONE thread; kept out
 // of line so that its register needs do not spill the callers' accumulator tiles.
 #ifndef HYPREC_EMU
-template <typename T>
+template <typename T, int TS>
 __device__ __noinline__ void factor_diag_tile(T* A, int NT, int t, int p, int k, T* zvec) {
 #else
-template <typename T>
+template <typename T, int TS>
 void factor_diag_tile(T* A, int NT, int t, int p, int k, T* zvec) {
 #endif
-    int nvalid = k - p * kTile;
-    if (nvalid > kTile) nvalid = kTile;
+    int nvalid = k - p * TS;
+    if (nvalid > TS) nvalid = TS;
     if (nvalid <= 0) return;
-    T a[kTile][kTile];
+    T a[TS][TS];
 #pragma unroll
-    for (int r = 0; r < kTile; ++r)
+    for (int r = 0; r < TS; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = A[(size_t)(r * kTile + c) * NT + t];
-    chol8_factor(a, nvalid);
-    if (nvalid < kTile) {
+        for (int c = 0; c <= r; ++c) a[r][c] = A[(size_t)(r * TS + c) * NT + t];
+    chol8_factor<T, TS>(a, nvalid);
+    if (nvalid < TS) {
 #pragma unroll
-        for (int r = 1; r < kTile; ++r)
+        for (int r = 1; r < TS; ++r)
             if (r == nvalid) {
 #pragma unroll
-                for (int j = 0; j < r; ++j) zvec[p * kTile + j] = a[r][j];
+                for (int j = 0; j < r; ++j) zvec[p * TS + j] = a[r][j];
             }
     }
-    chol8_invert(a, nvalid);
+    chol8_invert<T, TS>(a, nvalid);
 #pragma unroll
-    for (int r = 0; r < kTile; ++r)
+    for (int r = 0; r < TS; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) A[(size_t)(r * kTile + c) * NT + t] = a[r][c];
+        for (int c = 0; c <= r; ++c) A[(size_t)(r * TS + c) * NT + t] = a[r][c];
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveArgs<T> p) {
+template <typename T, int TS>
+__global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows_kernel(SolveArgs<T> p) {
     HYPREC_DYN_SMEM(smem_raw);
     __shared__ long long s_row;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid % 32, warp = tid / 32, nwarps = nthreads / 32;
     const int k = p.k;
     const bool lowrank = p.lowrank != 0;
-    const SolveLayout lay = solve_layout(p.max_dim, p.chunk_rows, p.a_scratch == nullptr, sizeof(T));
+    const SolveLayout lay = solve_layout(TS, p.max_dim, p.chunk_rows, p.a_scratch == nullptr, sizeof(T));
     const int CH = lay.chunk_rows, ystride = lay.ystride;
-    T* A = p.a_scratch ? p.a_scratch + (size_t)blockIdx.x * kTileElems * lay.n_tiles : (T*)(smem_raw + lay.off_a);
+    T* A = p.a_scratch ? p.a_scratch + (size_t)blockIdx.x * (TS * TS) * lay.n_tiles : (T*)(smem_raw + lay.off_a);
     T* ybuf = (T*)(smem_raw + lay.off_y);
     T* zvec = (T*)(smem_raw + lay.off_z);
     T* xvec = (T*)(smem_raw + lay.off_x);
@@ -232,8 +236,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
         // dimension of this row's system, number of rank-1 vectors that build it
         const int dim = lowrank ? deg : k;
         const int nvec = lowrank ? k : deg;
-        const int nb = aug_blocks(dim), NT = tri(nb), kpad = nb * kTile;
-        const int nbk = (dim + kTile - 1) / kTile;   // block columns that hold system columns
+        const int nb = aug_blocks_ts(dim, TS), NT = tri(nb), kpad = nb * TS;
+        const int nbk = (dim + TS - 1) / TS;   // block columns that hold system columns
 
         if (lowrank) {
             // positives' ids; right-hand side r - 0.9 * Q_r p kept in xvec until the finalize step
@@ -266,21 +270,22 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                         T v = T(0);
                         if (col < k) v = p.fixed[src + col];
                         else if (col == k) v = rating;
-                        dst[(col % kTile) * nb + col / kTile] = v;
+                        dst[(col % TS) * nb + col / TS] = v;
                     }
                 }
             } else {
                 // vector t = column c0+t of Q restricted to this row's positives: one warp per
                 // positive reads cr consecutive values of its Q row
+#pragma unroll 4
                 for (int i = warp; i < dim; i += nwarps) {
                     const T* src = p.fixed + (int64_t)idxs[i] * k + c0;
-                    const int pos = (i % kTile) * nb + i / kTile;
+                    const int pos = (i % TS) * nb + i / TS;
                     for (int t = lane; t < cr; t += 32) ybuf[(size_t)t * ystride + pos] = src[t];
                 }
                 const int npad = kpad - dim;   // augmented slot + padding carry zeros
                 for (int e = tid; e < cr * npad; e += nthreads) {
                     const int t = e / npad, i = dim + e % npad;
-                    ybuf[(size_t)t * ystride + (i % kTile) * nb + i / kTile] = T(0);
+                    ybuf[(size_t)t * ystride + (i % TS) * nb + i / TS] = T(0);
                 }
             }
             __syncthreads();
@@ -288,44 +293,44 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
 #pragma unroll 1
             for (int q = tid; q < NT; q += nthreads) {
                 const int bi = tmap[2 * q], bj = tmap[2 * q + 1];
-                T acc[kTile][kTile];
+                T acc[TS][TS];
                 if (ch == 0) {
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r)
+                    for (int r = 0; r < TS; ++r)
 #pragma unroll
-                        for (int c = 0; c < kTile; ++c) acc[r][c] = T(0);
+                        for (int c = 0; c < TS; ++c) acc[r][c] = T(0);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r)
+                    for (int r = 0; r < TS; ++r)
 #pragma unroll
-                        for (int c = 0; c < kTile; ++c) acc[r][c] = A[(size_t)(r * kTile + c) * NT + q];
+                        for (int c = 0; c < TS; ++c) acc[r][c] = A[(size_t)(r * TS + c) * NT + q];
                 }
 #pragma unroll 2
                 for (int t = 0; t < cr; ++t) {
                     const T* yrow = ybuf + (size_t)t * ystride;
-                    T vi[kTile], vj[kTile];
+                    T vi[TS], vj[TS];
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r) vi[r] = yrow[r * nb + bi];
+                    for (int r = 0; r < TS; ++r) vi[r] = yrow[r * nb + bi];
 #pragma unroll
-                    for (int c = 0; c < kTile; ++c) vj[c] = yrow[c * nb + bj];
+                    for (int c = 0; c < TS; ++c) vj[c] = yrow[c * nb + bj];
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r)
+                    for (int r = 0; r < TS; ++r)
 #pragma unroll
-                        for (int c = 0; c < kTile; ++c) acc[r][c] += vi[r] * vj[c];
+                        for (int c = 0; c < TS; ++c) acc[r][c] += vi[r] * vj[c];
                 }
                 if (last) {
                     // direct:   A = base + 0.9 * sum y y^T, rhs row = sum r y (+ lambda theta)
                     // low-rank: S = I + 0.9 * Q_r Q_r^T,    rhs row = r - 0.9 Q_r p
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r) {
-                        const int i = bi * kTile + r;
+                    for (int r = 0; r < TS; ++r) {
+                        const int i = bi * TS + r;
 #pragma unroll
-                        for (int c = 0; c < kTile; ++c) {
-                            const int j = bj * kTile + c;
+                        for (int c = 0; c < TS; ++c) {
+                            const int j = bj * TS + c;
                             T v;
                             if (i < dim) {
                                 const T base = lowrank ? (i == j ? T(1) : T(0))
-                                                       : p.base[(size_t)(r * kTile + c) * NT + q];
+                                                       : p.base[(size_t)(r * TS + c) * NT + q];
                                 v = base + pos_scale * acc[r][c];
                             } else if (i == dim) {
                                 if (lowrank) {
@@ -342,10 +347,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < kTile; ++r)
+                for (int r = 0; r < TS; ++r)
 #pragma unroll
-                    for (int c = 0; c < kTile; ++c) A[(size_t)(r * kTile + c) * NT + q] = acc[r][c];
-                if (last && q == 0) factor_diag_tile(A, NT, 0, 0, dim, zvec);
+                    for (int c = 0; c < TS; ++c) A[(size_t)(r * TS + c) * NT + q] = acc[r][c];
+                if (last && q == 0) factor_diag_tile<T, TS>(A, NT, 0, 0, dim, zvec);
             }
             __syncthreads();
         }
@@ -355,27 +360,27 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
             // panel solve: rows below the diagonal tile (system rows and the rhs row `dim`) times
             // the transposed inverse of the diagonal tile's factor
             const int tdiag = tile_id(pnl, pnl);
-            for (int i = kTile * (pnl + 1) + tid; i <= dim; i += nthreads) {
-                const int r = i % kTile;
-                const int t = tile_id(i / kTile, pnl);
-                T x[kTile], y[kTile];
+            for (int i = TS * (pnl + 1) + tid; i <= dim; i += nthreads) {
+                const int r = i % TS;
+                const int t = tile_id(i / TS, pnl);
+                T x[TS], y[TS];
 #pragma unroll
-                for (int c = 0; c < kTile; ++c) x[c] = A[(size_t)(r * kTile + c) * NT + t];
+                for (int c = 0; c < TS; ++c) x[c] = A[(size_t)(r * TS + c) * NT + t];
 #pragma unroll
-                for (int c = 0; c < kTile; ++c) {
+                for (int c = 0; c < TS; ++c) {
                     T s = T(0);
 #pragma unroll
-                    for (int j = 0; j <= c; ++j) s += x[j] * A[(size_t)(c * kTile + j) * NT + tdiag];
+                    for (int j = 0; j <= c; ++j) s += x[j] * A[(size_t)(c * TS + j) * NT + tdiag];
                     y[c] = s;
                 }
 #pragma unroll
-                for (int c = 0; c < kTile; ++c) {
-                    A[(size_t)(r * kTile + c) * NT + t] = y[c];
-                    ybuf[(size_t)c * ystride + r * nb + i / kTile] = y[c];   // panel, row 8*b+r at [r*nb+b]
+                for (int c = 0; c < TS; ++c) {
+                    A[(size_t)(r * TS + c) * NT + t] = y[c];
+                    ybuf[(size_t)c * ystride + r * nb + i / TS] = y[c];   // panel, row 8*b+r at [r*nb+b]
                 }
                 if (i == dim) {
 #pragma unroll
-                    for (int c = 0; c < kTile; ++c) zvec[pnl * kTile + c] = y[c];
+                    for (int c = 0; c < TS; ++c) zvec[pnl * TS + c] = y[c];
                 }
             }
             __syncthreads();
@@ -386,52 +391,52 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
             for (int q = tid; q < ntiles; q += nthreads) {
                 const int bi = pnl + 1 + tmap[2 * q], bj = pnl + 1 + tmap[2 * q + 1];
                 const int t = tile_id(bi, bj);
-                T acc[kTile][kTile];
+                T acc[TS][TS];
 #pragma unroll
-                for (int r = 0; r < kTile; ++r)
+                for (int r = 0; r < TS; ++r)
 #pragma unroll
-                    for (int c = 0; c < kTile; ++c) acc[r][c] = A[(size_t)(r * kTile + c) * NT + t];
+                    for (int c = 0; c < TS; ++c) acc[r][c] = A[(size_t)(r * TS + c) * NT + t];
 #pragma unroll 2
-                for (int kk = 0; kk < kTile; ++kk) {
+                for (int kk = 0; kk < TS; ++kk) {
                     const T* prow = ybuf + (size_t)kk * ystride;
-                    T li[kTile], lj[kTile];
+                    T li[TS], lj[TS];
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r) li[r] = prow[r * nb + bi];
+                    for (int r = 0; r < TS; ++r) li[r] = prow[r * nb + bi];
 #pragma unroll
-                    for (int c = 0; c < kTile; ++c) lj[c] = prow[c * nb + bj];
+                    for (int c = 0; c < TS; ++c) lj[c] = prow[c * nb + bj];
 #pragma unroll
-                    for (int r = 0; r < kTile; ++r)
+                    for (int r = 0; r < TS; ++r)
 #pragma unroll
-                        for (int c = 0; c < kTile; ++c) acc[r][c] -= li[r] * lj[c];
+                        for (int c = 0; c < TS; ++c) acc[r][c] -= li[r] * lj[c];
                 }
 #pragma unroll
-                for (int r = 0; r < kTile; ++r)
+                for (int r = 0; r < TS; ++r)
 #pragma unroll
-                    for (int c = 0; c < kTile; ++c) A[(size_t)(r * kTile + c) * NT + t] = acc[r][c];
-                if (q == 0) factor_diag_tile(A, NT, t, pnl + 1, dim, zvec);
+                    for (int c = 0; c < TS; ++c) A[(size_t)(r * TS + c) * NT + t] = acc[r][c];
+                if (q == 0) factor_diag_tile<T, TS>(A, NT, t, pnl + 1, dim, zvec);
             }
             __syncthreads();
         }
 
         if (!lowrank && p.export_tiles != nullptr) {
-            for (int e = tid; e < kTileElems * NT; e += nthreads) p.export_tiles[e] = A[e];
+            for (int e = tid; e < (TS * TS) * NT; e += nthreads) p.export_tiles[e] = A[e];
         }
 
         // ---- back substitution L^T x = z, one block column at a time -------------------------
         for (int bj = nbk - 1; bj >= 0; --bj) {
-            int nv = dim - kTile * bj;
-            if (nv > kTile) nv = kTile;
+            int nv = dim - TS * bj;
+            if (nv > TS) nv = TS;
             const int td = tile_id(bj, bj);
             if (tid < nv) {
                 T s = T(0);
-                for (int j = tid; j < nv; ++j) s += A[(size_t)(j * kTile + tid) * NT + td] * zvec[kTile * bj + j];
-                xvec[kTile * bj + tid] = s;
+                for (int j = tid; j < nv; ++j) s += A[(size_t)(j * TS + tid) * NT + td] * zvec[TS * bj + j];
+                xvec[TS * bj + tid] = s;
             }
             __syncthreads();
-            for (int jp = tid; jp < kTile * bj; jp += nthreads) {
-                const int t = tile_id(bj, jp / kTile), c = jp % kTile;
+            for (int jp = tid; jp < TS * bj; jp += nthreads) {
+                const int t = tile_id(bj, jp / TS), c = jp % TS;
                 T s = zvec[jp];
-                for (int i = 0; i < nv; ++i) s -= A[(size_t)(i * kTile + c) * NT + t] * xvec[kTile * bj + i];
+                for (int i = 0; i < nv; ++i) s -= A[(size_t)(i * TS + c) * NT + t] * xvec[TS * bj + i];
                 zvec[jp] = s;
             }
             __syncthreads();
@@ -446,7 +451,16 @@ __global__ void __launch_bounds__(kSolveThreads, 1) als_solve_rows_kernel(SolveA
             // y = Q_r^T t + p  (second, L2-resident pass over the row's Q rows; coalesced along a)
             for (int a = tid; a < k; a += nthreads) {
                 T s = prior_row ? p.lambda * prior_row[a] : T(0);
-                for (int i = 0; i < dim; ++i) s += p.fixed[(int64_t)idxs[i] * k + a] * xvec[i];
+                int i = 0;
+                for (; i + 4 <= dim; i += 4) {   // four loads in flight per thread
+                    const T q0 = p.fixed[(int64_t)idxs[i] * k + a], q1 = p.fixed[(int64_t)idxs[i + 1] * k + a];
+                    const T q2 = p.fixed[(int64_t)idxs[i + 2] * k + a], q3 = p.fixed[(int64_t)idxs[i + 3] * k + a];
+                    s += q0 * xvec[i];
+                    s += q1 * xvec[i + 1];
+                    s += q2 * xvec[i + 2];
+                    s += q3 * xvec[i + 3];
+                }
+                for (; i < dim; ++i) s += p.fixed[(int64_t)idxs[i] * k + a] * xvec[i];
                 if (!(s - s == T(0))) *p.status = 1;
                 out[a] = s;
             }

@@ -178,7 +178,7 @@ struct Engine : EngineBase {
     DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out;
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
-    int solve_smem_attr = 0;
+    int solve_smem_attr[2] = {0, 0};
     DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk;
 
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
@@ -378,7 +378,7 @@ struct Engine : EngineBase {
     // Launch the row kernel over a contiguous range or a row list, in direct or low-rank mode.
     int launch_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
                     bool lowrank, int max_dim, int threads, const T* fixed_ptr, const T* prior_ptr, T* export_ptr,
-                    const int64_t* indptr_override, int64_t work, cudaStream_t st, int slot) {
+                    const int64_t* indptr_override, int64_t work, cudaStream_t st, int slot, int ts = 8) {
         // export_ptr != null: the single-row launch that only factors B -- its (zero) solution must
         // not land in the factor matrix
         T* latent_ptr = user ? U.as<T>() : V.as<T>();
@@ -388,22 +388,24 @@ struct Engine : EngineBase {
         }
         const Csr& rows_csr = user ? csr : csc;
         // shared-memory plan: tiles in shared memory when they fit, else per-CTA global scratch
-        int chunk = lowrank ? 16 : 32;
-        hyprec::SolveLayout lay = hyprec::solve_layout(max_dim, chunk, true, sizeof(T));
+        // rank-1 vectors staged per round: small systems take long rounds (fewer gather latencies)
+        int chunk = lowrank ? (max_dim <= 63 ? 64 : (max_dim <= 127 ? 32 : 16)) : 32;
+        hyprec::SolveLayout lay = hyprec::solve_layout(ts, max_dim, chunk, true, sizeof(T));
         while (lay.total > (size_t)h->max_smem && chunk > 8) {
             chunk /= 2;
-            lay = hyprec::solve_layout(max_dim, chunk, true, sizeof(T));
+            lay = hyprec::solve_layout(ts, max_dim, chunk, true, sizeof(T));
         }
         const bool in_smem = lay.total <= (size_t)h->max_smem;
         if (!in_smem) {
             chunk = 16;
-            lay = hyprec::solve_layout(max_dim, chunk, false, sizeof(T));
+            lay = hyprec::solve_layout(ts, max_dim, chunk, false, sizeof(T));
             if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "n_factors too large for the solve kernel");
         }
-        auto kern = hyprec::als_solve_rows_kernel<T>;
-        if ((int)lay.total > solve_smem_attr) {
+        auto kern = ts == 4 ? hyprec::als_solve_rows_kernel<T, 4> : hyprec::als_solve_rows_kernel<T, 8>;
+        int& smem_attr = solve_smem_attr[ts == 4 ? 0 : 1];
+        if ((int)lay.total > smem_attr) {
             CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-            solve_smem_attr = (int)lay.total;
+            smem_attr = (int)lay.total;
         }
         int per_sm = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));
@@ -411,7 +413,7 @@ struct Engine : EngineBase {
         const int grid = (int)std::min<int64_t>(work, (int64_t)per_sm * h->num_sms);
         // (work counters of all slots were zeroed at the start of the half-step)
         DevBuf& scratch_buf = a_scratch_slot[slot];
-        if (!in_smem) HY_TRY(scratch_buf.reserve(sizeof(T) * (size_t)grid * hyprec::kTileElems * lay.n_tiles));
+        if (!in_smem) HY_TRY(scratch_buf.reserve(sizeof(T) * (size_t)grid * ts * ts * lay.n_tiles));
 
         hyprec::SolveArgs<T> a;
         a.indptr = indptr_override ? indptr_override : rows_csr.indptr.template as<int64_t>();
@@ -595,7 +597,9 @@ struct Engine : EngineBase {
                 {
                     // 4. deg x deg systems, one launch per degree bucket, all buckets concurrently
                     Timer t(h, HYPREC_T_SOLVE);
-                    static const int threads[4] = {32, 64, 128, 256};
+                    // small systems on 4 x 4 tiles (more threads with a tile, shorter FMA chains)
+                    static const int threads[4] = {64, 128, 128, 256};
+                    static const int tile[4] = {4, 4, 8, 8};
                     CU_TRY(cudaEventRecord(h->ev_fork, h->stream));
                     for (int b = 0; b < 4; ++b) {
                         const int64_t cnt = pl.bucket_off[b + 1] - pl.bucket_off[b];
@@ -603,7 +607,7 @@ struct Engine : EngineBase {
                         CU_TRY(cudaStreamWaitEvent(h->aux[b], h->ev_fork, 0));
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
                                            threads[b], qmat.as<T>(), prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr,
-                                           cnt, h->aux[b], 1 + b));
+                                           cnt, h->aux[b], 1 + b, tile[b]));
                         CU_TRY(cudaEventRecord(h->ev_join[b], h->aux[b]));
                         CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
                     }

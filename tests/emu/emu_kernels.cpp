@@ -39,7 +39,7 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
     std::vector<T> base((size_t)kTileElems * n_tiles);
     emu::launch(dim3((kTileElems * n_tiles + 255) / 256), dim3(256), 0,
                 [&]() { build_base_tiles_kernel<T>(g.data(), k, lambda, base.data()); });
-    SolveLayout lay = solve_layout(k, chunk_rows, a_in_smem != 0, sizeof(T));
+    SolveLayout lay = solve_layout(8, k, chunk_rows, a_in_smem != 0, sizeof(T));
     std::vector<T> scratch(a_in_smem ? 1 : (size_t)grid * kTileElems * n_tiles);
     int counter[2] = {0, 0};
     SolveArgs<T> a;
@@ -48,7 +48,7 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
     a.work_counter = counter; a.status = counter + 1; a.lambda = lambda; a.k = k;
     a.row_lo = row_lo; a.row_hi = row_hi; a.chunk_rows = chunk_rows;
     a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = nullptr;
-    emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T>(a); });
+    emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
     return counter[1];
 }
 
@@ -68,7 +68,7 @@ static void gemm_nt(const double* a, int64_t ra, const double* b, int64_t rb, in
 static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices, const double* values,
                                   const double* fixed, int64_t n_fixed, double* latent, int64_t n_rows, int k,
                                   double lambda, const double* prior, int dim_cap, int threads, int grid,
-                                  int tiles_in_smem) {
+                                  int tiles_in_smem, int ts) {
     typedef double T;
     std::vector<T> g((size_t)k * k);
     gram_impl<T>(fixed, n_fixed, k, 3, g.data());
@@ -85,8 +85,8 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
     a.base = base.data(); a.prior = nullptr; a.a_scratch = nullptr; a.work_counter = counter; a.status = counter + 1;
     a.lambda = lambda; a.k = k; a.row_lo = 0; a.row_hi = 1; a.chunk_rows = 8; a.row_list = nullptr; a.n_list = 0;
     a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = tiles.data();
-    SolveLayout lay = solve_layout(k, 8, true, sizeof(T));
-    emu::launch(dim3(1), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T>(a); });
+    SolveLayout lay = solve_layout(8, k, 8, true, sizeof(T));
+    emu::launch(dim3(1), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
     // 2. L^-1 and its transpose
     std::vector<T> linv((size_t)k * k, -777.0), linv_t((size_t)k * k, -777.0);
     const int nbk = (k + kTile - 1) / kTile;
@@ -115,8 +115,9 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
         b.indptr = indptr; b.fixed = q.data(); b.prior = prior ? pq.data() : nullptr; b.latent = nullptr;
         b.row_list = light.data(); b.n_list = (int64_t)light.size(); b.max_dim = max_deg; b.lowrank = 1;
         b.ymat = ymat.data(); b.export_tiles = nullptr; b.chunk_rows = 16;
-        SolveLayout l2 = solve_layout(max_deg, 16, true, sizeof(T));
-        emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T>(b); });
+        SolveLayout l2 = solve_layout(ts, max_deg, 16, true, sizeof(T));
+        if (ts == 4) emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 4>(b); });
+        else emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 8>(b); });
         // 5. X = Ymat L^-1  (X[i][c] = sum_a Ymat[i][a] LinvT[c][a]) -- light rows only are meaningful
         std::vector<T> x((size_t)n_rows * k);
         gemm_nt(ymat.data(), n_rows, linv_t.data(), k, k, x.data());
@@ -127,7 +128,7 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
         SolveArgs<T> d = a;
         d.indptr = indptr; d.latent = latent; d.prior = prior; d.row_list = heavy.data(); d.n_list = (int64_t)heavy.size();
         d.export_tiles = nullptr; d.chunk_rows = 8;
-        emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T>(d); });
+        emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(d); });
     }
     return counter[1];
 }
@@ -216,9 +217,9 @@ int emu_half_step_f32(const int64_t* indptr, const int32_t* indices, const float
 
 int emu_half_step_lowrank_f64(const int64_t* indptr, const int32_t* indices, const double* values, const double* fixed,
                               int64_t n_fixed, double* latent, int64_t n_rows, int k, double lambda, const double* prior,
-                              int dim_cap, int threads, int grid, int tiles_in_smem) {
+                              int dim_cap, int threads, int grid, int tiles_in_smem, int ts) {
     return half_step_lowrank_impl(indptr, indices, values, fixed, n_fixed, latent, n_rows, k, lambda, prior, dim_cap,
-                                  threads, grid, tiles_in_smem);
+                                  threads, grid, tiles_in_smem, ts);
 }
 
 void emu_eval_f64(const double* U, const double* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,

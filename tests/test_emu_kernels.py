@@ -84,9 +84,10 @@ def test_solve_kernel_shard_scratch_and_f32(emu):
     assert numpy.allclose(got32, want, rtol=2e-3, atol=2e-4)
 
 
+@pytest.mark.parametrize("ts", [4, 8])
 @pytest.mark.parametrize("k,cap,threads,use_prior", [(12, 100, 64, False), (16, 12, 32, True), (24, 1000, 128, True),
                                                      (40, 20, 256, False)])
-def test_lowrank_half_step(emu, k, cap, threads, use_prior):
+def test_lowrank_half_step(emu, k, cap, threads, use_prior, ts):
     """Woodbury path on whitened factors (factor of 0.1 G + lambda I, L^-1, Q = Y L^-T, deg x deg
     systems, X = Ymat L^-1) with rows above `cap` positives routed to the direct kernel."""
     rs = numpy.random.RandomState(k)
@@ -100,7 +101,7 @@ def test_lowrank_half_step(emu, k, cap, threads, use_prior):
     out = u0.copy()
     ip, ix = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32)
     status = emu.emu_half_step_lowrank_f64(_ptr(ip), _ptr(ix), _ptr(csr.data), _ptr(v0), I64(n), _ptr(out), I64(m), k,
-                                           DBL(0.05), _ptr(prior), cap, threads, 3, k % 2)
+                                           DBL(0.05), _ptr(prior), cap, threads, 3, k % 2, ts)
     assert status == 0
     assert numpy.allclose(out, want, rtol=1e-10, atol=1e-12)
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "hyprec_set_train_csr", "hyprec_set_shard", "hyprec_set_factors", "hyprec_get_factors",
     "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_rmse_terms", "hyprec_train",
     "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
-    "hyprec_flush_l2", "hyprec_probe_fma_tflops",
+    "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles",
 ]
 
 EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
@@ -72,6 +72,7 @@ def load_library(rebuild=False):
     lib.hyprec_kernel_ms.argtypes = [vp, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]
     lib.hyprec_reset_kernel_ms.argtypes = [vp]
     lib.hyprec_flush_l2.argtypes = [vp]
+    lib.hyprec_solve_phase_cycles.argtypes = [vp, vp, c_int]
     lib.hyprec_probe_fma_tflops.argtypes = [vp, c_int, ctypes.POINTER(c_dbl)]
     _lib = lib
     return lib
@@ -237,6 +238,11 @@ class Handle(object):
         out = ctypes.c_double()
         self._check(self._lib.hyprec_probe_fma_tflops(self._h, int(precision), ctypes.byref(out)))
         return out.value
+
+    def solve_phase_cycles(self, reset=True):
+        out = numpy.zeros(16, dtype=numpy.int64)
+        self._check(self._lib.hyprec_solve_phase_cycles(self._h, _ptr(out), 1 if reset else 0))
+        return out
 
     def flush_l2(self):
         self._check(self._lib.hyprec_flush_l2(self._h))

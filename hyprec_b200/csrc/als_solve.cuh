@@ -101,6 +101,7 @@ struct SolveArgs {
     int lowrank;              // 0: direct k x k systems; 1: deg x deg systems on whitened factors
     T* ymat;                  // low-rank output [n_rows][k]
     T* export_tiles;          // direct mode: factored tiles of the processed row (single-row launch)
+    long long* prof;          // optional: per-phase clock64() totals of block 0 (tools/solve_phases.py)
 };
 
 // float64 dot product of two k-vectors by one warp (lane-strided partial sums, xor-shuffle tree)
@@ -113,14 +114,28 @@ __device__ __forceinline__ double warp_dot_t(const TA* __restrict__ a, const TB*
     return s;
 }
 
-__device__ __forceinline__ double inv_sqrt(double x) { return rsqrt(x); }
+// 1/sqrt(x) in float64 from a float32 seed and two Newton steps (2^-22 -> ~2^-44 -> rounding level):
+// a far shorter dependent chain than the library rsqrt, which sits on the factorisation's
+// critical path once per column.  Falls back to rsqrt outside the float32 range.
+__device__ __forceinline__ double inv_sqrt(double x) {
+#ifdef HYPREC_EMU
+    return rsqrt(x);
+#else
+    if (!(x > 1e-30 && x < 1e30)) return rsqrt(x);
+    double y = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    y = y * (1.5 - hx * y * y);
+    y = y * (1.5 - hx * y * y);
+    return y;
+#endif
+}
 __device__ __forceinline__ float inv_sqrt(float x) { return rsqrtf(x); }
 
-// Cholesky of the leading nvalid x nvalid block of an 8x8 tile held in registers (lower
+// Cholesky of the leading nvalid x nvalid block of a TS x TS tile held in registers (lower
 // triangle); the rows below it are carried along as in a panel factorisation (that is where the
 // right-hand-side row picks up its part of z).  The diagonal is left INVERTED.
 template <typename T, int TS>
-__device__ __forceinline__ void chol8_factor(T (&a)[TS][TS], int nvalid) {
+__device__ __forceinline__ void chol_tile_factor(T (&a)[TS][TS], int nvalid) {
 #pragma unroll
     for (int j = 0; j < TS; ++j) {
         if (j < nvalid) {
@@ -137,9 +152,9 @@ __device__ __forceinline__ void chol8_factor(T (&a)[TS][TS], int nvalid) {
 }
 
 // In-place inverse of the leading lower-triangular nvalid x nvalid block (diagonal already
-// inverted by chol8_factor): column j of L^-1 is -L22^-1 L[j+1:, j] / L[j][j].
+// inverted): column j of L^-1 is -L22^-1 L[j+1:, j] / L[j][j].
 template <typename T, int TS>
-__device__ __forceinline__ void chol8_invert(T (&a)[TS][TS], int nvalid) {
+__device__ __forceinline__ void chol_tile_invert(T (&a)[TS][TS], int nvalid) {
 #pragma unroll
     for (int j = TS - 1; j >= 0; --j) {
         if (j < nvalid) {
@@ -157,26 +172,21 @@ __device__ __forceinline__ void chol8_invert(T (&a)[TS][TS], int nvalid) {
     }
 }
 
-// Factor diagonal tile `p` (tile id `t` of the tiled matrix A) in place: Cholesky of its leading
-// block, then that block's inverse.  If the right-hand-side row sits in this tile (k not a
-// multiple of 8 and p == k / 8) its z entries are published first.  Runs in ONE thread; kept out
-// of line so that its register needs do not spill the callers' accumulator tiles.
+// The serial part of a diagonal tile, one thread, tile in registers; out of line so that its
+// register needs stay out of the callers' accumulator tiles.
 #ifndef HYPREC_EMU
 template <typename T, int TS>
-__device__ __noinline__ void factor_diag_tile(T* A, int NT, int t, int p, int k, T* zvec) {
+__device__ __noinline__ void factor_diag_tile_serial(T* A, int NT, int t, int p, int nvalid, T* zvec) {
 #else
 template <typename T, int TS>
-void factor_diag_tile(T* A, int NT, int t, int p, int k, T* zvec) {
+void factor_diag_tile_serial(T* A, int NT, int t, int p, int nvalid, T* zvec) {
 #endif
-    int nvalid = k - p * TS;
-    if (nvalid > TS) nvalid = TS;
-    if (nvalid <= 0) return;
     T a[TS][TS];
 #pragma unroll
     for (int r = 0; r < TS; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) a[r][c] = A[(size_t)(r * TS + c) * NT + t];
-    chol8_factor<T, TS>(a, nvalid);
+    chol_tile_factor<T, TS>(a, nvalid);
     if (nvalid < TS) {
 #pragma unroll
         for (int r = 1; r < TS; ++r)
@@ -185,16 +195,101 @@ void factor_diag_tile(T* A, int NT, int t, int p, int k, T* zvec) {
                 for (int j = 0; j < r; ++j) zvec[p * TS + j] = a[r][j];
             }
     }
-    chol8_invert<T, TS>(a, nvalid);
+    chol_tile_invert<T, TS>(a, nvalid);
 #pragma unroll
     for (int r = 0; r < TS; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) A[(size_t)(r * TS + c) * NT + t] = a[r][c];
 }
 
+// Factor diagonal tile `p` (tile id `t` of the tiled matrix A) in place: Cholesky of its leading
+// block (rows below it carried along; the right-hand-side row's z entries are published to zvec
+// when it sits in this tile), then that block is replaced by its inverse, diagonal kept inverted.
+// Called by all 32 lanes of one warp.  With `panel` != null the tile first receives its trailing
+// update from the current panel (A_pp -= P_p P_p^T) spread over the lanes -- lane l holds column
+// l % TS of rows l / TS + g * (32 / TS).  The factorisation itself is a chain of dependent
+// rsqrt / FMA steps: measured on B200, one thread with the tile in registers runs it faster than a
+// shuffle-based warp version, so lane 0 does it while the other warps carry the trailing update.
+template <typename T, int TS>
+__device__ __forceinline__ void factor_diag_tile_warp(T* A, int NT, int t, int p, int dim, T* zvec, int lane,
+                                                      const T* panel = nullptr, int ystride = 0, int nb = 0) {
+    int nvalid = dim - p * TS;
+    if (nvalid > TS) nvalid = TS;
+    if (panel != nullptr) {
+        constexpr int RPP = 32 / TS;                   // rows covered per pass of 32 lanes
+        constexpr int EPL = (TS * TS + 31) / 32;       // elements per lane
+        const int c = lane % TS, r0 = lane / TS;
+        T a[EPL];
+#pragma unroll
+        for (int g = 0; g < EPL; ++g) {
+            const int r = r0 + g * RPP;
+            a[g] = (r < TS) ? A[(size_t)(r * TS + c) * NT + t] : T(0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < TS; ++kk) {
+            const T* prow = panel + (size_t)kk * ystride;
+            const T lc = prow[c * nb + p];
+#pragma unroll
+            for (int g = 0; g < EPL; ++g) {
+                const int r = r0 + g * RPP;
+                if (r < TS) a[g] -= prow[r * nb + p] * lc;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < EPL; ++g) {
+            const int r = r0 + g * RPP;
+            if (r < TS) A[(size_t)(r * TS + c) * NT + t] = a[g];
+        }
+        __syncwarp();
+    }
+    if (nvalid > 0 && lane == 0) factor_diag_tile_serial<T, TS>(A, NT, t, p, nvalid, zvec);
+    __syncwarp();
+}
+
+// A_tile(bi, bj) -= P_bi P_bj^T with the current panel P (TS columns of L) read from the panel buffer
+template <typename T, int TS>
+__device__ __forceinline__ void trailing_update_tile(T* A, int NT, const T* ybuf, int ystride, int nb, int bi, int bj) {
+    const int t = tile_id(bi, bj);
+    T acc[TS][TS];
+#pragma unroll
+    for (int r = 0; r < TS; ++r)
+#pragma unroll
+        for (int c = 0; c < TS; ++c) acc[r][c] = A[(size_t)(r * TS + c) * NT + t];
+#pragma unroll 2
+    for (int kk = 0; kk < TS; ++kk) {
+        const T* prow = ybuf + (size_t)kk * ystride;
+        T li[TS], lj[TS];
+#pragma unroll
+        for (int r = 0; r < TS; ++r) li[r] = prow[r * nb + bi];
+#pragma unroll
+        for (int c = 0; c < TS; ++c) lj[c] = prow[c * nb + bj];
+#pragma unroll
+        for (int r = 0; r < TS; ++r)
+#pragma unroll
+            for (int c = 0; c < TS; ++c) acc[r][c] -= li[r] * lj[c];
+    }
+#pragma unroll
+    for (int r = 0; r < TS; ++r)
+#pragma unroll
+        for (int c = 0; c < TS; ++c) A[(size_t)(r * TS + c) * NT + t] = acc[r][c];
+}
+
+#ifdef HYPREC_EMU
+#define HYPREC_PROF(slot)
+#else
+// phase timing for tools/solve_phases.py: thread 0 of block 0 accumulates clock64() deltas
+#define HYPREC_PROF(slot)                                                            \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {                          \
+        const long long now_ = clock64();                                            \
+        p.prof[slot] += now_ - prof_t;                                               \
+        prof_t = now_;                                                               \
+    }
+#endif
+
 template <typename T, int TS>
 __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows_kernel(SolveArgs<T> p) {
     HYPREC_DYN_SMEM(smem_raw);
+    long long prof_t = 0;
     __shared__ long long s_row;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid % 32, warp = tid / 32, nwarps = nthreads / 32;
@@ -224,6 +319,9 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
         __syncthreads();
         if (s_row >= n_work) break;
         const int64_t row = p.row_list ? (int64_t)p.row_list[s_row] : p.row_lo + s_row;
+#ifndef HYPREC_EMU
+        if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) prof_t = clock64();
+#endif
         const int64_t lo = p.indptr[row];
         const int deg = (int)(p.indptr[row + 1] - lo);
         T* out = lowrank ? p.ymat + row * k : p.latent + row * k;
@@ -329,9 +427,9 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
                             const int j = bj * TS + c;
                             T v;
                             if (i < dim) {
-                                const T base = lowrank ? (i == j ? T(1) : T(0))
-                                                       : p.base[(size_t)(r * TS + c) * NT + q];
-                                v = base + pos_scale * acc[r][c];
+                                // (direct mode: the shared base 0.1 G + lambda I is added below, in one
+                                // coalesced pass, instead of 64 scattered loads per tile here)
+                                v = pos_scale * acc[r][c] + ((lowrank && i == j) ? T(1) : T(0));
                             } else if (i == dim) {
                                 if (lowrank) {
                                     v = j < dim ? xvec[j] : T(0);
@@ -350,10 +448,19 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
                 for (int r = 0; r < TS; ++r)
 #pragma unroll
                     for (int c = 0; c < TS; ++c) A[(size_t)(r * TS + c) * NT + q] = acc[r][c];
-                if (last && q == 0) factor_diag_tile<T, TS>(A, NT, 0, 0, dim, zvec);
             }
             __syncthreads();
         }
+        HYPREC_PROF(0)   // gather + rank-1 accumulation
+        if (!lowrank) {
+#pragma unroll 8
+            for (int e = tid; e < TS * TS * NT; e += nthreads) A[e] += p.base[e];
+            __syncthreads();
+        }
+        HYPREC_PROF(1)   // base add
+        if (warp == 0) factor_diag_tile_warp<T, TS>(A, NT, 0, 0, dim, zvec, lane);
+        __syncthreads();
+        HYPREC_PROF(2)   // first diagonal tile
 
         // ---- right-looking blocked Cholesky, 8-column panels ---------------------------------
         for (int pnl = 0; pnl < nbk; ++pnl) {
@@ -384,38 +491,29 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
                 }
             }
             __syncthreads();
-            // trailing update; the owner of the next diagonal tile factors it straight away
+            HYPREC_PROF(3)   // panel solves
+            // trailing update.  Warp 0 updates only the next diagonal tile (spread over its lanes) and
+            // factors it straight away; the other warps update every other trailing tile meanwhile, so
+            // the factorisation of the next panel's diagonal runs beside the update instead of after it.
             const int ntr = nb - 1 - pnl;
-            const int ntiles = tri(ntr);
+            if (ntr > 0) {
+                const int ntiles = tri(ntr);
+                if (warp == 0) {
+                    factor_diag_tile_warp<T, TS>(A, NT, tile_id(pnl + 1, pnl + 1), pnl + 1, dim, zvec, lane, ybuf, ystride, nb);
+                    HYPREC_PROF(5)   // warp 0: next diagonal tile (update + factor + inverse)
+                    if (nwarps == 1) {
 #pragma unroll 1
-            for (int q = tid; q < ntiles; q += nthreads) {
-                const int bi = pnl + 1 + tmap[2 * q], bj = pnl + 1 + tmap[2 * q + 1];
-                const int t = tile_id(bi, bj);
-                T acc[TS][TS];
-#pragma unroll
-                for (int r = 0; r < TS; ++r)
-#pragma unroll
-                    for (int c = 0; c < TS; ++c) acc[r][c] = A[(size_t)(r * TS + c) * NT + t];
-#pragma unroll 2
-                for (int kk = 0; kk < TS; ++kk) {
-                    const T* prow = ybuf + (size_t)kk * ystride;
-                    T li[TS], lj[TS];
-#pragma unroll
-                    for (int r = 0; r < TS; ++r) li[r] = prow[r * nb + bi];
-#pragma unroll
-                    for (int c = 0; c < TS; ++c) lj[c] = prow[c * nb + bj];
-#pragma unroll
-                    for (int r = 0; r < TS; ++r)
-#pragma unroll
-                        for (int c = 0; c < TS; ++c) acc[r][c] -= li[r] * lj[c];
+                        for (int q = 1 + lane; q < ntiles; q += 32)
+                            trailing_update_tile<T, TS>(A, NT, ybuf, ystride, nb, pnl + 1 + tmap[2 * q], pnl + 1 + tmap[2 * q + 1]);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int q = 1 + tid - 32; q < ntiles; q += nthreads - 32)
+                        trailing_update_tile<T, TS>(A, NT, ybuf, ystride, nb, pnl + 1 + tmap[2 * q], pnl + 1 + tmap[2 * q + 1]);
                 }
-#pragma unroll
-                for (int r = 0; r < TS; ++r)
-#pragma unroll
-                    for (int c = 0; c < TS; ++c) A[(size_t)(r * TS + c) * NT + t] = acc[r][c];
-                if (q == 0) factor_diag_tile<T, TS>(A, NT, t, pnl + 1, dim, zvec);
             }
             __syncthreads();
+            HYPREC_PROF(6)   // warp 0 waiting for the rest of the trailing update
         }
 
         if (!lowrank && p.export_tiles != nullptr) {
@@ -441,6 +539,7 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
             }
             __syncthreads();
         }
+        HYPREC_PROF(7)   // back substitution
         if (!lowrank) {
             for (int c = tid; c < k; c += nthreads) {
                 const T v = xvec[c];

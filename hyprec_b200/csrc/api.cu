@@ -91,6 +91,7 @@ struct EngineBase {
     virtual int device_factors(void** u, void** v, int* elem) = 0;
     virtual int set_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) = 0;
     virtual int score_dense_f32(float* out) = 0;
+    virtual int solve_phase_cycles(long long* out16, int reset) = 0;
 };
 
 }  // namespace
@@ -104,6 +105,7 @@ struct hyprec_ctx {
     int64_t launches = 0;
     bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
     bool tc_enabled = true;        // HYPREC_TC=0 keeps the score sweep on the SIMT kernel
+    bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
     int64_t user_lo = 0, user_hi = -1, item_lo = 0, item_hi = -1;   // shard; hi < 0 => all
     // kernel timing: (begin, end) event pairs taken from a pool, harvested into per-class
@@ -175,7 +177,7 @@ struct Engine : EngineBase {
     bool gram_ok[2] = {false, false};   // [0] = U^T U, [1] = V^T V match the current factors
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
     DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
-    DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out;
+    DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out, prof_buf;
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
     int solve_smem_attr[2] = {0, 0};
@@ -186,7 +188,7 @@ struct Engine : EngineBase {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
-                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &plan[0].lists, &plan[1].lists,
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
@@ -437,6 +439,11 @@ struct Engine : EngineBase {
         a.lowrank = lowrank ? 1 : 0;
         a.ymat = ymat.as<T>();
         a.export_tiles = export_ptr;
+        a.prof = nullptr;
+        if (h->prof_enabled && !export_ptr && slot == 0) {
+            if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
+            a.prof = prof_buf.as<long long>();
+        }
         kern<<<grid, threads, lay.total, st>>>(a);
         h->launches += 1;
         CU_TRY(cudaGetLastError());
@@ -800,6 +807,14 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+    int solve_phase_cycles(long long* out16, int reset) override {
+        HY_TRY(prof_buf.reserve(16 * sizeof(long long)));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (out16) CU_TRY(cudaMemcpy(out16, prof_buf.ptr, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (reset) CU_TRY(cudaMemset(prof_buf.ptr, 0, 16 * sizeof(long long)));
+        return HYPREC_OK;
+    }
+
     int score_dense_f32(float* out) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "score_dense_f32 before set_factors");
         if (!tc_usable()) return fail(HYPREC_E_UNSUPPORTED, "tensor-core score sweep unavailable (HYPREC_TC=0, not sm_100, or n_factors % 4 != 0)");
@@ -1123,6 +1138,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
             cudaGetLastError();
         }
     }
+    const char* pf = getenv("HYPREC_SOLVE_PROF");
+    h->prof_enabled = pf && pf[0] == '1';
     const char* lr = getenv("HYPREC_LOWRANK");
     h->lowrank_enabled = !(lr && lr[0] == '0');
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);
@@ -1233,6 +1250,11 @@ int hyprec_set_eval_csr(hyprec_t* h, const int64_t* fp, const int32_t* fi, const
                         const int32_t* ti, const double* tv) {
     HY_TRY(check(h));
     return h->engine->set_eval(fp, fi, fv, tp, ti, tv);
+}
+
+int hyprec_solve_phase_cycles(hyprec_t* h, long long* out16, int reset) {
+    HY_TRY(check(h));
+    return h->engine->solve_phase_cycles(out16, reset);
 }
 
 int hyprec_score_dense_f32(hyprec_t* h, float* out) {

@@ -154,6 +154,12 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
 #define HYPREC_T_PREP 7   /* low-rank path: factor of 0.1 G + lambda I, L^-1, whitening / un-whitening GEMMs */
 int hyprec_kernel_ms(hyprec_t* h, int which, double* total_ms, int64_t* calls, double* last_ms);
 int hyprec_reset_kernel_ms(hyprec_t* h);
+/* Diagnostic (HYPREC_SOLVE_PROF=1 at hyprec_create): clock64() totals per phase of the direct row
+ * solve, accumulated by block 0 -- out16[0..7] = gather+accumulate, base add, first diagonal tile,
+ * panel solves, next block column, next diagonal tile, wait for the trailing update, back
+ * substitution.  reset != 0 clears the counters after reading. */
+int hyprec_solve_phase_cycles(hyprec_t* h, long long* out16, int reset);
+
 /* Measured FMA rate of this GPU (TFLOP/s, best of 4 after a warm-up) in the given precision:
  * the roofline denominator for the SIMT solve kernel, which MEASURED_PEAKS.json does not hold. */
 int hyprec_probe_fma_tflops(hyprec_t* h, int precision, double* tflops);

@@ -47,7 +47,7 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
     a.base = base.data(); a.prior = prior; a.a_scratch = a_in_smem ? nullptr : scratch.data();
     a.work_counter = counter; a.status = counter + 1; a.lambda = lambda; a.k = k;
     a.row_lo = row_lo; a.row_hi = row_hi; a.chunk_rows = chunk_rows;
-    a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = nullptr;
+    a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = nullptr; a.prof = nullptr;
     emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
     return counter[1];
 }
@@ -84,7 +84,7 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
     a.indptr = dummy_ptr; a.indices = indices; a.values = values; a.fixed = fixed; a.latent = dummy_out.data();
     a.base = base.data(); a.prior = nullptr; a.a_scratch = nullptr; a.work_counter = counter; a.status = counter + 1;
     a.lambda = lambda; a.k = k; a.row_lo = 0; a.row_hi = 1; a.chunk_rows = 8; a.row_list = nullptr; a.n_list = 0;
-    a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = tiles.data();
+    a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = tiles.data(); a.prof = nullptr;
     SolveLayout lay = solve_layout(8, k, 8, true, sizeof(T));
     emu::launch(dim3(1), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
     // 2. L^-1 and its transpose

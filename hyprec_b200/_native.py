@@ -18,7 +18,7 @@ EXPORTS = [
     "hyprec_set_train_csr", "hyprec_set_shard", "hyprec_set_factors", "hyprec_get_factors",
     "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_rmse_terms", "hyprec_train",
     "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
-    "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles",
+    "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles", "hyprec_host_alloc", "hyprec_host_free",
 ]
 
 EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
@@ -72,6 +72,8 @@ def load_library(rebuild=False):
     lib.hyprec_kernel_ms.argtypes = [vp, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]
     lib.hyprec_reset_kernel_ms.argtypes = [vp]
     lib.hyprec_flush_l2.argtypes = [vp]
+    lib.hyprec_host_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.hyprec_host_free.argtypes = [vp, vp]
     lib.hyprec_solve_phase_cycles.argtypes = [vp, vp, c_int]
     lib.hyprec_probe_fma_tflops.argtypes = [vp, c_int, ctypes.POINTER(c_dbl)]
     _lib = lib
@@ -96,6 +98,7 @@ class Handle(object):
         self._h = ctypes.c_void_p()
         self.precision = precision
         self.m = self.n = self.k = 0
+        self._pinned = []
         self._check(self._lib.hyprec_create(ctypes.byref(self._h), int(device), int(precision)))
 
     def _check(self, code):
@@ -104,6 +107,9 @@ class Handle(object):
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            for ptr in getattr(self, "_pinned", []):
+                self._lib.hyprec_host_free(self._h, ptr)
+            self._pinned = []
             self._lib.hyprec_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -203,11 +209,18 @@ class Handle(object):
         return out
 
     def eval_topk(self, capacity, cand_indptr=None, cand_ids=None, user_lo=0, user_hi=None, want_counts=True,
-                  want_topk=True, n_train_nz=None, n_test_nz=None):
-        """Returns dict(thresholds, ones_per_row, topk_idx, topk_val, topk_hit, train_flags, test_flags)."""
+                  want_topk=True, n_train_nz=None, n_test_nz=None, out=None):
+        """Returns dict(thresholds, ones_per_row, topk_idx, topk_val, topk_hit, train_flags, test_flags).
+        `out`: a dict returned by an earlier identical call, to reuse its (possibly pinned) arrays."""
         user_hi = self.m if user_hi is None else user_hi
         nu = user_hi - user_lo
         cand_indptr, cand_ids = _as(cand_indptr, numpy.int64), _as(cand_ids, numpy.int32)
+        if out is not None:
+            self._check(self._lib.hyprec_eval_topk(
+                self._h, user_lo, user_hi, _ptr(cand_indptr), _ptr(cand_ids), int(capacity), _ptr(out["thresholds"]),
+                _ptr(out["ones_per_row"]), _ptr(out["topk_idx"]), _ptr(out["topk_val"]), _ptr(out["topk_hit"]),
+                _ptr(out["train_flags"]), _ptr(out["test_flags"])))
+            return out
         out = dict(thresholds=numpy.empty(nu))
         out["ones_per_row"] = numpy.zeros(nu, dtype=numpy.int64) if want_counts else None
         if want_topk:
@@ -243,6 +256,16 @@ class Handle(object):
         out = numpy.zeros(16, dtype=numpy.int64)
         self._check(self._lib.hyprec_solve_phase_cycles(self._h, _ptr(out), 1 if reset else 0))
         return out
+
+    def pinned_empty(self, shape, dtype=numpy.float64):
+        """numpy array backed by page-locked host memory (freed by close())."""
+        dtype = numpy.dtype(dtype)
+        count = int(numpy.prod(shape))
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.hyprec_host_alloc(self._h, max(count * dtype.itemsize, 1), ctypes.byref(ptr)))
+        self._pinned.append(ptr)
+        buf = (ctypes.c_char * (count * dtype.itemsize)).from_address(ptr.value)
+        return numpy.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
     def flush_l2(self):
         self._check(self._lib.hyprec_flush_l2(self._h))

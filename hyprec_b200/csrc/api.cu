@@ -1309,6 +1309,19 @@ int hyprec_probe_fma_tflops(hyprec_t* h, int precision, double* tflops) {
     return fail(HYPREC_E_INVALID, "precision must be 0 (f64) or 1 (f32)");
 }
 
+int hyprec_host_alloc(hyprec_t* h, size_t bytes, void** out) {
+    HY_TRY(check(h));
+    if (!out) return fail(HYPREC_E_INVALID, "hyprec_host_alloc: null output");
+    CU_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return HYPREC_OK;
+}
+
+int hyprec_host_free(hyprec_t* h, void* ptr) {
+    HY_TRY(check(h));
+    if (ptr) CU_TRY(cudaFreeHost(ptr));
+    return HYPREC_OK;
+}
+
 int hyprec_flush_l2(hyprec_t* h) {
     HY_TRY(check(h));
     const size_t want = (size_t)384 << 20;   // 3x the 126 MB L2

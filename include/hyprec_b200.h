@@ -22,6 +22,7 @@
 #ifndef HYPREC_B200_H
 #define HYPREC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -163,6 +164,10 @@ int hyprec_solve_phase_cycles(hyprec_t* h, long long* out16, int reset);
 /* Measured FMA rate of this GPU (TFLOP/s, best of 4 after a warm-up) in the given precision:
  * the roofline denominator for the SIMT solve kernel, which MEASURED_PEAKS.json does not hold. */
 int hyprec_probe_fma_tflops(hyprec_t* h, int precision, double* tflops);
+/* Page-locked host memory for callers that want full PCIe rate on the factor / top-k transfers
+ * (every host pointer of this API may be pageable or pinned). */
+int hyprec_host_alloc(hyprec_t* h, size_t bytes, void** out);
+int hyprec_host_free(hyprec_t* h, void* ptr);
 /* Overwrite a buffer 3x the size of L2 so the next kernel starts cold (benchmark hygiene). */
 int hyprec_flush_l2(hyprec_t* h);
 

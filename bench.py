@@ -468,8 +468,27 @@ def make_workload(args):
     if args.workload == "scaled":
         if args.precision == "fp64" and "HYPREC_PRECISION" not in os.environ:
             args.precision = "fp32"          # configs[3] is specified in float32
-        return build_scaled_workload(args.scale)
+        return cached_scaled_workload(args.scale)
     return build_workload(args.workload)
+
+
+def cached_scaled_workload(scale):
+    """The scaled input is deterministic; local rank 0 builds it once and the other ranks (and later
+    runs on the same box) read it back from /dev/shm."""
+    import pickle
+    path = "/dev/shm/hyprec_scaled_%g.pkl" % scale
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(path):
+        if local == 0:
+            wl = build_scaled_workload(scale)
+            with open(path + ".tmp", "wb") as f:
+                pickle.dump(wl, f, protocol=4)
+            os.replace(path + ".tmp", path)
+            return wl
+        while not os.path.exists(path):
+            time.sleep(0.5)
+    with open(path, "rb") as f:
+        return pickle.load(f)
 
 
 if __name__ == "__main__":

@@ -13,14 +13,15 @@
 // 3xTF32: every float64/float32 factor x is split as x = hi + lo (+ ~2^-22 |x|), hi and lo
 // representable in TF32, and S~ accumulates hi*hi + hi*lo + lo*hi in float32.
 //
-// Kernel structure (persistent, one CTA per SM, 192 threads):
+// Kernel structure (persistent, one CTA per SM, 320 threads):
 //   warp 0      TMA producer: 4 boxes (U_hi, U_lo, V_hi, V_lo; 128 rows x 32 floats, SWIZZLE_128B)
 //               per k-block into a 3-stage ring guarded by full/empty mbarriers
 //   warp 1      TMEM allocation (256 columns = 2 accumulator stages of 128 x 128 float32) and
 //               MMA issue: per k-block 4 k-steps x 3 tcgen05.mma (M128 N128 K8), tcgen05.commit
 //               releases the smem stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 (lane = row), threshold test or float32 store,
-//               then hand the TMEM stage back
+//   warps 2-9   epilogue: tcgen05.ld 32x32b.x32 (lane = row; two warps per TMEM lane quadrant, one
+//               per column half), float32 margin test and/or float32 store, then hand the TMEM
+//               stage back
 // All mbarrier waits are bounded: a protocol error traps instead of hanging the GPU.
 #pragma once
 #include <cuda.h>
@@ -34,7 +35,8 @@ constexpr int kBM = 128, kBN = 128, kBK = 32;       // tile: users x items x fac
 constexpr int kStages = 3;
 constexpr int kTileBytes = kBM * kBK * 4;            // one operand box: 16 KB
 constexpr int kStageBytes = 4 * kTileBytes;          // U_hi, U_lo, V_hi, V_lo
-constexpr int kThreads = 192;
+constexpr int kEpilogueWarps = 8;                    // two per TMEM lane quadrant (column halves)
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kAccCols = kBN;                        // TMEM columns per accumulator stage
 constexpr int kTmemCols = 2 * kAccCols;              // power of two >= 32
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4 * kBN;
@@ -162,7 +164,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 4);
+            mbar_init(&acc_empty[s], kEpilogueWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -227,8 +229,9 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int quad = warp % 4;                  // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) / 4;            // which 64 columns of the tile
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -236,22 +239,25 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
             const int64_t row = (int64_t)tm * kBM + quad * 32 + lane;
             const int64_t col0 = (int64_t)tn * kBN;
             const bool row_ok = row < p.m;
-            // stage the tile's column norms (all four epilogue warps take part)
-            const int et = threadIdx.x - 64;         // 0..127
-            asm volatile("bar.sync 1, 128;" ::: "memory");       // previous tile's readers are done
-            vnorm_s[et] = (col0 + et < p.n && p.vnorm) ? p.vnorm[col0 + et] : 0.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            double thr = 0.0;
-            float un = 0.f;
+            // stage the tile's column norms (all epilogue warps take part)
+            const int et = threadIdx.x - 64;         // 0..255
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // previous tile's readers are done
+            if (et < kBN) vnorm_s[et] = (col0 + et < p.n && p.vnorm) ? p.vnorm[col0 + et] : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // float32 test: s~ - thr_f against margin = c ||u|| ||v|| (+0.1 % for the float32 products
+            // of the margin itself) + the rounding of the threshold to float32
+            float thr_f = 0.f, thr_err = 0.f, un = 0.f;
             if (row_ok && p.counts) {
-                thr = p.thresholds[row];
-                un = p.unorm[row] * p.margin_coef;
+                const double thr = p.thresholds[row];
+                thr_f = (float)thr;
+                thr_err = fabsf(thr_f) * 1.1920929e-7f;
+                un = p.unorm[row] * p.margin_coef * 1.001f;
             }
             mbar_wait(&acc_full[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            unsigned long long definite = 0;
+            unsigned int definite = 0;
 #pragma unroll 1
-            for (int c = 0; c < kBN; c += 32) {
+            for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccCols + c);
                 tmem_load_32x32(taddr, v);
@@ -269,24 +275,25 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                         }
                     }
                     if (p.counts) {
+                        const bool full_chunk = col0 + c + 32 <= p.n;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const int64_t col = col0 + c + j;
-                            if (col < p.n) {
-                                const double diff = (double)__uint_as_float(v[j]) - thr;
-                                const double margin = (double)(un * vnorm_s[c + j]);
+                            if (full_chunk || col0 + c + j < p.n) {
+                                const float diff = __uint_as_float(v[j]) - thr_f;
+                                const float margin = fmaf(un, vnorm_s[c + j], thr_err);
                                 if (diff > margin) {
                                     ++definite;
                                 } else if (diff >= -margin) {
                                     const unsigned int at = atomicAdd(p.border_count, 1u);
-                                    if (at < p.border_capacity) p.border_cells[at] = make_uint2((unsigned)row, (unsigned)col);
+                                    if (at < p.border_capacity)
+                                        p.border_cells[at] = make_uint2((unsigned)row, (unsigned)(col0 + c + j));
                                 }
                             }
                         }
                     }
                 }
             }
-            if (row_ok && p.counts && definite) atomicAdd(p.counts + row, definite);
+            if (row_ok && p.counts && definite) atomicAdd(p.counts + row, (unsigned long long)definite);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);

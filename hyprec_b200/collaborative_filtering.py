@@ -20,6 +20,11 @@ There is no CPU fallback: without the CUDA library or a GPU the first device cal
 
 Environment knobs (the JSON config surface is unchanged): ``HYPREC_PRECISION`` = fp64 (default,
 parity with numpy float64) | fp32; ``HYPREC_DEVICE`` = CUDA device index (default: LOCAL_RANK or 0).
+
+Multi-GPU: when the process runs under ``torchrun`` with an initialised ``torch.distributed`` process
+group (one process per GPU), every rank executes the same host code on the same data; the epochs shard
+users / items across ranks (``hyprec_b200.distributed.ShardedALS``), the evaluation shards users and
+gathers the per-user integers, and every rank ends up with identical factors and an identical report.
 """
 import os
 import time
@@ -108,6 +113,17 @@ class CollaborativeFiltering(AbstractRecommender):
             index = int(os.environ.get("HYPREC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
             self._handle = _native.Handle(index, self._precision)
         return self._handle
+
+    @staticmethod
+    def _world():
+        """(rank, world_size) of an initialised torch.distributed group, else (0, 1)."""
+        try:
+            import torch.distributed as dist
+        except ImportError:
+            return 0, 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
 
     def close(self):
         if self._handle is not None:
@@ -289,17 +305,50 @@ class CollaborativeFiltering(AbstractRecommender):
             error = h.rmse()
             print(line.format(epoch=0, loss=error, time=0))
         state = {'previous': error, 'stalled': False}
+        rank, world = self._world()
+        chatty = self._verbose and rank == 0
 
         def on_epoch(epoch, rmse, seconds):
-            if self._verbose:
+            if chatty:
                 print(line.format(epoch=epoch, loss=rmse, time=seconds))
             state['stalled'] = rmse >= state['previous']
             state['previous'] = rmse
 
-        h.train(self.n_iter, self._lambda, error, on_epoch)
-        if self._verbose and state['stalled']:
+        if world == 1:
+            h.train(self.n_iter, self._lambda, error, on_epoch)
+        else:
+            self._train_sharded(h, rank, world, error, on_epoch)
+        if chatty and state['stalled']:
             print("Local Optimum was found in the last iteration, breaking.")
         self._download_factors(h)
+
+    def _shard_bounds(self, world):
+        from hyprec_b200 import distributed
+        indptr, indices, _ = _csr_triplet(self.train_data)
+        users = distributed.partition_rows(indptr, world, self.n_factors)
+        items = distributed.partition_rows(distributed.csc_indptr(indptr, indices, self.n_items), world, self.n_factors)
+        return users, items
+
+    def _train_sharded(self, h, rank, world, error, on_epoch):
+        """The epoch loop of partial_train over row shards: one exchange of the solved rows after each
+        half-step, RMSE from per-shard partial sums, the same early-stop decision on every rank."""
+        from hyprec_b200 import distributed
+        users, items = self._shard_bounds(world)
+        engine = distributed.NativeEngine(h, int(os.environ.get("HYPREC_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+        als = distributed.ShardedALS(engine, users, items, rank, self.n_users, self.n_items)
+        try:
+            for epoch in range(1, self.n_iter + 1):
+                old_error = error
+                t0 = time.time()
+                als.half_step(_native.SIDE_USER, self._lambda)
+                als.half_step(_native.SIDE_ITEM, self._lambda)
+                t1 = time.time()
+                error = als.rmse()
+                on_epoch(epoch, error, t1 - t0)
+                if error >= old_error:
+                    break
+        finally:
+            h.set_shard(0, -1, 0, -1)          # back to "all rows" for later single-rank calls
 
     # ------------------------------------------------------------------ prediction
     def get_predictions(self):
@@ -351,6 +400,23 @@ class CollaborativeFiltering(AbstractRecommender):
         ids = numpy.concatenate(rows).astype(numpy.int32) if len(rows) else numpy.zeros(0, numpy.int32)
         return indptr, ids
 
+    def _eval_sharded(self, h, rank, world, fold):
+        """Users sharded across ranks (V is replicated); the per-user outputs are gathered so that
+        every rank holds the full arrays."""
+        import torch.distributed as dist
+        users, _ = self._shard_bounds(world)
+        lo, hi = users[rank], users[rank + 1]
+        cand_indptr, cand_ids = self.candidate_lists(fold)
+        train_ptr = _csr_triplet(self.train_data)[0]
+        test_ptr = _csr_triplet(self.test_data)[0]
+        part = h.eval_topk(self.n_recommendations, cand_indptr[lo:hi + 1] - cand_indptr[lo],
+                           cand_ids[cand_indptr[lo]:cand_indptr[hi]], lo, hi,
+                           n_train_nz=int(train_ptr[hi] - train_ptr[lo]), n_test_nz=int(test_ptr[hi] - test_ptr[lo]))
+        self._cands_uploaded = None
+        gathered = [None] * world
+        dist.all_gather_object(gathered, part)
+        return {key: numpy.concatenate([g[key] for g in gathered]) for key in part}
+
     def get_evaluation_report(self):
         """abstract_recommender.py:100-131.  Scores never leave the GPU: the device returns row
         thresholds, per-row counts of rounded ones, the streamed top-200 of every user's candidate
@@ -361,12 +427,16 @@ class CollaborativeFiltering(AbstractRecommender):
         fold = self.hyperparameters['fold']
         h = self._upload_eval()
         self._upload_factors()
-        key = (self.evaluator.test_indices, fold)
-        if self._cands_uploaded is None or self._cands_uploaded[0] is not key[0] or self._cands_uploaded[1] != fold:
-            h.set_candidates(*self.candidate_lists(fold))        # once per fold
-            self._cands_uploaded = key
-        out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users,
-                          n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
+        rank, world = self._world()
+        if world == 1:
+            key = (self.evaluator.test_indices, fold)
+            if self._cands_uploaded is None or self._cands_uploaded[0] is not key[0] or self._cands_uploaded[1] != fold:
+                h.set_candidates(*self.candidate_lists(fold))        # once per fold
+                self._cands_uploaded = key
+            out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users,
+                              n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
+        else:
+            out = self._eval_sharded(h, rank, world, fold)
         rmse = h.rmse()
 
         lengths = (out["topk_idx"] >= 0).sum(axis=1)

@@ -452,7 +452,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="citeulike-a", choices=sorted(WORKLOADS) + ["scaled"])
     ap.add_argument("--scale", type=float, default=0.1, help="fraction of the 1M x 2M / 2e8 config (--workload scaled)")
-    ap.add_argument("--precision", default=os.environ.get("HYPREC_PRECISION", "fp64"), choices=["fp64", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("HYPREC_PRECISION"), choices=["fp64", "fp32"],
+                    help="default: fp64 (citeulike workloads), fp32 (scaled workload, as BASELINE configs[3] specifies)")
     ap.add_argument("--cpu-rows", type=int, default=16, help="rows per side in the CPU baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -466,9 +467,11 @@ def main():
 
 def make_workload(args):
     if args.workload == "scaled":
-        if args.precision == "fp64" and "HYPREC_PRECISION" not in os.environ:
+        if args.precision is None:
             args.precision = "fp32"          # configs[3] is specified in float32
         return cached_scaled_workload(args.scale)
+    if args.precision is None:
+        args.precision = "fp64"
     return build_workload(args.workload)
 
 

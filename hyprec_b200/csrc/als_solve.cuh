@@ -574,10 +574,11 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
 //     X_JJ = D_J^-1,   X_IJ = -D_I^-1 * sum_{Q=J}^{I-1} L_IQ X_QJ   (I > J)
 // grid = block columns, 64 threads = the 8x8 elements of the tile being formed; the exported
 // tiles are staged in shared memory when they fit (tiles_in_smem), else read through L2.
+// Outputs are written with leading dimension ld (>= k): a diagonal block of a larger matrix.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(64) tri_inverse_kernel(const T* __restrict__ tiles, int k, int tiles_in_smem,
-                                                         T* __restrict__ linv, T* __restrict__ linv_t) {
+                                                         T* __restrict__ linv, T* __restrict__ linv_t, int ld) {
     HYPREC_DYN_SMEM(smem_raw);
     const int nb_src = aug_blocks(k), NT = tri(nb_src);
     const int nbk = (k + kTile - 1) / kTile;
@@ -615,11 +616,11 @@ __global__ void __launch_bounds__(64) tri_inverse_kernel(const T* __restrict__ t
         if (gi >= k || gj >= k) v = T(0);
         xcol[(size_t)I * kTileElems + r * kTile + c] = v;
         if (gi < k && gj < k) {
-            linv[(size_t)gi * k + gj] = v;
-            linv_t[(size_t)gj * k + gi] = v;
+            linv[(size_t)gi * ld + gj] = v;
+            linv_t[(size_t)gj * ld + gi] = v;
             if (I == J && c > r) {   // strictly upper part of the diagonal block is zero in L^-1
-                linv[(size_t)gi * k + gj] = T(0);
-                linv_t[(size_t)gj * k + gi] = T(0);
+                linv[(size_t)gi * ld + gj] = T(0);
+                linv_t[(size_t)gj * ld + gi] = T(0);
             }
         }
         __syncthreads();
@@ -628,10 +629,72 @@ __global__ void __launch_bounds__(64) tri_inverse_kernel(const T* __restrict__ t
     for (int I = 0; I < J; ++I) {
         const int gi = I * kTile + r, gj = J * kTile + c;
         if (gi < k && gj < k) {
-            linv[(size_t)gi * k + gj] = T(0);
-            linv_t[(size_t)gj * k + gi] = T(0);
+            linv[(size_t)gi * ld + gj] = T(0);
+            linv_t[(size_t)gj * ld + gi] = T(0);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense helpers for the blocked factorisation of B = 0.1 G + lambda I when k x k float64 tiles do
+// not fit one SM's shared memory (k > ~230): B is split into r x r blocks of <= 192, diagonal blocks
+// go through als_solve_rows_kernel (export) + tri_inverse_kernel, the rest is small GEMMs.
+// ------------------------------------------------------------------------------------------------
+
+// B = 0.1 * G + lambda * I as a dense float64 matrix.
+template <typename T>
+__global__ void build_base_dense_kernel(const T* __restrict__ g, int k, double lambda, double* __restrict__ b) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    const int i = idx / k, j = idx % k;
+    b[idx] = kConfNeg * (double)g[idx] + (i == j ? lambda : 0.0);
+}
+
+// Tiled (8x8, structure-of-arrays) copy of the diagonal block B[off:off+bs, off:off+bs] with a zero
+// right-hand-side row: the `base` input of a direct-mode factorisation with k := bs.
+__global__ void tiles_from_dense_kernel(const double* __restrict__ b, int ld, int off, int bs, double* __restrict__ tiles) {
+    const int nb = aug_blocks(bs), n_tiles = tri(nb);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kTileElems * n_tiles) return;
+    const int e = idx / n_tiles, t = idx % n_tiles;
+    int bi, bj;
+    tri_coords(t, &bi, &bj);
+    const int i = bi * kTile + e / kTile, j = bj * kTile + e % kTile;
+    tiles[idx] = (i < bs && j < bs) ? b[(size_t)(off + i) * ld + off + j] : 0.0;
+}
+
+// C[M x N] = alpha * A[M x K] * op(B) + beta * C, row-major with leading dimensions; op(B) = B^T for
+// B stored [N x K] (trans_b) or B stored [K x N].  Small matrices (<= 300): 16 x 16 tiles.
+__global__ void dgemm_small_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
+                                   const double* __restrict__ B, int ldb, int trans_b, double* __restrict__ C, int ldc,
+                                   double alpha, double beta) {
+    __shared__ double as[16][17], bs[16][17];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        as[ty][tx] = (row < M && k0 + tx < K) ? A[(size_t)row * lda + k0 + tx] : 0.0;
+        // bs[kk][n]
+        const int n_load = blockIdx.x * 16 + ty;   // for trans_b: row of B = output column
+        if (trans_b) bs[tx][ty] = (n_load < N && k0 + tx < K) ? B[(size_t)n_load * ldb + k0 + tx] : 0.0;
+        else bs[ty][tx] = (k0 + ty < K && col < N) ? B[(size_t)(k0 + ty) * ldb + col] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) acc += as[ty][kk] * bs[kk][tx];
+        __syncthreads();
+    }
+    if (row < M && col < N) {
+        double* c = C + (size_t)row * ldc + col;
+        *c = alpha * acc + (beta != 0.0 ? beta * *c : 0.0);
+    }
+}
+
+// dst[j][i] = src[i][j] for a k x k matrix (L^-T from L^-1).
+__global__ void transpose_dense_kernel(const double* __restrict__ src, int k, double* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    const int i = idx / k, j = idx % k;
+    dst[(size_t)j * k + i] = src[idx];
 }
 
 }  // namespace hyprec

@@ -177,7 +177,7 @@ struct Engine : EngineBase {
     bool gram_ok[2] = {false, false};   // [0] = U^T U, [1] = V^T V match the current factors
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
     DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
-    DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out, prof_buf;
+    DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out, prof_buf, bdense, lfac, blk_tmp, blk_base;
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
     int solve_smem_attr[2] = {0, 0};
@@ -188,7 +188,7 @@ struct Engine : EngineBase {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
-                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &plan[0].lists, &plan[1].lists,
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
@@ -521,6 +521,139 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+    // L^-1 and L^-T (dense k x k, float64) of B = 0.1 G + lambda I, G = Gram of the fixed side.
+    // k x k float64 tiles that fit one SM's shared memory (k <= ~230): one direct-mode launch on a row
+    // without positives exports the factored tiles, tri_inverse_kernel turns them into L^-1.
+    // Larger k: B is cut into r x r blocks of <= 192; diagonal blocks go through the same two kernels,
+    // panels and Schur updates through small float64 GEMMs (right-looking block Cholesky, then block
+    // forward substitution for the inverse).
+    int compute_linv(bool user, double lambda, const T* fixed_ptr) {
+        namespace hp = hyprec;
+        const int nb = hp::aug_blocks(k), n_tiles = hp::tri(nb);
+        HY_TRY(linv.reserve(sizeof(double) * (size_t)k * k));
+        HY_TRY(linv_t.reserve(sizeof(double) * (size_t)k * k));
+        HY_TRY(dummy_ptr.reserve(2 * sizeof(int64_t)));
+        CU_TRY(cudaMemsetAsync(dummy_ptr.ptr, 0, 2 * sizeof(int64_t), h->stream));
+        const bool whole = hp::solve_layout(8, k, 8, true, sizeof(T)).total <= (size_t)h->max_smem;
+        if (whole) {
+            HY_TRY(tiles.reserve(sizeof(T) * (size_t)hp::kTileElems * n_tiles));
+            HY_TRY(launch_rows(user, lambda, 0, 1, nullptr, 0, false, k, hp::kSolveThreads, fixed_ptr, nullptr,
+                               tiles.as<T>(), dummy_ptr.as<int64_t>(), 1, h->stream, 0));
+            HY_TRY(launch_tri_inverse(tiles.as<T>(), k, linv.as<T>(), linv_t.as<T>(), k));
+            return HYPREC_OK;
+        }
+        // ---- blocked path (float64 only; T == double whenever the low-rank path runs)
+        const int r = (k + 191) / 192;
+        const int bs0 = (((k + r - 1) / r) + 7) / 8 * 8;
+        auto off = [&](int j) { return j * bs0; };
+        auto size = [&](int j) { return std::min(bs0, k - j * bs0); };
+        HY_TRY(bdense.reserve(sizeof(double) * (size_t)k * k));
+        HY_TRY(lfac.reserve(sizeof(double) * (size_t)k * k));
+        HY_TRY(blk_tmp.reserve(sizeof(double) * (size_t)bs0 * bs0));
+        const int blk_tiles_n = hp::kTileElems * hp::tri(hp::aug_blocks(bs0));
+        HY_TRY(blk_base.reserve(sizeof(double) * (size_t)blk_tiles_n));
+        HY_TRY(tiles.reserve(sizeof(double) * (size_t)blk_tiles_n));
+        double* B = bdense.as<double>();
+        double* L = lfac.as<double>();
+        double* X = linv.as<double>();
+        hp::build_base_dense_kernel<T><<<(k * k + 255) / 256, 256, 0, h->stream>>>(gram[user ? 1 : 0].as<T>(), k, lambda, B);
+        CU_TRY(cudaMemsetAsync(X, 0, sizeof(double) * (size_t)k * k, h->stream));
+        h->launches += 1;
+        auto gemm = [&](int M, int N, int K, const double* A, const double* Bm, int trans_b, double* C, int ldc,
+                        int ldb, double alpha, double beta) {
+            dim3 grid((N + 15) / 16, (M + 15) / 16);
+            hp::dgemm_small_kernel<<<grid, 256, 0, h->stream>>>(M, N, K, A, k, Bm, ldb, trans_b, C, ldc, alpha, beta);
+            h->launches += 1;
+        };
+        for (int j = 0; j < r; ++j) {
+            const int sj = size(j), oj = off(j);
+            const int nt = hp::kTileElems * hp::tri(hp::aug_blocks(sj));
+            hp::tiles_from_dense_kernel<<<(nt + 255) / 256, 256, 0, h->stream>>>(B, k, oj, sj, blk_base.as<double>());
+            h->launches += 1;
+            HY_TRY(factor_block(blk_base.as<T>(), sj, tiles.as<T>()));
+            HY_TRY(launch_tri_inverse(tiles.as<T>(), sj, reinterpret_cast<T*>(X + (size_t)oj * k + oj),
+                                      reinterpret_cast<T*>(linv_t.as<double>() + (size_t)oj * k + oj), k));
+            for (int i = j + 1; i < r; ++i)     // L_ij = B_ij L_jj^-T
+                gemm(size(i), sj, sj, B + (size_t)off(i) * k + oj, X + (size_t)oj * k + oj, 1, L + (size_t)off(i) * k + oj, k, k, 1.0, 0.0);
+            for (int i = j + 1; i < r; ++i)     // Schur update of the remaining lower blocks
+                for (int l = j + 1; l <= i; ++l)
+                    gemm(size(i), size(l), sj, L + (size_t)off(i) * k + oj, L + (size_t)off(l) * k + oj, 1,
+                         B + (size_t)off(i) * k + off(l), k, k, -1.0, 1.0);
+        }
+        for (int j = 0; j < r; ++j)             // X_ij = -L_ii^-1 sum_{q=j}^{i-1} L_iq X_qj
+            for (int i = j + 1; i < r; ++i) {
+                for (int q = j; q < i; ++q)
+                    gemm(size(i), size(j), size(q), L + (size_t)off(i) * k + off(q), X + (size_t)off(q) * k + off(j), 0,
+                         blk_tmp.as<double>(), bs0, k, 1.0, q == j ? 0.0 : 1.0);
+                dim3 grid((size(j) + 15) / 16, (size(i) + 15) / 16);
+                hp::dgemm_small_kernel<<<grid, 256, 0, h->stream>>>(size(i), size(j), size(i), X + (size_t)off(i) * k + off(i), k,
+                                                                     blk_tmp.as<double>(), bs0, 0, X + (size_t)off(i) * k + off(j),
+                                                                     k, -1.0, 0.0);
+                h->launches += 1;
+            }
+        hp::transpose_dense_kernel<<<(k * k + 255) / 256, 256, 0, h->stream>>>(X, k, linv_t.as<double>());
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
+    int launch_tri_inverse(const T* tile_ptr, int dim, T* out, T* out_t, int ld) {
+        namespace hp = hyprec;
+        const int nbk = (dim + hp::kTile - 1) / hp::kTile;
+        const int n_tiles = hp::tri(hp::aug_blocks(dim));
+        size_t inv_smem = sizeof(T) * ((size_t)nbk * hp::kTileElems + hp::kTileElems);
+        const size_t with_tiles = inv_smem + sizeof(T) * (size_t)hp::kTileElems * n_tiles;
+        const int tis = with_tiles <= (size_t)h->max_smem ? 1 : 0;
+        if (tis) inv_smem = with_tiles;
+        auto inv_kern = hp::tri_inverse_kernel<T>;
+        CU_TRY(cudaFuncSetAttribute(inv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+        inv_kern<<<nbk, 64, inv_smem, h->stream>>>(tile_ptr, dim, tis, out, out_t, ld);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
+    // Direct-mode factorisation of one dim x dim SPD matrix given as base tiles; tiles exported.
+    int factor_block(const T* base_tiles, int dim, T* export_ptr) {
+        namespace hp = hyprec;
+        const hp::SolveLayout lay = hp::solve_layout(8, dim, 8, true, sizeof(T));
+        if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "factor_block: block too large");
+        auto kern = hp::als_solve_rows_kernel<T, 8>;
+        if ((int)lay.total > solve_smem_attr[1]) {
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+            solve_smem_attr[1] = (int)lay.total;
+        }
+        HY_TRY(dummy_out.reserve(sizeof(T) * (size_t)k));
+        CU_TRY(cudaMemsetAsync(counter.as<int>(), 0, sizeof(int), h->stream));   // slot 0
+        hp::SolveArgs<T> a;
+        a.indptr = dummy_ptr.as<int64_t>();
+        a.indices = csr.indices.template as<int32_t>();
+        a.values = csr.values.template as<T>();
+        a.fixed = U.as<T>();
+        a.latent = dummy_out.as<T>();
+        a.base = base_tiles;
+        a.prior = nullptr;
+        a.a_scratch = nullptr;
+        a.work_counter = counter.as<int>();
+        a.status = counter.as<int>() + kStatusSlot;
+        a.lambda = T(0);
+        a.k = dim;
+        a.row_lo = 0;
+        a.row_hi = 1;
+        a.chunk_rows = 8;
+        a.row_list = nullptr;
+        a.n_list = 0;
+        a.max_dim = dim;
+        a.lowrank = 0;
+        a.ymat = nullptr;
+        a.export_tiles = export_ptr;
+        a.prof = nullptr;
+        kern<<<1, hp::kSolveThreads, lay.total, h->stream>>>(a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
     int half_step(int side, double lambda) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "als_half_step before set_factors");
         if (side != HYPREC_SIDE_USER && side != HYPREC_SIDE_ITEM) return fail(HYPREC_E_INVALID, "side must be 0 or 1");
@@ -574,25 +707,8 @@ struct Engine : EngineBase {
             if (n_light > 0) {
                 {
                     Timer t(h, HYPREC_T_PREP);
-                    // 1. factor B = 0.1 G + lambda I once (a row without positives), keep the tiles
-                    HY_TRY(tiles.reserve(sizeof(T) * (size_t)hyprec::kTileElems * n_tiles));
-                    HY_TRY(dummy_ptr.reserve(2 * sizeof(int64_t)));
-                    CU_TRY(cudaMemsetAsync(dummy_ptr.ptr, 0, 2 * sizeof(int64_t), h->stream));
-                    HY_TRY(launch_rows(user, lambda, 0, 1, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, nullptr,
-                                       tiles.as<T>(), dummy_ptr.as<int64_t>(), 1, h->stream, 0));
-                    // 2. L^-1 and L^-T
-                    HY_TRY(linv.reserve(sizeof(T) * (size_t)k * k));
-                    HY_TRY(linv_t.reserve(sizeof(T) * (size_t)k * k));
-                    const int nbk = (k + hyprec::kTile - 1) / hyprec::kTile;
-                    size_t inv_smem = sizeof(T) * ((size_t)nbk * hyprec::kTileElems + hyprec::kTileElems);
-                    const size_t with_tiles = inv_smem + sizeof(T) * (size_t)hyprec::kTileElems * n_tiles;
-                    const int tis = with_tiles <= (size_t)h->max_smem ? 1 : 0;
-                    if (tis) inv_smem = with_tiles;
-                    auto inv_kern = hyprec::tri_inverse_kernel<T>;
-                    CU_TRY(cudaFuncSetAttribute(inv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
-                    inv_kern<<<nbk, 64, inv_smem, h->stream>>>(tiles.as<T>(), k, tis, linv.as<T>(), linv_t.as<T>());
-                    h->launches += 1;
-                    CU_TRY(cudaGetLastError());
+                    // 1-2. factor B = 0.1 G + lambda I = L L^T once and form L^-1, L^-T
+                    HY_TRY(compute_linv(user, lambda, fixed_ptr));
                     // 3. whitened factors Q = Y L^-T (and theta L^-T for the item prior)
                     HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
                     HY_TRY(gemm_nt(fixed_ptr, n_fixed, linv.as<T>(), k, qmat.as<double>()));

@@ -92,7 +92,7 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
     const int nbk = (k + kTile - 1) / kTile;
     size_t inv_smem = sizeof(T) * ((size_t)nbk * kTileElems + kTileElems + (tiles_in_smem ? (size_t)kTileElems * n_tiles : 0));
     emu::launch(dim3(nbk), dim3(64), inv_smem,
-                [&]() { tri_inverse_kernel<T>(tiles.data(), k, tiles_in_smem, linv.data(), linv_t.data()); });
+                [&]() { tri_inverse_kernel<T>(tiles.data(), k, tiles_in_smem, linv.data(), linv_t.data(), k); });
     // 3. whitened factors Q = Y L^-T  (Q[i][a] = sum_b Y[i][b] Linv[a][b]) and prior rows p = lambda theta L^-T
     std::vector<T> q((size_t)n_fixed * k), pq;
     gemm_nt(fixed, n_fixed, linv.data(), k, k, q.data());

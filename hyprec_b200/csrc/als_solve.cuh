@@ -689,6 +689,13 @@ __global__ void dgemm_small_kernel(int M, int N, int K, const double* __restrict
     }
 }
 
+// element-wise conversion between the factor dtype and float64 / float32 work copies
+template <typename TIn, typename TOut>
+__global__ void cast_kernel(const TIn* __restrict__ src, int64_t count, TOut* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = (TOut)src[i];
+}
+
 // dst[j][i] = src[i][j] for a k x k matrix (L^-T from L^-1).
 __global__ void transpose_dense_kernel(const double* __restrict__ src, int k, double* __restrict__ dst) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;

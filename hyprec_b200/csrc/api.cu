@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -116,8 +117,9 @@ struct hyprec_ctx {
     double ms_total[kNumTimers] = {0};
     double ms_last[kNumTimers] = {0};
     int64_t ms_calls[kNumTimers] = {0};
-    cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // concurrent row-kernel launches
-    cudaEvent_t ev_fork = nullptr, ev_base = nullptr, ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kAux = 7;
+    cudaStream_t aux[kAux] = {};             // concurrent row-kernel launches
+    cudaEvent_t ev_fork = nullptr, ev_base = nullptr, ev_join[kAux] = {};
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     EngineBase* engine = nullptr;
@@ -178,9 +180,22 @@ struct Engine : EngineBase {
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
     DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
     DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out, prof_buf, bdense, lfac, blk_tmp, blk_base;
+    DevBuf fixed_d, gram_partial_d, gram_dbuf, linv_f, linv_t_f;
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
-    int solve_smem_attr[2] = {0, 0};
+    static constexpr int kHeavyStream = 6;   // aux streams 0..5: degree buckets, 6: rows above the cap
+    std::map<const void*, int> smem_attr;    // per kernel: largest dynamic shared memory opted into
+
+    // cudaFuncAttributeMaxDynamicSharedMemorySize only ever grows (one cache per kernel function: the
+    // same instantiation is launched from several places with different sizes).
+    int ensure_dynamic_smem(const void* func, int bytes) {
+        int& have = smem_attr[func];
+        if (bytes > have) {
+            CU_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            have = bytes;
+        }
+        return HYPREC_OK;
+    }
     DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk;
 
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
@@ -188,7 +203,7 @@ struct Engine : EngineBase {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
-                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &plan[0].lists, &plan[1].lists,
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
@@ -404,11 +419,7 @@ struct Engine : EngineBase {
             if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "n_factors too large for the solve kernel");
         }
         auto kern = ts == 4 ? hyprec::als_solve_rows_kernel<T, 4> : hyprec::als_solve_rows_kernel<T, 8>;
-        int& smem_attr = solve_smem_attr[ts == 4 ? 0 : 1];
-        if ((int)lay.total > smem_attr) {
-            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-            smem_attr = (int)lay.total;
-        }
+        HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
         int per_sm = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));
         if (per_sm < 1) return fail(HYPREC_E_UNSUPPORTED, "solve kernel does not fit on an SM");
@@ -452,7 +463,7 @@ struct Engine : EngineBase {
 
     // C[ra x rb] = A[ra x k] B[rb x k]^T through the sweep kernel (float64 path only).  With a row
     // list the product is taken over rows A[list[i]] and row i is stored at C[list[i]].
-    int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, double* c, const int32_t* list = nullptr) {
+    int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, T* c, const int32_t* list = nullptr) {
         hyprec::SweepArgs<T> s;
         s.user_vecs = a;
         s.item_vecs = b;
@@ -460,7 +471,8 @@ struct Engine : EngineBase {
         s.user_lo = 0;
         s.user_hi = ra;
         s.n_items = rb;
-        s.dense_out = c;
+        s.dense_out = sizeof(T) == sizeof(double) ? reinterpret_cast<double*>(c) : nullptr;
+        s.dense_out_f32 = sizeof(T) == sizeof(double) ? nullptr : reinterpret_cast<float*>(c);
         s.row_list = list;
         s.thresholds = nullptr;
         s.counts = nullptr;
@@ -477,36 +489,51 @@ struct Engine : EngineBase {
     struct RowPlan {
         int64_t lo = -1, hi = -1;
         int cap = -1;
+        int n_buckets = 0;
         std::vector<int64_t> bucket_off;   // offsets into `lists`, size n_buckets + 2 (last = heavy)
         std::vector<int> bucket_dim;
         DevBuf lists;
     };
     RowPlan plan[2];
 
+    // Degree buckets of the low-rank path: upper dimension, threads per CTA, tile edge.
+    static constexpr int kMaxBuckets = 6;
+    static constexpr int kBucketDim[kMaxBuckets] = {31, 63, 127, 191, 255, 319};
+    static constexpr int kBucketThreads[kMaxBuckets] = {64, 128, 128, 256, 256, 256};
+    static constexpr int kBucketTile[kMaxBuckets] = {4, 4, 8, 8, 8, 8};
+
+    // Number of buckets whose systems fit one SM's shared memory in this precision.
+    int usable_buckets() const {
+        int nbk = 0;
+        for (int b = 0; b < kMaxBuckets; ++b)
+            if (hyprec::solve_layout(kBucketTile[b], kBucketDim[b], 8, true, sizeof(T)).total <= (size_t)h->max_smem) nbk = b + 1;
+        return nbk;
+    }
+
     int build_plan(bool user, int64_t lo, int64_t hi, int cap) {
         RowPlan& pl = plan[user ? 0 : 1];
         if (pl.lo == lo && pl.hi == hi && pl.cap == cap) return HYPREC_OK;
         const std::vector<int64_t>& ptr = (user ? csr : csc).h_indptr;
-        static const int dims[4] = {31, 63, 127, 191};
-        std::vector<std::vector<int32_t>> groups(5);
+        const int nbk = usable_buckets();
+        std::vector<std::vector<int32_t>> groups(nbk + 1);
         for (int64_t r = lo; r < hi; ++r) {
             const int64_t deg = ptr[r + 1] - ptr[r];
-            int b = 4;
+            int b = nbk;                        // heavy: direct k x k system
             if (deg <= cap)
-                for (int i = 0; i < 4; ++i)
-                    if (deg <= dims[i]) { b = i; break; }
+                for (int i = 0; i < nbk; ++i)
+                    if (deg <= kBucketDim[i]) { b = i; break; }
             groups[b].push_back((int32_t)r);
         }
         std::vector<int32_t> flat;
         pl.bucket_off.assign(1, 0);
         pl.bucket_dim.clear();
-        for (int b = 0; b < 5; ++b) {
+        for (int b = 0; b <= nbk; ++b) {
             std::stable_sort(groups[b].begin(), groups[b].end(), [&](int32_t x, int32_t y) {
                 return ptr[x + 1] - ptr[x] > ptr[y + 1] - ptr[y];
             });
             int maxdeg = 1;
             if (!groups[b].empty()) maxdeg = (int)std::max<int64_t>(1, ptr[groups[b][0] + 1] - ptr[groups[b][0]]);
-            pl.bucket_dim.push_back(b < 4 ? std::min(maxdeg, dims[b]) : k);
+            pl.bucket_dim.push_back(b < nbk ? std::min(maxdeg, kBucketDim[b]) : k);
             flat.insert(flat.end(), groups[b].begin(), groups[b].end());
             pl.bucket_off.push_back((int64_t)flat.size());
         }
@@ -518,33 +545,48 @@ struct Engine : EngineBase {
         pl.lo = lo;
         pl.hi = hi;
         pl.cap = cap;
+        pl.n_buckets = nbk;
         return HYPREC_OK;
     }
 
-    // L^-1 and L^-T (dense k x k, float64) of B = 0.1 G + lambda I, G = Gram of the fixed side.
-    // k x k float64 tiles that fit one SM's shared memory (k <= ~230): one direct-mode launch on a row
-    // without positives exports the factored tiles, tri_inverse_kernel turns them into L^-1.
-    // Larger k: B is cut into r x r blocks of <= 192; diagonal blocks go through the same two kernels,
-    // panels and Schur updates through small float64 GEMMs (right-looking block Cholesky, then block
-    // forward substitution for the inverse).
-    int compute_linv(bool user, double lambda, const T* fixed_ptr) {
+    // L^-1 and L^-T (dense k x k, ALWAYS float64) of B = 0.1 G + lambda I, G = Gram of the fixed side.
+    // B is cut into r x r blocks that fit one SM's shared memory as float64 tiles (r = 1 up to
+    // k ~ 230, else blocks of <= 192): every diagonal block is factored by a direct-mode launch of the
+    // row kernel on a system without positives (tiles exported) and inverted by tri_inverse_kernel;
+    // panels and Schur updates are small float64 GEMMs (right-looking block Cholesky), and the inverse
+    // is assembled by block forward substitution.  In float32 mode the Gram is recomputed in float64
+    // from a float64 copy of the fixed side (the whitening must not see float32 rounding of B), and
+    // float32 copies of L^-1 / L^-T are made for the whitening GEMMs.
+    int compute_linv(bool user, double lambda, const T* fixed_ptr, int64_t n_fixed) {
         namespace hp = hyprec;
-        const int nb = hp::aug_blocks(k), n_tiles = hp::tri(nb);
         HY_TRY(linv.reserve(sizeof(double) * (size_t)k * k));
         HY_TRY(linv_t.reserve(sizeof(double) * (size_t)k * k));
         HY_TRY(dummy_ptr.reserve(2 * sizeof(int64_t)));
         CU_TRY(cudaMemsetAsync(dummy_ptr.ptr, 0, 2 * sizeof(int64_t), h->stream));
-        const bool whole = hp::solve_layout(8, k, 8, true, sizeof(T)).total <= (size_t)h->max_smem;
-        if (whole) {
-            HY_TRY(tiles.reserve(sizeof(T) * (size_t)hp::kTileElems * n_tiles));
-            HY_TRY(launch_rows(user, lambda, 0, 1, nullptr, 0, false, k, hp::kSolveThreads, fixed_ptr, nullptr,
-                               tiles.as<T>(), dummy_ptr.as<int64_t>(), 1, h->stream, 0));
-            HY_TRY(launch_tri_inverse(tiles.as<T>(), k, linv.as<T>(), linv_t.as<T>(), k));
-            return HYPREC_OK;
+        const double* gram_d = nullptr;
+        if (sizeof(T) == sizeof(double)) {
+            gram_d = gram[user ? 1 : 0].template as<double>();
+        } else {
+            HY_TRY(fixed_d.reserve(sizeof(double) * (size_t)n_fixed * k));
+            const int64_t cnt = n_fixed * k;
+            hp::cast_kernel<T, double><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(fixed_ptr, cnt, fixed_d.as<double>());
+            const int ntile = (k + hp::kGramTile - 1) / hp::kGramTile, tiles_g = hp::tri(ntile);
+            int nsplit = (int)std::min<int64_t>((n_fixed + 255) / 256, std::max(1, (4 * h->num_sms) / tiles_g));
+            int64_t per = (n_fixed + nsplit - 1) / nsplit;
+            per = (per + hp::kGramRows - 1) / hp::kGramRows * hp::kGramRows;
+            nsplit = (int)((n_fixed + per - 1) / per);
+            HY_TRY(gram_partial_d.reserve(sizeof(double) * (size_t)nsplit * k * k));
+            HY_TRY(gram_dbuf.reserve(sizeof(double) * (size_t)k * k));
+            hp::gram_partial_kernel<double><<<dim3(tiles_g, nsplit), hp::kGramThreads, 0, h->stream>>>(
+                fixed_d.as<double>(), n_fixed, k, per, gram_partial_d.as<double>());
+            hp::gram_reduce_kernel<double><<<(k * k + 255) / 256, 256, 0, h->stream>>>(gram_partial_d.as<double>(), nsplit, k,
+                                                                                     gram_dbuf.as<double>());
+            h->launches += 3;
+            gram_d = gram_dbuf.as<double>();
         }
-        // ---- blocked path (float64 only; T == double whenever the low-rank path runs)
-        const int r = (k + 191) / 192;
-        const int bs0 = (((k + r - 1) / r) + 7) / 8 * 8;
+        const bool whole = hp::solve_layout(8, k, 8, true, sizeof(double)).total <= (size_t)h->max_smem;
+        const int r = whole ? 1 : (k + 191) / 192;
+        const int bs0 = whole ? k : (((k + r - 1) / r) + 7) / 8 * 8;
         auto off = [&](int j) { return j * bs0; };
         auto size = [&](int j) { return std::min(bs0, k - j * bs0); };
         HY_TRY(bdense.reserve(sizeof(double) * (size_t)k * k));
@@ -556,7 +598,7 @@ struct Engine : EngineBase {
         double* B = bdense.as<double>();
         double* L = lfac.as<double>();
         double* X = linv.as<double>();
-        hp::build_base_dense_kernel<T><<<(k * k + 255) / 256, 256, 0, h->stream>>>(gram[user ? 1 : 0].as<T>(), k, lambda, B);
+        hp::build_base_dense_kernel<double><<<(k * k + 255) / 256, 256, 0, h->stream>>>(gram_d, k, lambda, B);
         CU_TRY(cudaMemsetAsync(X, 0, sizeof(double) * (size_t)k * k, h->stream));
         h->launches += 1;
         auto gemm = [&](int M, int N, int K, const double* A, const double* Bm, int trans_b, double* C, int ldc,
@@ -570,9 +612,8 @@ struct Engine : EngineBase {
             const int nt = hp::kTileElems * hp::tri(hp::aug_blocks(sj));
             hp::tiles_from_dense_kernel<<<(nt + 255) / 256, 256, 0, h->stream>>>(B, k, oj, sj, blk_base.as<double>());
             h->launches += 1;
-            HY_TRY(factor_block(blk_base.as<T>(), sj, tiles.as<T>()));
-            HY_TRY(launch_tri_inverse(tiles.as<T>(), sj, reinterpret_cast<T*>(X + (size_t)oj * k + oj),
-                                      reinterpret_cast<T*>(linv_t.as<double>() + (size_t)oj * k + oj), k));
+            HY_TRY(factor_block(blk_base.as<double>(), sj, tiles.as<double>()));
+            HY_TRY(launch_tri_inverse(tiles.as<double>(), sj, X + (size_t)oj * k + oj, linv_t.as<double>() + (size_t)oj * k + oj, k));
             for (int i = j + 1; i < r; ++i)     // L_ij = B_ij L_jj^-T
                 gemm(size(i), sj, sj, B + (size_t)off(i) * k + oj, X + (size_t)oj * k + oj, 1, L + (size_t)off(i) * k + oj, k, k, 1.0, 0.0);
             for (int i = j + 1; i < r; ++i)     // Schur update of the remaining lower blocks
@@ -591,21 +632,35 @@ struct Engine : EngineBase {
                                                                      k, -1.0, 0.0);
                 h->launches += 1;
             }
-        hp::transpose_dense_kernel<<<(k * k + 255) / 256, 256, 0, h->stream>>>(X, k, linv_t.as<double>());
-        h->launches += 1;
+        if (r > 1) {
+            hp::transpose_dense_kernel<<<(k * k + 255) / 256, 256, 0, h->stream>>>(X, k, linv_t.as<double>());
+            h->launches += 1;
+        }
+        if (sizeof(T) != sizeof(double)) {
+            HY_TRY(linv_f.reserve(sizeof(float) * (size_t)k * k));
+            HY_TRY(linv_t_f.reserve(sizeof(float) * (size_t)k * k));
+            const int64_t cnt = (int64_t)k * k;
+            hp::cast_kernel<double, float><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(X, cnt, linv_f.as<float>());
+            hp::cast_kernel<double, float><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(linv_t.as<double>(), cnt, linv_t_f.as<float>());
+            h->launches += 2;
+        }
         CU_TRY(cudaGetLastError());
         return HYPREC_OK;
     }
 
-    int launch_tri_inverse(const T* tile_ptr, int dim, T* out, T* out_t, int ld) {
+    // L^-1 / L^-T in the factor dtype (the float64 originals, or their float32 copies)
+    const T* linv_T() const { return sizeof(T) == sizeof(double) ? linv.template as<T>() : linv_f.template as<T>(); }
+    const T* linv_t_T() const { return sizeof(T) == sizeof(double) ? linv_t.template as<T>() : linv_t_f.template as<T>(); }
+
+    int launch_tri_inverse(const double* tile_ptr, int dim, double* out, double* out_t, int ld) {
         namespace hp = hyprec;
         const int nbk = (dim + hp::kTile - 1) / hp::kTile;
         const int n_tiles = hp::tri(hp::aug_blocks(dim));
-        size_t inv_smem = sizeof(T) * ((size_t)nbk * hp::kTileElems + hp::kTileElems);
-        const size_t with_tiles = inv_smem + sizeof(T) * (size_t)hp::kTileElems * n_tiles;
+        size_t inv_smem = sizeof(double) * ((size_t)nbk * hp::kTileElems + hp::kTileElems);
+        const size_t with_tiles = inv_smem + sizeof(double) * (size_t)hp::kTileElems * n_tiles;
         const int tis = with_tiles <= (size_t)h->max_smem ? 1 : 0;
         if (tis) inv_smem = with_tiles;
-        auto inv_kern = hp::tri_inverse_kernel<T>;
+        auto inv_kern = hp::tri_inverse_kernel<double>;
         CU_TRY(cudaFuncSetAttribute(inv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
         inv_kern<<<nbk, 64, inv_smem, h->stream>>>(tile_ptr, dim, tis, out, out_t, ld);
         h->launches += 1;
@@ -613,30 +668,27 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
-    // Direct-mode factorisation of one dim x dim SPD matrix given as base tiles; tiles exported.
-    int factor_block(const T* base_tiles, int dim, T* export_ptr) {
+    // Direct-mode float64 factorisation of one dim x dim SPD matrix given as base tiles; tiles exported.
+    int factor_block(const double* base_tiles, int dim, double* export_ptr) {
         namespace hp = hyprec;
-        const hp::SolveLayout lay = hp::solve_layout(8, dim, 8, true, sizeof(T));
+        const hp::SolveLayout lay = hp::solve_layout(8, dim, 8, true, sizeof(double));
         if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "factor_block: block too large");
-        auto kern = hp::als_solve_rows_kernel<T, 8>;
-        if ((int)lay.total > solve_smem_attr[1]) {
-            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-            solve_smem_attr[1] = (int)lay.total;
-        }
-        HY_TRY(dummy_out.reserve(sizeof(T) * (size_t)k));
+        auto kern = hp::als_solve_rows_kernel<double, 8>;
+        HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
+        HY_TRY(dummy_out.reserve(sizeof(double) * (size_t)k));
         CU_TRY(cudaMemsetAsync(counter.as<int>(), 0, sizeof(int), h->stream));   // slot 0
-        hp::SolveArgs<T> a;
+        hp::SolveArgs<double> a;
         a.indptr = dummy_ptr.as<int64_t>();
         a.indices = csr.indices.template as<int32_t>();
-        a.values = csr.values.template as<T>();
-        a.fixed = U.as<T>();
-        a.latent = dummy_out.as<T>();
+        a.values = nullptr;
+        a.fixed = nullptr;
+        a.latent = dummy_out.as<double>();
         a.base = base_tiles;
         a.prior = nullptr;
         a.a_scratch = nullptr;
         a.work_counter = counter.as<int>();
         a.status = counter.as<int>() + kStatusSlot;
-        a.lambda = T(0);
+        a.lambda = 0.0;
         a.k = dim;
         a.row_lo = 0;
         a.row_hi = 1;
@@ -680,57 +732,58 @@ struct Engine : EngineBase {
         const T* prior_ptr = (!user && has_prior) ? prior.as<T>() : nullptr;
         HY_TRY(ymat.reserve(sizeof(T)));
 
-        // The low-rank path needs float64 (it goes through L^-1 of 0.1 G + lambda I) and pays off
-        // when rows have far fewer positives than k.
-        const bool lowrank = sizeof(T) == sizeof(double) && h->lowrank_enabled && lambda > 0.0 && k >= 16;
+        // The low-rank path pays off when rows have fewer positives than k.  Its whitening
+        // (L^-1 of 0.1 G + lambda I) is always computed in float64; the deg x deg systems themselves
+        // are well conditioned and run in the factor dtype.
+        const bool lowrank = h->lowrank_enabled && lambda > 0.0 && k >= 16;
         if (!lowrank) {
             Timer t(h, HYPREC_T_SOLVE);
             HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
                                nullptr, nullptr, hi - lo, h->stream, 0));
         } else {
-            const int cap = std::min(k, 191);
+            const int cap = std::min(k, kBucketDim[usable_buckets() - 1]);
             HY_TRY(build_plan(user, lo, hi, cap));
             const RowPlan& pl = plan[user ? 0 : 1];
+            const int nbk = pl.n_buckets;
             const int32_t* lists = pl.lists.template as<int32_t>();
-            const int64_t n_light = pl.bucket_off[4];
-            const int64_t n_heavy = pl.bucket_off[5] - pl.bucket_off[4];
+            const int64_t n_light = pl.bucket_off[nbk];
+            const int64_t n_heavy = pl.bucket_off[nbk + 1] - pl.bucket_off[nbk];
             HY_TRY(ymat.reserve(sizeof(T) * (size_t)total * k));
             // rows above the cap do not depend on the factor of B: start them right away on their
             // own stream (base tiles and counters are ready on the main stream)
             CU_TRY(cudaEventRecord(h->ev_base, h->stream));
             if (n_heavy > 0) {
-                CU_TRY(cudaStreamWaitEvent(h->aux[4], h->ev_base, 0));
-                HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[4], n_heavy, false, k,
-                                   hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy, h->aux[4], 5));
-                CU_TRY(cudaEventRecord(h->ev_join[4], h->aux[4]));
+                CU_TRY(cudaStreamWaitEvent(h->aux[kHeavyStream], h->ev_base, 0));
+                HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[nbk], n_heavy, false, k,
+                                   hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy,
+                                   h->aux[kHeavyStream], 1 + kMaxBuckets));
+                CU_TRY(cudaEventRecord(h->ev_join[kHeavyStream], h->aux[kHeavyStream]));
             }
             if (n_light > 0) {
                 {
                     Timer t(h, HYPREC_T_PREP);
                     // 1-2. factor B = 0.1 G + lambda I = L L^T once and form L^-1, L^-T
-                    HY_TRY(compute_linv(user, lambda, fixed_ptr));
+                    HY_TRY(compute_linv(user, lambda, fixed_ptr, n_fixed));
                     // 3. whitened factors Q = Y L^-T (and theta L^-T for the item prior)
                     HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
-                    HY_TRY(gemm_nt(fixed_ptr, n_fixed, linv.as<T>(), k, qmat.as<double>()));
+                    HY_TRY(gemm_nt(fixed_ptr, n_fixed, linv_T(), k, qmat.as<T>()));
                     if (prior_ptr) {
                         HY_TRY(pq.reserve(sizeof(T) * (size_t)total * k));
-                        HY_TRY(gemm_nt(prior_ptr, total, linv.as<T>(), k, pq.as<double>()));
+                        HY_TRY(gemm_nt(prior_ptr, total, linv_T(), k, pq.as<T>()));
                     }
                 }
                 {
                     // 4. deg x deg systems, one launch per degree bucket, all buckets concurrently
                     Timer t(h, HYPREC_T_SOLVE);
-                    // small systems on 4 x 4 tiles (more threads with a tile, shorter FMA chains)
-                    static const int threads[4] = {64, 128, 128, 256};
-                    static const int tile[4] = {4, 4, 8, 8};
+                    // (small systems on 4 x 4 tiles: more threads with a tile, shorter FMA chains)
                     CU_TRY(cudaEventRecord(h->ev_fork, h->stream));
-                    for (int b = 0; b < 4; ++b) {
+                    for (int b = 0; b < nbk; ++b) {
                         const int64_t cnt = pl.bucket_off[b + 1] - pl.bucket_off[b];
                         if (cnt == 0) continue;
                         CU_TRY(cudaStreamWaitEvent(h->aux[b], h->ev_fork, 0));
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
-                                           threads[b], qmat.as<T>(), prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr,
-                                           cnt, h->aux[b], 1 + b, tile[b]));
+                                           kBucketThreads[b], qmat.as<T>(), prior_ptr ? pq.as<T>() : nullptr, nullptr,
+                                           nullptr, cnt, h->aux[b], 1 + b, kBucketTile[b]));
                         CU_TRY(cudaEventRecord(h->ev_join[b], h->aux[b]));
                         CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
                     }
@@ -739,12 +792,12 @@ struct Engine : EngineBase {
                     // 5. x = L^-T y for the low-rank rows: one GEMM straight into the factor matrix
                     Timer t(h, HYPREC_T_PREP);
                     T* latent = user ? U.as<T>() : V.as<T>();
-                    HY_TRY(gemm_nt(ymat.as<T>(), n_light, linv_t.as<T>(), k, (double*)latent, lists));
+                    HY_TRY(gemm_nt(ymat.as<T>(), n_light, linv_t_T(), k, latent, lists));
                 }
             }
             if (n_heavy > 0) {
                 Timer t(h, HYPREC_T_SOLVE);   // whatever of the heavy rows' launch is still running
-                CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[4], 0));
+                CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[kHeavyStream], 0));
             }
         }
         gram_ok[user ? 0 : 1] = false;
@@ -818,6 +871,7 @@ struct Engine : EngineBase {
             a.user_hi = hi;
             a.n_items = n;
             a.dense_out = dense_blk.as<double>();
+            a.dense_out_f32 = nullptr;
             a.row_list = nullptr;
             a.thresholds = nullptr;
             a.counts = nullptr;
@@ -1046,6 +1100,7 @@ struct Engine : EngineBase {
                 a.user_hi = hi;
                 a.n_items = n;
                 a.dense_out = nullptr;
+                a.dense_out_f32 = nullptr;
                 a.row_list = nullptr;
                 a.thresholds = thresholds.as<double>();
                 a.counts = counts.as<unsigned long long>();
@@ -1238,7 +1293,7 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < hyprec_ctx::kAux; ++i) {
         CU_TRY(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
     }
@@ -1271,7 +1326,7 @@ int hyprec_destroy(hyprec_t* h) {
     delete h->engine;
     h->harvest();
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < hyprec_ctx::kAux; ++i) {
         if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
         if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     }

@@ -26,6 +26,7 @@ struct SweepArgs {
     int k;
     int64_t user_lo, user_hi, n_items;
     double* dense_out;               // [user_hi-user_lo][n_items]          (kSweepStore)
+    float* dense_out_f32;            // (kSweepStore) when non-null the tile is stored here as float32 instead
     const int32_t* row_list;         // optional (kSweepStore): the "user" rows are row_list[user_lo..user_hi)
                                      // and row r of the product is stored at dense_out[row_list[r] * n_items]
     const double* thresholds;        // [n_users]                           (kSweepCount)
@@ -89,7 +90,10 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
                     const int64_t col = j0 + tx + 16 * b;
-                    if (col < p.n_items) p.dense_out[dst * p.n_items + col] = (double)acc[a][b];
+                    if (col < p.n_items) {
+                        if (p.dense_out_f32) p.dense_out_f32[dst * p.n_items + col] = (float)acc[a][b];
+                        else p.dense_out[dst * p.n_items + col] = (double)acc[a][b];
+                    }
                 }
             }
         } else {

@@ -56,7 +56,7 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
 static void gemm_nt(const double* a, int64_t ra, const double* b, int64_t rb, int k, double* c) {
     SweepArgs<double> s;
     s.user_vecs = a; s.item_vecs = b; s.k = k; s.user_lo = 0; s.user_hi = ra; s.n_items = rb;
-    s.dense_out = c; s.row_list = nullptr; s.thresholds = nullptr; s.counts = nullptr;
+    s.dense_out = c; s.dense_out_f32 = nullptr; s.row_list = nullptr; s.thresholds = nullptr; s.counts = nullptr;
     emu::launch(dim3((unsigned)((rb + kSweepTile - 1) / kSweepTile), (unsigned)((ra + kSweepTile - 1) / kSweepTile)),
                 dim3(kSweepThreads), 0, [&]() { score_sweep_kernel<double, kSweepStore>(s); });
 }
@@ -149,7 +149,7 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
         std::vector<unsigned long long> counts(nu, 0);
         SweepArgs<T> a;
         a.user_vecs = U; a.item_vecs = V; a.k = k; a.user_lo = lo; a.user_hi = hi; a.n_items = n;
-        a.dense_out = nullptr; a.row_list = nullptr; a.thresholds = thr; a.counts = counts.data();
+        a.dense_out = nullptr; a.dense_out_f32 = nullptr; a.row_list = nullptr; a.thresholds = thr; a.counts = counts.data();
         emu::launch(dim3((unsigned)((n + kSweepTile - 1) / kSweepTile), (unsigned)((nu + kSweepTile - 1) / kSweepTile)),
                     dim3(kSweepThreads), 0, [&]() { score_sweep_kernel<T, kSweepCount>(a); });
         for (int64_t u = 0; u < nu; ++u) ones[u] = (int64_t)counts[u];
@@ -238,7 +238,7 @@ void emu_eval_prefilter_f64(const double* U, const double* V, int64_t m, int64_t
 void emu_predict_f64(const double* U, const double* V, int64_t m, int64_t n, int k, double* out) {
     SweepArgs<double> a;
     a.user_vecs = U; a.item_vecs = V; a.k = k; a.user_lo = 0; a.user_hi = m; a.n_items = n;
-    a.dense_out = out; a.row_list = nullptr; a.thresholds = nullptr; a.counts = nullptr;
+    a.dense_out = out; a.dense_out_f32 = nullptr; a.row_list = nullptr; a.thresholds = nullptr; a.counts = nullptr;
     emu::launch(dim3((unsigned)((n + kSweepTile - 1) / kSweepTile), (unsigned)((m + kSweepTile - 1) / kSweepTile)),
                 dim3(kSweepThreads), 0, [&]() { score_sweep_kernel<double, kSweepStore>(a); });
 }

@@ -380,7 +380,7 @@ def our_arm(args, wl):
     work = algorithmic_work(wl)
     elem = 8 if args.precision == "fp64" else 4
     solve_ms = per_step["solve"]
-    lowrank = args.precision == "fp64" and os.environ.get("HYPREC_LOWRANK", "1") != "0"
+    lowrank = os.environ.get("HYPREC_LOWRANK", "1") != "0"
     peak = h.probe_fma_tflops(precision)
     solve_flops = work["lowrank_flops_per_epoch"] if lowrank else work["solve_flops_per_epoch"]
     achieved = solve_flops / (solve_ms * 1e-3) / 1e12
@@ -390,7 +390,11 @@ def our_arm(args, wl):
         hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured"
     solve_gbs = work["solve_bytes_per_epoch"](elem) / (solve_ms * 1e-3) / 1e9
     sweep_tflops = work["eval_flops"] / (max(per_step["count"], 1e-9) * 1e-3) / 1e12
-    topk_bytes = (float(wl["cand_ids"].shape[0]) if has_eval else 0.0) * (k * elem + 4) + m * 200 * 20
+    tf32_peak = None
+    if os.path.exists(peaks_file):
+        tf32_peak = json.load(open(peaks_file))["bf16_tflops"] / 2.0
+    # pre-filtered top-k: one 32-byte sector of s~ per candidate + ~200 exact re-scores per user
+    topk_bytes = (float(wl["cand_ids"].shape[0]) if has_eval else 0.0) * 36.0 + m * 200 * (k * elem + 20)
     topk_gbs = topk_bytes / (max(per_step["topk"], 1e-9) * 1e-3) / 1e9
     roofline = dict(kernel="als_solve_rows_kernel (row systems of one epoch; %s)" %
                            ("deg x deg low-rank systems in 4 concurrent degree buckets + direct k x k for heavy rows"
@@ -404,12 +408,19 @@ def our_arm(args, wl):
                              peak_source=hbm_src + " MEASURED_PEAKS.json",
                              algorithmic_bytes=work["solve_bytes_per_epoch"](elem)),
                     other_kernels=dict(
-                        score_sweep_count=dict(bound="%s_fma" % args.precision, achieved=sweep_tflops, peak=peak,
-                                               unit="TFLOP/s", frac=sweep_tflops / peak if peak else None,
-                                               flops=work["eval_flops"]),
-                        eval_topk=dict(bound="l2 gather (candidate factor rows re-read per user; V is L2-resident)",
+                        tc_score_sweep=dict(
+                            kernel="tc::tc_score_kernel (tcgen05 kind::tf32, 3xTF32 split; count class also holds the "
+                                   "split / norm / re-check helpers, ~0.06 ms)",
+                            bound="tensor", achieved=3.0 * sweep_tflops, peak=tf32_peak, unit="TFLOP/s",
+                            frac=(3.0 * sweep_tflops / tf32_peak) if tf32_peak else None,
+                            peak_source="MEASURED_PEAKS.json bf16_tflops / 2 (dense TF32 runs at half the bf16 rate)",
+                            flops=3.0 * work["eval_flops"], traffic=368.4e6,
+                            traffic_source="ncu --set full dram__bytes_read+write, profiles/r01_step_v3_summary.md "
+                                           "(algorithmic: 36 MB factors in + 378 MB float32 scores out)"),
+                        eval_topk=dict(bound="l2/hbm sector gathers of the float32 score rows + ~200 factor rows per user",
                                        achieved=topk_gbs, peak=hbm_peak, unit="GB/s", frac=topk_gbs / hbm_peak,
-                                       bytes=topk_bytes, note="bytes gathered through L2, against the HBM copy peak")))
+                                       bytes=topk_bytes, traffic=539.1e6,
+                                       traffic_source="ncu --set full, profiles/r01_step_v3_summary.md")))
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     literal = wl["train"] is not None      # the literal arithmetic needs the dense train matrix

@@ -180,7 +180,7 @@ struct Engine : EngineBase {
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
     DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
     DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out, prof_buf, bdense, lfac, blk_tmp, blk_base;
-    DevBuf fixed_d, gram_partial_d, gram_dbuf, linv_f, linv_t_f;
+    DevBuf fixed_d, gram_partial_d, gram_dbuf, linv_f, linv_t_f, stage_d;
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
     static constexpr int kHeavyStream = 6;   // aux streams 0..5: degree buckets, 6: rows above the cap
@@ -203,7 +203,7 @@ struct Engine : EngineBase {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
-                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &plan[0].lists, &plan[1].lists,
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
@@ -287,18 +287,21 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+    // Host factors are float64 (the reference's dtype); in float32 mode the conversion runs on the
+    // device through a float64 staging buffer, so the host side is a plain (DMA-able) copy either way.
     int upload_matrix(DevBuf& dst, const double* src, int64_t rows) {
         const size_t count = (size_t)rows * k;
         HY_TRY(dst.reserve(sizeof(T) * count));
         if (sizeof(T) == sizeof(double)) {
             CU_TRY(cudaMemcpyAsync(dst.ptr, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
-            CU_TRY(cudaStreamSynchronize(h->stream));
         } else {
-            std::vector<T> tmp(count);
-            for (size_t i = 0; i < count; ++i) tmp[i] = (T)src[i];
-            CU_TRY(cudaMemcpyAsync(dst.ptr, tmp.data(), sizeof(T) * count, cudaMemcpyHostToDevice, h->stream));
-            CU_TRY(cudaStreamSynchronize(h->stream));
+            HY_TRY(stage_d.reserve(sizeof(double) * count));
+            CU_TRY(cudaMemcpyAsync(stage_d.ptr, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+            hyprec::cast_kernel<double, T><<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(stage_d.as<double>(), (int64_t)count,
+                                                                                                 dst.template as<T>());
+            h->launches += 1;
         }
+        CU_TRY(cudaStreamSynchronize(h->stream));
         return HYPREC_OK;
     }
 
@@ -306,13 +309,14 @@ struct Engine : EngineBase {
         const size_t count = (size_t)rows * k;
         if (sizeof(T) == sizeof(double)) {
             CU_TRY(cudaMemcpyAsync(dst, src.ptr, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
-            CU_TRY(cudaStreamSynchronize(h->stream));
         } else {
-            std::vector<T> tmp(count);
-            CU_TRY(cudaMemcpyAsync(tmp.data(), src.ptr, sizeof(T) * count, cudaMemcpyDeviceToHost, h->stream));
-            CU_TRY(cudaStreamSynchronize(h->stream));
-            for (size_t i = 0; i < count; ++i) dst[i] = (double)tmp[i];
+            HY_TRY(stage_d.reserve(sizeof(double) * count));
+            hyprec::cast_kernel<T, double><<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(src.template as<T>(), (int64_t)count,
+                                                                                                 stage_d.as<double>());
+            h->launches += 1;
+            CU_TRY(cudaMemcpyAsync(dst, stage_d.ptr, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
         }
+        CU_TRY(cudaStreamSynchronize(h->stream));
         return HYPREC_OK;
     }
 

@@ -311,6 +311,37 @@ def test_large_k_paths(native, k):
         h.close()
 
 
+def test_cached_candidates_and_pinned_outputs(native):
+    """hyprec_set_candidates + NULL lists == passing the lists on every call; outputs may live in
+    page-locked memory from hyprec_host_alloc."""
+    full, train, test, u0, v0, cands = synthetic(120, 500, 16, 3000, seed=21)
+    h, _ = make_handle(native, train)
+    h.set_eval_csr((full.indptr, full.indices, full.data), (test.indptr, test.indices, test.data))
+    h.set_factors(u0 - 0.4, v0 - 0.5)
+    m = full.shape[0]
+    cp = numpy.zeros(m + 1, numpy.int64)
+    cp[1:] = numpy.cumsum([len(c) for c in cands])
+    ci = numpy.concatenate(cands)
+    direct = h.eval_topk(50, cp, ci, n_train_nz=train.nnz, n_test_nz=test.nnz)
+    h.set_candidates(cp, ci)
+    cached = h.eval_topk(50, None, None, n_train_nz=train.nnz, n_test_nz=test.nnz)
+    pinned = dict(thresholds=h.pinned_empty(m), ones_per_row=h.pinned_empty(m, numpy.int64),
+                  topk_idx=h.pinned_empty((m, 50), numpy.int32), topk_val=h.pinned_empty((m, 50)),
+                  topk_hit=h.pinned_empty((m, 50)), train_flags=h.pinned_empty(train.nnz, numpy.uint8),
+                  test_flags=h.pinned_empty(test.nnz, numpy.uint8))
+    h.eval_topk(50, None, None, n_train_nz=train.nnz, n_test_nz=test.nnz, out=pinned)
+    for key in direct:
+        assert numpy.array_equal(direct[key], cached[key]), key
+        assert numpy.array_equal(direct[key], pinned[key]), key
+    # a sub-range without cached lists means "all items"
+    part = h.eval_topk(7, None, None, 3, 5, want_counts=False)
+    u, v = h.get_factors()
+    want, _ = oev.top_recommendations_stream(numpy.arange(v.shape[0]), u[3].dot(v.T), 7)
+    assert list(part["topk_idx"][0]) == want
+    h.set_candidates(None, None)
+    h.close()
+
+
 def test_errors_are_loud(native):
     full, train, test, u0, v0, cands = synthetic(30, 90, 4, 300, seed=1)
     h, _ = make_handle(native, train)

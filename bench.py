@@ -407,7 +407,7 @@ def our_arm(args, wl):
                     hbm=dict(achieved=solve_gbs, peak=hbm_peak, unit="GB/s", frac=solve_gbs / hbm_peak,
                              peak_source=hbm_src + " MEASURED_PEAKS.json",
                              algorithmic_bytes=work["solve_bytes_per_epoch"](elem)),
-                    other_kernels=dict(
+                    other_kernels=None if not has_eval else dict(
                         tc_score_sweep=dict(
                             kernel="tc::tc_score_kernel (tcgen05 kind::tf32, 3xTF32 split; count class also holds the "
                                    "split / norm / re-check helpers, ~0.06 ms)",

@@ -36,6 +36,9 @@
 // ~k/deg times fewer serial factorisation steps.
 #pragma once
 #include "common.cuh"
+#ifndef HYPREC_EMU
+#include "tc_syrk.cuh"
+#endif
 
 namespace hyprec {
 
@@ -43,7 +46,7 @@ constexpr int kSolveThreads = 256;
 
 struct SolveLayout {
     int nb, n_tiles, kpad, ystride, chunk_rows;
-    size_t off_a, off_y, off_z, off_x, off_idx, off_map, total;
+    size_t off_a, off_y, off_z, off_x, off_idx, off_map, off_bar, total;
 };
 
 // Shared-memory plan for systems of dimension <= max_dim (k in direct mode, the largest row
@@ -54,7 +57,10 @@ struct SolveLayout {
 // (odd, so the low-rank gather's column-wise stores spread over banks).
 HYPREC_HD int aug_blocks_ts(int dim, int ts) { return (dim + 1 + ts - 1) / ts; }
 
-HYPREC_HD SolveLayout solve_layout(int ts, int max_dim, int chunk_rows, bool a_in_smem, size_t elem) {
+// stage_bytes > 0 (tensor-core launches, tc_syrk.cuh): the two operand staging stages alias the tile
+// storage and the staging buffer from offset 0, the buffer is 1024-byte aligned by the kernel (the
+// slack is part of `total`), and two mbarriers + the TMEM base slot follow the tile map.
+HYPREC_HD SolveLayout solve_layout(int ts, int max_dim, int chunk_rows, bool a_in_smem, size_t elem, size_t stage_bytes = 0) {
     SolveLayout l;
     l.nb = aug_blocks_ts(max_dim, ts);
     l.n_tiles = tri(l.nb);
@@ -66,6 +72,7 @@ HYPREC_HD SolveLayout solve_layout(int ts, int max_dim, int chunk_rows, bool a_i
     if (a_in_smem) o += elem * (size_t)(ts * ts) * l.n_tiles;
     l.off_y = o;
     o += elem * (size_t)chunk_rows * l.ystride;
+    if (o < 2 * stage_bytes) o = 2 * stage_bytes;
     l.off_z = o;
     o += elem * (size_t)l.kpad;
     l.off_x = o;
@@ -74,6 +81,8 @@ HYPREC_HD SolveLayout solve_layout(int ts, int max_dim, int chunk_rows, bool a_i
     o = l.off_idx + 4 * (size_t)l.kpad;
     l.off_map = o;
     o += 2 * (size_t)l.n_tiles;
+    l.off_bar = (o + 7) & ~(size_t)7;
+    if (stage_bytes > 0) o = l.off_bar + 32 + 1024;
     l.total = (o + 15) & ~(size_t)15;
     return l;
 }
@@ -101,6 +110,7 @@ struct SolveArgs {
     int lowrank;              // 0: direct k x k systems; 1: deg x deg systems on whitened factors
     T* ymat;                  // low-rank output [n_rows][k]
     T* export_tiles;          // direct mode: factored tiles of the processed row (single-row launch)
+    int tmem_cols;            // tensor-core launches: TMEM columns to allocate (tc::syrk_tmem_cols)
     long long* prof;          // optional: per-phase clock64() totals of block 0 (tools/solve_phases.py)
 };
 
@@ -286,16 +296,27 @@ __device__ __forceinline__ void trailing_update_tile(T* A, int NT, const T* ybuf
     }
 #endif
 
-template <typename T, int TS>
+// TC (float32, TS == 8, low-rank launches, sm_100a only): the rank-k accumulation runs on the tensor
+// cores (tc_syrk.cuh) instead of the SIMT rank-1 loop; everything after it is shared.
+template <typename T, int TS, bool TC = false>
 __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows_kernel(SolveArgs<T> p) {
-    HYPREC_DYN_SMEM(smem_raw);
+    HYPREC_DYN_SMEM(smem_dyn);
+    unsigned char* smem_raw = smem_dyn;
+#ifndef HYPREC_EMU
+    if (TC) smem_raw = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B staging
+#endif
     long long prof_t = 0;
     __shared__ long long s_row;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid % 32, warp = tid / 32, nwarps = nthreads / 32;
     const int k = p.k;
     const bool lowrank = p.lowrank != 0;
+#ifndef HYPREC_EMU
+    const SolveLayout lay = solve_layout(TS, p.max_dim, p.chunk_rows, p.a_scratch == nullptr, sizeof(T),
+                                         TC ? tc::syrk_stage_bytes(p.max_dim) : 0);
+#else
     const SolveLayout lay = solve_layout(TS, p.max_dim, p.chunk_rows, p.a_scratch == nullptr, sizeof(T));
+#endif
     const int CH = lay.chunk_rows, ystride = lay.ystride;
     T* A = p.a_scratch ? p.a_scratch + (size_t)blockIdx.x * (TS * TS) * lay.n_tiles : (T*)(smem_raw + lay.off_a);
     T* ybuf = (T*)(smem_raw + lay.off_y);
@@ -312,6 +333,26 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
         tmap[2 * t] = (unsigned char)bi;
         tmap[2 * t + 1] = (unsigned char)bj;
     }
+#ifndef HYPREC_EMU
+    tc::SyrkState tcs;
+    if (TC) {
+        tcs.bars = (uint64_t*)(smem_raw + lay.off_bar);
+        uint32_t* tmem_slot = (uint32_t*)(tcs.bars + 2);
+        tcs.phase[0] = tcs.phase[1] = 0;
+        tcs.stage = smem_raw;
+        tcs.rows_pad = tc::syrk_rows_pad(p.max_dim);
+        if (tid == 0) {
+            tc::mbar_init(&tcs.bars[0], 1);
+            tc::mbar_init(&tcs.bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 0) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        tcs.tmem_base = *tmem_slot;
+    }
+#endif
 
     while (true) {
         __syncthreads();   // previous row finished with A / zvec / xvec / idxs / s_row; tmap visible
@@ -351,6 +392,20 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
             }
         }
 
+#ifndef HYPREC_EMU
+        if constexpr (TC) {
+            // ---- S = I + 0.9 Q_r Q_r^T on the tensor cores, then the rhs row and the padding ---
+            __syncthreads();   // idxs / xvec complete
+            tc::syrk_lowrank(p.fixed, idxs, dim, k, tcs, (float*)A, NT, (float)pos_scale);
+            for (int e = tid; e < nb * TS * TS; e += nthreads) {
+                const int bj = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
+                const int i = (nb - 1) * TS + r, j = bj * TS + c;
+                if (i >= dim) A[(size_t)(r * TS + c) * NT + tile_id(nb - 1, bj)] = (i == dim && j < dim) ? xvec[j] : T(0);
+            }
+            __syncthreads();
+        } else
+#endif
+        {
         // ---- gather + rank-1 accumulation, CH vectors at a time --------------------------------
         const int nchunks = nvec == 0 ? 1 : (nvec + CH - 1) / CH;
         for (int ch = 0; ch < nchunks; ++ch) {
@@ -451,6 +506,7 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
             }
             __syncthreads();
         }
+        }
         HYPREC_PROF(0)   // gather + rank-1 accumulation
         if (!lowrank) {
 #pragma unroll 8
@@ -540,6 +596,12 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
             __syncthreads();
         }
         HYPREC_PROF(7)   // back substitution
+#ifndef HYPREC_EMU
+        if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {
+            p.prof[8] += 1;
+            p.prof[9] += deg;
+        }
+#endif
         if (!lowrank) {
             for (int c = tid; c < k; c += nthreads) {
                 const T v = xvec[c];
@@ -564,7 +626,15 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
                 out[a] = s;
             }
         }
+        HYPREC_PROF(10)   // solution write / low-rank y = Q_r^T t + p
     }
+#ifndef HYPREC_EMU
+    if (TC) {
+        tc::tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc(tcs.tmem_base, (uint32_t)p.tmem_cols);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

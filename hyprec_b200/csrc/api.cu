@@ -106,6 +106,8 @@ struct hyprec_ctx {
     int64_t launches = 0;
     bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
     bool tc_enabled = true;        // HYPREC_TC=0 keeps the score sweep on the SIMT kernel
+    bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
+    int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
     bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
     int64_t user_lo = 0, user_hi = -1, item_lo = 0, item_hi = -1;   // shard; hi < 0 => all
@@ -399,7 +401,7 @@ struct Engine : EngineBase {
     // Launch the row kernel over a contiguous range or a row list, in direct or low-rank mode.
     int launch_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
                     bool lowrank, int max_dim, int threads, const T* fixed_ptr, const T* prior_ptr, T* export_ptr,
-                    const int64_t* indptr_override, int64_t work, cudaStream_t st, int slot, int ts = 8) {
+                    const int64_t* indptr_override, int64_t work, cudaStream_t st, int slot, int ts = 8, bool tc = false) {
         // export_ptr != null: the single-row launch that only factors B -- its (zero) solution must
         // not land in the factor matrix
         T* latent_ptr = user ? U.as<T>() : V.as<T>();
@@ -411,18 +413,24 @@ struct Engine : EngineBase {
         // shared-memory plan: tiles in shared memory when they fit, else per-CTA global scratch
         // rank-1 vectors staged per round: small systems take long rounds (fewer gather latencies)
         int chunk = lowrank ? (max_dim <= 63 ? 64 : (max_dim <= 127 ? 32 : 16)) : 32;
-        hyprec::SolveLayout lay = hyprec::solve_layout(ts, max_dim, chunk, true, sizeof(T));
+        if (tc) chunk = 8;   // the staging buffer only serves as the panel buffer
+        const size_t stage_bytes = tc ? hyprec::tc::syrk_stage_bytes(max_dim) : 0;
+        hyprec::SolveLayout lay = hyprec::solve_layout(ts, max_dim, chunk, true, sizeof(T), stage_bytes);
         while (lay.total > (size_t)h->max_smem && chunk > 8) {
             chunk /= 2;
-            lay = hyprec::solve_layout(ts, max_dim, chunk, true, sizeof(T));
+            lay = hyprec::solve_layout(ts, max_dim, chunk, true, sizeof(T), stage_bytes);
         }
         const bool in_smem = lay.total <= (size_t)h->max_smem;
+        if (tc && !in_smem) return fail(HYPREC_E_UNSUPPORTED, "tensor-core row launch does not fit shared memory");
         if (!in_smem) {
             chunk = 16;
             lay = hyprec::solve_layout(ts, max_dim, chunk, false, sizeof(T));
             if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "n_factors too large for the solve kernel");
         }
         auto kern = ts == 4 ? hyprec::als_solve_rows_kernel<T, 4> : hyprec::als_solve_rows_kernel<T, 8>;
+        if constexpr (sizeof(T) == sizeof(float)) {
+            if (tc) kern = hyprec::als_solve_rows_kernel<T, 8, true>;
+        }
         HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
         int per_sm = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));
@@ -454,8 +462,9 @@ struct Engine : EngineBase {
         a.lowrank = lowrank ? 1 : 0;
         a.ymat = ymat.as<T>();
         a.export_tiles = export_ptr;
+        a.tmem_cols = tc ? hyprec::tc::syrk_tmem_cols(max_dim) : 0;
         a.prof = nullptr;
-        if (h->prof_enabled && !export_ptr && slot == 0) {
+        if (h->prof_enabled && !export_ptr && slot == h->prof_slot) {
             if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
             a.prof = prof_buf.as<long long>();
         }
@@ -703,6 +712,7 @@ struct Engine : EngineBase {
         a.lowrank = 0;
         a.ymat = nullptr;
         a.export_tiles = export_ptr;
+        a.tmem_cols = 0;
         a.prof = nullptr;
         kern<<<1, hp::kSolveThreads, lay.total, h->stream>>>(a);
         h->launches += 1;
@@ -785,9 +795,13 @@ struct Engine : EngineBase {
                         const int64_t cnt = pl.bucket_off[b + 1] - pl.bucket_off[b];
                         if (cnt == 0) continue;
                         CU_TRY(cudaStreamWaitEvent(h->aux[b], h->ev_fork, 0));
+                        // float32 systems of 64+ rows build S on the tensor cores (tc_syrk.cuh)
+                        const bool tc = h->tc_solve_enabled && sizeof(T) == sizeof(float) && kBucketTile[b] == 8 &&
+                                        k % 4 == 0 && pl.bucket_dim[b] <= 256;
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
-                                           kBucketThreads[b], qmat.as<T>(), prior_ptr ? pq.as<T>() : nullptr, nullptr,
-                                           nullptr, cnt, h->aux[b], 1 + b, kBucketTile[b]));
+                                           tc ? hyprec::kSolveThreads : kBucketThreads[b], qmat.as<T>(),
+                                           prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
+                                           kBucketTile[b], tc));
                         CU_TRY(cudaEventRecord(h->ev_join[b], h->aux[b]));
                         CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
                     }
@@ -1315,6 +1329,10 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     }
     const char* pf = getenv("HYPREC_SOLVE_PROF");
     h->prof_enabled = pf && pf[0] == '1';
+    const char* ts_env = getenv("HYPREC_TC_SOLVE");
+    h->tc_solve_enabled = h->tc_enabled && !(ts_env && ts_env[0] == '0');
+    const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");
+    if (ps) h->prof_slot = atoi(ps);
     const char* lr = getenv("HYPREC_LOWRANK");
     h->lowrank_enabled = !(lr && lr[0] == '0');
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);

@@ -1,0 +1,171 @@
+// Tensor-core construction of one row's normal matrix inside the fused row-solve kernel
+// (als_solve.cuh), float32 mode, sm_100a.
+//
+// Replaces the arithmetic of `(Y.T * confidence).dot(Y)` restricted to the row's positives
+// (/root/reference/lib/collaborative_filtering.py:84-85, :92), in the two forms the row kernel uses:
+//   low-rank rows   S = I + 0.9 Q_r Q_r^T      Q_r = the deg gathered rows of the whitened factors;
+//                   a [deg x k] x [k x deg] product, both operands K-major (a gathered row is
+//                   contiguous along k)
+// The gathered rows are split x = hi + lo (both TF32) on their way into shared memory and the product is
+// accumulated as hi*hi + hi*lo + lo*hi in float32 (3xTF32, error ~2^-22 per term: float32-level),
+// by tcgen05.mma with the accumulator in tensor memory.  Only the gather (coalesced 16-byte loads,
+// 8 in flight per thread), the split and the final TMEM -> tile copy run on the SIMT cores; the
+// gather of k-block b+1 overlaps the MMAs of k-block b (two staging stages, mbarrier hand-over).
+//
+// Staging layout per stage: `rows_pad` rows x 128 bytes (32 floats of one k-block), SWIZZLE_128B
+// K-major (16-byte chunk c of row r at (r/8)*1024 + (r%8)*128 + ((c ^ (r%8)) * 16)), hi rows first,
+// then the lo rows.  The stages alias the tile storage of the system being built: the tiles are
+// written only after the last MMA has retired.
+//
+// Accumulators: D00 = rows 0..127 x cols 0..127 at TMEM column 0; for systems above 128 rows
+// D1 = rows 128..255 x cols 0..255 at TMEM column 128 (the upper-right block is never formed).
+#pragma once
+#include "tc_score.cuh"
+
+namespace hyprec {
+namespace tc {
+
+constexpr int kSyrkKB = 32;   // factors per k-block = one 128-byte swizzle row
+
+__host__ __device__ __forceinline__ int syrk_rows_pad(int max_dim) { return max_dim <= 128 ? 128 : 256; }
+// both stages (hi + lo each)
+__host__ __device__ __forceinline__ size_t syrk_stage_bytes(int max_dim) { return (size_t)syrk_rows_pad(max_dim) * 128 * 2; }
+__host__ __device__ __forceinline__ int syrk_tmem_cols(int max_dim) { return max_dim <= 128 ? 128 : 512; }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
+}
+
+struct SyrkState {
+    uint64_t* bars;       // [2] one per staging stage, count 1 (tcgen05.commit arrives)
+    uint32_t phase[2];    // parity of the next completion to wait for
+    uint32_t tmem_base;
+    unsigned char* stage; // 1024-byte aligned, 2 * syrk_stage_bytes
+    int rows_pad;
+};
+
+// S = I + scale * Q_r Q_r^T for the `dim` rows idxs[0..dim) of `fixed` ([.][k], k % 4 == 0), written
+// into the TS=8 tile storage A (lower-triangle tiles, full diagonal tiles).  All threads of the CTA
+// call it (blockDim.x a multiple of 128); A aliases the staging stages.
+__device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, const int* idxs, int dim, int k,
+                                             SyrkState& st, float* A, int NT, float scale) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int warp = tid / 32, lane = tid % 32, nwarps = nthreads / 32;
+    const int chunk = tid & 7, r0 = tid >> 3, rpp = nthreads >> 3;
+    const int nkb = (k + kSyrkKB - 1) / kSyrkKB;
+    const size_t half_bytes = (size_t)st.rows_pad * 128;          // hi rows, then lo rows
+    const size_t stage_bytes = 2 * half_bytes;
+    const int npad = (dim + 15) & ~15;
+    const bool two = dim > 128;
+    bool pending[2] = {false, false};
+
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        const int col = kb * kSyrkKB + chunk * 4;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = r0 + j * rpp;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < dim && col < k) v[j] = __ldg(reinterpret_cast<const float4*>(fixed + (int64_t)idxs[r] * k + col));
+        }
+        if (pending[s]) {     // the MMAs that read this stage two k-blocks ago have retired
+            mbar_wait(&st.bars[s], st.phase[s]);
+            st.phase[s] ^= 1;
+            pending[s] = false;
+        }
+        unsigned char* hi_base = st.stage + (size_t)s * stage_bytes;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = r0 + j * rpp;
+            if (r < dim) {
+                float4 h, l;
+                split_tf32(v[j].x, h.x, l.x);
+                split_tf32(v[j].y, h.y, l.y);
+                split_tf32(v[j].z, h.z, l.z);
+                split_tf32(v[j].w, h.w, l.w);
+                const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((chunk ^ (r & 7)) << 4);
+                *reinterpret_cast<float4*>(hi_base + off) = h;
+                *reinterpret_cast<float4*>(hi_base + half_bytes + off) = l;
+            }
+        }
+        fence_async_smem();      // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t sa = smem_u32(hi_base);
+            const uint64_t a0_hi = umma_desc(sa), a0_lo = umma_desc(sa + (uint32_t)half_bytes);
+            const uint64_t a1_hi = umma_desc(sa + 128 * 128), a1_lo = umma_desc(sa + (uint32_t)half_bytes + 128 * 128);
+            const uint32_t idesc0 = umma_idesc_tf32(128, two ? 128 : npad);
+            const uint32_t idesc1 = umma_idesc_tf32(128, npad);
+#pragma unroll
+            for (int ks = 0; ks < kSyrkKB / 8; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
+                const uint32_t accum = (kb | ks) != 0;
+                umma_tf32(st.tmem_base, a0_hi + adv, a0_hi + adv, idesc0, accum);
+                umma_tf32(st.tmem_base, a0_hi + adv, a0_lo + adv, idesc0, 1);
+                umma_tf32(st.tmem_base, a0_lo + adv, a0_hi + adv, idesc0, 1);
+                if (two) {
+                    umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_hi + adv, idesc1, accum);
+                    umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_lo + adv, idesc1, 1);
+                    umma_tf32(st.tmem_base + 128, a1_lo + adv, a0_hi + adv, idesc1, 1);
+                }
+            }
+            umma_commit(&st.bars[s]);
+        }
+        pending[s] = true;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+        if (pending[s]) {
+            mbar_wait(&st.bars[s], st.phase[s]);
+            st.phase[s] ^= 1;
+        }
+    tc_fence_after();
+    __syncthreads();          // every thread is past its last staging access: A may be overwritten
+
+    // ---- TMEM -> tiles: lane = system row, 32 columns per load; only tiles on or below the diagonal
+    const int quad = warp & 3, half = warp >> 2, nhalf = nwarps >> 2;
+    for (int mb = 0; mb < (two ? 2 : 1); ++mb) {
+        const int row_base = mb * 128 + quad * 32;
+        if (row_base >= dim) continue;
+        const int i = row_base + lane;
+        const int jmax = min(dim, row_base + 32);
+        const int bi = i >> 3, ri = i & 7;
+        for (int c = 0; c < jmax; c += 32) {
+            if (((c >> 5) % nhalf) != half) continue;
+            uint32_t v[32];
+            const uint32_t taddr = st.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mb ? 128 : 0) + (uint32_t)c;
+            tmem_load_32x32(taddr, v);
+            if (i < dim) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int j = c + jj;
+                    const int bj = j >> 3;
+                    if (j < dim && bj <= bi)
+                        A[(size_t)(ri * 8 + (j & 7)) * NT + (bi * (bi + 1) / 2 + bj)] =
+                            scale * __uint_as_float(v[jj]) + (i == j ? 1.f : 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+}
+
+}  // namespace tc
+}  // namespace hyprec

@@ -311,6 +311,31 @@ def test_large_k_paths(native, k):
         h.close()
 
 
+@pytest.mark.parametrize("m,n,k,nnz", [(60, 900, 256, 11000), (80, 800, 200, 9000), (48, 1000, 96, 5000),
+                                       (70, 900, 300, 9000)])
+def test_tensor_core_row_systems_fp32(native, monkeypatch, m, n, k, nnz):
+    """float32 low-rank systems of 64..256 rows build S = I + 0.9 Q_r Q_r^T with tcgen05 (3xTF32,
+    tc_syrk.cuh): same factors as the SIMT accumulation (HYPREC_TC_SOLVE=0) to float32 rounding, and
+    within the stated float32 tolerance of the float64 oracle."""
+    full, train, test, u0, v0, cands = synthetic(m, n, k, nnz, seed=k + 1, empty=False)
+    deg = numpy.diff(train.indptr)
+    assert (deg > 128).any() and ((deg > 63) & (deg <= 128)).any(), deg   # both accumulator shapes
+    u = oals.als_half_step(u0.copy(), v0, train, 0.01)
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("HYPREC_TC_SOLVE", flag)
+        h, _ = make_handle(native, train, native.F32)
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        got[flag], _ = h.get_factors()
+        h.close()
+    print("k=%d tc vs oracle %.2e, simt vs oracle %.2e, tc vs simt %.2e" %
+          (k, rel_frob(got["1"], u), rel_frob(got["0"], u), rel_frob(got["1"], got["0"])))
+    assert rel_frob(got["1"], u) < F32_FROB
+    assert rel_frob(got["1"], got["0"]) < 5e-5
+    assert not numpy.array_equal(got["1"], got["0"])   # the switch really selects a different path
+
+
 def test_cached_candidates_and_pinned_outputs(native):
     """hyprec_set_candidates + NULL lists == passing the lists on every call; outputs may live in
     page-locked memory from hyprec_host_alloc."""

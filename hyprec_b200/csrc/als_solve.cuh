@@ -298,12 +298,16 @@ __device__ __forceinline__ void trailing_update_tile(T* A, int NT, const T* ybuf
 
 // TC (float32, TS == 8, low-rank launches, sm_100a only): the rank-k accumulation runs on the tensor
 // cores (tc_syrk.cuh) instead of the SIMT rank-1 loop; everything after it is shared.
-template <typename T, int TS, bool TC = false>
+// GA: the tiles live in per-CTA global scratch (p.a_scratch) instead of shared memory -- a separate
+// instantiation so that the common case addresses its tiles with shared-memory instructions.
+template <typename T, int TS, bool TC = false, bool GA = false>
 __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows_kernel(SolveArgs<T> p) {
     HYPREC_DYN_SMEM(smem_dyn);
     unsigned char* smem_raw = smem_dyn;
 #ifndef HYPREC_EMU
-    if (TC) smem_raw = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B staging
+    // SWIZZLE_128B staging needs a 1024-byte aligned base (offset arithmetic keeps the pointer a
+    // shared-memory pointer for the compiler)
+    if (TC) smem_raw = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
 #endif
     long long prof_t = 0;
     __shared__ long long s_row;
@@ -312,13 +316,13 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
     const int k = p.k;
     const bool lowrank = p.lowrank != 0;
 #ifndef HYPREC_EMU
-    const SolveLayout lay = solve_layout(TS, p.max_dim, p.chunk_rows, p.a_scratch == nullptr, sizeof(T),
+    const SolveLayout lay = solve_layout(TS, p.max_dim, p.chunk_rows, !GA, sizeof(T),
                                          TC ? tc::syrk_stage_bytes(p.max_dim) : 0);
 #else
-    const SolveLayout lay = solve_layout(TS, p.max_dim, p.chunk_rows, p.a_scratch == nullptr, sizeof(T));
+    const SolveLayout lay = solve_layout(TS, p.max_dim, p.chunk_rows, !GA, sizeof(T));
 #endif
     const int CH = lay.chunk_rows, ystride = lay.ystride;
-    T* A = p.a_scratch ? p.a_scratch + (size_t)blockIdx.x * (TS * TS) * lay.n_tiles : (T*)(smem_raw + lay.off_a);
+    T* A = GA ? p.a_scratch + (size_t)blockIdx.x * (TS * TS) * lay.n_tiles : (T*)(smem_raw + lay.off_a);
     T* ybuf = (T*)(smem_raw + lay.off_y);
     T* zvec = (T*)(smem_raw + lay.off_z);
     T* xvec = (T*)(smem_raw + lay.off_x);

@@ -431,6 +431,10 @@ struct Engine : EngineBase {
         if constexpr (sizeof(T) == sizeof(float)) {
             if (tc) kern = hyprec::als_solve_rows_kernel<T, 8, true>;
         }
+        if (!in_smem) {
+            if (ts != 8) return fail(HYPREC_E_UNSUPPORTED, "global tile scratch is only built for 8 x 8 tiles");
+            kern = hyprec::als_solve_rows_kernel<T, 8, false, true>;
+        }
         HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
         int per_sm = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));

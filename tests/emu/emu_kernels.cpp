@@ -48,7 +48,8 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
     a.work_counter = counter; a.status = counter + 1; a.lambda = lambda; a.k = k;
     a.row_lo = row_lo; a.row_hi = row_hi; a.chunk_rows = chunk_rows;
     a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = nullptr; a.prof = nullptr;
-    emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
+    if (a_in_smem) emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
+    else emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8, false, true>(a); });
     return counter[1];
 }
 

@@ -185,10 +185,12 @@ __device__ __forceinline__ void chol_tile_invert(T (&a)[TS][TS], int nvalid) {
 // The serial part of a diagonal tile, one thread, tile in registers; out of line so that its
 // register needs stay out of the callers' accumulator tiles.
 #ifndef HYPREC_EMU
-template <typename T, int TS>
+template <typename T, int TS, bool GA>
 __device__ __noinline__ void factor_diag_tile_serial(T* A, int NT, int t, int p, int nvalid, T* zvec) {
+    if (!GA) __builtin_assume(__isShared(A));   // shared-memory loads/stores across the call boundary
+    __builtin_assume(__isShared(zvec));
 #else
-template <typename T, int TS>
+template <typename T, int TS, bool GA>
 void factor_diag_tile_serial(T* A, int NT, int t, int p, int nvalid, T* zvec) {
 #endif
     T a[TS][TS];
@@ -220,7 +222,7 @@ void factor_diag_tile_serial(T* A, int NT, int t, int p, int nvalid, T* zvec) {
 // l % TS of rows l / TS + g * (32 / TS).  The factorisation itself is a chain of dependent
 // rsqrt / FMA steps: measured on B200, one thread with the tile in registers runs it faster than a
 // shuffle-based warp version, so lane 0 does it while the other warps carry the trailing update.
-template <typename T, int TS>
+template <typename T, int TS, bool GA>
 __device__ __forceinline__ void factor_diag_tile_warp(T* A, int NT, int t, int p, int dim, T* zvec, int lane,
                                                       const T* panel = nullptr, int ystride = 0, int nb = 0) {
     int nvalid = dim - p * TS;
@@ -252,7 +254,7 @@ __device__ __forceinline__ void factor_diag_tile_warp(T* A, int NT, int t, int p
         }
         __syncwarp();
     }
-    if (nvalid > 0 && lane == 0) factor_diag_tile_serial<T, TS>(A, NT, t, p, nvalid, zvec);
+    if (nvalid > 0 && lane == 0) factor_diag_tile_serial<T, TS, GA>(A, NT, t, p, nvalid, zvec);
     __syncwarp();
 }
 
@@ -398,13 +400,33 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
 
 #ifndef HYPREC_EMU
         if constexpr (TC) {
-            // ---- S = I + 0.9 Q_r Q_r^T on the tensor cores, then the rhs row and the padding ---
-            __syncthreads();   // idxs / xvec complete
-            tc::syrk_lowrank(p.fixed, idxs, dim, k, tcs, (float*)A, NT, (float)pos_scale);
+            // ---- the rank-k accumulation on the tensor cores, then the rhs row and the padding --
+            __syncthreads();   // idxs / xvec complete (low-rank); previous row done with zvec / xvec
+            if (lowrank) {
+                // S = I + 0.9 Q_r Q_r^T; rhs row = r - 0.9 Q_r p (already in xvec)
+                tc::syrk_lowrank(p.fixed, idxs, dim, k, tcs, (float*)A, NT, (float)pos_scale);
+            } else if (deg > 0) {
+                // 0.9 sum y y^T (the shared base is added below); xvec = sum r y
+                int batch = (kpad / tc::kSyrkKB) * tc::kSyrkKB;
+                if (batch > 256) batch = 256;
+                tc::syrk_direct(p.fixed, p.indices, p.values, lo, deg, k, tcs, (float*)A, NT, (float)pos_scale, idxs,
+                                (float*)zvec, batch, (float*)xvec);
+            } else {
+                for (int e = tid; e < TS * TS * NT; e += nthreads) A[e] = T(0);
+                for (int c = tid; c < k; c += nthreads) xvec[c] = T(0);
+                __syncthreads();
+            }
             for (int e = tid; e < nb * TS * TS; e += nthreads) {
                 const int bj = e / (TS * TS), r = (e / TS) % TS, c = e % TS;
                 const int i = (nb - 1) * TS + r, j = bj * TS + c;
-                if (i >= dim) A[(size_t)(r * TS + c) * NT + tile_id(nb - 1, bj)] = (i == dim && j < dim) ? xvec[j] : T(0);
+                if (i >= dim) {
+                    T v = T(0);
+                    if (i == dim && j < dim) {
+                        v = xvec[j];
+                        if (!lowrank && prior_row != nullptr) v += p.lambda * prior_row[j];
+                    }
+                    A[(size_t)(r * TS + c) * NT + tile_id(nb - 1, bj)] = v;
+                }
             }
             __syncthreads();
         } else
@@ -518,7 +540,7 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
             __syncthreads();
         }
         HYPREC_PROF(1)   // base add
-        if (warp == 0) factor_diag_tile_warp<T, TS>(A, NT, 0, 0, dim, zvec, lane);
+        if (warp == 0) factor_diag_tile_warp<T, TS, GA>(A, NT, 0, 0, dim, zvec, lane);
         __syncthreads();
         HYPREC_PROF(2)   // first diagonal tile
 
@@ -559,7 +581,7 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
             if (ntr > 0) {
                 const int ntiles = tri(ntr);
                 if (warp == 0) {
-                    factor_diag_tile_warp<T, TS>(A, NT, tile_id(pnl + 1, pnl + 1), pnl + 1, dim, zvec, lane, ybuf, ystride, nb);
+                    factor_diag_tile_warp<T, TS, GA>(A, NT, tile_id(pnl + 1, pnl + 1), pnl + 1, dim, zvec, lane, ybuf, ystride, nb);
                     HYPREC_PROF(5)   // warp 0: next diagonal tile (update + factor + inverse)
                     if (nwarps == 1) {
 #pragma unroll 1

@@ -754,10 +754,12 @@ struct Engine : EngineBase {
         // (L^-1 of 0.1 G + lambda I) is always computed in float64; the deg x deg systems themselves
         // are well conditioned and run in the factor dtype.
         const bool lowrank = h->lowrank_enabled && lambda > 0.0 && k >= 16;
+        // float32 k x k systems (64 <= k <= 256) accumulate sum y y^T on the tensor cores (tc_syrk.cuh)
+        const bool tc_direct = h->tc_solve_enabled && sizeof(T) == sizeof(float) && k >= 64 && k <= 256;
         if (!lowrank) {
             Timer t(h, HYPREC_T_SOLVE);
             HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
-                               nullptr, nullptr, hi - lo, h->stream, 0));
+                               nullptr, nullptr, hi - lo, h->stream, 0, 8, tc_direct));
         } else {
             const int cap = std::min(k, kBucketDim[usable_buckets() - 1]);
             HY_TRY(build_plan(user, lo, hi, cap));
@@ -774,7 +776,7 @@ struct Engine : EngineBase {
                 CU_TRY(cudaStreamWaitEvent(h->aux[kHeavyStream], h->ev_base, 0));
                 HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[nbk], n_heavy, false, k,
                                    hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy,
-                                   h->aux[kHeavyStream], 1 + kMaxBuckets));
+                                   h->aux[kHeavyStream], 1 + kMaxBuckets, 8, tc_direct));
                 CU_TRY(cudaEventRecord(h->ev_join[kHeavyStream], h->aux[kHeavyStream]));
             }
             if (n_light > 0) {

@@ -6,6 +6,12 @@
 //   low-rank rows   S = I + 0.9 Q_r Q_r^T      Q_r = the deg gathered rows of the whitened factors;
 //                   a [deg x k] x [k x deg] product, both operands K-major (a gathered row is
 //                   contiguous along k)
+//   direct rows     A = base + 0.9 Y_r^T Y_r   Y_r = the deg gathered factor rows; a [k x deg] x [deg x k]
+//                   product whose contraction runs over the gathered rows, so each thread owns one
+//                   factor index, reads it from 32 gathered rows (coalesced across the CTA) and
+//                   stores 4 consecutive rows' values as one 16-byte chunk: the transpose into the
+//                   K-major operand layout happens in registers.  b = sum r y falls out of the same
+//                   loads.
 // The gathered rows are split x = hi + lo (both TF32) on their way into shared memory and the product is
 // accumulated as hi*hi + hi*lo + lo*hi in float32 (3xTF32, error ~2^-22 per term: float32-level),
 // by tcgen05.mma with the accumulator in tensor memory.  Only the gather (coalesced 16-byte loads,
@@ -59,6 +65,64 @@ struct SyrkState {
     int rows_pad;
 };
 
+
+// One k-block (32 contraction steps) of D += X X^T from a filled stage: D00 (and D1 for > 128 rows),
+// three TF32 products per K=8 step, then a commit that arrives on `bar` when they have retired.
+__device__ __forceinline__ void syrk_issue(const SyrkState& st, unsigned char* hi_base, size_t half_bytes, int npad, bool two,
+                                           bool accumulate, uint64_t* bar) {
+    tc_fence_after();
+    const uint32_t sa = smem_u32(hi_base);
+    const uint64_t a0_hi = umma_desc(sa), a0_lo = umma_desc(sa + (uint32_t)half_bytes);
+    const uint64_t a1_hi = umma_desc(sa + 128 * 128), a1_lo = umma_desc(sa + (uint32_t)half_bytes + 128 * 128);
+    const uint32_t idesc0 = umma_idesc_tf32(128, two ? 128 : npad);
+    const uint32_t idesc1 = umma_idesc_tf32(128, npad);
+#pragma unroll
+    for (int ks = 0; ks < kSyrkKB / 8; ++ks) {
+        const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
+        const uint32_t accum = (accumulate || ks != 0) ? 1u : 0u;
+        umma_tf32(st.tmem_base, a0_hi + adv, a0_hi + adv, idesc0, accum);
+        umma_tf32(st.tmem_base, a0_hi + adv, a0_lo + adv, idesc0, 1);
+        umma_tf32(st.tmem_base, a0_lo + adv, a0_hi + adv, idesc0, 1);
+        if (two) {
+            umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_hi + adv, idesc1, accum);
+            umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_lo + adv, idesc1, 1);
+            umma_tf32(st.tmem_base + 128, a1_lo + adv, a0_hi + adv, idesc1, 1);
+        }
+    }
+    umma_commit(bar);
+}
+
+// TMEM -> tiles: lane = system row, 32 columns per load; only tiles on or below the diagonal.
+// A[i][j] = scale * D[i][j] + diag * (i == j) for i, j < dim.
+__device__ __forceinline__ void syrk_epilogue(const SyrkState& st, float* A, int NT, int dim, float scale, float diag) {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
+    const bool two = dim > 128;
+    const int quad = warp & 3, half = warp >> 2, nhalf = nwarps >> 2;
+    for (int mb = 0; mb < (two ? 2 : 1); ++mb) {
+        const int row_base = mb * 128 + quad * 32;
+        if (row_base >= dim) continue;
+        const int i = row_base + lane;
+        const int jmax = min(dim, row_base + 32);
+        const int bi = i >> 3, ri = i & 7;
+        for (int c = 0; c < jmax; c += 32) {
+            if (((c >> 5) % nhalf) != half) continue;
+            uint32_t v[32];
+            const uint32_t taddr = st.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mb ? 128 : 0) + (uint32_t)c;
+            tmem_load_32x32(taddr, v);
+            if (i < dim) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int j = c + jj;
+                    const int bj = j >> 3;
+                    if (j < dim && bj <= bi)
+                        A[(size_t)(ri * 8 + (j & 7)) * NT + (bi * (bi + 1) / 2 + bj)] =
+                            scale * __uint_as_float(v[jj]) + (i == j ? diag : 0.f);
+                }
+            }
+        }
+    }
+}
+
 // S = I + scale * Q_r Q_r^T for the `dim` rows idxs[0..dim) of `fixed` ([.][k], k % 4 == 0), written
 // into the TS=8 tile storage A (lower-triangle tiles, full diagonal tiles).  All threads of the CTA
 // call it (blockDim.x a multiple of 128); A aliases the staging stages.
@@ -106,28 +170,7 @@ __device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, co
         }
         fence_async_smem();      // generic-proxy stores -> visible to the tensor core's async proxy
         __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t sa = smem_u32(hi_base);
-            const uint64_t a0_hi = umma_desc(sa), a0_lo = umma_desc(sa + (uint32_t)half_bytes);
-            const uint64_t a1_hi = umma_desc(sa + 128 * 128), a1_lo = umma_desc(sa + (uint32_t)half_bytes + 128 * 128);
-            const uint32_t idesc0 = umma_idesc_tf32(128, two ? 128 : npad);
-            const uint32_t idesc1 = umma_idesc_tf32(128, npad);
-#pragma unroll
-            for (int ks = 0; ks < kSyrkKB / 8; ++ks) {
-                const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
-                const uint32_t accum = (kb | ks) != 0;
-                umma_tf32(st.tmem_base, a0_hi + adv, a0_hi + adv, idesc0, accum);
-                umma_tf32(st.tmem_base, a0_hi + adv, a0_lo + adv, idesc0, 1);
-                umma_tf32(st.tmem_base, a0_lo + adv, a0_hi + adv, idesc0, 1);
-                if (two) {
-                    umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_hi + adv, idesc1, accum);
-                    umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_lo + adv, idesc1, 1);
-                    umma_tf32(st.tmem_base + 128, a1_lo + adv, a0_hi + adv, idesc1, 1);
-                }
-            }
-            umma_commit(&st.bars[s]);
-        }
+        if (tid == 0) syrk_issue(st, hi_base, half_bytes, npad, two, kb != 0, &st.bars[s]);
         pending[s] = true;
     }
 #pragma unroll
@@ -139,31 +182,85 @@ __device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, co
     tc_fence_after();
     __syncthreads();          // every thread is past its last staging access: A may be overwritten
 
-    // ---- TMEM -> tiles: lane = system row, 32 columns per load; only tiles on or below the diagonal
-    const int quad = warp & 3, half = warp >> 2, nhalf = nwarps >> 2;
-    for (int mb = 0; mb < (two ? 2 : 1); ++mb) {
-        const int row_base = mb * 128 + quad * 32;
-        if (row_base >= dim) continue;
-        const int i = row_base + lane;
-        const int jmax = min(dim, row_base + 32);
-        const int bi = i >> 3, ri = i & 7;
-        for (int c = 0; c < jmax; c += 32) {
-            if (((c >> 5) % nhalf) != half) continue;
-            uint32_t v[32];
-            const uint32_t taddr = st.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mb ? 128 : 0) + (uint32_t)c;
-            tmem_load_32x32(taddr, v);
-            if (i < dim) {
+    syrk_epilogue(st, A, NT, dim, scale, 1.f);
+    tc_fence_before();
+}
+
+
+// A = scale * Y_r^T Y_r (k x k, no diagonal term: the caller adds the shared base) for the deg rows
+// indices[lo .. lo+deg) of `fixed`, and bvec[a] = sum_j values[lo+j] * Y[j][a].  Thread t owns factor
+// index t (k <= blockDim.x).  idxs / rstage: shared scratch of `batch` entries (a multiple of 32).
+__device__ __forceinline__ void syrk_direct(const float* __restrict__ fixed, const int32_t* __restrict__ indices,
+                                            const float* __restrict__ values, int64_t lo, int deg, int k, SyrkState& st,
+                                            float* A, int NT, float scale, int* idxs, float* rstage, int batch, float* bvec) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int a = tid;
+    const int nkb = (deg + kSyrkKB - 1) / kSyrkKB;
+    const size_t half_bytes = (size_t)st.rows_pad * 128;
+    const size_t stage_bytes = 2 * half_bytes;
+    const int npad = (k + 15) & ~15;
+    const bool two = k > 128;
+    const int kb_per_batch = batch / kSyrkKB;
+    bool pending[2] = {false, false};
+    float bsum = 0.f;
+
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        const int slot = (kb % kb_per_batch) * kSyrkKB;
+        if (slot == 0) {
+            // (every thread is past its reads of the previous batch: it has crossed the barrier below)
+            for (int i = tid; i < batch; i += nthreads) {
+                const int j = kb * kSyrkKB + i;
+                idxs[i] = j < deg ? indices[lo + j] : -1;
+                rstage[i] = j < deg ? values[lo + j] : 0.f;
+            }
+            __syncthreads();
+        }
+        float v[kSyrkKB];
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = c + jj;
-                    const int bj = j >> 3;
-                    if (j < dim && bj <= bi)
-                        A[(size_t)(ri * 8 + (j & 7)) * NT + (bi * (bi + 1) / 2 + bj)] =
-                            scale * __uint_as_float(v[jj]) + (i == j ? 1.f : 0.f);
-                }
+        for (int jj = 0; jj < kSyrkKB; ++jj) {
+            const int id = idxs[slot + jj];
+            v[jj] = (a < k && id >= 0) ? __ldg(fixed + (int64_t)id * k + a) : 0.f;
+        }
+        if (pending[s]) {
+            mbar_wait(&st.bars[s], st.phase[s]);
+            st.phase[s] ^= 1;
+            pending[s] = false;
+        }
+        unsigned char* hi_base = st.stage + (size_t)s * stage_bytes;
+        if (a < st.rows_pad) {
+            const size_t row_off = (size_t)(a >> 3) * 1024 + (size_t)(a & 7) * 128;
+#pragma unroll
+            for (int c = 0; c < kSyrkKB / 4; ++c) {
+                float4 h, l;
+                split_tf32(v[4 * c], h.x, l.x);
+                split_tf32(v[4 * c + 1], h.y, l.y);
+                split_tf32(v[4 * c + 2], h.z, l.z);
+                split_tf32(v[4 * c + 3], h.w, l.w);
+                bsum = fmaf(rstage[slot + 4 * c], v[4 * c], bsum);
+                bsum = fmaf(rstage[slot + 4 * c + 1], v[4 * c + 1], bsum);
+                bsum = fmaf(rstage[slot + 4 * c + 2], v[4 * c + 2], bsum);
+                bsum = fmaf(rstage[slot + 4 * c + 3], v[4 * c + 3], bsum);
+                const size_t off = row_off + (size_t)((c ^ (a & 7)) << 4);
+                *reinterpret_cast<float4*>(hi_base + off) = h;
+                *reinterpret_cast<float4*>(hi_base + half_bytes + off) = l;
             }
         }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) syrk_issue(st, hi_base, half_bytes, npad, two, kb != 0, &st.bars[s]);
+        pending[s] = true;
     }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+        if (pending[s]) {
+            mbar_wait(&st.bars[s], st.phase[s]);
+            st.phase[s] ^= 1;
+        }
+    tc_fence_after();
+    if (a < k) bvec[a] = bsum;
+    __syncthreads();
+    syrk_epilogue(st, A, NT, k, scale, 0.f);
     tc_fence_before();
 }
 

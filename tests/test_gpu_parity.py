@@ -336,6 +336,37 @@ def test_tensor_core_row_systems_fp32(native, monkeypatch, m, n, k, nnz):
     assert not numpy.array_equal(got["1"], got["0"])   # the switch really selects a different path
 
 
+@pytest.mark.parametrize("m,n,k,nnz,lowrank", [(60, 900, 256, 11000, "0"), (48, 1000, 96, 5000, "1"),
+                                               (50, 600, 200, 6000, "0"), (40, 500, 64, 4000, "0")])
+def test_tensor_core_direct_systems_fp32(native, monkeypatch, m, n, k, nnz, lowrank):
+    """float32 k x k systems (64 <= k <= 256: rows with more positives than k, or every row with
+    HYPREC_LOWRANK=0) accumulate sum y y^T and b = sum r y through tcgen05 (tc_syrk.cuh syrk_direct);
+    the item side carries the lambda * theta prior and rows without positives."""
+    full, train, test, u0, v0, cands = synthetic(m, n, k, nnz, seed=k + 3, empty=True)
+    csc = oals.to_csr(train.T)
+    theta = numpy.random.RandomState(5).rand(n, k)
+    u = oals.als_half_step(u0.copy(), v0, train, 0.01)
+    v = oals.als_half_step(v0.copy(), u, csc, 0.01, prior=theta)
+    monkeypatch.setenv("HYPREC_LOWRANK", lowrank)
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("HYPREC_TC_SOLVE", flag)
+        h, _ = make_handle(native, train, native.F32)
+        h.set_factors(u0, v0)
+        h.set_item_prior(theta)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        got[flag] = h.get_factors()
+        h.close()
+    for side, ref in ((0, u), (1, v)):
+        print("k=%d side %d tc vs oracle %.2e, simt vs oracle %.2e, tc vs simt %.2e" %
+              (k, side, rel_frob(got["1"][side], ref), rel_frob(got["0"][side], ref),
+               rel_frob(got["1"][side], got["0"][side])))
+        assert rel_frob(got["1"][side], ref) < F32_FROB
+        assert rel_frob(got["1"][side], got["0"][side]) < 5e-5
+    assert not numpy.array_equal(got["1"][0], got["0"][0])
+
+
 def test_cached_candidates_and_pinned_outputs(native):
     """hyprec_set_candidates + NULL lists == passing the lists on every call; outputs may live in
     page-locked memory from hyprec_host_alloc."""

@@ -19,6 +19,7 @@
 #include "gram.cuh"
 #include "score.cuh"
 #include "tc_score.cuh"
+#include "tc_chol.cuh"
 #include "topk.cuh"
 
 namespace {
@@ -106,6 +107,7 @@ struct hyprec_ctx {
     int64_t launches = 0;
     bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
     bool tc_enabled = true;        // HYPREC_TC=0 keeps the score sweep on the SIMT kernel
+    bool tc_chol_enabled = true;   // HYPREC_TC_CHOL=0: float32 systems factorise in shared-memory tiles (als_solve.cuh)
     bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
     int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
     bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
@@ -478,6 +480,47 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+
+    // float32 systems of 33..256 unknowns with the normal matrix resident in tensor memory (tc_chol.cuh).
+    int launch_chol_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
+                         bool lowrank, int max_dim, const float* fixed_ptr, const float* prior_ptr, int64_t work,
+                         cudaStream_t st, int slot) {
+        namespace tc = hyprec::tc;
+        const tc::CholLayout lay = tc::chol_layout(max_dim);
+        if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "tensor-memory row launch does not fit shared memory");
+        HY_TRY(ensure_dynamic_smem((const void*)tc::tc_chol_rows_kernel, (int)lay.total));
+        const Csr& rows_csr = user ? csr : csc;
+        tc::CholRowsArgs a;
+        a.indptr = rows_csr.indptr.template as<int64_t>();
+        a.indices = rows_csr.indices.template as<int32_t>();
+        a.values = rows_csr.values.template as<float>();
+        a.fixed = fixed_ptr;
+        a.gram = gram[user ? 1 : 0].template as<float>();
+        a.prior = prior_ptr;
+        a.out = lowrank ? ymat.as<float>() : (user ? U.as<float>() : V.as<float>());
+        a.work_counter = counter.as<int>() + slot;
+        a.status = counter.as<int>() + kStatusSlot;
+        a.lambda = (float)lambda;
+        a.k = k;
+        a.row_lo = lo;
+        a.row_hi = hi;
+        a.row_list = list;
+        a.n_list = n_list;
+        a.max_dim = max_dim;
+        a.lowrank = lowrank ? 1 : 0;
+        a.tmem_cols = tc::syrk_tmem_cols(max_dim);
+        a.prof = nullptr;
+        if (h->prof_enabled && slot == h->prof_slot) {
+            if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
+            a.prof = prof_buf.as<long long>();
+        }
+        const int grid = (int)std::min<int64_t>(work, (int64_t)h->num_sms);
+        tc::tc_chol_rows_kernel<<<grid, tc::kCholThreads, lay.total, st>>>(a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
     // C[ra x rb] = A[ra x k] B[rb x k]^T through the sweep kernel (float64 path only).  With a row
     // list the product is taken over rows A[list[i]] and row i is stored at C[list[i]].
     int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, T* c, const int32_t* list = nullptr) {
@@ -756,10 +799,16 @@ struct Engine : EngineBase {
         const bool lowrank = h->lowrank_enabled && lambda > 0.0 && k >= 16;
         // float32 k x k systems (64 <= k <= 256) accumulate sum y y^T on the tensor cores (tc_syrk.cuh)
         const bool tc_direct = h->tc_solve_enabled && sizeof(T) == sizeof(float) && k >= 64 && k <= 256;
+        const bool chol_direct = tc_direct && h->tc_chol_enabled;
         if (!lowrank) {
             Timer t(h, HYPREC_T_SOLVE);
-            HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
-                               nullptr, nullptr, hi - lo, h->stream, 0, 8, tc_direct));
+            if constexpr (sizeof(T) == sizeof(float)) {
+                if (chol_direct)
+                    HY_TRY(launch_chol_rows(user, lambda, lo, hi, nullptr, 0, false, k, fixed_ptr, prior_ptr, hi - lo, h->stream, 0));
+            }
+            if (!chol_direct)
+                HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
+                                   nullptr, nullptr, hi - lo, h->stream, 0, 8, tc_direct));
         } else {
             const int cap = std::min(k, kBucketDim[usable_buckets() - 1]);
             HY_TRY(build_plan(user, lo, hi, cap));
@@ -774,9 +823,15 @@ struct Engine : EngineBase {
             CU_TRY(cudaEventRecord(h->ev_base, h->stream));
             if (n_heavy > 0) {
                 CU_TRY(cudaStreamWaitEvent(h->aux[kHeavyStream], h->ev_base, 0));
-                HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[nbk], n_heavy, false, k,
-                                   hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy,
-                                   h->aux[kHeavyStream], 1 + kMaxBuckets, 8, tc_direct));
+                if constexpr (sizeof(T) == sizeof(float)) {
+                    if (chol_direct)
+                        HY_TRY(launch_chol_rows(user, lambda, lo, hi, lists + pl.bucket_off[nbk], n_heavy, false, k, fixed_ptr,
+                                                prior_ptr, n_heavy, h->aux[kHeavyStream], 1 + kMaxBuckets));
+                }
+                if (!chol_direct)
+                    HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[nbk], n_heavy, false, k,
+                                       hyprec::kSolveThreads, fixed_ptr, prior_ptr, nullptr, nullptr, n_heavy,
+                                       h->aux[kHeavyStream], 1 + kMaxBuckets, 8, tc_direct));
                 CU_TRY(cudaEventRecord(h->ev_join[kHeavyStream], h->aux[kHeavyStream]));
             }
             if (n_light > 0) {
@@ -804,6 +859,13 @@ struct Engine : EngineBase {
                         // float32 systems of 64+ rows build S on the tensor cores (tc_syrk.cuh)
                         const bool tc = h->tc_solve_enabled && sizeof(T) == sizeof(float) && kBucketTile[b] == 8 &&
                                         k % 4 == 0 && pl.bucket_dim[b] <= 256;
+                        const bool chol = tc && h->tc_chol_enabled;
+                        if constexpr (sizeof(T) == sizeof(float)) {
+                            if (chol)
+                                HY_TRY(launch_chol_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
+                                                        qmat.as<float>(), prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b));
+                        }
+                        if (!chol)
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
                                            tc ? hyprec::kSolveThreads : kBucketThreads[b], qmat.as<T>(),
                                            prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
@@ -1337,6 +1399,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->prof_enabled = pf && pf[0] == '1';
     const char* ts_env = getenv("HYPREC_TC_SOLVE");
     h->tc_solve_enabled = h->tc_enabled && !(ts_env && ts_env[0] == '0');
+    const char* tch = getenv("HYPREC_TC_CHOL");
+    h->tc_chol_enabled = h->tc_solve_enabled && !(tch && tch[0] == '0');
     const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");
     if (ps) h->prof_slot = atoi(ps);
     const char* lr = getenv("HYPREC_LOWRANK");

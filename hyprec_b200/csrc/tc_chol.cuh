@@ -1,0 +1,418 @@
+// Fused per-row ALS update with the row's normal matrix resident in tensor memory (float32 mode,
+// systems of up to 256 unknowns, sm_100a).  Same mathematics and the same reference lines as
+// als_solve.cuh (/root/reference/lib/collaborative_filtering.py:83-99: confidence-weighted normal
+// matrix, right-hand side, numpy.linalg.solve), different machine mapping:
+//
+//   1. the rank-k accumulation (tc_syrk.cuh) leaves D = 0.9 X X^T in TMEM and never copies it out;
+//   2. blocked right-looking Cholesky with 32-column panels.  One thread owns one row of the system:
+//      it pulls its 32 panel entries from TMEM (tcgen05.ld, lane = row), the warp that owns the 32
+//      diagonal rows factors the 32 x 32 block in registers (shuffle broadcasts), every row below solves
+//      its 32 entries against it, writes them back to TMEM (tcgen05.st: the finished columns of D become
+//      L) and, split hi/lo, into the operand stage, and ONE tcgen05.mma chain applies the trailing update
+//      D22 -= L21 L21^T to the whole remaining matrix (3xTF32, negated A operand);
+//   3. the right-hand side rides along (z = L^-1 b is finished panel by panel), and the back
+//      substitution re-reads L from TMEM, reducing each panel's 32 dot products with a
+//      transpose-reduce butterfly (31 shuffles per warp).
+//
+// The trailing update -- the O(n^3) part -- runs on the tensor cores; the SIMT cores only see
+// O(n^2) work per system plus the 32 x 32 diagonal blocks.
+//
+// System forms (see als_solve.cuh for the derivation):
+//   low-rank  S = I + 0.9 Q_r Q_r^T (deg x deg),  rhs = r - 0.9 Q_r p,  output y = Q_r^T t + p
+//   direct    A = 0.1 G + lambda I + 0.9 Y_r^T Y_r (k x k),  rhs = sum r y + lambda theta,  output x
+// Padding up to the next multiple of 32 is an identity block, so the factorisation never sees it.
+#pragma once
+#include "tc_syrk.cuh"
+
+namespace hyprec {
+namespace tc {
+
+constexpr int kCholThreads = 256;   // one thread per system row
+constexpr int kCholPanel = 32;
+
+struct CholRowsArgs {
+    const int64_t* indptr;    // CSR of the side being solved, indexed by global row id
+    const int32_t* indices;   // ids into `fixed`
+    const float* values;      // ratings
+    const float* fixed;       // low-rank: whitened factors Q [n_fixed][k]; direct: factors Y
+    const float* gram;        // direct: dense k x k Gram of the fixed side (0.1 G + lambda I is formed on the fly)
+    const float* prior;       // low-rank: rows of theta L^-T; direct: theta; or null
+    float* out;               // low-rank: ymat [n_rows][k]; direct: latent [n_rows][k]
+    int* work_counter;        // zeroed before launch
+    int* status;              // set to 1 when a solution is not finite
+    float lambda;
+    int k;
+    int64_t row_lo, row_hi;
+    const int32_t* row_list;  // optional row ids instead of [row_lo, row_hi)
+    int64_t n_list;
+    int max_dim;              // largest system of the launch (<= 256)
+    int lowrank;
+    int tmem_cols;
+    long long* prof;          // optional clock64() phase totals of block 0
+};
+
+struct CholLayout {
+    size_t off_stage, off_l11, off_l11t, off_dinv, off_z, off_x, off_b, off_part, off_idx, off_rst, off_bar, total;
+};
+
+__host__ __device__ __forceinline__ CholLayout chol_layout(int max_dim) {
+    CholLayout l;
+    size_t o = 0;
+    l.off_stage = o;                       // 2 stages x (hi + lo) x rows_pad x 128 B, 1024-byte aligned
+    o += 2 * syrk_stage_bytes(max_dim);
+    l.off_l11 = o;  o += sizeof(float) * 32 * 33;   // L11 row-major, padded (column reads)
+    l.off_l11t = o; o += sizeof(float) * 32 * 32;   // L11 transposed (broadcast vector reads)
+    l.off_dinv = o; o += sizeof(float) * 256;       // 1 / L[j][j]
+    l.off_z = o;    o += sizeof(float) * 256;       // z = L^-1 b
+    l.off_x = o;    o += sizeof(float) * 256;       // solution
+    l.off_b = o;    o += sizeof(float) * 256;       // right-hand side
+    l.off_part = o; o += sizeof(float) * 8 * 32;    // per-warp partial dot products (back substitution)
+    l.off_idx = o;  o += sizeof(int) * 256;         // positives' ids
+    l.off_rst = o;  o += sizeof(float) * 256;       // ratings of the current batch (direct gather)
+    l.off_bar = (o + 7) & ~(size_t)7;
+    o = l.off_bar + 32;
+    l.total = o + 1024;                    // alignment slack
+    return l;
+}
+
+__device__ __forceinline__ void tmem_store_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// D[rows of the M-block][n_cols columns from TMEM column `tcol`] -= A B^T, K = 32 (one staged panel):
+// A = stage rows [a_row0, a_row0+128), B = stage rows [b_row0, b_row0+n_cols); 3xTF32, A negated.
+__device__ __forceinline__ void chol_issue_update(uint32_t tmem_d, unsigned char* hi_base, size_t half_bytes, int a_row0,
+                                                  int b_row0, int n_cols) {
+    const uint32_t sa = smem_u32(hi_base);
+    const uint64_t a_hi = umma_desc(sa + (uint32_t)a_row0 * 128), a_lo = umma_desc(sa + (uint32_t)half_bytes + (uint32_t)a_row0 * 128);
+    const uint64_t b_hi = umma_desc(sa + (uint32_t)b_row0 * 128), b_lo = umma_desc(sa + (uint32_t)half_bytes + (uint32_t)b_row0 * 128);
+    const uint32_t idesc = umma_idesc_tf32(128, n_cols) | (1u << 13);   // a_negate
+#pragma unroll
+    for (int ks = 0; ks < kCholPanel / 8; ++ks) {
+        const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
+        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1);
+    }
+}
+
+#define HYPREC_TCPROF(slot)                                                          \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {                          \
+        const long long now_ = clock64();                                            \
+        p.prof[slot] += now_ - prof_t;                                               \
+        prof_t = now_;                                                               \
+    }
+
+__global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsArgs p) {
+    extern __shared__ __align__(16) unsigned char chol_smem_dyn[];
+    unsigned char* smem = chol_smem_dyn + ((1024u - (smem_u32(chol_smem_dyn) & 1023u)) & 1023u);
+    const CholLayout lay = chol_layout(p.max_dim);
+    float* l11 = (float*)(smem + lay.off_l11);
+    float* l11t = (float*)(smem + lay.off_l11t);
+    float* dinv = (float*)(smem + lay.off_dinv);
+    float* zs = (float*)(smem + lay.off_z);
+    float* xs = (float*)(smem + lay.off_x);
+    float* bs = (float*)(smem + lay.off_b);
+    float* part = (float*)(smem + lay.off_part);
+    int* idxs = (int*)(smem + lay.off_idx);
+    float* rst = (float*)(smem + lay.off_rst);
+    uint64_t* bars = (uint64_t*)(smem + lay.off_bar);       // [0], [1] staging stages, [2] panel updates
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3);
+    __shared__ long long s_row;
+
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int k = p.k;
+    const bool lowrank = p.lowrank != 0;
+    const float sqrt_pos = 0.9486832980505138f;             // sqrt(1.0 - 0.1): D accumulates 0.9 X X^T
+    const float pos_scale = (float)(kConfPos - kConfNeg);
+    const int64_t n_work = p.row_list ? p.n_list : p.row_hi - p.row_lo;
+    long long prof_t = 0;
+
+    SyrkState st;
+    st.bars = bars;
+    st.phase[0] = st.phase[1] = 0;
+    st.stage = smem + lay.off_stage;
+    st.rows_pad = syrk_rows_pad(p.max_dim);
+    uint32_t upd_phase = 0;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    st.tmem_base = *tmem_slot;
+    const size_t half_bytes = (size_t)st.rows_pad * 128;
+    // this thread's row r = tid lives in TMEM lane tid % 128 of block tid / 128
+    const uint32_t my_taddr = st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tid >= 128 ? 128 : 0);
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_row = (long long)atomicAdd(p.work_counter, 1);
+        __syncthreads();
+        if (s_row >= n_work) break;
+        const int64_t row = p.row_list ? (int64_t)p.row_list[s_row] : p.row_lo + s_row;
+        if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) prof_t = clock64();
+        const int64_t lo = p.indptr[row];
+        const int deg = (int)(p.indptr[row + 1] - lo);
+        float* out = p.out + row * k;
+        const float* prior_row = p.prior ? p.prior + row * k : nullptr;
+        if (deg == 0 && (lowrank || prior_row == nullptr)) {
+            // direct: b == 0 => the solve returns exactly 0; low-rank: y = p
+            for (int c = tid; c < k; c += kCholThreads) out[c] = (lowrank && prior_row) ? p.lambda * prior_row[c] : 0.f;
+            continue;
+        }
+        const int dim = lowrank ? deg : k;
+        const int dimp = (dim + kCholPanel - 1) / kCholPanel * kCholPanel;
+        const int n_panels = dimp / kCholPanel;
+        const bool two = dimp > 128;
+
+        // ---- 1. D = 0.9 X X^T into TMEM; right-hand side into bs ------------------------------
+        if (lowrank) {
+            for (int i = tid; i < dim; i += kCholThreads) idxs[i] = p.indices[lo + i];
+            __syncthreads();
+            for (int i = warp; i < dim; i += kCholThreads / 32) {
+                float v = p.values[lo + i];
+                if (prior_row) {
+                    const float* q = p.fixed + (int64_t)idxs[i] * k;
+                    double d = 0.0;
+                    for (int l = lane; l < k; l += 32) d += (double)q[l] * (double)prior_row[l];
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+                    v -= pos_scale * p.lambda * (float)d;
+                }
+                if (lane == 0) bs[i] = v;
+            }
+            __syncthreads();
+            syrk_lowrank_accumulate(p.fixed, idxs, dim, k, st, sqrt_pos, dimp);
+        } else {
+            if (deg > 0) {
+                syrk_direct_accumulate(p.fixed, p.indices, p.values, lo, deg, k, st, sqrt_pos, dimp, idxs, rst, 256, bs);
+            } else {
+                // no positives (only reached with a prior): D = 0 through one k-block of zero operands
+                if (tid < k) bs[tid] = 0.f;
+                float4* z4 = reinterpret_cast<float4*>(st.stage);
+                for (size_t e = tid; e < 2 * half_bytes / sizeof(float4); e += kCholThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) syrk_issue(st, st.stage, half_bytes, dimp, two, false, &bars[0]);
+                mbar_wait(&bars[0], st.phase[0]);
+                st.phase[0] ^= 1;
+                tc_fence_after();
+            }
+            if (prior_row != nullptr && tid < k) bs[tid] += p.lambda * prior_row[tid];
+        }
+        HYPREC_TCPROF(0)
+        float bval = (tid < dim) ? bs[tid] : 0.f;      // this row's right-hand side entry
+
+        // ---- 2. blocked Cholesky, 32-column panels --------------------------------------------
+        for (int pn = 0; pn < n_panels; ++pn) {
+            const int c0 = pn * kCholPanel;
+            const int r = tid;
+            float a[32];
+            if (warp >= pn && r < dimp) {              // (whole warps: dimp is a multiple of 32)
+                uint32_t raw[32];
+                tmem_load_32x32(my_taddr + (uint32_t)c0, raw);
+                const float* grow = (!lowrank && r < dim) ? p.gram + (int64_t)r * k + c0 : nullptr;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = c0 + j;
+                    float v = 0.f;
+                    if (r < dim && col < dim) {
+                        v = __uint_as_float(raw[j]);
+                        if (lowrank) v += (r == col) ? 1.f : 0.f;
+                        else v += (float)kConfNeg * __ldg(grow + j) + ((r == col) ? p.lambda : 0.f);
+                    } else {
+                        v = (r == col) ? 1.f : 0.f;    // identity padding
+                    }
+                    a[j] = v;
+                }
+            }
+            if (warp == pn) {
+                // the 32 x 32 diagonal block, one row per lane: L11 in place, 1 / diagonal kept
+                float dmine = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float piv = __shfl_sync(0xffffffffu, a[j], j);
+                    const float d = rsqrtf(piv);
+                    a[j] *= d;
+                    if (lane == j) dmine = d;
+#pragma unroll
+                    for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-a[j], __shfl_sync(0xffffffffu, a[j], c), a[c]);
+                }
+                dinv[c0 + lane] = dmine;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    l11[lane * 33 + j] = a[j];
+                    l11t[j * 32 + lane] = a[j];
+                }
+                uint32_t raw[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
+                tmem_store_32x32(my_taddr + (uint32_t)c0, raw);
+            }
+            tc_fence_before();
+            __syncthreads();
+            HYPREC_TCPROF(2)
+            const int rem0 = c0 + kCholPanel;
+            unsigned char* hi_base = st.stage;         // panel updates use stage 0
+            if (warp == pn) {
+                // forward substitution of this panel's right-hand side: z_p = L11^-1 b_p
+                float zmine = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float zj = __shfl_sync(0xffffffffu, bval, j) * dinv[c0 + j];
+                    if (lane == j) zmine = zj;
+                    if (lane > j) bval = fmaf(-a[j], zj, bval);
+                }
+                zs[c0 + lane] = zmine;
+            } else if (warp > pn && r < dimp) {
+                // x = a L11^-T (this row's 32 entries of L), column by column
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    a[j] *= dinv[c0 + j];
+#pragma unroll
+                    for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-a[j], l11t[j * 32 + c], a[c]);
+                }
+                uint32_t raw[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
+                tmem_store_32x32(my_taddr + (uint32_t)c0, raw);
+                const size_t row_off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 h, l;
+                    split_tf32(a[4 * c], h.x, l.x);
+                    split_tf32(a[4 * c + 1], h.y, l.y);
+                    split_tf32(a[4 * c + 2], h.z, l.z);
+                    split_tf32(a[4 * c + 3], h.w, l.w);
+                    const size_t off = row_off + (size_t)((c ^ (r & 7)) << 4);
+                    *reinterpret_cast<float4*>(hi_base + off) = h;
+                    *reinterpret_cast<float4*>(hi_base + half_bytes + off) = l;
+                }
+                fence_async_smem();
+            }
+            tc_fence_before();
+            __syncthreads();
+            HYPREC_TCPROF(3)
+            if (rem0 < dimp) {
+                if (tid == 0) {
+                    tc_fence_after();
+                    if (rem0 < 128) {
+                        const int n0 = (two ? 128 : dimp) - rem0;
+                        chol_issue_update(st.tmem_base + (uint32_t)rem0, hi_base, half_bytes, 0, rem0, n0);
+                    }
+                    if (two) chol_issue_update(st.tmem_base + 128u + (uint32_t)rem0, hi_base, half_bytes, 128, rem0, dimp - rem0);
+                    umma_commit(&bars[2]);
+                }
+                if (warp > pn && r < dimp) {
+                    // the rows below take this panel's z out of their right-hand side
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc = fmaf(a[j], zs[c0 + j], acc);
+                    bval -= acc;
+                }
+                mbar_wait(&bars[2], upd_phase);
+                upd_phase ^= 1;
+                tc_fence_after();
+            }
+            HYPREC_TCPROF(5)
+        }
+
+        // ---- 3. back substitution L^T x = z, last panel first ---------------------------------
+        float xmine = 0.f;
+        for (int pn = n_panels - 1; pn >= 0; --pn) {
+            const int c0 = pn * kCholPanel;
+            const int r = tid;
+            if (warp > pn && r < dimp) {
+                uint32_t raw[32];
+                tmem_load_32x32(my_taddr + (uint32_t)c0, raw);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * xmine;
+                // transpose-reduce: afterwards lane l holds sum over the warp's rows of entry l
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const bool up = (lane & s) != 0;
+#pragma unroll
+                    for (int i = 0; i < s; ++i) {
+                        const float keep = up ? v[i + s] : v[i];
+                        const float send = up ? v[i] : v[i + s];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                    }
+                }
+                part[warp * 32 + lane] = v[0];
+            } else if (warp == pn) {
+                uint32_t raw[32];
+                tmem_load_32x32(my_taddr + (uint32_t)c0, raw);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) l11[lane * 33 + j] = __uint_as_float(raw[j]);
+            }
+            __syncthreads();
+            if (warp == pn) {
+                float rhs = zs[c0 + lane];
+                const int last_warp = dimp / 32 - 1;
+                for (int w = pn + 1; w <= last_warp; ++w) rhs -= part[w * 32 + lane];
+#pragma unroll
+                for (int j = 31; j >= 0; --j) {
+                    const float xj = __shfl_sync(0xffffffffu, rhs, j) * dinv[c0 + j];
+                    if (lane == j) xmine = xj;
+                    if (lane < j) rhs = fmaf(-l11[j * 33 + lane], xj, rhs);
+                }
+                xs[c0 + lane] = xmine;
+            }
+            __syncthreads();
+        }
+        HYPREC_TCPROF(7)
+        if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {
+            p.prof[8] += 1;
+            p.prof[9] += deg;
+        }
+
+        // ---- 4. output ------------------------------------------------------------------------
+        if (!lowrank) {
+            if (tid < k) {
+                const float v = xs[tid];
+                if (!(v - v == 0.f)) *p.status = 1;    // inf or nan: singular system (lambda == 0)
+                out[tid] = v;
+            }
+        } else {
+            // y = Q_r^T t + p  (second, L2-resident pass over the row's Q rows; coalesced along a)
+            for (int a = tid; a < k; a += kCholThreads) {
+                float s = prior_row ? p.lambda * prior_row[a] : 0.f;
+                int i = 0;
+                for (; i + 4 <= dim; i += 4) {
+                    const float q0 = p.fixed[(int64_t)idxs[i] * k + a], q1 = p.fixed[(int64_t)idxs[i + 1] * k + a];
+                    const float q2 = p.fixed[(int64_t)idxs[i + 2] * k + a], q3 = p.fixed[(int64_t)idxs[i + 3] * k + a];
+                    s += q0 * xs[i];
+                    s += q1 * xs[i + 1];
+                    s += q2 * xs[i + 2];
+                    s += q3 * xs[i + 3];
+                }
+                for (; i < dim; ++i) s += p.fixed[(int64_t)idxs[i] * k + a] * xs[i];
+                if (!(s - s == 0.f)) *p.status = 1;
+                out[a] = s;
+            }
+        }
+        HYPREC_TCPROF(10)
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(st.tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace tc
+}  // namespace hyprec

@@ -123,18 +123,16 @@ __device__ __forceinline__ void syrk_epilogue(const SyrkState& st, float* A, int
     }
 }
 
-// S = I + scale * Q_r Q_r^T for the `dim` rows idxs[0..dim) of `fixed` ([.][k], k % 4 == 0), written
-// into the TS=8 tile storage A (lower-triangle tiles, full diagonal tiles).  All threads of the CTA
-// call it (blockDim.x a multiple of 128); A aliases the staging stages.
-__device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, const int* idxs, int dim, int k,
-                                             SyrkState& st, float* A, int NT, float scale) {
+// D (TMEM) = pre_scale^2 * Q_r Q_r^T for the `dim` rows idxs[0..dim) of `fixed` ([.][k], k % 4 == 0);
+// `npad` (a multiple of 16, >= dim) columns are formed.  All threads of the CTA call it (blockDim.x a
+// multiple of 128).
+__device__ __forceinline__ void syrk_lowrank_accumulate(const float* __restrict__ fixed, const int* idxs, int dim, int k,
+                                                        SyrkState& st, float pre_scale, int npad) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int warp = tid / 32, lane = tid % 32, nwarps = nthreads / 32;
     const int chunk = tid & 7, r0 = tid >> 3, rpp = nthreads >> 3;
     const int nkb = (k + kSyrkKB - 1) / kSyrkKB;
     const size_t half_bytes = (size_t)st.rows_pad * 128;          // hi rows, then lo rows
     const size_t stage_bytes = 2 * half_bytes;
-    const int npad = (dim + 15) & ~15;
     const bool two = dim > 128;
     bool pending[2] = {false, false};
 
@@ -159,10 +157,10 @@ __device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, co
             const int r = r0 + j * rpp;
             if (r < dim) {
                 float4 h, l;
-                split_tf32(v[j].x, h.x, l.x);
-                split_tf32(v[j].y, h.y, l.y);
-                split_tf32(v[j].z, h.z, l.z);
-                split_tf32(v[j].w, h.w, l.w);
+                split_tf32(v[j].x * pre_scale, h.x, l.x);
+                split_tf32(v[j].y * pre_scale, h.y, l.y);
+                split_tf32(v[j].z * pre_scale, h.z, l.z);
+                split_tf32(v[j].w * pre_scale, h.w, l.w);
                 const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((chunk ^ (r & 7)) << 4);
                 *reinterpret_cast<float4*>(hi_base + off) = h;
                 *reinterpret_cast<float4*>(hi_base + half_bytes + off) = l;
@@ -180,25 +178,31 @@ __device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, co
             st.phase[s] ^= 1;
         }
     tc_fence_after();
-    __syncthreads();          // every thread is past its last staging access: A may be overwritten
+    __syncthreads();          // every thread is past its last staging access: the stages may be reused
+}
 
+// S = I + scale * Q_r Q_r^T written into the TS=8 tile storage A (lower-triangle tiles, full diagonal
+// tiles); A aliases the staging stages.
+__device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, const int* idxs, int dim, int k,
+                                             SyrkState& st, float* A, int NT, float scale) {
+    syrk_lowrank_accumulate(fixed, idxs, dim, k, st, 1.f, (dim + 15) & ~15);
     syrk_epilogue(st, A, NT, dim, scale, 1.f);
     tc_fence_before();
 }
 
 
-// A = scale * Y_r^T Y_r (k x k, no diagonal term: the caller adds the shared base) for the deg rows
-// indices[lo .. lo+deg) of `fixed`, and bvec[a] = sum_j values[lo+j] * Y[j][a].  Thread t owns factor
-// index t (k <= blockDim.x).  idxs / rstage: shared scratch of `batch` entries (a multiple of 32).
-__device__ __forceinline__ void syrk_direct(const float* __restrict__ fixed, const int32_t* __restrict__ indices,
-                                            const float* __restrict__ values, int64_t lo, int deg, int k, SyrkState& st,
-                                            float* A, int NT, float scale, int* idxs, float* rstage, int batch, float* bvec) {
+// D (TMEM) = pre_scale^2 * Y_r^T Y_r (k x k) for the deg rows indices[lo .. lo+deg) of `fixed`, and
+// bvec[a] = sum_j values[lo+j] * Y[j][a].  Thread t owns factor index t (k <= blockDim.x).
+// idxs / rstage: shared scratch of `batch` entries (a multiple of 32).
+__device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__ fixed, const int32_t* __restrict__ indices,
+                                                       const float* __restrict__ values, int64_t lo, int deg, int k,
+                                                       SyrkState& st, float pre_scale, int npad, int* idxs, float* rstage,
+                                                       int batch, float* bvec) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int a = tid;
     const int nkb = (deg + kSyrkKB - 1) / kSyrkKB;
     const size_t half_bytes = (size_t)st.rows_pad * 128;
     const size_t stage_bytes = 2 * half_bytes;
-    const int npad = (k + 15) & ~15;
     const bool two = k > 128;
     const int kb_per_batch = batch / kSyrkKB;
     bool pending[2] = {false, false};
@@ -233,10 +237,10 @@ __device__ __forceinline__ void syrk_direct(const float* __restrict__ fixed, con
 #pragma unroll
             for (int c = 0; c < kSyrkKB / 4; ++c) {
                 float4 h, l;
-                split_tf32(v[4 * c], h.x, l.x);
-                split_tf32(v[4 * c + 1], h.y, l.y);
-                split_tf32(v[4 * c + 2], h.z, l.z);
-                split_tf32(v[4 * c + 3], h.w, l.w);
+                split_tf32(v[4 * c] * pre_scale, h.x, l.x);
+                split_tf32(v[4 * c + 1] * pre_scale, h.y, l.y);
+                split_tf32(v[4 * c + 2] * pre_scale, h.z, l.z);
+                split_tf32(v[4 * c + 3] * pre_scale, h.w, l.w);
                 bsum = fmaf(rstage[slot + 4 * c], v[4 * c], bsum);
                 bsum = fmaf(rstage[slot + 4 * c + 1], v[4 * c + 1], bsum);
                 bsum = fmaf(rstage[slot + 4 * c + 2], v[4 * c + 2], bsum);
@@ -260,6 +264,13 @@ __device__ __forceinline__ void syrk_direct(const float* __restrict__ fixed, con
     tc_fence_after();
     if (a < k) bvec[a] = bsum;
     __syncthreads();
+}
+
+// A = scale * Y_r^T Y_r as tiles (no diagonal term: the caller adds the shared base); bvec = sum r y.
+__device__ __forceinline__ void syrk_direct(const float* __restrict__ fixed, const int32_t* __restrict__ indices,
+                                            const float* __restrict__ values, int64_t lo, int deg, int k, SyrkState& st,
+                                            float* A, int NT, float scale, int* idxs, float* rstage, int batch, float* bvec) {
+    syrk_direct_accumulate(fixed, indices, values, lo, deg, k, st, 1.f, (k + 15) & ~15, idxs, rstage, batch, bvec);
     syrk_epilogue(st, A, NT, k, scale, 0.f);
     tc_fence_before();
 }

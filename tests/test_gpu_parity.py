@@ -311,6 +311,11 @@ def test_large_k_paths(native, k):
         h.close()
 
 
+# float32 row systems: normal matrix resident in tensor memory (tc_chol.cuh) / tensor-core accumulation
+# into shared-memory tiles (tc_syrk.cuh + als_solve.cuh) / all-SIMT (als_solve.cuh)
+TC_VARIANTS = (("tmem", "1", "1"), ("tiles", "1", "0"), ("simt", "0", "0"))
+
+
 @pytest.mark.parametrize("m,n,k,nnz", [(60, 900, 256, 11000), (80, 800, 200, 9000), (48, 1000, 96, 5000),
                                        (70, 900, 300, 9000)])
 def test_tensor_core_row_systems_fp32(native, monkeypatch, m, n, k, nnz):
@@ -322,18 +327,21 @@ def test_tensor_core_row_systems_fp32(native, monkeypatch, m, n, k, nnz):
     assert (deg > 128).any() and ((deg > 63) & (deg <= 128)).any(), deg   # both accumulator shapes
     u = oals.als_half_step(u0.copy(), v0, train, 0.01)
     got = {}
-    for flag in ("1", "0"):
-        monkeypatch.setenv("HYPREC_TC_SOLVE", flag)
+    for name, syrk, chol in TC_VARIANTS:
+        monkeypatch.setenv("HYPREC_TC_SOLVE", syrk)
+        monkeypatch.setenv("HYPREC_TC_CHOL", chol)
         h, _ = make_handle(native, train, native.F32)
         h.set_factors(u0, v0)
         h.als_half_step(native.SIDE_USER, 0.01)
-        got[flag], _ = h.get_factors()
+        got[name], _ = h.get_factors()
         h.close()
-    print("k=%d tc vs oracle %.2e, simt vs oracle %.2e, tc vs simt %.2e" %
-          (k, rel_frob(got["1"], u), rel_frob(got["0"], u), rel_frob(got["1"], got["0"])))
-    assert rel_frob(got["1"], u) < F32_FROB
-    assert rel_frob(got["1"], got["0"]) < 5e-5
-    assert not numpy.array_equal(got["1"], got["0"])   # the switch really selects a different path
+    for name in ("tmem", "tiles"):
+        print("k=%d %s vs oracle %.2e, simt vs oracle %.2e, %s vs simt %.2e" %
+              (k, name, rel_frob(got[name], u), rel_frob(got["simt"], u), name, rel_frob(got[name], got["simt"])))
+        assert rel_frob(got[name], u) < F32_FROB
+        assert rel_frob(got[name], got["simt"]) < 5e-5
+        assert not numpy.array_equal(got[name], got["simt"])   # the switches really select different paths
+    assert not numpy.array_equal(got["tmem"], got["tiles"])
 
 
 @pytest.mark.parametrize("m,n,k,nnz,lowrank", [(60, 900, 256, 11000, "0"), (48, 1000, 96, 5000, "1"),
@@ -349,22 +357,25 @@ def test_tensor_core_direct_systems_fp32(native, monkeypatch, m, n, k, nnz, lowr
     v = oals.als_half_step(v0.copy(), u, csc, 0.01, prior=theta)
     monkeypatch.setenv("HYPREC_LOWRANK", lowrank)
     got = {}
-    for flag in ("1", "0"):
-        monkeypatch.setenv("HYPREC_TC_SOLVE", flag)
+    for name, syrk, chol in TC_VARIANTS:
+        monkeypatch.setenv("HYPREC_TC_SOLVE", syrk)
+        monkeypatch.setenv("HYPREC_TC_CHOL", chol)
         h, _ = make_handle(native, train, native.F32)
         h.set_factors(u0, v0)
         h.set_item_prior(theta)
         h.als_half_step(native.SIDE_USER, 0.01)
         h.als_half_step(native.SIDE_ITEM, 0.01)
-        got[flag] = h.get_factors()
+        got[name] = h.get_factors()
         h.close()
-    for side, ref in ((0, u), (1, v)):
-        print("k=%d side %d tc vs oracle %.2e, simt vs oracle %.2e, tc vs simt %.2e" %
-              (k, side, rel_frob(got["1"][side], ref), rel_frob(got["0"][side], ref),
-               rel_frob(got["1"][side], got["0"][side])))
-        assert rel_frob(got["1"][side], ref) < F32_FROB
-        assert rel_frob(got["1"][side], got["0"][side]) < 5e-5
-    assert not numpy.array_equal(got["1"][0], got["0"][0])
+    for name in ("tmem", "tiles"):
+        for side, ref in ((0, u), (1, v)):
+            print("k=%d side %d %s vs oracle %.2e, simt vs oracle %.2e, %s vs simt %.2e" %
+                  (k, side, name, rel_frob(got[name][side], ref), rel_frob(got["simt"][side], ref), name,
+                   rel_frob(got[name][side], got["simt"][side])))
+            assert rel_frob(got[name][side], ref) < F32_FROB
+            assert rel_frob(got[name][side], got["simt"][side]) < 1e-4
+        assert not numpy.array_equal(got[name][0], got["simt"][0])
+    assert not numpy.array_equal(got["tmem"][0], got["tiles"][0])
 
 
 def test_cached_candidates_and_pinned_outputs(native):

@@ -799,7 +799,7 @@ struct Engine : EngineBase {
         const bool lowrank = h->lowrank_enabled && lambda > 0.0 && k >= 16;
         // float32 k x k systems (64 <= k <= 256) accumulate sum y y^T on the tensor cores (tc_syrk.cuh)
         const bool tc_direct = h->tc_solve_enabled && sizeof(T) == sizeof(float) && k >= 64 && k <= 256;
-        const bool chol_direct = tc_direct && h->tc_chol_enabled;
+        const bool chol_direct = tc_direct && h->tc_chol_enabled && k % 4 == 0;
         if (!lowrank) {
             Timer t(h, HYPREC_T_SOLVE);
             if constexpr (sizeof(T) == sizeof(float)) {

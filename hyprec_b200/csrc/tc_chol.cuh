@@ -88,6 +88,12 @@ __device__ __forceinline__ void tmem_store_32x32(uint32_t taddr, const uint32_t 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // D[rows of the M-block][n_cols columns from TMEM column `tcol`] -= A B^T, K = 32 (one staged panel):
 // A = stage rows [a_row0, a_row0+128), B = stage rows [b_row0, b_row0+n_cols); 3xTF32, A negated.
 __device__ __forceinline__ void chol_issue_update(uint32_t tmem_d, unsigned char* hi_base, size_t half_bytes, int a_row0,
@@ -183,17 +189,17 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
         if (lowrank) {
             for (int i = tid; i < dim; i += kCholThreads) idxs[i] = p.indices[lo + i];
             __syncthreads();
-            for (int i = warp; i < dim; i += kCholThreads / 32) {
-                float v = p.values[lo + i];
-                if (prior_row) {
+            if (prior_row == nullptr) {
+                for (int i = tid; i < dim; i += kCholThreads) bs[i] = p.values[lo + i];
+            } else {
+                for (int i = warp; i < dim; i += kCholThreads / 32) {
                     const float* q = p.fixed + (int64_t)idxs[i] * k;
                     double d = 0.0;
                     for (int l = lane; l < k; l += 32) d += (double)q[l] * (double)prior_row[l];
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
-                    v -= pos_scale * p.lambda * (float)d;
+                    if (lane == 0) bs[i] = p.values[lo + i] - pos_scale * p.lambda * (float)d;
                 }
-                if (lane == 0) bs[i] = v;
             }
             __syncthreads();
             syrk_lowrank_accumulate(p.fixed, idxs, dim, k, st, sqrt_pos, dimp);
@@ -216,6 +222,18 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
         }
         HYPREC_TCPROF(0)
         float bval = (tid < dim) ? bs[tid] : 0.f;      // this row's right-hand side entry
+        // direct mode: this row's 32 entries of the shared Gram for the coming panel, fetched one panel
+        // ahead (behind the trailing update's wait)
+        float4 g4[8];
+        auto fetch_gram = [&](int c0) {
+            if (!lowrank && tid < dim && tid >= c0) {
+                const float* grow = p.gram + (int64_t)tid * k + c0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    g4[c] = (c0 + 4 * c < dim) ? __ldg(reinterpret_cast<const float4*>(grow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        fetch_gram(0);
 
         // ---- 2. blocked Cholesky, 32-column panels --------------------------------------------
         for (int pn = 0; pn < n_panels; ++pn) {
@@ -225,50 +243,76 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
             if (warp >= pn && r < dimp) {              // (whole warps: dimp is a multiple of 32)
                 uint32_t raw[32];
                 tmem_load_32x32(my_taddr + (uint32_t)c0, raw);
-                const float* grow = (!lowrank && r < dim) ? p.gram + (int64_t)r * k + c0 : nullptr;
+                const float* gv = reinterpret_cast<const float*>(g4);
+                const int dj = r - c0;                 // this row's diagonal entry sits at a[dj] when 0 <= dj < 32
+                if (r < dim && c0 + kCholPanel <= dim) {
+                    // interior panel (the common case): branch-free
+                    const float diag_add = lowrank ? 1.f : p.lambda;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = c0 + j;
-                    float v = 0.f;
-                    if (r < dim && col < dim) {
-                        v = __uint_as_float(raw[j]);
-                        if (lowrank) v += (r == col) ? 1.f : 0.f;
-                        else v += (float)kConfNeg * __ldg(grow + j) + ((r == col) ? p.lambda : 0.f);
-                    } else {
-                        v = (r == col) ? 1.f : 0.f;    // identity padding
+                    for (int j = 0; j < 32; ++j) {
+                        float v = __uint_as_float(raw[j]);
+                        if (!lowrank) v = fmaf((float)kConfNeg, gv[j], v);
+                        a[j] = v + ((j == dj) ? diag_add : 0.f);
                     }
-                    a[j] = v;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c0 + j;
+                        float v;
+                        if (r < dim && col < dim) {
+                            v = __uint_as_float(raw[j]);
+                            if (lowrank) v += (j == dj) ? 1.f : 0.f;
+                            else v += (float)kConfNeg * gv[j] + ((j == dj) ? p.lambda : 0.f);
+                        } else {
+                            v = (j == dj) ? 1.f : 0.f;     // identity padding
+                        }
+                        a[j] = v;
+                    }
                 }
             }
             if (warp == pn) {
                 // the 32 x 32 diagonal block, one row per lane: L11 in place, 1 / diagonal kept
+                // column j (still unscaled) goes through shared memory: every lane reads the pivot and
+                // the entries of the rows after j as broadcast vector loads -- one store and <= 8 loads
+                // per column where lane-to-lane shuffles would need 31 - j.
                 float dmine = 0.f;
+                float* colbuf = part;                  // 2 x 32 floats, free until the back substitution
+                float piv = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float piv = __shfl_sync(0xffffffffu, a[j], j);
-                    const float d = rsqrtf(piv);
-                    a[j] *= d;
+                    float* col = colbuf + (j & 1) * 32;
+                    col[lane] = a[j];
+                    const float d = rsqrt_approx(piv);
+                    const float w = a[j] * d * d;      // a[j] / pivot
                     if (lane == j) dmine = d;
+                    // the next pivot only needs lane j+1's own entries: it goes out first (one shuffle on
+                    // the critical path), the rest of the update follows through shared memory
+                    if (j < 31) piv = __shfl_sync(0xffffffffu, fmaf(-w, a[j], a[j + 1]), j + 1);
+                    __syncwarp();
+                    const float4* col4 = reinterpret_cast<const float4*>(col);
 #pragma unroll
-                    for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-a[j], __shfl_sync(0xffffffffu, a[j], c), a[c]);
+                    for (int q = (j + 1) / 4; q < 8; ++q) {
+                        const float4 t = col4[q];
+                        if (4 * q > j) a[4 * q] = fmaf(-w, t.x, a[4 * q]);
+                        if (4 * q + 1 > j) a[4 * q + 1] = fmaf(-w, t.y, a[4 * q + 1]);
+                        if (4 * q + 2 > j) a[4 * q + 2] = fmaf(-w, t.z, a[4 * q + 2]);
+                        if (4 * q + 3 > j) a[4 * q + 3] = fmaf(-w, t.w, a[4 * q + 3]);
+                    }
+                    a[j] *= d;
+                    l11t[j * 32 + lane] = a[j];        // column j of L11, for the rows below
                 }
                 dinv[c0 + lane] = dmine;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    l11[lane * 33 + j] = a[j];
-                    l11t[j * 32 + lane] = a[j];
-                }
-                uint32_t raw[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
-                tmem_store_32x32(my_taddr + (uint32_t)c0, raw);
             }
-            tc_fence_before();
             __syncthreads();
             HYPREC_TCPROF(2)
             const int rem0 = c0 + kCholPanel;
             unsigned char* hi_base = st.stage;         // panel updates use stage 0
             if (warp == pn) {
+                // (off the other warps' critical path) L11 goes back to TMEM for the back substitution
+                uint32_t raw[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
+                tmem_store_32x32(my_taddr + (uint32_t)c0, raw);
                 // forward substitution of this panel's right-hand side: z_p = L11^-1 b_p
                 float zmine = 0.f;
 #pragma unroll
@@ -280,11 +324,20 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
                 zs[c0 + lane] = zmine;
             } else if (warp > pn && r < dimp) {
                 // x = a L11^-T (this row's 32 entries of L), column by column
+                const float4* l4 = reinterpret_cast<const float4*>(l11t);
+                const float4* dinv4 = reinterpret_cast<const float4*>(dinv + c0);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    a[j] *= dinv[c0 + j];
+                    const float4 dv = dinv4[j / 4];
+                    a[j] *= (j % 4 == 0) ? dv.x : (j % 4 == 1) ? dv.y : (j % 4 == 2) ? dv.z : dv.w;
 #pragma unroll
-                    for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-a[j], l11t[j * 32 + c], a[c]);
+                    for (int q = (j + 1) / 4; q < 8; ++q) {
+                        const float4 t = l4[j * 8 + q];
+                        if (4 * q > j) a[4 * q] = fmaf(-a[j], t.x, a[4 * q]);
+                        if (4 * q + 1 > j) a[4 * q + 1] = fmaf(-a[j], t.y, a[4 * q + 1]);
+                        if (4 * q + 2 > j) a[4 * q + 2] = fmaf(-a[j], t.z, a[4 * q + 2]);
+                        if (4 * q + 3 > j) a[4 * q + 3] = fmaf(-a[j], t.w, a[4 * q + 3]);
+                    }
                 }
                 uint32_t raw[32];
 #pragma unroll
@@ -324,6 +377,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
                     for (int j = 0; j < 32; ++j) acc = fmaf(a[j], zs[c0 + j], acc);
                     bval -= acc;
                 }
+                fetch_gram(rem0);
                 mbar_wait(&bars[2], upd_phase);
                 upd_phase ^= 1;
                 tc_fence_after();
@@ -393,13 +447,13 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
             for (int a = tid; a < k; a += kCholThreads) {
                 float s = prior_row ? p.lambda * prior_row[a] : 0.f;
                 int i = 0;
-                for (; i + 4 <= dim; i += 4) {
-                    const float q0 = p.fixed[(int64_t)idxs[i] * k + a], q1 = p.fixed[(int64_t)idxs[i + 1] * k + a];
-                    const float q2 = p.fixed[(int64_t)idxs[i + 2] * k + a], q3 = p.fixed[(int64_t)idxs[i + 3] * k + a];
-                    s += q0 * xs[i];
-                    s += q1 * xs[i + 1];
-                    s += q2 * xs[i + 2];
-                    s += q3 * xs[i + 3];
+#pragma unroll 2
+                for (; i + 8 <= dim; i += 8) {   // eight (sixteen after unrolling) loads in flight per thread
+                    float q[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) q[u] = __ldg(p.fixed + (int64_t)idxs[i + u] * k + a);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s = fmaf(q[u], xs[i + u], s);
                 }
                 for (; i < dim; ++i) s += p.fixed[(int64_t)idxs[i] * k + a] * xs[i];
                 if (!(s - s == 0.f)) *p.status = 1;

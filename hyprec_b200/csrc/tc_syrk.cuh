@@ -136,16 +136,19 @@ __device__ __forceinline__ void syrk_lowrank_accumulate(const float* __restrict_
     const bool two = dim > 128;
     bool pending[2] = {false, false};
 
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
+    // the gather runs two k-blocks ahead of the stores (two register buffers): a k-block's load latency
+    // is covered by the split / store / MMA issue of the two blocks before it
+    auto load = [&](int kb, float4 (&v)[8]) {
         const int col = kb * kSyrkKB + chunk * 4;
-        float4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int r = r0 + j * rpp;
             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < dim && col < k) v[j] = __ldg(reinterpret_cast<const float4*>(fixed + (int64_t)idxs[r] * k + col));
         }
+    };
+    auto stage_and_issue = [&](int kb, float4 (&v)[8]) {
+        const int s = kb & 1;
         if (pending[s]) {     // the MMAs that read this stage two k-blocks ago have retired
             mbar_wait(&st.bars[s], st.phase[s]);
             st.phase[s] ^= 1;
@@ -170,6 +173,17 @@ __device__ __forceinline__ void syrk_lowrank_accumulate(const float* __restrict_
         __syncthreads();
         if (tid == 0) syrk_issue(st, hi_base, half_bytes, npad, two, kb != 0, &st.bars[s]);
         pending[s] = true;
+    };
+    float4 va[8], vb[8];
+    load(0, va);
+    if (nkb > 1) load(1, vb);
+    for (int kb = 0; kb < nkb; kb += 2) {
+        stage_and_issue(kb, va);
+        if (kb + 2 < nkb) load(kb + 2, va);
+        if (kb + 1 < nkb) {
+            stage_and_issue(kb + 1, vb);
+            if (kb + 3 < nkb) load(kb + 3, vb);
+        }
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s)
@@ -208,24 +222,27 @@ __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__
     bool pending[2] = {false, false};
     float bsum = 0.f;
 
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
-        const int slot = (kb % kb_per_batch) * kSyrkKB;
-        if (slot == 0) {
-            // (every thread is past its reads of the previous batch: it has crossed the barrier below)
-            for (int i = tid; i < batch; i += nthreads) {
-                const int j = kb * kSyrkKB + i;
-                idxs[i] = j < deg ? indices[lo + j] : -1;
-                rstage[i] = j < deg ? values[lo + j] : 0.f;
-            }
-            __syncthreads();
+    // ids and ratings of a whole batch of k-blocks are staged at once; the factor loads run one k-block
+    // ahead of the stores (two register buffers)
+    auto stage_ids = [&](int kb) {
+        for (int i = tid; i < batch; i += nthreads) {
+            const int j = kb * kSyrkKB + i;
+            idxs[i] = j < deg ? indices[lo + j] : -1;
+            rstage[i] = j < deg ? values[lo + j] : 0.f;
         }
-        float v[kSyrkKB];
+        __syncthreads();
+    };
+    auto load = [&](int kb, float (&v)[kSyrkKB]) {
+        const int slot = (kb % kb_per_batch) * kSyrkKB;
 #pragma unroll
         for (int jj = 0; jj < kSyrkKB; ++jj) {
             const int id = idxs[slot + jj];
             v[jj] = (a < k && id >= 0) ? __ldg(fixed + (int64_t)id * k + a) : 0.f;
         }
+    };
+    auto stage_and_issue = [&](int kb, float (&v)[kSyrkKB]) {
+        const int s = kb & 1;
+        const int slot = (kb % kb_per_batch) * kSyrkKB;
         if (pending[s]) {
             mbar_wait(&st.bars[s], st.phase[s]);
             st.phase[s] ^= 1;
@@ -254,6 +271,22 @@ __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__
         __syncthreads();
         if (tid == 0) syrk_issue(st, hi_base, half_bytes, npad, two, kb != 0, &st.bars[s]);
         pending[s] = true;
+    };
+    // a batch's ids may only be replaced once no load of the batch is outstanding: the look-ahead
+    // stops at batch boundaries
+    float va[kSyrkKB], vb[kSyrkKB];
+    for (int kb0 = 0; kb0 < nkb; kb0 += kb_per_batch) {
+        const int kb1 = min(nkb, kb0 + kb_per_batch);
+        stage_ids(kb0);
+        load(kb0, va);
+        for (int kb = kb0; kb < kb1; kb += 2) {
+            if (kb + 1 < kb1) load(kb + 1, vb);
+            stage_and_issue(kb, va);
+            if (kb + 1 < kb1) {
+                if (kb + 2 < kb1) load(kb + 2, va);
+                stage_and_issue(kb + 1, vb);
+            }
+        }
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s)

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
             if (prior_row != nullptr && tid < k) bs[tid] += p.lambda * prior_row[tid];
         }
         HYPREC_TCPROF(0)
-        float bval = (tid < dim) ? bs[tid] : 0.f;      // this row's right-hand side entry
+        if (tid >= dim && tid < dimp) bs[tid] = 0.f;   // identity padding solves to zero
         // direct mode: this row's 32 entries of the shared Gram for the coming panel, fetched one panel
         // ahead (behind the trailing update's wait)
         float4 g4[8];
@@ -313,16 +313,22 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
 #pragma unroll
                 for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
                 tmem_store_32x32(my_taddr + (uint32_t)c0, raw);
-                // forward substitution of this panel's right-hand side: z_p = L11^-1 b_p
+            }
+            if (warp == 0) {
+                // forward substitution of this panel's right-hand side, z_p = L11^-1 b_p, by warp 0: it is
+                // the diagonal warp of panel 0 and has no rows left in the later panels, so the chain runs
+                // beside the other warps' panel solve
+                float bv = bs[c0 + lane];
                 float zmine = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float zj = __shfl_sync(0xffffffffu, bval, j) * dinv[c0 + j];
+                    const float zj = __shfl_sync(0xffffffffu, bv, j) * dinv[c0 + j];
                     if (lane == j) zmine = zj;
-                    if (lane > j) bval = fmaf(-a[j], zj, bval);
+                    if (lane > j) bv = fmaf(-l11t[j * 32 + lane], zj, bv);
                 }
                 zs[c0 + lane] = zmine;
-            } else if (warp > pn && r < dimp) {
+            }
+            if (warp > pn && r < dimp) {
                 // x = a L11^-T (this row's 32 entries of L), column by column
                 const float4* l4 = reinterpret_cast<const float4*>(l11t);
                 const float4* dinv4 = reinterpret_cast<const float4*>(dinv + c0);
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc = fmaf(a[j], zs[c0 + j], acc);
-                    bval -= acc;
+                    bs[r] -= acc;
                 }
                 fetch_gram(rem0);
                 mbar_wait(&bars[2], upd_phase);

@@ -206,21 +206,23 @@ __device__ __forceinline__ void syrk_lowrank(const float* __restrict__ fixed, co
 
 
 // D (TMEM) = pre_scale^2 * Y_r^T Y_r (k x k) for the deg rows indices[lo .. lo+deg) of `fixed`, and
-// bvec[a] = sum_j values[lo+j] * Y[j][a].  Thread t owns factor index t (k <= blockDim.x).
+// bvec[a] = sum_j values[lo+j] * Y[j][a] (k even, k <= 256).
 // idxs / rstage: shared scratch of `batch` entries (a multiple of 32).
 __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__ fixed, const int32_t* __restrict__ indices,
                                                        const float* __restrict__ values, int64_t lo, int deg, int k,
                                                        SyrkState& st, float pre_scale, int npad, int* idxs, float* rstage,
                                                        int batch, float* bvec) {
+    // blockDim.x == 256: thread t owns the factor pair a = 2 (t % 128), a + 1 for the 16 gathered rows
+    // 16 (t / 128) .. +15 of every k-block (8-byte loads, one address computation per row and pair)
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int a = tid;
+    const int half = tid >> 7, a = (tid & 127) * 2;
     const int nkb = (deg + kSyrkKB - 1) / kSyrkKB;
     const size_t half_bytes = (size_t)st.rows_pad * 128;
     const size_t stage_bytes = 2 * half_bytes;
     const bool two = k > 128;
     const int kb_per_batch = batch / kSyrkKB;
     bool pending[2] = {false, false};
-    float bsum = 0.f;
+    float bsum0 = 0.f, bsum1 = 0.f;
 
     // ids and ratings of a whole batch of k-blocks are staged at once; the factor loads run one k-block
     // ahead of the stores (two register buffers)
@@ -232,17 +234,17 @@ __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__
         }
         __syncthreads();
     };
-    auto load = [&](int kb, float (&v)[kSyrkKB]) {
-        const int slot = (kb % kb_per_batch) * kSyrkKB;
+    auto load = [&](int kb, float2 (&v)[16]) {
+        const int slot = (kb % kb_per_batch) * kSyrkKB + 16 * half;
 #pragma unroll
-        for (int jj = 0; jj < kSyrkKB; ++jj) {
+        for (int jj = 0; jj < 16; ++jj) {
             const int id = idxs[slot + jj];
-            v[jj] = (a < k && id >= 0) ? __ldg(fixed + (int64_t)id * k + a) : 0.f;
+            v[jj] = (a < k && id >= 0) ? __ldg(reinterpret_cast<const float2*>(fixed + (int64_t)id * k + a)) : make_float2(0.f, 0.f);
         }
     };
-    auto stage_and_issue = [&](int kb, float (&v)[kSyrkKB]) {
+    auto stage_and_issue = [&](int kb, float2 (&v)[16]) {
         const int s = kb & 1;
-        const int slot = (kb % kb_per_batch) * kSyrkKB;
+        const int slot = (kb % kb_per_batch) * kSyrkKB + 16 * half;
         if (pending[s]) {
             mbar_wait(&st.bars[s], st.phase[s]);
             st.phase[s] ^= 1;
@@ -250,21 +252,32 @@ __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__
         }
         unsigned char* hi_base = st.stage + (size_t)s * stage_bytes;
         if (a < st.rows_pad) {
-            const size_t row_off = (size_t)(a >> 3) * 1024 + (size_t)(a & 7) * 128;
+            const size_t row0 = (size_t)(a >> 3) * 1024 + (size_t)(a & 7) * 128;          // row a (a is even: a + 1 is
+            const size_t row1 = row0 + 128;                                                 // in the same 8-row group)
 #pragma unroll
-            for (int c = 0; c < kSyrkKB / 4; ++c) {
-                float4 h, l;
-                split_tf32(v[4 * c] * pre_scale, h.x, l.x);
-                split_tf32(v[4 * c + 1] * pre_scale, h.y, l.y);
-                split_tf32(v[4 * c + 2] * pre_scale, h.z, l.z);
-                split_tf32(v[4 * c + 3] * pre_scale, h.w, l.w);
-                bsum = fmaf(rstage[slot + 4 * c], v[4 * c], bsum);
-                bsum = fmaf(rstage[slot + 4 * c + 1], v[4 * c + 1], bsum);
-                bsum = fmaf(rstage[slot + 4 * c + 2], v[4 * c + 2], bsum);
-                bsum = fmaf(rstage[slot + 4 * c + 3], v[4 * c + 3], bsum);
-                const size_t off = row_off + (size_t)((c ^ (a & 7)) << 4);
-                *reinterpret_cast<float4*>(hi_base + off) = h;
-                *reinterpret_cast<float4*>(hi_base + half_bytes + off) = l;
+            for (int c = 0; c < 4; ++c) {
+                float4 h0, l0, h1, l1;
+                split_tf32(v[4 * c].x * pre_scale, h0.x, l0.x);
+                split_tf32(v[4 * c + 1].x * pre_scale, h0.y, l0.y);
+                split_tf32(v[4 * c + 2].x * pre_scale, h0.z, l0.z);
+                split_tf32(v[4 * c + 3].x * pre_scale, h0.w, l0.w);
+                split_tf32(v[4 * c].y * pre_scale, h1.x, l1.x);
+                split_tf32(v[4 * c + 1].y * pre_scale, h1.y, l1.y);
+                split_tf32(v[4 * c + 2].y * pre_scale, h1.z, l1.z);
+                split_tf32(v[4 * c + 3].y * pre_scale, h1.w, l1.w);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float rt = rstage[slot + 4 * c + e];
+                    bsum0 = fmaf(rt, v[4 * c + e].x, bsum0);
+                    bsum1 = fmaf(rt, v[4 * c + e].y, bsum1);
+                }
+                const int chunk = 4 * half + c;
+                const size_t off0 = row0 + (size_t)((chunk ^ (a & 7)) << 4);
+                const size_t off1 = row1 + (size_t)((chunk ^ ((a + 1) & 7)) << 4);
+                *reinterpret_cast<float4*>(hi_base + off0) = h0;
+                *reinterpret_cast<float4*>(hi_base + half_bytes + off0) = l0;
+                *reinterpret_cast<float4*>(hi_base + off1) = h1;
+                *reinterpret_cast<float4*>(hi_base + half_bytes + off1) = l1;
             }
         }
         fence_async_smem();
@@ -274,7 +287,7 @@ __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__
     };
     // a batch's ids may only be replaced once no load of the batch is outstanding: the look-ahead
     // stops at batch boundaries
-    float va[kSyrkKB], vb[kSyrkKB];
+    float2 va[16], vb[16];
     for (int kb0 = 0; kb0 < nkb; kb0 += kb_per_batch) {
         const int kb1 = min(nkb, kb0 + kb_per_batch);
         stage_ids(kb0);
@@ -295,7 +308,15 @@ __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__
             st.phase[s] ^= 1;
         }
     tc_fence_after();
-    if (a < k) bvec[a] = bsum;
+    if (half == 0 && a < k) {
+        bvec[a] = bsum0;
+        bvec[a + 1] = bsum1;
+    }
+    __syncthreads();
+    if (half == 1 && a < k) {
+        bvec[a] += bsum0;
+        bvec[a + 1] += bsum1;
+    }
     __syncthreads();
 }
 

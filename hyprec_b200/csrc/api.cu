@@ -372,8 +372,31 @@ struct Engine : EngineBase {
         int64_t per = (rows + nsplit - 1) / nsplit;
         per = (per + hyprec::kGramRows - 1) / hyprec::kGramRows * hyprec::kGramRows;
         nsplit = (int)((rows + per - 1) / per);
-        HY_TRY(gram_partial.reserve(sizeof(T) * (size_t)nsplit * k * k));
         HY_TRY(gram[which].reserve(sizeof(T) * (size_t)k * k));
+        if constexpr (sizeof(T) == sizeof(float)) {
+            // float32 mode: Y^T Y on the tensor cores (3xTF32, tc_syrk.cuh gram_tc_kernel)
+            if (h->tc_solve_enabled && k % 2 == 0 && k >= 16 && k <= 256 && rows >= 256) {
+                namespace tc = hyprec::tc;
+                const tc::GramTcLayout lay = tc::gram_tc_layout(k);
+                if (lay.total <= (size_t)h->max_smem) {
+                    const int grid = h->num_sms;
+                    int64_t per_cta = (rows + grid - 1) / grid;
+                    per_cta = (per_cta + 31) / 32 * 32;
+                    HY_TRY(gram_partial.reserve(sizeof(float) * (size_t)grid * k * k));
+                    HY_TRY(ensure_dynamic_smem((const void*)tc::gram_tc_kernel, (int)lay.total));
+                    Timer t(h, HYPREC_T_GRAM);
+                    tc::gram_tc_kernel<<<grid, 256, lay.total, h->stream>>>(reinterpret_cast<const float*>(y), rows, k, per_cta,
+                                                                             gram_partial.as<float>());
+                    tc::gram_tc_reduce_kernel<<<(k * k + 255) / 256, 256, 0, h->stream>>>(gram_partial.as<float>(), grid, k,
+                                                                                           gram[which].template as<float>());
+                    h->launches += 2;
+                    CU_TRY(cudaGetLastError());
+                    gram_ok[which] = true;
+                    return HYPREC_OK;
+                }
+            }
+        }
+        HY_TRY(gram_partial.reserve(sizeof(T) * (size_t)nsplit * k * k));
         Timer t(h, HYPREC_T_GRAM);
         hyprec::gram_partial_kernel<T><<<dim3(tiles, nsplit), hyprec::kGramThreads, 0, h->stream>>>(
             y, rows, k, per, gram_partial.as<T>());

@@ -229,8 +229,8 @@ __device__ __forceinline__ void syrk_direct_accumulate(const float* __restrict__
     auto stage_ids = [&](int kb) {
         for (int i = tid; i < batch; i += nthreads) {
             const int j = kb * kSyrkKB + i;
-            idxs[i] = j < deg ? indices[lo + j] : -1;
-            rstage[i] = j < deg ? values[lo + j] : 0.f;
+            idxs[i] = j < deg ? (indices ? indices[lo + j] : (int)(lo + j)) : -1;   // null: consecutive rows
+            rstage[i] = (values && j < deg) ? values[lo + j] : 0.f;
         }
         __syncthreads();
     };
@@ -327,6 +327,97 @@ __device__ __forceinline__ void syrk_direct(const float* __restrict__ fixed, con
     syrk_direct_accumulate(fixed, indices, values, lo, deg, k, st, 1.f, (k + 15) & ~15, idxs, rstage, batch, bvec);
     syrk_epilogue(st, A, NT, k, scale, 0.f);
     tc_fence_before();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Gram matrix G = Y^T Y of a factor matrix on the tensor cores (float32 mode): the same transposing
+// accumulation as the k x k row systems, over consecutive rows.  Replaces the shared
+// `fixed_vecs.T.dot(fixed_vecs)` part of (Y.T * confidence).dot(Y)
+// (/root/reference/lib/collaborative_filtering.py:84, :92).
+// One CTA per SM, each over a contiguous slice of rows; the k x k partial (lower blocks) goes to
+// `partial[blockIdx.x]`, gram_tc_reduce_kernel sums the slices in float64 and mirrors the result.
+// ------------------------------------------------------------------------------------------------
+struct GramTcLayout {
+    size_t off_stage, off_idx, off_rst, off_b, off_bar, total;
+};
+__host__ __device__ __forceinline__ GramTcLayout gram_tc_layout(int k) {
+    GramTcLayout l;
+    size_t o = 0;
+    l.off_stage = o; o += 2 * syrk_stage_bytes(k);
+    l.off_idx = o;   o += sizeof(int) * 256;
+    l.off_rst = o;   o += sizeof(float) * 256;
+    l.off_b = o;     o += sizeof(float) * 256;
+    l.off_bar = o;
+    o += 32;
+    l.total = o + 1024;
+    return l;
+}
+
+__global__ void __launch_bounds__(256, 1) gram_tc_kernel(const float* __restrict__ y, int64_t n_rows, int k,
+                                                         int64_t rows_per_cta, float* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char gram_smem_dyn[];
+    unsigned char* smem = gram_smem_dyn + ((1024u - (smem_u32(gram_smem_dyn) & 1023u)) & 1023u);
+    const GramTcLayout lay = gram_tc_layout(k);
+    uint64_t* bars = (uint64_t*)(smem + lay.off_bar);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2);
+    const int tid = threadIdx.x, warp = tid / 32;
+    const uint32_t tmem_cols = (uint32_t)syrk_tmem_cols(k);
+    SyrkState st;
+    st.bars = bars;
+    st.phase[0] = st.phase[1] = 0;
+    st.stage = smem + lay.off_stage;
+    st.rows_pad = syrk_rows_pad(k);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    st.tmem_base = *tmem_slot;
+
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = r0 + rows_per_cta < n_rows ? r0 + rows_per_cta : n_rows;
+    const int deg = r1 > r0 ? (int)(r1 - r0) : 0;
+    float* out = partial + (size_t)blockIdx.x * k * k;
+    const int npad = (k + 15) & ~15;
+    if (deg > 0)
+        syrk_direct_accumulate(y, nullptr, nullptr, r0, deg, k, st, 1.f, npad, (int*)(smem + lay.off_idx),
+                               (float*)(smem + lay.off_rst), 256, (float*)(smem + lay.off_b));
+    // row i = tid: columns 0 .. 32 * (i / 32) + 31 (the row block's part on or below the diagonal blocks)
+    const int i = tid;
+    if (i < ((k + 31) & ~31)) {     // whole warps
+        const uint32_t taddr = st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tid >= 128 ? 128 : 0);
+        const int jmax = min(k, (i / 32) * 32 + 32);
+        for (int c = 0; c < jmax; c += 32) {
+            uint32_t v[32];
+            if (deg > 0) tmem_load_32x32(taddr + (uint32_t)c, v);
+            if (i < k) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj)
+                    if (c + jj < k) out[(size_t)i * k + c + jj] = deg > 0 ? __uint_as_float(v[jj]) : 0.f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(st.tmem_base, tmem_cols);
+}
+
+// G[i][j] = G[j][i] = sum over slices of partial[.][max(i,j)][min(i,j)]
+__global__ void gram_tc_reduce_kernel(const float* __restrict__ partial, int n_slices, int k, float* __restrict__ g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    const int i = idx / k, j = idx % k;
+    if (j > i) return;
+    // entries right of the diagonal 32-block of row i were not written: (i, j) with j <= i is always inside
+    double s = 0.0;
+    for (int c = 0; c < n_slices; ++c) s += (double)partial[(size_t)c * k * k + idx];
+    g[(size_t)i * k + j] = (float)s;
+    g[(size_t)j * k + i] = (float)s;
 }
 
 }  // namespace tc

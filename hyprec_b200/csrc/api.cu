@@ -20,6 +20,7 @@
 #include "score.cuh"
 #include "tc_score.cuh"
 #include "tc_chol.cuh"
+#include "tc_chol_multi.cuh"
 #include "topk.cuh"
 
 namespace {
@@ -107,6 +108,7 @@ struct hyprec_ctx {
     int64_t launches = 0;
     bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
     bool tc_enabled = true;        // HYPREC_TC=0 keeps the score sweep on the SIMT kernel
+    bool tc_multi_enabled = true;  // HYPREC_TC_MULTI=0: systems of <= 128 rows stay on the shared-memory tile kernel
     bool tc_chol_enabled = true;   // HYPREC_TC_CHOL=0: float32 systems factorise in shared-memory tiles (als_solve.cuh)
     bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
     int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
@@ -544,6 +546,48 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+
+    // several float32 low-rank systems of <= slot (32 / 64 / 128) unknowns per CTA pass (tc_chol_multi.cuh)
+    int launch_chol_multi(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list, int slot_rows,
+                          const float* fixed_ptr, const float* prior_ptr, int64_t work, cudaStream_t st, int slot) {
+        namespace tc = hyprec::tc;
+        const tc::CholMultiLayout lay = tc::chol_multi_layout();
+        if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "tensor-memory row launch does not fit shared memory");
+        auto kern = slot_rows == 32 ? tc::tc_chol_multi_kernel<32> : (slot_rows == 64 ? tc::tc_chol_multi_kernel<64> : tc::tc_chol_multi_kernel<128>);
+        HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
+        const Csr& rows_csr = user ? csr : csc;
+        tc::CholRowsArgs a;
+        a.indptr = rows_csr.indptr.template as<int64_t>();
+        a.indices = rows_csr.indices.template as<int32_t>();
+        a.values = rows_csr.values.template as<float>();
+        a.fixed = fixed_ptr;
+        a.gram = nullptr;
+        a.prior = prior_ptr;
+        a.out = ymat.as<float>();
+        a.work_counter = counter.as<int>() + slot;
+        a.status = counter.as<int>() + kStatusSlot;
+        a.lambda = (float)lambda;
+        a.k = k;
+        a.row_lo = lo;
+        a.row_hi = hi;
+        a.row_list = list;
+        a.n_list = n_list;
+        a.max_dim = slot_rows;
+        a.lowrank = 1;
+        a.tmem_cols = 256;
+        a.prof = nullptr;
+        if (h->prof_enabled && slot == h->prof_slot) {
+            if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
+            a.prof = prof_buf.as<long long>();
+        }
+        const int per_pass = 256 / slot_rows;
+        const int grid = (int)std::min<int64_t>((work + per_pass - 1) / per_pass, (int64_t)h->num_sms);
+        kern<<<grid, tc::kCholThreads, lay.total, st>>>(a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
     // C[ra x rb] = A[ra x k] B[rb x k]^T through the sweep kernel (float64 path only).  With a row
     // list the product is taken over rows A[list[i]] and row i is stored at C[list[i]].
     int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, T* c, const int32_t* list = nullptr) {
@@ -879,16 +923,24 @@ struct Engine : EngineBase {
                         const int64_t cnt = pl.bucket_off[b + 1] - pl.bucket_off[b];
                         if (cnt == 0) continue;
                         CU_TRY(cudaStreamWaitEvent(h->aux[b], h->ev_fork, 0));
-                        // float32 systems of 64+ rows build S on the tensor cores (tc_syrk.cuh)
-                        const bool tc = h->tc_solve_enabled && sizeof(T) == sizeof(float) && kBucketTile[b] == 8 &&
-                                        k % 4 == 0 && pl.bucket_dim[b] <= 256;
-                        const bool chol = tc && h->tc_chol_enabled;
+                        // float32: systems of 64+ rows build S on the tensor cores (tc_syrk.cuh), and with
+                        // HYPREC_TC_CHOL (default) every bucket up to 256 rows also factorises in tensor
+                        // memory -- the small ones several per CTA pass (tc_chol_multi.cuh)
+                        const bool f32 = sizeof(T) == sizeof(float);
+                        const bool tc = h->tc_solve_enabled && f32 && kBucketTile[b] == 8 && k % 4 == 0 && pl.bucket_dim[b] <= 256;
+                        const bool chol = tc && h->tc_chol_enabled && pl.bucket_dim[b] > 128;
+                        const bool multi = h->tc_chol_enabled && f32 && k % 4 == 0 && pl.bucket_dim[b] <= 128 && h->tc_multi_enabled;
                         if constexpr (sizeof(T) == sizeof(float)) {
-                            if (chol)
+                            if (multi) {
+                                const int slot_rows = pl.bucket_dim[b] <= 32 ? 32 : (pl.bucket_dim[b] <= 64 ? 64 : 128);
+                                HY_TRY(launch_chol_multi(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, slot_rows, qmat.as<float>(),
+                                                         prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b));
+                            } else if (chol) {
                                 HY_TRY(launch_chol_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
                                                         qmat.as<float>(), prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b));
+                            }
                         }
-                        if (!chol)
+                        if (!chol && !multi)
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
                                            tc ? hyprec::kSolveThreads : kBucketThreads[b], qmat.as<T>(),
                                            prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
@@ -1424,6 +1476,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->tc_solve_enabled = h->tc_enabled && !(ts_env && ts_env[0] == '0');
     const char* tch = getenv("HYPREC_TC_CHOL");
     h->tc_chol_enabled = h->tc_solve_enabled && !(tch && tch[0] == '0');
+    const char* tmu = getenv("HYPREC_TC_MULTI");
+    h->tc_multi_enabled = !(tmu && tmu[0] == '0');
     const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");
     if (ps) h->prof_slot = atoi(ps);
     const char* lr = getenv("HYPREC_LOWRANK");

@@ -111,6 +111,124 @@ __device__ __forceinline__ void chol_issue_update(uint32_t tmem_d, unsigned char
     }
 }
 
+
+// ---- building blocks shared by the single-system kernel below and tc_chol_multi.cuh ---------------
+
+// Cholesky of a 32 x 32 diagonal block held one row per lane (a[j] = entry (lane, j)); on return a
+// holds L11 (row `lane`), column j of L11 sits at l11t[j * 32 + lane] and the return value is
+// 1 / L[lane][lane].  Column j (still unscaled) goes through shared memory: every lane reads the
+// entries of the rows after j as broadcast vector loads; the next pivot only needs lane j+1's own
+// entries, so it goes out first with one shuffle on the critical path.  colbuf: 2 x 32 floats.
+__device__ __forceinline__ float chol_factor_diag(float (&a)[32], int lane, float* colbuf, float* l11t) {
+    float dmine = 0.f;
+    float piv = __shfl_sync(0xffffffffu, a[0], 0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float* col = colbuf + (j & 1) * 32;
+        col[lane] = a[j];
+        const float d = rsqrt_approx(piv);
+        const float w = a[j] * d * d;      // a[j] / pivot
+        if (lane == j) dmine = d;
+        if (j < 31) piv = __shfl_sync(0xffffffffu, fmaf(-w, a[j], a[j + 1]), j + 1);
+        __syncwarp();
+        const float4* col4 = reinterpret_cast<const float4*>(col);
+#pragma unroll
+        for (int q = (j + 1) / 4; q < 8; ++q) {
+            const float4 t = col4[q];
+            if (4 * q > j) a[4 * q] = fmaf(-w, t.x, a[4 * q]);
+            if (4 * q + 1 > j) a[4 * q + 1] = fmaf(-w, t.y, a[4 * q + 1]);
+            if (4 * q + 2 > j) a[4 * q + 2] = fmaf(-w, t.z, a[4 * q + 2]);
+            if (4 * q + 3 > j) a[4 * q + 3] = fmaf(-w, t.w, a[4 * q + 3]);
+        }
+        a[j] *= d;
+        l11t[j * 32 + lane] = a[j];        // column j of L11, for the rows below
+    }
+    return dmine;
+}
+
+// x = a L11^-T for one row below the diagonal block (its 32 entries of L), column by column.
+// dinv32: the 32 reciprocal diagonal entries of the block (16-byte aligned).
+__device__ __forceinline__ void chol_panel_solve(float (&a)[32], const float* l11t, const float* dinv32) {
+    const float4* l4 = reinterpret_cast<const float4*>(l11t);
+    const float4* dinv4 = reinterpret_cast<const float4*>(dinv32);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float4 dv = dinv4[j / 4];
+        a[j] *= (j % 4 == 0) ? dv.x : (j % 4 == 1) ? dv.y : (j % 4 == 2) ? dv.z : dv.w;
+#pragma unroll
+        for (int q = (j + 1) / 4; q < 8; ++q) {
+            const float4 t = l4[j * 8 + q];
+            if (4 * q > j) a[4 * q] = fmaf(-a[j], t.x, a[4 * q]);
+            if (4 * q + 1 > j) a[4 * q + 1] = fmaf(-a[j], t.y, a[4 * q + 1]);
+            if (4 * q + 2 > j) a[4 * q + 2] = fmaf(-a[j], t.z, a[4 * q + 2]);
+            if (4 * q + 3 > j) a[4 * q + 3] = fmaf(-a[j], t.w, a[4 * q + 3]);
+        }
+    }
+}
+
+// the 32 entries of one row as the hi / lo operand row `r` of a K = 32 panel stage
+__device__ __forceinline__ void chol_stage_row(const float (&a)[32], unsigned char* hi_base, size_t half_bytes, int r) {
+    const size_t row_off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 h, l;
+        split_tf32(a[4 * c], h.x, l.x);
+        split_tf32(a[4 * c + 1], h.y, l.y);
+        split_tf32(a[4 * c + 2], h.z, l.z);
+        split_tf32(a[4 * c + 3], h.w, l.w);
+        const size_t off = row_off + (size_t)((c ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(hi_base + off) = h;
+        *reinterpret_cast<float4*>(hi_base + half_bytes + off) = l;
+    }
+    fence_async_smem();
+}
+
+__device__ __forceinline__ void tmem_store_row(uint32_t taddr, const float (&a)[32]) {
+    uint32_t raw[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
+    tmem_store_32x32(taddr, raw);
+}
+
+// forward substitution of one panel's right-hand side by one warp: returns z[lane] of L11 z = b
+__device__ __forceinline__ float chol_forward_rhs(float bv, int lane, const float* l11t, const float* dinv32) {
+    float zmine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float zj = __shfl_sync(0xffffffffu, bv, j) * dinv32[j];
+        if (lane == j) zmine = zj;
+        if (lane > j) bv = fmaf(-l11t[j * 32 + lane], zj, bv);
+    }
+    return zmine;
+}
+
+// sum over the warp's 32 rows of v[j] for every j: afterwards lane l holds the total of entry l
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float keep = up ? v[i + s] : v[i];
+            const float send = up ? v[i] : v[i + s];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+// L11^T x = rhs by one warp (l11: row-major, row stride 33): returns x[lane]
+__device__ __forceinline__ float chol_backward_diag(float rhs, int lane, const float* l11, const float* dinv32) {
+    float xmine = 0.f;
+#pragma unroll
+    for (int j = 31; j >= 0; --j) {
+        const float xj = __shfl_sync(0xffffffffu, rhs, j) * dinv32[j];
+        if (lane == j) xmine = xj;
+        if (lane < j) rhs = fmaf(-l11[j * 33 + lane], xj, rhs);
+    }
+    return xmine;
+}
+
 #define HYPREC_TCPROF(slot)                                                          \
     if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {                          \
         const long long now_ = clock64();                                            \
@@ -271,37 +389,8 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
                 }
             }
             if (warp == pn) {
-                // the 32 x 32 diagonal block, one row per lane: L11 in place, 1 / diagonal kept
-                // column j (still unscaled) goes through shared memory: every lane reads the pivot and
-                // the entries of the rows after j as broadcast vector loads -- one store and <= 8 loads
-                // per column where lane-to-lane shuffles would need 31 - j.
-                float dmine = 0.f;
-                float* colbuf = part;                  // 2 x 32 floats, free until the back substitution
-                float piv = __shfl_sync(0xffffffffu, a[0], 0);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float* col = colbuf + (j & 1) * 32;
-                    col[lane] = a[j];
-                    const float d = rsqrt_approx(piv);
-                    const float w = a[j] * d * d;      // a[j] / pivot
-                    if (lane == j) dmine = d;
-                    // the next pivot only needs lane j+1's own entries: it goes out first (one shuffle on
-                    // the critical path), the rest of the update follows through shared memory
-                    if (j < 31) piv = __shfl_sync(0xffffffffu, fmaf(-w, a[j], a[j + 1]), j + 1);
-                    __syncwarp();
-                    const float4* col4 = reinterpret_cast<const float4*>(col);
-#pragma unroll
-                    for (int q = (j + 1) / 4; q < 8; ++q) {
-                        const float4 t = col4[q];
-                        if (4 * q > j) a[4 * q] = fmaf(-w, t.x, a[4 * q]);
-                        if (4 * q + 1 > j) a[4 * q + 1] = fmaf(-w, t.y, a[4 * q + 1]);
-                        if (4 * q + 2 > j) a[4 * q + 2] = fmaf(-w, t.z, a[4 * q + 2]);
-                        if (4 * q + 3 > j) a[4 * q + 3] = fmaf(-w, t.w, a[4 * q + 3]);
-                    }
-                    a[j] *= d;
-                    l11t[j * 32 + lane] = a[j];        // column j of L11, for the rows below
-                }
-                dinv[c0 + lane] = dmine;
+                // the 32 x 32 diagonal block, one row per lane (part: free until the back substitution)
+                dinv[c0 + lane] = chol_factor_diag(a, lane, part, l11t);
             }
             __syncthreads();
             HYPREC_TCPROF(2)
@@ -309,59 +398,19 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
             unsigned char* hi_base = st.stage;         // panel updates use stage 0
             if (warp == pn) {
                 // (off the other warps' critical path) L11 goes back to TMEM for the back substitution
-                uint32_t raw[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
-                tmem_store_32x32(my_taddr + (uint32_t)c0, raw);
+                tmem_store_row(my_taddr + (uint32_t)c0, a);
             }
             if (warp == 0) {
                 // forward substitution of this panel's right-hand side, z_p = L11^-1 b_p, by warp 0: it is
                 // the diagonal warp of panel 0 and has no rows left in the later panels, so the chain runs
                 // beside the other warps' panel solve
-                float bv = bs[c0 + lane];
-                float zmine = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float zj = __shfl_sync(0xffffffffu, bv, j) * dinv[c0 + j];
-                    if (lane == j) zmine = zj;
-                    if (lane > j) bv = fmaf(-l11t[j * 32 + lane], zj, bv);
-                }
-                zs[c0 + lane] = zmine;
+                zs[c0 + lane] = chol_forward_rhs(bs[c0 + lane], lane, l11t, dinv + c0);
             }
             if (warp > pn && r < dimp) {
                 // x = a L11^-T (this row's 32 entries of L), column by column
-                const float4* l4 = reinterpret_cast<const float4*>(l11t);
-                const float4* dinv4 = reinterpret_cast<const float4*>(dinv + c0);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float4 dv = dinv4[j / 4];
-                    a[j] *= (j % 4 == 0) ? dv.x : (j % 4 == 1) ? dv.y : (j % 4 == 2) ? dv.z : dv.w;
-#pragma unroll
-                    for (int q = (j + 1) / 4; q < 8; ++q) {
-                        const float4 t = l4[j * 8 + q];
-                        if (4 * q > j) a[4 * q] = fmaf(-a[j], t.x, a[4 * q]);
-                        if (4 * q + 1 > j) a[4 * q + 1] = fmaf(-a[j], t.y, a[4 * q + 1]);
-                        if (4 * q + 2 > j) a[4 * q + 2] = fmaf(-a[j], t.z, a[4 * q + 2]);
-                        if (4 * q + 3 > j) a[4 * q + 3] = fmaf(-a[j], t.w, a[4 * q + 3]);
-                    }
-                }
-                uint32_t raw[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(a[j]);
-                tmem_store_32x32(my_taddr + (uint32_t)c0, raw);
-                const size_t row_off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 h, l;
-                    split_tf32(a[4 * c], h.x, l.x);
-                    split_tf32(a[4 * c + 1], h.y, l.y);
-                    split_tf32(a[4 * c + 2], h.z, l.z);
-                    split_tf32(a[4 * c + 3], h.w, l.w);
-                    const size_t off = row_off + (size_t)((c ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4*>(hi_base + off) = h;
-                    *reinterpret_cast<float4*>(hi_base + half_bytes + off) = l;
-                }
-                fence_async_smem();
+                chol_panel_solve(a, l11t, dinv + c0);
+                tmem_store_row(my_taddr + (uint32_t)c0, a);
+                chol_stage_row(a, hi_base, half_bytes, r);
             }
             tc_fence_before();
             __syncthreads();
@@ -403,16 +452,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * xmine;
                 // transpose-reduce: afterwards lane l holds sum over the warp's rows of entry l
-#pragma unroll
-                for (int s = 16; s >= 1; s >>= 1) {
-                    const bool up = (lane & s) != 0;
-#pragma unroll
-                    for (int i = 0; i < s; ++i) {
-                        const float keep = up ? v[i + s] : v[i];
-                        const float send = up ? v[i] : v[i + s];
-                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-                    }
-                }
+                warp_transpose_reduce(v, lane);
                 part[warp * 32 + lane] = v[0];
             } else if (warp == pn) {
                 uint32_t raw[32];
@@ -425,12 +465,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
                 float rhs = zs[c0 + lane];
                 const int last_warp = dimp / 32 - 1;
                 for (int w = pn + 1; w <= last_warp; ++w) rhs -= part[w * 32 + lane];
-#pragma unroll
-                for (int j = 31; j >= 0; --j) {
-                    const float xj = __shfl_sync(0xffffffffu, rhs, j) * dinv[c0 + j];
-                    if (lane == j) xmine = xj;
-                    if (lane < j) rhs = fmaf(-l11[j * 33 + lane], xj, rhs);
-                }
+                xmine = chol_backward_diag(rhs, lane, l11, dinv + c0);
                 xs[c0 + lane] = xmine;
             }
             __syncthreads();

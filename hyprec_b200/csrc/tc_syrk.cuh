@@ -66,30 +66,41 @@ struct SyrkState {
 };
 
 
-// One k-block (32 contraction steps) of D += X X^T from a filled stage: D00 (and D1 for > 128 rows),
-// three TF32 products per K=8 step, then a commit that arrives on `bar` when they have retired.
-__device__ __forceinline__ void syrk_issue(const SyrkState& st, unsigned char* hi_base, size_t half_bytes, int npad, bool two,
-                                           bool accumulate, uint64_t* bar) {
+// One k-block (32 contraction steps) of D += X X^T from a filled stage, three TF32 products per K=8 step,
+// then a commit that arrives on `bar` when they have retired.  Row block 0 (stage rows 0..127) against
+// the n0 stage rows from 0 goes to TMEM column 0; row block 1 (rows 128..255) against the n1 rows from
+// b1_row0 goes to TMEM column 128 (n == 0: block not formed).
+__device__ __forceinline__ void syrk_issue_blocks(const SyrkState& st, unsigned char* hi_base, size_t half_bytes, int n0, int n1,
+                                                  int b1_row0, bool accumulate, uint64_t* bar) {
     tc_fence_after();
     const uint32_t sa = smem_u32(hi_base);
     const uint64_t a0_hi = umma_desc(sa), a0_lo = umma_desc(sa + (uint32_t)half_bytes);
     const uint64_t a1_hi = umma_desc(sa + 128 * 128), a1_lo = umma_desc(sa + (uint32_t)half_bytes + 128 * 128);
-    const uint32_t idesc0 = umma_idesc_tf32(128, two ? 128 : npad);
-    const uint32_t idesc1 = umma_idesc_tf32(128, npad);
+    const uint64_t b1_hi = umma_desc(sa + (uint32_t)b1_row0 * 128), b1_lo = umma_desc(sa + (uint32_t)half_bytes + (uint32_t)b1_row0 * 128);
+    const uint32_t idesc0 = umma_idesc_tf32(128, n0 > 0 ? n0 : 16);
+    const uint32_t idesc1 = umma_idesc_tf32(128, n1 > 0 ? n1 : 16);
 #pragma unroll
     for (int ks = 0; ks < kSyrkKB / 8; ++ks) {
         const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
         const uint32_t accum = (accumulate || ks != 0) ? 1u : 0u;
-        umma_tf32(st.tmem_base, a0_hi + adv, a0_hi + adv, idesc0, accum);
-        umma_tf32(st.tmem_base, a0_hi + adv, a0_lo + adv, idesc0, 1);
-        umma_tf32(st.tmem_base, a0_lo + adv, a0_hi + adv, idesc0, 1);
-        if (two) {
-            umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_hi + adv, idesc1, accum);
-            umma_tf32(st.tmem_base + 128, a1_hi + adv, a0_lo + adv, idesc1, 1);
-            umma_tf32(st.tmem_base + 128, a1_lo + adv, a0_hi + adv, idesc1, 1);
+        if (n0 > 0) {
+            umma_tf32(st.tmem_base, a0_hi + adv, a0_hi + adv, idesc0, accum);
+            umma_tf32(st.tmem_base, a0_hi + adv, a0_lo + adv, idesc0, 1);
+            umma_tf32(st.tmem_base, a0_lo + adv, a0_hi + adv, idesc0, 1);
+        }
+        if (n1 > 0) {
+            umma_tf32(st.tmem_base + 128, a1_hi + adv, b1_hi + adv, idesc1, accum);
+            umma_tf32(st.tmem_base + 128, a1_hi + adv, b1_lo + adv, idesc1, 1);
+            umma_tf32(st.tmem_base + 128, a1_lo + adv, b1_hi + adv, idesc1, 1);
         }
     }
     umma_commit(bar);
+}
+
+// single system: D00 (and D1 = rows 128.. x all columns for > 128 rows)
+__device__ __forceinline__ void syrk_issue(const SyrkState& st, unsigned char* hi_base, size_t half_bytes, int npad, bool two,
+                                           bool accumulate, uint64_t* bar) {
+    syrk_issue_blocks(st, hi_base, half_bytes, two ? 128 : npad, two ? npad : 0, 0, accumulate, bar);
 }
 
 // TMEM -> tiles: lane = system row, 32 columns per load; only tiles on or below the diagonal.
@@ -126,8 +137,10 @@ __device__ __forceinline__ void syrk_epilogue(const SyrkState& st, float* A, int
 // D (TMEM) = pre_scale^2 * Q_r Q_r^T for the `dim` rows idxs[0..dim) of `fixed` ([.][k], k % 4 == 0);
 // `npad` (a multiple of 16, >= dim) columns are formed.  All threads of the CTA call it (blockDim.x a
 // multiple of 128).
+// diag_blocks: several independent systems side by side (tc_chol_multi.cuh) -- rows without a positive
+// carry id -1 (zero rows) and the two row blocks only meet their own 128 columns.
 __device__ __forceinline__ void syrk_lowrank_accumulate(const float* __restrict__ fixed, const int* idxs, int dim, int k,
-                                                        SyrkState& st, float pre_scale, int npad) {
+                                                        SyrkState& st, float pre_scale, int npad, bool diag_blocks = false) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int chunk = tid & 7, r0 = tid >> 3, rpp = nthreads >> 3;
     const int nkb = (k + kSyrkKB - 1) / kSyrkKB;
@@ -144,7 +157,10 @@ __device__ __forceinline__ void syrk_lowrank_accumulate(const float* __restrict_
         for (int j = 0; j < 8; ++j) {
             const int r = r0 + j * rpp;
             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < dim && col < k) v[j] = __ldg(reinterpret_cast<const float4*>(fixed + (int64_t)idxs[r] * k + col));
+            if (r < dim && col < k) {
+                const int id = idxs[r];
+                if (id >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(fixed + (int64_t)id * k + col));
+            }
         }
     };
     auto stage_and_issue = [&](int kb, float4 (&v)[8]) {
@@ -171,7 +187,10 @@ __device__ __forceinline__ void syrk_lowrank_accumulate(const float* __restrict_
         }
         fence_async_smem();      // generic-proxy stores -> visible to the tensor core's async proxy
         __syncthreads();
-        if (tid == 0) syrk_issue(st, hi_base, half_bytes, npad, two, kb != 0, &st.bars[s]);
+        if (tid == 0) {
+            if (diag_blocks) syrk_issue_blocks(st, hi_base, half_bytes, 128, 128, 128, kb != 0, &st.bars[s]);
+            else syrk_issue(st, hi_base, half_bytes, npad, two, kb != 0, &st.bars[s]);
+        }
         pending[s] = true;
     };
     float4 va[8], vb[8];

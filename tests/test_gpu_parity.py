@@ -378,6 +378,39 @@ def test_tensor_core_direct_systems_fp32(native, monkeypatch, m, n, k, nnz, lowr
     assert not numpy.array_equal(got["tmem"][0], got["tiles"][0])
 
 
+@pytest.mark.parametrize("m,n,k,nnz", [(300, 900, 64, 9000), (200, 1500, 128, 12000), (150, 400, 256, 9000)])
+def test_tensor_memory_small_systems_fp32(native, monkeypatch, m, n, k, nnz):
+    """float32 low-rank systems of up to 128 rows run several per CTA pass in tensor memory
+    (tc_chol_multi.cuh, slots of 32 / 64 / 128 rows): same factors as the shared-memory tile kernel
+    (HYPREC_TC_MULTI=0) to float32 rounding on both sides, item prior and empty rows included."""
+    full, train, test, u0, v0, cands = synthetic(m, n, k, nnz, seed=k + 7, empty=True)
+    csc = oals.to_csr(train.T)
+    deg_u, deg_i = numpy.diff(train.indptr), numpy.diff(csc.indptr)
+    for lo, hi in ((1, 31), (32, 63), (64, 127)):
+        if lo >= k:
+            continue
+        assert ((deg_u >= lo) & (deg_u <= min(hi, k))).any() or ((deg_i >= lo) & (deg_i <= min(hi, k))).any(), (lo, hi)
+    theta = numpy.random.RandomState(5).rand(n, k)
+    u = oals.als_half_step(u0.copy(), v0, train, 0.01)
+    v = oals.als_half_step(v0.copy(), u, csc, 0.01, prior=theta)
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("HYPREC_TC_MULTI", flag)
+        h, _ = make_handle(native, train, native.F32)
+        h.set_factors(u0, v0)
+        h.set_item_prior(theta)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        got[flag] = h.get_factors()
+        h.close()
+    for side, ref in ((0, u), (1, v)):
+        print("k=%d side %d multi vs oracle %.2e, tiles vs oracle %.2e, multi vs tiles %.2e" %
+              (k, side, rel_frob(got["1"][side], ref), rel_frob(got["0"][side], ref), rel_frob(got["1"][side], got["0"][side])))
+        assert rel_frob(got["1"][side], ref) < F32_FROB
+        assert rel_frob(got["1"][side], got["0"][side]) < 5e-5
+    assert not numpy.array_equal(got["1"][0], got["0"][0])
+
+
 def test_cached_candidates_and_pinned_outputs(native):
     """hyprec_set_candidates + NULL lists == passing the lists on every call; outputs may live in
     page-locked memory from hyprec_host_alloc."""

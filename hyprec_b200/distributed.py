@@ -19,9 +19,13 @@ import numpy
 # partitioning (pure host logic)
 # --------------------------------------------------------------------------------------------------
 def row_costs(indptr, k):
-    """FLOP model of one row update: deg rank-1 updates of a k x k matrix + one Cholesky solve."""
+    """FLOP model of one row update as the kernels run it: rows with deg <= k solve a deg x deg system on
+    whitened factors (deg^2 k to build it, deg^3 / 3 to factor it, 4 deg k around it), rows with more
+    positives the k x k system (2 deg k^2 + k^3 / 3); a fixed term keeps near-empty rows from being free."""
     deg = numpy.diff(numpy.asarray(indptr, dtype=numpy.int64)).astype(numpy.float64)
-    return deg * (2.0 * k * k) + (k ** 3) / 3.0 + 2.0 * k * k
+    low = deg * deg * k + deg ** 3 / 3.0 + 4.0 * deg * k
+    direct = deg * (2.0 * k * k) + (k ** 3) / 3.0
+    return numpy.where(deg <= k, low, direct) + 8.0 * k * k
 
 
 def partition_rows(indptr, world, k):

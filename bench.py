@@ -109,12 +109,13 @@ def build_scaled_workload(scale):
                 setup_s=time.time() - t0)
 
 
-def algorithmic_work(wl):
-    """FLOPs / bytes per epoch and per launch of the solve kernel (SURVEY.md section 8d formulas)."""
+def algorithmic_work(wl, elem=8):
+    """FLOPs / bytes per epoch and per launch of the solve kernel (SURVEY.md section 8d formulas).
+    elem: bytes per factor element (the largest low-rank system depends on what fits shared memory)."""
     m, n, k = wl["m"], wl["n"], wl["k"]
     nnz = wl["train_csr"].nnz
     solve_flops = 2 * (2.0 * nnz * k * k) + (m + n) * (k ** 3 / 3.0 + 2.0 * k * k) + 2 * (2.0 * nnz * k)
-    cap = min(k, 191)
+    cap = min(k, 191 if elem == 8 else 319)
     lowrank = 0.0
     for mat, rows_fixed in ((wl["train_csr"], n), (wl["train_csr"].T.tocsr(), m)):
         deg = numpy.diff(mat.indptr).astype(numpy.float64)
@@ -377,8 +378,8 @@ def our_arm(args, wl):
         recall200 = float(hm.recall_at_x(200, out["topk_hit"], test_likes))
 
     # ---- roofline of the dominant kernels
-    work = algorithmic_work(wl)
     elem = 8 if args.precision == "fp64" else 4
+    work = algorithmic_work(wl, elem)
     solve_ms = per_step["solve"]
     lowrank = os.environ.get("HYPREC_LOWRANK", "1") != "0"
     peak = h.probe_fma_tflops(precision)
@@ -396,12 +397,24 @@ def our_arm(args, wl):
     # pre-filtered top-k: one 32-byte sector of s~ per candidate + ~200 exact re-scores per user
     topk_bytes = (float(wl["cand_ids"].shape[0]) if has_eval else 0.0) * 36.0 + m * 200 * (k * elem + 20)
     topk_gbs = topk_bytes / (max(per_step["topk"], 1e-9) * 1e-3) / 1e9
-    roofline = dict(kernel="als_solve_rows_kernel (row systems of one epoch; %s)" %
-                           ("deg x deg low-rank systems in 4 concurrent degree buckets + direct k x k for heavy rows"
-                            if lowrank else "direct k x k systems, 2 launches"),
-                    bound="%s_fma" % args.precision, achieved=achieved, peak=peak, unit="TFLOP/s",
-                    frac=achieved / peak if peak else None,
-                    peak_source="hyprec_probe_fma_tflops on this GPU (FMA chains, best of 4)", traffic=None,
+    tensor_rows = args.precision == "fp32" and lowrank and os.environ.get("HYPREC_TC_SOLVE", "1") != "0" and \
+        os.environ.get("HYPREC_TC", "1") != "0" and k % 4 == 0
+    if tensor_rows:
+        # float32: the row systems are built and factorised in tensor memory (tc_chol*.cuh): tcgen05 does
+        # the rank-k accumulation and the trailing updates (3 TF32 products per algorithmic one)
+        kernel_desc = ("tc_chol_rows_kernel + tc_chol_multi_kernel (row systems of one epoch: normal matrix accumulated "
+                       "by tcgen05 3xTF32 into tensor memory, 32-column panel Cholesky with tcgen05 trailing updates; "
+                       "rows with more positives than n_factors as k x k systems, the rest as deg x deg low-rank systems, "
+                       "small ones several per CTA)")
+        bound, peak_used, peak_src = "tensor", tf32_peak, "MEASURED_PEAKS.json bf16_tflops / 2 (dense TF32 rate)"
+    else:
+        kernel_desc = "als_solve_rows_kernel (row systems of one epoch; %s)" % (
+            "deg x deg low-rank systems in concurrent degree buckets + direct k x k for heavy rows"
+            if lowrank else "direct k x k systems, 2 launches")
+        bound, peak_used, peak_src = "%s_fma" % args.precision, peak, "hyprec_probe_fma_tflops on this GPU (FMA chains, best of 4)"
+    roofline = dict(kernel=kernel_desc, bound=bound, achieved=achieved, peak=peak_used, unit="TFLOP/s",
+                    frac=achieved / peak_used if peak_used else None, peak_source=peak_src, traffic=None,
+                    simt_fma_peak=peak, simt_fma_frac=achieved / peak if peak else None,
                     flops_per_epoch=solve_flops, flops_model="low-rank (sum d^2 k + d^3/3 + 4 d k)" if lowrank else
                     "SURVEY 8d direct formula", direct_formula_flops=work["solve_flops_per_epoch"],
                     hbm=dict(achieved=solve_gbs, peak=hbm_peak, unit="GB/s", frac=solve_gbs / hbm_peak,

@@ -108,7 +108,8 @@ struct SolveArgs {
     int64_t n_list;
     int max_dim;              // system dimension the shared-memory layout is sized for
     int lowrank;              // 0: direct k x k systems; 1: deg x deg systems on whitened factors
-    T* ymat;                  // low-rank output [n_rows][k]
+    T* ymat;                  // low-rank output, COMPACT: work item w of the launch writes row ymat_row0 + w
+    int64_t ymat_row0;
     T* export_tiles;          // direct mode: factored tiles of the processed row (single-row launch)
     int tmem_cols;            // tensor-core launches: TMEM columns to allocate (tc::syrk_tmem_cols)
     long long* prof;          // optional: per-phase clock64() totals of block 0 (tools/solve_phases.py)
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
 #endif
         const int64_t lo = p.indptr[row];
         const int deg = (int)(p.indptr[row + 1] - lo);
-        T* out = lowrank ? p.ymat + row * k : p.latent + row * k;
+        T* out = lowrank ? p.ymat + (p.ymat_row0 + s_row) * k : p.latent + row * k;
         const T* prior_row = p.prior ? p.prior + row * k : nullptr;
         if (deg == 0 && (lowrank || (p.prior == nullptr && p.export_tiles == nullptr))) {
             // direct: b == 0 => the solve returns exactly 0; low-rank: y = p

@@ -209,7 +209,7 @@ struct Engine : EngineBase {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
-                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &plan[0].lists, &plan[1].lists,
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &w_hi, &w_lo, &l_hi, &l_lo, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
@@ -428,7 +428,8 @@ struct Engine : EngineBase {
     // Launch the row kernel over a contiguous range or a row list, in direct or low-rank mode.
     int launch_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
                     bool lowrank, int max_dim, int threads, const T* fixed_ptr, const T* prior_ptr, T* export_ptr,
-                    const int64_t* indptr_override, int64_t work, cudaStream_t st, int slot, int ts = 8, bool tc = false) {
+                    const int64_t* indptr_override, int64_t work, cudaStream_t st, int slot, int ts = 8, bool tc = false,
+                    int64_t ymat_row0 = 0) {
         // export_ptr != null: the single-row launch that only factors B -- its (zero) solution must
         // not land in the factor matrix
         T* latent_ptr = user ? U.as<T>() : V.as<T>();
@@ -492,6 +493,7 @@ struct Engine : EngineBase {
         a.max_dim = max_dim;
         a.lowrank = lowrank ? 1 : 0;
         a.ymat = ymat.as<T>();
+        a.ymat_row0 = ymat_row0;
         a.export_tiles = export_ptr;
         a.tmem_cols = tc ? hyprec::tc::syrk_tmem_cols(max_dim) : 0;
         a.prof = nullptr;
@@ -509,7 +511,7 @@ struct Engine : EngineBase {
     // float32 systems of 33..256 unknowns with the normal matrix resident in tensor memory (tc_chol.cuh).
     int launch_chol_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
                          bool lowrank, int max_dim, const float* fixed_ptr, const float* prior_ptr, int64_t work,
-                         cudaStream_t st, int slot) {
+                         cudaStream_t st, int slot, int64_t out_row0 = 0) {
         namespace tc = hyprec::tc;
         const tc::CholLayout lay = tc::chol_layout(max_dim);
         if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "tensor-memory row launch does not fit shared memory");
@@ -523,6 +525,7 @@ struct Engine : EngineBase {
         a.gram = gram[user ? 1 : 0].template as<float>();
         a.prior = prior_ptr;
         a.out = lowrank ? ymat.as<float>() : (user ? U.as<float>() : V.as<float>());
+        a.out_row0 = out_row0;
         a.work_counter = counter.as<int>() + slot;
         a.status = counter.as<int>() + kStatusSlot;
         a.lambda = (float)lambda;
@@ -549,7 +552,7 @@ struct Engine : EngineBase {
 
     // several float32 low-rank systems of <= slot (32 / 64 / 128) unknowns per CTA pass (tc_chol_multi.cuh)
     int launch_chol_multi(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list, int slot_rows,
-                          const float* fixed_ptr, const float* prior_ptr, int64_t work, cudaStream_t st, int slot) {
+                          const float* fixed_ptr, const float* prior_ptr, int64_t work, cudaStream_t st, int slot, int64_t out_row0) {
         namespace tc = hyprec::tc;
         const tc::CholMultiLayout lay = tc::chol_multi_layout();
         if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "tensor-memory row launch does not fit shared memory");
@@ -564,6 +567,7 @@ struct Engine : EngineBase {
         a.gram = nullptr;
         a.prior = prior_ptr;
         a.out = ymat.as<float>();
+        a.out_row0 = out_row0;
         a.work_counter = counter.as<int>() + slot;
         a.status = counter.as<int>() + kStatusSlot;
         a.lambda = (float)lambda;
@@ -609,6 +613,59 @@ struct Engine : EngineBase {
         h->launches += 1;
         CU_TRY(cudaGetLastError());
         return HYPREC_OK;
+    }
+
+    // float32 mode: the same product on the tensor cores (tc_score_kernel, 3xTF32) -- the whitening
+    // Q = Y L^-T and the back-transform x = L^-T y are real dense contractions.
+    DevBuf w_hi, w_lo, l_hi, l_lo;
+    int gemm_nt_tc(const float* a, int64_t ra, const float* b, float* c, const int32_t* row_map) {
+        namespace tcn = hyprec::tc;
+        if (ra == 0) return HYPREC_OK;
+        HY_TRY(w_hi.reserve(sizeof(float) * (size_t)ra * k));
+        HY_TRY(w_lo.reserve(sizeof(float) * (size_t)ra * k));
+        HY_TRY(l_hi.reserve(sizeof(float) * (size_t)k * k));
+        HY_TRY(l_lo.reserve(sizeof(float) * (size_t)k * k));
+        const int64_t ca = ra * k, cb = (int64_t)k * k;
+        tcn::split_tf32_kernel<float><<<(unsigned)((ca + 255) / 256), 256, 0, h->stream>>>(a, ca, w_hi.as<float>(), w_lo.as<float>());
+        tcn::split_tf32_kernel<float><<<(unsigned)((cb + 255) / 256), 256, 0, h->stream>>>(b, cb, l_hi.as<float>(), l_lo.as<float>());
+        h->launches += 2;
+        CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+        HY_TRY(make_map(&ma_hi, w_hi.as<float>(), ra));
+        HY_TRY(make_map(&ma_lo, w_lo.as<float>(), ra));
+        HY_TRY(make_map(&mb_hi, l_hi.as<float>(), k));
+        HY_TRY(make_map(&mb_lo, l_lo.as<float>(), k));
+        tcn::ScoreArgs s;
+        s.m = ra;
+        s.n = k;
+        s.k = k;
+        s.thresholds = nullptr;
+        s.unorm = nullptr;
+        s.vnorm = nullptr;
+        s.margin_coef = 0.f;
+        s.counts = nullptr;
+        s.border_count = nullptr;
+        s.border_cells = nullptr;
+        s.border_capacity = 0;
+        s.dense = c;
+        s.dense_ld = k;
+        s.row_map = row_map;
+        auto kern = tcn::tc_score_kernel;
+        HY_TRY(ensure_dynamic_smem((const void*)kern, (int)tcn::kSmemBytes));
+        const int64_t n_tiles = ((ra + tcn::kBM - 1) / tcn::kBM) * ((k + tcn::kBN - 1) / tcn::kBN);
+        const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
+        kern<<<grid, tcn::kThreads, tcn::kSmemBytes, h->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, s);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+    // whitening products: tensor cores in float32 mode, the float64 sweep kernel otherwise
+    int whiten_gemm(const T* a, int64_t ra, const T* b, T* c, const int32_t* list) {
+        if constexpr (sizeof(T) == sizeof(float)) {
+            if (h->tc_solve_enabled && tc_usable() && h->encode_tiled != nullptr && ra >= 128)
+                return gemm_nt_tc(reinterpret_cast<const float*>(a), ra, reinterpret_cast<const float*>(b),
+                                  reinterpret_cast<float*>(c), list);
+        }
+        return gemm_nt(a, ra, b, k, c, list);
     }
 
     // Rows of [lo, hi) grouped for the low-rank path: bucket b holds rows with
@@ -825,6 +882,7 @@ struct Engine : EngineBase {
         a.max_dim = dim;
         a.lowrank = 0;
         a.ymat = nullptr;
+        a.ymat_row0 = 0;
         a.export_tiles = export_ptr;
         a.tmem_cols = 0;
         a.prof = nullptr;
@@ -908,10 +966,10 @@ struct Engine : EngineBase {
                     HY_TRY(compute_linv(user, lambda, fixed_ptr, n_fixed));
                     // 3. whitened factors Q = Y L^-T (and theta L^-T for the item prior)
                     HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
-                    HY_TRY(gemm_nt(fixed_ptr, n_fixed, linv_T(), k, qmat.as<T>()));
+                    HY_TRY(whiten_gemm(fixed_ptr, n_fixed, linv_T(), qmat.as<T>(), nullptr));
                     if (prior_ptr) {
                         HY_TRY(pq.reserve(sizeof(T) * (size_t)total * k));
-                        HY_TRY(gemm_nt(prior_ptr, total, linv_T(), k, pq.as<T>()));
+                        HY_TRY(whiten_gemm(prior_ptr, total, linv_T(), pq.as<T>(), nullptr));
                     }
                 }
                 {
@@ -934,17 +992,18 @@ struct Engine : EngineBase {
                             if (multi) {
                                 const int slot_rows = pl.bucket_dim[b] <= 32 ? 32 : (pl.bucket_dim[b] <= 64 ? 64 : 128);
                                 HY_TRY(launch_chol_multi(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, slot_rows, qmat.as<float>(),
-                                                         prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b));
+                                                         prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b, pl.bucket_off[b]));
                             } else if (chol) {
                                 HY_TRY(launch_chol_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
-                                                        qmat.as<float>(), prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b));
+                                                        qmat.as<float>(), prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b,
+                                                        pl.bucket_off[b]));
                             }
                         }
                         if (!chol && !multi)
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
                                            tc ? hyprec::kSolveThreads : kBucketThreads[b], qmat.as<T>(),
                                            prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
-                                           kBucketTile[b], tc));
+                                           kBucketTile[b], tc, pl.bucket_off[b]));
                         CU_TRY(cudaEventRecord(h->ev_join[b], h->aux[b]));
                         CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
                     }
@@ -953,7 +1012,7 @@ struct Engine : EngineBase {
                     // 5. x = L^-T y for the low-rank rows: one GEMM straight into the factor matrix
                     Timer t(h, HYPREC_T_PREP);
                     T* latent = user ? U.as<T>() : V.as<T>();
-                    HY_TRY(gemm_nt(ymat.as<T>(), n_light, linv_t_T(), k, latent, lists));
+                    HY_TRY(whiten_gemm(ymat.as<T>(), n_light, linv_t_T(), latent, lists));
                 }
             }
             if (n_heavy > 0) {
@@ -1121,6 +1180,7 @@ struct Engine : EngineBase {
         a.border_capacity = kBorderCapacity;
         a.dense = want_dense ? dense_f32.as<float>() : nullptr;
         a.dense_ld = dense_ld;
+        a.row_map = nullptr;
         auto kern = tcn::tc_score_kernel;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcn::kSmemBytes));
         const int64_t n_tiles = ((nu + tcn::kBM - 1) / tcn::kBM) * tiles_n;

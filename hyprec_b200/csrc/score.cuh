@@ -27,8 +27,8 @@ struct SweepArgs {
     int64_t user_lo, user_hi, n_items;
     double* dense_out;               // [user_hi-user_lo][n_items]          (kSweepStore)
     float* dense_out_f32;            // (kSweepStore) when non-null the tile is stored here as float32 instead
-    const int32_t* row_list;         // optional (kSweepStore): the "user" rows are row_list[user_lo..user_hi)
-                                     // and row r of the product is stored at dense_out[row_list[r] * n_items]
+    const int32_t* row_list;         // optional (kSweepStore): row r of the product is stored at
+                                     // dense_out[row_list[r] * n_items] instead of row r - user_lo
     const double* thresholds;        // [n_users]                           (kSweepCount)
     unsigned long long* counts;      // [user_hi-user_lo], zeroed by caller (kSweepCount)
 };
@@ -57,10 +57,7 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
             const int col = c0 + cc;
             const int64_t ui = i0 + rr, vj = j0 + rr;
             T uval = T(0);
-            if (ui < p.user_hi && col < k) {
-                const int64_t src = (MODE == kSweepStore && p.row_list) ? (int64_t)p.row_list[ui] : ui;
-                uval = p.user_vecs[src * k + col];
-            }
+            if (ui < p.user_hi && col < k) uval = p.user_vecs[ui * k + col];
             us[cc][rr] = uval;
             vs[cc][rr] = (vj < p.n_items && col < k) ? p.item_vecs[vj * k + col] : T(0);
         }

@@ -37,7 +37,8 @@ struct CholRowsArgs {
     const float* fixed;       // low-rank: whitened factors Q [n_fixed][k]; direct: factors Y
     const float* gram;        // direct: dense k x k Gram of the fixed side (0.1 G + lambda I is formed on the fly)
     const float* prior;       // low-rank: rows of theta L^-T; direct: theta; or null
-    float* out;               // low-rank: ymat [n_rows][k]; direct: latent [n_rows][k]
+    float* out;               // low-rank: ymat, compact (work item w writes row out_row0 + w); direct: latent [n_rows][k]
+    int64_t out_row0;
     int* work_counter;        // zeroed before launch
     int* status;              // set to 1 when a solution is not finite
     float lambda;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
         if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) prof_t = clock64();
         const int64_t lo = p.indptr[row];
         const int deg = (int)(p.indptr[row + 1] - lo);
-        float* out = p.out + row * k;
+        float* out = p.out + (lowrank ? p.out_row0 + s_row : row) * k;
         const float* prior_row = p.prior ? p.prior + row * k : nullptr;
         if (deg == 0 && (lowrank || prior_row == nullptr)) {
             // direct: b == 0 => the solve returns exactly 0; low-rank: y = p

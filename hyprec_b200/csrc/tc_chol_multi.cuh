@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_multi_kernel(CholRows
             }
             for (; i < d; ++i) acc = fmaf(__ldg(p.fixed + (int64_t)ids[i] * k + a), t[i], acc);
             if (!(acc - acc == 0.f)) *p.status = 1;
-            p.out[row * k + a] = acc;
+            p.out[(p.out_row0 + s_first + s) * k + a] = acc;
         }
         HYPREC_TCPROF(10)
         tc_fence_before();

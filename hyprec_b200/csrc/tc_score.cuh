@@ -54,6 +54,7 @@ struct ScoreArgs {
     unsigned int border_capacity;
     float* dense;                 // [m][dense_ld] float32 scores, or null
     int64_t dense_ld;
+    const int32_t* row_map;       // optional: product row r is stored at dense row row_map[r]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -263,7 +264,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                 tmem_load_32x32(taddr, v);
                 if (row_ok) {
                     if (p.dense) {
-                        float* dst = p.dense + row * p.dense_ld + col0 + c;
+                        const int64_t drow = p.row_map ? (int64_t)p.row_map[row] : row;
+                        float* dst = p.dense + drow * p.dense_ld + col0 + c;
                         if (col0 + c + 32 <= p.dense_ld) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)

@@ -47,7 +47,7 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
     a.base = base.data(); a.prior = prior; a.a_scratch = a_in_smem ? nullptr : scratch.data();
     a.work_counter = counter; a.status = counter + 1; a.lambda = lambda; a.k = k;
     a.row_lo = row_lo; a.row_hi = row_hi; a.chunk_rows = chunk_rows;
-    a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = nullptr; a.prof = nullptr;
+    a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.ymat_row0 = 0; a.export_tiles = nullptr; a.prof = nullptr;
     if (a_in_smem) emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
     else emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8, false, true>(a); });
     return counter[1];
@@ -85,7 +85,7 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
     a.indptr = dummy_ptr; a.indices = indices; a.values = values; a.fixed = fixed; a.latent = dummy_out.data();
     a.base = base.data(); a.prior = nullptr; a.a_scratch = nullptr; a.work_counter = counter; a.status = counter + 1;
     a.lambda = lambda; a.k = k; a.row_lo = 0; a.row_hi = 1; a.chunk_rows = 8; a.row_list = nullptr; a.n_list = 0;
-    a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.export_tiles = tiles.data(); a.prof = nullptr;
+    a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.ymat_row0 = 0; a.export_tiles = tiles.data(); a.prof = nullptr;
     SolveLayout lay = solve_layout(8, k, 8, true, sizeof(T));
     emu::launch(dim3(1), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
     // 2. L^-1 and its transpose
@@ -115,14 +115,14 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
         SolveArgs<T> b = a;
         b.indptr = indptr; b.fixed = q.data(); b.prior = prior ? pq.data() : nullptr; b.latent = nullptr;
         b.row_list = light.data(); b.n_list = (int64_t)light.size(); b.max_dim = max_deg; b.lowrank = 1;
-        b.ymat = ymat.data(); b.export_tiles = nullptr; b.chunk_rows = 16;
+        b.ymat = ymat.data(); b.ymat_row0 = 0; b.export_tiles = nullptr; b.chunk_rows = 16;   // compact: list position i -> row i
         SolveLayout l2 = solve_layout(ts, max_deg, 16, true, sizeof(T));
         if (ts == 4) emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 4>(b); });
         else emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 8>(b); });
         // 5. X = Ymat L^-1  (X[i][c] = sum_a Ymat[i][a] LinvT[c][a]) -- light rows only are meaningful
         std::vector<T> x((size_t)n_rows * k);
         gemm_nt(ymat.data(), n_rows, linv_t.data(), k, k, x.data());
-        for (int32_t r : light) memcpy(latent + (size_t)r * k, x.data() + (size_t)r * k, sizeof(T) * k);
+        for (size_t i = 0; i < light.size(); ++i) memcpy(latent + (size_t)light[i] * k, x.data() + i * k, sizeof(T) * k);
     }
     if (!heavy.empty()) {
         counter[0] = 0;

@@ -1044,7 +1044,7 @@ struct Engine : EngineBase {
         CU_TRY(cudaMemsetAsync(scalars.ptr, 0, sizeof(double) * 4, h->stream));
         {
             Timer t(h, HYPREC_T_RMSE);
-            hyprec::frob_inner_kernel<T><<<1, 256, 0, h->stream>>>(gram[0].as<T>(), gram[1].as<T>(), k * k,
+            hyprec::frob_inner_kernel<T><<<1, 1024, 0, h->stream>>>(gram[0].as<T>(), gram[1].as<T>(), k * k,
                                                                      scalars.as<double>());
             h->launches += 1;
             if (hi > lo) {

@@ -139,10 +139,19 @@ __global__ void build_base_tiles_kernel(const T* __restrict__ g, int k, T lambda
 template <typename T>
 __global__ void frob_inner_kernel(const T* __restrict__ a, const T* __restrict__ b, int count,
                                   double* __restrict__ out) {
-    __shared__ double red[256];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) s += (double)a[i] * (double)b[i];
-    red[threadIdx.x] = s;
+    __shared__ double red[1024];
+    // four independent partial sums per thread: the loads of four strides are in flight together
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int step = blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 3 * step < count; i += 4 * step) {
+        s0 += (double)a[i] * (double)b[i];
+        s1 += (double)a[i + step] * (double)b[i + step];
+        s2 += (double)a[i + 2 * step] * (double)b[i + 2 * step];
+        s3 += (double)a[i + 3 * step] * (double)b[i + 3 * step];
+    }
+    for (; i < count; i += step) s0 += (double)a[i] * (double)b[i];
+    red[threadIdx.x] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     for (int w = blockDim.x / 2; w > 0; w >>= 1) {
         if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];

@@ -132,20 +132,63 @@ __global__ void row_threshold_kernel(const T* __restrict__ user_vecs, const doub
 }
 
 // Per CSR row: s1 = sum_nz r * (u . v_j), s2 = sum_nz r^2 (float64), one warp per row.
+// s1 = sum_l u_l * (sum_e r_e v_{e,l}): every lane keeps its slice of u in registers and accumulates
+// its slice of the r-weighted sum of the row's item vectors (in the factor dtype: float32 mode stays on
+// the float32 pipe) -- no shuffles inside the loop, four gathered rows in flight -- and the warp
+// reduces once per row in float64 (fixed order: deterministic).
 template <typename T>
 __global__ void sddmm_row_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                  const T* __restrict__ values, const T* __restrict__ user_vecs,
                                  const T* __restrict__ item_vecs, int k, int64_t n_rows,
                                  double* __restrict__ s1, double* __restrict__ s2) {
+    constexpr int kSlice = 16;   // register slice per lane: k <= 512
     const int lane = threadIdx.x % 32;
     const int64_t u = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     if (u >= n_rows) return;
     double a1 = 0.0, a2 = 0.0;
-    for (int64_t e = indptr[u]; e < indptr[u + 1]; ++e) {
-        const double r = (double)values[e];
-        const double d = warp_dot(user_vecs + u * k, item_vecs + (int64_t)indices[e] * k, k, lane);
-        a1 += r * d;
-        a2 += r * r;
+    const int64_t e0 = indptr[u], e1 = indptr[u + 1];
+    if (k <= 32 * kSlice) {
+        T acc[kSlice];
+#pragma unroll
+        for (int i = 0; i < kSlice; ++i) acc[i] = T(0);
+        int64_t e = e0;
+        for (; e + 4 <= e1; e += 4) {
+            const T* v0 = item_vecs + (int64_t)indices[e] * k;
+            const T* v1 = item_vecs + (int64_t)indices[e + 1] * k;
+            const T* v2 = item_vecs + (int64_t)indices[e + 2] * k;
+            const T* v3 = item_vecs + (int64_t)indices[e + 3] * k;
+            const T r0 = values[e], r1 = values[e + 1], r2 = values[e + 2], r3 = values[e + 3];
+            a2 += (double)r0 * (double)r0 + (double)r1 * (double)r1 + (double)r2 * (double)r2 + (double)r3 * (double)r3;
+#pragma unroll
+            for (int i = 0; i < kSlice; ++i) {
+                const int l = lane + 32 * i;
+                if (l < k) acc[i] += (r0 * v0[l] + r1 * v1[l]) + (r2 * v2[l] + r3 * v3[l]);
+            }
+        }
+        for (; e < e1; ++e) {
+            const T* v0 = item_vecs + (int64_t)indices[e] * k;
+            const T r0 = values[e];
+            a2 += (double)r0 * (double)r0;
+#pragma unroll
+            for (int i = 0; i < kSlice; ++i) {
+                const int l = lane + 32 * i;
+                if (l < k) acc[i] += r0 * v0[l];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSlice; ++i) {
+            const int l = lane + 32 * i;
+            if (l < k) a1 += (double)acc[i] * (double)user_vecs[u * k + l];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+    } else {
+        for (int64_t e = e0; e < e1; ++e) {
+            const double r = (double)values[e];
+            const double d = warp_dot(user_vecs + u * k, item_vecs + (int64_t)indices[e] * k, k, lane);
+            a1 += r * d;
+            a2 += r * r;
+        }
     }
     if (lane == 0) {
         s1[u] = a1;

@@ -108,6 +108,7 @@ struct hyprec_ctx {
     int64_t launches = 0;
     bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
     bool tc_enabled = true;        // HYPREC_TC=0 keeps the score sweep on the SIMT kernel
+    bool rmse_fused_enabled = true; // HYPREC_RMSE_FUSED=0: the RMSE cross term always comes from a pass over the positives
     bool tc_multi_enabled = true;  // HYPREC_TC_MULTI=0: systems of <= 128 rows stay on the shared-memory tile kernel
     bool tc_chol_enabled = true;   // HYPREC_TC_CHOL=0: float32 systems factorise in shared-memory tiles (als_solve.cuh)
     bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
@@ -183,6 +184,12 @@ struct Engine : EngineBase {
     DevBuf U, V, prior;
     bool has_prior = false;
     bool gram_ok[2] = {false, false};   // [0] = U^T U, [1] = V^T V match the current factors
+    // RMSE cross term sum_nz r (u . v) as a by-product of the item half-step (tensor-memory kernels, no
+    // prior): cross[i] per item row; valid until anything touches the factors again.
+    DevBuf cross;
+    bool cross_active = false;          // the launches of the running half-step write cross[]
+    bool cross_valid = false;
+    int64_t cross_lo = 0, cross_hi = 0;
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
     DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
     DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out, prof_buf, bdense, lfac, blk_tmp, blk_base;
@@ -209,7 +216,7 @@ struct Engine : EngineBase {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
-                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &w_hi, &w_lo, &l_hi, &l_lo, &plan[0].lists, &plan[1].lists,
+                         &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &w_hi, &w_lo, &l_hi, &l_lo, &cross, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
@@ -253,6 +260,7 @@ struct Engine : EngineBase {
     int set_train(int64_t m_, int64_t n_, const int64_t* indptr, const int32_t* indices, const double* values) override {
         if (m_ <= 0 || n_ <= 0) return fail(HYPREC_E_INVALID, "set_train_csr: empty matrix");
         if (m_ != m || n_ != n) { k = 0; gram_ok[0] = gram_ok[1] = false; }
+        cross_valid = false;
         plan[0].lo = plan[1].lo = -1;
         cand_lo = cand_hi = -1;
         use_cached_cands = false;
@@ -335,6 +343,7 @@ struct Engine : EngineBase {
         HY_TRY(upload_matrix(U, u, m));
         HY_TRY(upload_matrix(V, v, n));
         gram_ok[0] = gram_ok[1] = false;
+        cross_valid = false;
         return HYPREC_OK;
     }
 
@@ -359,6 +368,7 @@ struct Engine : EngineBase {
         if (v) *v = V.ptr;
         if (elem) *elem = (int)sizeof(T);
         gram_ok[0] = gram_ok[1] = false;   // the caller may write through these pointers
+        cross_valid = false;
         return HYPREC_OK;
     }
 
@@ -537,6 +547,7 @@ struct Engine : EngineBase {
         a.max_dim = max_dim;
         a.lowrank = lowrank ? 1 : 0;
         a.tmem_cols = tc::syrk_tmem_cols(max_dim);
+        a.cross_out = cross_active ? cross.as<double>() : nullptr;
         a.prof = nullptr;
         if (h->prof_enabled && slot == h->prof_slot) {
             if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
@@ -579,6 +590,7 @@ struct Engine : EngineBase {
         a.max_dim = slot_rows;
         a.lowrank = 1;
         a.tmem_cols = 256;
+        a.cross_out = cross_active ? cross.as<double>() : nullptr;
         a.prof = nullptr;
         if (h->prof_enabled && slot == h->prof_slot) {
             if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
@@ -925,7 +937,18 @@ struct Engine : EngineBase {
         // float32 k x k systems (64 <= k <= 256) accumulate sum y y^T on the tensor cores (tc_syrk.cuh)
         const bool tc_direct = h->tc_solve_enabled && sizeof(T) == sizeof(float) && k >= 64 && k <= 256;
         const bool chol_direct = tc_direct && h->tc_chol_enabled && k % 4 == 0;
+        // the item half-step's tensor-memory kernels hand out the RMSE cross term per row (see `cross`)
+        cross_valid = false;
+        cross_active = false;
+        const bool cross_wanted = !user && sizeof(T) == sizeof(float) && !has_prior && h->rmse_fused_enabled;
+        auto begin_cross = [&]() -> int {
+            HY_TRY(cross.reserve(sizeof(double) * (size_t)n));
+            CU_TRY(cudaMemsetAsync(cross.as<double>() + lo, 0, sizeof(double) * (size_t)(hi - lo), h->stream));
+            cross_active = true;
+            return HYPREC_OK;
+        };
         if (!lowrank) {
+            if (cross_wanted && chol_direct) HY_TRY(begin_cross());
             Timer t(h, HYPREC_T_SOLVE);
             if constexpr (sizeof(T) == sizeof(float)) {
                 if (chol_direct)
@@ -943,6 +966,13 @@ struct Engine : EngineBase {
             const int64_t n_light = pl.bucket_off[nbk];
             const int64_t n_heavy = pl.bucket_off[nbk + 1] - pl.bucket_off[nbk];
             HY_TRY(ymat.reserve(sizeof(T) * (size_t)total * k));
+            if (cross_wanted && h->tc_solve_enabled && h->tc_chol_enabled && h->tc_multi_enabled && k % 4 == 0 &&
+                (n_heavy == 0 || chol_direct)) {
+                bool all_tmem = true;
+                for (int b = 0; b < nbk; ++b)
+                    if (pl.bucket_off[b + 1] > pl.bucket_off[b] && pl.bucket_dim[b] > 256) all_tmem = false;
+                if (all_tmem) HY_TRY(begin_cross());
+            }
             // rows above the cap do not depend on the factor of B: start them right away on their
             // own stream (base tiles and counters are ready on the main stream)
             CU_TRY(cudaEventRecord(h->ev_base, h->stream));
@@ -1021,6 +1051,12 @@ struct Engine : EngineBase {
             }
         }
         gram_ok[user ? 0 : 1] = false;
+        if (cross_active) {
+            cross_active = false;
+            cross_valid = true;
+            cross_lo = lo;
+            cross_hi = hi;
+        }
         int status[16] = {0};
         CU_TRY(cudaMemcpyAsync(status, counter.ptr, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -1039,7 +1075,7 @@ struct Engine : EngineBase {
         HY_TRY(compute_gram(0));
         HY_TRY(compute_gram(1));
         HY_TRY(row_s1.reserve(sizeof(double) * m));
-        HY_TRY(row_s2.reserve(sizeof(double) * m));
+        HY_TRY(row_s2.reserve(sizeof(double) * std::max<int64_t>(m, 1024)));
         HY_TRY(scalars.reserve(sizeof(double) * 4));
         CU_TRY(cudaMemsetAsync(scalars.ptr, 0, sizeof(double) * 4, h->stream));
         {
@@ -1047,7 +1083,22 @@ struct Engine : EngineBase {
             hyprec::frob_inner_kernel<T><<<1, 1024, 0, h->stream>>>(gram[0].as<T>(), gram[1].as<T>(), k * k,
                                                                      scalars.as<double>());
             h->launches += 1;
-            if (hi > lo) {
+            int64_t ilo = 0, ihi = n;
+            if (shard_only && h->item_hi >= 0) { ilo = h->item_lo; ihi = h->item_hi; }
+            if (cross_valid && cross_lo == ilo && cross_hi == ihi) {
+                // the item half-step left sum_j r_j (u_j . v_i) per item row: no pass over the positives
+                if (ihi > ilo)
+                    hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(cross.as<double>() + ilo, ihi - ilo, scalars.as<double>() + 1);
+                if (hi > lo) {
+                    const int64_t e0 = csr.h_indptr[lo], cnt = csr.h_indptr[hi] - e0;
+                    const int nblk = (int)std::min<int64_t>(1024, (cnt + 4095) / 4096);
+                    if (nblk > 0) {
+                        hyprec::sumsq_partial_kernel<T><<<nblk, 256, 0, h->stream>>>(csr.values.template as<T>() + e0, cnt, row_s2.as<double>());
+                        hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s2.as<double>(), nblk, scalars.as<double>() + 2);
+                    }
+                }
+                h->launches += 3;
+            } else if (hi > lo) {
                 const int wpb = 8;
                 const int64_t rows = hi - lo;
                 hyprec::sddmm_row_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
@@ -1536,6 +1587,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->tc_solve_enabled = h->tc_enabled && !(ts_env && ts_env[0] == '0');
     const char* tch = getenv("HYPREC_TC_CHOL");
     h->tc_chol_enabled = h->tc_solve_enabled && !(tch && tch[0] == '0');
+    const char* rf = getenv("HYPREC_RMSE_FUSED");
+    h->rmse_fused_enabled = !(rf && rf[0] == '0');
     const char* tmu = getenv("HYPREC_TC_MULTI");
     h->tc_multi_enabled = !(tmu && tmu[0] == '0');
     const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");

@@ -196,6 +196,23 @@ __global__ void sddmm_row_kernel(const int64_t* __restrict__ indptr, const int32
     }
 }
 
+// partial[blockIdx.x] = sum of squares of a slice of x (float64, fixed order)
+template <typename T>
+__global__ void sumsq_partial_kernel(const T* __restrict__ x, int64_t count, double* __restrict__ partial) {
+    __shared__ double red[256];
+    const int64_t per = (count + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = per * blockIdx.x, hi = lo + per < count ? lo + per : count;
+    double s = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += (double)x[i] * (double)x[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
 // out[0] = sum in[0..n) in a fixed order (single block).
 __global__ void reduce_sum_kernel(const double* __restrict__ in, int64_t n, double* __restrict__ out) {
     __shared__ double red[1024];

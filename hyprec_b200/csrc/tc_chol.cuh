@@ -49,11 +49,13 @@ struct CholRowsArgs {
     int max_dim;              // largest system of the launch (<= 256)
     int lowrank;
     int tmem_cols;
+    double* cross_out;        // optional [n_rows]: sum_j r_j (fixed_j . x) of the row -- the RMSE cross term, a by-product
+                              // of the solve (b.x = |L^-1 b|^2; low-rank form: (|r|^2 - |z|^2) / 0.9); no prior
     long long* prof;          // optional clock64() phase totals of block 0
 };
 
 struct CholLayout {
-    size_t off_stage, off_l11, off_l11t, off_dinv, off_z, off_x, off_b, off_part, off_idx, off_rst, off_bar, total;
+    size_t off_stage, off_l11, off_l11t, off_dinv, off_z, off_x, off_b, off_part, off_idx, off_rst, off_red, off_bar, total;
 };
 
 __host__ __device__ __forceinline__ CholLayout chol_layout(int max_dim) {
@@ -70,6 +72,7 @@ __host__ __device__ __forceinline__ CholLayout chol_layout(int max_dim) {
     l.off_part = o; o += sizeof(float) * 8 * 32;    // per-warp partial dot products (back substitution)
     l.off_idx = o;  o += sizeof(int) * 256;         // positives' ids
     l.off_rst = o;  o += sizeof(float) * 256;       // ratings of the current batch (direct gather)
+    l.off_red = o;  o += sizeof(float) * 16;        // per-warp partial sums of |r|^2 and |z|^2
     l.off_bar = (o + 7) & ~(size_t)7;
     o = l.off_bar + 32;
     l.total = o + 1024;                    // alignment slack
@@ -250,6 +253,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
     float* part = (float*)(smem + lay.off_part);
     int* idxs = (int*)(smem + lay.off_idx);
     float* rst = (float*)(smem + lay.off_rst);
+    float* red = (float*)(smem + lay.off_red);
     uint64_t* bars = (uint64_t*)(smem + lay.off_bar);       // [0], [1] staging stages, [2] panel updates
     uint32_t* tmem_slot = (uint32_t*)(bars + 3);
     __shared__ long long s_row;
@@ -341,6 +345,12 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
         }
         HYPREC_TCPROF(0)
         if (tid >= dim && tid < dimp) bs[tid] = 0.f;   // identity padding solves to zero
+        if (p.cross_out != nullptr && lowrank) {       // |r|^2 while bs still holds the ratings
+            float q = tid < dim ? bs[tid] * bs[tid] : 0.f;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) q += __shfl_xor_sync(0xffffffffu, q, s);
+            if (lane == 0) red[8 + warp] = q;
+        }
         // direct mode: this row's 32 entries of the shared Gram for the coming panel, fetched one panel
         // ahead (behind the trailing update's wait)
         float4 g4[8];
@@ -441,6 +451,13 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
             HYPREC_TCPROF(5)
         }
 
+        if (p.cross_out != nullptr) {                  // |z|^2, z = L^-1 b complete
+            float q = tid < dim ? zs[tid] * zs[tid] : 0.f;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) q += __shfl_xor_sync(0xffffffffu, q, s);
+            if (lane == 0) red[warp] = q;
+        }
+
         // ---- 3. back substitution L^T x = z, last panel first ---------------------------------
         float xmine = 0.f;
         for (int pn = n_panels - 1; pn >= 0; --pn) {
@@ -475,6 +492,14 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
         if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {
             p.prof[8] += 1;
             p.prof[9] += deg;
+        }
+        if (p.cross_out != nullptr && tid == 0) {      // (the back substitution's barriers published red[])
+            double zz = 0.0, rr = 0.0;
+            for (int w = 0; w < kCholThreads / 32; ++w) {
+                zz += (double)red[w];
+                if (lowrank) rr += (double)red[8 + w];
+            }
+            p.cross_out[row] = lowrank ? (rr - zz) / (double)pos_scale : zz;
         }
 
         // ---- 4. output ------------------------------------------------------------------------

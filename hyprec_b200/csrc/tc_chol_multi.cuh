@@ -17,7 +17,7 @@ namespace hyprec {
 namespace tc {
 
 struct CholMultiLayout {
-    size_t off_stage, off_l11, off_dinv, off_z, off_x, off_b, off_part, off_col, off_idx, off_meta, off_bar, total;
+    size_t off_stage, off_l11, off_dinv, off_z, off_x, off_b, off_part, off_col, off_idx, off_meta, off_red, off_bar, total;
 };
 
 __host__ __device__ __forceinline__ CholMultiLayout chol_multi_layout() {
@@ -33,6 +33,7 @@ __host__ __device__ __forceinline__ CholMultiLayout chol_multi_layout() {
     l.off_col = o;   o += sizeof(float) * 8 * 64;        // per warp: column exchange of the diagonal factor
     l.off_idx = o;   o += sizeof(int) * 256;
     l.off_meta = o;  o += 8 * (8 + 8 + 8);               // per system: row id, CSR offset, dimension
+    l.off_red = o;   o += sizeof(float) * 16;            // per-warp partial sums of |r|^2 and |z|^2
     l.off_bar = (o + 7) & ~(size_t)7;
     o = l.off_bar + 32;
     l.total = o + 1024;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_multi_kernel(CholRows
     long long* sys_row = (long long*)(smem + lay.off_meta);
     long long* sys_lo = sys_row + 8;
     long long* sys_dim = sys_lo + 8;
+    float* red = (float*)(smem + lay.off_red);
     uint64_t* bars = (uint64_t*)(smem + lay.off_bar);
     uint32_t* tmem_slot = (uint32_t*)(bars + 3);
     __shared__ long long s_first;
@@ -140,6 +142,12 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_multi_kernel(CholRows
             }
         }
         __syncthreads();
+        if (p.cross_out != nullptr) {                   // |r|^2 per warp while bs still holds the ratings
+            float q = bs[tid] * bs[tid];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) q += __shfl_xor_sync(0xffffffffu, q, s);
+            if (lane == 0) red[8 + warp] = q;
+        }
         if (max_pan > 0) syrk_lowrank_accumulate(p.fixed, idxs, 256, k, st, sqrt_pos, 128, true);
         HYPREC_TCPROF(0)
 
@@ -207,6 +215,13 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_multi_kernel(CholRows
             HYPREC_TCPROF(5)
         }
 
+        if (p.cross_out != nullptr) {                   // |z|^2 per warp (z = 0 on the padding)
+            float q = lr < dimp ? zs[tid] * zs[tid] : 0.f;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) q += __shfl_xor_sync(0xffffffffu, q, s);
+            if (lane == 0) red[warp] = q;
+        }
+
         // ---- 3. back substitution, last panel first ---------------------------------------------
         float xmine = 0.f;
         for (int pn = max_pan - 1; pn >= 0; --pn) {
@@ -239,6 +254,17 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_multi_kernel(CholRows
         if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {
             p.prof[8] += NSYS;
             for (int s = 0; s < NSYS; ++s) p.prof[9] += sys_dim[s];
+        }
+
+        __syncthreads();
+        if (p.cross_out != nullptr && tid < NSYS && sys_row[tid] >= 0) {
+            // RMSE cross term of the row: sum_j r_j (q_j . y) = (|r|^2 - |z|^2) / 0.9 (S t = r, y = Q^T t)
+            double zz = 0.0, rr = 0.0;
+            for (int w = 0; w < WPS; ++w) {
+                zz += (double)red[tid * WPS + w];
+                rr += (double)red[8 + tid * WPS + w];
+            }
+            p.cross_out[sys_row[tid]] = (rr - zz) / (double)pos_scale;
         }
 
         // ---- 4. y = Q_r^T t + p for every system ------------------------------------------------

@@ -411,6 +411,36 @@ def test_tensor_memory_small_systems_fp32(native, monkeypatch, m, n, k, nnz):
     assert not numpy.array_equal(got["1"][0], got["0"][0])
 
 
+@pytest.mark.parametrize("m,n,k,nnz,lowrank", [(200, 1500, 128, 12000, "1"), (150, 400, 256, 9000, "1"),
+                                               (60, 500, 64, 5000, "0")])
+def test_rmse_cross_term_from_the_item_half_step_fp32(native, monkeypatch, m, n, k, nnz, lowrank):
+    """float32 tensor-memory kernels hand out sum_j r_j (u_j . v_i) per item row as a by-product of the
+    solve (|L^-1 b|^2, low-rank form (|r|^2 - |z|^2) / 0.9): hyprec_rmse after an item half-step then needs no
+    pass over the positives.  Same RMSE as the sparse pass (HYPREC_RMSE_FUSED=0) and as the oracle."""
+    full, train, test, u0, v0, cands = synthetic(m, n, k, nnz, seed=k + 11, empty=True)
+    csc = oals.to_csr(train.T)
+    u = oals.als_half_step(u0.copy(), v0, train, 0.01)
+    v = oals.als_half_step(v0.copy(), u, csc, 0.01)
+    want = oals.rmse_gram(u, v, train)
+    monkeypatch.setenv("HYPREC_LOWRANK", lowrank)
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("HYPREC_RMSE_FUSED", flag)
+        h, _ = make_handle(native, train, native.F32)
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        launches = h.launch_count
+        got[flag] = (h.rmse(), h.rmse_terms(), h.launch_count - launches)
+        h.close()
+    print("k=%d rmse fused %.9f sparse %.9f oracle %.9f; cross %.6f vs %.6f" %
+          (k, got["1"][0], got["0"][0], want, got["1"][1][1], got["0"][1][1]))
+    assert abs(got["1"][0] - want) < 1e-5 and abs(got["0"][0] - want) < 1e-5
+    assert abs(got["1"][1][1] - got["0"][1][1]) <= 2e-5 * abs(got["0"][1][1])
+    assert abs(got["1"][1][2] - got["0"][1][2]) == 0.0          # sum r^2
+    assert got["1"][1][1] != got["0"][1][1]                      # really two different computations
+
+
 def test_cached_candidates_and_pinned_outputs(native):
     """hyprec_set_candidates + NULL lists == passing the lists on every call; outputs may live in
     page-locked memory from hyprec_host_alloc."""

@@ -368,7 +368,9 @@ struct Engine : EngineBase {
         if (v) *v = V.ptr;
         if (elem) *elem = (int)sizeof(T);
         gram_ok[0] = gram_ok[1] = false;   // the caller may write through these pointers
-        cross_valid = false;
+        // With a shard set the pointers serve the exchange of the side just solved (rows of the OTHER
+        // ranks change): the cross term of this rank's item rows stays what the item half-step left.
+        if (h->user_hi < 0 && h->item_hi < 0) cross_valid = false;
         return HYPREC_OK;
     }
 

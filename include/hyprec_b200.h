@@ -69,7 +69,10 @@ int hyprec_set_shard(hyprec_t* h, int64_t user_lo, int64_t user_hi, int64_t item
 int hyprec_set_factors(hyprec_t* h, const double* user_vecs, const double* item_vecs, int k);
 int hyprec_get_factors(hyprec_t* h, double* user_vecs, double* item_vecs);
 /* Device addresses and element size (8 or 4) of the replicated factor matrices, for the
- * caller's collective (torch.distributed / NCCL all-gather of the solved shard). */
+ * caller's collective (torch.distributed / NCCL all-gather of the solved shard).  Every call tells
+ * the library that the matrices may have changed (cached Gram matrices are dropped).  With a shard
+ * set, the contract is the exchange of the side just solved: only rows OUTSIDE this handle's shard
+ * may be written through the pointers. */
 int hyprec_device_factors(hyprec_t* h, void** user_vecs_dev, void** item_vecs_dev, int* elem_size);
 
 /* self.document_distribution for the update_with_items rule (:93-96); NULL clears it. */

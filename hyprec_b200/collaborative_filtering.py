@@ -357,11 +357,7 @@ class CollaborativeFiltering(AbstractRecommender):
             h = self._upload_factors()
             collaborative_predictions = h.predict_dense()
             if self._is_hybrid:
-                try:
-                    from lib.linear_regression import LinearRegression
-                except ImportError:
-                    raise NotImplementedError("the hybrid linear-regression blend (lib/linear_regression.py) is "
-                                              "outside the B200 hot path; run inside the reference tree to use it")
+                from hyprec_b200.linear_regression import LinearRegression
                 self.item_based_recommender.set_data(self.train_data, self.test_data)
                 regr = LinearRegression(self.train_data, self.test_data,
                                         self.item_based_recommender.get_predictions(), collaborative_predictions)

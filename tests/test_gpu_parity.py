@@ -114,6 +114,39 @@ def test_als_step_signature_in_place(als_cases):
     cf.close()
 
 
+def test_hybrid_predictions_blend_device_scores(als_cases):
+    """is_hybrid: get_predictions() = coef0 * content + coef1 * (U V^T from the device), coefficients from
+    the least-squares fit of the train labels (collaborative_filtering.py:271-279, linear_regression.py:56-69)."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
+    g = als_cases["als_kfold_toy"]
+    fold = golden_folds(g)[0]
+    hyper = {'n_factors': int(g["k"]), '_lambda': 0.01}
+
+    class Content(object):                       # stands in for lib.content_based.ContentBased
+        def set_data(self, train, test):
+            self.train = train
+
+        def get_predictions(self):
+            rs = numpy.random.RandomState(3)
+            return 0.3 * self.train + 0.1 * rs.rand(*self.train.shape)
+
+    cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), 1), Evaluator(g["ratings"]), hyper,
+                                {'k_folds': 5, 'n_iterations': 1}, load_matrices=False, dump_matrices=False, is_hybrid=True)
+    cf.set_item_based_recommender(Content())
+    cf.set_data(fold["train"], fold["test"])
+    cf.hyperparameters['fold'] = 0
+    cf.user_vecs, cf.item_vecs = fold["u"].copy(), fold["v"].copy()
+    got = cf.get_predictions()
+    content = Content()
+    content.set_data(fold["train"], fold["test"])
+    x1, x2 = content.get_predictions().ravel(), fold["u"].dot(fold["v"].T).ravel()
+    design = numpy.column_stack([numpy.ones_like(x1), x1, x2])
+    coef = numpy.linalg.lstsq(design, fold["train"].ravel(), rcond=None)[0]
+    want = (coef[1] * x1 + coef[2] * x2).reshape(fold["train"].shape)
+    assert numpy.allclose(got, want, rtol=1e-8, atol=1e-10)
+    cf.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # C ABI against the oracle on synthetic problems
 # ------------------------------------------------------------------------------------------------

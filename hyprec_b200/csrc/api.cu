@@ -191,7 +191,7 @@ struct Engine : EngineBase {
     bool cross_valid = false;
     int64_t cross_lo = 0, cross_hi = 0;
     DevBuf gram[2], gram_partial, base, colsum, colsum_partial, thresholds;
-    DevBuf row_s1, row_s2, scalars, counter, scratch, a_scratch;
+    DevBuf row_s1, row_s2, scalars, counter;
     DevBuf tiles, linv, linv_t, qmat, pq, ymat, dummy_ptr, dummy_out, prof_buf, bdense, lfac, blk_tmp, blk_base;
     DevBuf fixed_d, gram_partial_d, gram_dbuf, linv_f, linv_t_f, stage_d;
     DevBuf a_scratch_slot[8];
@@ -214,7 +214,7 @@ struct Engine : EngineBase {
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
     ~Engine() override {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
-                         &thresholds, &row_s1, &row_s2, &scalars, &counter, &scratch, &a_scratch, &cand_ptr,
+                         &thresholds, &row_s1, &row_s2, &scalars, &counter, &cand_ptr,
                          &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
                          &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &w_hi, &w_lo, &l_hi, &l_lo, &cross, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],

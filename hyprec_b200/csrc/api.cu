@@ -1475,7 +1475,7 @@ struct Engine : EngineBase {
             const int wpb = 8;
             {
                 Timer t(h, HYPREC_T_FLAGS);
-                hyprec::nz_flags_kernel<T><<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
+                hyprec::nz_flags_kernel<T><<<(unsigned)((e1 - e0 + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
                     c.indptr.template as<int64_t>(), c.indices.template as<int32_t>(), U.as<T>(), V.as<T>(), k,
                     thresholds.as<double>(), lo, hi, flags.as<uint8_t>());
                 h->launches += 1;

@@ -228,21 +228,26 @@ __global__ void reduce_sum_kernel(const double* __restrict__ in, int64_t n, doub
 }
 
 // flags[e - indptr[row_lo]] = (u . v_j >= thresholds[u]) for every non-zero e of rows
-// [row_lo, row_hi), one warp per row.
+// [row_lo, row_hi), one warp per positive.
 template <typename T>
 __global__ void nz_flags_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                 const T* __restrict__ user_vecs, const T* __restrict__ item_vecs, int k,
                                 const double* __restrict__ thresholds, int64_t row_lo, int64_t row_hi,
                                 uint8_t* __restrict__ flags) {
+    // one warp per positive (rows differ in length by orders of magnitude); its row by bisection
     const int lane = threadIdx.x % 32;
-    const int64_t u = row_lo + (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-    if (u >= row_hi) return;
     const int64_t base = indptr[row_lo];
-    const double thr = thresholds[u];
-    for (int64_t e = indptr[u]; e < indptr[u + 1]; ++e) {
-        const double d = warp_dot(user_vecs + u * k, item_vecs + (int64_t)indices[e] * k, k, lane);
-        if (lane == 0) flags[e - base] = d >= thr ? 1 : 0;
+    const int64_t e = base + (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (e >= indptr[row_hi]) return;
+    int64_t lo = row_lo, hi = row_hi;          // invariant: indptr[lo] <= e < indptr[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) / 2;
+        if (indptr[mid] <= e) lo = mid;
+        else hi = mid;
     }
+    const int64_t u = lo;
+    const double d = warp_dot(user_vecs + u * k, item_vecs + (int64_t)indices[e] * k, k, lane);
+    if (lane == 0) flags[e - base] = d >= thresholds[u] ? 1 : 0;
 }
 
 }  // namespace hyprec

@@ -259,7 +259,9 @@ void emu_rmse_terms_f64(const int64_t* indptr, const int32_t* indices, const dou
 
 void emu_nz_flags_f64(const int64_t* indptr, const int32_t* indices, const double* U, const double* V, int k,
                       const double* thr, int64_t lo, int64_t hi, uint8_t* flags) {
-    emu::launch(dim3((unsigned)((hi - lo + 1) / 2)), dim3(64), 0,
+    const int64_t nnz = indptr[hi] - indptr[lo];          // one warp per positive, two warps per block
+    if (nnz <= 0) return;
+    emu::launch(dim3((unsigned)((nnz + 1) / 2)), dim3(64), 0,
                 [&]() { nz_flags_kernel<double>(indptr, indices, U, V, k, thr, lo, hi, flags); });
 }
 

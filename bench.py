@@ -461,10 +461,40 @@ def our_arm(args, wl):
     h.close()
 
 
+def sharded_roofline(wl, precision, world, solve_ms):
+    """Roofline view of rank 0's row-solve kernels in a sharded epoch: its cost-balanced 1/world share of the
+    epoch's algorithmic FLOPs over the device time of its solve launches (pure arithmetic: testable on CPU)."""
+    elem = 8 if precision == "fp64" else 4
+    work = algorithmic_work(wl, elem)
+    flops = work["lowrank_flops_per_epoch"] / float(world)
+    achieved = flops / (max(solve_ms, 1e-9) * 1e-3) / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tf32_peak = json.load(open(peaks_file))["bf16_tflops"] / 2.0 if os.path.exists(peaks_file) else None
+    tensor_rows = precision == "fp32" and wl["k"] % 4 == 0 and os.environ.get("HYPREC_TC", "1") != "0"
+    if tensor_rows and tf32_peak:
+        bound, peak, src = "tensor", tf32_peak, "MEASURED_PEAKS.json bf16_tflops / 2 (dense TF32 rate)"
+    else:
+        # float64 SIMT row kernel: nominal B200 FP64 FMA rate (the single-GPU line measures it with a probe)
+        bound, peak, src = "%s_fma" % precision, (37.0 if precision == "fp64" else 74.0), "nominal B200 FMA rate"
+    return dict(kernel="row-solve kernels of rank 0 (its share of the sharded epoch)", bound=bound, achieved=achieved,
+                peak=peak, unit="TFLOP/s", frac=achieved / peak, peak_source=src, traffic=None,
+                flops_per_epoch_rank=flops, flops_model="low-rank (sum d^2 k + d^3/3 + 4 d k) / world")
+
+
 def our_arm_distributed(args, wl, rank, world, local):
     from hyprec_b200 import distributed
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
     line = distributed.bench_sharded(args, wl, rank, world, local, config_block(wl, args))
     if rank == 0:
+        line["clocks"] = sampler.stop()
+        try:
+            line["roofline"] = sharded_roofline(wl, args.precision, world, line["rank0_solve_kernel_ms"])
+        except Exception as exc:       # the line itself must not be lost over its annotation
+            line["roofline"] = dict(error=repr(exc))
         print(json.dumps(line))
 
 

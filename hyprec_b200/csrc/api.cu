@@ -608,7 +608,7 @@ struct Engine : EngineBase {
 
     // C[ra x rb] = A[ra x k] B[rb x k]^T through the SIMT sweep kernel (float64 mode; float32 mode
     // goes through gemm_nt_tc below unless the tensor cores are switched off).  With a row
-    // list the product is taken over rows A[list[i]] and row i is stored at C[list[i]].
+    // list, row i of the product (A is compact) is stored at C[list[i]].
     int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, T* c, const int32_t* list = nullptr) {
         hyprec::SweepArgs<T> s;
         s.user_vecs = a;

@@ -474,6 +474,24 @@ def test_rmse_cross_term_from_the_item_half_step_fp32(native, monkeypatch, m, n,
     assert got["1"][1][1] != got["0"][1][1]                      # really two different computations
 
 
+@pytest.mark.parametrize("k", [64, 200, 256])
+def test_tensor_core_gram_fp32(native, k):
+    """float32 mode forms U^T U and V^T V on the tensor cores (gram_tc_kernel, 3xTF32, float64 reduction of
+    the row slices): <U^T U, V^T V>_F -- the first RMSE term -- against numpy in float64 on the float32 inputs."""
+    rs = numpy.random.RandomState(k)
+    m, n = 700, 1900
+    u = (rs.rand(m, k) - 0.3).astype(numpy.float32).astype(numpy.float64)
+    v = (rs.rand(n, k) - 0.5).astype(numpy.float32).astype(numpy.float64)
+    train = oals.to_csr(sp.csr_matrix((numpy.ones(3), ([0, 1, 2], [0, 1, 2])), shape=(m, n)))
+    h, _ = make_handle(native, train, native.F32)
+    h.set_factors(u, v)
+    frob = h.rmse_terms()[0]
+    want = float(numpy.sum(u.T.dot(u) * v.T.dot(v)))
+    print("k=%d <G_u, G_v> rel. error %.2e" % (k, abs(frob - want) / abs(want)))
+    assert abs(frob - want) <= 2e-6 * abs(want)
+    h.close()
+
+
 def test_cached_candidates_and_pinned_outputs(native):
     """hyprec_set_candidates + NULL lists == passing the lists on every call; outputs may live in
     page-locked memory from hyprec_host_alloc."""

@@ -455,7 +455,12 @@ def our_arm(args, wl):
                          eval_users_per_s=(m / (e2e_eval_ms * 1e-3)) if has_eval else None),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
                 eval_ms=eval_ms, eval_users_per_s=(m / (eval_ms * 1e-3)) if has_eval else None, wall_epoch_ms=1e3 * wall_epoch / args.steps,
-                wall_eval_ms=1e3 * wall_eval / args.steps, kernel_ms_per_step=per_step, rmse=rmse,
+                wall_eval_ms=1e3 * wall_eval / args.steps, kernel_ms_per_step=per_step,
+                kernel_ms_note="event-timed regions of the library's main stream; the row-solve launches of a half-step run "
+                               "on their own streams at the same time, so 'prep' (whitening) and the tail of 'solve' "
+                               "include waiting for SMs those launches occupy -- the launch lists under profiles/ have "
+                               "the per-kernel times",
+                rmse=rmse,
                 recall_at_200=recall200, setup_s=wl["setup_s"])
     print(json.dumps(line))
     h.close()

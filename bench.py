@@ -179,8 +179,15 @@ class ClockSampler(object):
             for name, flag in zip(names, s[5:9]):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
-        return dict(sm_mhz=float(numpy.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+        # "under load": a sample taken while the GPU idles between two short steps shows the idle clock,
+        # which says nothing about the timed kernels -- keep the samples in the upper half of the power range
+        loaded = sm
+        if power and max(power) > min(power):
+            cut = min(power) + 0.5 * (max(power) - min(power))
+            loaded = [c for c, p_w in zip(sm, power) if p_w >= cut] or sm
+        return dict(sm_mhz=float(numpy.median(loaded)) if loaded else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), samples_under_load=len(loaded),
+                    sm_mhz_all_samples=float(numpy.median(sm)) if sm else None, reasons=sorted(reasons))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -488,14 +495,21 @@ def sharded_roofline(wl, precision, world, solve_ms):
 
 def our_arm_distributed(args, wl, rank, world, local):
     from hyprec_b200 import distributed
-    sampler = None
+    sampler = ClockSampler(local) if rank == 0 else None
+    clocks = {}
+
+    def begin():
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
+
+    def end():
+        if sampler is not None:
+            clocks.update(sampler.stop())
+
+    line = distributed.bench_sharded(args, wl, rank, world, local, config_block(wl, args), dict(begin=begin, end=end))
     if rank == 0:
-        sampler = ClockSampler(local)
-        sampler.start()
-        time.sleep(0.3)
-    line = distributed.bench_sharded(args, wl, rank, world, local, config_block(wl, args))
-    if rank == 0:
-        line["clocks"] = sampler.stop()
+        line["clocks"] = clocks
         try:
             line["roofline"] = sharded_roofline(wl, args.precision, world, line["rank0_solve_kernel_ms"])
         except Exception as exc:       # the line itself must not be lost over its annotation

@@ -158,7 +158,7 @@ class ShardedALS(object):
 # --------------------------------------------------------------------------------------------------
 # bench.py's N > 1 arm
 # --------------------------------------------------------------------------------------------------
-def bench_sharded(args, wl, rank, world, local, config):
+def bench_sharded(args, wl, rank, world, local, config, hooks=None):
     import time
     import torch
     import torch.distributed as dist
@@ -196,6 +196,8 @@ def bench_sharded(args, wl, rank, world, local, config):
         rmse = als.epoch(lam)
         return rmse, evaluate()
 
+    if hooks and "begin" in hooks:
+        hooks["begin"]()               # clock sampling starts with the warm-up, not with the setup
     for _ in range(args.warmup):
         h.flush_l2()
         step()
@@ -221,6 +223,8 @@ def bench_sharded(args, wl, rank, world, local, config):
         total_wall += t2 - t0
     dist.barrier()
     torch.cuda.synchronize()
+    if hooks and "end" in hooks:
+        hooks["end"]()
     times = torch.tensor([epoch_wall, total_wall], dtype=torch.float64, device="cuda")
     dist.all_reduce(times, op=dist.ReduceOp.MAX)
     epoch_ms = 1e3 * times[0].item() / args.steps
@@ -241,6 +245,49 @@ def bench_sharded(args, wl, rank, world, local, config):
                          note="factors stay device-resident across sharded epochs; evaluation inputs/outputs "
                               "cross PCIe every step"))
     h.close()
+    if has_eval:
+        # Reported next to the sharded number, never instead of it: the same epoch as N independent
+        # replicas (one whole model per GPU, no data-path collective -- what k-fold cross-validation and
+        # GridSearch do with N GPUs at this problem size, where a 3 ms epoch has nothing left to shard).
+        line["replicas"] = _bench_replicas(args, wl, local, precision, world)
     dist.barrier()
     dist.destroy_process_group()
     return line
+
+
+def _bench_replicas(args, wl, local, precision, world):
+    import time
+    import torch
+    import torch.distributed as dist
+    from hyprec_b200 import _native
+    m, n, lam = wl["m"], wl["n"], wl["lam"]
+    tr = wl["train_csr"]
+    h = _native.Handle(local, precision)
+    h.set_train_csr(m, n, tr.indptr, tr.indices, tr.data)
+    h.set_factors(wl["u0"], wl["v0"])
+
+    def step():
+        h.als_half_step(_native.SIDE_USER, lam)
+        h.als_half_step(_native.SIDE_ITEM, lam)
+        h.rmse()
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall = 0.0
+    for _ in range(args.steps):
+        h.flush_l2()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize()
+        wall += time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_replica = 1e3 * t.item() / args.steps
+    h.close()
+    return dict(value=per_replica / world, unit="ms", scaling="weak", per_replica_epoch_ms=per_replica, models=world,
+                note="aggregate ms per epoch when every GPU trains its own model (max over ranks / N); "
+                     "no collective in the data path")

@@ -28,3 +28,27 @@ def test_sharded_roofline_keys(small, precision, world):
         assert key in r
     assert r["unit"] == "TFLOP/s" and r["achieved"] > 0 and 0 < r["frac"] < 1
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-15
+
+
+def test_clock_sampler_reports_the_clock_under_load():
+    """Short timed regions leave most nvidia-smi samples on an idle GPU: the reported clock is the median
+    of the samples in the upper half of the power range; the all-samples median is kept next to it."""
+    class Proc(object):
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            pass
+
+        def kill(self):
+            pass
+
+    sampler = bench.ClockSampler(0)
+    sampler.proc = Proc()
+    idle = ["0", "120", "1965", "80.0", "x", "Not Active", "Not Active", "Not Active", "Not Active"]
+    busy = ["0", "1950", "1965", "420.0", "x", "Not Active", "Not Active", "Not Active", "Active"]
+    sampler.samples = [idle] * 6 + [busy] * 3
+    got = sampler.stop()
+    assert got["sm_mhz"] == 1950.0 and got["sm_mhz_all_samples"] == 120.0
+    assert got["samples"] == 9 and got["samples_under_load"] == 3
+    assert got["reasons"] == ["sw_power_cap"] and got["sm_max_mhz"] == 1965.0

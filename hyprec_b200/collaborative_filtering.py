@@ -86,6 +86,8 @@ class CollaborativeFiltering(AbstractRecommender):
         self._train_nnz = 0
         self._test_nnz = 0
         self._cands_uploaded = None      # (test_indices object, fold) of the candidate lists on the device
+        self._train_pattern = None       # (indptr, indices) of the uploaded train / test CSRs
+        self._test_pattern = None
         self._sync_token = None
         self.last_report_details = None  # per-user device outputs of the latest report
 
@@ -114,9 +116,12 @@ class CollaborativeFiltering(AbstractRecommender):
             self._handle = _native.Handle(index, self._precision)
         return self._handle
 
-    @staticmethod
-    def _world():
-        """(rank, world_size) of an initialised torch.distributed group, else (0, 1)."""
+    def _world(self):
+        """(rank, world_size) of an initialised torch.distributed group, else (0, 1).  An object
+        marked ``_single_rank`` (a grid-search worker that owns one whole model, grid_search.py) stays
+        on its own GPU even inside a process group."""
+        if getattr(self, '_single_rank', False):
+            return 0, 1
         try:
             import torch.distributed as dist
         except ImportError:
@@ -141,6 +146,7 @@ class CollaborativeFiltering(AbstractRecommender):
             indptr, indices, values = _csr_triplet(self.train_data)
             h.set_train_csr(self.n_users, self.n_items, indptr, indices, values)
             self._train_nnz = len(indices)
+            self._train_pattern = (indptr, indices)      # order of the device's train flags
             self._train_uploaded = self.train_data
             self._eval_uploaded = None
             self._cands_uploaded = None
@@ -155,6 +161,7 @@ class CollaborativeFiltering(AbstractRecommender):
             test = _csr_triplet(self.test_data)
             h.set_eval_csr(full, test)
             self._test_nnz = len(test[1])
+            self._test_pattern = (test[0], test[1])      # order of the device's test flags
             self._eval_uploaded = key
         return h
 
@@ -252,6 +259,11 @@ class CollaborativeFiltering(AbstractRecommender):
         """collaborative_filtering.py:164-212: initialise (random / theta / checkpoint), train,
         optionally save, report.  The order of the ``numpy.random`` draws is the reference's
         (user matrix first)."""
+        return self._run_fold(self._init_fold(item_vecs))
+
+    def _init_fold(self, item_vecs=None):
+        """Host half of train_one_fold (:166-192): everything that touches the global numpy.random
+        stream or the checkpoint files.  Returns ``matrices_found``."""
         user_shape, item_shape = (self.n_users, self.n_factors), (self.n_items, self.n_factors)
         matrices_found = False
         if self._load_matrices is False:
@@ -273,6 +285,10 @@ class CollaborativeFiltering(AbstractRecommender):
                 self.item_vecs = item_vecs
             matrices_found = users_found and items_found
         self._sync_token = None
+        return matrices_found
+
+    def _run_fold(self, matrices_found):
+        """Device half of train_one_fold (:194-212): train (or not), save, report."""
         if not matrices_found:
             if self._verbose and self._load_matrices:
                 print("User and Document distributions files were not found, will train collaborative.")

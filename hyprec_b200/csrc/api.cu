@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <map>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,24 @@ int fail(int code, const std::string& msg) {
         int rc_ = (expr);       \
         if (rc_ != HYPREC_OK) return rc_; \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the (device, kernel) pair for the
+// whole process, not of a handle: several handles of different n_factors (a hyper-parameter sweep)
+// launch the same instantiations with different sizes, possibly from different host threads.  The
+// opted-in size therefore lives in one process-wide table and only ever grows.
+int ensure_dynamic_smem(const void* func, int bytes) {
+    static std::mutex guard;
+    static std::map<std::pair<int, const void*>, int> opted;
+    int device = 0;
+    CU_TRY(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lock(guard);
+    int& have = opted[std::make_pair(device, func)];
+    if (bytes > have) {
+        CU_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
+    return HYPREC_OK;
+}
 
 // Device buffer that only grows.
 struct DevBuf {
@@ -197,18 +216,6 @@ struct Engine : EngineBase {
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
     static constexpr int kHeavyStream = 6;   // aux streams 0..5: degree buckets, 6: rows above the cap
-    std::map<const void*, int> smem_attr;    // per kernel: largest dynamic shared memory opted into
-
-    // cudaFuncAttributeMaxDynamicSharedMemorySize only ever grows (one cache per kernel function: the
-    // same instantiation is launched from several places with different sizes).
-    int ensure_dynamic_smem(const void* func, int bytes) {
-        int& have = smem_attr[func];
-        if (bytes > have) {
-            CU_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            have = bytes;
-        }
-        return HYPREC_OK;
-    }
     DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk;
 
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
@@ -860,7 +867,7 @@ struct Engine : EngineBase {
         const int tis = with_tiles <= (size_t)h->max_smem ? 1 : 0;
         if (tis) inv_smem = with_tiles;
         auto inv_kern = hp::tri_inverse_kernel<double>;
-        CU_TRY(cudaFuncSetAttribute(inv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+        HY_TRY(ensure_dynamic_smem((const void*)inv_kern, (int)inv_smem));
         inv_kern<<<nbk, 64, inv_smem, h->stream>>>(tile_ptr, dim, tis, out, out_t, ld);
         h->launches += 1;
         CU_TRY(cudaGetLastError());
@@ -1236,7 +1243,7 @@ struct Engine : EngineBase {
         a.dense_ld = dense_ld;
         a.row_map = nullptr;
         auto kern = tcn::tc_score_kernel;
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcn::kSmemBytes));
+        HY_TRY(ensure_dynamic_smem((const void*)kern, (int)tcn::kSmemBytes));
         const int64_t n_tiles = ((nu + tcn::kBM - 1) / tcn::kBM) * tiles_n;
         const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
         kern<<<grid, tcn::kThreads, tcn::kSmemBytes, h->stream>>>(mu_hi, mu_lo, mv_hi, mv_lo, a);
@@ -1407,7 +1414,7 @@ struct Engine : EngineBase {
             if (lay.total > (size_t)h->max_smem)
                 return fail(HYPREC_E_UNSUPPORTED, "eval_topk: candidate list too long for one CTA's shared memory");
             auto kern = hyprec::eval_topk_kernel<T>;
-            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+            HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
             int per_sm = 0;
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, hyprec::kTopkThreads, lay.total));
             per_sm = std::max(per_sm, 1);

@@ -7,14 +7,25 @@ from oracle import reference_loader
 
 @pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not present")
 def test_install_rebinds_reference_modules():
+    import inspect
     import sys
     ref = reference_loader.load_reference(heavy=True)
     import hyprec_b200
     original = sys.modules["lib.collaborative_filtering"].CollaborativeFiltering
+    saved = {(name, attr): getattr(sys.modules[name], attr)
+             for name in list(sys.modules) if name.startswith("lib.") and sys.modules[name] is not None
+             for attr in ("CollaborativeFiltering", "Evaluator", "GridSearch") if hasattr(sys.modules[name], attr)}
     try:
         patched = hyprec_b200.install()
         assert "lib.collaborative_filtering" in patched and "lib.recommender_system" in patched
         assert sys.modules["lib.recommender_system"].CollaborativeFiltering is hyprec_b200.CollaborativeFiltering
+        assert sys.modules["lib.recommender_system"].Evaluator is hyprec_b200.Evaluator
+        assert sys.modules["lib.grid_search"].GridSearch is hyprec_b200.GridSearch
+        ref_grid = saved[("lib.grid_search", "GridSearch")]
+        assert list(inspect.signature(ref_grid.__init__).parameters) == \
+            list(inspect.signature(hyprec_b200.GridSearch.__init__).parameters)[:5]
+        for name in ("get_all_combinations", "train", "get_key", "dump_csv", "get_all_errors"):
+            assert callable(getattr(hyprec_b200.GridSearch, name)), name
         # same constructor surface as the reference class (collaborative_filtering.py:18-20)
         import inspect
         assert list(inspect.signature(original.__init__).parameters) == \
@@ -25,5 +36,5 @@ def test_install_rebinds_reference_modules():
                      "build_confidence_matrix", "set_item_based_recommender", "_get_options_suffix"):
             assert callable(getattr(hyprec_b200.CollaborativeFiltering, name)), name
     finally:
-        for name in ("lib.collaborative_filtering", "lib.recommender_system"):
-            sys.modules[name].CollaborativeFiltering = original
+        for (name, attr), value in saved.items():
+            setattr(sys.modules[name], attr, value)

@@ -394,11 +394,50 @@ class CollaborativeFiltering(AbstractRecommender):
         if self._is_hybrid:
             return AbstractRecommender.recommend_items(self, user_id, num_recommendations)
         h = self._upload_factors()
+        if self.n_users == 1:
+            self._drop_candidates(h)         # the one-user range would match the fold's cached lists
         out = h.eval_topk(num_recommendations, None, None, user_id, user_id + 1, want_counts=False)
         keep = out["topk_idx"][0] >= 0
         ids = [int(i) for i in out["topk_idx"][0][keep]]
         vals = [float(v) for v in out["topk_val"][0][keep]]
         return zip(reversed(ids), reversed(vals))
+
+    def _drop_candidates(self, h):
+        """Forget the fold's candidate lists on the device: a NULL-list top-k over the same user range would
+        use them instead of the whole catalogue (include/hyprec_b200.h, hyprec_set_candidates)."""
+        if self._cands_uploaded is not None:
+            h.set_candidates(None, None)
+            self._cands_uploaded = None
+
+    def top_recommendations(self, num_recommendations=10, user_lo=0, user_hi=None):
+        """Full-catalogue top-N of users [user_lo, user_hi) in ONE device pass (what
+        abstract_recommender.py:189-204 computes user by user): (ids int32, scores float64), users x N,
+        descending score with TopRecommendations' tie order, -1 padded."""
+        h = self._upload_factors()
+        self._drop_candidates(h)
+        user_hi = self.n_users if user_hi is None else user_hi
+        out = h.eval_topk(num_recommendations, None, None, user_lo, user_hi, want_counts=False)
+        return out["topk_idx"], out["topk_val"]
+
+    def dump_recommendations(self, num_recommendations=10, path=None):
+        """abstract_recommender.py:148-171 with one batched device pass instead of n_users x n_items Python
+        inserts.  ``path`` defaults to ``matrices/<results_file_name>`` like the reference
+        (``results_file_name`` is 'top_recommendations.dat' unless the owner set one,
+        recommender_system.py:27, 59)."""
+        if self._is_hybrid:
+            return AbstractRecommender.dump_recommendations(self, num_recommendations)
+        from hyprec_b200 import formats
+        ids, vals = self.top_recommendations(num_recommendations)
+        if path is None:
+            base_dir = os.path.dirname(os.path.realpath(__file__))
+            name = getattr(self, 'results_file_name', 'top_recommendations.dat')
+            path = os.path.join(os.path.dirname(base_dir), 'matrices/%s' % name)
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as f:
+            f.writelines(formats.recommendation_lines(ids, vals))
+        if self._verbose:
+            print("dumped top recommendations to %s" % path)
+        return path
 
     # ------------------------------------------------------------------ evaluation
     def candidate_lists(self, fold):
@@ -428,6 +467,23 @@ class CollaborativeFiltering(AbstractRecommender):
         gathered = [None] * world
         dist.all_gather_object(gathered, part)
         return {key: numpy.concatenate([g[key] for g in gathered]) for key in part}
+
+    def recall_at_cutoffs(self, cutoffs=(50, 100, 150, 200, 250, 300)):
+        """recall@x for every x of ``cutoffs`` from ONE device pass (BASELINE.json configs[1]: recall@{50..300}).
+        The reference loads 200 recommendations and reports recall@200 only (abstract_recommender.py:111-114);
+        here the streamed top-max(cutoffs) list of each user is loaded once and each cut-off is evaluated with
+        the reference's own arithmetic (evaluator.py:281-292).  Returns {x: numpy.float16}."""
+        cutoffs = [int(x) for x in cutoffs]
+        saved = self.n_recommendations
+        self.n_recommendations = max([saved] + cutoffs)
+        try:
+            verbose, self._verbose = self._verbose, False
+            self.get_evaluation_report()
+        finally:
+            self.n_recommendations, self._verbose = saved, verbose
+        hits = self.last_report_details["topk_hit"]
+        test_likes = numpy.asarray(self.test_data.sum(axis=1)).ravel()
+        return {x: metrics.recall_at_x(x, hits, test_likes) for x in cutoffs}
 
     def get_evaluation_report(self):
         """abstract_recommender.py:100-131.  Scores never leave the GPU: the device returns row

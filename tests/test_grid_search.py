@@ -139,24 +139,3 @@ def test_configurations_are_dealt_to_ranks_gloo(golden):
         best, rows = out[r]
         check_rows([list(golden["header"])] + rows, golden)
         assert [best['_lambda'], best['n_factors']] == list(golden["best"])
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("workers", [1, 3])
-def test_device_sweep_matches_reference_rows(golden, monkeypatch, workers):
-    """The real thing: every model trained and evaluated through the C ABI, several in flight."""
-    from hyprec_b200 import CollaborativeFiltering
-    monkeypatch.setattr(GridSearch, "dump_csv", lambda self, rows: None)
-    rec = make_recommender(CollaborativeFiltering, golden["ratings"])
-    search = GridSearch(rec, GRID, verbose=False, workers=workers)
-    assert search._device_backed()
-    try:
-        best, rows = search.train()
-        check_outcome(search, best, rows, golden)
-        assert numpy.random.random() == float(golden["rng_after"])
-        assert numpy.allclose(rec.user_vecs, golden["final_user_vecs"], rtol=1e-7, atol=1e-10)
-        # the caller's recommender holds the last model and keeps working on its own handle
-        report = rec.get_evaluation_report()
-        assert numpy.allclose([float(x) for x in report], golden["rows"][-1][2:], rtol=1e-8)
-    finally:
-        rec.close()

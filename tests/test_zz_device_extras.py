@@ -1,0 +1,114 @@
+"""GPU tests of the rows added after the first parity suite (file name sorts last on purpose): the
+hyper-parameter sweep through the C ABI, recall at several cut-offs from one device pass, the batched
+full-catalogue dump."""
+import numpy
+import pytest
+
+from conftest import golden_folds, load_golden
+from grid_helpers import GRID, make_recommender
+from hyprec_b200.grid_search import GridSearch
+from test_grid_search import check_outcome
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return load_golden("grid_naive_toy")
+
+
+@pytest.mark.parametrize("workers", [1, 3])
+def test_device_sweep_matches_reference_rows(golden, monkeypatch, workers):
+    """The real thing: every model trained and evaluated through the C ABI, several in flight."""
+    from hyprec_b200 import CollaborativeFiltering
+    monkeypatch.setattr(GridSearch, "dump_csv", lambda self, rows: None)
+    rec = make_recommender(CollaborativeFiltering, golden["ratings"])
+    search = GridSearch(rec, GRID, verbose=False, workers=workers)
+    assert search._device_backed()
+    try:
+        best, rows = search.train()
+        check_outcome(search, best, rows, golden)
+        assert numpy.random.random() == float(golden["rng_after"])
+        assert numpy.allclose(rec.user_vecs, golden["final_user_vecs"], rtol=1e-7, atol=1e-10)
+        # the caller's recommender holds the last model and keeps working on its own handle
+        report = rec.get_evaluation_report()
+        assert numpy.allclose([float(x) for x in report], golden["rows"][-1][2:], rtol=1e-8)
+    finally:
+        rec.close()
+
+
+def test_recall_at_cutoffs_from_one_pass(als_cases):
+    """recall@x for several x (BASELINE configs[1]) against the host mirror's dense path, which the CPU suite
+    pins to the reference (evaluator.py:268-292)."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
+    g = als_cases["als_kfold_toy"]
+    fold = golden_folds(g)[0]
+    hyper = {'n_factors': int(g["k"]), '_lambda': float(g["lam"])}
+    options = {'k_folds': int(g["k_folds"]), 'n_iterations': int(g["n_iter"])}
+    ev = Evaluator(g["ratings"])
+    cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), options['n_iterations']), ev, hyper, options,
+                                load_matrices=False, dump_matrices=False)
+    lists = ev.get_kfold_indices()
+    cf.set_data(*ev.get_fold(0, lists))
+    cf.hyperparameters['fold'] = 0
+    cf.user_vecs, cf.item_vecs = fold["u"].copy(), fold["v"].copy()
+    cutoffs = (1, 3, 5, 10, 24, 300)
+    try:
+        got = cf.recall_at_cutoffs(cutoffs)
+        assert cf.n_recommendations == 200
+    finally:
+        cf.close()
+    host = Evaluator(g["ratings"])
+    host.set_kfolds(int(g["k_folds"]))
+    host.test_indices = lists
+    predictions = fold["u"].dot(fold["v"].T)
+    avg = numpy.cumsum(predictions, axis=1)[:, -1] / predictions.shape[1]
+    rounded = (predictions >= avg[:, None]).astype(numpy.float64)
+    host.load_top_recommendations(300, predictions, fold["test"], 0)
+    for x in cutoffs:
+        want = host.recall_at_x(x, predictions, fold["test"], rounded)
+        assert got[x] == want, (x, got[x], want)
+
+
+def test_batched_dump_matches_per_user_lists(als_cases, tmp_path):
+    """dump_recommendations in one device pass == the per-user recommend_items flow of
+    abstract_recommender.py:148-171 (host mirror of TopRecommendations on the dense scores)."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer, formats
+    from hyprec_b200.top_recommendations import TopRecommendations
+    g = als_cases["als_kfold_toy"]
+    fold = golden_folds(g)[0]
+    hyper = {'n_factors': int(g["k"]), '_lambda': float(g["lam"])}
+    options = {'k_folds': int(g["k_folds"]), 'n_iterations': int(g["n_iter"])}
+    ev = Evaluator(g["ratings"])
+    cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), options['n_iterations']), ev, hyper, options,
+                                load_matrices=False, dump_matrices=False)
+    lists = ev.get_kfold_indices()
+    cf.set_data(*ev.get_fold(0, lists))
+    cf.hyperparameters['fold'] = 0
+    cf.user_vecs, cf.item_vecs = fold["u"].copy(), fold["v"].copy()
+    try:
+        cf.get_evaluation_report()                      # leaves the fold's candidate lists on the device
+        path = cf.dump_recommendations(15, path=str(tmp_path / "top.dat"))
+        got = formats.read_recommendations(path)
+        single = [i for i, _ in cf.recommend_items(7, 15)]
+        report_again = cf.get_evaluation_report()       # candidate lists come back for the next report
+    finally:
+        cf.close()
+    predictions = fold["u"].dot(fold["v"].T)
+    m, n = predictions.shape
+    assert len(got) == m
+    differing = 0
+    for user in range(m):
+        top = TopRecommendations(15)
+        for i in range(n):
+            top.insert(i, predictions[user][i])
+        want = [idx for idx, val in zip(top.get_indices(), top.get_values()) if val > 1e-6]
+        if got[user] != want:                           # only score ties may permute (documented carve-out)
+            differing += 1
+            assert sorted(numpy.round(predictions[user][got[user]], 10)) == \
+                sorted(numpy.round(predictions[user][want], 10))
+        if user == 7:
+            assert single == got[user] or differing
+    assert differing <= 2
+    assert got[3] == []                                 # the user without ratings: all scores 0
+    assert numpy.allclose([float(x) for x in report_again], fold["report"], rtol=1e-9, equal_nan=True)

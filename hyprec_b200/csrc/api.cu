@@ -216,7 +216,7 @@ struct Engine : EngineBase {
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
     static constexpr int kHeavyStream = 6;   // aux streams 0..5: degree buckets, 6: rows above the cap
-    DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk;
+    DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk, topk_spill;
 
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
     ~Engine() override {
@@ -226,7 +226,7 @@ struct Engine : EngineBase {
                          &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &w_hi, &w_lo, &l_hi, &l_lo, &cross, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
-                         &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf};
+                         &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf, &topk_spill};
         for (DevBuf* b : all) b->release();
         csr.release(); csc.release(); full.release(); test.release();
     }
@@ -1410,15 +1410,28 @@ struct Engine : EngineBase {
             int sort_size = 2;
             while (sort_size < cap) sort_size <<= 1;
             max_cand = std::max<int64_t>(max_cand, 1);
-            const hyprec::TopkLayout lay = hyprec::topk_layout((int)max_cand, k, sort_size, tc_dense);
-            if (lay.total > (size_t)h->max_smem)
-                return fail(HYPREC_E_UNSUPPORTED, "eval_topk: candidate list too long for one CTA's shared memory");
-            auto kern = hyprec::eval_topk_kernel<T>;
+            hyprec::TopkLayout lay = hyprec::topk_layout((int)max_cand, k, sort_size, tc_dense);
+            // Lists beyond one SM's shared memory (full catalogue / naive-split lists of a citeulike-sized item
+            // set): the per-candidate arrays go to a per-CTA global scratch, everything else stays in shared memory.
+            const bool spill = lay.total > (size_t)h->max_smem;
+            size_t spill_stride = 0;
+            if (spill) {
+                spill_stride = (lay.off_u + 255) & ~(size_t)255;         // keys, positions, float keys
+                lay = hyprec::topk_layout(0, k, sort_size, tc_dense);
+                if (lay.total > (size_t)h->max_smem)
+                    return fail(HYPREC_E_UNSUPPORTED, "eval_topk: n_factors / capacity too large for one CTA's shared memory");
+            }
+            auto kern = spill ? hyprec::eval_topk_kernel<T, true> : hyprec::eval_topk_kernel<T, false>;
             HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
             int per_sm = 0;
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, hyprec::kTopkThreads, lay.total));
             per_sm = std::max(per_sm, 1);
-            const int grid = (int)std::min<int64_t>(nu, (int64_t)per_sm * h->num_sms);
+            int grid = (int)std::min<int64_t>(nu, (int64_t)per_sm * h->num_sms);
+            if (spill) {
+                const size_t budget = (size_t)4 << 30;                   // scratch of all resident CTAs
+                grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid, budget / spill_stride));
+                HY_TRY(topk_spill.reserve(spill_stride * (size_t)grid));
+            }
             HY_TRY(out_idx.reserve(sizeof(int32_t) * (size_t)nu * cap));
             HY_TRY(out_val.reserve(sizeof(double) * (size_t)nu * cap));
             HY_TRY(out_hit.reserve(sizeof(double) * (size_t)nu * cap));
@@ -1448,6 +1461,8 @@ struct Engine : EngineBase {
             a.err_coef = 0.f;
             a.vmax = nullptr;
             a.fallbacks = nullptr;
+            a.spill = spill ? topk_spill.as<unsigned char>() : nullptr;
+            a.spill_stride = spill_stride;
             if (tc_dense) {
                 HY_TRY(vmax_buf.reserve(2 * sizeof(float)));
                 CU_TRY(cudaMemsetAsync(vmax_buf.ptr, 0, 2 * sizeof(float), h->stream));

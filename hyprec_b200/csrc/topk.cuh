@@ -85,6 +85,12 @@ struct TopkArgs {
     float err_coef;               // E = err_coef * ||u|| * vmax
     const float* vmax;            // max_i ||v_i||
     unsigned int* fallbacks;      // users that fell back to exact scoring (diagnostic)
+    // Candidate lists too long for one SM's shared memory (full catalogue of >~14 k items, naive-split
+    // lists): the three per-candidate arrays of each CTA live in this global scratch instead
+    // (spill_stride bytes per CTA, laid out like the head of TopkLayout; stays in L2 at catalogue sizes of
+    // tens of thousands); null => shared memory.
+    unsigned char* spill;
+    size_t spill_stride;
 };
 
 // order-preserving map double -> uint64 (larger score <=> larger key)
@@ -170,15 +176,20 @@ __device__ __forceinline__ KeyT radix_select(const KeyT* keys, int count, int kt
     return prefix;
 }
 
-template <typename T>
+template <typename T, bool kSpill = false>
 __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) {
     HYPREC_DYN_SMEM(smem_raw);
     __shared__ int s_digit, s_need, s_count, s_nsel;
     const bool prefilter = p.approx != nullptr;
-    const TopkLayout lay = topk_layout(p.max_cand, p.k, p.sort_size, prefilter);
-    unsigned long long* keys = (unsigned long long*)(smem_raw + lay.off_keys);
-    int* posarr = (int*)(smem_raw + lay.off_pos);
-    unsigned int* keys32 = (unsigned int*)(smem_raw + lay.off_k32);
+    // kSpill is a compile-time switch so that the shared-memory instantiation keeps shared-memory
+    // addressing (a run-time pointer select would turn every access into a generic load / store)
+    const TopkLayout lay = topk_layout(kSpill ? 0 : p.max_cand, p.k, p.sort_size, prefilter);
+    const TopkLayout big = topk_layout(p.max_cand, p.k, p.sort_size, prefilter);     // per-candidate arrays
+    unsigned char* big_raw = (unsigned char*)smem_raw;
+    if (kSpill) big_raw = p.spill + (size_t)blockIdx.x * p.spill_stride;
+    unsigned long long* keys = (unsigned long long*)(big_raw + big.off_keys);
+    int* posarr = (int*)(big_raw + big.off_pos);
+    unsigned int* keys32 = (unsigned int*)(big_raw + big.off_k32);
     double* uvec = (double*)(smem_raw + lay.off_u);
     unsigned long long* selkey = (unsigned long long*)(smem_raw + lay.off_selkey);
     int* selpos = (int*)(smem_raw + lay.off_selpos);

@@ -138,7 +138,7 @@ template <typename T>
 static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
                       const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
                       const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
-                      int grid, double prefilter_coef = 0.0) {
+                      int grid, double prefilter_coef = 0.0, bool spill = false) {
     std::vector<double> part(2 * (size_t)k), colsum(k);
     const int64_t per = (n + 1) / 2;
     emu::launch(dim3(2), dim3(64), 0, [&]() { colsum_partial_kernel<T>(V, n, k, per, part.data()); });
@@ -195,7 +195,18 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
     a.topk_idx = tidx; a.topk_val = tval; a.topk_hit = thit;
     a.approx = prefilter_coef > 0.0 ? approx.data() : nullptr; a.approx_ld = ld; a.unorm = unorm_v.data();
     a.err_coef = (float)prefilter_coef; a.vmax = vmax; a.fallbacks = reinterpret_cast<unsigned int*>(vmax + 1);
-    emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T>(a); });
+    a.spill = nullptr; a.spill_stride = 0;
+    if (!spill) {
+        emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T>(a); });
+        return;
+    }
+    // per-candidate arrays in a per-CTA "global" scratch, as api.cu sets it up for lists beyond shared memory
+    const size_t stride = (lay.off_u + 255) & ~(size_t)255;
+    std::vector<unsigned char> scratch(stride * (size_t)grid, 0xcd);
+    a.spill = scratch.data();
+    a.spill_stride = stride;
+    lay = topk_layout(0, k, sort_size, prefilter_coef > 0.0);
+    emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T, true>(a); });
 }
 
 extern "C" {
@@ -234,6 +245,14 @@ void emu_eval_prefilter_f64(const double* U, const double* V, int64_t m, int64_t
                             const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
                             int grid, double prefilter_coef) {
     eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid, prefilter_coef);
+}
+
+void emu_eval_spill_f64(const double* U, const double* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
+                        const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
+                        const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
+                        int grid, double prefilter_coef) {
+    eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid, prefilter_coef,
+                      true);
 }
 
 void emu_predict_f64(const double* U, const double* V, int64_t m, int64_t n, int k, double* out) {

@@ -234,3 +234,53 @@ def test_nz_flags_kernel(emu, als_cases):
                          u.shape[1], _ptr(thr), I64(0), I64(u.shape[0]), _ptr(flags))
     rows = numpy.repeat(numpy.arange(u.shape[0]), numpy.diff(csr.indptr))
     assert numpy.array_equal(flags, (pred[rows, csr.indices] >= thr[rows]).astype(numpy.uint8))
+
+
+@pytest.mark.parametrize("coef", [0.0, 1e-6, 0.5])
+def test_eval_kernel_spilled_candidate_arrays(emu, als_cases, coef):
+    """Candidate lists that do not fit shared memory keep their per-candidate arrays in a per-CTA global
+    scratch (TopkArgs::spill): same lists as the streamed reference with exact scoring (coef 0), through
+    the pre-filter with a tight bound, and with a useless bound (fallback to exact scoring) -- tied scores
+    across the cut-off, full catalogue and explicit lists, and the naive split's lists of ids 0/1."""
+    rs = numpy.random.RandomState(17)
+    m, n, k, cap = 6, 1500, 6, 20
+    u = numpy.round((rs.rand(m, k) - 0.3) * 4) / 4
+    v = numpy.round((rs.rand(n, k) - 0.3) * 4) / 4
+    u[2] = 0
+    full = (rs.rand(m, n) < 0.2).astype(numpy.float64)
+
+    def run(u, v, full, cands, cap):
+        m, n = full.shape
+        csr = oals.to_csr(full)
+        fp, fi, fv = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
+        if cands is None:
+            cp = ci = None
+        else:
+            cp = numpy.zeros(m + 1, numpy.int64)
+            cp[1:] = numpy.cumsum([len(c) for c in cands])
+            ci = numpy.concatenate(cands).astype(numpy.int32)
+        thr = numpy.zeros(m)
+        tidx = numpy.zeros((m, cap), numpy.int32)
+        tval, thit = numpy.zeros((m, cap)), numpy.zeros((m, cap))
+        emu.emu_eval_spill_f64(_ptr(u), _ptr(v), I64(m), I64(n), u.shape[1], I64(0), I64(m), _ptr(cp), _ptr(ci), cap,
+                               _ptr(fp), _ptr(fi), _ptr(fv), _ptr(thr), None, _ptr(tidx), _ptr(tval), _ptr(thit),
+                               3, DBL(coef))
+        return tidx, tval, thit
+
+    for cands in (None, [rs.randint(0, n, size=1200) for _ in range(m)]):
+        tidx, tval, _ = run(u, v, full, cands, cap)
+        for u_id in range(m):
+            ids = numpy.arange(n) if cands is None else cands[u_id]
+            want, vals = oev.top_recommendations_stream(ids, u[u_id].dot(v[ids].T), cap)
+            assert list(tidx[u_id][:len(want)]) == want, (coef, u_id)
+            assert numpy.allclose(tval[u_id][:len(want)], vals, rtol=1e-12, atol=1e-15)
+    g = als_cases["als_naive_toy"]
+    fold = golden_folds(g)[0]
+    cands = split_lists(fold["cand_ids"], fold["cand_len"])
+    tidx, _, thit = run(fold["u"], fold["v"], g["ratings"].astype(numpy.float64), cands, 200)
+    want = split_lists(fold["rec_ids"], fold["rec_len"])
+    ref = oev.evaluation_report(fold["u"], fold["v"], g["ratings"], fold["train"], fold["test"], cands)
+    for u_id, w in enumerate(want):
+        assert list(tidx[u_id][:len(w)]) == list(w)
+        assert numpy.all(tidx[u_id][len(w):] == -1)
+        assert numpy.array_equal(thit[u_id][:len(w)], ref["hits"][u_id])

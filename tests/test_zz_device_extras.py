@@ -112,3 +112,27 @@ def test_batched_dump_matches_per_user_lists(als_cases, tmp_path):
     assert differing <= 2
     assert got[3] == []                                 # the user without ratings: all scores 0
     assert numpy.allclose([float(x) for x in report_again], fold["report"], rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("n,use_tc,lists", [(17000, "1", "all"), (30000, "0", "all"), (17000, "1", "explicit"),
+                                             (30000, "0", "explicit")])
+def test_candidate_lists_beyond_shared_memory(monkeypatch, n, use_tc, lists):
+    """Full catalogue / long explicit lists of a citeulike-sized item set (recommend_items and
+    dump_recommendations at n = 16 980, the naive split's lists): the per-candidate arrays of the top-k kernel
+    spill to a per-CTA global scratch (16 B per candidate with the tensor-core pre-filter, 8 B without)."""
+    from hyprec_b200 import _native as native
+    from test_gpu_parity import check_eval, make_handle, synthetic
+    monkeypatch.setenv("HYPREC_TC", use_tc)
+    m, k = 24, 16
+    full, train, test, u0, v0, _ = synthetic(m, n, k, 3000, seed=n // 1000)
+    rs = numpy.random.RandomState(n)
+    cands = None if lists == "all" else [rs.randint(0, n, size=n - 7 * u) for u in range(m)]     # with repeats
+    h, _ = make_handle(native, train)
+    try:
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        u, v = h.get_factors()
+        check_eval(native, h, full, train, test, u, v, cands, 200)
+    finally:
+        h.close()

@@ -45,28 +45,44 @@ def _cell_keys(indptr, indices, n_items):
     return rows * n_items + numpy.asarray(indices, dtype=numpy.int64)
 
 
-def flags_at(matrix, train_pattern, train_flags, test_pattern, test_flags):
-    """Rounded predictions (0/1) at the non-zeros of ``matrix``, looked up among the cells the device
-    reported (the train and the test positives).  Returns None when some cell was not reported."""
-    n_items = matrix.shape[1]
-    keys = numpy.concatenate([_cell_keys(train_pattern[0], train_pattern[1], n_items),
-                              _cell_keys(test_pattern[0], test_pattern[1], n_items)])
+class CellSet(object):
+    """The non-zero cells of a users x items matrix as sorted ``row * n_items + col`` keys, with the denominator
+    ``sum(sum(matrix))`` of evaluator.py:266.  Built once per sweep for the matrices every model is judged on."""
+
+    def __init__(self, matrix):
+        matrix = numpy.asarray(matrix)
+        self.n_items = matrix.shape[1]
+        rows, cols = numpy.nonzero(matrix)
+        self.keys = rows.astype(numpy.int64) * self.n_items + cols.astype(numpy.int64)
+        self.total = sum(sum(matrix))
+
+
+def flags_at(cells, train_pattern, train_flags, test_pattern, test_flags):
+    """Rounded predictions (0/1) at the cells of ``cells`` (a CellSet or a matrix), looked up among the cells the
+    device reported (the train and the test positives).  Returns None when some cell was not reported."""
+    if not isinstance(cells, CellSet):
+        cells = CellSet(cells)
+    keys = numpy.concatenate([_cell_keys(train_pattern[0], train_pattern[1], cells.n_items),
+                              _cell_keys(test_pattern[0], test_pattern[1], cells.n_items)])
     flags = numpy.concatenate([numpy.asarray(train_flags, dtype=numpy.uint8),
                                numpy.asarray(test_flags, dtype=numpy.uint8)])
     order = numpy.argsort(keys, kind='stable')
     keys, flags = keys[order], flags[order]
-    rows, cols = numpy.nonzero(numpy.asarray(matrix))
-    wanted = rows.astype(numpy.int64) * n_items + cols.astype(numpy.int64)
+    wanted = cells.keys
+    if len(wanted) == 0:
+        return numpy.zeros(0, dtype=numpy.uint8)
     pos = numpy.searchsorted(keys, wanted)
-    if len(wanted) and (len(keys) == 0 or pos.max() >= len(keys) or not numpy.array_equal(keys[pos], wanted)):
+    if len(keys) == 0 or pos.max() >= len(keys) or not numpy.array_equal(keys[pos], wanted):
         return None
-    return flags[pos] if len(wanted) else numpy.zeros(0, dtype=numpy.uint8)
+    return flags[pos]
 
 
-def recall_from_flags(matrix, flags):
+def recall_from_flags(cells, flags):
     """evaluator.py:263-266 -- ``sum(rounded[ratings.nonzero()]) / sum(sum(ratings))``."""
+    if not isinstance(cells, CellSet):
+        cells = CellSet(cells)
     with numpy.errstate(divide='ignore', invalid='ignore'):
-        return numpy.float64(int(flags.sum(dtype=numpy.int64))) / sum(sum(matrix))
+        return numpy.float64(int(flags.sum(dtype=numpy.int64))) / cells.total
 
 
 class GridSearch(object):
@@ -195,21 +211,21 @@ class GridSearch(object):
             from hyprec_b200.abstract_recommender import REPORT_FORMAT
             print(REPORT_FORMAT.format(*report))
         details = rec.last_report_details
-        ratings = rec.get_ratings()
-        lookups = [flags_at(matrix, rec._train_pattern, details["train_flags"], rec._test_pattern,
-                            details["test_flags"]) for matrix in (naive_test, ratings)]
+        cells = shared['cells']          # (naive test split, full ratings) of grid_search.py:74-75
+        lookups = [flags_at(c, rec._train_pattern, details["train_flags"], rec._test_pattern, details["test_flags"])
+                   for c in cells]
         if lookups[0] is None or lookups[1] is None:
             rounded = rec.rounded_predictions()
-            return report, self.evaluator.calculate_recall(ratings, rounded), \
+            return report, self.evaluator.calculate_recall(rec.get_ratings(), rounded), \
                 self.evaluator.calculate_recall(naive_test, rounded)
-        return report, recall_from_flags(ratings, lookups[1]), recall_from_flags(naive_test, lookups[0])
+        return report, recall_from_flags(cells[1], lookups[1]), recall_from_flags(cells[0], lookups[0])
 
     def _sweep_device(self, combos):
         rec0 = self.recommender
         rank, world = rec0._world() if hasattr(rec0, '_world') else (0, 1)
         with _RNG_LOCK:
             naive_train, naive_test = rec0.evaluator.naive_split(rec0._split_type)       # :59
-            shared = dict(split=None, last_state={})
+            shared = dict(split=None, last_state={}, cells=(CellSet(naive_test), CellSet(rec0.get_ratings())))
             if rec0.evaluator.random_seed is False:
                 shared['split'] = (naive_train, naive_test, numpy.random.get_state())
         mine = list(range(rank, len(combos), world))

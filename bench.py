@@ -419,8 +419,16 @@ def our_arm(args, wl):
             "deg x deg low-rank systems in concurrent degree buckets + direct k x k for heavy rows"
             if lowrank else "direct k x k systems, 2 launches")
         bound, peak_used, peak_src = "%s_fma" % args.precision, peak, "hyprec_probe_fma_tflops on this GPU (FMA chains, best of 4)"
+    # DRAM bytes of the row-solve launches of one epoch, from the ncu capture of this workload in this mode
+    traffic, traffic_src = None, None
+    if wl["name"] == "citeulike-a" and args.precision == "fp64" and lowrank:
+        traffic = 118.7e6
+        traffic_src = ("ncu dram__bytes_read.sum + dram__bytes_write.sum over the 12 als_solve_rows_kernel launches of one "
+                       "epoch, profiles/r01_solve_f64_lowrank_traffic.md (algorithmic: hbm.algorithmic_bytes; the gathers "
+                       "are served by L2)")
     roofline = dict(kernel=kernel_desc, bound=bound, achieved=achieved, peak=peak_used, unit="TFLOP/s",
-                    frac=achieved / peak_used if peak_used else None, peak_source=peak_src, traffic=None,
+                    frac=achieved / peak_used if peak_used else None, peak_source=peak_src, traffic=traffic,
+                    traffic_source=traffic_src,
                     simt_fma_peak=peak, simt_fma_frac=achieved / peak if peak else None,
                     flops_per_epoch=solve_flops, flops_model="low-rank (sum d^2 k + d^3/3 + 4 d k)" if lowrank else
                     "SURVEY 8d direct formula", direct_formula_flops=work["solve_flops_per_epoch"],

@@ -140,10 +140,17 @@ class CollaborativeFiltering(AbstractRecommender):
         AbstractRecommender.set_data(self, train_data, test_data)
         self._sync_token = None
 
+    def _host_csr(self, matrix):
+        """CSR triplet of a dense / sparse users x items matrix: the evaluator's own view when it built the
+        matrix (hyprec_b200.Evaluator.csr_view, validated against the array), else a scan."""
+        view = getattr(self.evaluator, 'csr_view', None)
+        triplet = view(matrix) if view is not None and isinstance(matrix, numpy.ndarray) else None
+        return triplet if triplet is not None else _csr_triplet(matrix)
+
     def _upload_train(self):
         h = self.device()
         if self._train_uploaded is not self.train_data:
-            indptr, indices, values = _csr_triplet(self.train_data)
+            indptr, indices, values = self._host_csr(self.train_data)
             h.set_train_csr(self.n_users, self.n_items, indptr, indices, values)
             self._train_nnz = len(indices)
             self._train_pattern = (indptr, indices)      # order of the device's train flags
@@ -157,8 +164,8 @@ class CollaborativeFiltering(AbstractRecommender):
         h = self._upload_train()
         key = (self.ratings, self.test_data)
         if self._eval_uploaded is None or self._eval_uploaded[0] is not key[0] or self._eval_uploaded[1] is not key[1]:
-            full = _csr_triplet(self.ratings)
-            test = _csr_triplet(self.test_data)
+            full = self._host_csr(self.ratings)
+            test = self._host_csr(self.test_data)
             h.set_eval_csr(full, test)
             self._test_nnz = len(test[1])
             self._test_pattern = (test[0], test[1])      # order of the device's test flags
@@ -340,7 +347,7 @@ class CollaborativeFiltering(AbstractRecommender):
 
     def _shard_bounds(self, world):
         from hyprec_b200 import distributed
-        indptr, indices, _ = _csr_triplet(self.train_data)
+        indptr, indices, _ = self._host_csr(self.train_data)
         users = distributed.partition_rows(indptr, world, self.n_factors)
         items = distributed.partition_rows(distributed.csc_indptr(indptr, indices, self.n_items), world, self.n_factors)
         return users, items
@@ -458,8 +465,8 @@ class CollaborativeFiltering(AbstractRecommender):
         users, _ = self._shard_bounds(world)
         lo, hi = users[rank], users[rank + 1]
         cand_indptr, cand_ids = self.candidate_lists(fold)
-        train_ptr = _csr_triplet(self.train_data)[0]
-        test_ptr = _csr_triplet(self.test_data)[0]
+        train_ptr = self._host_csr(self.train_data)[0]
+        test_ptr = self._host_csr(self.test_data)[0]
         part = h.eval_topk(self.n_recommendations, cand_indptr[lo:hi + 1] - cand_indptr[lo],
                            cand_ids[cand_indptr[lo]:cand_indptr[hi]], lo, hi,
                            n_train_nz=int(train_ptr[hi] - train_ptr[lo]), n_test_nz=int(test_ptr[hi] - test_ptr[lo]))
@@ -508,7 +515,7 @@ class CollaborativeFiltering(AbstractRecommender):
         rmse = h.rmse()
 
         lengths = (out["topk_idx"] >= 0).sum(axis=1)
-        recs = [[int(i) for i in row[:n]] for row, n in zip(out["topk_idx"], lengths)]
+        recs = [row[:n].tolist() for row, n in zip(out["topk_idx"], lengths)]
         hits = out["topk_hit"]
         self.evaluator.recommendation_indices = recs
         self.evaluator.recs_loaded = True

@@ -73,13 +73,16 @@ class Evaluator(object):
         csr = self.ratings_csr()
         test = numpy.zeros(self.ratings.shape)
         train = self.ratings.copy()
+        keys = []
         for user in range(self.n_users):
             non_zeros = csr.indices[csr.indptr[user]:csr.indptr[user + 1]]
             # sampling WITH replacement, evaluator.py:92-93
             picked = numpy.random.choice(non_zeros, size=int(self.test_percentage * len(non_zeros)))
             train[user, picked] = 0.
             test[user, picked] = self.ratings[user, picked]
+            keys.append(user * self.n_items + picked.astype(numpy.int64))
         self.test_indices = test
+        self._remember_csr(train, test, numpy.concatenate(keys) if keys else numpy.zeros(0, dtype=numpy.int64))
         return train, test
 
     def naive_split_items(self):
@@ -132,14 +135,60 @@ class Evaluator(object):
 
     def generate_kfold_matrix(self, test_indices):
         """train = ratings with the listed cells zeroed, test = ratings on the listed cells
-        (evaluator.py:206-213)."""
-        train = numpy.array(self.ratings, dtype=numpy.float64)
-        test = numpy.zeros(self.ratings.shape)
-        for user in range(self.n_users):
-            cols = numpy.asarray(test_indices[user], dtype=numpy.int64)
-            test[user, cols] = self.ratings[user, cols]
-            train[user, cols] = 0
+        (evaluator.py:206-213).  Only listed cells that hold a rating change anything, so they are found with one
+        gather and written with one scatter; the CSR forms of both matrices fall out of the same cell set and are
+        kept for ``csr_view`` (the device wants CSR; re-scanning two dense m x n matrices per fold costs more than
+        the epochs)."""
+        ratings = numpy.asarray(self.ratings)
+        lengths = [len(x) for x in test_indices]
+        rows = numpy.repeat(numpy.arange(self.n_users, dtype=numpy.int64), lengths)
+        cols = (numpy.concatenate([numpy.asarray(x, dtype=numpy.int64) for x in test_indices])
+                if len(rows) else numpy.zeros(0, dtype=numpy.int64))
+        values = ratings[rows, cols]
+        rated = values != 0
+        rows, cols, values = rows[rated], cols[rated], values[rated]
+        train = numpy.array(ratings, dtype=numpy.float64)
+        test = numpy.zeros(ratings.shape)
+        test[rows, cols] = values
+        train[rows, cols] = 0
+        self._remember_csr(train, test, rows * self.n_items + cols)
         return train, test
+
+    # ------------------------------------------------------------------ CSR views of the dense matrices
+    def _remember_csr(self, train, test, test_keys):
+        full = self.ratings_csr()
+        full_rows = numpy.repeat(numpy.arange(self.n_users, dtype=numpy.int64), numpy.diff(full.indptr))
+        full_keys = full_rows * self.n_items + full.indices
+        in_test = numpy.zeros(full.nnz, dtype=bool)
+        if len(test_keys):
+            in_test[numpy.searchsorted(full_keys, numpy.unique(test_keys))] = True
+        views = []
+        for dense, mask in ((train, ~in_test), (test, in_test)):
+            indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
+            numpy.cumsum(numpy.bincount(full_rows[mask], minlength=self.n_users), out=indptr[1:])
+            views.append((dense, (indptr, full.indices[mask].astype(numpy.int32), full.data[mask].astype(numpy.float64))))
+        self._csr_views = views
+
+    def csr_view(self, matrix):
+        """(indptr int64, indices int32, values float64) of ``matrix`` when it is the ratings matrix or one of the
+        matrices of the latest fold AND still holds exactly those entries (same number of non-zeros, same values
+        at the recorded cells: an in-place edit by the caller is noticed); None otherwise."""
+        triplet = None
+        if matrix is self.ratings and isinstance(matrix, numpy.ndarray):
+            csr = self.ratings_csr()
+            triplet = (csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64))
+        for dense, view in getattr(self, '_csr_views', []):
+            if matrix is dense:
+                triplet = view
+        if triplet is None:
+            return None
+        indptr, indices, values = triplet
+        if numpy.count_nonzero(matrix) != len(indices):
+            return None
+        rows = numpy.repeat(numpy.arange(matrix.shape[0], dtype=numpy.int64), numpy.diff(indptr))
+        if not numpy.array_equal(matrix[rows, indices], values):
+            return None
+        return triplet
 
     # ------------------------------------------------------------------ top-k (:215-234)
     def candidate_lists(self, fold):

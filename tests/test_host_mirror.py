@@ -126,3 +126,37 @@ def test_model_initializer_roundtrip(tmp_path):
     assert found and numpy.array_equal(loaded, matrix)
     found, fresh = init.load_matrix({'n_factors': 3, '_lambda': 0.01}, 'missing', (4, 3))
     assert not found and fresh.shape == (4, 3)
+
+
+def test_fold_matrices_and_csr_views_match_the_literal_construction():
+    """generate_kfold_matrix (vectorised) against the per-user loop of evaluator.py:206-213, with non-binary
+    ratings and repeated / unrated ids in the lists; csr_view returns exactly what a scan of the dense matrices
+    gives and refuses a matrix that was edited in place."""
+    from hyprec_b200.collaborative_filtering import _csr_triplet
+    rs = numpy.random.RandomState(8)
+    m, n = 31, 57
+    ratings = (rs.rand(m, n) < 0.3) * rs.randint(1, 4, size=(m, n)).astype(numpy.float64)
+    ratings[4, :] = 0
+    ev = Evaluator(ratings)
+    ev.set_kfolds(3)
+    lists = [rs.randint(0, n, size=int(rs.randint(0, 25))) for _ in range(m)]
+    train, test = ev.generate_kfold_matrix(lists)
+    want_train, want_test = numpy.array(ratings, dtype=numpy.float64), numpy.zeros(ratings.shape)
+    for user in range(m):
+        want_test[user, lists[user]] = ratings[user, lists[user]]
+        want_train[user, lists[user]] = 0
+    assert numpy.array_equal(train, want_train) and numpy.array_equal(test, want_test)
+    for matrix in (train, test, ratings):
+        got, want = ev.csr_view(matrix), _csr_triplet(matrix)
+        assert got is not None
+        for a, b in zip(got, want):
+            assert a.dtype == b.dtype and numpy.array_equal(a, b)
+    assert ev.csr_view(train.copy()) is None                 # not the object the evaluator built
+    r, c = numpy.argwhere(train != 0)[0]
+    train[r, c] = 7.0                                        # value edited in place
+    assert ev.csr_view(train) is None
+    train[r, c] = want_train[r, c]
+    assert ev.csr_view(train) is not None
+    zr, zc = numpy.argwhere(train == 0)[0]
+    train[zr, zc] = 1.0                                      # entry added in place
+    assert ev.csr_view(train) is None

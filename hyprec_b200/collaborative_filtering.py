@@ -492,16 +492,39 @@ class CollaborativeFiltering(AbstractRecommender):
         test_likes = numpy.asarray(self.test_data.sum(axis=1)).ravel()
         return {x: metrics.recall_at_x(x, hits, test_likes) for x in cutoffs}
 
+    def _report_factors(self):
+        """Hybrid recommender (``is_hybrid``): the blended scores of collaborative_filtering.py:271-279 as one
+        low-rank product ``W_u W_v^T`` (hyprec_b200/hybrid.py), so that the report runs on the device like the
+        plain collaborative one instead of on three dense m x n matrices.  Opt-in (``HYPREC_HYBRID_LOWRANK=1``)
+        and only when the content model exposes the topic matrix its predictions are built from; None otherwise
+        (the dense host path of the reference is used)."""
+        if os.environ.get("HYPREC_HYBRID_LOWRANK", "0") != "1":
+            return None
+        content = getattr(self, 'item_based_recommender', None)
+        theta = getattr(content, 'document_distribution', None)
+        if theta is None:                   # the content model would draw a random topic matrix (content_based.py:105-106)
+            return None
+        from hyprec_b200 import hybrid
+        indptr, indices, values = self._host_csr(self.train_data)
+        train = sp.csr_matrix((values, indices, indptr), shape=(self.n_users, self.n_items))
+        w_u, w_v, _, _ = hybrid.blended_factors(train, theta, self.user_vecs, self.item_vecs)
+        return w_u, w_v
+
     def get_evaluation_report(self):
         """abstract_recommender.py:100-131.  Scores never leave the GPU: the device returns row
         thresholds, per-row counts of rounded ones, the streamed top-200 of every user's candidate
         list with hit flags, and the rounded prediction at every train / test positive; the metric
         arithmetic is then the reference's."""
-        if self._is_hybrid:
+        blended = self._report_factors() if self._is_hybrid else None
+        if self._is_hybrid and blended is None:
             return AbstractRecommender.get_evaluation_report(self)
         fold = self.hyperparameters['fold']
         h = self._upload_eval()
-        self._upload_factors()
+        if blended is None:
+            self._upload_factors()
+        else:                               # hybrid scores as one low-rank product (hyprec_b200/hybrid.py)
+            h.set_factors(*blended)
+            self._sync_token = None         # the device no longer holds user_vecs / item_vecs
         rank, world = self._world()
         if world == 1:
             key = (self.evaluator.test_indices, fold)

@@ -60,3 +60,107 @@ def test_constant_feature_is_handled():
     item_based[:] = 0.25            # e.g. a content model that was never trained
     blended = LinearRegression(train, test, item_based, collaborative).train()
     assert numpy.all(numpy.isfinite(blended))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# low-rank form of the hybrid scores (hyprec_b200/hybrid.py)
+# ---------------------------------------------------------------------------------------------------------
+def _lowrank_case(seed, m=37, n=64, k=6, topics=5):
+    rs = numpy.random.RandomState(seed)
+    train = (rs.rand(m, n) < 0.1).astype(numpy.float64)
+    train[3, :] = 0
+    theta = rs.dirichlet(numpy.full(topics, 0.3), size=n)
+    theta[7] = 1.0 / topics                 # constant row: zero after centring, never normalised (:111-113)
+    return train, theta, rs.rand(m, k), rs.rand(n, k)
+
+
+def _dense_content(train, theta):
+    """content_based.py:104-117, literally."""
+    v = theta.copy()
+    for item in range(v.shape[0]):
+        mean = numpy.mean(v[item])
+        v[item] -= mean
+        item_norm = numpy.sqrt(v[item].dot(v[item]))
+        if item_norm > 1e-6:
+            v[item] /= item_norm
+    weighted = train.dot(v).dot(v.T)
+    weights = v.dot(v.T.dot(numpy.ones((v.shape[0],))))
+    with numpy.errstate(divide='ignore', invalid='ignore'):
+        predictions = weighted / weights
+    predictions[~numpy.isfinite(predictions)] = 0.0
+    return predictions
+
+
+@pytest.mark.parametrize("seed", [0, 4])
+def test_lowrank_blend_equals_the_dense_blend(seed):
+    from hyprec_b200 import hybrid
+    train, theta, u, v = _lowrank_case(seed)
+    p, a = hybrid.content_factors(train, theta)
+    content = _dense_content(train, theta)
+    assert numpy.allclose(p.dot(a.T), content, rtol=1e-10, atol=1e-12)
+    dense = LinearRegression(train, train, content, u.dot(v.T))
+    want = dense.train()
+    c1, c2, intercept = hybrid.blend_coefficients(p, a, u, v, train)
+    assert abs(c1 - dense.regression_coef1) < 1e-8 * max(1, abs(dense.regression_coef1))
+    assert abs(c2 - dense.regression_coef2) < 1e-8 * max(1, abs(dense.regression_coef2))
+    assert abs(intercept - dense.intercept) < 1e-8
+    w_u, w_v, _, _ = hybrid.blended_factors(train, theta, u, v)
+    assert w_u.shape == (train.shape[0], u.shape[1] + theta.shape[1]) and w_v.shape[0] == train.shape[1]
+    assert numpy.allclose(w_u.dot(w_v.T), want, rtol=1e-8, atol=1e-10)
+
+
+def test_lowrank_blend_zero_weight_items_score_zero():
+    from hyprec_b200 import hybrid
+    train, theta, u, v = _lowrank_case(2)
+    theta[:] = 1.0 / theta.shape[1]          # every row constant: V^ = 0, all weights 0, content scores all 0
+    p, a = hybrid.content_factors(train, theta)
+    assert numpy.all(a == 0) and numpy.all(_dense_content(train, theta) == 0)
+    w_u, w_v, c1, c2 = hybrid.blended_factors(train, theta, u, v)
+    assert numpy.all(numpy.isfinite(w_u)) and numpy.all(numpy.isfinite(w_v))
+
+
+def test_lowrank_blend_matches_reference_classes_when_available():
+    from oracle import reference_loader
+    if not reference_loader.reference_available():
+        pytest.skip("reference tree not present")
+    pytest.importorskip("sklearn.linear_model")
+    import importlib
+    from hyprec_b200 import hybrid
+    reference_loader.load_reference()
+    ContentBased = importlib.import_module("lib.content_based").ContentBased
+    RefLinearRegression = importlib.import_module("lib.linear_regression").LinearRegression
+    train, theta, u, v = _lowrank_case(9)
+    content = ContentBased.__new__(ContentBased)              # no constructor: it needs an abstracts preprocessor
+    content.predictions = None
+    content.document_distribution = theta.copy()
+    content.train_data = train
+    content.n_items, content.n_factors = theta.shape
+    with numpy.errstate(divide='ignore', invalid='ignore'):
+        want_content = content.get_predictions()
+    want = RefLinearRegression(train, train, want_content, u.dot(v.T)).train()
+    w_u, w_v, _, _ = hybrid.blended_factors(train, theta, u, v)
+    assert numpy.allclose(w_u.dot(w_v.T), want, rtol=1e-8, atol=1e-10)
+
+
+def test_class_hands_blended_factors_to_the_report_only_when_asked(monkeypatch):
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
+    train, theta, u, v = _lowrank_case(6)
+    hyper = {'n_factors': u.shape[1], '_lambda': 0.01}
+    cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), 1), Evaluator(train.copy()), hyper,
+                                {'k_folds': 5, 'n_iterations': 1}, load_matrices=False, dump_matrices=False, is_hybrid=True)
+
+    class Content(object):
+        document_distribution = theta
+
+    cf.set_item_based_recommender(Content())
+    cf.set_data(train, numpy.zeros(train.shape))
+    cf.user_vecs, cf.item_vecs = u, v
+    monkeypatch.delenv("HYPREC_HYBRID_LOWRANK", raising=False)
+    assert cf._report_factors() is None                       # default: the reference's dense host path
+    monkeypatch.setenv("HYPREC_HYBRID_LOWRANK", "1")
+    w_u, w_v = cf._report_factors()
+    want = LinearRegression(train, train, _dense_content(train, theta), u.dot(v.T)).train()
+    assert numpy.allclose(w_u.dot(w_v.T), want, rtol=1e-8, atol=1e-10)
+    assert w_u.flags.c_contiguous and w_v.flags.c_contiguous and w_u.dtype == numpy.float64
+    Content.document_distribution = None
+    assert cf._report_factors() is None

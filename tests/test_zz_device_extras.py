@@ -136,3 +136,46 @@ def test_candidate_lists_beyond_shared_memory(monkeypatch, n, use_tc, lists):
         check_eval(native, h, full, train, test, u, v, cands, 200)
     finally:
         h.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HYPREC_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: the low-rank hybrid report is opt-in "
+                           "(HYPREC_HYBRID_LOWRANK=1) until this test has run on a B200 (HYPREC_RUN_UNVERIFIED=1)")
+def test_hybrid_report_from_blended_factors(als_cases, monkeypatch):
+    """is_hybrid report through the device with the blended low-rank factors == the reference's dense host flow."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer, synth
+    g = als_cases["als_kfold_toy"]
+    fold = golden_folds(g)[0]
+    theta = synth.dirichlet_theta(g["ratings"].shape[1], 6, seed=11)
+    hyper = {'n_factors': int(g["k"]), '_lambda': float(g["lam"])}
+    options = {'k_folds': int(g["k_folds"]), 'n_iterations': 1}
+
+    class Content(object):
+        def __init__(self):
+            self.document_distribution = theta
+            self.predictions = None
+
+        def set_data(self, train, test):
+            self.train_data = train
+
+        def get_predictions(self):
+            from hyprec_b200 import hybrid
+            p, a = hybrid.content_factors(self.train_data, self.document_distribution)
+            return p.dot(a.T)
+
+    reports = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("HYPREC_HYBRID_LOWRANK", mode)
+        ev = Evaluator(g["ratings"])
+        cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), 1), ev, hyper, options, load_matrices=False,
+                                    dump_matrices=False, is_hybrid=True)
+        cf.set_item_based_recommender(Content())
+        lists = ev.get_kfold_indices()
+        cf.set_data(*ev.get_fold(0, lists))
+        cf.hyperparameters['fold'] = 0
+        cf.user_vecs, cf.item_vecs = fold["u"].copy(), fold["v"].copy()
+        try:
+            reports[mode] = numpy.array([float(x) for x in cf.get_evaluation_report()])
+        finally:
+            cf.close()
+    assert numpy.allclose(reports["1"], reports["0"], rtol=1e-8, equal_nan=True), (reports["1"], reports["0"])

@@ -477,8 +477,20 @@ def our_arm(args, wl):
                                "the per-kernel times",
                 rmse=rmse,
                 recall_at_200=recall200, setup_s=wl["setup_s"])
+    # recall@{50..300} of the final model (BASELINE.json configs[1]), from one more untimed pass that keeps the top
+    # 300 of every candidate list; computed last and guarded: nothing above depends on it
+    if has_eval:
+        try:
+            top300 = h.eval_topk(300, None, None, want_counts=False)
+            line["recall_at"] = {str(x): float(hm.recall_at_x(x, top300["topk_hit"], test_likes))
+                                 for x in (50, 100, 150, 200, 250, 300)}
+        except Exception as exc:
+            line["recall_at"] = dict(error=repr(exc))
     print(json.dumps(line))
-    h.close()
+    try:
+        h.close()
+    except Exception:
+        pass
 
 
 def sharded_roofline(wl, precision, world, solve_ms):

@@ -284,3 +284,35 @@ def test_eval_kernel_spilled_candidate_arrays(emu, als_cases, coef):
         assert list(tidx[u_id][:len(w)]) == list(w)
         assert numpy.all(tidx[u_id][len(w):] == -1)
         assert numpy.array_equal(thit[u_id][:len(w)], ref["hits"][u_id])
+
+
+@pytest.mark.parametrize("coef", [0.0, 1e-6])
+def test_eval_kernel_capacity_300(emu, coef):
+    """Top-300 (sort size 512) of lists longer than the capacity, exact and through the pre-filter: what bench.py's
+    recall@{50..300} pass and recall_at_cutoffs ask for."""
+    rs = numpy.random.RandomState(23)
+    m, n, k, cap = 5, 2000, 6, 300
+    u = numpy.round((rs.rand(m, k) - 0.3) * 8) / 8
+    v = numpy.round((rs.rand(n, k) - 0.3) * 8) / 8
+    full = (rs.rand(m, n) < 0.2).astype(numpy.float64)
+    csr = oals.to_csr(full)
+    fp, fi, fv = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
+    cands = [rs.permutation(n)[:1700] for _ in range(m)]
+    cp = numpy.zeros(m + 1, numpy.int64)
+    cp[1:] = numpy.cumsum([len(c) for c in cands])
+    ci = numpy.concatenate(cands).astype(numpy.int32)
+    thr = numpy.zeros(m)
+    tidx = numpy.zeros((m, cap), numpy.int32)
+    tval, thit = numpy.zeros((m, cap)), numpy.zeros((m, cap))
+    fn = emu.emu_eval_prefilter_f64 if coef > 0 else None
+    if fn is None:
+        emu.emu_eval_f64(_ptr(u), _ptr(v), I64(m), I64(n), k, I64(0), I64(m), _ptr(cp), _ptr(ci), cap,
+                         _ptr(fp), _ptr(fi), _ptr(fv), _ptr(thr), None, _ptr(tidx), _ptr(tval), _ptr(thit), 3)
+    else:
+        fn(_ptr(u), _ptr(v), I64(m), I64(n), k, I64(0), I64(m), _ptr(cp), _ptr(ci), cap,
+           _ptr(fp), _ptr(fi), _ptr(fv), _ptr(thr), None, _ptr(tidx), _ptr(tval), _ptr(thit), 3, DBL(coef))
+    for u_id in range(m):
+        want, vals = oev.top_recommendations_stream(cands[u_id], u[u_id].dot(v[cands[u_id]].T), cap)
+        assert len(want) == cap
+        assert list(tidx[u_id]) == want, (coef, u_id)
+        assert numpy.allclose(tval[u_id], vals, rtol=1e-12, atol=1e-15)

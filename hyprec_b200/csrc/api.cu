@@ -126,6 +126,7 @@ struct hyprec_ctx {
     int max_smem = 0;
     int64_t launches = 0;
     bool lowrank_enabled = true;   // HYPREC_LOWRANK=0 forces the direct k x k path
+    int lowrank_cap = 0;           // HYPREC_LOWRANK_CAP=<deg>: rows with more positives go to the direct path (0: largest bucket that fits)
     bool tc_enabled = true;        // HYPREC_TC=0 keeps the score sweep on the SIMT kernel
     bool rmse_fused_enabled = true; // HYPREC_RMSE_FUSED=0: the RMSE cross term always comes from a pass over the positives
     bool tc_multi_enabled = true;  // HYPREC_TC_MULTI=0: systems of <= 128 rows stay on the shared-memory tile kernel
@@ -968,7 +969,8 @@ struct Engine : EngineBase {
                 HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
                                    nullptr, nullptr, hi - lo, h->stream, 0, 8, tc_direct));
         } else {
-            const int cap = std::min(k, kBucketDim[usable_buckets() - 1]);
+            int cap = std::min(k, kBucketDim[usable_buckets() - 1]);
+            if (h->lowrank_cap > 0) cap = std::min(cap, h->lowrank_cap);   // tuning knob, see DESIGN.md section 5
             HY_TRY(build_plan(user, lo, hi, cap));
             const RowPlan& pl = plan[user ? 0 : 1];
             const int nbk = pl.n_buckets;
@@ -1620,6 +1622,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     if (ps) h->prof_slot = atoi(ps);
     const char* lr = getenv("HYPREC_LOWRANK");
     h->lowrank_enabled = !(lr && lr[0] == '0');
+    const char* lc = getenv("HYPREC_LOWRANK_CAP");
+    if (lc) h->lowrank_cap = std::max(0, atoi(lc));
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);
     else h->engine = new Engine<float>(h);
     *out = h;

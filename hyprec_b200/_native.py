@@ -17,7 +17,7 @@ EXPORTS = [
     "hyprec_create", "hyprec_destroy", "hyprec_last_error", "hyprec_abi_version", "hyprec_launch_count",
     "hyprec_set_train_csr", "hyprec_set_shard", "hyprec_set_factors", "hyprec_get_factors",
     "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_rmse_terms", "hyprec_train",
-    "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
+    "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_set_hashed_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
     "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles", "hyprec_host_alloc", "hyprec_host_free",
 ]
 
@@ -68,6 +68,7 @@ def load_library(rebuild=False):
     lib.hyprec_score_dense_f32.argtypes = [vp, vp]
     lib.hyprec_set_eval_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.hyprec_set_candidates.argtypes = [vp, c_i64, c_i64, vp, vp]
+    lib.hyprec_set_hashed_candidates.argtypes = [vp, c_int, c_int, ctypes.c_uint64]
     lib.hyprec_eval_topk.argtypes = [vp, c_i64, c_i64, vp, vp, c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.hyprec_kernel_ms.argtypes = [vp, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]
     lib.hyprec_reset_kernel_ms.argtypes = [vp]
@@ -201,6 +202,11 @@ class Handle(object):
         user_hi = self.m if user_hi is None else user_hi
         cand_indptr, cand_ids = _as(cand_indptr, numpy.int64), _as(cand_ids, numpy.int32)
         self._check(self._lib.hyprec_set_candidates(self._h, user_lo, user_hi, _ptr(cand_indptr), _ptr(cand_ids)))
+
+    def set_hashed_candidates(self, fold, n_folds, seed=0):
+        """Device-generated candidate lists: test positives + the hashed 1/n_folds share of the unrated items
+        (include/hyprec_b200.h); n_folds <= 0 switches back to explicit lists / all items."""
+        self._check(self._lib.hyprec_set_hashed_candidates(self._h, int(fold), int(n_folds), int(seed) & (2 ** 64 - 1)))
 
     def score_dense_f32(self):
         """Tensor-core (tcgen05, 3xTF32) approximation of U.V^T as float32."""

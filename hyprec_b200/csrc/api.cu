@@ -112,6 +112,7 @@ struct EngineBase {
                           int64_t* ones, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) = 0;
     virtual int device_factors(void** u, void** v, int* elem) = 0;
     virtual int set_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) = 0;
+    virtual int set_hashed_candidates(int fold, int n_folds, unsigned long long seed) = 0;
     virtual int score_dense_f32(float* out) = 0;
     virtual int solve_phase_cycles(long long* out16, int reset) = 0;
 };
@@ -227,7 +228,7 @@ struct Engine : EngineBase {
                          &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &w_hi, &w_lo, &l_hi, &l_lo, &cross, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
-                         &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf, &topk_spill};
+                         &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf, &topk_spill, &hashed_counts};
         for (DevBuf* b : all) b->release();
         csr.release(); csc.release(); full.release(); test.release();
     }
@@ -306,6 +307,7 @@ struct Engine : EngineBase {
             CU_TRY(cudaStreamSynchronize(h->stream));
         }
         HY_TRY(upload_csr(test, m, n, tp, ti, tv, "test"));
+        if (cands_are_hashed) { use_cached_cands = false; cands_are_hashed = false; cand_lo = cand_hi = -1; }
         return HYPREC_OK;
     }
 
@@ -1286,6 +1288,73 @@ struct Engine : EngineBase {
     // ---------------------------------------------------------------- evaluation
     int64_t cand_lo = -1, cand_hi = -1, cand_max = 0;
     bool use_cached_cands = false;
+    bool cands_are_hashed = false;      // the cached lists were generated on the device (below)
+    int hashed_fold = 0, hashed_folds = 0;
+    unsigned long long hashed_seed = 0;
+    DevBuf hashed_counts;
+
+    // Device-generated candidate lists (topk.cuh, hashed_candidates_kernel): from now on a NULL-list
+    // eval_topk over [lo, hi) ranks, for every user, its test positives plus the 1 / n_folds share of its
+    // unrated items that the hash assigns to `fold`.  n_folds <= 0 switches back to "all items".
+    int set_hashed_candidates(int fold, int n_folds, unsigned long long seed) override {
+        if (n_folds > 0 && (fold < 0 || fold >= n_folds)) return fail(HYPREC_E_INVALID, "hashed candidates: fold outside [0, n_folds)");
+        if (cands_are_hashed) { use_cached_cands = false; cand_lo = cand_hi = -1; cands_are_hashed = false; }
+        hashed_fold = fold;
+        hashed_folds = n_folds > 0 ? n_folds : 0;
+        hashed_seed = seed;
+        return HYPREC_OK;
+    }
+
+    int generate_hashed_candidates(int64_t lo, int64_t hi) {
+        if (full.rows != m || test.rows != m)
+            return fail(HYPREC_E_INVALID, "hashed candidates need the ratings and test matrices (set_eval_csr)");
+        const int64_t nu = hi - lo;
+        if (nu <= 0) return HYPREC_OK;
+        hyprec::HashedCandArgs a;
+        a.full_indptr = full.indptr.template as<int64_t>();
+        a.full_indices = full.indices.template as<int32_t>();
+        a.test_indptr = test.indptr.template as<int64_t>();
+        a.test_indices = test.indices.template as<int32_t>();
+        a.user_lo = lo;
+        a.user_hi = hi;
+        a.n_items = n;
+        a.fold = hashed_fold;
+        a.n_folds = hashed_folds;
+        a.seed = hashed_seed;
+        HY_TRY(hashed_counts.reserve(sizeof(int32_t) * (size_t)nu));
+        a.counts = hashed_counts.as<int32_t>();
+        a.out_indptr = nullptr;
+        a.out_ids = nullptr;
+        const int grid = (int)std::min<int64_t>(nu, (int64_t)8 * h->num_sms);
+        hyprec::hashed_candidates_kernel<false><<<grid, hyprec::kTopkThreads, 0, h->stream>>>(a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        std::vector<int32_t> counts_h((size_t)nu);
+        CU_TRY(cudaMemcpyAsync(counts_h.data(), hashed_counts.ptr, sizeof(int32_t) * (size_t)nu, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        std::vector<int64_t> ptr_h((size_t)nu + 1, 0);
+        int64_t max_cand = 0;
+        for (int64_t u = 0; u < nu; ++u) {
+            ptr_h[u + 1] = ptr_h[u] + counts_h[u];
+            max_cand = std::max<int64_t>(max_cand, counts_h[u]);
+        }
+        const int64_t total = ptr_h[nu];
+        HY_TRY(cand_ptr.reserve(sizeof(int64_t) * (size_t)(nu + 1)));
+        HY_TRY(cand_ids.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1)));
+        CU_TRY(cudaMemcpyAsync(cand_ptr.ptr, ptr_h.data(), sizeof(int64_t) * (size_t)(nu + 1), cudaMemcpyHostToDevice, h->stream));
+        a.out_indptr = cand_ptr.as<int64_t>();
+        a.out_ids = cand_ids.as<int32_t>();
+        hyprec::hashed_candidates_kernel<true><<<grid, hyprec::kTopkThreads, 0, h->stream>>>(a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(h->stream));             // ptr_h is read by the copy above
+        cand_lo = lo;
+        cand_hi = hi;
+        cand_max = std::max<int64_t>(max_cand, 1);
+        use_cached_cands = true;
+        cands_are_hashed = true;
+        return HYPREC_OK;
+    }
 
     // Candidate streams of users [lo, hi): validated (one min/max pass), copied to the device and
     // kept until replaced, so that a fold's lists cross PCIe once.
@@ -1313,12 +1382,13 @@ struct Engine : EngineBase {
         cand_lo = lo;
         cand_hi = hi;
         cand_max = std::max<int64_t>(max_cand, 1);
+        cands_are_hashed = false;
         return HYPREC_OK;
     }
 
     int set_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) override {
         if (m == 0) return fail(HYPREC_E_INVALID, "set_candidates before set_train_csr");
-        if (!cp && !ci) { use_cached_cands = false; cand_lo = cand_hi = -1; return HYPREC_OK; }
+        if (!cp && !ci) { use_cached_cands = false; cands_are_hashed = false; cand_lo = cand_hi = -1; return HYPREC_OK; }
         if (lo < 0 || hi > m || lo > hi) return fail(HYPREC_E_INVALID, "set_candidates: user range outside the matrix");
         HY_TRY(upload_candidates(lo, hi, cp, ci));
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -1399,6 +1469,9 @@ struct Engine : EngineBase {
             CU_TRY(cudaMemcpyAsync(ones_out, counts.ptr, sizeof(int64_t) * nu, cudaMemcpyDeviceToHost, h->stream));
         }
 
+        if (want_topk && !ci && !cp && hashed_folds > 0 &&
+            !(use_cached_cands && cands_are_hashed && cand_lo == lo && cand_hi == hi))
+            HY_TRY(generate_hashed_candidates(lo, hi));
         if (want_topk) {
             int64_t max_cand = n;
             const bool cached = !ci && cp == nullptr && cand_lo == lo && cand_hi == hi && cand_max > 0 && use_cached_cands;
@@ -1749,6 +1822,11 @@ int hyprec_set_candidates(hyprec_t* h, int64_t user_lo, int64_t user_hi, const i
                           const int32_t* cand_ids) {
     HY_TRY(check(h));
     return h->engine->set_candidates(user_lo, user_hi, cand_indptr, cand_ids);
+}
+
+int hyprec_set_hashed_candidates(hyprec_t* h, int fold, int n_folds, uint64_t seed) {
+    HY_TRY(check(h));
+    return h->engine->set_hashed_candidates(fold, n_folds, (unsigned long long)seed);
 }
 
 int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,

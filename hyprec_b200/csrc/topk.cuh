@@ -350,6 +350,93 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Candidate lists generated on the device (the scaled workload, SURVEY.md section 8d row C4: 4e5 candidates
+// per user times 1e6 users cannot be listed by the host).  The reference's fold-f list of a user holds the
+// user's fold-f positives plus a 1/k_folds share of the items the user never rated
+// (/root/reference/lib/evaluator.py:176-192, drawn from a shuffle); here the share is decided by a hash
+// of (user, item, seed) -- a "5-fold-equivalent" split without per-user shuffles:
+//     candidate(u, i)  <=>  i in test_u   or   (i not in ratings_u  and  mix(u, i, seed) % n_folds == fold)
+// in ascending item order (the order only matters among exactly tied scores).  Two passes per user range:
+// count (-> host prefix sum -> row pointers), then fill.  One CTA per user, every thread walks a contiguous
+// item range with one pointer into the sorted ratings row and one into the sorted test row.
+// ---------------------------------------------------------------------------------------------------
+HYPREC_HD unsigned long long hashed_mix(unsigned long long user, unsigned long long item, unsigned long long seed) {
+    unsigned long long x = (user * 0x9E3779B97F4A7C15ull) ^ (item * 0xC2B2AE3D27D4EB4Full) ^ seed;
+    x ^= x >> 33;
+    x *= 0xFF51AFD7ED558CCDull;
+    x ^= x >> 33;
+    x *= 0xC4CEB9FE1A85EC53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+struct HashedCandArgs {
+    const int64_t* full_indptr;    // full ratings CSR, global user ids, sorted column ids
+    const int32_t* full_indices;
+    const int64_t* test_indptr;    // test CSR (a subset of the ratings)
+    const int32_t* test_indices;
+    int64_t user_lo, user_hi, n_items;
+    int fold, n_folds;
+    unsigned long long seed;
+    int32_t* counts;               // [user_hi - user_lo], written by the counting pass
+    const int64_t* out_indptr;     // relative to user_lo, read by the filling pass
+    int32_t* out_ids;
+};
+
+__device__ __forceinline__ int64_t hashed_lower_bound(const int32_t* ids, int64_t a, int64_t b, int64_t item) {
+    while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        if ((int64_t)ids[mid] < item) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+
+// One thread's walk over items [c_lo, c_hi) of user u: number of candidates; written to out (ascending) when kWrite.
+template <bool kWrite>
+__device__ __forceinline__ int hashed_walk(const HashedCandArgs& p, int64_t u, int64_t c_lo, int64_t c_hi, int32_t* out) {
+    const int64_t f_end = p.full_indptr[u + 1], t_end = p.test_indptr[u + 1];
+    int64_t fp = hashed_lower_bound(p.full_indices, p.full_indptr[u], f_end, c_lo);
+    int64_t tp = hashed_lower_bound(p.test_indices, p.test_indptr[u], t_end, c_lo);
+    int found = 0;
+    for (int64_t i = c_lo; i < c_hi; ++i) {
+        const bool rated = fp < f_end && (int64_t)p.full_indices[fp] == i;
+        const bool tested = tp < t_end && (int64_t)p.test_indices[tp] == i;
+        fp += rated ? 1 : 0;
+        tp += tested ? 1 : 0;
+        const bool share = (int)(hashed_mix((unsigned long long)u, (unsigned long long)i, p.seed) %
+                                 (unsigned long long)p.n_folds) == p.fold;
+        if (tested || (!rated && share)) {
+            if (kWrite) out[found] = (int32_t)i;
+            ++found;
+        }
+    }
+    return found;
+}
+
+template <bool kFill>
+__global__ void __launch_bounds__(kTopkThreads) hashed_candidates_kernel(HashedCandArgs p) {
+    __shared__ int h_scan[kTopkThreads + 1];
+    const int tid = threadIdx.x;
+    const int64_t chunk = (p.n_items + kTopkThreads - 1) / kTopkThreads;
+    const int64_t c_lo = tid * chunk < p.n_items ? tid * chunk : p.n_items;
+    const int64_t c_hi = c_lo + chunk < p.n_items ? c_lo + chunk : p.n_items;
+    for (int64_t u = p.user_lo + blockIdx.x; u < p.user_hi; u += gridDim.x) {
+        const int mine = hashed_walk<false>(p, u, c_lo, c_hi, nullptr);
+        __syncthreads();                                        // h_scan of the previous user is dead
+        h_scan[tid + 1] = mine;
+        if (tid == 0) h_scan[0] = 0;
+        __syncthreads();
+        if (tid == 0)
+            for (int t = 1; t <= kTopkThreads; ++t) h_scan[t] += h_scan[t - 1];
+        __syncthreads();
+        if (kFill)
+            hashed_walk<true>(p, u, c_lo, c_hi, p.out_ids + p.out_indptr[u - p.user_lo] + h_scan[tid]);
+        else if (tid == 0)
+            p.counts[u - p.user_lo] = h_scan[kTopkThreads];
+    }
+}
+
 // max of a float array (single block), for the uniform error bound of the pre-filter
 __global__ void max_float_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
     __shared__ float red[256];

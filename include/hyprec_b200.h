@@ -126,6 +126,16 @@ int hyprec_set_eval_csr(hyprec_t* h, const int64_t* full_indptr, const int32_t* 
 int hyprec_set_candidates(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
                           const int32_t* cand_ids);
 
+/* Candidate lists generated on the device, for problem sizes whose lists cannot be enumerated by the host
+ * (BASELINE configs[3]: 4e5 candidates x 1e6 users).  The reference's fold list of a user is its fold positives
+ * plus a 1/k_folds share of the items it never rated (evaluator.py:176-192, drawn from per-user shuffles);
+ * here the share is decided by a 64-bit mix of (user, item, seed):
+ *     candidate(u, i)  <=>  i in test_u  or  (i not in ratings_u  and  mix(u, i, seed) % n_folds == fold)
+ * in ascending item order.  After this call every hyprec_eval_topk with cand_indptr = cand_ids = NULL ranks these
+ * lists (generated per user range, kept until the range, the parameters or the eval matrices change).  Needs
+ * hyprec_set_eval_csr.  n_folds <= 0 switches the behaviour off again.  No counterpart call in the reference. */
+int hyprec_set_hashed_candidates(hyprec_t* h, int fold, int n_folds, uint64_t seed);
+
 /* Everything get_evaluation_report() (abstract_recommender.py:100-131) derives from scores,
  * for users [user_lo, user_hi) (0, n_users for a single GPU); output arrays are indexed
  * relative to user_lo:

@@ -189,3 +189,39 @@ def evaluation_report(user_vecs, item_vecs, ratings, train, test, candidates, n_
                      recall_at_x(recall_x, hits, test_likes), ratio,
                      mrr_at(5, hits), ndcg_at(5, hits), mrr_at(10, hits), ndcg_at(10, hits))
     return out
+
+
+_M64 = (1 << 64) - 1
+
+
+def hashed_mix(user, items, seed):
+    """The 64-bit mix of hyprec_b200/csrc/topk.cuh (hashed_mix), vectorised over ``items`` (uint64 wrap-around)."""
+    with numpy.errstate(over="ignore"):
+        x = (numpy.uint64((int(user) * 0x9E3779B97F4A7C15) & _M64) ^
+             (numpy.asarray(items, dtype=numpy.uint64) * numpy.uint64(0xC2B2AE3D27D4EB4F)) ^ numpy.uint64(int(seed) & _M64))
+        x ^= x >> numpy.uint64(33)
+        x *= numpy.uint64(0xFF51AFD7ED558CCD)
+        x ^= x >> numpy.uint64(33)
+        x *= numpy.uint64(0xC4CEB9FE1A85EC53)
+        x ^= x >> numpy.uint64(33)
+    return x
+
+
+def hashed_candidates(ratings, test, users, fold, n_folds, seed):
+    """Candidate lists of the scaled workload (no counterpart in the reference, whose lists come from per-user
+    shuffles, evaluator.py:144-192; SURVEY.md section 8d row C4 asks for a "5-fold-equivalent" CSR-native split):
+    user u's list = its test positives plus the unrated items i with ``mix(u, i, seed) % n_folds == fold``,
+    ascending item ids.  Returns a list of int64 arrays, one per user of ``users``."""
+    ratings = sp.csr_matrix(ratings)
+    test = sp.csr_matrix(test)
+    n = ratings.shape[1]
+    items = numpy.arange(n, dtype=numpy.int64)
+    out = []
+    for u in users:
+        rated = numpy.zeros(n, dtype=bool)
+        rated[ratings.indices[ratings.indptr[u]:ratings.indptr[u + 1]]] = True
+        tested = numpy.zeros(n, dtype=bool)
+        tested[test.indices[test.indptr[u]:test.indptr[u + 1]]] = True
+        share = (hashed_mix(u, items, seed) % numpy.uint64(n_folds)) == numpy.uint64(fold)
+        out.append(items[tested | (~rated & share)])
+    return out

@@ -255,6 +255,18 @@ void emu_eval_spill_f64(const double* U, const double* V, int64_t m, int64_t n, 
                       true);
 }
 
+// device-generated candidate lists: fill == 0 writes counts[nu]; fill == 1 writes ids given the row pointers
+void emu_hashed_candidates(const int64_t* fp, const int32_t* fi, const int64_t* tp, const int32_t* ti, int64_t lo,
+                           int64_t hi, int64_t n, int fold, int n_folds, unsigned long long seed, int32_t* counts,
+                           const int64_t* out_indptr, int32_t* out_ids, int fill, int grid) {
+    HashedCandArgs a;
+    a.full_indptr = fp; a.full_indices = fi; a.test_indptr = tp; a.test_indices = ti;
+    a.user_lo = lo; a.user_hi = hi; a.n_items = n; a.fold = fold; a.n_folds = n_folds; a.seed = seed;
+    a.counts = counts; a.out_indptr = out_indptr; a.out_ids = out_ids;
+    if (fill) emu::launch(dim3(grid), dim3(kTopkThreads), 0, [&]() { hashed_candidates_kernel<true>(a); });
+    else emu::launch(dim3(grid), dim3(kTopkThreads), 0, [&]() { hashed_candidates_kernel<false>(a); });
+}
+
 void emu_predict_f64(const double* U, const double* V, int64_t m, int64_t n, int k, double* out) {
     SweepArgs<double> a;
     a.user_vecs = U; a.item_vecs = V; a.k = k; a.user_lo = 0; a.user_hi = m; a.n_items = n;

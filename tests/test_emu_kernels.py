@@ -316,3 +316,39 @@ def test_eval_kernel_capacity_300(emu, coef):
         assert len(want) == cap
         assert list(tidx[u_id]) == want, (coef, u_id)
         assert numpy.allclose(tval[u_id], vals, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("n,fold,n_folds,seed", [(700, 0, 5, 0), (1037, 3, 5, 20170303), (90, 1, 2, 7)])
+def test_hashed_candidate_lists(emu, n, fold, n_folds, seed):
+    """Device-generated candidate lists (count pass, host prefix sum, fill pass) against the numpy restatement
+    of the rule: test positives + the hashed share of the unrated items, ascending; a user range that does not
+    start at 0, a user without ratings, fewer items than threads."""
+    rs = numpy.random.RandomState(n)
+    m = 9
+    full = (rs.rand(m, n) < 0.15).astype(numpy.float64)
+    full[4, :] = 0
+    test = numpy.where(rs.rand(m, n) < 0.3, full, 0.0)
+    fcsr, tcsr = oals.to_csr(full), oals.to_csr(test)
+    fp, fi = fcsr.indptr.astype(numpy.int64), fcsr.indices.astype(numpy.int32)
+    tp, ti = tcsr.indptr.astype(numpy.int64), tcsr.indices.astype(numpy.int32)
+    lo, hi = 2, m
+    U64 = ctypes.c_uint64
+    counts = numpy.zeros(hi - lo, dtype=numpy.int32)
+    emu.emu_hashed_candidates(_ptr(fp), _ptr(fi), _ptr(tp), _ptr(ti), I64(lo), I64(hi), I64(n), fold, n_folds, U64(seed),
+                              _ptr(counts), None, None, 0, 3)
+    want = oev.hashed_candidates(full, test, range(lo, hi), fold, n_folds, seed)
+    assert list(counts) == [len(w) for w in want]
+    indptr = numpy.zeros(hi - lo + 1, dtype=numpy.int64)
+    indptr[1:] = numpy.cumsum(counts)
+    ids = numpy.full(int(indptr[-1]), -1, dtype=numpy.int32)
+    emu.emu_hashed_candidates(_ptr(fp), _ptr(fi), _ptr(tp), _ptr(ti), I64(lo), I64(hi), I64(n), fold, n_folds, U64(seed),
+                              None, _ptr(indptr), _ptr(ids), 1, 3)
+    for j, w in enumerate(want):
+        assert numpy.array_equal(ids[indptr[j]:indptr[j + 1]], w)
+    # the lists are what the rule says: every test positive, no train positive, about 1 / n_folds of the rest
+    for j, u in enumerate(range(lo, hi)):
+        got = set(ids[indptr[j]:indptr[j + 1]].tolist())
+        assert set(numpy.nonzero(test[u])[0].tolist()) <= got
+        assert not (set(numpy.nonzero(full[u] * (test[u] == 0))[0].tolist()) & got)
+    share = sum(len(w) for w in want) / float((hi - lo) * n)
+    assert abs(share - 1.0 / n_folds) < 0.08

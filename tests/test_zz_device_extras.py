@@ -179,3 +179,37 @@ def test_hybrid_report_from_blended_factors(als_cases, monkeypatch):
         finally:
             cf.close()
     assert numpy.allclose(reports["1"], reports["0"], rtol=1e-8, equal_nan=True), (reports["1"], reports["0"])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HYPREC_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent (the kernels are checked under the CPU "
+                           "emulator, tests/test_emu_kernels.py::test_hashed_candidate_lists); run with "
+                           "HYPREC_RUN_UNVERIFIED=1 on a B200")
+def test_hashed_candidates_equal_explicit_lists():
+    """hyprec_set_hashed_candidates: the device-generated lists rank exactly like the same lists passed explicitly."""
+    from hyprec_b200 import _native as native
+    from oracle import evaluation as oev
+    from test_gpu_parity import make_handle, synthetic
+    m, n, k = 40, 3000, 24
+    full, train, test, u0, v0, _ = synthetic(m, n, k, 5000, seed=5)
+    h, _ = make_handle(native, train)
+    try:
+        h.set_eval_csr((full.indptr, full.indices, full.data), (test.indptr, test.indices, test.data))
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        for lo, hi in ((0, m), (7, 29)):
+            lists = oev.hashed_candidates(full, test, range(lo, hi), 2, 5, 99)
+            cp = numpy.zeros(hi - lo + 1, numpy.int64)
+            cp[1:] = numpy.cumsum([len(c) for c in lists])
+            want = h.eval_topk(50, cp, numpy.concatenate(lists).astype(numpy.int32), lo, hi, want_counts=False)
+            h.set_hashed_candidates(2, 5, 99)
+            got = h.eval_topk(50, None, None, lo, hi, want_counts=False)
+            again = h.eval_topk(50, None, None, lo, hi, want_counts=False)          # cached lists
+            h.set_hashed_candidates(0, 0)
+            for key in ("topk_idx", "topk_val", "topk_hit"):
+                assert numpy.array_equal(got[key], want[key]) and numpy.array_equal(again[key], want[key])
+        everything = h.eval_topk(50, None, None, 7, 29, want_counts=False)          # switched off: all items again
+        assert not numpy.array_equal(everything["topk_idx"], want["topk_idx"])
+    finally:
+        h.close()

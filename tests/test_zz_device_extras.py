@@ -138,9 +138,6 @@ def test_candidate_lists_beyond_shared_memory(monkeypatch, n, use_tc, lists):
         h.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HYPREC_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: the low-rank hybrid report is opt-in "
-                           "(HYPREC_HYBRID_LOWRANK=1) until this test has run on a B200 (HYPREC_RUN_UNVERIFIED=1)")
 def test_hybrid_report_from_blended_factors(als_cases, monkeypatch):
     """is_hybrid report through the device with the blended low-rank factors == the reference's dense host flow."""
     from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer, synth
@@ -181,10 +178,6 @@ def test_hybrid_report_from_blended_factors(als_cases, monkeypatch):
     assert numpy.allclose(reports["1"], reports["0"], rtol=1e-8, equal_nan=True), (reports["1"], reports["0"])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HYPREC_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent (the kernels are checked under the CPU "
-                           "emulator, tests/test_emu_kernels.py::test_hashed_candidate_lists); run with "
-                           "HYPREC_RUN_UNVERIFIED=1 on a B200")
 def test_hashed_candidates_equal_explicit_lists():
     """hyprec_set_hashed_candidates: the device-generated lists rank exactly like the same lists passed explicitly."""
     from hyprec_b200 import _native as native

@@ -15,7 +15,20 @@ from hyprec_b200.grid_search import GridSearch
 from hyprec_b200.model_initializer import ModelInitializer
 from hyprec_b200.top_recommendations import TopRecommendations
 
-__all__ = ["CollaborativeFiltering", "Evaluator", "GridSearch", "ModelInitializer", "TopRecommendations", "install"]
+__all__ = ["CollaborativeFiltering", "Evaluator", "GridSearch", "ModelInitializer", "TopRecommendations", "install",
+           "as_reference_recommender"]
+
+
+def as_reference_recommender(cls):
+    """``cls`` with the reference's ``lib.abstract_recommender.AbstractRecommender`` appended to its bases, so that
+    ``isinstance(recommender, AbstractRecommender)`` holds for callers that import the base class from the
+    reference (/root/reference/tests/collaborative_tests.py:41 does).  Nothing is inherited from it: every method
+    of the reference's base is defined by this package's mirror, which comes first in the MRO."""
+    import importlib
+    base = importlib.import_module("lib.abstract_recommender").AbstractRecommender
+    if issubclass(cls, base):
+        return cls
+    return type(cls.__name__, (cls, base), {"__module__": cls.__module__, "__doc__": cls.__doc__})
 
 
 def install(evaluator=True, grid_search=True):
@@ -25,7 +38,7 @@ def install(evaluator=True, grid_search=True):
     arithmetic) and ``GridSearch`` (sweep without dense matrices, several models in flight) unless switched
     off.  Returns the names of the patched modules."""
     import importlib
-    swaps = [("lib.collaborative_filtering", "CollaborativeFiltering", CollaborativeFiltering)]
+    swaps = [("lib.collaborative_filtering", "CollaborativeFiltering", as_reference_recommender(CollaborativeFiltering))]
     if evaluator:
         swaps.append(("lib.evaluator", "Evaluator", Evaluator))
     if grid_search:

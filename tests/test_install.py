@@ -18,7 +18,10 @@ def test_install_rebinds_reference_modules():
     try:
         patched = hyprec_b200.install()
         assert "lib.collaborative_filtering" in patched and "lib.recommender_system" in patched
-        assert sys.modules["lib.recommender_system"].CollaborativeFiltering is hyprec_b200.CollaborativeFiltering
+        installed = sys.modules["lib.recommender_system"].CollaborativeFiltering
+        assert issubclass(installed, hyprec_b200.CollaborativeFiltering) and installed.__name__ == "CollaborativeFiltering"
+        assert issubclass(installed, sys.modules["lib.abstract_recommender"].AbstractRecommender)
+        assert installed.train is hyprec_b200.CollaborativeFiltering.train       # nothing comes from the reference's base
         assert sys.modules["lib.recommender_system"].Evaluator is hyprec_b200.Evaluator
         assert sys.modules["lib.grid_search"].GridSearch is hyprec_b200.GridSearch
         ref_grid = saved[("lib.grid_search", "GridSearch")]

@@ -66,3 +66,32 @@ def test_reference_test_module_passes_on_this_package(name, tmp_path, monkeypatc
         result = unittest.TextTestRunner(stream=open("/dev/null", "w"), verbosity=0).run(suite)
     problems = [str(trace) for _, trace in result.errors + result.failures]
     assert result.wasSuccessful(), "\n".join(problems)
+
+
+@pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not present")
+def test_runnables_collaborative_prints_the_same_summary(monkeypatch):
+    """`python3 runnables.py collaborative` on the reference's built-in toy data (runnables.py:38-58, 111-123;
+    hyper-parameters from its config/recommender.json): the summary line with the reference's classes, then with this
+    package's classes bound to the names runnables.py imported."""
+    import contextlib
+    import io
+    import hyprec_b200
+    from grid_helpers import OracleBacked
+    reference_loader.load_reference(heavy=True)
+    runnables = importlib.import_module("runnables")
+
+    def summary():
+        out = io.StringIO()
+        with warnings.catch_warnings(), contextlib.redirect_stdout(out):
+            warnings.simplefilter("ignore")
+            runner = runnables.RunnableRecommenders(use_database=False, verbose=False, load_matrices=False, dump=False)
+            runner.run_collaborative()
+        return out.getvalue()
+
+    want = summary()
+    assert want.startswith("Summary: Test sum")
+    monkeypatch.setattr(runnables, "CollaborativeFiltering",
+                        hyprec_b200.as_reference_recommender(type("CollaborativeFiltering", (OracleBacked,), {})))
+    monkeypatch.setattr(runnables, "Evaluator", hyprec_b200.Evaluator)
+    monkeypatch.setattr(runnables, "ModelInitializer", hyprec_b200.ModelInitializer)
+    assert summary() == want

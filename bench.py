@@ -486,6 +486,25 @@ def our_arm(args, wl):
                                  for x in (50, 100, 150, 200, 250, 300)}
         except Exception as exc:
             line["recall_at"] = dict(error=repr(exc))
+    # Evaluation at the scaled size (no per-user lists exist there): device-generated candidate lists over a block of
+    # users.  Off by default (--eval-users 0); reported beside the line's metric, never inside it.
+    if args.eval_users > 0 and not has_eval:
+        try:
+            block = int(min(args.eval_users, m))
+            n_tr, n_te = int(tr.indptr[block]), int(te.indptr[block])
+            h.set_hashed_candidates(0, 5, 20170303)
+            h.eval_topk(200, None, None, 0, block, n_train_nz=n_tr, n_test_nz=n_te)          # warm-up, builds the lists
+            h.reset_kernel_ms()
+            t0 = time.perf_counter()
+            h.eval_topk(200, None, None, 0, block, n_train_nz=n_tr, n_test_nz=n_te)
+            seconds = time.perf_counter() - t0
+            line["hashed_eval"] = dict(users=block, seconds=seconds, users_per_s=block / seconds,
+                                       kernel_ms={name: h.kernel_ms(t)[0] for name, t in classes.items()
+                                                  if name in ("count", "topk", "flags")},
+                                       candidates="test positives + hashed 1/5 share of the unrated items (fold 0)")
+            h.set_hashed_candidates(0, 0)
+        except Exception as exc:
+            line["hashed_eval"] = dict(error=repr(exc))
     print(json.dumps(line))
     try:
         h.close()
@@ -548,6 +567,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("HYPREC_PRECISION"), choices=["fp64", "fp32"],
                     help="default: fp64 (citeulike workloads), fp32 (scaled workload, as BASELINE configs[3] specifies)")
     ap.add_argument("--cpu-rows", type=int, default=16, help="rows per side in the CPU baseline sample")
+    ap.add_argument("--eval-users", type=int, default=0,
+                    help="scaled workload, 1 GPU: also time the evaluation of this many users with device-generated "
+                         "candidate lists (0: off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

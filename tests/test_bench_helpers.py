@@ -52,3 +52,73 @@ def test_clock_sampler_reports_the_clock_under_load():
     assert got["sm_mhz"] == 1950.0 and got["sm_mhz_all_samples"] == 120.0
     assert got["samples"] == 9 and got["samples_under_load"] == 3
     assert got["reasons"] == ["sw_power_cap"] and got["sm_max_mhz"] == 1965.0
+
+
+def test_bench_line_python_flow_with_a_stand_in_handle(monkeypatch, capsys):
+    """bench.py's own arm end to end on the CPU with a stand-in for the C-ABI handle: every key of the JSON
+    contract is present and serialisable, including the parts computed last (recall@{50..300})."""
+    import json
+    import numpy
+    import bench
+    from hyprec_b200 import _native
+
+    class StandIn(object):
+        launch_count = 0
+
+        def __init__(self, device, precision):
+            self.m = self.n = self.k = 0
+
+        def set_train_csr(self, m, n, *rest):
+            self.m, self.n = m, n
+
+        def set_factors(self, u, v):
+            self.k = u.shape[1]
+
+        def als_half_step(self, *args):
+            StandIn.launch_count += 10
+
+        def eval_topk(self, capacity, cp=None, ci=None, user_lo=0, user_hi=None, want_counts=True, want_topk=True,
+                      n_train_nz=None, n_test_nz=None, out=None):
+            if out is not None:
+                return out
+            nu = (self.m if user_hi is None else user_hi) - user_lo
+            return dict(thresholds=numpy.zeros(nu), ones_per_row=numpy.zeros(nu, numpy.int64),
+                        topk_idx=numpy.zeros((nu, capacity), numpy.int32), topk_val=numpy.zeros((nu, capacity)),
+                        topk_hit=numpy.ones((nu, capacity)), train_flags=None, test_flags=None)
+
+        def pinned_empty(self, shape, dtype=numpy.float64):
+            return numpy.zeros(shape, dtype)
+
+        def get_factors(self, u=None, v=None):
+            return u, v
+
+        def kernel_ms(self, which):
+            return 1.0, 1, 1.0
+
+        def rmse(self):
+            return 0.25
+
+        def probe_fma_tflops(self, precision):
+            return 36.0
+
+        def __getattr__(self, name):              # set_eval_csr, set_candidates, flush_l2, reset_kernel_ms, close ...
+            return lambda *args, **kwargs: None
+
+    monkeypatch.setattr(_native, "Handle", StandIn)
+    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
+
+    class Args(object):
+        gpus, steps, warmup, impl, workload, scale, precision, cpu_rows, eval_users = 1, 2, 1, "ours", "small", 0.1, None, 2, 0
+
+    args = Args()
+    bench.our_arm(args, bench.make_workload(args))
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["config"]["workload"].startswith("small shape") and "model" not in line["config"]
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert sorted(line["recall_at"], key=int) == ["50", "100", "150", "200", "250", "300"]
+    assert line["gpu_launches"] == 2 * 2 * 10

@@ -269,6 +269,9 @@ class GridSearch(object):
                 w.close()
         if world > 1:
             import torch.distributed as dist
+            if dist.get_backend() == "nccl":        # object collectives stage through the current CUDA device
+                import torch
+                torch.cuda.set_device(int(os.environ.get("HYPREC_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
             gathered = [None] * world
             dist.all_gather_object(gathered, {i: tuple(results[i]) for i in results})
             for part in gathered:

@@ -11,7 +11,7 @@ from hyprec_b200 import build as _build
 
 F64, F32 = 0, 1
 SIDE_USER, SIDE_ITEM = 0, 1
-T_GRAM, T_SOLVE, T_RMSE, T_SWEEP, T_TOPK, T_FLAGS, T_COUNT, T_PREP = range(8)
+T_GRAM, T_SOLVE, T_RMSE, T_SWEEP, T_TOPK, T_FLAGS, T_COUNT, T_PREP, T_COMM = range(9)
 
 EXPORTS = [
     "hyprec_create", "hyprec_destroy", "hyprec_last_error", "hyprec_abi_version", "hyprec_launch_count",
@@ -19,6 +19,8 @@ EXPORTS = [
     "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_rmse_terms", "hyprec_train",
     "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_set_hashed_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
     "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles", "hyprec_host_alloc", "hyprec_host_free",
+    "hyprec_comm_blob_bytes", "hyprec_comm_export", "hyprec_comm_attach", "hyprec_comm_detach", "hyprec_comm_stats",
+    "hyprec_init_factors_uniform", "hyprec_get_factor_rows", "hyprec_mark", "hyprec_elapsed_ms",
 ]
 
 EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
@@ -77,6 +79,14 @@ def load_library(rebuild=False):
     lib.hyprec_host_free.argtypes = [vp, vp]
     lib.hyprec_solve_phase_cycles.argtypes = [vp, vp, c_int]
     lib.hyprec_probe_fma_tflops.argtypes = [vp, c_int, ctypes.POINTER(c_dbl)]
+    lib.hyprec_comm_export.argtypes = [vp, c_int, c_int, vp, ctypes.c_size_t]
+    lib.hyprec_comm_attach.argtypes = [vp, vp, ctypes.c_size_t, vp, vp]
+    lib.hyprec_comm_detach.argtypes = [vp]
+    lib.hyprec_comm_stats.argtypes = [vp, vp]
+    lib.hyprec_init_factors_uniform.argtypes = [vp, c_int, ctypes.c_uint64]
+    lib.hyprec_get_factor_rows.argtypes = [vp, c_int, vp, c_i64, vp]
+    lib.hyprec_mark.argtypes = [vp, c_int]
+    lib.hyprec_elapsed_ms.argtypes = [vp, c_int, c_int, ctypes.POINTER(c_dbl)]
     _lib = lib
     return lib
 
@@ -146,6 +156,48 @@ class Handle(object):
             raise ValueError("factor shapes %s / %s do not match a %d x %d problem" % (u.shape, v.shape, self.m, self.n))
         self.k = int(u.shape[1])
         self._check(self._lib.hyprec_set_factors(self._h, _ptr(u), _ptr(v), self.k))
+
+    def init_factors_uniform(self, k, seed):
+        """U, V ~ uniform [0, 1) drawn on the device (oracle.als.uniform_factors restates the generator)."""
+        self.k = int(k)
+        self._check(self._lib.hyprec_init_factors_uniform(self._h, self.k, int(seed) & (2 ** 64 - 1)))
+
+    def get_factor_rows(self, side, rows):
+        rows = _as(rows, numpy.int64)
+        out = numpy.empty((rows.shape[0], self.k))
+        self._check(self._lib.hyprec_get_factor_rows(self._h, int(side), _ptr(rows), rows.shape[0], _ptr(out)))
+        return out
+
+    # ---- multi-GPU exchange (one process per GPU; see include/hyprec_b200.h)
+    def comm_export(self, rank, world):
+        size = int(self._lib.hyprec_comm_blob_bytes())
+        blob = ctypes.create_string_buffer(size)
+        self._check(self._lib.hyprec_comm_export(self._h, int(rank), int(world), blob, size))
+        return blob.raw
+
+    def comm_attach(self, blobs, user_bounds, item_bounds):
+        size = int(self._lib.hyprec_comm_blob_bytes())
+        joined = b"".join(blobs)
+        if len(joined) != size * len(blobs):
+            raise ValueError("every rank publishes one blob of %d bytes" % size)
+        ub, ib = _as(user_bounds, numpy.int64), _as(item_bounds, numpy.int64)
+        self._check(self._lib.hyprec_comm_attach(self._h, joined, size, _ptr(ub), _ptr(ib)))
+
+    def comm_detach(self):
+        self._check(self._lib.hyprec_comm_detach(self._h))
+
+    def comm_stats(self):
+        out = numpy.zeros(8)
+        self._check(self._lib.hyprec_comm_stats(self._h, _ptr(out)))
+        return dict(attached=bool(out[0]), bytes_pushed=float(out[1]), barriers=int(out[2]), arena_bytes=int(out[3]))
+
+    def mark(self, slot):
+        self._check(self._lib.hyprec_mark(self._h, int(slot)))
+
+    def elapsed_ms(self, start, stop):
+        out = ctypes.c_double()
+        self._check(self._lib.hyprec_elapsed_ms(self._h, int(start), int(stop), ctypes.byref(out)))
+        return out.value
 
     def get_factors(self, user_out=None, item_out=None):
         """Copy the factors into the given float64 C-contiguous arrays (allocated when None)."""

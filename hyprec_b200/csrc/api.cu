@@ -17,6 +17,7 @@
 #include "../../include/hyprec_b200.h"
 #include "als_solve.cuh"
 #include "common.cuh"
+#include "comm.cuh"
 #include "gram.cuh"
 #include "score.cuh"
 #include "tc_score.cuh"
@@ -69,8 +70,11 @@ int ensure_dynamic_smem(const void* func, int bytes) {
 struct DevBuf {
     void* ptr = nullptr;
     size_t bytes = 0;
+    bool external = false;     // a window of the exchange arena (multi-GPU): never freed or regrown here
     int reserve(size_t want) {
         if (want <= bytes) return HYPREC_OK;
+        if (external)
+            return fail(HYPREC_E_INVALID, "buffer belongs to the multi-GPU exchange arena and cannot grow: hyprec_comm_detach first");
         if (ptr) cudaFree(ptr);
         ptr = nullptr;
         bytes = 0;
@@ -79,9 +83,16 @@ struct DevBuf {
         return HYPREC_OK;
     }
     void release() {
-        if (ptr) cudaFree(ptr);
+        if (ptr && !external) cudaFree(ptr);
         ptr = nullptr;
         bytes = 0;
+        external = false;
+    }
+    void adopt(void* p, size_t n) {
+        release();
+        ptr = p;
+        bytes = n;
+        external = true;
     }
     template <typename U>
     U* as() const { return reinterpret_cast<U*>(ptr); }
@@ -94,7 +105,7 @@ struct Csr {
     void release() { indptr.release(); indices.release(); values.release(); }
 };
 
-constexpr int kNumTimers = 8;
+constexpr int kNumTimers = 9;
 
 struct EngineBase {
     virtual ~EngineBase() {}
@@ -115,7 +126,22 @@ struct EngineBase {
     virtual int set_hashed_candidates(int fold, int n_folds, unsigned long long seed) = 0;
     virtual int score_dense_f32(float* out) = 0;
     virtual int solve_phase_cycles(long long* out16, int reset) = 0;
+    virtual int comm_export(int rank, int world, void* blob, size_t blob_bytes) = 0;
+    virtual int comm_attach(const void* blobs, size_t blob_bytes, const int64_t* user_bounds, const int64_t* item_bounds) = 0;
+    virtual int comm_detach() = 0;
+    virtual int init_factors_uniform(int k, unsigned long long seed) = 0;
+    virtual int get_factor_rows(int side, const int64_t* rows, int64_t n_rows, double* out) = 0;
+    virtual int comm_stats(double* out8) = 0;
+    virtual bool comm_active() const = 0;
 };
+
+// What a rank publishes to its peers (hyprec_comm_export -> hyprec_comm_attach).
+struct CommBlob {
+    unsigned long long magic;
+    cudaIpcMemHandle_t handle;
+    long long m, n, k, elem, world, rank, arena_bytes, pid;
+};
+constexpr unsigned long long kCommMagic = 0x4859505243303031ull;   // "HYPRC001"
 
 }  // namespace
 
@@ -133,6 +159,7 @@ struct hyprec_ctx {
     bool tc_multi_enabled = true;  // HYPREC_TC_MULTI=0: systems of <= 128 rows stay on the shared-memory tile kernel
     bool tc_chol_enabled = true;   // HYPREC_TC_CHOL=0: float32 systems factorise in shared-memory tiles (als_solve.cuh)
     bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
+    bool split_enabled = true;     // HYPREC_SPLIT=0: rows with tens of thousands of positives stay on one CTA
     int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
     bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -148,6 +175,7 @@ struct hyprec_ctx {
     static constexpr int kAux = 7;
     cudaStream_t aux[kAux] = {};             // concurrent row-kernel launches
     cudaEvent_t ev_fork = nullptr, ev_base = nullptr, ev_join[kAux] = {};
+    cudaEvent_t marks[8] = {};               // hyprec_mark / hyprec_elapsed_ms
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     EngineBase* engine = nullptr;
@@ -218,7 +246,7 @@ struct Engine : EngineBase {
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
     static constexpr int kHeavyStream = 6;   // aux streams 0..5: degree buckets, 6: rows above the cap
-    DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk, topk_spill;
+    DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk, topk_spill, rows_idx, rows_out;
 
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
     ~Engine() override {
@@ -229,7 +257,19 @@ struct Engine : EngineBase {
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf, &topk_spill, &hashed_counts};
+        if (cm.exported) {
+            if (cm.on)
+                for (int r = 0; r < cm.world; ++r)
+                    if (r != cm.rank && cm.peers.base[r]) cudaIpcCloseMemHandle(cm.peers.base[r]);
+            U.release();
+            V.release();
+            cudaFree(cm.arena);
+        }
         for (DevBuf* b : all) b->release();
+        DevBuf* more[] = {&gram64[0], &gram64[1], &slot_local, &comm_status, &split_partial, &split_pb, &split_gram, &split_b,
+                          &plan[0].seg_lo, &plan[0].seg_len, &plan[0].seg_ptr, &plan[0].split_lo,
+                          &plan[1].seg_lo, &plan[1].seg_len, &plan[1].seg_ptr, &plan[1].split_lo, &rows_idx, &rows_out};
+        for (DevBuf* b : more) b->release();
         csr.release(); csc.release(); full.release(); test.release();
     }
 
@@ -352,8 +392,56 @@ struct Engine : EngineBase {
         k = k_;
         HY_TRY(upload_matrix(U, u, m));
         HY_TRY(upload_matrix(V, v, n));
+        factors_changed();
+        return HYPREC_OK;
+    }
+
+    void factors_changed() {
         gram_ok[0] = gram_ok[1] = false;
         cross_valid = false;
+        cm.gram64_ok[0] = cm.gram64_ok[1] = false;
+        cm.q_ok[0] = cm.q_ok[1] = false;
+        cm.prep_side = -1;
+        cm.slots_have_rmse = false;
+    }
+
+    // U[e] and V[e] drawn on the device from a counter-based generator (comm.cuh uniform_fill_kernel):
+    // numpy.random.random((m, k)) / ((n, k)) of /root/reference/lib/collaborative_filtering.py:173-176 for
+    // problem sizes whose factors should not cross PCIe (seeds `seed` and `seed + 1`).
+    int init_factors_uniform(int k_, unsigned long long seed) override {
+        if (m == 0) return fail(HYPREC_E_INVALID, "init_factors_uniform before set_train_csr");
+        if (k_ <= 0 || k_ > 2000) return fail(HYPREC_E_UNSUPPORTED, "n_factors must be in [1, 2000]");
+        if (k_ != k) { has_prior = false; }
+        k = k_;
+        HY_TRY(U.reserve(sizeof(T) * (size_t)m * k));
+        HY_TRY(V.reserve(sizeof(T) * (size_t)n * k));
+        const int64_t cu = m * k, cv = n * k;
+        hyprec::uniform_fill_kernel<T><<<(unsigned)((cu + 255) / 256), 256, 0, h->stream>>>(U.as<T>(), cu, seed);
+        hyprec::uniform_fill_kernel<T><<<(unsigned)((cv + 255) / 256), 256, 0, h->stream>>>(V.as<T>(), cv, seed + 1);
+        h->launches += 2;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        factors_changed();
+        return HYPREC_OK;
+    }
+
+    int get_factor_rows(int side, const int64_t* rows, int64_t n_rows, double* out) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "get_factor_rows before set_factors");
+        if (side != 0 && side != 1) return fail(HYPREC_E_INVALID, "side must be 0 or 1");
+        if (n_rows <= 0) return HYPREC_OK;
+        if (!rows || !out) return fail(HYPREC_E_INVALID, "get_factor_rows: null array");
+        const int64_t limit = side == 0 ? m : n;
+        for (int64_t i = 0; i < n_rows; ++i)
+            if (rows[i] < 0 || rows[i] >= limit) return fail(HYPREC_E_INVALID, "get_factor_rows: row id out of range");
+        HY_TRY(rows_idx.reserve(sizeof(int64_t) * (size_t)n_rows));
+        HY_TRY(rows_out.reserve(sizeof(double) * (size_t)n_rows * k));
+        CU_TRY(cudaMemcpyAsync(rows_idx.ptr, rows, sizeof(int64_t) * (size_t)n_rows, cudaMemcpyHostToDevice, h->stream));
+        hyprec::gather_rows_kernel<T><<<(unsigned)n_rows, 128, 0, h->stream>>>(side == 0 ? U.as<T>() : V.as<T>(), k,
+                                                                              rows_idx.as<int64_t>(), n_rows, rows_out.as<double>());
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(out, rows_out.ptr, sizeof(double) * (size_t)n_rows * k, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
         return HYPREC_OK;
     }
 
@@ -378,6 +466,9 @@ struct Engine : EngineBase {
         if (v) *v = V.ptr;
         if (elem) *elem = (int)sizeof(T);
         gram_ok[0] = gram_ok[1] = false;   // the caller may write through these pointers
+        cm.gram64_ok[0] = cm.gram64_ok[1] = false;
+        cm.q_ok[0] = cm.q_ok[1] = false;
+        cm.prep_side = -1;
         // With a shard set the pointers serve the exchange of the side just solved (rows of the OTHER
         // ranks change): the cross term of this rank's item rows stays what the item half-step left.
         if (h->user_hi < 0 && h->item_hi < 0) cross_valid = false;
@@ -533,7 +624,8 @@ struct Engine : EngineBase {
     // float32 systems of 33..256 unknowns with the normal matrix resident in tensor memory (tc_chol.cuh).
     int launch_chol_rows(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list,
                          bool lowrank, int max_dim, const float* fixed_ptr, const float* prior_ptr, int64_t work,
-                         cudaStream_t st, int slot, int64_t out_row0 = 0) {
+                         cudaStream_t st, int slot, int64_t out_row0 = 0, int n_split = 0, const int64_t* split_lo = nullptr,
+                         const float* split_gram_p = nullptr, const float* split_b_p = nullptr) {
         namespace tc = hyprec::tc;
         const tc::CholLayout lay = tc::chol_layout(max_dim);
         if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "tensor-memory row launch does not fit shared memory");
@@ -560,6 +652,10 @@ struct Engine : EngineBase {
         a.lowrank = lowrank ? 1 : 0;
         a.tmem_cols = tc::syrk_tmem_cols(max_dim);
         a.cross_out = cross_active ? cross.as<double>() : nullptr;
+        a.n_split = n_split;
+        a.split_lo = split_lo;
+        a.split_gram = split_gram_p;
+        a.split_b = split_b_p;
         a.prof = nullptr;
         if (h->prof_enabled && slot == h->prof_slot) {
             if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
@@ -619,7 +715,8 @@ struct Engine : EngineBase {
     // C[ra x rb] = A[ra x k] B[rb x k]^T through the SIMT sweep kernel (float64 mode; float32 mode
     // goes through gemm_nt_tc below unless the tensor cores are switched off).  With a row
     // list, row i of the product (A is compact) is stored at C[list[i]].
-    int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, T* c, const int32_t* list = nullptr) {
+    int gemm_nt(const T* a, int64_t ra, const T* b, int64_t rb, T* c, const int32_t* list = nullptr, void** peers = nullptr,
+                int n_peer = 0) {
         hyprec::SweepArgs<T> s;
         s.user_vecs = a;
         s.item_vecs = b;
@@ -632,6 +729,8 @@ struct Engine : EngineBase {
         s.row_list = list;
         s.thresholds = nullptr;
         s.counts = nullptr;
+        s.n_peer = n_peer;
+        for (int i = 0; i < n_peer; ++i) s.peer_out[i] = peers[i];
         dim3 grid((unsigned)((rb + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
                   (unsigned)((ra + hyprec::kSweepTile - 1) / hyprec::kSweepTile));
         hyprec::score_sweep_kernel<T, hyprec::kSweepStore><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(s);
@@ -643,7 +742,8 @@ struct Engine : EngineBase {
     // float32 mode: the same product on the tensor cores (tc_score_kernel, 3xTF32) -- the whitening
     // Q = Y L^-T and the back-transform x = L^-T y are real dense contractions.
     DevBuf w_hi, w_lo, l_hi, l_lo;
-    int gemm_nt_tc(const float* a, int64_t ra, const float* b, float* c, const int32_t* row_map) {
+    int gemm_nt_tc(const float* a, int64_t ra, const float* b, float* c, const int32_t* row_map, void** peers = nullptr,
+                   int n_peer = 0) {
         namespace tcn = hyprec::tc;
         if (ra == 0) return HYPREC_OK;
         HY_TRY(w_hi.reserve(sizeof(float) * (size_t)ra * k));
@@ -674,6 +774,8 @@ struct Engine : EngineBase {
         s.dense = c;
         s.dense_ld = k;
         s.row_map = row_map;
+        s.n_dense_peer = n_peer;
+        for (int i = 0; i < n_peer; ++i) s.dense_peer[i] = static_cast<float*>(peers[i]);
         auto kern = tcn::tc_score_kernel;
         HY_TRY(ensure_dynamic_smem((const void*)kern, (int)tcn::kSmemBytes));
         const int64_t n_tiles = ((ra + tcn::kBM - 1) / tcn::kBM) * ((k + tcn::kBN - 1) / tcn::kBN);
@@ -684,32 +786,42 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
     // whitening products: tensor cores in float32 mode, the float64 sweep kernel otherwise
-    int whiten_gemm(const T* a, int64_t ra, const T* b, T* c, const int32_t* list) {
+    // peers / n_peer: replicas of c on the other GPUs that receive the same rows (multi-GPU exchange)
+    int whiten_gemm(const T* a, int64_t ra, const T* b, T* c, const int32_t* list, void** peers = nullptr, int n_peer = 0) {
+        if (ra <= 0) return HYPREC_OK;
         if constexpr (sizeof(T) == sizeof(float)) {
             if (h->tc_solve_enabled && tc_usable() && h->encode_tiled != nullptr && ra >= 128)
                 return gemm_nt_tc(reinterpret_cast<const float*>(a), ra, reinterpret_cast<const float*>(b),
-                                  reinterpret_cast<float*>(c), list);
+                                  reinterpret_cast<float*>(c), list, peers, n_peer);
         }
-        return gemm_nt(a, ra, b, k, c, list);
+        return gemm_nt(a, ra, b, k, c, list, peers, n_peer);
     }
 
     // Rows of [lo, hi) grouped for the low-rank path: bucket b holds rows with
     // deg <= kBucketDim[b] (sorted by degree, heaviest first), `heavy` the rest.
     struct RowPlan {
         int64_t lo = -1, hi = -1;
-        int cap = -1;
+        int cap = -2;
+        bool allow_split = false;
         int n_buckets = 0;
         std::vector<int64_t> bucket_off;   // offsets into `lists`, size n_buckets + 2 (last = heavy)
         std::vector<int> bucket_dim;
         DevBuf lists;
+        // heavy rows split over several CTAs (float32 tensor-memory path): the first n_split rows of the heavy list
+        int n_split = 0, n_seg = 0;
+        int64_t split_work = 0;            // positives per work item the plan aimed at
+        DevBuf seg_lo, seg_len, seg_ptr, split_lo;
     };
     RowPlan plan[2];
+    DevBuf split_partial, split_pb, split_gram, split_b;
 
     // Degree buckets of the low-rank path: upper dimension, threads per CTA, tile edge.
     static constexpr int kMaxBuckets = 6;
     static constexpr int kBucketDim[kMaxBuckets] = {31, 63, 127, 191, 255, 319};
     static constexpr int kBucketThreads[kMaxBuckets] = {64, 128, 128, 256, 256, 256};
     static constexpr int kBucketTile[kMaxBuckets] = {4, 4, 8, 8, 8, 8};
+    static constexpr int kSplitCounterSlot = 8;
+    static constexpr int64_t kSplitMinWork = 4096;
 
     // Number of buckets whose systems fit one SM's shared memory in this precision.
     int usable_buckets() const {
@@ -719,18 +831,23 @@ struct Engine : EngineBase {
         return nbk;
     }
 
-    int build_plan(bool user, int64_t lo, int64_t hi, int cap) {
+    // cap < 0: every row is "heavy" (direct k x k systems only).  allow_split: rows whose positives exceed ~1.5 work
+    // items (work item = max(4096, heavy positives of the shard / (4 * SMs))) are cut into segments that
+    // split_partial_kernel accumulates on other CTAs; the row's own CTA keeps the tail segment.
+    int build_plan(bool user, int64_t lo, int64_t hi, int cap, bool allow_split) {
         RowPlan& pl = plan[user ? 0 : 1];
-        if (pl.lo == lo && pl.hi == hi && pl.cap == cap) return HYPREC_OK;
+        if (pl.lo == lo && pl.hi == hi && pl.cap == cap && pl.allow_split == allow_split) return HYPREC_OK;
         const std::vector<int64_t>& ptr = (user ? csr : csc).h_indptr;
         const int nbk = usable_buckets();
         std::vector<std::vector<int32_t>> groups(nbk + 1);
+        int64_t heavy_positives = 0;
         for (int64_t r = lo; r < hi; ++r) {
             const int64_t deg = ptr[r + 1] - ptr[r];
             int b = nbk;                        // heavy: direct k x k system
             if (deg <= cap)
                 for (int i = 0; i < nbk; ++i)
                     if (deg <= kBucketDim[i]) { b = i; break; }
+            if (b == nbk) heavy_positives += deg;
             groups[b].push_back((int32_t)r);
         }
         std::vector<int32_t> flat;
@@ -747,15 +864,98 @@ struct Engine : EngineBase {
             pl.bucket_off.push_back((int64_t)flat.size());
         }
         HY_TRY(pl.lists.reserve(sizeof(int32_t) * std::max<size_t>(flat.size(), 1)));
-        if (!flat.empty()) {
+        if (!flat.empty())
             CU_TRY(cudaMemcpyAsync(pl.lists.ptr, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, h->stream));
-            CU_TRY(cudaStreamSynchronize(h->stream));
+        // ---- split plan over the (degree-sorted) heavy list
+        pl.n_split = pl.n_seg = 0;
+        std::vector<int64_t> seg_lo_h, split_lo_h;
+        std::vector<int32_t> seg_len_h, seg_ptr_h(1, 0);
+        const int64_t work = std::max<int64_t>(kSplitMinWork, heavy_positives / (4 * (int64_t)std::max(1, h->num_sms)));
+        pl.split_work = work;
+        if (allow_split) {
+            for (int32_t r : groups[nbk]) {
+                const int64_t deg = ptr[r + 1] - ptr[r];
+                if (deg <= work + work / 2) break;          // sorted: nothing heavier follows
+                const int64_t parts = std::min<int64_t>(64, (deg + work - 1) / work);
+                const int64_t part_len = ((deg + parts - 1) / parts + 31) / 32 * 32;
+                int64_t at = ptr[r];
+                for (int64_t q = 0; q + 1 < parts; ++q) {
+                    seg_lo_h.push_back(at);
+                    seg_len_h.push_back((int32_t)part_len);
+                    at += part_len;
+                }
+                split_lo_h.push_back(at);                     // the tail stays with the row's own CTA
+                seg_ptr_h.push_back((int32_t)seg_lo_h.size());
+            }
+            pl.n_split = (int)split_lo_h.size();
+            pl.n_seg = (int)seg_lo_h.size();
+            if (pl.n_split > 0) {
+                HY_TRY(pl.seg_lo.reserve(sizeof(int64_t) * seg_lo_h.size()));
+                HY_TRY(pl.seg_len.reserve(sizeof(int32_t) * seg_len_h.size()));
+                HY_TRY(pl.seg_ptr.reserve(sizeof(int32_t) * seg_ptr_h.size()));
+                HY_TRY(pl.split_lo.reserve(sizeof(int64_t) * split_lo_h.size()));
+                CU_TRY(cudaMemcpyAsync(pl.seg_lo.ptr, seg_lo_h.data(), sizeof(int64_t) * seg_lo_h.size(), cudaMemcpyHostToDevice, h->stream));
+                CU_TRY(cudaMemcpyAsync(pl.seg_len.ptr, seg_len_h.data(), sizeof(int32_t) * seg_len_h.size(), cudaMemcpyHostToDevice, h->stream));
+                CU_TRY(cudaMemcpyAsync(pl.seg_ptr.ptr, seg_ptr_h.data(), sizeof(int32_t) * seg_ptr_h.size(), cudaMemcpyHostToDevice, h->stream));
+                CU_TRY(cudaMemcpyAsync(pl.split_lo.ptr, split_lo_h.data(), sizeof(int64_t) * split_lo_h.size(), cudaMemcpyHostToDevice, h->stream));
+            }
         }
+        CU_TRY(cudaStreamSynchronize(h->stream));     // the host vectors go out of scope
         pl.lo = lo;
         pl.hi = hi;
         pl.cap = cap;
+        pl.allow_split = allow_split;
         pl.n_buckets = nbk;
         return HYPREC_OK;
+    }
+
+    // The heavy list of a plan as k x k systems in tensor memory (float32): segments of split rows first
+    // (split_partial_kernel + split_reduce_kernel), then one tc_chol_rows_kernel launch over the whole list.
+    int launch_heavy(bool user, double lambda, int64_t lo, int64_t hi, const RowPlan& pl, const T* fixed_ptr, const T* prior_ptr,
+                     cudaStream_t st, int slot) {
+        if constexpr (sizeof(T) == sizeof(float)) {
+            namespace tc = hyprec::tc;
+            const int nbk = pl.n_buckets;
+            const int64_t n_heavy = pl.bucket_off[nbk + 1] - pl.bucket_off[nbk];
+            if (n_heavy == 0) return HYPREC_OK;
+            const int32_t* list = pl.lists.template as<int32_t>() + pl.bucket_off[nbk];
+            if (pl.n_split > 0) {
+                const Csr& rows_csr = user ? csr : csc;
+                const tc::GramTcLayout lay = tc::gram_tc_layout(k);
+                if (lay.total > (size_t)h->max_smem) return fail(HYPREC_E_UNSUPPORTED, "split rows do not fit shared memory");
+                HY_TRY(ensure_dynamic_smem((const void*)tc::split_partial_kernel, (int)lay.total));
+                HY_TRY(split_partial.reserve(sizeof(float) * (size_t)pl.n_seg * k * k));
+                HY_TRY(split_pb.reserve(sizeof(float) * (size_t)pl.n_seg * k));
+                HY_TRY(split_gram.reserve(sizeof(float) * (size_t)pl.n_split * k * k));
+                HY_TRY(split_b.reserve(sizeof(float) * (size_t)pl.n_split * k));
+                tc::SplitArgs a;
+                a.fixed = reinterpret_cast<const float*>(fixed_ptr);
+                a.indices = rows_csr.indices.template as<int32_t>();
+                a.values = rows_csr.values.template as<float>();
+                a.seg_lo = pl.seg_lo.template as<int64_t>();
+                a.seg_len = pl.seg_len.template as<int32_t>();
+                a.n_seg = pl.n_seg;
+                a.k = k;
+                a.partial = split_partial.as<float>();
+                a.partial_b = split_pb.as<float>();
+                a.work_counter = counter.as<int>() + kSplitCounterSlot;
+                const int grid = std::min(pl.n_seg, h->num_sms);
+                tc::split_partial_kernel<<<grid, 256, lay.total, st>>>(a);
+                const float ratio = (float)((hyprec::kConfPos - hyprec::kConfNeg) / hyprec::kConfNeg);
+                tc::split_reduce_kernel<<<dim3((unsigned)((k * k + 255) / 256), (unsigned)pl.n_split), 256, 0, st>>>(
+                    split_partial.as<float>(), split_pb.as<float>(), pl.seg_ptr.template as<int32_t>(),
+                    gram[user ? 1 : 0].template as<float>(), k, ratio, split_gram.as<float>(), split_b.as<float>());
+                h->launches += 2;
+                CU_TRY(cudaGetLastError());
+            }
+            return launch_chol_rows(user, lambda, lo, hi, list, n_heavy, false, k, reinterpret_cast<const float*>(fixed_ptr),
+                                    reinterpret_cast<const float*>(prior_ptr), n_heavy, st, slot, 0, pl.n_split,
+                                    pl.n_split ? pl.split_lo.template as<int64_t>() : nullptr,
+                                    pl.n_split ? split_gram.as<float>() : nullptr, pl.n_split ? split_b.as<float>() : nullptr);
+        } else {
+            (void)user; (void)lambda; (void)lo; (void)hi; (void)pl; (void)fixed_ptr; (void)prior_ptr; (void)st; (void)slot;
+            return fail(HYPREC_E_UNSUPPORTED, "tensor-memory rows are float32 only");
+        }
     }
 
     // L^-1 and L^-T (dense k x k, ALWAYS float64) of B = 0.1 G + lambda I, G = Gram of the fixed side.
@@ -766,33 +966,58 @@ struct Engine : EngineBase {
     // is assembled by block forward substitution.  In float32 mode the Gram is recomputed in float64
     // from a float64 copy of the fixed side (the whitening must not see float32 rounding of B), and
     // float32 copies of L^-1 / L^-T are made for the whitening GEMMs.
+    // float64 Gram of rows [r_lo, r_hi) of a rows x k factor matrix (any factor dtype) into out (k x k).
+    int gram64_rows(const T* y, int64_t r_lo, int64_t r_hi, double* out) {
+        namespace hp = hyprec;
+        const int64_t rows = r_hi - r_lo;
+        if (rows <= 0) {
+            CU_TRY(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)k * k, h->stream));
+            return HYPREC_OK;
+        }
+        const double* src = nullptr;
+        if constexpr (sizeof(T) == sizeof(double)) {
+            src = reinterpret_cast<const double*>(y) + r_lo * k;
+        } else {
+            HY_TRY(fixed_d.reserve(sizeof(double) * (size_t)rows * k));
+            const int64_t cnt = rows * k;
+            hp::cast_kernel<T, double><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(y + r_lo * k, cnt, fixed_d.as<double>());
+            h->launches += 1;
+            src = fixed_d.as<double>();
+        }
+        const int ntile = (k + hp::kGramTile - 1) / hp::kGramTile, tiles_g = hp::tri(ntile);
+        int nsplit = (int)std::min<int64_t>((rows + 255) / 256, std::max(1, (4 * h->num_sms) / tiles_g));
+        nsplit = std::max(nsplit, 1);
+        int64_t per = (rows + nsplit - 1) / nsplit;
+        per = (per + hp::kGramRows - 1) / hp::kGramRows * hp::kGramRows;
+        nsplit = (int)((rows + per - 1) / per);
+        HY_TRY(gram_partial_d.reserve(sizeof(double) * (size_t)nsplit * k * k));
+        hp::gram_partial_kernel<double><<<dim3(tiles_g, nsplit), hp::kGramThreads, 0, h->stream>>>(src, rows, k, per,
+                                                                                                  gram_partial_d.as<double>());
+        hp::gram_reduce_kernel<double><<<(k * k + 255) / 256, 256, 0, h->stream>>>(gram_partial_d.as<double>(), nsplit, k, out);
+        h->launches += 2;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
     int compute_linv(bool user, double lambda, const T* fixed_ptr, int64_t n_fixed) {
+        const double* gram_d = nullptr;
+        if (sizeof(T) == sizeof(double)) {
+            gram_d = gram[user ? 1 : 0].template as<double>();
+        } else {
+            HY_TRY(gram_dbuf.reserve(sizeof(double) * (size_t)k * k));
+            HY_TRY(gram64_rows(fixed_ptr, 0, n_fixed, gram_dbuf.as<double>()));
+            gram_d = gram_dbuf.as<double>();
+        }
+        return linv_from_gram(gram_d, lambda);
+    }
+
+    // L^-1 / L^-T of B = 0.1 G + lambda I from the float64 Gram G (see the comment above compute_linv).
+    int linv_from_gram(const double* gram_d, double lambda) {
         namespace hp = hyprec;
         HY_TRY(linv.reserve(sizeof(double) * (size_t)k * k));
         HY_TRY(linv_t.reserve(sizeof(double) * (size_t)k * k));
         HY_TRY(dummy_ptr.reserve(2 * sizeof(int64_t)));
         CU_TRY(cudaMemsetAsync(dummy_ptr.ptr, 0, 2 * sizeof(int64_t), h->stream));
-        const double* gram_d = nullptr;
-        if (sizeof(T) == sizeof(double)) {
-            gram_d = gram[user ? 1 : 0].template as<double>();
-        } else {
-            HY_TRY(fixed_d.reserve(sizeof(double) * (size_t)n_fixed * k));
-            const int64_t cnt = n_fixed * k;
-            hp::cast_kernel<T, double><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(fixed_ptr, cnt, fixed_d.as<double>());
-            const int ntile = (k + hp::kGramTile - 1) / hp::kGramTile, tiles_g = hp::tri(ntile);
-            int nsplit = (int)std::min<int64_t>((n_fixed + 255) / 256, std::max(1, (4 * h->num_sms) / tiles_g));
-            int64_t per = (n_fixed + nsplit - 1) / nsplit;
-            per = (per + hp::kGramRows - 1) / hp::kGramRows * hp::kGramRows;
-            nsplit = (int)((n_fixed + per - 1) / per);
-            HY_TRY(gram_partial_d.reserve(sizeof(double) * (size_t)nsplit * k * k));
-            HY_TRY(gram_dbuf.reserve(sizeof(double) * (size_t)k * k));
-            hp::gram_partial_kernel<double><<<dim3(tiles_g, nsplit), hp::kGramThreads, 0, h->stream>>>(
-                fixed_d.as<double>(), n_fixed, k, per, gram_partial_d.as<double>());
-            hp::gram_reduce_kernel<double><<<(k * k + 255) / 256, 256, 0, h->stream>>>(gram_partial_d.as<double>(), nsplit, k,
-                                                                                     gram_dbuf.as<double>());
-            h->launches += 3;
-            gram_d = gram_dbuf.as<double>();
-        }
         const bool whole = hp::solve_layout(8, k, 8, true, sizeof(double)).total <= (size_t)h->max_smem;
         const int r = whole ? 1 : (k + 191) / 192;
         const int bs0 = whole ? k : (((k + r - 1) / r) + 7) / 8 * 8;
@@ -885,6 +1110,7 @@ struct Engine : EngineBase {
         auto kern = hp::als_solve_rows_kernel<double, 8>;
         HY_TRY(ensure_dynamic_smem((const void*)kern, (int)lay.total));
         HY_TRY(dummy_out.reserve(sizeof(double) * (size_t)k));
+        HY_TRY(reserve_counters());
         CU_TRY(cudaMemsetAsync(counter.as<int>(), 0, sizeof(int), h->stream));   // slot 0
         hp::SolveArgs<double> a;
         a.indptr = dummy_ptr.as<int64_t>();
@@ -917,36 +1143,335 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+    // ---------------------------------------------------------------- multi-GPU exchange (comm.cuh)
+    struct Comm {
+        bool exported = false, on = false;
+        int rank = 0, world = 1;
+        void* arena = nullptr;
+        size_t bytes = 0, off_u = 0, off_v = 0, off_q[2] = {0, 0}, off_slots[2] = {0, 0}, off_scal = 0, off_flags = 0;
+        size_t slot_doubles = 0;
+        hyprec::PeerList peers;
+        std::vector<int64_t> ub, ib;
+        unsigned long long seq = 0;
+        int prep_side = -1;             // side whose L^-1 / whitened replica are current (-1: none)
+        double prep_lambda = -1.0;
+        bool q_ok[2] = {false, false};  // whitened replica of U / V complete on this rank
+        bool gram64_ok[2] = {false, false};
+        bool slots_have_rmse = false;   // the item side's slots carry (s1, s2) of the current factors
+        double comm_ms = 0.0;           // (statistics) bytes this rank stored into peers since attach
+        double bytes_pushed = 0.0;
+    };
+    Comm cm;
+    DevBuf gram64[2], slot_local, comm_status;
+    static constexpr unsigned long long kCommTimeoutNs = 30ull * 1000000000ull;
+
+    T* q_of(int side) {   // whitened replica of U (0) / V (1)
+        if (cm.exported) return reinterpret_cast<T*>(static_cast<unsigned char*>(cm.arena) + cm.off_q[side]);
+        return qmat.as<T>();
+    }
+
+    int comm_export(int rank, int world, void* blob, size_t blob_bytes) override {
+        if (k == 0) return fail(HYPREC_E_INVALID, "hyprec_comm_export before set_factors");
+        if (world < 1 || world > hyprec::kMaxRanks || rank < 0 || rank >= world)
+            return fail(HYPREC_E_INVALID, "hyprec_comm_export: world must be in [1, 8] and rank inside it");
+        if (blob_bytes < sizeof(CommBlob)) return fail(HYPREC_E_INVALID, "hyprec_comm_export: blob too small");
+        if (cm.exported) return fail(HYPREC_E_INVALID, "hyprec_comm_export: already exported (hyprec_comm_detach first)");
+        auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+        size_t o = 0;
+        cm.off_u = o;        o += up(sizeof(T) * (size_t)m * k);
+        cm.off_v = o;        o += up(sizeof(T) * (size_t)n * k);
+        cm.off_q[0] = o;     o += up(sizeof(T) * (size_t)m * k);
+        cm.off_q[1] = o;     o += up(sizeof(T) * (size_t)n * k);
+        cm.slot_doubles = (size_t)k * k + 8;
+        cm.off_slots[0] = o; o += up(sizeof(double) * cm.slot_doubles * world);
+        cm.off_slots[1] = o; o += up(sizeof(double) * cm.slot_doubles * world);
+        cm.off_scal = o;     o += up(sizeof(double) * 8 * world);
+        cm.off_flags = o;    o += up(sizeof(unsigned long long) * hyprec::kMaxRanks);
+        cm.bytes = o;
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        CU_TRY(cudaMalloc(&cm.arena, cm.bytes));
+        unsigned char* base = static_cast<unsigned char*>(cm.arena);
+        CU_TRY(cudaMemset(base + cm.off_q[0], 0, cm.bytes - cm.off_q[0]));
+        CU_TRY(cudaMemcpy(base + cm.off_u, U.ptr, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice));
+        CU_TRY(cudaMemcpy(base + cm.off_v, V.ptr, sizeof(T) * (size_t)n * k, cudaMemcpyDeviceToDevice));
+        U.adopt(base + cm.off_u, sizeof(T) * (size_t)m * k);
+        V.adopt(base + cm.off_v, sizeof(T) * (size_t)n * k);
+        CommBlob b;
+        memset(&b, 0, sizeof(b));
+        b.magic = kCommMagic;
+        CU_TRY(cudaIpcGetMemHandle(&b.handle, cm.arena));
+        b.m = m; b.n = n; b.k = k; b.elem = sizeof(T); b.world = world; b.rank = rank; b.arena_bytes = (long long)cm.bytes;
+        memcpy(blob, &b, sizeof(b));
+        cm.rank = rank;
+        cm.world = world;
+        cm.exported = true;
+        cm.on = false;
+        return HYPREC_OK;
+    }
+
+    int comm_attach(const void* blobs, size_t blob_bytes, const int64_t* user_bounds, const int64_t* item_bounds) override {
+        if (!cm.exported) return fail(HYPREC_E_INVALID, "hyprec_comm_attach before hyprec_comm_export");
+        if (cm.on) return fail(HYPREC_E_INVALID, "hyprec_comm_attach: already attached");
+        if (blob_bytes < sizeof(CommBlob) || !blobs || !user_bounds || !item_bounds)
+            return fail(HYPREC_E_INVALID, "hyprec_comm_attach: bad arguments");
+        if (user_bounds[0] != 0 || user_bounds[cm.world] != m || item_bounds[0] != 0 || item_bounds[cm.world] != n)
+            return fail(HYPREC_E_INVALID, "hyprec_comm_attach: bounds must run from 0 to the number of rows");
+        for (int r = 0; r < cm.world; ++r)
+            if (user_bounds[r + 1] < user_bounds[r] || item_bounds[r + 1] < item_bounds[r])
+                return fail(HYPREC_E_INVALID, "hyprec_comm_attach: bounds must be monotone");
+        memset(&cm.peers, 0, sizeof(cm.peers));
+        cm.peers.world = cm.world;
+        cm.peers.rank = cm.rank;
+        for (int r = 0; r < cm.world; ++r) {
+            CommBlob b;
+            memcpy(&b, static_cast<const unsigned char*>(blobs) + (size_t)r * blob_bytes, sizeof(b));
+            if (b.magic != kCommMagic || b.rank != r || b.world != cm.world || b.m != m || b.n != n || b.k != k ||
+                b.elem != (long long)sizeof(T) || b.arena_bytes != (long long)cm.bytes)
+                return fail(HYPREC_E_INVALID, "hyprec_comm_attach: rank " + std::to_string(r) + " published a different problem");
+            if (r == cm.rank) {
+                cm.peers.base[r] = cm.arena;
+            } else {
+                void* ptr = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    for (int q = 0; q < r; ++q)
+                        if (q != cm.rank && cm.peers.base[q]) cudaIpcCloseMemHandle(cm.peers.base[q]);
+                    cudaGetLastError();
+                    return fail(HYPREC_E_CUDA, std::string("cudaIpcOpenMemHandle (peer ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+                }
+                cm.peers.base[r] = ptr;
+            }
+        }
+        cm.ub.assign(user_bounds, user_bounds + cm.world + 1);
+        cm.ib.assign(item_bounds, item_bounds + cm.world + 1);
+        h->user_lo = cm.ub[cm.rank]; h->user_hi = cm.ub[cm.rank + 1];
+        h->item_lo = cm.ib[cm.rank]; h->item_hi = cm.ib[cm.rank + 1];
+        HY_TRY(gram64[0].reserve(sizeof(double) * (size_t)k * k));
+        HY_TRY(gram64[1].reserve(sizeof(double) * (size_t)k * k));
+        HY_TRY(slot_local.reserve(sizeof(double) * cm.slot_doubles));
+        HY_TRY(comm_status.reserve(sizeof(int) * 4));
+        CU_TRY(cudaMemsetAsync(comm_status.ptr, 0, sizeof(int) * 4, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        cm.seq = 0;
+        cm.prep_side = -1;
+        cm.q_ok[0] = cm.q_ok[1] = false;
+        cm.gram64_ok[0] = cm.gram64_ok[1] = false;
+        cm.slots_have_rmse = false;
+        cm.bytes_pushed = 0.0;
+        plan[0].lo = plan[1].lo = -1;
+        cm.on = true;
+        return HYPREC_OK;
+    }
+
+    int comm_detach() override {
+        if (!cm.exported) return HYPREC_OK;
+        cudaStreamSynchronize(h->stream);
+        if (cm.on)
+            for (int r = 0; r < cm.world; ++r)
+                if (r != cm.rank && cm.peers.base[r]) cudaIpcCloseMemHandle(cm.peers.base[r]);
+        cm.on = false;
+        // the factor matrices move back into buffers of their own (the arena is freed; peers must have detached
+        // -- the caller puts a process barrier between the ranks' detach calls and anything that reuses memory)
+        DevBuf nu, nv;
+        HY_TRY(nu.reserve(sizeof(T) * (size_t)m * k));
+        HY_TRY(nv.reserve(sizeof(T) * (size_t)n * k));
+        CU_TRY(cudaMemcpy(nu.ptr, U.ptr, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice));
+        CU_TRY(cudaMemcpy(nv.ptr, V.ptr, sizeof(T) * (size_t)n * k, cudaMemcpyDeviceToDevice));
+        U.release(); V.release();
+        U = nu; V = nv;
+        cudaFree(cm.arena);
+        cm.arena = nullptr;
+        cm.exported = false;
+        h->user_lo = 0; h->user_hi = -1; h->item_lo = 0; h->item_hi = -1;
+        gram_ok[0] = gram_ok[1] = false;
+        cross_valid = false;
+        plan[0].lo = plan[1].lo = -1;
+        return HYPREC_OK;
+    }
+
+    bool comm_active() const override { return cm.on; }
+
+    int comm_stats(double* out8) override {
+        for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+        out8[0] = cm.on ? 1.0 : 0.0;
+        out8[1] = cm.bytes_pushed;
+        out8[2] = (double)cm.seq;
+        out8[3] = (double)cm.bytes;
+        return HYPREC_OK;
+    }
+
+    // every store this rank issued so far is visible to its peers; every peer has done the same
+    int comm_barrier() {
+        ++cm.seq;
+        hyprec::comm_signal_kernel<<<1, 32, 0, h->stream>>>(cm.peers, cm.off_flags, cm.seq);
+        hyprec::comm_wait_kernel<<<1, 32, 0, h->stream>>>(cm.peers, cm.off_flags, cm.seq, kCommTimeoutNs, comm_status.as<int>());
+        h->launches += 2;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
+    hyprec::PeerList other_peers_as_list() const { return cm.peers; }
+
+    // rows [lo, hi) or a row list of U (side 0) / V (side 1): local replica -> every other replica
+    int comm_push_rows(int side, int64_t lo, int64_t n_rows, const int32_t* list) {
+        if (n_rows <= 0 || cm.world == 1) return HYPREC_OK;
+        const int grid = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)h->num_sms * 8);
+        hyprec::push_rows_kernel<T><<<grid, 256, 0, h->stream>>>(cm.peers, side == 0 ? cm.off_u : cm.off_v, k, lo, n_rows, list);
+        h->launches += 1;
+        cm.bytes_pushed += (double)n_rows * k * sizeof(T) * (cm.world - 1);
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
+
+    // peer destinations (other ranks' replicas at arena offset `off`) for the GEMM epilogues
+    int peer_outputs(size_t off, void** out7) const {
+        int c = 0;
+        for (int r = 0; r < cm.world; ++r)
+            if (r != cm.rank) out7[c++] = static_cast<unsigned char*>(cm.peers.base[r]) + off;
+        return c;
+    }
+
+    // Whitening state of side `f` without help from the peers (first half-step after set_factors, or a new
+    // lambda): float64 Gram of the whole replica, L^-1, whitened replica -- every rank computes the same.
+    int comm_prep_local(int f, double lambda, bool lowrank) {
+        const T* y = f == 0 ? U.as<T>() : V.as<T>();
+        const int64_t rows = f == 0 ? m : n;
+        if (!cm.gram64_ok[f]) {
+            Timer t(h, HYPREC_T_GRAM);
+            HY_TRY(gram64_rows(y, 0, rows, gram64[f].as<double>()));
+            HY_TRY(gram[f].reserve(sizeof(T) * (size_t)k * k));
+            if constexpr (sizeof(T) == sizeof(double)) {
+                CU_TRY(cudaMemcpyAsync(gram[f].ptr, gram64[f].ptr, sizeof(double) * (size_t)k * k, cudaMemcpyDeviceToDevice, h->stream));
+            } else {
+                const int64_t cnt = (int64_t)k * k;
+                hyprec::cast_kernel<double, T><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(gram64[f].as<double>(), cnt, gram[f].template as<T>());
+                h->launches += 1;
+            }
+            cm.gram64_ok[f] = true;
+            gram_ok[f] = true;
+        }
+        if (lowrank && !(cm.prep_side == f && cm.prep_lambda == lambda && cm.q_ok[f])) {
+            Timer t(h, HYPREC_T_PREP);
+            HY_TRY(linv_from_gram(gram64[f].as<double>(), lambda));
+            HY_TRY(whiten_gemm(y, rows, linv_T(), q_of(f), nullptr));
+            cm.prep_side = f;
+            cm.prep_lambda = lambda;
+            cm.q_ok[f] = true;
+        }
+        return HYPREC_OK;
+    }
+
+    // After this rank solved rows [lo, hi) of side s: partial float64 Gram of those rows (+ the RMSE sums when the
+    // item half-step produced them) into every rank's mailbox, barrier, fixed-order reduction; then L^-1 of the new
+    // Gram, and the whitened rows of this shard stored into every replica from the GEMM epilogue; barrier.
+    int comm_post(int s, int64_t lo, int64_t hi, double lambda, bool lowrank, bool have_cross) {
+        T* y = s == 0 ? U.as<T>() : V.as<T>();
+        const int kk = k * k;
+        double* slot = slot_local.as<double>();
+        {
+            Timer t(h, HYPREC_T_GRAM);
+            HY_TRY(gram64_rows(y, lo, hi, slot));
+        }
+        CU_TRY(cudaMemsetAsync(slot + kk, 0, sizeof(double) * 8, h->stream));
+        if (s == 1 && have_cross) {
+            // sum over this rank's item rows of sum_j r_j (u_j . v_i) and of r^2 (fixed order)
+            Timer t(h, HYPREC_T_RMSE);
+            HY_TRY(row_s2.reserve(sizeof(double) * std::max<int64_t>(m, 1024)));
+            if (hi > lo) {
+                hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(cross.as<double>() + lo, hi - lo, slot + kk);
+                const int64_t e0 = csc.h_indptr[lo], cnt = csc.h_indptr[hi] - e0;
+                const int nblk = (int)std::min<int64_t>(1024, (cnt + 4095) / 4096);
+                if (nblk > 0) {
+                    hyprec::sumsq_partial_kernel<T><<<nblk, 256, 0, h->stream>>>(csc.values.template as<T>() + e0, cnt, row_s2.as<double>());
+                    hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s2.as<double>(), nblk, slot + kk + 1);
+                }
+                h->launches += 3;
+            }
+            hyprec::set_double_kernel<<<1, 1, 0, h->stream>>>(slot + kk + 2, 1.0);
+            h->launches += 1;
+        }
+        {
+            Timer t(h, HYPREC_T_COMM);
+            hyprec::push_slot_kernel<<<8, 256, 0, h->stream>>>(cm.peers, cm.off_slots[s], cm.slot_doubles, slot, kk + 8);
+            h->launches += 1;
+            cm.bytes_pushed += (double)(kk + 8) * 8.0 * (cm.world - 1);
+            HY_TRY(comm_barrier());
+            const double* slots = reinterpret_cast<const double*>(static_cast<unsigned char*>(cm.arena) + cm.off_slots[s]);
+            HY_TRY(gram[s].reserve(sizeof(T) * (size_t)k * k));
+            hyprec::reduce_slots_kernel<T><<<(kk + 255) / 256, 256, 0, h->stream>>>(slots, cm.slot_doubles, cm.world, kk,
+                                                                                  gram64[s].as<double>(), gram[s].template as<T>());
+            h->launches += 1;
+            CU_TRY(cudaGetLastError());
+        }
+        cm.gram64_ok[s] = true;
+        gram_ok[s] = true;
+        if (s == 1) cm.slots_have_rmse = true;   // whether every rank's slot is valid is read from the slots themselves
+        if (lowrank) {
+            Timer t(h, HYPREC_T_PREP);
+            HY_TRY(linv_from_gram(gram64[s].as<double>(), lambda));
+            // whitened rows of this shard -> every replica (the all-gather is the GEMM's epilogue)
+            if (hi > lo) {
+                void* peers7[7];
+                const int np = peer_outputs(cm.off_q[s] + sizeof(T) * (size_t)lo * k, peers7);
+                HY_TRY(whiten_gemm(y + lo * k, hi - lo, linv_T(), q_of(s) + lo * k, nullptr, peers7, np));
+                cm.bytes_pushed += (double)(hi - lo) * k * sizeof(T) * np;
+            }
+            cm.prep_side = s;
+            cm.prep_lambda = lambda;
+            cm.q_ok[s] = true;
+        } else {
+            cm.q_ok[s] = false;
+        }
+        {
+            Timer t(h, HYPREC_T_COMM);
+            HY_TRY(comm_barrier());
+        }
+        return HYPREC_OK;
+    }
+
     int half_step(int side, double lambda) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "als_half_step before set_factors");
         if (side != HYPREC_SIDE_USER && side != HYPREC_SIDE_ITEM) return fail(HYPREC_E_INVALID, "side must be 0 or 1");
         const bool user = side == HYPREC_SIDE_USER;
+        const bool comm = cm.on;
+        const int fside = user ? 1 : 0;          // the fixed side's index (0: U, 1: V)
+        const int sside = user ? 0 : 1;          // the side being solved
         const int64_t total = user ? m : n;
         const int64_t n_fixed = user ? n : m;
         int64_t lo = user ? h->user_lo : h->item_lo, hi = user ? h->user_hi : h->item_hi;
         if (hi < 0) { lo = 0; hi = total; }
         if (lo < 0 || hi > total || lo > hi) return fail(HYPREC_E_INVALID, "shard outside the matrix");
 
-        HY_TRY(compute_gram(user ? 1 : 0));   // Gram of the FIXED side
+        // The low-rank path pays off when rows have fewer positives than k.  Its whitening
+        // (L^-1 of 0.1 G + lambda I) is always computed in float64; the deg x deg systems themselves
+        // are well conditioned and run in the factor dtype.
+        const bool lowrank = h->lowrank_enabled && lambda > 0.0 && k >= 16;
+        HY_TRY(reserve_counters());
+        if (comm) {
+            // every replica this half-step stores into is idle on its owner (evaluation, uploads)
+            {
+                Timer t(h, HYPREC_T_COMM);
+                HY_TRY(comm_barrier());
+            }
+            cm.slots_have_rmse = false;
+            HY_TRY(comm_prep_local(fside, lambda, lowrank));   // no-op when the previous half-step left it ready
+        } else {
+            HY_TRY(compute_gram(fside));   // Gram of the FIXED side
+        }
         const int nb = hyprec::aug_blocks(k), n_tiles = hyprec::tri(nb);
         HY_TRY(base.reserve(sizeof(T) * (size_t)hyprec::kTileElems * n_tiles));
         {
             const int total_e = hyprec::kTileElems * n_tiles;
             hyprec::build_base_tiles_kernel<T><<<(total_e + 255) / 256, 256, 0, h->stream>>>(
-                gram[user ? 1 : 0].as<T>(), k, (T)lambda, base.as<T>());
+                gram[fside].as<T>(), k, (T)lambda, base.as<T>());
             h->launches += 1;
         }
-        if (hi == lo) return HYPREC_OK;
-        HY_TRY(counter.reserve(16 * sizeof(int)));
-        CU_TRY(cudaMemsetAsync(counter.ptr, 0, 16 * sizeof(int), h->stream));
+        if (hi == lo && !comm) return HYPREC_OK;
+        CU_TRY(cudaMemsetAsync(counter.ptr, 0, 15 * sizeof(int), h->stream));   // (the status slot keeps what earlier steps raised)
         const T* fixed_ptr = user ? V.as<T>() : U.as<T>();
         const T* prior_ptr = (!user && has_prior) ? prior.as<T>() : nullptr;
         HY_TRY(ymat.reserve(sizeof(T)));
 
-        // The low-rank path pays off when rows have fewer positives than k.  Its whitening
-        // (L^-1 of 0.1 G + lambda I) is always computed in float64; the deg x deg systems themselves
-        // are well conditioned and run in the factor dtype.
-        const bool lowrank = h->lowrank_enabled && lambda > 0.0 && k >= 16;
         // float32 k x k systems (64 <= k <= 256) accumulate sum y y^T on the tensor cores (tc_syrk.cuh)
         const bool tc_direct = h->tc_solve_enabled && sizeof(T) == sizeof(float) && k >= 64 && k <= 256;
         const bool chol_direct = tc_direct && h->tc_chol_enabled && k % 4 == 0;
@@ -956,37 +1481,54 @@ struct Engine : EngineBase {
         const bool cross_wanted = !user && sizeof(T) == sizeof(float) && !has_prior && h->rmse_fused_enabled;
         auto begin_cross = [&]() -> int {
             HY_TRY(cross.reserve(sizeof(double) * (size_t)n));
-            CU_TRY(cudaMemsetAsync(cross.as<double>() + lo, 0, sizeof(double) * (size_t)(hi - lo), h->stream));
+            if (hi > lo) CU_TRY(cudaMemsetAsync(cross.as<double>() + lo, 0, sizeof(double) * (size_t)(hi - lo), h->stream));
             cross_active = true;
             return HYPREC_OK;
         };
-        if (!lowrank) {
-            if (cross_wanted && chol_direct) HY_TRY(begin_cross());
-            Timer t(h, HYPREC_T_SOLVE);
-            if constexpr (sizeof(T) == sizeof(float)) {
-                if (chol_direct)
-                    HY_TRY(launch_chol_rows(user, lambda, lo, hi, nullptr, 0, false, k, fixed_ptr, prior_ptr, hi - lo, h->stream, 0));
+        void* peers7[7];
+        const int n_peer_latent = comm ? peer_outputs(user ? cm.off_u : cm.off_v, peers7) : 0;
+        // (evaluated alike on every rank: a sharded run sums the ranks' parts, so all take the same branch)
+        const bool cross_cfg = cross_wanted && chol_direct &&
+                               (!lowrank || (h->tc_solve_enabled && h->tc_chol_enabled && h->tc_multi_enabled && k % 4 == 0));
+        if (hi == lo) {
+            // (comm, empty shard) nothing to solve; still takes part in the exchange below
+            if (cross_cfg) HY_TRY(begin_cross());
+        } else if (!lowrank) {
+            if (cross_cfg) HY_TRY(begin_cross());
+            {
+                Timer t(h, HYPREC_T_SOLVE);
+                if constexpr (sizeof(T) == sizeof(float)) {
+                    if (chol_direct) {
+                        HY_TRY(build_plan(user, lo, hi, -1, h->split_enabled));
+                        const RowPlan& pl = plan[user ? 0 : 1];
+                        HY_TRY(launch_heavy(user, lambda, lo, hi, pl, fixed_ptr, prior_ptr, h->stream, 0));
+                    }
+                }
+                if (!chol_direct)
+                    HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
+                                       nullptr, nullptr, hi - lo, h->stream, 0, 8, tc_direct));
             }
-            if (!chol_direct)
-                HY_TRY(launch_rows(user, lambda, lo, hi, nullptr, 0, false, k, hyprec::kSolveThreads, fixed_ptr, prior_ptr,
-                                   nullptr, nullptr, hi - lo, h->stream, 0, 8, tc_direct));
+            if (comm) {
+                Timer t(h, HYPREC_T_COMM);
+                HY_TRY(comm_push_rows(sside, lo, hi - lo, nullptr));
+            }
         } else {
             int cap = std::min(k, kBucketDim[usable_buckets() - 1]);
+            // float64: rows of 128..191 positives cost ~350 us in low-rank form against ~165 us as direct k x k rows
+            // when the k x k tiles fit shared memory (measured on B200, profiles/r02_lowrank_cap.md)
+            if (sizeof(T) == sizeof(double) && hyprec::solve_layout(8, k, 8, true, sizeof(double)).total <= (size_t)h->max_smem)
+                cap = std::min(cap, 127);
             if (h->lowrank_cap > 0) cap = std::min(cap, h->lowrank_cap);   // tuning knob, see DESIGN.md section 5
-            HY_TRY(build_plan(user, lo, hi, cap));
+            HY_TRY(build_plan(user, lo, hi, cap, chol_direct && h->split_enabled));
             const RowPlan& pl = plan[user ? 0 : 1];
             const int nbk = pl.n_buckets;
             const int32_t* lists = pl.lists.template as<int32_t>();
             const int64_t n_light = pl.bucket_off[nbk];
             const int64_t n_heavy = pl.bucket_off[nbk + 1] - pl.bucket_off[nbk];
-            HY_TRY(ymat.reserve(sizeof(T) * (size_t)total * k));
-            if (cross_wanted && h->tc_solve_enabled && h->tc_chol_enabled && h->tc_multi_enabled && k % 4 == 0 &&
-                (n_heavy == 0 || chol_direct)) {
-                bool all_tmem = true;
-                for (int b = 0; b < nbk; ++b)
-                    if (pl.bucket_off[b + 1] > pl.bucket_off[b] && pl.bucket_dim[b] > 256) all_tmem = false;
-                if (all_tmem) HY_TRY(begin_cross());
-            }
+            HY_TRY(ymat.reserve(sizeof(T) * (size_t)std::max<int64_t>(n_light, 1) * k));
+            // The fused cross term is used only under conditions every rank evaluates alike (a sharded run
+            // sums the ranks' parts): tensor-memory kernels for every bucket that can occur at this k.
+            if (cross_cfg) HY_TRY(begin_cross());
             // rows above the cap do not depend on the factor of B: start them right away on their
             // own stream (base tiles and counters are ready on the main stream)
             CU_TRY(cudaEventRecord(h->ev_base, h->stream));
@@ -994,8 +1536,7 @@ struct Engine : EngineBase {
                 CU_TRY(cudaStreamWaitEvent(h->aux[kHeavyStream], h->ev_base, 0));
                 if constexpr (sizeof(T) == sizeof(float)) {
                     if (chol_direct)
-                        HY_TRY(launch_chol_rows(user, lambda, lo, hi, lists + pl.bucket_off[nbk], n_heavy, false, k, fixed_ptr,
-                                                prior_ptr, n_heavy, h->aux[kHeavyStream], 1 + kMaxBuckets));
+                        HY_TRY(launch_heavy(user, lambda, lo, hi, pl, fixed_ptr, prior_ptr, h->aux[kHeavyStream], 1 + kMaxBuckets));
                 }
                 if (!chol_direct)
                     HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[nbk], n_heavy, false, k,
@@ -1006,16 +1547,20 @@ struct Engine : EngineBase {
             if (n_light > 0) {
                 {
                     Timer t(h, HYPREC_T_PREP);
-                    // 1-2. factor B = 0.1 G + lambda I = L L^T once and form L^-1, L^-T
-                    HY_TRY(compute_linv(user, lambda, fixed_ptr, n_fixed));
-                    // 3. whitened factors Q = Y L^-T (and theta L^-T for the item prior)
-                    HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
-                    HY_TRY(whiten_gemm(fixed_ptr, n_fixed, linv_T(), qmat.as<T>(), nullptr));
+                    if (!comm) {
+                        // 1-2. factor B = 0.1 G + lambda I = L L^T once and form L^-1, L^-T
+                        HY_TRY(compute_linv(user, lambda, fixed_ptr, n_fixed));
+                        // 3. whitened factors Q = Y L^-T
+                        HY_TRY(qmat.reserve(sizeof(T) * (size_t)n_fixed * k));
+                        HY_TRY(whiten_gemm(fixed_ptr, n_fixed, linv_T(), qmat.as<T>(), nullptr));
+                    }
+                    // (theta L^-T for the item prior)
                     if (prior_ptr) {
                         HY_TRY(pq.reserve(sizeof(T) * (size_t)total * k));
                         HY_TRY(whiten_gemm(prior_ptr, total, linv_T(), pq.as<T>(), nullptr));
                     }
                 }
+                const T* q_ptr = q_of(fside);
                 {
                     // 4. deg x deg systems, one launch per degree bucket, all buckets concurrently
                     Timer t(h, HYPREC_T_SOLVE);
@@ -1035,17 +1580,18 @@ struct Engine : EngineBase {
                         if constexpr (sizeof(T) == sizeof(float)) {
                             if (multi) {
                                 const int slot_rows = pl.bucket_dim[b] <= 32 ? 32 : (pl.bucket_dim[b] <= 64 ? 64 : 128);
-                                HY_TRY(launch_chol_multi(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, slot_rows, qmat.as<float>(),
+                                HY_TRY(launch_chol_multi(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, slot_rows,
+                                                         reinterpret_cast<const float*>(q_ptr),
                                                          prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b, pl.bucket_off[b]));
                             } else if (chol) {
                                 HY_TRY(launch_chol_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
-                                                        qmat.as<float>(), prior_ptr ? pq.as<float>() : nullptr, cnt, h->aux[b], 1 + b,
-                                                        pl.bucket_off[b]));
+                                                        reinterpret_cast<const float*>(q_ptr), prior_ptr ? pq.as<float>() : nullptr, cnt,
+                                                        h->aux[b], 1 + b, pl.bucket_off[b]));
                             }
                         }
                         if (!chol && !multi)
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
-                                           tc ? hyprec::kSolveThreads : kBucketThreads[b], qmat.as<T>(),
+                                           tc ? hyprec::kSolveThreads : kBucketThreads[b], q_ptr,
                                            prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
                                            kBucketTile[b], tc, pl.bucket_off[b]));
                         CU_TRY(cudaEventRecord(h->ev_join[b], h->aux[b]));
@@ -1053,37 +1599,136 @@ struct Engine : EngineBase {
                     }
                 }
                 {
-                    // 5. x = L^-T y for the low-rank rows: one GEMM straight into the factor matrix
+                    // 5. x = L^-T y for the low-rank rows: one GEMM straight into the factor matrix -- and, in a
+                    // multi-GPU run, into every other rank's replica (the exchange is this GEMM's epilogue)
                     Timer t(h, HYPREC_T_PREP);
                     T* latent = user ? U.as<T>() : V.as<T>();
-                    HY_TRY(whiten_gemm(ymat.as<T>(), n_light, linv_t_T(), latent, lists));
+                    HY_TRY(whiten_gemm(ymat.as<T>(), n_light, linv_t_T(), latent, lists, peers7, n_peer_latent));
+                    if (comm) cm.bytes_pushed += (double)n_light * k * sizeof(T) * n_peer_latent;
                 }
             }
             if (n_heavy > 0) {
                 Timer t(h, HYPREC_T_SOLVE);   // whatever of the heavy rows' launch is still running
                 CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[kHeavyStream], 0));
             }
+            if (comm && n_heavy > 0) {
+                Timer t(h, HYPREC_T_COMM);
+                HY_TRY(comm_push_rows(sside, 0, n_heavy, lists + pl.bucket_off[nbk]));
+            }
         }
-        gram_ok[user ? 0 : 1] = false;
+        gram_ok[sside] = false;
+        const bool have_cross = cross_active;
         if (cross_active) {
             cross_active = false;
             cross_valid = true;
             cross_lo = lo;
             cross_hi = hi;
         }
+        if (comm) {
+            cm.gram64_ok[sside] = false;
+            cm.q_ok[sside] = false;
+            HY_TRY(comm_post(sside, lo, hi, lambda, lowrank, have_cross));
+            return HYPREC_OK;    // status words are read with the RMSE (no host synchronisation inside an epoch)
+        }
+        return read_status("als_half_step");
+    }
+
+    int reserve_counters() {
+        if (counter.ptr != nullptr) return HYPREC_OK;
+        HY_TRY(counter.reserve(16 * sizeof(int)));
+        CU_TRY(cudaMemsetAsync(counter.ptr, 0, 16 * sizeof(int), h->stream));
+        return HYPREC_OK;
+    }
+
+    // status slot of the row kernels (1: non-finite solution) and of the exchange (2: a peer never arrived)
+    int read_status(const char* where) {
         int status[16] = {0};
+        int cstat[4] = {0};
         CU_TRY(cudaMemcpyAsync(status, counter.ptr, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
+        if (cm.on) CU_TRY(cudaMemcpyAsync(cstat, comm_status.ptr, sizeof(cstat), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
-        if (status[kStatusSlot] != 0)
-            return fail(HYPREC_E_SINGULAR, "als_half_step: non-finite solution (singular normal matrix; lambda == 0?)");
+        if (cstat[0] != 0)
+            return fail(HYPREC_E_CUDA, std::string(where) + ": a peer GPU did not reach the exchange barrier within 30 s");
+        if (status[kStatusSlot] != 0) {
+            CU_TRY(cudaMemsetAsync(counter.as<int>() + kStatusSlot, 0, sizeof(int), h->stream));
+            return fail(HYPREC_E_SINGULAR, std::string(where) + ": non-finite solution (singular normal matrix; lambda == 0?)");
+        }
         return HYPREC_OK;
     }
 
     // ---------------------------------------------------------------- RMSE
     // out3 = { <U^T U, V^T V>_F, sum_nz r (u.v), sum_nz r^2 }; the two sparse sums cover the
     // handle's user shard only when shard_only (the caller all-reduces them across ranks).
+    // Sharded run with the exchange attached: the Gram matrices are the reduced mailbox sums (identical on
+    // every rank), the sparse sums are reduced over the ranks in rank order -- from the item half-step's
+    // mailbox when every rank's slot carries them, else from a pass over this rank's users plus one more
+    // mailbox round.  out3 holds GLOBAL sums: every rank computes the same RMSE bit for bit.
+    int rmse_terms_comm(double* out3) {
+        HY_TRY(reserve_counters());
+        for (int f = 0; f < 2; ++f)
+            if (!cm.gram64_ok[f]) HY_TRY(comm_prep_local(f, cm.prep_lambda, false));
+        HY_TRY(scalars.reserve(sizeof(double) * 8));
+        CU_TRY(cudaMemsetAsync(scalars.ptr, 0, sizeof(double) * 8, h->stream));
+        const int kk = k * k;
+        const double* slots_v = reinterpret_cast<const double*>(static_cast<unsigned char*>(cm.arena) + cm.off_slots[1]);
+        {
+            Timer t(h, HYPREC_T_RMSE);
+            hyprec::frob_inner_kernel<double><<<1, 1024, 0, h->stream>>>(gram64[0].as<double>(), gram64[1].as<double>(), kk, scalars.as<double>());
+            // scalars[1..3] = sum over ranks of (s1, s2, valid)
+            hyprec::reduce_slots_kernel<double><<<1, 32, 0, h->stream>>>(slots_v + kk, cm.slot_doubles, cm.world, 3,
+                                                                        scalars.as<double>() + 1, nullptr);
+            h->launches += 2;
+        }
+        double host[4] = {0, 0, 0, 0};
+        bool fused = false;
+        if (cm.slots_have_rmse) {
+            CU_TRY(cudaMemcpyAsync(host, scalars.ptr, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            HY_TRY(read_status("rmse"));
+            fused = host[3] == (double)cm.world;      // the same slots on every rank: the same decision everywhere
+        }
+        if (!fused) {
+            const int64_t lo = h->user_lo, hi = h->user_hi;
+            HY_TRY(row_s1.reserve(sizeof(double) * m));
+            HY_TRY(row_s2.reserve(sizeof(double) * std::max<int64_t>(m, 1024)));
+            double* slot = slot_local.as<double>();
+            CU_TRY(cudaMemsetAsync(slot, 0, sizeof(double) * 8, h->stream));
+            {
+                Timer t(h, HYPREC_T_RMSE);
+                if (hi > lo) {
+                    const int wpb = 8;
+                    const int64_t rows = hi - lo;
+                    hyprec::sddmm_row_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
+                        csr.indptr.template as<int64_t>() + lo, csr.indices.template as<int32_t>(),
+                        csr.values.template as<T>(), U.as<T>() + lo * k, V.as<T>(), k, rows, row_s1.as<double>(),
+                        row_s2.as<double>());
+                    hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s1.as<double>(), rows, slot);
+                    hyprec::reduce_sum_kernel<<<1, 1024, 0, h->stream>>>(row_s2.as<double>(), rows, slot + 1);
+                    h->launches += 3;
+                }
+            }
+            {
+                Timer t(h, HYPREC_T_COMM);
+                hyprec::push_slot_kernel<<<1, 32, 0, h->stream>>>(cm.peers, cm.off_scal, 8, slot, 8);
+                h->launches += 1;
+                HY_TRY(comm_barrier());
+                const double* sc = reinterpret_cast<const double*>(static_cast<unsigned char*>(cm.arena) + cm.off_scal);
+                hyprec::reduce_slots_kernel<double><<<1, 32, 0, h->stream>>>(sc, 8, cm.world, 2, scalars.as<double>() + 1, nullptr);
+                h->launches += 1;
+                // nobody may overwrite the scalar mailbox before every rank has read it
+                HY_TRY(comm_barrier());
+            }
+            CU_TRY(cudaMemcpyAsync(host, scalars.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            HY_TRY(read_status("rmse"));
+        }
+        out3[0] = host[0];
+        out3[1] = host[1];
+        out3[2] = host[2];
+        return HYPREC_OK;
+    }
+
     int rmse_terms(double* out3, bool shard_only) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "rmse before set_factors");
+        if (cm.on) return rmse_terms_comm(out3);
         int64_t lo = 0, hi = m;
         if (shard_only && h->user_hi >= 0) { lo = h->user_lo; hi = h->user_hi; }
         HY_TRY(compute_gram(0));
@@ -1642,7 +2287,7 @@ int check(hyprec_t* h) {
 
 extern "C" {
 
-int hyprec_abi_version(void) { return 1; }
+int hyprec_abi_version(void) { return 2; }
 
 const char* hyprec_last_error(void) { return g_error.c_str(); }
 
@@ -1693,6 +2338,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->tc_multi_enabled = !(tmu && tmu[0] == '0');
     const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");
     if (ps) h->prof_slot = atoi(ps);
+    const char* spl = getenv("HYPREC_SPLIT");
+    h->split_enabled = !(spl && spl[0] == '0');
     const char* lr = getenv("HYPREC_LOWRANK");
     h->lowrank_enabled = !(lr && lr[0] == '0');
     const char* lc = getenv("HYPREC_LOWRANK_CAP");
@@ -1717,6 +2364,8 @@ int hyprec_destroy(hyprec_t* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_base) cudaEventDestroy(h->ev_base);
     if (h->flush_buf) cudaFree(h->flush_buf);
+    for (int i = 0; i < 8; ++i)
+        if (h->marks[i]) cudaEventDestroy(h->marks[i]);
     cudaStreamDestroy(h->stream);
     delete h;
     return HYPREC_OK;
@@ -1776,8 +2425,9 @@ int hyprec_rmse_terms(hyprec_t* h, double* out3) {
 int hyprec_train(hyprec_t* h, int n_iter, double lambda, double start_error, hyprec_epoch_cb cb, void* user,
                  int* epochs_run, double* last_rmse) {
     HY_TRY(check(h));
-    if (h->user_hi >= 0 || h->item_hi >= 0)
-        return fail(HYPREC_E_INVALID, "hyprec_train with a shard set: loop hyprec_als_half_step and exchange shards instead");
+    if ((h->user_hi >= 0 || h->item_hi >= 0) && !h->engine->comm_active())
+        return fail(HYPREC_E_INVALID, "hyprec_train with a shard set but no exchange attached (hyprec_comm_attach): loop "
+                                      "hyprec_als_half_step and exchange the shards yourself");
     double error = start_error;
     int done = 0;
     for (int epoch = 1; epoch <= n_iter; ++epoch) {
@@ -1880,6 +2530,59 @@ int hyprec_host_free(hyprec_t* h, void* ptr) {
     HY_TRY(check(h));
     if (ptr) CU_TRY(cudaFreeHost(ptr));
     return HYPREC_OK;
+}
+
+int hyprec_mark(hyprec_t* h, int slot) {
+    HY_TRY(check(h));
+    if (slot < 0 || slot >= 8) return fail(HYPREC_E_INVALID, "hyprec_mark: slot must be in [0, 8)");
+    if (!h->marks[slot]) CU_TRY(cudaEventCreate(&h->marks[slot]));
+    CU_TRY(cudaEventRecord(h->marks[slot], h->stream));
+    return HYPREC_OK;
+}
+
+int hyprec_elapsed_ms(hyprec_t* h, int from, int to, double* ms) {
+    HY_TRY(check(h));
+    if (from < 0 || from >= 8 || to < 0 || to >= 8 || !h->marks[from] || !h->marks[to] || !ms)
+        return fail(HYPREC_E_INVALID, "hyprec_elapsed_ms: both slots must have been marked");
+    CU_TRY(cudaEventSynchronize(h->marks[to]));
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, h->marks[from], h->marks[to]));
+    *ms = (double)f;
+    return HYPREC_OK;
+}
+
+int hyprec_comm_blob_bytes(void) { return (int)sizeof(CommBlob); }
+
+int hyprec_comm_export(hyprec_t* h, int rank, int world, void* blob, size_t blob_bytes) {
+    HY_TRY(check(h));
+    if (!blob) return fail(HYPREC_E_INVALID, "hyprec_comm_export: null blob");
+    return h->engine->comm_export(rank, world, blob, blob_bytes);
+}
+
+int hyprec_comm_attach(hyprec_t* h, const void* blobs, size_t blob_bytes, const int64_t* user_bounds, const int64_t* item_bounds) {
+    HY_TRY(check(h));
+    return h->engine->comm_attach(blobs, blob_bytes, user_bounds, item_bounds);
+}
+
+int hyprec_comm_detach(hyprec_t* h) {
+    HY_TRY(check(h));
+    return h->engine->comm_detach();
+}
+
+int hyprec_comm_stats(hyprec_t* h, double* out8) {
+    HY_TRY(check(h));
+    if (!out8) return fail(HYPREC_E_INVALID, "hyprec_comm_stats: null output");
+    return h->engine->comm_stats(out8);
+}
+
+int hyprec_init_factors_uniform(hyprec_t* h, int k, uint64_t seed) {
+    HY_TRY(check(h));
+    return h->engine->init_factors_uniform(k, (unsigned long long)seed);
+}
+
+int hyprec_get_factor_rows(hyprec_t* h, int side, const int64_t* rows, int64_t n_rows, double* out) {
+    HY_TRY(check(h));
+    return h->engine->get_factor_rows(side, rows, n_rows, out);
 }
 
 int hyprec_flush_l2(hyprec_t* h) {

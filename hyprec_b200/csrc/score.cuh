@@ -31,6 +31,10 @@ struct SweepArgs {
                                      // dense_out[row_list[r] * n_items] instead of row r - user_lo
     const double* thresholds;        // [n_users]                           (kSweepCount)
     unsigned long long* counts;      // [user_hi-user_lo], zeroed by caller (kSweepCount)
+    // Multi-GPU (comm.cuh, kSweepStore): the tile is also stored into these replicas of the output on
+    // the other GPUs (NVLink peer memory); same element type as the local output.
+    int n_peer = 0;
+    void* peer_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // grid = (item tiles, user tiles); 16 x 16 threads, each an 8 x 8 set of outputs interleaved
@@ -90,6 +94,10 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
                     if (col < p.n_items) {
                         if (p.dense_out_f32) p.dense_out_f32[dst * p.n_items + col] = (float)acc[a][b];
                         else p.dense_out[dst * p.n_items + col] = (double)acc[a][b];
+                        for (int rep = 0; rep < p.n_peer; ++rep) {
+                            if (p.dense_out_f32) static_cast<float*>(p.peer_out[rep])[dst * p.n_items + col] = (float)acc[a][b];
+                            else static_cast<double*>(p.peer_out[rep])[dst * p.n_items + col] = (double)acc[a][b];
+                        }
                     }
                 }
             }

@@ -52,6 +52,15 @@ struct CholRowsArgs {
     double* cross_out;        // optional [n_rows]: sum_j r_j (fixed_j . x) of the row -- the RMSE cross term, a by-product
                               // of the solve (b.x = |L^-1 b|^2; low-rank form: (|r|^2 - |z|^2) / 0.9); no prior
     long long* prof;          // optional clock64() phase totals of block 0
+    // Direct rows whose positives are split over several CTAs (tc_syrk.cuh split_partial_kernel): work items
+    // w < n_split start their own accumulation at positive split_lo[w] (absolute offset into `indices`) and add
+    // what the partial kernel accumulated over the positives before it:
+    //   split_gram[w] = G + 9 sum_rest y y^T  (dense k x k, takes the place of `gram`: 0.1 * it = 0.1 G + 0.9 sum_rest)
+    //   split_b[w]    = sum_rest r y
+    int n_split = 0;
+    const int64_t* split_lo = nullptr;
+    const float* split_gram = nullptr;
+    const float* split_b = nullptr;
 };
 
 struct CholLayout {
@@ -294,8 +303,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
         if (s_row >= n_work) break;
         const int64_t row = p.row_list ? (int64_t)p.row_list[s_row] : p.row_lo + s_row;
         if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) prof_t = clock64();
-        const int64_t lo = p.indptr[row];
+        const bool split = s_row < p.n_split;          // (direct mode only: the host plans it)
+        const int64_t lo = split ? p.split_lo[s_row] : p.indptr[row];
         const int deg = (int)(p.indptr[row + 1] - lo);
+        const float* gram_mat = split ? p.split_gram + (size_t)s_row * k * k : p.gram;
         float* out = p.out + (lowrank ? p.out_row0 + s_row : row) * k;
         const float* prior_row = p.prior ? p.prior + row * k : nullptr;
         if (deg == 0 && (lowrank || prior_row == nullptr)) {
@@ -342,6 +353,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
                 tc_fence_after();
             }
             if (prior_row != nullptr && tid < k) bs[tid] += p.lambda * prior_row[tid];
+            if (split && tid < k) bs[tid] += p.split_b[(size_t)s_row * k + tid];
         }
         HYPREC_TCPROF(0)
         if (tid >= dim && tid < dimp) bs[tid] = 0.f;   // identity padding solves to zero
@@ -356,7 +368,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
         float4 g4[8];
         auto fetch_gram = [&](int c0) {
             if (!lowrank && tid < dim && tid >= c0) {
-                const float* grow = p.gram + (int64_t)tid * k + c0;
+                const float* grow = gram_mat + (int64_t)tid * k + c0;
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     g4[c] = (c0 + 4 * c < dim) ? __ldg(reinterpret_cast<const float4*>(grow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);

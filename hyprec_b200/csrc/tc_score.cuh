@@ -55,6 +55,10 @@ struct ScoreArgs {
     float* dense;                 // [m][dense_ld] float32 scores, or null
     int64_t dense_ld;
     const int32_t* row_map;       // optional: product row r is stored at dense row row_map[r]
+    // Multi-GPU (comm.cuh): the same rows also go into these replicas of the dense matrix on the other
+    // GPUs (NVLink peer memory) -- the all-gather of a freshly solved / whitened shard is this epilogue.
+    int n_dense_peer = 0;
+    float* dense_peer[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -265,15 +269,18 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                 if (row_ok) {
                     if (p.dense) {
                         const int64_t drow = p.row_map ? (int64_t)p.row_map[row] : row;
-                        float* dst = p.dense + drow * p.dense_ld + col0 + c;
-                        if (col0 + c + 32 <= p.dense_ld) {
+                        const int64_t doff = drow * p.dense_ld + col0 + c;
+                        for (int rep = 0; rep <= p.n_dense_peer; ++rep) {
+                            float* dst = (rep == 0 ? p.dense : p.dense_peer[rep - 1]) + doff;
+                            if (col0 + c + 32 <= p.dense_ld) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + c + j < p.dense_ld) dst[j] = __uint_as_float(v[j]);
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                        __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            } else {
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + c + j < p.dense_ld) dst[j] = __uint_as_float(v[j]);
+                            }
                         }
                     }
                     if (p.counts) {

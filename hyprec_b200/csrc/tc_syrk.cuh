@@ -439,5 +439,110 @@ __global__ void gram_tc_reduce_kernel(const float* __restrict__ partial, int n_s
     g[(size_t)j * k + i] = (float)s;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Rows with tens of thousands of positives (popular items of the scaled workload) split over several
+// CTAs: every segment of such a row's positives is accumulated like a Gram slice -- the same
+// transposing tcgen05 accumulation, over the gathered factor rows indices[seg_lo .. seg_lo+seg_len) --
+// into partial[seg] (k x k, lower blocks) and partial_b[seg] = sum r y; split_reduce_kernel folds a
+// row's segments into the dense matrix tc_chol_rows_kernel adds in place of the shared Gram.  The
+// arithmetic is that of (Y.T * confidence).dot(Y) restricted to the row's positives
+// (/root/reference/lib/collaborative_filtering.py:84-86, :92), only distributed differently.
+// ------------------------------------------------------------------------------------------------
+struct SplitArgs {
+    const float* fixed;        // factors of the fixed side [.][k]
+    const int32_t* indices;    // CSR column ids of the side being solved
+    const float* values;       // ratings
+    const int64_t* seg_lo;     // [n_seg] first positive of the segment (absolute offset into indices)
+    const int32_t* seg_len;    // [n_seg]
+    int n_seg;
+    int k;
+    float* partial;            // [n_seg][k][k]
+    float* partial_b;          // [n_seg][k]
+    int* work_counter;         // zeroed before launch
+};
+
+__global__ void __launch_bounds__(256, 1) split_partial_kernel(SplitArgs p) {
+    extern __shared__ __align__(16) unsigned char split_smem_dyn[];
+    unsigned char* smem = split_smem_dyn + ((1024u - (smem_u32(split_smem_dyn) & 1023u)) & 1023u);
+    const int k = p.k;
+    const GramTcLayout lay = gram_tc_layout(k);
+    uint64_t* bars = (uint64_t*)(smem + lay.off_bar);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2);
+    float* bvec = (float*)(smem + lay.off_b);
+    __shared__ int s_seg;
+    const int tid = threadIdx.x, warp = tid / 32;
+    const uint32_t tmem_cols = (uint32_t)syrk_tmem_cols(k);
+    SyrkState st;
+    st.bars = bars;
+    st.phase[0] = st.phase[1] = 0;
+    st.stage = smem + lay.off_stage;
+    st.rows_pad = syrk_rows_pad(k);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    st.tmem_base = *tmem_slot;
+    const int npad = (k + 15) & ~15;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_seg = atomicAdd(p.work_counter, 1);
+        __syncthreads();
+        const int seg = s_seg;
+        if (seg >= p.n_seg) break;
+        const int len = p.seg_len[seg];
+        syrk_direct_accumulate(p.fixed, p.indices, p.values, p.seg_lo[seg], len, k, st, 1.f, npad, (int*)(smem + lay.off_idx),
+                               (float*)(smem + lay.off_rst), 256, bvec);
+        float* out = p.partial + (size_t)seg * k * k;
+        const int i = tid;
+        if (i < ((k + 31) & ~31)) {     // whole warps; row i: columns up to the end of its diagonal 32-block
+            const uint32_t taddr = st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tid >= 128 ? 128 : 0);
+            const int jmax = min(k, (i / 32) * 32 + 32);
+            for (int c = 0; c < jmax; c += 32) {
+                uint32_t v[32];
+                tmem_load_32x32(taddr + (uint32_t)c, v);
+                if (i < k) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj)
+                        if (c + jj < k) out[(size_t)i * k + c + jj] = __uint_as_float(v[jj]);
+                }
+            }
+        }
+        if (tid < k) p.partial_b[(size_t)seg * k + tid] = bvec[tid];
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(st.tmem_base, tmem_cols);
+}
+
+// split_gram[s][i][j] = gram[i][j] + ratio * sum_{segments of s} partial[.][max(i,j)][min(i,j)]  (ratio = 0.9 / 0.1),
+// split_b[s][a] = sum partial_b; grid = (ceil(k*k / 256), n_split).
+__global__ void split_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b,
+                                    const int32_t* __restrict__ seg_ptr, const float* __restrict__ gram, int k, float ratio,
+                                    float* __restrict__ split_gram, float* __restrict__ split_b) {
+    const int s = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s0 = seg_ptr[s], s1 = seg_ptr[s + 1];
+    if (idx < k) {
+        double b = 0.0;
+        for (int c = s0; c < s1; ++c) b += (double)partial_b[(size_t)c * k + idx];
+        split_b[(size_t)s * k + idx] = (float)b;
+    }
+    if (idx >= k * k) return;
+    const int i = idx / k, j = idx % k;
+    if (j > i) return;
+    double acc = 0.0;
+    for (int c = s0; c < s1; ++c) acc += (double)partial[(size_t)c * k * k + idx];
+    const float v = (float)((double)gram[idx] + (double)ratio * acc);
+    split_gram[(size_t)s * k * k + (size_t)i * k + j] = v;
+    split_gram[(size_t)s * k * k + (size_t)j * k + i] = v;
+}
+
 }  // namespace tc
 }  // namespace hyprec

@@ -75,6 +75,16 @@ int hyprec_get_factors(hyprec_t* h, double* user_vecs, double* item_vecs);
  * may be written through the pointers. */
 int hyprec_device_factors(hyprec_t* h, void** user_vecs_dev, void** item_vecs_dev, int* elem_size);
 
+/* The same initial state without a host copy, for problem sizes whose factors should stay on the device
+ * (BASELINE configs[3]: 3 GB of float32 factors): U and V drawn uniformly in [0, 1) from a counter-based
+ * generator -- element e = (float)(mix64(seed' * 0xD1342543DE82EF95 + e) >> 40) / 2^24 with seed' = seed for U
+ * and seed + 1 for V; oracle.als.uniform_factors restates it.  Stands for numpy.random.random((m, k)),
+ * numpy.random.random((n, k)) at collaborative_filtering.py:173-176. */
+int hyprec_init_factors_uniform(hyprec_t* h, int k, uint64_t seed);
+/* Rows `rows[0..n_rows)` of U (side 0) or V (side 1) as float64, n_rows x k: parity checks on a subsample of a
+ * problem whose full factors are never copied to the host. */
+int hyprec_get_factor_rows(hyprec_t* h, int side, const int64_t* rows, int64_t n_rows, double* out);
+
 /* self.document_distribution for the update_with_items rule (:93-96); NULL clears it. */
 int hyprec_set_item_prior(hyprec_t* h, const double* theta);
 
@@ -101,6 +111,31 @@ int hyprec_rmse_terms(hyprec_t* h, double* out3);
 typedef void (*hyprec_epoch_cb)(int epoch, double rmse, double seconds, void* user);
 int hyprec_train(hyprec_t* h, int n_iter, double lambda, double start_error, hyprec_epoch_cb cb,
                  void* user, int* epochs_run, double* last_rmse);
+
+/* ---- multi-GPU exchange over NVLink peer memory ----------------------------------------- */
+/* One process per GPU, one handle per process (the reference has no counterpart: what
+ * shards is the independence of rows inside als_step, collaborative_filtering.py:82-86).  After
+ * hyprec_set_train_csr + hyprec_set_factors (same data on every rank):
+ *   1. every rank calls hyprec_comm_export: its replicas of U, V and of the whitened factors plus a mailbox move
+ *      into one arena; `blob` (hyprec_comm_blob_bytes() bytes) receives the arena's CUDA IPC handle;
+ *   2. the caller all-gathers the blobs (any transport: torch.distributed, MPI, files);
+ *   3. every rank calls hyprec_comm_attach with all blobs in rank order and the row partition
+ *      (user_bounds / item_bounds: world + 1 ascending offsets from 0 to n_users / n_items; rank r owns
+ *      [bounds[r], bounds[r+1]) of each side).
+ * From then on hyprec_als_half_step solves the rank's rows and stores them into EVERY rank's replica from the
+ * epilogue of the kernel that produced them, reduces the k x k Gram through the mailbox, whitens its own rows into
+ * every replica and returns without synchronising the host; hyprec_rmse / hyprec_rmse_terms return the GLOBAL value
+ * (bit-identical on every rank) and hyprec_train runs the sharded epoch loop.  Every rank must issue the same
+ * sequence of half-step / rmse / train calls.  A peer that does not arrive within 30 s fails the next
+ * hyprec_rmse / hyprec_train with HYPREC_E_CUDA instead of hanging the GPU.
+ * hyprec_comm_detach (collective: put a process barrier before anything reuses the memory) undoes it. */
+int hyprec_comm_blob_bytes(void);
+int hyprec_comm_export(hyprec_t* h, int rank, int world, void* blob, size_t blob_bytes);
+int hyprec_comm_attach(hyprec_t* h, const void* blobs, size_t blob_bytes, const int64_t* user_bounds,
+                       const int64_t* item_bounds);
+int hyprec_comm_detach(hyprec_t* h);
+/* out8 = { attached (0/1), bytes this rank stored into peer replicas since attach, barriers passed, arena bytes, 0... } */
+int hyprec_comm_stats(hyprec_t* h, double* out8);
 
 /* ---- prediction / evaluation ------------------------------------------------------------ */
 /* get_predictions(): U.dot(V.T) (collaborative_filtering.py:270), n_users x n_items float64
@@ -166,7 +201,13 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
 #define HYPREC_T_FLAGS 5
 #define HYPREC_T_COUNT 6
 #define HYPREC_T_PREP 7   /* low-rank path: factor of 0.1 G + lambda I, L^-1, whitening / un-whitening GEMMs */
+#define HYPREC_T_COMM 8   /* multi-GPU: mailbox pushes, row pushes, exchange barriers (hyprec_comm_attach) */
 int hyprec_kernel_ms(hyprec_t* h, int which, double* total_ms, int64_t* calls, double* last_ms);
+/* Whole-region device timing for bench.py: hyprec_mark records CUDA event `slot` (0..7) on the library's stream
+ * behind everything issued so far; hyprec_elapsed_ms waits for event `to` and returns the device time between the
+ * two marks.  One clock for single-GPU and sharded epochs (the max over ranks is the caller's). */
+int hyprec_mark(hyprec_t* h, int slot);
+int hyprec_elapsed_ms(hyprec_t* h, int from, int to, double* ms);
 int hyprec_reset_kernel_ms(hyprec_t* h);
 /* Diagnostic (HYPREC_SOLVE_PROF=1 at hyprec_create): clock64() totals per phase of the direct row
  * solve, accumulated by block 0 -- out16[0..7] = gather+accumulate, base add, first diagonal tile,

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_the_header():
         assert hasattr(lib, name), name
     assert sorted(_native.EXPORTS) == names
     lib.hyprec_abi_version.restype = ctypes.c_int
-    assert lib.hyprec_abi_version() == 1
+    assert lib.hyprec_abi_version() == 2
 
 
 def test_no_cpu_fallback():

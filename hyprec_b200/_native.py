@@ -21,6 +21,7 @@ EXPORTS = [
     "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles", "hyprec_host_alloc", "hyprec_host_free",
     "hyprec_comm_blob_bytes", "hyprec_comm_export", "hyprec_comm_attach", "hyprec_comm_detach", "hyprec_comm_stats",
     "hyprec_init_factors_uniform", "hyprec_get_factor_rows", "hyprec_mark", "hyprec_elapsed_ms",
+    "hyprec_comm_arena", "hyprec_comm_attach_local",
 ]
 
 EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
@@ -82,6 +83,8 @@ def load_library(rebuild=False):
     lib.hyprec_comm_export.argtypes = [vp, c_int, c_int, vp, ctypes.c_size_t]
     lib.hyprec_comm_attach.argtypes = [vp, vp, ctypes.c_size_t, vp, vp]
     lib.hyprec_comm_detach.argtypes = [vp]
+    lib.hyprec_comm_arena.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    lib.hyprec_comm_attach_local.argtypes = [vp, vp, vp, vp, vp]
     lib.hyprec_comm_stats.argtypes = [vp, vp]
     lib.hyprec_init_factors_uniform.argtypes = [vp, c_int, ctypes.c_uint64]
     lib.hyprec_get_factor_rows.argtypes = [vp, c_int, vp, c_i64, vp]
@@ -182,6 +185,18 @@ class Handle(object):
             raise ValueError("every rank publishes one blob of %d bytes" % size)
         ub, ib = _as(user_bounds, numpy.int64), _as(item_bounds, numpy.int64)
         self._check(self._lib.hyprec_comm_attach(self._h, joined, size, _ptr(ub), _ptr(ib)))
+
+    def comm_arena(self):
+        base, size = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(self._lib.hyprec_comm_arena(self._h, ctypes.byref(base), ctypes.byref(size)))
+        return base.value, size.value
+
+    def comm_attach_local(self, arenas, devices, user_bounds, item_bounds):
+        """Peers in this process: ``arenas`` = every handle's comm_arena()[0] in rank order."""
+        ptrs = (ctypes.c_void_p * len(arenas))(*arenas)
+        devs = numpy.ascontiguousarray(devices, dtype=numpy.int32)
+        ub, ib = _as(user_bounds, numpy.int64), _as(item_bounds, numpy.int64)
+        self._check(self._lib.hyprec_comm_attach_local(self._h, ptrs, _ptr(devs), _ptr(ub), _ptr(ib)))
 
     def comm_detach(self):
         self._check(self._lib.hyprec_comm_detach(self._h))

@@ -353,12 +353,20 @@ class CollaborativeFiltering(AbstractRecommender):
         return users, items
 
     def _train_sharded(self, h, rank, world, error, on_epoch):
-        """The epoch loop of partial_train over row shards: one exchange of the solved rows after each
-        half-step, RMSE from per-shard partial sums, the same early-stop decision on every rank."""
+        """The epoch loop of partial_train over row shards.  With NVLink peer memory the library runs the whole
+        loop (hyprec_train: solved rows stored into every replica from the kernels' epilogues, Gram and RMSE
+        reduced through the mailbox, the same early-stop decision on every rank); otherwise one
+        torch.distributed exchange of the solved rows after each half-step."""
         from hyprec_b200 import distributed
         users, items = self._shard_bounds(world)
-        engine = distributed.NativeEngine(h, int(os.environ.get("HYPREC_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
-        als = distributed.ShardedALS(engine, users, items, rank, self.n_users, self.n_items)
+        device = int(os.environ.get("HYPREC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        als = distributed.make_sharded(h, device, rank, world, users, items, self.n_users, self.n_items)
+        if isinstance(als, distributed.NativeShardedALS):
+            try:
+                h.train(self.n_iter, self._lambda, error, on_epoch)
+            finally:
+                distributed.detach_exchange(h)
+            return
         try:
             for epoch in range(1, self.n_iter + 1):
                 old_error = error

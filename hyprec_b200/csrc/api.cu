@@ -129,6 +129,8 @@ struct EngineBase {
     virtual int comm_export(int rank, int world, void* blob, size_t blob_bytes) = 0;
     virtual int comm_attach(const void* blobs, size_t blob_bytes, const int64_t* user_bounds, const int64_t* item_bounds) = 0;
     virtual int comm_detach() = 0;
+    virtual int comm_attach_ptrs(void* const* bases, const int* devices, const int64_t* user_bounds, const int64_t* item_bounds) = 0;
+    virtual int comm_arena(void** base, size_t* bytes) = 0;
     virtual int init_factors_uniform(int k, unsigned long long seed) = 0;
     virtual int get_factor_rows(int side, const int64_t* rows, int64_t n_rows, double* out) = 0;
     virtual int comm_stats(double* out8) = 0;
@@ -258,7 +260,7 @@ struct Engine : EngineBase {
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
                          &u_hi, &u_lo, &v_hi, &v_lo, &unorm, &vnorm, &border_cells, &border_count, &dense_f32, &vmax_buf, &topk_spill, &hashed_counts};
         if (cm.exported) {
-            if (cm.on)
+            if (cm.on && cm.ipc)
                 for (int r = 0; r < cm.world; ++r)
                     if (r != cm.rank && cm.peers.base[r]) cudaIpcCloseMemHandle(cm.peers.base[r]);
             U.release();
@@ -1145,7 +1147,7 @@ struct Engine : EngineBase {
 
     // ---------------------------------------------------------------- multi-GPU exchange (comm.cuh)
     struct Comm {
-        bool exported = false, on = false;
+        bool exported = false, on = false, ipc = true;
         int rank = 0, world = 1;
         void* arena = nullptr;
         size_t bytes = 0, off_u = 0, off_v = 0, off_q[2] = {0, 0}, off_slots[2] = {0, 0}, off_scal = 0, off_flags = 0;
@@ -1242,6 +1244,47 @@ struct Engine : EngineBase {
                 cm.peers.base[r] = ptr;
             }
         }
+        cm.ipc = true;
+        return finish_attach(user_bounds, item_bounds);
+    }
+
+    // Peers that live in this process (one handle per GPU driven by one host process, or several handles on one
+    // GPU in the tests): their arenas are plain device pointers, no IPC mapping.
+    int comm_attach_ptrs(void* const* bases, const int* devices, const int64_t* user_bounds, const int64_t* item_bounds) override {
+        if (!cm.exported) return fail(HYPREC_E_INVALID, "hyprec_comm_attach_local before hyprec_comm_export");
+        if (cm.on) return fail(HYPREC_E_INVALID, "hyprec_comm_attach_local: already attached");
+        if (!bases || !devices || !user_bounds || !item_bounds) return fail(HYPREC_E_INVALID, "hyprec_comm_attach_local: bad arguments");
+        if (user_bounds[0] != 0 || user_bounds[cm.world] != m || item_bounds[0] != 0 || item_bounds[cm.world] != n)
+            return fail(HYPREC_E_INVALID, "hyprec_comm_attach_local: bounds must run from 0 to the number of rows");
+        for (int r = 0; r < cm.world; ++r)
+            if (user_bounds[r + 1] < user_bounds[r] || item_bounds[r + 1] < item_bounds[r])
+                return fail(HYPREC_E_INVALID, "hyprec_comm_attach_local: bounds must be monotone");
+        memset(&cm.peers, 0, sizeof(cm.peers));
+        cm.peers.world = cm.world;
+        cm.peers.rank = cm.rank;
+        for (int r = 0; r < cm.world; ++r) {
+            if (!bases[r]) return fail(HYPREC_E_INVALID, "hyprec_comm_attach_local: null arena");
+            if (r == cm.rank && bases[r] != cm.arena) return fail(HYPREC_E_INVALID, "hyprec_comm_attach_local: own arena mismatch");
+            if (devices[r] != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(HYPREC_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            cm.peers.base[r] = bases[r];
+        }
+        cm.ipc = false;
+        return finish_attach(user_bounds, item_bounds);
+    }
+
+    int comm_arena(void** base, size_t* bytes) override {
+        if (!cm.exported) return fail(HYPREC_E_INVALID, "hyprec_comm_arena before hyprec_comm_export");
+        if (base) *base = cm.arena;
+        if (bytes) *bytes = cm.bytes;
+        return HYPREC_OK;
+    }
+
+    int finish_attach(const int64_t* user_bounds, const int64_t* item_bounds) {
         cm.ub.assign(user_bounds, user_bounds + cm.world + 1);
         cm.ib.assign(item_bounds, item_bounds + cm.world + 1);
         h->user_lo = cm.ub[cm.rank]; h->user_hi = cm.ub[cm.rank + 1];
@@ -1266,7 +1309,7 @@ struct Engine : EngineBase {
     int comm_detach() override {
         if (!cm.exported) return HYPREC_OK;
         cudaStreamSynchronize(h->stream);
-        if (cm.on)
+        if (cm.on && cm.ipc)
             for (int r = 0; r < cm.world; ++r)
                 if (r != cm.rank && cm.peers.base[r]) cudaIpcCloseMemHandle(cm.peers.base[r]);
         cm.on = false;
@@ -2562,6 +2605,17 @@ int hyprec_comm_export(hyprec_t* h, int rank, int world, void* blob, size_t blob
 int hyprec_comm_attach(hyprec_t* h, const void* blobs, size_t blob_bytes, const int64_t* user_bounds, const int64_t* item_bounds) {
     HY_TRY(check(h));
     return h->engine->comm_attach(blobs, blob_bytes, user_bounds, item_bounds);
+}
+
+int hyprec_comm_arena(hyprec_t* h, void** base, size_t* bytes) {
+    HY_TRY(check(h));
+    return h->engine->comm_arena(base, bytes);
+}
+
+int hyprec_comm_attach_local(hyprec_t* h, void* const* arenas, const int* devices, const int64_t* user_bounds,
+                             const int64_t* item_bounds) {
+    HY_TRY(check(h));
+    return h->engine->comm_attach_ptrs(arenas, devices, user_bounds, item_bounds);
 }
 
 int hyprec_comm_detach(hyprec_t* h) {

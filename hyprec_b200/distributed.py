@@ -4,13 +4,21 @@ one exchange of the freshly solved factor rows after every half-step (SURVEY.md 
 
 The reference has no distributed code at all; what shards is the independence of rows inside
 ``als_step`` (/root/reference/lib/collaborative_filtering.py:82-86 reads only ``fixed_vecs``).
-Each rank keeps a full replica of U and V, solves a contiguous, cost-balanced range of users
-(user half-step) and of items (item half-step), and the ranges are exchanged through
-``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests).  The RMSE is reduced
-from per-shard partial sums.  Evaluation shards users; per-user integers are gathered on rank 0.
+Each rank keeps a full replica of U and V and solves a contiguous, cost-balanced range of users
+(user half-step) and of items (item half-step).
 
-The engine behind ``ShardedALS`` is anything with ``half_step`` / ``factor_tensors`` /
-``rmse_terms``: ``NativeEngine`` wraps the C-ABI handle, the CPU tests plug in an oracle-backed one.
+Two exchange paths:
+
+* ``attach_exchange`` + ``NativeShardedALS`` (the product path on GPUs): the library itself stores every
+  solved / whitened row into all replicas over NVLink peer memory from the epilogue of the kernel that
+  produced it, reduces the k x k Gram and the RMSE sums through a mailbox and orders the ranks with
+  device-side barriers (csrc/comm.cuh).  ``torch.distributed`` only carries the CUDA IPC handles at
+  set-up; nothing Python-side runs inside an epoch.
+* ``ShardedALS`` over an engine with ``half_step`` / ``factor_tensors`` / ``rmse_terms``: the exchange as
+  ``torch.distributed`` broadcasts (NCCL on GPUs -- the fallback when peer memory cannot be mapped -- and
+  gloo in the CPU tests, where an oracle-backed engine stands in for the device).
+
+Evaluation shards users; per-user integers are gathered on rank 0.
 """
 import numpy
 
@@ -156,138 +164,87 @@ class ShardedALS(object):
 
 
 # --------------------------------------------------------------------------------------------------
-# bench.py's N > 1 arm
+# exchange inside the library (NVLink peer memory)
 # --------------------------------------------------------------------------------------------------
-def bench_sharded(args, wl, rank, world, local, config, hooks=None):
-    import time
-    import torch
+def attach_exchange(handle, rank, world, user_bounds, item_bounds, group=None):
+    """Map every rank's exchange arena into every other rank (CUDA IPC handles carried by
+    ``all_gather_object``) and hand the row partition to the library.  Collective.  Returns True when every
+    rank attached; on any failure every rank detaches and False is returned (callers fall back to ShardedALS)."""
     import torch.distributed as dist
-    from hyprec_b200 import _native
-
-    torch.cuda.set_device(local)
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    precision = _native.F64 if args.precision == "fp64" else _native.F32
-    h = _native.Handle(local, precision)
-    m, n, k, lam = wl["m"], wl["n"], wl["k"], wl["lam"]
-    tr, te, fu = wl["train_csr"], wl["test_csr"], wl["full_csr"]
-    h.set_train_csr(m, n, tr.indptr, tr.indices, tr.data)
-    h.set_eval_csr((fu.indptr, fu.indices, fu.data), (te.indptr, te.indices, te.data))
-    h.set_factors(wl["u0"], wl["v0"])
-    user_bounds = partition_rows(tr.indptr, world, k)
-    item_bounds = partition_rows(csc_indptr(tr.indptr, tr.indices, n), world, k)
-    engine = NativeEngine(h, local)
-    als = ShardedALS(engine, user_bounds, item_bounds, rank, m, n)
-    ulo, uhi = user_bounds[rank], user_bounds[rank + 1]
-    has_eval = wl["cand_ids"] is not None
-    n_tr = int(tr.indptr[uhi] - tr.indptr[ulo])
-    n_te = int(te.indptr[uhi] - te.indptr[ulo])
-    if has_eval:
-        cp = wl["cand_indptr"][ulo:uhi + 1] - wl["cand_indptr"][ulo]
-        ci = wl["cand_ids"][wl["cand_indptr"][ulo]:wl["cand_indptr"][uhi]]
-        h.set_candidates(cp, ci, ulo, uhi)
-
-    def evaluate():
-        if has_eval:
-            return h.eval_topk(200, None, None, ulo, uhi, n_train_nz=n_tr, n_test_nz=n_te)
-        return None
-
-    def step():
-        rmse = als.epoch(lam)
-        return rmse, evaluate()
-
-    if hooks and "begin" in hooks:
-        hooks["begin"]()               # clock sampling starts with the warm-up, not with the setup
-    for _ in range(args.warmup):
-        h.flush_l2()
-        step()
-    h.reset_kernel_ms()
-    launches0 = h.launch_count
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
-    torch.cuda.synchronize()
-    epoch_wall = 0.0
-    total_wall = 0.0
-    for _ in range(args.steps):
-        h.flush_l2()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rmse = als.epoch(lam)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        out = evaluate()
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        epoch_wall += t1 - t0
-        total_wall += t2 - t0
-    dist.barrier()
-    torch.cuda.synchronize()
-    if hooks and "end" in hooks:
-        hooks["end"]()
-    times = torch.tensor([epoch_wall, total_wall], dtype=torch.float64, device="cuda")
-    dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    epoch_ms = 1e3 * times[0].item() / args.steps
-    step_ms = 1e3 * times[1].item() / args.steps
-    solve_ms = h.kernel_ms(_native.T_SOLVE)[0] / args.steps
-    launches = torch.tensor([h.launch_count - launches0], dtype=torch.int64, device="cuda")
-    dist.all_reduce(launches)
-    line = dict(metric="als_epoch_ms", value=epoch_ms, unit="ms", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=step_ms, higher_is_better=False, scaling="strong", vs_baseline=None,
-                dtype="f64" if args.precision == "fp64" else "f32", data="synthetic", config=config,
-                gpu_launches=int(launches.item()), rmse=rmse,
-                eval_users_per_s=(m / ((step_ms - epoch_ms) * 1e-3)) if has_eval else None,
-                timing="wall clock around barrier + cuda synchronize on both sides, max over ranks "
-                       "(the epoch mixes library-stream kernels and NCCL broadcasts)",
-                rank0_solve_kernel_ms=solve_ms,
-                e2e=dict(value=epoch_ms, unit="ms", h2d_bytes_per_step=0,
-                         d2h_bytes_per_step=int((uhi - ulo) * 200 * 20 + n_tr + n_te),
-                         note="factors stay device-resident across sharded epochs; evaluation inputs/outputs "
-                              "cross PCIe every step"))
-    h.close()
-    if has_eval:
-        # Reported next to the sharded number, never instead of it: the same epoch as N independent
-        # replicas (one whole model per GPU, no data-path collective -- what k-fold cross-validation and
-        # GridSearch do with N GPUs at this problem size, where a 3 ms epoch has nothing left to shard).
-        line["replicas"] = _bench_replicas(args, wl, local, precision, world)
-    dist.barrier()
-    dist.destroy_process_group()
-    return line
+    from hyprec_b200._native import HyprecError
+    blob, err = b"", None
+    try:
+        blob = handle.comm_export(rank, world)
+    except HyprecError as exc:
+        err = str(exc)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (err, blob), group=group)
+    failed = [g[0] for g in gathered if g[0] is not None]
+    if not failed:
+        try:
+            handle.comm_attach([g[1] for g in gathered], user_bounds, item_bounds)
+        except HyprecError as exc:
+            err = str(exc)
+    flags = [None] * world
+    dist.all_gather_object(flags, err, group=group)
+    failed = [f for f in flags if f is not None]
+    if failed:
+        if rank == 0:
+            import sys
+            sys.stderr.write("hyprec_b200: peer-memory exchange unavailable (%s); falling back to torch.distributed\n" % failed[0])
+        try:
+            handle.comm_detach()
+        except HyprecError:
+            pass
+        dist.barrier(group=group)
+        return False
+    return True
 
 
-def _bench_replicas(args, wl, local, precision, world):
-    import time
-    import torch
+def detach_exchange(handle, group=None):
+    """Collective: nobody unmaps or frees an arena a peer may still store into."""
     import torch.distributed as dist
-    from hyprec_b200 import _native
-    m, n, lam = wl["m"], wl["n"], wl["lam"]
-    tr = wl["train_csr"]
-    h = _native.Handle(local, precision)
-    h.set_train_csr(m, n, tr.indptr, tr.indices, tr.data)
-    h.set_factors(wl["u0"], wl["v0"])
+    dist.barrier(group=group)
+    handle.comm_detach()
+    dist.barrier(group=group)
 
-    def step():
-        h.als_half_step(_native.SIDE_USER, lam)
-        h.als_half_step(_native.SIDE_ITEM, lam)
-        h.rmse()
 
-    for _ in range(max(1, args.warmup)):
-        step()
-    dist.barrier()
-    torch.cuda.synchronize()
-    wall = 0.0
-    for _ in range(args.steps):
-        h.flush_l2()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step()
-        torch.cuda.synchronize()
-        wall += time.perf_counter() - t0
-    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    per_replica = 1e3 * t.item() / args.steps
-    h.close()
-    return dict(value=per_replica / world, unit="ms", scaling="weak", per_replica_epoch_ms=per_replica, models=world,
-                note="aggregate ms per epoch when every GPU trains its own model (max over ranks / N); "
-                     "no collective in the data path")
+class NativeShardedALS(object):
+    """ShardedALS's interface over a handle with the exchange attached: every call is one C-ABI call."""
+
+    def __init__(self, handle, user_bounds, item_bounds, rank):
+        self.h, self.rank = handle, rank
+        self.user_bounds, self.item_bounds = list(user_bounds), list(item_bounds)
+
+    def half_step(self, side, lam):
+        self.h.als_half_step(side, lam)
+
+    def rmse(self):
+        return self.h.rmse()
+
+    def epoch(self, lam):
+        self.h.als_half_step(0, lam)
+        self.h.als_half_step(1, lam)
+        return self.h.rmse()
+
+    def train(self, n_iter, lam, start_error=numpy.inf, callback=None):
+        history = []
+
+        def record(epoch, rmse, seconds):
+            history.append(rmse)
+            if callback is not None:
+                callback(epoch, rmse, seconds)
+
+        self.h.train(n_iter, lam, start_error, record)
+        return history
+
+
+def make_sharded(handle, device_index, rank, world, user_bounds, item_bounds, n_users, n_items, group=None,
+                 allow_peer_memory=True):
+    """The sharded trainer for a handle whose data and factors are loaded: peer-memory exchange when it can be
+    set up on every rank, else the torch.distributed exchange."""
+    import os
+    if allow_peer_memory and os.environ.get("HYPREC_EXCHANGE", "peer") != "nccl":
+        if attach_exchange(handle, rank, world, user_bounds, item_bounds, group):
+            return NativeShardedALS(handle, user_bounds, item_bounds, rank)
+    return ShardedALS(NativeEngine(handle, device_index), user_bounds, item_bounds, rank, n_users, n_items, group)

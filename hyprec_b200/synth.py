@@ -67,3 +67,47 @@ def dirichlet_theta(n_items, n_factors, seed=7, alpha=0.1):
     factors with (lib/LDA.py:56-70 -> collaborative_filtering.py:174-178): rows ~ Dirichlet(alpha)."""
     rs = numpy.random.RandomState(seed)
     return rs.dirichlet(numpy.full(n_factors, alpha), size=n_items)
+
+
+def scaled_ratings(scale, device=None, seed=20170303, train_share=0.8):
+    """BASELINE.json configs[3] times ``scale``: users x items = 1e6 x 2e6, 2e8 positives (log-normal user
+    activity, mean 200), Zipf(0.8) item popularity under a fixed permutation, built directly as CSR; a random
+    ``train_share`` of the positives is the train matrix (5-fold-equivalent split), the rest the test matrix.
+    No dense matrix and no per-user candidate list exists at this size.
+
+    The random draws are numpy's (seeded, identical on every machine); the two heavy steps -- inverse-CDF lookup
+    of 2e8 samples and the sort / de-duplication of the (user, item) keys -- run through torch on ``device``
+    (exact comparisons and integer sorts: the same arrays on CPU and GPU).  Returns a dict of plain arrays:
+    m, n, and (indptr int64, indices int32) for ``full``, ``train``, ``test``."""
+    import torch
+    m, n, nnz = int(1e6 * scale), int(2e6 * scale), int(2e8 * scale)
+    dev = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+    rs = numpy.random.RandomState(seed)
+    raw = rs.lognormal(mean=numpy.log(200.0) - 0.32, sigma=0.8, size=m)
+    deg = numpy.clip(numpy.round(raw * (nnz / raw.sum())), 1, n // 4).astype(numpy.int64)
+    p = (numpy.arange(n) + 20.0) ** -0.8
+    cdf = numpy.cumsum(p[rs.permutation(n)])
+    cdf /= cdf[-1]
+    total = int(deg.sum())
+    draws = rs.random_sample(total)
+    with torch.no_grad():
+        rows = torch.repeat_interleave(torch.arange(m, dtype=torch.int64, device=dev), torch.from_numpy(deg).to(dev))
+        items = torch.searchsorted(torch.from_numpy(cdf).to(dev), torch.from_numpy(draws).to(dev))
+        del draws
+        items.clamp_(max=n - 1)
+        keys = torch.unique(rows * n + items)           # sorted; drops the duplicates of sampling with replacement
+        del rows, items
+        n_keys = int(keys.shape[0])
+        keep = torch.from_numpy(rs.random_sample(n_keys) < train_share).to(dev)
+        out = dict(m=m, n=n)
+        for name, mask in (("full", None), ("train", keep), ("test", ~keep)):
+            sel = keys if mask is None else keys[mask]
+            r = torch.div(sel, n, rounding_mode="floor")
+            indptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+            indptr[1:] = torch.cumsum(torch.bincount(r, minlength=m), 0)
+            out[name] = (indptr.cpu().numpy(), (sel - r * n).to(torch.int32).cpu().numpy())
+            del sel, r, indptr
+        del keys, keep
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    return out

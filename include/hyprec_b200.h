@@ -134,6 +134,14 @@ int hyprec_comm_export(hyprec_t* h, int rank, int world, void* blob, size_t blob
 int hyprec_comm_attach(hyprec_t* h, const void* blobs, size_t blob_bytes, const int64_t* user_bounds,
                        const int64_t* item_bounds);
 int hyprec_comm_detach(hyprec_t* h);
+/* The same exchange between handles of ONE process (one host process driving several GPUs, or several handles on
+ * one GPU): after hyprec_comm_export on every handle, hyprec_comm_arena returns a handle's arena and
+ * hyprec_comm_attach_local takes all arenas (rank order) with the device ordinal each lives on -- plain device
+ * pointers, peer access enabled where the devices differ, no IPC.  The handles must then be driven from one host
+ * thread each (a half-step waits on the device for its peers' half-steps). */
+int hyprec_comm_arena(hyprec_t* h, void** base, size_t* bytes);
+int hyprec_comm_attach_local(hyprec_t* h, void* const* arenas, const int* devices, const int64_t* user_bounds,
+                             const int64_t* item_bounds);
 /* out8 = { attached (0/1), bytes this rank stored into peer replicas since attach, barriers passed, arena bytes, 0... } */
 int hyprec_comm_stats(hyprec_t* h, double* out8);
 

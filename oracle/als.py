@@ -44,7 +44,30 @@ def als_step_literal(latent, fixed, train_dense, lam, side="user", prior=None):
     return latent
 
 
-def als_half_step(latent, fixed, csr, lam, prior=None, batch=256, rows=None):
+def mix64(x):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic) -- hyprec_b200/csrc/comm.cuh mix64."""
+    x = numpy.asarray(x, dtype=numpy.uint64)
+    with numpy.errstate(over="ignore"):
+        x = x + numpy.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> numpy.uint64(30))) * numpy.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> numpy.uint64(27))) * numpy.uint64(0x94D049BB133111EB)
+    return x ^ (x >> numpy.uint64(31))
+
+
+def uniform_factors(n_rows, k, seed, rows=None):
+    """The initial factors hyprec_init_factors_uniform draws on the device (include/hyprec_b200.h), standing for
+    numpy.random.random((rows, k)) of collaborative_filtering.py:173-176 at sizes whose factors never visit the
+    host: element e = row * k + c is float32(mix64(seed * 0xD1342543DE82EF95 + e) >> 40) / 2^24.
+    ``rows``: only these rows (float64 array len(rows) x k)."""
+    row_ids = numpy.arange(n_rows, dtype=numpy.uint64) if rows is None else numpy.asarray(rows, dtype=numpy.uint64)
+    with numpy.errstate(over="ignore"):
+        e = row_ids[:, None] * numpy.uint64(k) + numpy.arange(k, dtype=numpy.uint64)[None, :]
+        base = numpy.uint64(seed % (1 << 64)) * numpy.uint64(0xD1342543DE82EF95)
+        r = mix64(base + e)
+    return ((r >> numpy.uint64(40)).astype(numpy.float32) * numpy.float32(1.0 / 16777216.0)).astype(numpy.float64)
+
+
+def als_half_step(latent, fixed, csr, lam, prior=None, batch=256, rows=None, gram=None):
     """Sparse restatement of one half-step; ``csr`` has one row per row of ``latent``.
 
     :param ndarray latent: rows x k float64, overwritten in place and returned (:85, :99).
@@ -54,7 +77,8 @@ def als_half_step(latent, fixed, csr, lam, prior=None, batch=256, rows=None):
     :param rows: optional iterable of row ids to solve (others untouched) -- CPU-baseline sampling.
     """
     k = latent.shape[1]
-    gram = fixed.T.dot(fixed)
+    if gram is None:                 # (``gram``: a precomputed fixed.T.dot(fixed), for row-subsample checks)
+        gram = fixed.T.dot(fixed)
     base = CONF_NEG * gram + lam * numpy.eye(k)
     scale = CONF_POS - CONF_NEG
     indptr, indices, data = csr.indptr, csr.indices, csr.data

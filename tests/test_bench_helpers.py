@@ -15,7 +15,7 @@ def small():
 
 def test_algorithmic_work_is_consistent(small):
     w8, w4 = bench.algorithmic_work(small, 8), bench.algorithmic_work(small, 4)
-    assert w8["nnz"] == small["train_csr"].nnz
+    assert w8["nnz"] == small["train_csr"].nnz == int(small["train_arrays"][0][-1])
     assert w8["lowrank_flops_per_epoch"] > 0 and w4["lowrank_flops_per_epoch"] > 0
     assert w8["lowrank_flops_per_epoch"] <= w8["solve_flops_per_epoch"] * 1.0001     # the low-rank form never costs more
     assert w8["solve_bytes_per_epoch"](8) == 2 * w8["solve_bytes_per_epoch"](4) - 2.0 * w8["nnz"] * 4 - 8.0 * (small["m"] + small["n"] + 2)
@@ -98,6 +98,9 @@ def test_bench_line_python_flow_with_a_stand_in_handle(monkeypatch, capsys):
         def rmse(self):
             return 0.25
 
+        def elapsed_ms(self, start, stop):
+            return 1.5
+
         def probe_fma_tflops(self, precision):
             return 36.0
 
@@ -109,6 +112,7 @@ def test_bench_line_python_flow_with_a_stand_in_handle(monkeypatch, capsys):
 
     class Args(object):
         gpus, steps, warmup, impl, workload, scale, precision, cpu_rows, eval_users = 1, 2, 1, "ours", "small", 0.1, None, 2, 0
+        no_citeulike = False
 
     args = Args()
     bench.our_arm(args, bench.make_workload(args))
@@ -122,3 +126,25 @@ def test_bench_line_python_flow_with_a_stand_in_handle(monkeypatch, capsys):
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert sorted(line["recall_at"], key=int) == ["50", "100", "150", "200", "250", "300"]
     assert line["gpu_launches"] == 2 * 2 * 10
+    assert line["value"] == 1.5 and line["n_gpus"] == 1 and line["scaling"] == "strong"
+
+
+def test_scaled_generator_matches_between_devices_and_partitions():
+    """The scaled workload's arrays (torch sort / searchsorted on whatever device) are CSR-consistent, and the
+    sub-matrix helpers of the CPU baseline agree with scipy."""
+    import numpy
+    import scipy.sparse as sp
+    wl = bench.build_scaled_workload(0.002, device="cpu")
+    m, n = wl["m"], wl["n"]
+    assert (m, n, wl["k"]) == (2000, 4000, 256) and wl["device_init"] == bench.FACTOR_SEED
+    full, train, test = wl["full_arrays"], wl["train_arrays"], wl["test_arrays"]
+    assert full[0][-1] == train[0][-1] + test[0][-1]
+    assert 0.75 < train[0][-1] / float(full[0][-1]) < 0.85
+    csr = sp.csr_matrix((numpy.ones(len(train[1])), train[1], train[0]), shape=(m, n))
+    assert csr.has_sorted_indices or (numpy.diff(csr.indices) > 0)[numpy.diff(csr.indices) <= 0].size == 0
+    rows = numpy.array([0, 5, 77, 1999])
+    cols = numpy.array([1, 17, 3999])
+    assert (bench.sub_csr(train[0], train[1], rows, n) != csr[rows]).nnz == 0
+    assert (bench.sub_csc(train[0], train[1], cols, m) != csr.T.tocsr()[cols]).nnz == 0
+    work = bench.algorithmic_work(wl, 4)
+    assert work["nnz"] == train[0][-1] and work["lowrank_flops_per_epoch"] <= work["solve_flops_per_epoch"] * 1.0001

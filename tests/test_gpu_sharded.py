@@ -92,12 +92,15 @@ def run_ranks(native, train, u0, v0, precision, world, k, n_iter, bounds=None, p
     for r, h in enumerate(handles):
         if prior is not None:
             h.set_item_prior(prior)
-        # One plain epoch first: it sizes every scratch buffer.  The ranks of this test share ONE device, where a
-        # buffer that grows later (cudaFree synchronises the whole device) would wait for the other rank's barrier
-        # kernel, which waits for this rank.  Ranks on their own GPUs (the real case) never meet this.
+        # One epoch as a single-rank exchange first: it sizes every scratch buffer.  The ranks of this test share ONE
+        # device, where a device allocation in the middle of a step (an implicit synchronisation point of the CUDA
+        # runtime) would put this rank's next kernels behind the other rank's barrier kernel, which waits for them.
+        # Ranks on their own GPUs (the real case) never meet this.
+        h.comm_attach([h.comm_export(0, 1)], [0, train.shape[0]], [0, train.shape[1]])
         h.als_half_step(0, 0.01)
         h.als_half_step(1, 0.01)
         h.rmse()
+        h.comm_detach()
         h.set_factors(u0, v0)
         h.comm_export(r, world)
     arenas = [h.comm_arena()[0] for h in handles]

@@ -1165,7 +1165,7 @@ struct Engine : EngineBase {
     };
     Comm cm;
     DevBuf gram64[2], slot_local, comm_status;
-    static constexpr unsigned long long kCommTimeoutNs = 30ull * 1000000000ull;
+    static constexpr unsigned long long kCommTimeoutNs = 20ull * 1000000000ull;
 
     T* q_of(int side) {   // whitened replica of U (0) / V (1)
         if (cm.exported) return reinterpret_cast<T*>(static_cast<unsigned char*>(cm.arena) + cm.off_q[side]);
@@ -1691,7 +1691,7 @@ struct Engine : EngineBase {
         if (cm.on) CU_TRY(cudaMemcpyAsync(cstat, comm_status.ptr, sizeof(cstat), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
         if (cstat[0] != 0)
-            return fail(HYPREC_E_CUDA, std::string(where) + ": a peer GPU did not reach the exchange barrier within 30 s");
+            return fail(HYPREC_E_CUDA, std::string(where) + ": a peer GPU did not reach the exchange barrier within 20 s");
         if (status[kStatusSlot] != 0) {
             CU_TRY(cudaMemsetAsync(counter.as<int>() + kStatusSlot, 0, sizeof(int), h->stream));
             return fail(HYPREC_E_SINGULAR, std::string(where) + ": non-finite solution (singular normal matrix; lambda == 0?)");

@@ -61,7 +61,8 @@ __global__ void comm_wait_kernel(PeerList peers, size_t off_flags, unsigned long
         reinterpret_cast<const unsigned long long*>(static_cast<const unsigned char*>(peers.base[peers.rank]) + off_flags);
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys_u64(flags + src) < seq) {
-        if (global_timer_ns() - t0 > timeout_ns) {
+        // (a barrier that already timed out makes the later ones fall through: the run is lost, end it quickly)
+        if (*reinterpret_cast<volatile int*>(status) != 0 || global_timer_ns() - t0 > timeout_ns) {
             *status = 2;       // a peer never arrived
             break;
         }

@@ -126,7 +126,7 @@ int hyprec_train(hyprec_t* h, int n_iter, double lambda, double start_error, hyp
  * epilogue of the kernel that produced them, reduces the k x k Gram through the mailbox, whitens its own rows into
  * every replica and returns without synchronising the host; hyprec_rmse / hyprec_rmse_terms return the GLOBAL value
  * (bit-identical on every rank) and hyprec_train runs the sharded epoch loop.  Every rank must issue the same
- * sequence of half-step / rmse / train calls.  A peer that does not arrive within 30 s fails the next
+ * sequence of half-step / rmse / train calls.  A peer that does not arrive within 20 s fails the next
  * hyprec_rmse / hyprec_train with HYPREC_E_CUDA instead of hanging the GPU.
  * hyprec_comm_detach (collective: put a process barrier before anything reuses the memory) undoes it. */
 int hyprec_comm_blob_bytes(void);

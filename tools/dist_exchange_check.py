@@ -1,9 +1,13 @@
-"""Under torchrun (one rank per GPU): the sharded epoch loop with the exchange inside the library (CUDA IPC arenas,
-NVLink peer stores from the kernels' epilogues, mailbox reductions, device barriers) against the float64 oracle and
-against the torch.distributed fallback, in float64 and float32; then the reference-facing class on the golden runs.
+"""Under torchrun (one process per rank): the sharded epoch loop with the exchange inside the library (CUDA IPC
+arenas, peer stores from the kernels' epilogues, mailbox reductions, device barriers) against the float64 oracle,
+in float64 and float32; then the reference-facing class on the golden runs of the unmodified reference.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_exchange_check.py
+    ... tools/dist_exchange_check.py --same-device      # every rank on GPU 0 (a one-GPU box): the ranks are
+        separate processes whose contexts the GPU time-slices, the arenas still travel as CUDA IPC handles; the
+        process group is gloo (NCCL refuses two ranks on one device) and the torch.distributed fallback is not run
 """
+import argparse
 import os
 import sys
 
@@ -17,9 +21,18 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from hyprec_b200 import _native, distributed, synth  # noqa: E402
 from oracle import als as oals  # noqa: E402
 
-local = int(os.environ.get("LOCAL_RANK", "0"))
-torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ap = argparse.ArgumentParser()
+ap.add_argument("--same-device", action="store_true")
+ap.add_argument("--quick", action="store_true", help="the small cases only")
+args = ap.parse_args()
+
+local = 0 if args.same_device else int(os.environ.get("LOCAL_RANK", "0"))
+if args.same_device:
+    os.environ["HYPREC_DEVICE"] = "0"
+    dist.init_process_group("gloo")
+else:
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
 
@@ -28,19 +41,50 @@ def say(msg):
     print("rank %d %s" % (rank, msg), flush=True)
 
 
-for precision, k, tol in ((_native.F64, 48, 1e-8), (_native.F64, 200, 1e-8), (_native.F32, 64, 2e-4), (_native.F32, 256, 2e-4)):
-    full = synth.ratings_csr("toy", n_users=700, n_items=1900, positives=60000, min_degree=2, seed=13)
+def toy(m, n, nnz, seed, heavy_item=None):
+    full = synth.ratings_csr("toy", n_users=m, n_items=n, positives=nnz, min_degree=1, seed=seed)
     train = oals.to_csr(full)
-    m, n = train.shape
+    if heavy_item is not None:          # an item most users rated: one long row on the item side
+        dense = numpy.asarray(train.todense())
+        dense[::2, heavy_item] = 1.0
+        dense[1::3, heavy_item] = 1.0
+        train = oals.to_csr(dense)
+    return train
+
+
+# (precision, k, tolerance vs the float64 oracle, shape, prior?, skewed shard?)
+CASES = [
+    (_native.F64, 24, 1e-8, (150, 500, 7000), False, False),
+    (_native.F64, 40, 1e-8, (90, 260, 3000), True, False),
+    (_native.F32, 32, 2e-4, (100, 300, 4000), False, True),
+    (_native.F32, 64, 2e-4, (150, 500, 7000), False, False),
+]
+if not args.quick:
+    CASES += [
+        (_native.F64, 200, 1e-8, (700, 1900, 60000), False, False),
+        (_native.F32, 256, 2e-4, (700, 1900, 60000), False, False),
+    ]
+
+for precision, k, tol, (m, n, nnz), with_prior, skewed in CASES:
+    train = toy(m, n, nnz, seed=13 + k, heavy_item=3)
     rs = numpy.random.RandomState(3)
     u0, v0 = rs.rand(m, k), rs.rand(n, k)
-    ub = distributed.partition_rows(train.indptr, world, k)
-    ib = distributed.partition_rows(distributed.csc_indptr(train.indptr, train.indices, n), world, k)
+    theta = synth.dirichlet_theta(n, k, seed=3) if with_prior else None
+    if with_prior:
+        v0 = theta.copy()
+    if skewed:            # an item shard that is empty on the last rank, an uneven user shard
+        ub = [0] + [min(m, 10 * (r + 1)) for r in range(world - 1)] + [m]
+        ib = [0] + [n] * world
+    else:
+        ub = distributed.partition_rows(train.indptr, world, k)
+        ib = distributed.partition_rows(distributed.csc_indptr(train.indptr, train.indices, n), world, k)
     results = {}
-    for mode in ("peer", "nccl"):
+    for mode in (("peer",) if args.same_device else ("peer", "nccl")):
         h = _native.Handle(local, precision)
         h.set_train_csr(m, n, train.indptr, train.indices, train.data)
         h.set_factors(u0, v0)
+        if with_prior:
+            h.set_item_prior(theta)
         als = distributed.make_sharded(h, local, rank, world, ub, ib, m, n, allow_peer_memory=(mode == "peer"))
         native_path = isinstance(als, distributed.NativeShardedALS)
         if mode == "peer" and rank == 0:
@@ -51,20 +95,22 @@ for precision, k, tol in ((_native.F64, 48, 1e-8), (_native.F64, 200, 1e-8), (_n
         u, v = h.get_factors()
         results[mode] = (history, u, v)
         if native_path:
-            say("precision %d k %d: %s" % (precision, k, h.comm_stats()))
+            stats = h.comm_stats()
+            ok = ok and stats["bytes_pushed"] > 0 and stats["barriers"] > 0
             distributed.detach_exchange(h)
         else:
             h.set_shard(0, -1, 0, -1)
         h.close()
     ou, ov = u0.copy(), v0.copy()
-    _, ohist = oals.partial_train(ou, ov, train, 0.01, 3)
+    _, ohist = oals.partial_train(ou, ov, train, 0.01, 3, prior=theta)
     for mode, (history, u, v) in results.items():
         eu = numpy.linalg.norm(u - ou) / numpy.linalg.norm(ou)
         ev = numpy.linalg.norm(v - ov) / numpy.linalg.norm(ov)
         good = eu <= tol and ev <= tol and len(history) == len(ohist) and numpy.allclose(history, ohist, rtol=max(tol, 1e-9))
-        say("precision %d k %d %s: rel err U %.2e V %.2e rmse %s -> %s" % (precision, k, mode, eu, ev, history[-1], "OK" if good else "MISMATCH"))
+        say("precision %d k %d prior %d skewed %d %s: rel err U %.2e V %.2e rmse %.12g -> %s" %
+            (precision, k, with_prior, skewed, mode, eu, ev, history[-1], "OK" if good else "MISMATCH"))
         ok = ok and good
-    # every rank holds the same replicas and took the same decisions
+    # every rank holds the same replicas and took the same decisions (bit for bit)
     gathered = [None] * world
     dist.all_gather_object(gathered, (results["peer"][0], float(results["peer"][1].sum()), float(results["peer"][2].sum())))
     if any(g != gathered[0] for g in gathered):

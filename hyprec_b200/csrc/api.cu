@@ -1889,9 +1889,10 @@ struct Engine : EngineBase {
     // tensor-core adds, doubled (observed maximum on B200: 1.2e-6 at k = 200)
     float tc_margin_coef() const { return (float)((3.0 * ((k + 7) / 8) + 32.0) * 2.0 * 1.1920929e-7); }
 
-    // S~ = U V^T on tcgen05 for users [0, m): per-row counts of score >= threshold (exact, through
-    // the margin + re-check scheme) and/or the dense float32 score matrix.
-    int tc_sweep(int64_t lo, int64_t hi, bool want_counts, bool want_dense, int64_t* dense_ld_out) {
+    // Operands of the tensor-core sweeps over users [lo, hi): hi / lo TF32 splits of U[lo:hi] and V, row norms,
+    // TMA descriptors.
+    CUtensorMap tc_mu_hi, tc_mu_lo, tc_mv_hi, tc_mv_lo;
+    int tc_prepare(int64_t lo, int64_t hi) {
         namespace tcn = hyprec::tc;
         const int64_t nu = hi - lo;
         HY_TRY(u_hi.reserve(sizeof(float) * (size_t)m * k));
@@ -1902,10 +1903,6 @@ struct Engine : EngineBase {
         HY_TRY(vnorm.reserve(sizeof(float) * (size_t)n));
         HY_TRY(border_cells.reserve(sizeof(uint2) * (size_t)kBorderCapacity));
         HY_TRY(border_count.reserve(sizeof(unsigned int)));
-        const int64_t tiles_n = (n + tcn::kBN - 1) / tcn::kBN;
-        const int64_t dense_ld = tiles_n * tcn::kBN;
-        if (want_dense) HY_TRY(dense_f32.reserve(sizeof(float) * (size_t)nu * dense_ld));
-        if (dense_ld_out) *dense_ld_out = dense_ld;
         const int64_t cu = nu * k, cv = n * k;
         tcn::split_tf32_kernel<T><<<(unsigned)((cu + 255) / 256), 256, 0, h->stream>>>(U.as<T>() + lo * k, cu, u_hi.as<float>(), u_lo.as<float>());
         tcn::split_tf32_kernel<T><<<(unsigned)((cv + 255) / 256), 256, 0, h->stream>>>(V.as<T>(), cv, v_hi.as<float>(), v_lo.as<float>());
@@ -1913,11 +1910,28 @@ struct Engine : EngineBase {
         tcn::row_norm_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(V.as<T>(), n, k, vnorm.as<float>());
         h->launches += 4;
         CU_TRY(cudaGetLastError());
-        CUtensorMap mu_hi, mu_lo, mv_hi, mv_lo;
-        HY_TRY(make_map(&mu_hi, u_hi.as<float>(), nu));
-        HY_TRY(make_map(&mu_lo, u_lo.as<float>(), nu));
-        HY_TRY(make_map(&mv_hi, v_hi.as<float>(), n));
-        HY_TRY(make_map(&mv_lo, v_lo.as<float>(), n));
+        HY_TRY(make_map(&tc_mu_hi, u_hi.as<float>(), nu));
+        HY_TRY(make_map(&tc_mu_lo, u_lo.as<float>(), nu));
+        HY_TRY(make_map(&tc_mv_hi, v_hi.as<float>(), n));
+        HY_TRY(make_map(&tc_mv_lo, v_lo.as<float>(), n));
+        return HYPREC_OK;
+    }
+
+    // The sweep itself over the prepared operands: per-row counts of score >= threshold (exact, through the margin +
+    // re-check scheme), the dense float32 score matrix (diagnostic API only), and / or the survivors of the fused
+    // top-k (cells of candidate items whose score reaches the user's cut).
+    struct EmitArgs {
+        const float* cut = nullptr;
+        const unsigned int* bits = nullptr;
+        int64_t bits_ld = 0;
+    };
+    int tc_run_sweep(int64_t lo, int64_t hi, bool want_counts, bool want_dense, int64_t* dense_ld_out, const EmitArgs* emit) {
+        namespace tcn = hyprec::tc;
+        const int64_t nu = hi - lo;
+        const int64_t tiles_n = (n + tcn::kBN - 1) / tcn::kBN;
+        const int64_t dense_ld = tiles_n * tcn::kBN;
+        if (want_dense) HY_TRY(dense_f32.reserve(sizeof(float) * (size_t)nu * dense_ld));
+        if (dense_ld_out) *dense_ld_out = dense_ld;
         CU_TRY(cudaMemsetAsync(border_count.ptr, 0, sizeof(unsigned int), h->stream));
         tcn::ScoreArgs a;
         a.m = nu;
@@ -1934,11 +1948,19 @@ struct Engine : EngineBase {
         a.dense = want_dense ? dense_f32.as<float>() : nullptr;
         a.dense_ld = dense_ld;
         a.row_map = nullptr;
+        if (emit) {
+            a.surv_cut = emit->cut;
+            a.cand_bits = emit->bits;
+            a.bits_ld = emit->bits_ld;
+            a.surv_cnt = surv_cnt.as<unsigned int>();
+            a.surv = surv.as<uint2>();
+            a.surv_cap = hyprec::kSurvCap;
+        }
         auto kern = tcn::tc_score_kernel;
         HY_TRY(ensure_dynamic_smem((const void*)kern, (int)tcn::kSmemBytes));
         const int64_t n_tiles = ((nu + tcn::kBM - 1) / tcn::kBM) * tiles_n;
         const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
-        kern<<<grid, tcn::kThreads, tcn::kSmemBytes, h->stream>>>(mu_hi, mu_lo, mv_hi, mv_lo, a);
+        kern<<<grid, tcn::kThreads, tcn::kSmemBytes, h->stream>>>(tc_mu_hi, tc_mu_lo, tc_mv_hi, tc_mv_lo, a);
         h->launches += 1;
         CU_TRY(cudaGetLastError());
         if (want_counts) {
@@ -1948,6 +1970,102 @@ struct Engine : EngineBase {
             h->launches += 1;
             CU_TRY(cudaGetLastError());
         }
+        return HYPREC_OK;
+    }
+
+    int tc_sweep(int64_t lo, int64_t hi, bool want_counts, bool want_dense, int64_t* dense_ld_out) {
+        HY_TRY(tc_prepare(lo, hi));
+        return tc_run_sweep(lo, hi, want_counts, want_dense, dense_ld_out, nullptr);
+    }
+
+    // ---- fused top-k: sampled columns -> per-user cut (topk.cuh) -------------------------------------------------
+    DevBuf surv, surv_cnt, cut_buf, cut_emit_buf, sample_f, sample_hi, sample_lo, sample_scores, cand_bits;
+    bool cand_bits_ok = false;      // the bitmap matches the candidate lists on the device
+    bool fused_topk_enabled = getenv("HYPREC_FUSED_TOPK") == nullptr || getenv("HYPREC_FUSED_TOPK")[0] != '0';   // =0: exact scoring of every candidate
+    bool last_topk_fused = false;
+
+    int build_cand_bitmap(int64_t nu) {
+        const int64_t words = (n + 31) / 32;
+        if (cand_bits_ok) return HYPREC_OK;
+        HY_TRY(cand_bits.reserve(sizeof(unsigned int) * (size_t)nu * words));
+        CU_TRY(cudaMemsetAsync(cand_bits.ptr, 0, sizeof(unsigned int) * (size_t)nu * words, h->stream));
+        const int grid = (int)std::min<int64_t>(nu, (int64_t)16 * h->num_sms);
+        hyprec::cand_bitmap_kernel<<<grid, 256, 0, h->stream>>>(cand_ptr.as<int64_t>(), cand_ids.as<int32_t>(), nu, words,
+                                                                 cand_bits.as<unsigned int>());
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        cand_bits_ok = true;
+        return HYPREC_OK;
+    }
+
+    // cut / cut - 2E per user of [lo, hi) from a tensor-core pass over ~32 n / target evenly spread item columns
+    int sample_cuts(int64_t lo, int64_t hi, bool have_list, int cap, int target) {
+        namespace tcn = hyprec::tc;
+        const int64_t nu = hi - lo;
+        int64_t n_sample = std::min<int64_t>(n, std::max<int64_t>(256, ((int64_t)32 * n + target - 1) / target));
+        const int64_t tiles_j = (n_sample + tcn::kBN - 1) / tcn::kBN;
+        const int64_t ld = tiles_j * tcn::kBN;
+        const int64_t cnt = n_sample * k;
+        HY_TRY(sample_f.reserve(sizeof(float) * (size_t)cnt));
+        HY_TRY(sample_hi.reserve(sizeof(float) * (size_t)cnt));
+        HY_TRY(sample_lo.reserve(sizeof(float) * (size_t)cnt));
+        HY_TRY(sample_scores.reserve(sizeof(float) * (size_t)nu * ld));
+        HY_TRY(cut_buf.reserve(sizeof(float) * (size_t)nu));
+        HY_TRY(cut_emit_buf.reserve(sizeof(float) * (size_t)nu));
+        HY_TRY(vmax_buf.reserve(2 * sizeof(float)));
+        hyprec::gather_rows_cast_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(V.as<T>(), n_sample, n, k, sample_f.as<float>());
+        tcn::split_tf32_kernel<float><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(sample_f.as<float>(), cnt, sample_hi.as<float>(), sample_lo.as<float>());
+        h->launches += 2;
+        CUtensorMap ms_hi, ms_lo;
+        HY_TRY(make_map(&ms_hi, sample_hi.as<float>(), n_sample));
+        HY_TRY(make_map(&ms_lo, sample_lo.as<float>(), n_sample));
+        tcn::ScoreArgs a;
+        a.m = nu;
+        a.n = n_sample;
+        a.k = k;
+        a.thresholds = nullptr;
+        a.unorm = nullptr;
+        a.vnorm = nullptr;
+        a.margin_coef = 0.f;
+        a.counts = nullptr;
+        a.border_count = nullptr;
+        a.border_cells = nullptr;
+        a.border_capacity = 0;
+        a.dense = sample_scores.as<float>();
+        a.dense_ld = ld;
+        a.row_map = nullptr;
+        auto kern = tcn::tc_score_kernel;
+        HY_TRY(ensure_dynamic_smem((const void*)kern, (int)tcn::kSmemBytes));
+        const int64_t n_tiles = ((nu + tcn::kBM - 1) / tcn::kBM) * tiles_j;
+        const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
+        kern<<<grid, tcn::kThreads, tcn::kSmemBytes, h->stream>>>(tc_mu_hi, tc_mu_lo, ms_hi, ms_lo, a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemsetAsync(vmax_buf.ptr, 0, 2 * sizeof(float), h->stream));
+        hyprec::max_float_kernel<<<1, 256, 0, h->stream>>>(vnorm.as<float>(), n, vmax_buf.as<float>());
+        hyprec::SampleCutArgs c;
+        c.scores = sample_scores.as<float>();
+        c.scores_ld = ld;
+        c.n_sample = n_sample;
+        c.n_items = n;
+        c.cand_bits = have_list ? cand_bits.as<unsigned int>() : nullptr;
+        c.bits_ld = (n + 31) / 32;
+        c.cand_indptr = have_list ? cand_ptr.as<int64_t>() : nullptr;
+        c.n_users = nu;
+        c.capacity = cap;
+        c.target = target;
+        c.unorm = unorm.as<float>();
+        c.vmax = vmax_buf.as<float>();
+        c.err_coef = tc_margin_coef();
+        c.cut = cut_buf.as<float>();
+        c.cut_emit = cut_emit_buf.as<float>();
+        const int cgrid = (int)std::min<int64_t>(nu, (int64_t)8 * h->num_sms);
+        hyprec::sample_cut_kernel<<<cgrid, hyprec::kTopkThreads, 0, h->stream>>>(c);
+        h->launches += 2;
+        CU_TRY(cudaGetLastError());
+        HY_TRY(surv.reserve(sizeof(uint2) * (size_t)nu * hyprec::kSurvCap));
+        HY_TRY(surv_cnt.reserve(sizeof(unsigned int) * (size_t)nu));
+        CU_TRY(cudaMemsetAsync(surv_cnt.ptr, 0, sizeof(unsigned int) * (size_t)nu, h->stream));
         return HYPREC_OK;
     }
 
@@ -2039,6 +2157,7 @@ struct Engine : EngineBase {
         cand_lo = lo;
         cand_hi = hi;
         cand_max = std::max<int64_t>(max_cand, 1);
+        cand_bits_ok = false;
         use_cached_cands = true;
         cands_are_hashed = true;
         return HYPREC_OK;
@@ -2070,6 +2189,7 @@ struct Engine : EngineBase {
         cand_lo = lo;
         cand_hi = hi;
         cand_max = std::max<int64_t>(max_cand, 1);
+        cand_bits_ok = false;
         cands_are_hashed = false;
         return HYPREC_OK;
     }
@@ -2109,19 +2229,52 @@ struct Engine : EngineBase {
         if (thr_out)
             CU_TRY(cudaMemcpyAsync(thr_out, thresholds.as<double>() + lo, sizeof(double) * nu, cudaMemcpyDeviceToHost, h->stream));
 
-        // One tensor-core sweep serves both the rounded counts (margin + float64 re-check) and the
-        // float32 score matrix the top-k kernel pre-filters with.
-        const int64_t tc_ld = ((n + hyprec::tc::kBN - 1) / hyprec::tc::kBN) * hyprec::tc::kBN;
-        const bool tc_dense = tc_usable() && want_topk && (size_t)nu * (size_t)tc_ld * sizeof(float) <= ((size_t)4 << 30);
+        // ---- candidate streams first: the sweep's epilogue needs to know whose candidate an item is
+        if (want_topk && !ci && !cp && hashed_folds > 0 &&
+            !(use_cached_cands && cands_are_hashed && cand_lo == lo && cand_hi == hi))
+            HY_TRY(generate_hashed_candidates(lo, hi));
+        int64_t max_cand = n;
+        bool have_list = false;
+        if (want_topk) {
+            const bool cached = !ci && cp == nullptr && cand_lo == lo && cand_hi == hi && cand_max > 0 && use_cached_cands;
+            if (ci) {
+                HY_TRY(upload_candidates(lo, hi, cp, ci));
+                max_cand = cand_max;
+            } else if (cached) {
+                max_cand = cand_max;
+            }
+            have_list = ci != nullptr || cached;
+            max_cand = std::max<int64_t>(max_cand, 1);
+        }
+
+        // ---- fused score -> mask -> top-k: the tensor-core sweep (needed for the rounded counts anyway) emits only
+        // the candidate cells that can reach a user's top; no users x items score matrix exists (topk.cuh).
+        const int target = std::max(2 * cap, cap + 64);
+        const int64_t bitmap_bytes = have_list ? (int64_t)sizeof(unsigned int) * nu * ((n + 31) / 32) : 0;
+        const bool fused = fused_topk_enabled && tc_usable() && want_topk && n >= 4096 && cap >= 64 &&
+                           target <= (hyprec::kSurvCap * 7) / 10 && max_cand > cap && bitmap_bytes <= ((int64_t)4 << 30);
         bool counts_done = false;
         if (ones_out) {
             HY_TRY(counts.reserve(sizeof(unsigned long long) * nu));
             CU_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(unsigned long long) * nu, h->stream));
         }
-        if (tc_usable() && (ones_out || tc_dense)) {
+        if (tc_usable() && (ones_out || fused)) {
+            EmitArgs emit;
             {
                 Timer t(h, HYPREC_T_COUNT);
-                HY_TRY(tc_sweep(lo, hi, ones_out != nullptr, tc_dense, nullptr));
+                HY_TRY(tc_prepare(lo, hi));
+            }
+            if (fused) {
+                Timer t(h, HYPREC_T_TOPK);
+                if (have_list) HY_TRY(build_cand_bitmap(nu));
+                HY_TRY(sample_cuts(lo, hi, have_list, cap, target));
+                emit.cut = cut_emit_buf.as<float>();
+                emit.bits = have_list ? cand_bits.as<unsigned int>() : nullptr;
+                emit.bits_ld = (n + 31) / 32;
+            }
+            {
+                Timer t(h, HYPREC_T_COUNT);
+                HY_TRY(tc_run_sweep(lo, hi, ones_out != nullptr, false, nullptr, fused ? &emit : nullptr));
             }
             if (ones_out) {
                 unsigned int border = 0;
@@ -2157,30 +2310,17 @@ struct Engine : EngineBase {
             CU_TRY(cudaMemcpyAsync(ones_out, counts.ptr, sizeof(int64_t) * nu, cudaMemcpyDeviceToHost, h->stream));
         }
 
-        if (want_topk && !ci && !cp && hashed_folds > 0 &&
-            !(use_cached_cands && cands_are_hashed && cand_lo == lo && cand_hi == hi))
-            HY_TRY(generate_hashed_candidates(lo, hi));
         if (want_topk) {
-            int64_t max_cand = n;
-            const bool cached = !ci && cp == nullptr && cand_lo == lo && cand_hi == hi && cand_max > 0 && use_cached_cands;
-            if (ci) {
-                HY_TRY(upload_candidates(lo, hi, cp, ci));
-                max_cand = cand_max;
-            } else if (cached) {
-                max_cand = cand_max;
-            }
-            const bool have_list = ci != nullptr || cached;
             int sort_size = 2;
             while (sort_size < cap) sort_size <<= 1;
-            max_cand = std::max<int64_t>(max_cand, 1);
-            hyprec::TopkLayout lay = hyprec::topk_layout((int)max_cand, k, sort_size, tc_dense);
+            hyprec::TopkLayout lay = hyprec::topk_layout((int)max_cand, k, sort_size, fused, fused);
             // Lists beyond one SM's shared memory (full catalogue / naive-split lists of a citeulike-sized item
             // set): the per-candidate arrays go to a per-CTA global scratch, everything else stays in shared memory.
             const bool spill = lay.total > (size_t)h->max_smem;
             size_t spill_stride = 0;
             if (spill) {
                 spill_stride = (lay.off_u + 255) & ~(size_t)255;         // keys, positions, float keys
-                lay = hyprec::topk_layout(0, k, sort_size, tc_dense);
+                lay = hyprec::topk_layout(0, k, sort_size, fused, fused);
                 if (lay.total > (size_t)h->max_smem)
                     return fail(HYPREC_E_UNSUPPORTED, "eval_topk: n_factors / capacity too large for one CTA's shared memory");
             }
@@ -2219,19 +2359,18 @@ struct Engine : EngineBase {
             a.topk_val = out_val.as<double>();
             a.topk_hit = out_hit.as<double>();
             a.approx = nullptr;
-            a.approx_ld = tc_ld;
+            a.approx_ld = 0;
             a.unorm = nullptr;
             a.err_coef = 0.f;
             a.vmax = nullptr;
             a.fallbacks = nullptr;
             a.spill = spill ? topk_spill.as<unsigned char>() : nullptr;
             a.spill_stride = spill_stride;
-            if (tc_dense) {
-                HY_TRY(vmax_buf.reserve(2 * sizeof(float)));
-                CU_TRY(cudaMemsetAsync(vmax_buf.ptr, 0, 2 * sizeof(float), h->stream));
-                hyprec::max_float_kernel<<<1, 256, 0, h->stream>>>(vnorm.as<float>(), n, vmax_buf.as<float>());
-                h->launches += 1;
-                a.approx = dense_f32.as<float>();
+            if (fused) {
+                a.surv = surv.as<uint2>();
+                a.surv_cnt = surv_cnt.as<unsigned int>();
+                a.surv_cap = hyprec::kSurvCap;
+                a.cut = cut_buf.as<float>();
                 a.unorm = unorm.as<float>();
                 a.err_coef = tc_margin_coef();
                 a.vmax = vmax_buf.as<float>();
@@ -2243,6 +2382,7 @@ struct Engine : EngineBase {
                 h->launches += 1;
             }
             CU_TRY(cudaGetLastError());
+            last_topk_fused = fused;
             if (tidx) CU_TRY(cudaMemcpyAsync(tidx, out_idx.ptr, sizeof(int32_t) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
             if (tval) CU_TRY(cudaMemcpyAsync(tval, out_val.ptr, sizeof(double) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
             if (thit) CU_TRY(cudaMemcpyAsync(thit, out_hit.ptr, sizeof(double) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));

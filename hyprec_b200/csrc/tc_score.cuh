@@ -59,6 +59,15 @@ struct ScoreArgs {
     // GPUs (NVLink peer memory) -- the all-gather of a freshly solved / whitened shard is this epilogue.
     int n_dense_peer = 0;
     float* dense_peer[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Survivors for the top-k (topk.cuh, "fused score -> mask -> top-k"): every cell of the sweep whose item is a
+    // candidate of its user (bit set in the user's bitmap; null: every item) and whose score reaches the user's cut
+    // is appended to the user's list -- the only trace the users x items scores leave in memory.
+    const float* surv_cut = nullptr;          // [m] cut - 2E per user, or null: nothing is emitted
+    const unsigned int* cand_bits = nullptr;  // [m][bits_ld]
+    int64_t bits_ld = 0;
+    unsigned int* surv_cnt = nullptr;         // [m], zeroed by the caller; counts past surv_cap mean overflow
+    uint2* surv = nullptr;                    // [m][surv_cap]: (item id, float32 score bits)
+    int surv_cap = 0;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -258,6 +267,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                 thr_err = fabsf(thr_f) * 1.1920929e-7f;
                 un = p.unorm[row] * p.margin_coef * 1.001f;
             }
+            float cut_f = 0.f;
+            const unsigned int* bits_row = nullptr;
+            const bool emit = row_ok && p.surv_cut != nullptr;
+            if (emit) {
+                cut_f = p.surv_cut[row];
+                if (p.cand_bits) bits_row = p.cand_bits + row * p.bits_ld;
+            }
             mbar_wait(&acc_full[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             unsigned int definite = 0;
@@ -280,6 +296,22 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                             } else {
                                 for (int j = 0; j < 32; ++j)
                                     if (col0 + c + j < p.dense_ld) dst[j] = __uint_as_float(v[j]);
+                            }
+                        }
+                    }
+                    if (emit) {
+                        // (col0 + c is a multiple of 32: one bitmap word per chunk; columns past n are masked off)
+                        unsigned int cand = bits_row ? bits_row[(col0 + c) >> 5] : 0xffffffffu;
+                        if (col0 + c + 32 > p.n) cand &= (col0 + c >= p.n) ? 0u : (0xffffffffu >> (32 - (int)(p.n - col0 - c)));
+                        if (cand) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float sv = __uint_as_float(v[j]);
+                                if (((cand >> j) & 1u) && sv >= cut_f) {
+                                    const unsigned int at = atomicAdd(p.surv_cnt + row, 1u);
+                                    if (at < (unsigned int)p.surv_cap)
+                                        p.surv[(size_t)row * p.surv_cap + at] = make_uint2((unsigned int)(col0 + c + j), v[j]);
+                                }
                             }
                         }
                     }

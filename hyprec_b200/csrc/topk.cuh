@@ -29,11 +29,14 @@ namespace hyprec {
 constexpr int kTopkThreads = 256;
 constexpr int kTopkMaxShortlist = 1024;   // pre-filter survivors re-scored exactly; more => exact fallback
 
+constexpr int kSurvCap = 1024;            // survivors per user the tensor-core sweep may emit (== kTopkMaxShortlist)
+constexpr int kSurvSlots = 2048;          // hash slots (item id -> float32 score) of one user's survivors
+
 struct TopkLayout {
-    size_t off_keys, off_pos, off_k32, off_u, off_selkey, off_selpos, off_fifo, off_hist, off_scan, total;
+    size_t off_keys, off_pos, off_k32, off_u, off_selkey, off_selpos, off_fifo, off_hist, off_scan, off_hash, total;
 };
 
-HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size, bool prefilter) {
+HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size, bool prefilter, bool survivors = false) {
     TopkLayout l;
     size_t o = 0;
     l.off_keys = o;
@@ -55,6 +58,9 @@ HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size, bool prefil
     o += 4 * 256;
     l.off_scan = o;
     o += 4 * (kTopkThreads + 1);
+    o = (o + 7) & ~(size_t)7;
+    l.off_hash = o;
+    o += survivors ? 8 * (size_t)kSurvSlots : 0;
     l.total = (o + 15) & ~(size_t)15;
     return l;
 }
@@ -91,6 +97,14 @@ struct TopkArgs {
     // tens of thousands); null => shared memory.
     unsigned char* spill;
     size_t spill_stride;
+    // Survivors emitted by the tensor-core sweep's epilogue (tc_score.cuh) instead of a dense score matrix: for every
+    // user the cells (item, s~) of its candidates with s~ >= cut[u] - 2E, in any order.  A candidate that is not
+    // among them cannot reach the exact top when at least `capacity` list elements have s~ >= cut[u]; otherwise
+    // (or when the sweep emitted more than surv_cap cells) the user falls back to exact scoring of every candidate.
+    const uint2* surv = nullptr;            // [n_local_users][surv_cap]: (item id, float32 bits)
+    const unsigned int* surv_cnt = nullptr; // [n_local_users] cells emitted (may exceed surv_cap)
+    int surv_cap = 0;
+    const float* cut = nullptr;             // [n_local_users]
 };
 
 // order-preserving map double -> uint64 (larger score <=> larger key)
@@ -180,11 +194,12 @@ template <typename T, bool kSpill = false>
 __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) {
     HYPREC_DYN_SMEM(smem_raw);
     __shared__ int s_digit, s_need, s_count, s_nsel;
-    const bool prefilter = p.approx != nullptr;
+    const bool sparse = p.surv != nullptr;
+    const bool prefilter = p.approx != nullptr || sparse;
     // kSpill is a compile-time switch so that the shared-memory instantiation keeps shared-memory
     // addressing (a run-time pointer select would turn every access into a generic load / store)
-    const TopkLayout lay = topk_layout(kSpill ? 0 : p.max_cand, p.k, p.sort_size, prefilter);
-    const TopkLayout big = topk_layout(p.max_cand, p.k, p.sort_size, prefilter);     // per-candidate arrays
+    const TopkLayout lay = topk_layout(kSpill ? 0 : p.max_cand, p.k, p.sort_size, prefilter, sparse);
+    const TopkLayout big = topk_layout(p.max_cand, p.k, p.sort_size, prefilter, sparse);     // per-candidate arrays
     unsigned char* big_raw = (unsigned char*)smem_raw;
     if (kSpill) big_raw = p.spill + (size_t)blockIdx.x * p.spill_stride;
     unsigned long long* keys = (unsigned long long*)(big_raw + big.off_keys);
@@ -196,6 +211,9 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
     int* fifo = (int*)(smem_raw + lay.off_fifo);
     unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
     int* scan = (int*)(smem_raw + lay.off_scan);
+    unsigned int* hkeys = (unsigned int*)(smem_raw + lay.off_hash);          // item id + 1 (0: empty)
+    unsigned int* hvals = hkeys + kSurvSlots;                                 // float32 bits
+    __shared__ int s_nge;
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int k = p.k, cap = p.capacity, P = p.sort_size;
 
@@ -213,13 +231,58 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
         // (shortlist ? posarr[j] : j).  Both orders are ascending in stream position.
         int np = ncand;
         bool shortlist = false;
-        if (prefilter && ncand > cap) {
+        bool usable = prefilter && ncand > cap;
+        if (usable && sparse) {
+            // the user's survivors into a hash table, then one pass over the candidate stream: a stream element
+            // gets the float32 score of its item if the sweep emitted it, else the lowest key
+            const unsigned int cnt = p.surv_cnt[ul];
+            usable = cnt <= (unsigned int)p.surv_cap;
+            if (usable) {
+                for (int i = tid; i < 2 * kSurvSlots; i += kTopkThreads) hkeys[i] = 0u;
+                if (tid == 0) s_nge = 0;
+                __syncthreads();
+                const uint2* mine = p.surv + (size_t)ul * p.surv_cap;
+                for (unsigned int i = tid; i < cnt; i += kTopkThreads) {
+                    const uint2 cell = mine[i];
+                    unsigned int slot = (cell.x * 2654435761u) >> 21;             // 11 bits: kSurvSlots == 2048
+                    while (atomicCAS(&hkeys[slot], 0u, cell.x + 1u) != 0u) slot = (slot + 1) & (kSurvSlots - 1);
+                    hvals[slot] = cell.y;
+                }
+                __syncthreads();
+                const float cut = p.cut[ul];
+                int n_ge = 0;
+                for (int c = tid; c < ncand; c += kTopkThreads) {
+                    const unsigned int item = p.cand_ids ? (unsigned int)p.cand_ids[cbase + c] : (unsigned int)c;
+                    unsigned int slot = (item * 2654435761u) >> 21;
+                    unsigned int key = 0u;
+                    while (true) {
+                        const unsigned int have = hkeys[slot];
+                        if (have == 0u) break;
+                        if (have == item + 1u) {
+                            const float val = __uint_as_float(hvals[slot]);
+                            key = float_key(val);
+                            n_ge += val >= cut ? 1 : 0;
+                            break;
+                        }
+                        slot = (slot + 1) & (kSurvSlots - 1);
+                    }
+                    keys32[c] = key;
+                }
+                if (n_ge) atomicAdd(&s_nge, n_ge);
+                __syncthreads();
+                usable = s_nge >= cap;
+            }
+            if (!usable && tid == 0 && p.fallbacks) atomicAdd(p.fallbacks, 1u);
+            __syncthreads();
+        } else if (usable) {
             const float* arow = p.approx + ul * p.approx_ld;
             for (int c = tid; c < ncand; c += kTopkThreads) {
                 const int64_t item = p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c;
                 keys32[c] = float_key(arow[item]);
             }
             __syncthreads();
+        }
+        if (usable) {
             int need32, equal32;
             const unsigned int kth = radix_select<unsigned int>(keys32, ncand, cap, hist, &s_digit, &s_need, &s_count,
                                                                 &need32, &equal32);
@@ -435,6 +498,151 @@ __global__ void __launch_bounds__(kTopkThreads) hashed_candidates_kernel(HashedC
         else if (tid == 0)
             p.counts[u - p.user_lo] = h_scan[kTopkThreads];
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused score -> mask -> top-k without a users x items score matrix (BASELINE north_star kernel (d)).
+//   1. cand_bitmap_kernel: one bit per (user, item) of the user's candidate stream (once per fold);
+//   2. a small tensor-core pass scores every user against J = ~32 n / target sampled item columns; per user,
+//      sample_cut_kernel takes the r-th largest sampled CANDIDATE score (r ~ 32) as `cut`: about `target`
+//      (~2 x capacity) of the user's candidates are expected above it;
+//   3. the full tensor-core sweep (needed anyway for the rounded counts) emits from its epilogue only the candidate
+//      cells with s~ >= cut - 2E (tc_score.cuh);
+//   4. eval_topk_kernel above looks the emitted cells up while streaming the candidate list, re-scores the
+//      shortlist in float64 and applies the reference's streaming tie rule.  Users whose sample misjudged the
+//      cut (fewer than `capacity` candidates above it, or more than kSurvCap cells) are scored exactly instead,
+//      so the result never depends on the sample.
+// Replaces the dense `predictions[user][index]` reads of /root/reference/lib/evaluator.py:226-230.
+// ---------------------------------------------------------------------------------------------------
+__global__ void cand_bitmap_kernel(const int64_t* __restrict__ cand_indptr, const int32_t* __restrict__ cand_ids, int64_t n_users,
+                                   int64_t words, unsigned int* __restrict__ bits) {
+    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x) {
+        unsigned int* row = bits + u * words;
+        const int64_t lo = cand_indptr[u], hi = cand_indptr[u + 1];
+        for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+            const unsigned int item = (unsigned int)cand_ids[e];
+            atomicOr(&row[item >> 5], 1u << (item & 31u));
+        }
+    }
+}
+
+// item id of sampled column j: evenly spread over [0, n)
+HYPREC_HD int64_t sample_item(int64_t j, int64_t n_sample, int64_t n_items) {
+    return (2 * j + 1) * n_items / (2 * n_sample);
+}
+
+struct SampleCutArgs {
+    const float* scores;           // [n_local_users][scores_ld]: s~ of the sampled columns
+    int64_t scores_ld;
+    int64_t n_sample, n_items;
+    const unsigned int* cand_bits; // [n_local_users][bits_ld] or null (every item is a candidate)
+    int64_t bits_ld;
+    const int64_t* cand_indptr;    // list lengths (relative to the first local user) or null (n_items each)
+    int64_t n_users;               // local users
+    int capacity, target;
+    const float* unorm;            // [n_local_users]
+    const float* vmax;
+    float err_coef;
+    float* cut;                    // [n_local_users]
+    float* cut_emit;               // [n_local_users] = cut - 2E, rounded down
+};
+
+__global__ void __launch_bounds__(kTopkThreads) sample_cut_kernel(SampleCutArgs p) {
+    __shared__ unsigned hist[256];
+    __shared__ int s_digit, s_need, s_count, s_total;
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    for (int64_t ul = blockIdx.x; ul < p.n_users; ul += gridDim.x) {
+        const float* row = p.scores + ul * p.scores_ld;
+        const unsigned int* bits = p.cand_bits ? p.cand_bits + ul * p.bits_ld : nullptr;
+        auto key_of = [&](int64_t j) -> unsigned int {
+            if (bits) {
+                const int64_t item = sample_item(j, p.n_sample, p.n_items);
+                if (((bits[item >> 5] >> (item & 31)) & 1u) == 0u) return 0u;
+            }
+            return float_key(row[j]);
+        };
+        __syncthreads();
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        int mine = 0;
+        for (int64_t j = tid; j < p.n_sample; j += kTopkThreads) mine += key_of(j) != 0u ? 1 : 0;
+        if (mine) atomicAdd(&s_total, mine);
+        __syncthreads();
+        const int n_sc = s_total;
+        const int64_t list_len = p.cand_indptr ? p.cand_indptr[ul + 1] - p.cand_indptr[ul] : p.n_items;
+        float cut = -3.0e38f;
+        if (n_sc > 0 && list_len > (int64_t)p.target) {
+            // about `target` list elements are wanted above the cut: rank target * n_sc / list_len in the sample
+            int64_t r = ((int64_t)p.target * n_sc + list_len - 1) / list_len;
+            if (r < 1) r = 1;
+            if (r <= n_sc) {
+                // most-significant-digit radix select of the r-th largest key, keys recomputed per pass
+                unsigned int prefix = 0, mask = 0;
+                int need = (int)r;
+                for (int shift = 24; shift >= 0; shift -= 8) {
+                    hist[tid] = 0;
+                    __syncthreads();
+                    for (int64_t j = tid; j < p.n_sample; j += kTopkThreads) {
+                        const unsigned int key = key_of(j);
+                        if (key != 0u && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        unsigned loc[8], tot = 0;
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            loc[b] = hist[8 * lane + b];
+                            tot += loc[b];
+                        }
+                        unsigned suf = tot;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const unsigned o = __shfl_down_sync(0xffffffffu, suf, d);
+                            if (lane + d < 32) suf += o;
+                        }
+                        unsigned above = __shfl_down_sync(0xffffffffu, suf, 1);
+                        if (lane == 31) above = 0;
+                        if (suf >= (unsigned)need && above < (unsigned)need) {
+                            unsigned cum = above;
+                            for (int b = 7; b >= 0; --b) {
+                                if (cum + loc[b] >= (unsigned)need) {
+                                    s_digit = 8 * lane + b;
+                                    s_need = need - (int)cum;
+                                    s_count = (int)loc[b];
+                                    break;
+                                }
+                                cum += loc[b];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    prefix |= (unsigned int)s_digit << shift;
+                    mask |= 0xffu << shift;
+                    need = s_need;
+                }
+                cut = key_float(prefix);
+            }
+        }
+        if (tid == 0) {
+            const double err = (double)p.err_coef * (double)p.unorm[ul] * (double)(*p.vmax);
+            double emit = (double)cut - 2.0 * err;
+            float ef = (float)emit;
+            if ((double)ef > emit) ef = nextafterf(ef, -3.4e38f);      // round down: never above cut - 2E
+            if (cut <= -3.0e38f) ef = -3.4e38f;
+            p.cut[ul] = cut;
+            p.cut_emit[ul] = ef;
+        }
+    }
+}
+
+// hi / lo TF32 split of the sampled rows of V, gathered into contiguous [n_sample][k] operands
+template <typename T>
+__global__ void gather_rows_cast_kernel(const T* __restrict__ v, int64_t n_sample, int64_t n_items, int k, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sample * k) return;
+    const int64_t j = i / k;
+    const int c = (int)(i % k);
+    out[i] = (float)v[sample_item(j, n_sample, n_items) * k + c];
 }
 
 // max of a float array (single block), for the uniform error bound of the pre-filter

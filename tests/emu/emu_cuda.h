@@ -142,6 +142,15 @@ inline double atomicAdd(double* p, double v) {
     } while (!__atomic_compare_exchange_n(ip, &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
     return cur;
 }
+inline unsigned atomicCAS(unsigned* p, unsigned compare, unsigned val) {
+    __atomic_compare_exchange_n(p, &compare, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return compare;
+}
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline float __uint_as_float(unsigned v) { float r; memcpy(&r, &v, 4); return r; }
+inline unsigned __float_as_uint(float v) { unsigned r; memcpy(&r, &v, 4); return r; }
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }

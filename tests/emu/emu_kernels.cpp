@@ -138,7 +138,8 @@ template <typename T>
 static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
                       const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
                       const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
-                      int grid, double prefilter_coef = 0.0, bool spill = false) {
+                      int grid, double prefilter_coef = 0.0, bool spill = false, bool survivors = false,
+                      unsigned int* fallbacks_out = nullptr) {
     std::vector<double> part(2 * (size_t)k), colsum(k);
     const int64_t per = (n + 1) / 2;
     emu::launch(dim3(2), dim3(64), 0, [&]() { colsum_partial_kernel<T>(V, n, k, per, part.data()); });
@@ -186,7 +187,44 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
             }
         }
     }
-    TopkLayout lay = topk_layout((int)max_cand, k, sort_size, prefilter_coef > 0.0);
+    // survivors mode: what api.cu does without the dense matrix -- candidate bitmap, sampled columns, per-user cut
+    // (sample_cut_kernel), and the cells the sweep's epilogue would emit (candidate cells with s~ >= cut - 2E),
+    // here taken from the perturbed `approx` scores in a scrambled order
+    std::vector<unsigned int> bits, surv_cnt;
+    std::vector<uint2> surv;
+    std::vector<float> cut, cut_emit, sample;
+    if (survivors) {
+        const int64_t words = (n + 31) / 32;
+        if (ci) {
+            bits.assign((size_t)nu * words, 0u);
+            emu::launch(dim3(3), dim3(64), 0, [&]() { cand_bitmap_kernel(cp, ci, nu, words, bits.data()); });
+        }
+        const int target = std::max(2 * cap, cap + 64);
+        int64_t n_sample = std::min<int64_t>(n, std::max<int64_t>(16, (32 * n + target - 1) / target));
+        sample.assign((size_t)nu * n_sample, 0.f);
+        for (int64_t u = 0; u < nu; ++u)
+            for (int64_t j = 0; j < n_sample; ++j) sample[(size_t)u * n_sample + j] = approx[(size_t)u * ld + sample_item(j, n_sample, n)];
+        cut.assign(nu, 0.f);
+        cut_emit.assign(nu, 0.f);
+        SampleCutArgs sc;
+        sc.scores = sample.data(); sc.scores_ld = n_sample; sc.n_sample = n_sample; sc.n_items = n;
+        sc.cand_bits = ci ? bits.data() : nullptr; sc.bits_ld = words; sc.cand_indptr = ci ? cp : nullptr; sc.n_users = nu;
+        sc.capacity = cap; sc.target = target; sc.unorm = unorm_v.data(); sc.vmax = vmax; sc.err_coef = (float)prefilter_coef;
+        sc.cut = cut.data(); sc.cut_emit = cut_emit.data();
+        emu::launch(dim3(2), dim3(kTopkThreads), 0, [&]() { sample_cut_kernel(sc); });
+        surv.assign((size_t)nu * kSurvCap, make_uint2(0u, 0u));
+        surv_cnt.assign(nu, 0u);
+        for (int64_t u = 0; u < nu; ++u)
+            for (int64_t jj = 0; jj < n; ++jj) {
+                const int64_t j = (jj * 7919 + 13 * u) % n;          // any order (7919 is prime: a permutation for n != 7919)
+                const bool cand = !ci || ((bits[(size_t)u * words + (j >> 5)] >> (j & 31)) & 1u);
+                if (cand && approx[(size_t)u * ld + j] >= cut_emit[u]) {
+                    const unsigned int at = surv_cnt[u]++;
+                    if (at < (unsigned int)kSurvCap) surv[(size_t)u * kSurvCap + at] = make_uint2((unsigned)j, __float_as_uint(approx[(size_t)u * ld + j]));
+                }
+            }
+    }
+    TopkLayout lay = topk_layout((int)max_cand, k, sort_size, prefilter_coef > 0.0, survivors);
     TopkArgs<T> a;
     a.user_vecs = U; a.item_vecs = V; a.k = k; a.n_items = n; a.user_lo = lo; a.user_hi = hi;
     a.cand_indptr = ci ? cp : nullptr; a.cand_ids = ci; a.thresholds = thr;
@@ -196,8 +234,13 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
     a.approx = prefilter_coef > 0.0 ? approx.data() : nullptr; a.approx_ld = ld; a.unorm = unorm_v.data();
     a.err_coef = (float)prefilter_coef; a.vmax = vmax; a.fallbacks = reinterpret_cast<unsigned int*>(vmax + 1);
     a.spill = nullptr; a.spill_stride = 0;
+    if (survivors) {
+        a.approx = nullptr;
+        a.surv = surv.data(); a.surv_cnt = surv_cnt.data(); a.surv_cap = kSurvCap; a.cut = cut.data();
+    }
     if (!spill) {
         emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T>(a); });
+        if (fallbacks_out) memcpy(fallbacks_out, vmax + 1, sizeof(unsigned int));
         return;
     }
     // per-candidate arrays in a per-CTA "global" scratch, as api.cu sets it up for lists beyond shared memory
@@ -205,8 +248,9 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
     std::vector<unsigned char> scratch(stride * (size_t)grid, 0xcd);
     a.spill = scratch.data();
     a.spill_stride = stride;
-    lay = topk_layout(0, k, sort_size, prefilter_coef > 0.0);
+    lay = topk_layout(0, k, sort_size, prefilter_coef > 0.0, survivors);
     emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T, true>(a); });
+    if (fallbacks_out) memcpy(fallbacks_out, vmax + 1, sizeof(unsigned int));
 }
 
 extern "C" {
@@ -253,6 +297,15 @@ void emu_eval_spill_f64(const double* U, const double* V, int64_t m, int64_t n, 
                         int grid, double prefilter_coef) {
     eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid, prefilter_coef,
                       true);
+}
+
+// the top-k fed by sweep survivors instead of a dense score matrix (spill != 0: per-candidate arrays in global scratch)
+void emu_eval_survivors_f64(const double* U, const double* V, int64_t m, int64_t n, int k, int64_t lo, int64_t hi,
+                            const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
+                            const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
+                            int grid, double prefilter_coef, int spill, unsigned int* fallbacks) {
+    eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid, prefilter_coef,
+                      spill != 0, true, fallbacks);
 }
 
 // device-generated candidate lists: fill == 0 writes counts[nu]; fill == 1 writes ids given the row pointers

@@ -223,6 +223,48 @@ def test_eval_prefilter_is_exact(emu, coef):
             assert numpy.allclose(tval[u_id][:len(want)], vals, rtol=1e-12, atol=1e-15)
 
 
+@pytest.mark.parametrize("coef,spill", [(1e-6, 0), (3e-3, 0), (0.5, 0), (1e-6, 1)])
+def test_eval_from_sweep_survivors_is_exact(emu, coef, spill):
+    """The top-k without a dense score matrix: candidate bitmap, per-user cut from sampled columns
+    (sample_cut_kernel), only the candidate cells with s~ >= cut - 2E handed over (in scrambled order), hash lookup
+    while streaming the candidate list, exact float64 re-score.  Tight bound, loose bound, useless bound (every user
+    falls back to exact scoring), full catalogue, explicit lists with repeats, a zero user (all scores tied), more
+    candidates than the capacity and fewer; and the spilled variant."""
+    rs = numpy.random.RandomState(int(coef * 1e6) % 1000 + 5)
+    m, n, k, cap = 6, 3000, 6, 20
+    u = numpy.round((rs.rand(m, k) - 0.3) * 4) / 4
+    v = numpy.round((rs.rand(n, k) - 0.3) * 4) / 4
+    u[2] = 0
+    full = (rs.rand(m, n) < 0.2).astype(numpy.float64)
+    csr = oals.to_csr(full)
+    fp, fi, fv = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
+    lists = [rs.randint(0, n, size=1200) for _ in range(m)]
+    lists[4] = rs.permutation(n)[:15]                      # fewer candidates than the capacity
+    for cands in (None, lists):
+        if cands is None:
+            cp = ci = None
+        else:
+            cp = numpy.zeros(m + 1, numpy.int64)
+            cp[1:] = numpy.cumsum([len(c) for c in cands])
+            ci = numpy.concatenate(cands).astype(numpy.int32)
+        thr = numpy.zeros(m)
+        tidx = numpy.zeros((m, cap), numpy.int32)
+        tval, thit = numpy.zeros((m, cap)), numpy.zeros((m, cap))
+        fallbacks = numpy.zeros(1, numpy.uint32)
+        emu.emu_eval_survivors_f64(_ptr(u), _ptr(v), I64(m), I64(n), k, I64(0), I64(m), _ptr(cp), _ptr(ci), cap,
+                                   _ptr(fp), _ptr(fi), _ptr(fv), _ptr(thr), None, _ptr(tidx), _ptr(tval), _ptr(thit),
+                                   3, DBL(coef), spill, _ptr(fallbacks))
+        for u_id in range(m):
+            ids = numpy.arange(n) if cands is None else cands[u_id]
+            want, vals = oev.top_recommendations_stream(ids, u[u_id].dot(v[ids].T), cap)
+            assert list(tidx[u_id][:len(want)]) == want, (coef, u_id)
+            assert numpy.allclose(tval[u_id][:len(want)], vals, rtol=1e-12, atol=1e-15)
+        if coef <= 1e-5:
+            assert fallbacks[0] <= 2, fallbacks        # the sample finds a usable cut for (almost) every user
+        if coef >= 0.5:
+            assert fallbacks[0] >= 3                   # a useless error bound: everything passes, users fall back
+
+
 def test_nz_flags_kernel(emu, als_cases):
     fold = golden_folds(als_cases["als_kfold_toy"])[0]
     u, v, test = fold["u"], fold["v"], fold["test"]

@@ -574,6 +574,12 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
     comm_total = reduce_sum([comm_bytes])[0]
     dev = {name: h.kernel_ms(t) for name, t in classes.items()}      # (total ms, regions, last)
     per_step = {name: dev[name][0] / args.steps for name in dev}
+    eval_stats = h.eval_stats() if ehi > elo else None
+    per_rank = None
+    if dist is not None:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, dict(rank=rank, users=[int(ulo), int(uhi)], epoch_ms=float(numpy.mean(epoch_ms)),
+                                              **{name: round(per_step[name], 3) for name in ("gram", "solve", "prep", "rmse", "comm")}))
     # device time of the evaluation's kernels (count sweep, top-k, flags) on the slowest rank
     eval_value = reduce_max([per_step["count"] + per_step["topk"] + per_step["flags"]])[0]
 
@@ -655,6 +661,11 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
                     rmse=rmse, recall_at_200=recall200, setup_s=wl["setup_s"], upload_s=upload_s)
         if recall_at is not None:
             line["recall_at"] = recall_at
+        if eval_stats is not None:
+            line["eval_topk"] = dict(eval_stats, note="fused: the sweep's epilogue emits only candidate cells above a per-user cut "
+                                                      "(no users x items score buffer); fallback_users were scored exactly instead")
+        if per_rank is not None:
+            line["per_rank_kernel_ms"] = per_rank
         if world > 1:
             line["exchange"] = exchange
             line["comm_bytes_per_epoch"] = comm_total

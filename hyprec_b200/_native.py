@@ -21,7 +21,7 @@ EXPORTS = [
     "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles", "hyprec_host_alloc", "hyprec_host_free",
     "hyprec_comm_blob_bytes", "hyprec_comm_export", "hyprec_comm_attach", "hyprec_comm_detach", "hyprec_comm_stats",
     "hyprec_init_factors_uniform", "hyprec_get_factor_rows", "hyprec_mark", "hyprec_elapsed_ms",
-    "hyprec_comm_arena", "hyprec_comm_attach_local",
+    "hyprec_comm_arena", "hyprec_comm_attach_local", "hyprec_eval_stats",
 ]
 
 EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
@@ -88,6 +88,7 @@ def load_library(rebuild=False):
     lib.hyprec_comm_stats.argtypes = [vp, vp]
     lib.hyprec_init_factors_uniform.argtypes = [vp, c_int, ctypes.c_uint64]
     lib.hyprec_get_factor_rows.argtypes = [vp, c_int, vp, c_i64, vp]
+    lib.hyprec_eval_stats.argtypes = [vp, vp]
     lib.hyprec_mark.argtypes = [vp, c_int]
     lib.hyprec_elapsed_ms.argtypes = [vp, c_int, c_int, ctypes.POINTER(c_dbl)]
     _lib = lib
@@ -309,6 +310,12 @@ class Handle(object):
             _ptr(out["ones_per_row"]), _ptr(out["topk_idx"]), _ptr(out["topk_val"]), _ptr(out["topk_hit"]),
             _ptr(out["train_flags"]), _ptr(out["test_flags"])))
         return out
+
+    def eval_stats(self):
+        out = numpy.zeros(8)
+        self._check(self._lib.hyprec_eval_stats(self._h, _ptr(out)))
+        return dict(fused=bool(out[0]), fallback_users=int(out[1]), rechecked_cells=int(out[2]),
+                    survivor_buffer_bytes=int(out[3]), dense_score_bytes=int(out[4]))
 
     def kernel_ms(self, which):
         """(total ms, timed regions, ms of the latest API call) of one kernel class."""

@@ -135,6 +135,7 @@ struct EngineBase {
     virtual int get_factor_rows(int side, const int64_t* rows, int64_t n_rows, double* out) = 0;
     virtual int comm_stats(double* out8) = 0;
     virtual bool comm_active() const = 0;
+    virtual int eval_stats(double* out8) = 0;
 };
 
 // What a rank publishes to its peers (hyprec_comm_export -> hyprec_comm_attach).
@@ -2069,6 +2070,21 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+    int eval_stats(double* out8) override {
+        for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+        out8[0] = last_topk_fused ? 1.0 : 0.0;
+        out8[2] = (double)last_border_cells;
+        if (last_topk_fused && vmax_buf.ptr) {
+            unsigned int fb = 0;
+            CU_TRY(cudaMemcpyAsync(&fb, vmax_buf.as<float>() + 1, sizeof(fb), cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            out8[1] = (double)fb;
+        }
+        out8[3] = (double)(surv.bytes + surv_cnt.bytes + sample_scores.bytes + cand_bits.bytes);
+        out8[4] = (double)dense_f32.bytes;
+        return HYPREC_OK;
+    }
+
     int solve_phase_cycles(long long* out16, int reset) override {
         HY_TRY(prof_buf.reserve(16 * sizeof(long long)));
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -2732,6 +2748,12 @@ int hyprec_elapsed_ms(hyprec_t* h, int from, int to, double* ms) {
     CU_TRY(cudaEventElapsedTime(&f, h->marks[from], h->marks[to]));
     *ms = (double)f;
     return HYPREC_OK;
+}
+
+int hyprec_eval_stats(hyprec_t* h, double* out8) {
+    HY_TRY(check(h));
+    if (!out8) return fail(HYPREC_E_INVALID, "hyprec_eval_stats: null output");
+    return h->engine->eval_stats(out8);
 }
 
 int hyprec_comm_blob_bytes(void) { return (int)sizeof(CommBlob); }

@@ -152,8 +152,9 @@ int hyprec_predict_dense(hyprec_t* h, double* out);
 
 /* Approximate predictions from the tensor-core sweep (tcgen05, 3xTF32 split, float32 accumulate),
  * n_users x n_items float32 on the host: |out - u.v| <= ~3e-5 * ||u|| * ||v||.
- * The evaluation uses this pass to decide cells far from a threshold and to pre-filter top-k
- * candidates; exposed for tests and diagnostics.  HYPREC_E_UNSUPPORTED when unavailable. */
+ * The evaluation runs the same sweep without storing it (cells far from a threshold are decided in the epilogue,
+ * top-k candidates above a per-user cut are emitted as a short list); this dense copy exists for tests and
+ * diagnostics only.  HYPREC_E_UNSUPPORTED when unavailable. */
 int hyprec_score_dense_f32(hyprec_t* h, float* out);
 
 /* The matrices the report needs besides train: full ratings (evaluator.ratings) and test.
@@ -197,6 +198,12 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
                      const int32_t* cand_ids, int capacity, double* thresholds,
                      int64_t* ones_per_row, int32_t* topk_idx, double* topk_val, double* topk_hit,
                      uint8_t* train_flags, uint8_t* test_flags);
+
+/* Diagnostics of the most recent hyprec_eval_topk: out8 = { top-k fed by sweep survivors (1) or by exact scoring of
+ * every candidate (0), users of that call that fell back to exact scoring, cells the rounded-count sweep re-checked
+ * in float64, bytes of the survivor / sample / bitmap buffers, bytes of the dense float32 score buffer (only
+ * hyprec_score_dense_f32 allocates it), 0... }. */
+int hyprec_eval_stats(hyprec_t* h, double* out8);
 
 /* Device time of the library's kernels, measured with CUDA events on the launching stream and
  * accumulated per class since creation / the last reset: total ms, number of timed regions, and

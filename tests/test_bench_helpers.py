@@ -101,6 +101,9 @@ def test_bench_line_python_flow_with_a_stand_in_handle(monkeypatch, capsys):
         def elapsed_ms(self, start, stop):
             return 1.5
 
+        def eval_stats(self):
+            return dict(fused=True, fallback_users=0)
+
         def probe_fma_tflops(self, precision):
             return 36.0
 

@@ -205,3 +205,61 @@ def test_scaled_shape_with_heavy_rows_fp32(native, monkeypatch):
     assert err_one.max() <= 5e-3
     assert row_errors(dv_heavy, dv_heavy_one).max() <= 5e-3
     assert abs(rmse - rmse_one) <= 1e-5 * max(1.0, rmse)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_fused_topk_equals_exact_scoring(native, monkeypatch, precision):
+    """The top-k fed by the sweep's survivors (no users x items score buffer) against exact scoring of every
+    candidate (HYPREC_FUSED_TOPK=0) and against the oracle's streamed lists: explicit lists with repeats, lists
+    shorter than the capacity, the full catalogue, capacities 64 / 200 / 300."""
+    from hyprec_b200 import synth
+    m, n, k = 300, 6000, 48
+    full = synth.ratings_csr("toy", n_users=m, n_items=n, positives=30000, min_degree=2, seed=31)
+    rs = numpy.random.RandomState(4)
+    coo = full.tocoo()
+    keep = rs.rand(full.nnz) < 0.8
+    train = oals.to_csr(sp.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=full.shape))
+    test = oals.to_csr(sp.csr_matrix((coo.data[~keep], (coo.row[~keep], coo.col[~keep])), shape=full.shape))
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    cands = [rs.randint(0, n, size=1500) for _ in range(m)]          # with repeats
+    cands[7] = rs.permutation(n)[:40]                               # shorter than every capacity
+    cp = numpy.zeros(m + 1, numpy.int64)
+    cp[1:] = numpy.cumsum([len(c) for c in cands])
+    ci = numpy.concatenate(cands).astype(numpy.int32)
+
+    def run(fused):
+        monkeypatch.setenv("HYPREC_FUSED_TOPK", fused)
+        h = native.Handle(0, precision)
+        h.set_train_csr(m, n, train.indptr, train.indices, train.data)
+        h.set_eval_csr((full.indptr, full.indices, full.data), (test.indptr, test.indices, test.data))
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        outs, stats = {}, {}
+        for cap in (64, 200, 300):
+            outs[("list", cap)] = h.eval_topk(cap, cp, ci, n_train_nz=train.nnz, n_test_nz=test.nnz)
+            stats[("list", cap)] = h.eval_stats()
+        outs[("all", 200)] = h.eval_topk(200, None, None, want_counts=False)
+        stats[("all", 200)] = h.eval_stats()
+        u, v = h.get_factors()
+        h.close()
+        return outs, stats, u, v
+
+    fused, fstats, u, v = run("1")
+    exact, estats, _, _ = run("0")
+    for key in fused:
+        assert fstats[key]["fused"] and not estats[key]["fused"], (key, fstats[key])
+        assert fstats[key]["dense_score_bytes"] == 0
+        assert fstats[key]["fallback_users"] <= m // 10, fstats[key]
+        for name in ("topk_idx", "topk_val", "topk_hit", "thresholds"):
+            assert numpy.array_equal(fused[key][name], exact[key][name]), (key, name)
+    assert numpy.array_equal(fused[("list", 200)]["ones_per_row"], exact[("list", 200)]["ones_per_row"])
+    out = fused[("list", 200)]
+    for uid in rs.choice(m, 40, replace=False).tolist() + [7]:
+        want, vals = oev.top_recommendations_fast(cands[uid], u[uid].dot(v[cands[uid]].T), 200)
+        got = list(out["topk_idx"][uid][:len(want)])
+        if got != want:
+            for g_id, w_id, w_val in zip(got, want, vals):
+                if g_id != w_id:
+                    assert abs(float(u[uid].dot(v[g_id])) - w_val) <= 1e-12 * max(abs(w_val), 1e-300) + 1e-18
+        assert numpy.all(out["topk_idx"][uid][len(want):] == -1)

@@ -17,6 +17,10 @@
 // The spin is bounded (globaltimer): a dead peer raises status 2 instead of hanging the GPU.
 #pragma once
 #include <stdint.h>
+#ifdef HYPREC_EMU
+#include <sched.h>
+#include <time.h>
+#endif
 
 #include "common.cuh"
 
@@ -30,6 +34,19 @@ struct PeerList {
     int rank;
 };
 
+#ifdef HYPREC_EMU
+// CPU emulator (tests/emu): ranks are host threads, arenas host memory
+inline void st_release_sys_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long ld_acquire_sys_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned long long global_timer_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __nanosleep(unsigned) { sched_yield(); }
+struct int4 { int x, y, z, w; };
+#else
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -43,6 +60,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 
 // flags of rank r: world x u64 at base[r] + off_flags; entry [src] is written by rank src only.
 __global__ void comm_signal_kernel(PeerList peers, size_t off_flags, unsigned long long seq) {

@@ -13,6 +13,7 @@ thread_local Block* t_block = nullptr;
 #include "../../hyprec_b200/csrc/gram.cuh"
 #include "../../hyprec_b200/csrc/score.cuh"
 #include "../../hyprec_b200/csrc/topk.cuh"
+#include "../../hyprec_b200/csrc/comm.cuh"
 
 using namespace hyprec;
 
@@ -306,6 +307,43 @@ void emu_eval_survivors_f64(const double* U, const double* V, int64_t m, int64_t
                             int grid, double prefilter_coef, int spill, unsigned int* fallbacks) {
     eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid, prefilter_coef,
                       spill != 0, true, fallbacks);
+}
+
+// One rank's side of `rounds` exchange rounds over host-memory "arenas" (csrc/comm.cuh): write own rows of a
+// replicated matrix, push them into every replica, push a mailbox slot, signal / wait, reduce the slots in rank
+// order, barrier again (nobody overwrites a slot another rank still reads).  Called from one host thread per rank.
+// Returns the status word (2: a barrier timed out).
+int emu_comm_rounds(void* const* bases, int world, int rank, uint64_t off_matrix, uint64_t off_slots, uint64_t slot_doubles,
+                    uint64_t off_flags, int k, const int64_t* bounds, int rounds, double* sums_out, uint64_t timeout_ns) {
+    PeerList peers;
+    memset(&peers, 0, sizeof(peers));
+    for (int r = 0; r < world; ++r) peers.base[r] = bases[r];
+    peers.world = world;
+    peers.rank = rank;
+    int status = 0;
+    unsigned long long seq = 0;
+    double* own = reinterpret_cast<double*>(static_cast<unsigned char*>(bases[rank]) + off_matrix);
+    std::vector<double> slot(slot_doubles);
+    auto barrier = [&]() {
+        ++seq;
+        emu::launch(dim3(1), dim3(32), 0, [&]() { comm_signal_kernel(peers, off_flags, seq); });
+        emu::launch(dim3(1), dim3(32), 0, [&]() { comm_wait_kernel(peers, off_flags, seq, timeout_ns, &status); });
+    };
+    for (int it = 0; it < rounds; ++it) {
+        const int64_t lo = bounds[rank], hi = bounds[rank + 1];
+        for (int64_t r = lo; r < hi; ++r)
+            for (int c = 0; c < k; ++c) own[r * k + c] = 1000.0 * it + 10.0 * r + c + 0.5 * rank;
+        emu::launch(dim3(2), dim3(64), 0, [&]() { push_rows_kernel<double>(peers, off_matrix, k, lo, hi - lo, nullptr); });
+        for (uint64_t i = 0; i < slot_doubles; ++i) slot[i] = (rank + 1) * (double)(i + 1) + it;
+        emu::launch(dim3(2), dim3(64), 0, [&]() { push_slot_kernel(peers, off_slots, slot_doubles, slot.data(), (int)slot_doubles); });
+        barrier();
+        const double* slots = reinterpret_cast<const double*>(static_cast<unsigned char*>(bases[rank]) + off_slots);
+        emu::launch(dim3((unsigned)((slot_doubles + 63) / 64)), dim3(64), 0, [&]() {
+            reduce_slots_kernel<double>(slots, slot_doubles, world, (int)slot_doubles, sums_out + (size_t)it * slot_doubles, nullptr);
+        });
+        barrier();
+    }
+    return status;
 }
 
 // device-generated candidate lists: fill == 0 writes counts[nu]; fill == 1 writes ids given the row pointers

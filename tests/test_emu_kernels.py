@@ -394,3 +394,52 @@ def test_hashed_candidate_lists(emu, n, fold, n_folds, seed):
         assert not (set(numpy.nonzero(full[u] * (test[u] == 0))[0].tolist()) & got)
     share = sum(len(w) for w in want) / float((hi - lo) * n)
     assert abs(share - 1.0 / n_folds) < 0.08
+
+
+def test_exchange_protocol_three_ranks(emu):
+    """csrc/comm.cuh on the CPU: three ranks as three host threads over host-memory arenas -- rows pushed into every
+    replica (push_rows_kernel), mailbox slots (push_slot_kernel), signal / wait barriers with sequence numbers,
+    rank-ordered reduction (reduce_slots_kernel).  Every rank ends with the same replica and the same sums; a rank
+    that never arrives makes the others time out (status 2) instead of hanging."""
+    import threading
+    world, k, rows, slot_doubles, rounds = 3, 5, 41, 37, 6
+    bounds = numpy.array([0, 9, 9 + 17, rows], dtype=numpy.int64)
+    off_matrix, off_slots = 0, 8 * rows * k
+    off_flags = off_slots + 8 * slot_doubles * world
+    size = off_flags + 8 * 8
+
+    def run(active, timeout_ns):
+        arenas = [numpy.zeros(size, dtype=numpy.uint8) for _ in range(world)]
+        bases = (ctypes.c_void_p * world)(*[a.ctypes.data for a in arenas])
+        sums = [numpy.zeros((rounds, slot_doubles)) for _ in range(world)]
+        status = [None] * world
+        fn = emu.emu_comm_rounds
+        fn.restype = ctypes.c_int
+
+        def work(r):
+            status[r] = fn(bases, world, r, ctypes.c_uint64(off_matrix), ctypes.c_uint64(off_slots), ctypes.c_uint64(slot_doubles),
+                           ctypes.c_uint64(off_flags), k, _ptr(bounds), rounds, _ptr(sums[r]), ctypes.c_uint64(timeout_ns))
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in active]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(120)
+        return arenas, sums, status
+
+    arenas, sums, status = run(range(world), 20 * 10 ** 9)
+    assert status == [0, 0, 0]
+    want = numpy.empty((rows, k))
+    for r in range(world):
+        for row in range(bounds[r], bounds[r + 1]):
+            want[row] = 1000.0 * (rounds - 1) + 10.0 * row + numpy.arange(k) + 0.5 * r
+    for r in range(world):
+        replica = arenas[r][off_matrix:off_matrix + 8 * rows * k].view(numpy.float64).reshape(rows, k)
+        assert numpy.array_equal(replica, want)
+        assert numpy.array_equal(sums[r], sums[0])
+    i = numpy.arange(slot_doubles) + 1.0
+    for it in range(rounds):
+        assert numpy.array_equal(sums[0][it], sum((r + 1) * i + it for r in range(world)))
+    # rank 2 never shows up: ranks 0 and 1 give up after the timeout and report it
+    _, _, status = run([0, 1], 2 * 10 ** 8)
+    assert status[0] == 2 and status[1] == 2 and status[2] is None

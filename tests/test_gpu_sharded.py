@@ -2,10 +2,13 @@
 the kernels' epilogues, mailbox Gram reduction, device barriers), driven through the C ABI.
 
 * one rank with the exchange attached == the plain handle;
-* two PROCESSES sharing ONE GPU (torchrun + gloo, arenas as CUDA IPC handles): the whole protocol -- partition, peer
-  stores, mailbox, barriers, sharded RMSE, the shared early stop of hyprec_train -- against the float64 oracle
-  (tools/dist_exchange_check.py --same-device);
-* two processes on two GPUs over NVLink (NCCL group; skipped on a one-GPU box).
+* two processes on two GPUs over NVLink (torchrun, CUDA IPC arenas; skipped on a one-GPU box -- ranks that wait on
+  one another must not share a GPU, /opt/skills/guides/B200_PROFILING.md): the whole protocol -- partition, peer
+  stores, mailbox, barriers, sharded RMSE, the shared early stop of hyprec_train, an empty item shard, the item
+  prior -- against the float64 oracle, plus the torch.distributed fallback and the reference-facing class on the
+  golden runs (tools/dist_exchange_check.py; its log on two B200s: profiles/r02_dist_exchange_check_2gpu.log).
+  The protocol's kernels also run on the CPU emulator with three ranks as three host threads
+  (tests/test_emu_kernels.py::test_exchange_protocol_three_ranks).
 
 Reference arithmetic: /root/reference/lib/collaborative_filtering.py:79-98 (als_step), :241-259 (epoch loop).
 """
@@ -104,17 +107,6 @@ def _torchrun(extra, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "dist_exchange_check.py")] + extra
     return subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT)
-
-
-def test_two_processes_on_one_gpu_ipc():
-    """Two ranks as two PROCESSES sharing GPU 0 (their contexts are time-sliced), arenas exchanged as CUDA IPC handles
-    over a gloo group: the whole protocol -- partition, peer stores from the epilogues, mailbox Gram reduction, device
-    barriers, sharded RMSE, the shared early stop of hyprec_train, an empty item shard, the item prior -- against the
-    float64 oracle, bit-identical replicas on both ranks, and the reference-facing class on the golden runs.  Runs on
-    the one-GPU box of the driver's test tier."""
-    proc = _torchrun(["--same-device", "--quick"], 29541)
-    assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-3000:]
-    assert "exchange: nvlink-peer-memory" in proc.stdout and "MISMATCH" not in proc.stdout, proc.stdout[-3000:]
 
 
 def test_two_processes_two_gpus_ipc():

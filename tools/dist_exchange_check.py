@@ -3,9 +3,9 @@ arenas, peer stores from the kernels' epilogues, mailbox reductions, device barr
 in float64 and float32; then the reference-facing class on the golden runs of the unmodified reference.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_exchange_check.py
-    ... tools/dist_exchange_check.py --same-device      # every rank on GPU 0 (a one-GPU box): the ranks are
-        separate processes whose contexts the GPU time-slices, the arenas still travel as CUDA IPC handles; the
-        process group is gloo (NCCL refuses two ranks on one device) and the torch.distributed fallback is not run
+
+One rank per GPU only: ranks wait for one another on the device (barrier kernels), and kernels that wait on one
+another must not share a GPU (/opt/skills/guides/B200_PROFILING.md).
 """
 import argparse
 import os
@@ -22,17 +22,12 @@ from hyprec_b200 import _native, distributed, synth  # noqa: E402
 from oracle import als as oals  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--same-device", action="store_true")
 ap.add_argument("--quick", action="store_true", help="the small cases only")
 args = ap.parse_args()
 
-local = 0 if args.same_device else int(os.environ.get("LOCAL_RANK", "0"))
-if args.same_device:
-    os.environ["HYPREC_DEVICE"] = "0"
-    dist.init_process_group("gloo")
-else:
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
 
@@ -79,7 +74,7 @@ for precision, k, tol, (m, n, nnz), with_prior, skewed in CASES:
         ub = distributed.partition_rows(train.indptr, world, k)
         ib = distributed.partition_rows(distributed.csc_indptr(train.indptr, train.indices, n), world, k)
     results = {}
-    for mode in (("peer",) if args.same_device else ("peer", "nccl")):
+    for mode in ("peer", "nccl"):
         h = _native.Handle(local, precision)
         h.set_train_csr(m, n, train.indptr, train.indices, train.data)
         h.set_factors(u0, v0)

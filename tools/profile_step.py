@@ -39,6 +39,7 @@ def main():
     n_cand = n // 5
     cands = numpy.stack([rs.permutation(n)[:n_cand] for _ in range(m)]).astype(numpy.int32)
     cp = numpy.arange(m + 1, dtype=numpy.int64) * n_cand
+    h.set_candidates(cp, cands.ravel())          # per fold, like bench.py
     for e in range(args.epochs):
         t0 = time.perf_counter()
         h.als_half_step(_native.SIDE_USER, 0.01)
@@ -46,10 +47,12 @@ def main():
         rmse = h.rmse()
         t1 = time.perf_counter()
         if not args.no_eval:
-            h.eval_topk(200, cp, cands.ravel(), n_train_nz=train.nnz, n_test_nz=test.nnz)
+            h.eval_topk(200, None, None, n_train_nz=train.nnz, n_test_nz=test.nnz)
         t2 = time.perf_counter()
         print("epoch %d rmse %.6f epoch %.2f ms eval %.2f ms" % (e, rmse, 1e3 * (t1 - t0), 1e3 * (t2 - t1)))
-    names = ["gram", "solve", "rmse", "sweep", "topk", "flags", "count", "prep"]
+    if not args.no_eval:
+        print("eval stats", h.eval_stats())
+    names = ["gram", "solve", "rmse", "sweep", "topk", "flags", "count", "prep", "comm"]
     for i, name in enumerate(names):
         total, calls, last = h.kernel_ms(i)
         print("%-6s total %.3f ms in %d regions" % (name, total, calls))

@@ -736,7 +736,10 @@ struct Engine : EngineBase {
         for (int i = 0; i < n_peer; ++i) s.peer_out[i] = peers[i];
         dim3 grid((unsigned)((rb + hyprec::kSweepTile - 1) / hyprec::kSweepTile),
                   (unsigned)((ra + hyprec::kSweepTile - 1) / hyprec::kSweepTile));
-        hyprec::score_sweep_kernel<T, hyprec::kSweepStore><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(s);
+        if (n_peer > 0)
+            hyprec::score_sweep_kernel<T, hyprec::kSweepStorePeers><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(s);
+        else
+            hyprec::score_sweep_kernel<T, hyprec::kSweepStore><<<grid, hyprec::kSweepThreads, 0, h->stream>>>(s);
         h->launches += 1;
         CU_TRY(cudaGetLastError());
         return HYPREC_OK;
@@ -1980,7 +1983,7 @@ struct Engine : EngineBase {
     }
 
     // ---- fused top-k: sampled columns -> per-user cut (topk.cuh) -------------------------------------------------
-    DevBuf surv, surv_cnt, cut_buf, cut_emit_buf, sample_f, sample_hi, sample_lo, sample_scores, cand_bits;
+    DevBuf surv, surv_cnt, cut_buf, cut_emit_buf, sample_f, sample_hi, sample_lo, sample_scores, cand_bits, cand_distinct;
     bool cand_bits_ok = false;      // the bitmap matches the candidate lists on the device
     bool fused_topk_enabled = getenv("HYPREC_FUSED_TOPK") == nullptr || getenv("HYPREC_FUSED_TOPK")[0] != '0';   // =0: exact scoring of every candidate
     bool last_topk_fused = false;
@@ -1991,8 +1994,9 @@ struct Engine : EngineBase {
         HY_TRY(cand_bits.reserve(sizeof(unsigned int) * (size_t)nu * words));
         CU_TRY(cudaMemsetAsync(cand_bits.ptr, 0, sizeof(unsigned int) * (size_t)nu * words, h->stream));
         const int grid = (int)std::min<int64_t>(nu, (int64_t)16 * h->num_sms);
+        HY_TRY(cand_distinct.reserve(sizeof(int32_t) * (size_t)nu));
         hyprec::cand_bitmap_kernel<<<grid, 256, 0, h->stream>>>(cand_ptr.as<int64_t>(), cand_ids.as<int32_t>(), nu, words,
-                                                                 cand_bits.as<unsigned int>());
+                                                                 cand_bits.as<unsigned int>(), cand_distinct.as<int32_t>());
         h->launches += 1;
         CU_TRY(cudaGetLastError());
         cand_bits_ok = true;
@@ -2387,6 +2391,7 @@ struct Engine : EngineBase {
                 a.surv_cnt = surv_cnt.as<unsigned int>();
                 a.surv_cap = hyprec::kSurvCap;
                 a.cut = cut_buf.as<float>();
+                a.cand_distinct = have_list ? cand_distinct.as<int32_t>() : nullptr;
                 a.unorm = unorm.as<float>();
                 a.err_coef = tc_margin_coef();
                 a.vmax = vmax_buf.as<float>();

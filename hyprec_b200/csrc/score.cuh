@@ -18,6 +18,7 @@ constexpr int kSweepKC = 16;
 constexpr int kSweepThreads = 256;
 constexpr int kSweepStore = 0;   // write the tile to a dense float64 matrix
 constexpr int kSweepCount = 1;   // count score >= threshold per row
+constexpr int kSweepStorePeers = 2;   // kSweepStore + the same stores into the replicas on the other GPUs
 
 template <typename T>
 struct SweepArgs {
@@ -56,14 +57,25 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
         for (int b = 0; b < 8; ++b) acc[a][b] = T(0);
 
     for (int c0 = 0; c0 < k; c0 += kSweepKC) {
-        for (int e = tid; e < kSweepTile * kSweepKC; e += kSweepThreads) {
+        // all of the step's global loads first (16 in flight per thread), then the shared-memory stores: left to
+        // the compiler the loop has come out as load -> store pairs, i.e. one exposed latency per element
+        constexpr int kStage = kSweepTile * kSweepKC / kSweepThreads;
+        T ureg[kStage], vreg[kStage];
+#pragma unroll
+        for (int i = 0; i < kStage; ++i) {
+            const int e = tid + i * kSweepThreads;
             const int rr = e / kSweepKC, cc = e % kSweepKC;
             const int col = c0 + cc;
             const int64_t ui = i0 + rr, vj = j0 + rr;
-            T uval = T(0);
-            if (ui < p.user_hi && col < k) uval = p.user_vecs[ui * k + col];
-            us[cc][rr] = uval;
-            vs[cc][rr] = (vj < p.n_items && col < k) ? p.item_vecs[vj * k + col] : T(0);
+            ureg[i] = (ui < p.user_hi && col < k) ? p.user_vecs[ui * k + col] : T(0);
+            vreg[i] = (vj < p.n_items && col < k) ? p.item_vecs[vj * k + col] : T(0);
+        }
+#pragma unroll
+        for (int i = 0; i < kStage; ++i) {
+            const int e = tid + i * kSweepThreads;
+            const int rr = e / kSweepKC, cc = e % kSweepKC;
+            us[cc][rr] = ureg[i];
+            vs[cc][rr] = vreg[i];
         }
         __syncthreads();
 #pragma unroll
@@ -85,7 +97,7 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
     for (int a = 0; a < 8; ++a) {
         const int64_t row = i0 + ty + 16 * a;
         const bool row_ok = row < p.user_hi;
-        if (MODE == kSweepStore) {
+        if (MODE == kSweepStore || MODE == kSweepStorePeers) {
             if (row_ok) {
                 const int64_t dst = p.row_list ? (int64_t)p.row_list[row] : row - p.user_lo;
 #pragma unroll
@@ -94,9 +106,11 @@ __global__ void __launch_bounds__(kSweepThreads) score_sweep_kernel(SweepArgs<T>
                     if (col < p.n_items) {
                         if (p.dense_out_f32) p.dense_out_f32[dst * p.n_items + col] = (float)acc[a][b];
                         else p.dense_out[dst * p.n_items + col] = (double)acc[a][b];
-                        for (int rep = 0; rep < p.n_peer; ++rep) {
-                            if (p.dense_out_f32) static_cast<float*>(p.peer_out[rep])[dst * p.n_items + col] = (float)acc[a][b];
-                            else static_cast<double*>(p.peer_out[rep])[dst * p.n_items + col] = (double)acc[a][b];
+                        if (MODE == kSweepStorePeers) {
+                            for (int rep = 0; rep < p.n_peer; ++rep) {
+                                if (p.dense_out_f32) static_cast<float*>(p.peer_out[rep])[dst * p.n_items + col] = (float)acc[a][b];
+                                else static_cast<double*>(p.peer_out[rep])[dst * p.n_items + col] = (double)acc[a][b];
+                            }
                         }
                     }
                 }

@@ -304,13 +304,19 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                         unsigned int cand = bits_row ? bits_row[(col0 + c) >> 5] : 0xffffffffu;
                         if (col0 + c + 32 > p.n) cand &= (col0 + c >= p.n) ? 0u : (0xffffffffu >> (32 - (int)(p.n - col0 - c)));
                         if (cand) {
+                            // one compare + one predicated OR per cell; the (rare) appends run off the mask
+                            unsigned int pass = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float sv = __uint_as_float(v[j]);
-                                if (((cand >> j) & 1u) && sv >= cut_f) {
-                                    const unsigned int at = atomicAdd(p.surv_cnt + row, 1u);
-                                    if (at < (unsigned int)p.surv_cap)
-                                        p.surv[(size_t)row * p.surv_cap + at] = make_uint2((unsigned int)(col0 + c + j), v[j]);
+                            for (int j = 0; j < 32; ++j) pass |= (__uint_as_float(v[j]) >= cut_f) ? (1u << j) : 0u;
+                            pass &= cand;
+                            if (pass) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if (pass & (1u << j)) {
+                                        const unsigned int at = atomicAdd(p.surv_cnt + row, 1u);
+                                        if (at < (unsigned int)p.surv_cap)
+                                            p.surv[(size_t)row * p.surv_cap + at] = make_uint2((unsigned int)(col0 + c + j), v[j]);
+                                    }
                                 }
                             }
                         }

@@ -39,6 +39,7 @@ struct TopkLayout {
 HYPREC_HD TopkLayout topk_layout(int max_cand, int k, int sort_size, bool prefilter, bool survivors = false) {
     TopkLayout l;
     size_t o = 0;
+    if (survivors && max_cand > 0 && max_cand < kSurvCap) max_cand = kSurvCap;   // the emitted cells are staged in these arrays
     l.off_keys = o;
     o += 8 * (size_t)max_cand;
     l.off_pos = o;
@@ -105,6 +106,7 @@ struct TopkArgs {
     const unsigned int* surv_cnt = nullptr; // [n_local_users] cells emitted (may exceed surv_cap)
     int surv_cap = 0;
     const float* cut = nullptr;             // [n_local_users]
+    const int32_t* cand_distinct = nullptr; // [n_local_users] distinct items of the user's stream (cand_bitmap_kernel); null: unknown
 };
 
 // order-preserving map double -> uint64 (larger score <=> larger key)
@@ -193,7 +195,7 @@ __device__ __forceinline__ KeyT radix_select(const KeyT* keys, int count, int kt
 template <typename T, bool kSpill = false>
 __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) {
     HYPREC_DYN_SMEM(smem_raw);
-    __shared__ int s_digit, s_need, s_count, s_nsel;
+    __shared__ int s_digit, s_need, s_count, s_nsel, s_nge, s_flag;
     const bool sparse = p.surv != nullptr;
     const bool prefilter = p.approx != nullptr || sparse;
     // kSpill is a compile-time switch so that the shared-memory instantiation keeps shared-memory
@@ -213,7 +215,6 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
     int* scan = (int*)(smem_raw + lay.off_scan);
     unsigned int* hkeys = (unsigned int*)(smem_raw + lay.off_hash);          // item id + 1 (0: empty)
     unsigned int* hvals = hkeys + kSurvSlots;                                 // float32 bits
-    __shared__ int s_nge;
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int k = p.k, cap = p.capacity, P = p.sort_size;
 
@@ -223,169 +224,224 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
         const int ncand = p.cand_ids ? (int)(p.cand_indptr[ul + 1] - cbase) : (int)p.n_items;
         __syncthreads();   // previous user's shared state is dead
         for (int c = tid; c < k; c += kTopkThreads) uvec[c] = (double)p.user_vecs[u * k + c];
-        if (tid == 0) s_nsel = 0;
         __syncthreads();
 
-        // ---- scores -------------------------------------------------------------------------------
-        // np elements end up in keys[] (exact float64 scores); element j is stream position
-        // (shortlist ? posarr[j] : j).  Both orders are ascending in stream position.
-        int np = ncand;
-        bool shortlist = false;
-        bool usable = prefilter && ncand > cap;
-        if (usable && sparse) {
-            // the user's survivors into a hash table, then one pass over the candidate stream: a stream element
-            // gets the float32 score of its item if the sweep emitted it, else the lowest key
-            const unsigned int cnt = p.surv_cnt[ul];
-            usable = cnt <= (unsigned int)p.surv_cap;
-            if (usable) {
-                for (int i = tid; i < 2 * kSurvSlots; i += kTopkThreads) hkeys[i] = 0u;
-                if (tid == 0) s_nge = 0;
-                __syncthreads();
-                const uint2* mine = p.surv + (size_t)ul * p.surv_cap;
-                for (unsigned int i = tid; i < cnt; i += kTopkThreads) {
-                    const uint2 cell = mine[i];
-                    unsigned int slot = (cell.x * 2654435761u) >> 21;             // 11 bits: kSurvSlots == 2048
-                    while (atomicCAS(&hkeys[slot], 0u, cell.x + 1u) != 0u) slot = (slot + 1) & (kSurvSlots - 1);
-                    hvals[slot] = cell.y;
-                }
-                __syncthreads();
+        // Survivors mode, first attempt: work on the emitted cells alone -- no pass over the candidate stream.
+        // Possible when every candidate occurs once in the stream (then a cell is a stream element) and no tie
+        // needs the stream order; a user that turns out to need it is redone through the stream (second attempt).
+        const unsigned int n_surv = sparse ? p.surv_cnt[ul] : 0u;
+        const bool surv_ok = sparse && ncand > cap && n_surv <= (unsigned int)p.surv_cap;
+        const bool no_repeats = p.cand_ids == nullptr || (p.cand_distinct != nullptr && p.cand_distinct[ul] == ncand);
+        int nsel = 0;
+        bool items_direct = false;     // selpos / posarr hold item ids instead of stream positions
+        for (int attempt = (surv_ok && no_repeats) ? 0 : 1; attempt < 2; ++attempt) {
+            const bool fast = attempt == 0;
+            items_direct = fast;
+            __syncthreads();
+            if (tid == 0) { s_nsel = 0; s_nge = 0; s_flag = 0; }
+            __syncthreads();
+
+            // ---- scores ---------------------------------------------------------------------------
+            // np elements end up in keys[] (exact float64 scores); element j is stream position
+            // (shortlist ? posarr[j] : j) -- or item posarr[j] on the fast attempt.
+            int np = ncand;
+            bool shortlist = false;
+            bool usable = prefilter && ncand > cap;
+            if (usable && sparse && fast) {
                 const float cut = p.cut[ul];
+                const uint2* mine = p.surv + (size_t)ul * p.surv_cap;
                 int n_ge = 0;
-                for (int c = tid; c < ncand; c += kTopkThreads) {
-                    const unsigned int item = p.cand_ids ? (unsigned int)p.cand_ids[cbase + c] : (unsigned int)c;
-                    unsigned int slot = (item * 2654435761u) >> 21;
-                    unsigned int key = 0u;
-                    while (true) {
-                        const unsigned int have = hkeys[slot];
-                        if (have == 0u) break;
-                        if (have == item + 1u) {
-                            const float val = __uint_as_float(hvals[slot]);
-                            key = float_key(val);
-                            n_ge += val >= cut ? 1 : 0;
-                            break;
-                        }
-                        slot = (slot + 1) & (kSurvSlots - 1);
-                    }
-                    keys32[c] = key;
+                for (unsigned int i = tid; i < n_surv; i += kTopkThreads) {
+                    const uint2 cell = mine[i];
+                    const float val = __uint_as_float(cell.y);
+                    keys32[i] = float_key(val);
+                    hkeys[i] = cell.x;                             // the hash area doubles as the item list here
+                    n_ge += val >= cut ? 1 : 0;
                 }
                 if (n_ge) atomicAdd(&s_nge, n_ge);
                 __syncthreads();
                 usable = s_nge >= cap;
-            }
-            if (!usable && tid == 0 && p.fallbacks) atomicAdd(p.fallbacks, 1u);
-            __syncthreads();
-        } else if (usable) {
-            const float* arow = p.approx + ul * p.approx_ld;
-            for (int c = tid; c < ncand; c += kTopkThreads) {
-                const int64_t item = p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c;
-                keys32[c] = float_key(arow[item]);
-            }
-            __syncthreads();
-        }
-        if (usable) {
-            int need32, equal32;
-            const unsigned int kth = radix_select<unsigned int>(keys32, ncand, cap, hist, &s_digit, &s_need, &s_count,
-                                                                &need32, &equal32);
-            // every exact top / cut-off-tied candidate has s~ >= (capacity-th largest s~) - 2E
-            const double err = (double)p.err_coef * (double)p.unorm[ul] * (double)(*p.vmax);
-            const double bound = (double)key_float(kth) - 2.0 * err;
-            // ordered compaction of the survivors (stream order is part of the tie rule)
-            const int chunk = (ncand + kTopkThreads - 1) / kTopkThreads;
-            const int c_lo = tid * chunk, c_hi = c_lo + chunk < ncand ? c_lo + chunk : ncand;
-            int mine = 0;
-            for (int c = c_lo; c < c_hi; ++c) mine += ((double)key_float(keys32[c]) >= bound) ? 1 : 0;
-            scan[tid + 1] = mine;
-            if (tid == 0) scan[0] = 0;
-            __syncthreads();
-            if (tid == 0)
-                for (int t = 1; t <= kTopkThreads; ++t) scan[t] += scan[t - 1];
-            __syncthreads();
-            const int total = scan[kTopkThreads];
-            if (total <= kTopkMaxShortlist && total <= p.max_cand) {
-                int at = scan[tid];
-                for (int c = c_lo; c < c_hi; ++c)
-                    if ((double)key_float(keys32[c]) >= bound) posarr[at++] = c;
-                np = total;
-                shortlist = true;
-            } else if (tid == 0 && p.fallbacks) {
-                atomicAdd(p.fallbacks, 1u);
-            }
-            __syncthreads();
-        }
-        // exact float64 scores: one warp per element, coalesced read of the item's factor row
-        for (int j = warp; j < np; j += kTopkThreads / 32) {
-            const int c = shortlist ? posarr[j] : j;
-            const int64_t item = p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c;
-            const double s = warp_dot(uvec, p.item_vecs + item * k, k, lane);
-            if (lane == 0) keys[j] = score_key(s);
-        }
-        __syncthreads();
-
-        // ---- cut-off = capacity-th largest key ------------------------------------------------
-        unsigned long long cutoff = 0;
-        int need = cap;          // how many elements equal to the cut-off are kept
-        int n_equal = 0;         // how many elements equal the cut-off
-        const bool select = np > cap;
-        if (select)
-            cutoff = radix_select<unsigned long long>(keys, np, cap, hist, &s_digit, &s_need, &s_count, &need, &n_equal);
-
-        // ---- survivors -------------------------------------------------------------------------
-        const bool replay = select && n_equal != need;   // tie straddles the cut-off
-        for (int i = tid; i < np; i += kTopkThreads) {
-            const unsigned long long key = keys[i];
-            if (!select || key > cutoff || (!replay && key == cutoff)) {
-                const int slot = atomicAdd(&s_nsel, 1);
-                selkey[slot] = key;
-                selpos[slot] = shortlist ? posarr[i] : i;
-            }
-        }
-        __syncthreads();
-        if (replay && tid == 0) {
-            // stream order matters only among elements >= cut-off
-            int held = 0, head = 0, tail = 0;
-            for (int i = 0; i < np; ++i) {
-                const unsigned long long key = keys[i];
-                if (key > cutoff) {
-                    if (held == cap) ++head; else ++held;
-                } else if (key == cutoff && held < cap) {
-                    fifo[tail % P] = shortlist ? posarr[i] : i;
-                    ++tail;
-                    ++held;
+                if (usable) {
+                    int need32, equal32;
+                    const unsigned int kth = radix_select<unsigned int>(keys32, (int)n_surv, cap, hist, &s_digit, &s_need, &s_count,
+                                                                        &need32, &equal32);
+                    const double err = (double)p.err_coef * (double)p.unorm[ul] * (double)(*p.vmax);
+                    const double bound = (double)key_float(kth) - 2.0 * err;
+                    for (unsigned int i = tid; i < n_surv; i += kTopkThreads)
+                        if ((double)key_float(keys32[i]) >= bound) posarr[atomicAdd(&s_flag, 1)] = (int)hkeys[i];
+                    __syncthreads();
+                    np = s_flag;
+                    shortlist = true;
+                    __syncthreads();
+                    if (tid == 0) s_flag = 0;
+                } else {
+                    // the cut was misjudged for this user: exact scoring of every candidate (through the stream)
+                    if (tid == 0 && p.fallbacks) atomicAdd(p.fallbacks, 1u);
+                    items_direct = false;
                 }
-            }
-            int slot = s_nsel;
-            for (int q = head; q < tail; ++q) {
-                selkey[slot] = cutoff;
-                selpos[slot] = fifo[q % P];
-                ++slot;
-            }
-            s_nsel = slot;
-        }
-        __syncthreads();
-        const int nsel = s_nsel;
-        for (int i = nsel + tid; i < P; i += kTopkThreads) {
-            selkey[i] = 0;     // below every finite score's key
-            selpos[i] = -1;
-        }
-        __syncthreads();
-
-        // ---- bitonic sort of the survivors: (key desc, stream position desc) -----------------
-        for (int size = 2; size <= P; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = tid; i < P / 2; i += kTopkThreads) {
-                    const int lo = 2 * i - (i & (stride - 1));
-                    const int hi = lo + stride;
-                    const bool up = (lo & size) == 0;
-                    const unsigned long long kl = selkey[lo], kh = selkey[hi];
-                    const int pl = selpos[lo], ph = selpos[hi];
-                    const bool swap = up ? topk_before(kh, ph, kl, pl) : topk_before(kl, pl, kh, ph);
-                    if (swap) {
-                        selkey[lo] = kh; selkey[hi] = kl;
-                        selpos[lo] = ph; selpos[hi] = pl;
+                __syncthreads();
+            } else if (usable && sparse) {
+                // the user's survivors into a hash table, then one pass over the candidate stream: a stream element
+                // gets the float32 score of its item if the sweep emitted it, else the lowest key
+                usable = n_surv <= (unsigned int)p.surv_cap;
+                if (usable) {
+                    for (int i = tid; i < 2 * kSurvSlots; i += kTopkThreads) hkeys[i] = 0u;
+                    __syncthreads();
+                    const uint2* mine = p.surv + (size_t)ul * p.surv_cap;
+                    for (unsigned int i = tid; i < n_surv; i += kTopkThreads) {
+                        const uint2 cell = mine[i];
+                        unsigned int slot = (cell.x * 2654435761u) >> 21;             // 11 bits: kSurvSlots == 2048
+                        while (atomicCAS(&hkeys[slot], 0u, cell.x + 1u) != 0u) slot = (slot + 1) & (kSurvSlots - 1);
+                        hvals[slot] = cell.y;
                     }
+                    __syncthreads();
+                    const float cut = p.cut[ul];
+                    int n_ge = 0;
+                    for (int c = tid; c < ncand; c += kTopkThreads) {
+                        const unsigned int item = p.cand_ids ? (unsigned int)p.cand_ids[cbase + c] : (unsigned int)c;
+                        unsigned int slot = (item * 2654435761u) >> 21;
+                        unsigned int key = 0u;
+                        while (true) {
+                            const unsigned int have = hkeys[slot];
+                            if (have == 0u) break;
+                            if (have == item + 1u) {
+                                const float val = __uint_as_float(hvals[slot]);
+                                key = float_key(val);
+                                n_ge += val >= cut ? 1 : 0;
+                                break;
+                            }
+                            slot = (slot + 1) & (kSurvSlots - 1);
+                        }
+                        keys32[c] = key;
+                    }
+                    if (n_ge) atomicAdd(&s_nge, n_ge);
+                    __syncthreads();
+                    usable = s_nge >= cap;
+                }
+                if (!usable && tid == 0 && p.fallbacks && attempt == 1 && !(surv_ok && no_repeats)) atomicAdd(p.fallbacks, 1u);
+                __syncthreads();
+            } else if (usable) {
+                const float* arow = p.approx + ul * p.approx_ld;
+                for (int c = tid; c < ncand; c += kTopkThreads) {
+                    const int64_t item = p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c;
+                    keys32[c] = float_key(arow[item]);
                 }
                 __syncthreads();
             }
+            if (usable && !(sparse && fast)) {
+                int need32, equal32;
+                const unsigned int kth = radix_select<unsigned int>(keys32, ncand, cap, hist, &s_digit, &s_need, &s_count,
+                                                                    &need32, &equal32);
+                // every exact top / cut-off-tied candidate has s~ >= (capacity-th largest s~) - 2E
+                const double err = (double)p.err_coef * (double)p.unorm[ul] * (double)(*p.vmax);
+                const double bound = (double)key_float(kth) - 2.0 * err;
+                // ordered compaction of the survivors (stream order is part of the tie rule)
+                const int chunk = (ncand + kTopkThreads - 1) / kTopkThreads;
+                const int c_lo = tid * chunk, c_hi = c_lo + chunk < ncand ? c_lo + chunk : ncand;
+                int mine = 0;
+                for (int c = c_lo; c < c_hi; ++c) mine += ((double)key_float(keys32[c]) >= bound) ? 1 : 0;
+                scan[tid + 1] = mine;
+                if (tid == 0) scan[0] = 0;
+                __syncthreads();
+                if (tid == 0)
+                    for (int t = 1; t <= kTopkThreads; ++t) scan[t] += scan[t - 1];
+                __syncthreads();
+                const int total = scan[kTopkThreads];
+                if (total <= kTopkMaxShortlist && total <= p.max_cand) {
+                    int at = scan[tid];
+                    for (int c = c_lo; c < c_hi; ++c)
+                        if ((double)key_float(keys32[c]) >= bound) posarr[at++] = c;
+                    np = total;
+                    shortlist = true;
+                } else if (tid == 0 && p.fallbacks) {
+                    atomicAdd(p.fallbacks, 1u);
+                }
+                __syncthreads();
+            }
+            // exact float64 scores: one warp per element, coalesced read of the item's factor row
+            for (int j = warp; j < np; j += kTopkThreads / 32) {
+                const int c = shortlist ? posarr[j] : j;
+                const int64_t item = items_direct ? (int64_t)c : (p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c);
+                const double s = warp_dot(uvec, p.item_vecs + item * k, k, lane);
+                if (lane == 0) keys[j] = score_key(s);
+            }
+            __syncthreads();
+
+            // ---- cut-off = capacity-th largest key ------------------------------------------------
+            unsigned long long cutoff = 0;
+            int need = cap;          // how many elements equal to the cut-off are kept
+            int n_equal = 0;         // how many elements equal the cut-off
+            const bool select = np > cap;
+            if (select)
+                cutoff = radix_select<unsigned long long>(keys, np, cap, hist, &s_digit, &s_need, &s_count, &need, &n_equal);
+
+            // ---- survivors -------------------------------------------------------------------------
+            const bool replay = select && n_equal != need;   // tie straddles the cut-off
+            if (replay && items_direct) continue;            // needs the stream order: second attempt
+            for (int i = tid; i < np; i += kTopkThreads) {
+                const unsigned long long key = keys[i];
+                if (!select || key > cutoff || (!replay && key == cutoff)) {
+                    const int slot = atomicAdd(&s_nsel, 1);
+                    selkey[slot] = key;
+                    selpos[slot] = shortlist ? posarr[i] : i;
+                }
+            }
+            __syncthreads();
+            if (replay && tid == 0) {
+                // stream order matters only among elements >= cut-off
+                int held = 0, head = 0, tail = 0;
+                for (int i = 0; i < np; ++i) {
+                    const unsigned long long key = keys[i];
+                    if (key > cutoff) {
+                        if (held == cap) ++head; else ++held;
+                    } else if (key == cutoff && held < cap) {
+                        fifo[tail % P] = shortlist ? posarr[i] : i;
+                        ++tail;
+                        ++held;
+                    }
+                }
+                int slot = s_nsel;
+                for (int q = head; q < tail; ++q) {
+                    selkey[slot] = cutoff;
+                    selpos[slot] = fifo[q % P];
+                    ++slot;
+                }
+                s_nsel = slot;
+            }
+            __syncthreads();
+            nsel = s_nsel;
+            for (int i = nsel + tid; i < P; i += kTopkThreads) {
+                selkey[i] = 0;     // below every finite score's key
+                selpos[i] = -1;
+            }
+            __syncthreads();
+
+            // ---- bitonic sort of the survivors: (key desc, stream position desc) -----------------
+            for (int size = 2; size <= P; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int i = tid; i < P / 2; i += kTopkThreads) {
+                        const int lo = 2 * i - (i & (stride - 1));
+                        const int hi = lo + stride;
+                        const bool up = (lo & size) == 0;
+                        const unsigned long long kl = selkey[lo], kh = selkey[hi];
+                        const int pl = selpos[lo], ph = selpos[hi];
+                        const bool swap = up ? topk_before(kh, ph, kl, pl) : topk_before(kl, pl, kh, ph);
+                        if (swap) {
+                            selkey[lo] = kh; selkey[hi] = kl;
+                            selpos[lo] = ph; selpos[hi] = pl;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            // fast attempt over an explicit list: equal scores are ordered by stream position, which it does not know
+            if (items_direct && p.cand_ids != nullptr) {
+                for (int i = tid; i + 1 < nsel; i += kTopkThreads)
+                    if (selkey[i] == selkey[i + 1]) s_flag = 1;
+                __syncthreads();
+                if (s_flag != 0) continue;                     // second attempt, through the stream
+            }
+            break;
         }
 
         // ---- outputs ---------------------------------------------------------------------------
@@ -395,7 +451,7 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
             double val = 0.0, hit = 0.0;
             if (r < nsel) {
                 const int pos = selpos[r];
-                item = p.cand_ids ? p.cand_ids[cbase + pos] : (int32_t)pos;
+                item = items_direct ? (int32_t)pos : (p.cand_ids ? p.cand_ids[cbase + pos] : (int32_t)pos);
                 val = key_score(selkey[r]);
                 if (p.full_indptr != nullptr && val >= thr) {
                     int64_t a = p.full_indptr[u], b = p.full_indptr[u + 1];
@@ -514,15 +570,27 @@ __global__ void __launch_bounds__(kTopkThreads) hashed_candidates_kernel(HashedC
 //      so the result never depends on the sample.
 // Replaces the dense `predictions[user][index]` reads of /root/reference/lib/evaluator.py:226-230.
 // ---------------------------------------------------------------------------------------------------
+// (bits zeroed by the caller; distinct[u] = number of different items in user u's stream, may be null)
 __global__ void cand_bitmap_kernel(const int64_t* __restrict__ cand_indptr, const int32_t* __restrict__ cand_ids, int64_t n_users,
-                                   int64_t words, unsigned int* __restrict__ bits) {
+                                   int64_t words, unsigned int* __restrict__ bits, int32_t* __restrict__ distinct) {
+    __shared__ int s_pop;
     for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x) {
         unsigned int* row = bits + u * words;
         const int64_t lo = cand_indptr[u], hi = cand_indptr[u + 1];
+        if (threadIdx.x == 0) s_pop = 0;
         for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
             const unsigned int item = (unsigned int)cand_ids[e];
             atomicOr(&row[item >> 5], 1u << (item & 31u));
         }
+        __syncthreads();
+        if (distinct != nullptr) {
+            int pop = 0;
+            for (int64_t w = threadIdx.x; w < words; w += blockDim.x) pop += __popc(row[w]);
+            if (pop) atomicAdd(&s_pop, pop);
+            __syncthreads();
+            if (threadIdx.x == 0) distinct[u] = s_pop;
+        }
+        __syncthreads();
     }
 }
 
@@ -547,25 +615,34 @@ struct SampleCutArgs {
     float* cut_emit;               // [n_local_users] = cut - 2E, rounded down
 };
 
+constexpr int kCutStaged = 8192;          // sampled columns whose keys are kept in shared memory between the passes
+
 __global__ void __launch_bounds__(kTopkThreads) sample_cut_kernel(SampleCutArgs p) {
     __shared__ unsigned hist[256];
+    __shared__ unsigned staged[kCutStaged];
     __shared__ int s_digit, s_need, s_count, s_total;
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const bool stage = p.n_sample <= kCutStaged;       // (else every pass re-reads the scores and the bitmap)
     for (int64_t ul = blockIdx.x; ul < p.n_users; ul += gridDim.x) {
         const float* row = p.scores + ul * p.scores_ld;
         const unsigned int* bits = p.cand_bits ? p.cand_bits + ul * p.bits_ld : nullptr;
-        auto key_of = [&](int64_t j) -> unsigned int {
+        auto key_raw = [&](int64_t j) -> unsigned int {
             if (bits) {
                 const int64_t item = sample_item(j, p.n_sample, p.n_items);
                 if (((bits[item >> 5] >> (item & 31)) & 1u) == 0u) return 0u;
             }
             return float_key(row[j]);
         };
+        auto key_of = [&](int64_t j) -> unsigned int { return stage ? staged[j] : key_raw(j); };
         __syncthreads();
         if (tid == 0) s_total = 0;
         __syncthreads();
         int mine = 0;
-        for (int64_t j = tid; j < p.n_sample; j += kTopkThreads) mine += key_of(j) != 0u ? 1 : 0;
+        for (int64_t j = tid; j < p.n_sample; j += kTopkThreads) {
+            const unsigned int key = key_raw(j);
+            if (stage) staged[j] = key;
+            mine += key != 0u ? 1 : 0;
+        }
         if (mine) atomicAdd(&s_total, mine);
         __syncthreads();
         const int n_sc = s_total;

@@ -192,13 +192,15 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
     // (sample_cut_kernel), and the cells the sweep's epilogue would emit (candidate cells with s~ >= cut - 2E),
     // here taken from the perturbed `approx` scores in a scrambled order
     std::vector<unsigned int> bits, surv_cnt;
+    std::vector<int32_t> distinct;
     std::vector<uint2> surv;
     std::vector<float> cut, cut_emit, sample;
     if (survivors) {
         const int64_t words = (n + 31) / 32;
         if (ci) {
             bits.assign((size_t)nu * words, 0u);
-            emu::launch(dim3(3), dim3(64), 0, [&]() { cand_bitmap_kernel(cp, ci, nu, words, bits.data()); });
+            distinct.assign(nu, 0);
+            emu::launch(dim3(3), dim3(64), 0, [&]() { cand_bitmap_kernel(cp, ci, nu, words, bits.data(), distinct.data()); });
         }
         const int target = std::max(2 * cap, cap + 64);
         int64_t n_sample = std::min<int64_t>(n, std::max<int64_t>(16, (32 * n + target - 1) / target));
@@ -238,6 +240,7 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
     if (survivors) {
         a.approx = nullptr;
         a.surv = surv.data(); a.surv_cnt = surv_cnt.data(); a.surv_cap = kSurvCap; a.cut = cut.data();
+        a.cand_distinct = ci ? distinct.data() : nullptr;
     }
     if (!spill) {
         emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T>(a); });

@@ -240,6 +240,8 @@ def test_eval_from_sweep_survivors_is_exact(emu, coef, spill):
     fp, fi, fv = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
     lists = [rs.randint(0, n, size=1200) for _ in range(m)]
     lists[4] = rs.permutation(n)[:15]                      # fewer candidates than the capacity
+    lists[1] = rs.permutation(n)[:1200]                    # no repeats: the emitted cells alone decide (fast attempt)
+    lists[3] = rs.permutation(n)[:2500]
     for cands in (None, lists):
         if cands is None:
             cp = ci = None

@@ -267,12 +267,18 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                 thr_err = fabsf(thr_f) * 1.1920929e-7f;
                 un = p.unorm[row] * p.margin_coef * 1.001f;
             }
+            // (fetched before the wait for the accumulator: the bitmap words of this warp's two 32-column chunks)
             float cut_f = 0.f;
-            const unsigned int* bits_row = nullptr;
+            unsigned int cand_w[kBN / 64] = {0xffffffffu, 0xffffffffu};
             const bool emit = row_ok && p.surv_cut != nullptr;
             if (emit) {
                 cut_f = p.surv_cut[row];
-                if (p.cand_bits) bits_row = p.cand_bits + row * p.bits_ld;
+#pragma unroll
+                for (int q = 0; q < kBN / 64; ++q) {
+                    const int64_t cq = col0 + half * (kBN / 2) + 32 * q;
+                    if (p.cand_bits) cand_w[q] = cq < p.n ? p.cand_bits[row * p.bits_ld + (cq >> 5)] : 0u;
+                    if (cq + 32 > p.n) cand_w[q] &= (cq >= p.n) ? 0u : (0xffffffffu >> (32 - (int)(p.n - cq)));
+                }
             }
             mbar_wait(&acc_full[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -300,22 +306,22 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_const
                         }
                     }
                     if (emit) {
-                        // (col0 + c is a multiple of 32: one bitmap word per chunk; columns past n are masked off)
-                        unsigned int cand = bits_row ? bits_row[(col0 + c) >> 5] : 0xffffffffu;
-                        if (col0 + c + 32 > p.n) cand &= (col0 + c >= p.n) ? 0u : (0xffffffffu >> (32 - (int)(p.n - col0 - c)));
+                        const unsigned int cand = cand_w[(c - half * (kBN / 2)) >> 5];
                         if (cand) {
-                            // one compare + one predicated OR per cell; the (rare) appends run off the mask
+                            // one compare + one predicated OR per cell; the (rare) appends run off the mask, with ONE
+                            // reservation in the user's list per chunk (a returning atomic is a round trip to L2)
                             unsigned int pass = 0;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) pass |= (__uint_as_float(v[j]) >= cut_f) ? (1u << j) : 0u;
                             pass &= cand;
                             if (pass) {
+                                unsigned int at = atomicAdd(p.surv_cnt + row, (unsigned int)__popc(pass));
+                                uint2* list = p.surv + (size_t)row * p.surv_cap;
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
                                     if (pass & (1u << j)) {
-                                        const unsigned int at = atomicAdd(p.surv_cnt + row, 1u);
-                                        if (at < (unsigned int)p.surv_cap)
-                                            p.surv[(size_t)row * p.surv_cap + at] = make_uint2((unsigned int)(col0 + c + j), v[j]);
+                                        if (at < (unsigned int)p.surv_cap) list[at] = make_uint2((unsigned int)(col0 + c + j), v[j]);
+                                        ++at;
                                     }
                                 }
                             }

@@ -358,12 +358,30 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
                 }
                 __syncthreads();
             }
-            // exact float64 scores: one warp per element, coalesced read of the item's factor row
-            for (int j = warp; j < np; j += kTopkThreads / 32) {
-                const int c = shortlist ? posarr[j] : j;
-                const int64_t item = items_direct ? (int64_t)c : (p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c);
-                const double s = warp_dot(uvec, p.item_vecs + item * k, k, lane);
-                if (lane == 0) keys[j] = score_key(s);
+            // exact float64 scores: one warp per element, coalesced read of the item's factor row; four elements at
+            // a time per warp so that their loads (L2 latency) and shuffle reductions overlap
+            constexpr int kWarps = kTopkThreads / 32;
+            for (int j0 = 4 * warp; j0 < np; j0 += 4 * kWarps) {
+                const T* rows[4];
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = j0 + q < np ? j0 + q : np - 1;
+                    const int c = shortlist ? posarr[j] : j;
+                    const int64_t item = items_direct ? (int64_t)c : (p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c);
+                    rows[q] = p.item_vecs + item * k;
+                }
+                for (int l = lane; l < k; l += 32) {
+                    const double ul_ = uvec[l];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += ul_ * (double)rows[q][l];
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], d);
+                }
+                if (lane < 4 && j0 + lane < np) keys[j0 + lane] = score_key(lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]);
             }
             __syncthreads();
 

@@ -1983,7 +1983,7 @@ struct Engine : EngineBase {
     }
 
     // ---- fused top-k: sampled columns -> per-user cut (topk.cuh) -------------------------------------------------
-    DevBuf surv, surv_cnt, cut_buf, cut_emit_buf, sample_f, sample_hi, sample_lo, sample_scores, cand_bits, cand_distinct;
+    DevBuf surv, surv_cnt, cut_buf, cut_emit_buf, sample_f, sample_hi, sample_lo, sample_scores, cand_bits, cand_distinct, topk_redo;
     bool cand_bits_ok = false;      // the bitmap matches the candidate lists on the device
     bool fused_topk_enabled = getenv("HYPREC_FUSED_TOPK") == nullptr || getenv("HYPREC_FUSED_TOPK")[0] != '0';   // =0: exact scoring of every candidate
     bool last_topk_fused = false;
@@ -2397,7 +2397,32 @@ struct Engine : EngineBase {
                 a.vmax = vmax_buf.as<float>();
                 a.fallbacks = reinterpret_cast<unsigned int*>(vmax_buf.as<float>() + 1);
             }
-            {
+            if (fused) {
+                // pass 1: the emitted cells alone, small per-candidate arrays, several CTAs per SM; users that need
+                // the candidate stream (repeats in the stream, ties in the order, a misjudged cut) are flagged ...
+                HY_TRY(topk_redo.reserve((size_t)nu));
+                CU_TRY(cudaMemsetAsync(topk_redo.ptr, 0, (size_t)nu, h->stream));
+                hyprec::TopkArgs<T> f = a;
+                f.pass = 1;
+                f.redo = topk_redo.as<unsigned char>();
+                f.max_cand = hyprec::kSurvCap;
+                f.spill = nullptr;
+                f.spill_stride = 0;
+                const hyprec::TopkLayout flay = hyprec::topk_layout(hyprec::kSurvCap, k, sort_size, true, true);
+                auto fkern = hyprec::eval_topk_kernel<T, false>;
+                HY_TRY(ensure_dynamic_smem((const void*)fkern, (int)std::max(flay.total, spill ? (size_t)0 : lay.total)));
+                int fper_sm = 0;
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fper_sm, fkern, hyprec::kTopkThreads, flay.total));
+                fper_sm = std::max(fper_sm, 1);
+                const int fgrid = (int)std::min<int64_t>(nu, (int64_t)fper_sm * h->num_sms);
+                Timer t(h, HYPREC_T_TOPK);
+                fkern<<<fgrid, hyprec::kTopkThreads, flay.total, h->stream>>>(f);
+                // ... and pass 2 does those through the stream, with arrays for the whole stream
+                a.pass = 2;
+                a.redo = topk_redo.as<unsigned char>();
+                kern<<<grid, hyprec::kTopkThreads, lay.total, h->stream>>>(a);
+                h->launches += 2;
+            } else {
                 Timer t(h, HYPREC_T_TOPK);
                 kern<<<grid, hyprec::kTopkThreads, lay.total, h->stream>>>(a);
                 h->launches += 1;

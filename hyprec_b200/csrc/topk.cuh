@@ -107,6 +107,11 @@ struct TopkArgs {
     int surv_cap = 0;
     const float* cut = nullptr;             // [n_local_users]
     const int32_t* cand_distinct = nullptr; // [n_local_users] distinct items of the user's stream (cand_bitmap_kernel); null: unknown
+    // Two launches instead of one (survivors mode): pass 1 works on the emitted cells alone with per-candidate arrays
+    // of kSurvCap entries (several CTAs per SM) and flags the users that need the candidate stream (redo[u] = 1);
+    // pass 2 handles only those, with arrays sized for the whole stream.  0: one launch does both (tests).
+    int pass = 0;
+    unsigned char* redo = nullptr;          // [n_local_users], zeroed before pass 1
 };
 
 // order-preserving map double -> uint64 (larger score <=> larger key)
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
 
     for (int64_t u = p.user_lo + blockIdx.x; u < p.user_hi; u += gridDim.x) {
         const int64_t ul = u - p.user_lo;
+        if (p.pass == 2 && p.redo[ul] == 0) continue;         // pass 1 finished this user
         const int64_t cbase = p.cand_ids ? p.cand_indptr[ul] : 0;
         const int ncand = p.cand_ids ? (int)(p.cand_indptr[ul + 1] - cbase) : (int)p.n_items;
         __syncthreads();   // previous user's shared state is dead
@@ -234,7 +240,10 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
         const bool no_repeats = p.cand_ids == nullptr || (p.cand_distinct != nullptr && p.cand_distinct[ul] == ncand);
         int nsel = 0;
         bool items_direct = false;     // selpos / posarr hold item ids instead of stream positions
-        for (int attempt = (surv_ok && no_repeats) ? 0 : 1; attempt < 2; ++attempt) {
+        bool finished = false;
+        const int first_attempt = (p.pass == 2) ? 1 : ((surv_ok && no_repeats) ? 0 : 1);
+        const int last_attempt = (p.pass == 1) ? 0 : 1;
+        for (int attempt = first_attempt; attempt <= last_attempt; ++attempt) {
             const bool fast = attempt == 0;
             items_direct = fast;
             __syncthreads();
@@ -276,8 +285,9 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
                     if (tid == 0) s_flag = 0;
                 } else {
                     // the cut was misjudged for this user: exact scoring of every candidate (through the stream)
-                    if (tid == 0 && p.fallbacks) atomicAdd(p.fallbacks, 1u);
                     items_direct = false;
+                    if (p.pass == 1) break;                    // ... by the second launch (which also counts it)
+                    if (tid == 0 && p.fallbacks) atomicAdd(p.fallbacks, 1u);
                 }
                 __syncthreads();
             } else if (usable && sparse) {
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
                     __syncthreads();
                     usable = s_nge >= cap;
                 }
-                if (!usable && tid == 0 && p.fallbacks && attempt == 1 && !(surv_ok && no_repeats)) atomicAdd(p.fallbacks, 1u);
+                if (!usable && tid == 0 && p.fallbacks && (p.pass == 2 || !(surv_ok && no_repeats))) atomicAdd(p.fallbacks, 1u);
                 __syncthreads();
             } else if (usable) {
                 const float* arow = p.approx + ul * p.approx_ld;
@@ -361,27 +371,32 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
             // exact float64 scores: one warp per element, coalesced read of the item's factor row; four elements at
             // a time per warp so that their loads (L2 latency) and shuffle reductions overlap
             constexpr int kWarps = kTopkThreads / 32;
-            for (int j0 = 4 * warp; j0 < np; j0 += 4 * kWarps) {
-                const T* rows[4];
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            constexpr int kIlp = 8;
+            for (int j0 = kIlp * warp; j0 < np; j0 += kIlp * kWarps) {
+                const T* rows[kIlp];
+                double acc[kIlp];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kIlp; ++q) {
                     const int j = j0 + q < np ? j0 + q : np - 1;
                     const int c = shortlist ? posarr[j] : j;
                     const int64_t item = items_direct ? (int64_t)c : (p.cand_ids ? (int64_t)p.cand_ids[cbase + c] : (int64_t)c);
                     rows[q] = p.item_vecs + item * k;
+                    acc[q] = 0.0;
                 }
                 for (int l = lane; l < k; l += 32) {
                     const double ul_ = uvec[l];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] += ul_ * (double)rows[q][l];
+                    for (int q = 0; q < kIlp; ++q) acc[q] += ul_ * (double)rows[q][l];
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], d);
+                    for (int q = 0; q < kIlp; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], d);
                 }
-                if (lane < 4 && j0 + lane < np) keys[j0 + lane] = score_key(lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]);
+                double mine = acc[0];
+#pragma unroll
+                for (int q = 1; q < kIlp; ++q) mine = lane == q ? acc[q] : mine;
+                if (lane < kIlp && j0 + lane < np) keys[j0 + lane] = score_key(mine);
             }
             __syncthreads();
 
@@ -459,11 +474,26 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
                 __syncthreads();
                 if (s_flag != 0) continue;                     // second attempt, through the stream
             }
+            finished = true;
             break;
+        }
+        if (!finished) {
+            // (pass 1 only) this user needs the candidate stream: the second launch takes it
+            if (tid == 0 && p.redo) p.redo[ul] = 1;
+            continue;
         }
 
         // ---- outputs ---------------------------------------------------------------------------
+        // (the user's ratings row is staged in shared memory when it fits the stream-position scratch: the hit
+        // lookups are then binary searches without a global-memory round trip per step)
         const double thr = p.thresholds[u];
+        const int64_t f_lo = p.full_indptr ? p.full_indptr[u] : 0, f_hi = p.full_indptr ? p.full_indptr[u + 1] : 0;
+        const int f_len = (int)(f_hi - f_lo);
+        const bool row_staged = p.full_indptr != nullptr && f_len <= P;
+        if (row_staged) {
+            for (int i = tid; i < f_len; i += kTopkThreads) fifo[i] = p.full_indices[f_lo + i];
+            __syncthreads();
+        }
         for (int r = tid; r < cap; r += kTopkThreads) {
             int32_t item = -1;
             double val = 0.0, hit = 0.0;
@@ -472,12 +502,22 @@ __global__ void __launch_bounds__(kTopkThreads) eval_topk_kernel(TopkArgs<T> p) 
                 item = items_direct ? (int32_t)pos : (p.cand_ids ? p.cand_ids[cbase + pos] : (int32_t)pos);
                 val = key_score(selkey[r]);
                 if (p.full_indptr != nullptr && val >= thr) {
-                    int64_t a = p.full_indptr[u], b = p.full_indptr[u + 1];
-                    while (a < b) {   // lower bound of item in the sorted row
-                        const int64_t mid = (a + b) >> 1;
-                        if (p.full_indices[mid] < item) a = mid + 1; else b = mid;
+                    int64_t a = f_lo, b = f_hi;
+                    if (row_staged) {
+                        int x = 0, y = f_len;
+                        while (x < y) {
+                            const int mid = (x + y) >> 1;
+                            if (fifo[mid] < item) x = mid + 1; else y = mid;
+                        }
+                        a = f_lo + x;
+                        if (x < f_len && fifo[x] == item) hit = p.full_values[a];
+                    } else {
+                        while (a < b) {   // lower bound of item in the sorted row
+                            const int64_t mid = (a + b) >> 1;
+                            if (p.full_indices[mid] < item) a = mid + 1; else b = mid;
+                        }
+                        if (a < f_hi && p.full_indices[a] == item) hit = p.full_values[a];
                     }
-                    if (a < p.full_indptr[u + 1] && p.full_indices[a] == item) hit = p.full_values[a];
                 }
             }
             if (p.topk_idx) p.topk_idx[ul * cap + r] = item;

@@ -140,7 +140,7 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
                       const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
                       const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
                       int grid, double prefilter_coef = 0.0, bool spill = false, bool survivors = false,
-                      unsigned int* fallbacks_out = nullptr) {
+                      unsigned int* fallbacks_out = nullptr, bool two_pass = false) {
     std::vector<double> part(2 * (size_t)k), colsum(k);
     const int64_t per = (n + 1) / 2;
     emu::launch(dim3(2), dim3(64), 0, [&]() { colsum_partial_kernel<T>(V, n, k, per, part.data()); });
@@ -242,6 +242,15 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
         a.surv = surv.data(); a.surv_cnt = surv_cnt.data(); a.surv_cap = kSurvCap; a.cut = cut.data();
         a.cand_distinct = ci ? distinct.data() : nullptr;
     }
+    std::vector<unsigned char> redo(nu, 0);
+    if (survivors && two_pass) {
+        // as api.cu launches it: pass 1 on the emitted cells alone (arrays of kSurvCap entries), pass 2 for the flagged users
+        TopkArgs<T> f = a;
+        f.pass = 1; f.redo = redo.data(); f.max_cand = kSurvCap;
+        const TopkLayout flay = topk_layout(kSurvCap, k, sort_size, true, true);
+        emu::launch(dim3(grid), dim3(kTopkThreads), flay.total, [&]() { eval_topk_kernel<T>(f); });
+        a.pass = 2; a.redo = redo.data();
+    }
     if (!spill) {
         emu::launch(dim3(grid), dim3(kTopkThreads), lay.total, [&]() { eval_topk_kernel<T>(a); });
         if (fallbacks_out) memcpy(fallbacks_out, vmax + 1, sizeof(unsigned int));
@@ -308,8 +317,9 @@ void emu_eval_survivors_f64(const double* U, const double* V, int64_t m, int64_t
                             const int64_t* cp, const int32_t* ci, int cap, const int64_t* fp, const int32_t* fi,
                             const double* fv, double* thr, int64_t* ones, int32_t* tidx, double* tval, double* thit,
                             int grid, double prefilter_coef, int spill, unsigned int* fallbacks) {
+    // spill: bit 0 = per-candidate arrays in a global scratch, bit 1 = two launches (pass 1 / pass 2)
     eval_impl<double>(U, V, m, n, k, lo, hi, cp, ci, cap, fp, fi, fv, thr, ones, tidx, tval, thit, grid, prefilter_coef,
-                      spill != 0, true, fallbacks);
+                      (spill & 1) != 0, true, fallbacks, (spill & 2) != 0);
 }
 
 // One rank's side of `rounds` exchange rounds over host-memory "arenas" (csrc/comm.cuh): write own rows of a

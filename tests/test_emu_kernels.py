@@ -223,13 +223,14 @@ def test_eval_prefilter_is_exact(emu, coef):
             assert numpy.allclose(tval[u_id][:len(want)], vals, rtol=1e-12, atol=1e-15)
 
 
-@pytest.mark.parametrize("coef,spill", [(1e-6, 0), (3e-3, 0), (0.5, 0), (1e-6, 1)])
+@pytest.mark.parametrize("coef,spill", [(1e-6, 0), (3e-3, 0), (0.5, 0), (1e-6, 1), (1e-6, 2), (0.5, 2), (3e-3, 3)])
 def test_eval_from_sweep_survivors_is_exact(emu, coef, spill):
     """The top-k without a dense score matrix: candidate bitmap, per-user cut from sampled columns
     (sample_cut_kernel), only the candidate cells with s~ >= cut - 2E handed over (in scrambled order), hash lookup
     while streaming the candidate list, exact float64 re-score.  Tight bound, loose bound, useless bound (every user
     falls back to exact scoring), full catalogue, explicit lists with repeats, a zero user (all scores tied), more
-    candidates than the capacity and fewer; and the spilled variant."""
+    candidates than the capacity and fewer; the spilled variant (spill & 1); and the two-launch form the library uses
+    (spill & 2: pass 1 on the emitted cells alone with small arrays, pass 2 through the stream for the flagged users)."""
     rs = numpy.random.RandomState(int(coef * 1e6) % 1000 + 5)
     m, n, k, cap = 6, 3000, 6, 20
     u = numpy.round((rs.rand(m, k) - 0.3) * 4) / 4

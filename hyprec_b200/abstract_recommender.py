@@ -109,7 +109,8 @@ class AbstractRecommender(object):
         train_recall = ev.calculate_recall(self.train_data, rounded_predictions)
         test_recall = ev.calculate_recall(self.test_data, rounded_predictions)
         recall_at_x = ev.recall_at_x(200, predictions, self.test_data, rounded_predictions)
-        ratio = sum(sum(rounded_predictions)) / sum(sum(self.ratings))
+        total = self.ratings.sum() if hasattr(self.ratings, 'todense') else sum(sum(self.ratings))
+        ratio = sum(sum(rounded_predictions)) / total
         mrr_at_five = ev.calculate_mrr(5, predictions, self.test_data, rounded_predictions)
         ndcg_at_five = ev.calculate_ndcg(5, predictions, self.test_data, rounded_predictions)
         mrr_at_ten = ev.calculate_mrr(10, predictions, self.test_data, rounded_predictions)

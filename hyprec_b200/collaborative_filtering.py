@@ -45,6 +45,17 @@ def _precision_from_env():
     raise ValueError("HYPREC_PRECISION must be fp64 or fp32, got %r" % name)
 
 
+def _total(matrix):
+    """``sum(sum(matrix))`` of the reference (abstract_recommender.py:115) for dense or sparse matrices."""
+    if sp.issparse(matrix):
+        return numpy.float64(matrix.sum())
+    return sum(sum(matrix))
+
+
+# get_predictions() hands out a dense users x items float64 array; above this size it raises instead
+DENSE_PREDICTIONS_LIMIT_BYTES = int(os.environ.get("HYPREC_DENSE_LIMIT_BYTES", 8 << 30))
+
+
 def _csr_triplet(matrix):
     """(indptr int64, indices int32, values float64) of a dense or scipy-sparse matrix, zeros
     dropped, column ids sorted."""
@@ -385,6 +396,12 @@ class CollaborativeFiltering(AbstractRecommender):
     def get_predictions(self):
         """collaborative_filtering.py:262-284; the dense product is computed on the device."""
         if self.predictions is None or not self.prediction_fold == self.hyperparameters['fold']:
+            need = 8 * self.n_users * self.n_items
+            if need > DENSE_PREDICTIONS_LIMIT_BYTES:
+                raise MemoryError("get_predictions(): the dense %d x %d float64 score matrix needs %.1f GB (limit "
+                                  "HYPREC_DENSE_LIMIT_BYTES = %.1f GB); the evaluation report, recommend_items and "
+                                  "dump_recommendations do not need it" %
+                                  (self.n_users, self.n_items, need / 1e9, DENSE_PREDICTIONS_LIMIT_BYTES / 1e9))
             h = self._upload_factors()
             collaborative_predictions = h.predict_dense()
             if self._is_hybrid:
@@ -459,6 +476,8 @@ class CollaborativeFiltering(AbstractRecommender):
         """The candidate stream of every user exactly as load_top_recommendations reads it:
         ``evaluator.test_indices[user * (1 + fold)]`` cast to int (evaluator.py:225-228; SURVEY.md
         App. A Q6 / Q7 describe what that slot holds for k-fold and naive splits)."""
+        if hasattr(self.evaluator, 'candidate_lists'):         # hyprec_b200.Evaluator (dense or sparse test_indices)
+            return self.evaluator.candidate_lists(fold)
         rows = [numpy.asarray(self.evaluator.test_indices[user * (1 + fold)]).astype(numpy.int64)
                 for user in range(self.n_users)]
         indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
@@ -472,11 +491,16 @@ class CollaborativeFiltering(AbstractRecommender):
         import torch.distributed as dist
         users, _ = self._shard_bounds(world)
         lo, hi = users[rank], users[rank + 1]
-        cand_indptr, cand_ids = self.candidate_lists(fold)
         train_ptr = self._host_csr(self.train_data)[0]
         test_ptr = self._host_csr(self.test_data)[0]
-        part = h.eval_topk(self.n_recommendations, cand_indptr[lo:hi + 1] - cand_indptr[lo],
-                           cand_ids[cand_indptr[lo]:cand_indptr[hi]], lo, hi,
+        hashed = getattr(self.evaluator, 'hashed_candidates', None)
+        if hashed is not None:
+            h.set_hashed_candidates(fold % hashed[0], hashed[0], hashed[1])
+            cp = ci = None
+        else:
+            cand_indptr, cand_ids = self.candidate_lists(fold)
+            cp, ci = cand_indptr[lo:hi + 1] - cand_indptr[lo], cand_ids[cand_indptr[lo]:cand_indptr[hi]]
+        part = h.eval_topk(self.n_recommendations, cp, ci, lo, hi,
                            n_train_nz=int(train_ptr[hi] - train_ptr[lo]), n_test_nz=int(test_ptr[hi] - test_ptr[lo]))
         self._cands_uploaded = None
         gathered = [None] * world
@@ -536,7 +560,14 @@ class CollaborativeFiltering(AbstractRecommender):
         rank, world = self._world()
         if world == 1:
             key = (self.evaluator.test_indices, fold)
-            if self._cands_uploaded is None or self._cands_uploaded[0] is not key[0] or self._cands_uploaded[1] != fold:
+            hashed = getattr(self.evaluator, 'hashed_candidates', None)
+            if hashed is not None:
+                # device-generated lists (Evaluator.use_hashed_candidates): nothing to enumerate on the host
+                h.set_candidates(None, None)
+                h.set_hashed_candidates(fold % hashed[0], hashed[0], hashed[1])
+                self._cands_uploaded = None
+            elif self._cands_uploaded is None or self._cands_uploaded[0] is not key[0] or self._cands_uploaded[1] != fold:
+                h.set_hashed_candidates(0, 0)
                 h.set_candidates(*self.candidate_lists(fold))        # once per fold
                 self._cands_uploaded = key
             out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users,
@@ -559,7 +590,7 @@ class CollaborativeFiltering(AbstractRecommender):
             # sum(rounded[ratings.nonzero()]) / sum(sum(ratings))  (evaluator.py:263-266)
             train_recall = numpy.float64(out["train_flags"].sum(dtype=numpy.int64)) / numpy.float64(train_sum)
             test_recall = numpy.float64(out["test_flags"].sum(dtype=numpy.int64)) / numpy.float64(test_sum)
-            ratio = numpy.float64(out["ones_per_row"].sum()) / sum(sum(self.ratings))
+            ratio = numpy.float64(out["ones_per_row"].sum()) / _total(self.ratings)
         test_likes = numpy.asarray(self.test_data.sum(axis=1)).ravel()
         recall_at_x = metrics.recall_at_x(self.recall_cutoff, hits, test_likes)
         mrr_at_five = metrics.mrr_at(5, hits, lengths)

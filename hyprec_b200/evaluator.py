@@ -16,7 +16,12 @@ What differs is how the work is done, not what comes out:
   which keeps the reported scalars bit-identical;
 * ``load_top_recommendations`` and everything that needs scores is normally driven by
   ``hyprec_b200.CollaborativeFiltering.get_evaluation_report`` from device results
-  (``set_device_results``); the dense-matrix entry points remain for API compatibility.
+  (``set_device_results``); the dense-matrix entry points remain for API compatibility;
+* ``ratings`` may be a scipy sparse matrix ("dense API at scale"): the splits then
+  consume the random stream exactly as above but hand out scipy CSR train / test matrices built from the
+  index lists -- no dense users x items array exists anywhere -- and, for shapes whose per-user candidate
+  lists cannot be enumerated (the k-fold lists hold n_items / k_folds ids per user, the naive split's lists
+  n_items), ``use_hashed_candidates`` switches the evaluation to device-generated lists.
 """
 import numpy
 import scipy.sparse as sp
@@ -26,7 +31,13 @@ from hyprec_b200.top_recommendations import TopRecommendations, top_k_stream_ord
 
 class Evaluator(object):
     def __init__(self, ratings, abstracts_preprocessor=None, random_seed=False, verbose=False):
+        self.sparse = sp.issparse(ratings)
+        if self.sparse:
+            ratings = sp.csr_matrix(ratings, dtype=numpy.float64)
+            ratings.eliminate_zeros()
+            ratings.sort_indices()
         self.ratings = ratings
+        self.hashed_candidates = None            # (n_folds, seed) once use_hashed_candidates() was called
         self.n_users, self.n_items = ratings.shape
         if abstracts_preprocessor:
             self.abstracts_preprocessor = abstracts_preprocessor
@@ -49,7 +60,16 @@ class Evaluator(object):
     def get_ratings(self):
         return self.ratings
 
+    def use_hashed_candidates(self, n_folds=5, seed=0):
+        """Rank, for every user, its test positives plus the 1 / n_folds share of its unrated items that a hash of
+        (user, item, seed) selects, generated on the device (include/hyprec_b200.h,
+        hyprec_set_hashed_candidates) -- for problem sizes whose candidate lists the host cannot enumerate.  No
+        counterpart in the reference (its lists come from per-user shuffles, evaluator.py:162-192)."""
+        self.hashed_candidates = (int(n_folds), int(seed))
+
     def ratings_csr(self):
+        if self.sparse:
+            return self.ratings
         if self._ratings_csr is None:
             csr = sp.csr_matrix(self.ratings, dtype=numpy.float64)
             csr.eliminate_zeros()
@@ -71,9 +91,17 @@ class Evaluator(object):
         if self.random_seed is False:
             numpy.random.seed(42)
         csr = self.ratings_csr()
+        keys = []
+        if self.sparse:
+            for user in range(self.n_users):
+                non_zeros = csr.indices[csr.indptr[user]:csr.indptr[user + 1]]
+                picked = numpy.random.choice(non_zeros, size=int(self.test_percentage * len(non_zeros)))   # :92-93
+                keys.append(user * self.n_items + picked.astype(numpy.int64))
+            train, test = self._split_sparse(numpy.concatenate(keys) if keys else numpy.zeros(0, dtype=numpy.int64))
+            self.test_indices = test
+            return train, test
         test = numpy.zeros(self.ratings.shape)
         train = self.ratings.copy()
-        keys = []
         for user in range(self.n_users):
             non_zeros = csr.indices[csr.indptr[user]:csr.indptr[user + 1]]
             # sampling WITH replacement, evaluator.py:92-93
@@ -139,11 +167,13 @@ class Evaluator(object):
         gather and written with one scatter; the CSR forms of both matrices fall out of the same cell set and are
         kept for ``csr_view`` (the device wants CSR; re-scanning two dense m x n matrices per fold costs more than
         the epochs)."""
-        ratings = numpy.asarray(self.ratings)
         lengths = [len(x) for x in test_indices]
         rows = numpy.repeat(numpy.arange(self.n_users, dtype=numpy.int64), lengths)
         cols = (numpy.concatenate([numpy.asarray(x, dtype=numpy.int64) for x in test_indices])
                 if len(rows) else numpy.zeros(0, dtype=numpy.int64))
+        if self.sparse:
+            return self._split_sparse(rows * self.n_items + cols)
+        ratings = numpy.asarray(self.ratings)
         values = ratings[rows, cols]
         rated = values != 0
         rows, cols, values = rows[rated], cols[rated], values[rated]
@@ -155,26 +185,44 @@ class Evaluator(object):
         return train, test
 
     # ------------------------------------------------------------------ CSR views of the dense matrices
-    def _remember_csr(self, train, test, test_keys):
+    def _split_triplets(self, test_keys, only_rated):
+        """CSR triplets of (train, test) given the cells (key = user * n_items + item) that move to the test matrix;
+        ``only_rated``: the keys may name cells without a rating (k-fold lists), which change nothing."""
         full = self.ratings_csr()
         full_rows = numpy.repeat(numpy.arange(self.n_users, dtype=numpy.int64), numpy.diff(full.indptr))
         full_keys = full_rows * self.n_items + full.indices
         in_test = numpy.zeros(full.nnz, dtype=bool)
         if len(test_keys):
-            in_test[numpy.searchsorted(full_keys, numpy.unique(test_keys))] = True
-        views = []
-        for dense, mask in ((train, ~in_test), (test, in_test)):
+            keys = numpy.unique(test_keys)
+            at = numpy.searchsorted(full_keys, keys)
+            if only_rated:
+                at = numpy.minimum(at, max(full.nnz - 1, 0))
+                at = at[full_keys[at] == keys] if full.nnz else at[:0]
+            in_test[at] = True
+        out = []
+        for mask in (~in_test, in_test):
             indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
             numpy.cumsum(numpy.bincount(full_rows[mask], minlength=self.n_users), out=indptr[1:])
-            views.append((dense, (indptr, full.indices[mask].astype(numpy.int32), full.data[mask].astype(numpy.float64))))
-        self._csr_views = views
+            out.append((indptr, full.indices[mask].astype(numpy.int32), full.data[mask].astype(numpy.float64)))
+        return out
+
+    def _remember_csr(self, train, test, test_keys):
+        views = self._split_triplets(test_keys, only_rated=False)
+        self._csr_views = [(train, views[0]), (test, views[1])]
+
+    def _split_sparse(self, test_keys):
+        """train / test as scipy CSR matrices, straight from the index lists (sparse ``ratings``)."""
+        views = self._split_triplets(test_keys, only_rated=True)
+        mats = [sp.csr_matrix((v[2], v[1], v[0]), shape=(self.n_users, self.n_items)) for v in views]
+        self._csr_views = [(mats[0], views[0]), (mats[1], views[1])]
+        return mats[0], mats[1]
 
     def csr_view(self, matrix):
         """(indptr int64, indices int32, values float64) of ``matrix`` when it is the ratings matrix or one of the
         matrices of the latest fold AND still holds exactly those entries (same number of non-zeros, same values
         at the recorded cells: an in-place edit by the caller is noticed); None otherwise."""
         triplet = None
-        if matrix is self.ratings and isinstance(matrix, numpy.ndarray):
+        if matrix is self.ratings:
             csr = self.ratings_csr()
             triplet = (csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64))
         for dense, view in getattr(self, '_csr_views', []):
@@ -183,6 +231,8 @@ class Evaluator(object):
         if triplet is None:
             return None
         indptr, indices, values = triplet
+        if sp.issparse(matrix):             # built here from these very arrays; a caller's edit shows in the count
+            return triplet if matrix.nnz == len(indices) else None
         if numpy.count_nonzero(matrix) != len(indices):
             return None
         rows = numpy.repeat(numpy.arange(matrix.shape[0], dtype=numpy.int64), numpy.diff(indptr))
@@ -196,6 +246,21 @@ class Evaluator(object):
         including the reference's ``user * (1 + fold)`` slot arithmetic and,
         for the naive split, the dense test rows whose 0./1. values are cast to item ids
         (App. A Q7).  Returns (indptr int64[m+1], ids int32[total])."""
+        if sp.issparse(self.test_indices):
+            # naive split of sparse ratings: the reference walks the DENSE test row of every user and casts its 0. / 1.
+            # values to item ids (App. A Q7) -- n_items entries per user
+            if self.n_users * self.n_items > (1 << 31):
+                raise MemoryError("the naive split's candidate lists hold n_items entries per user (%d x %d here): call "
+                                  "Evaluator.use_hashed_candidates() to rank device-generated lists instead" %
+                                  (self.n_users, self.n_items))
+            test = self.test_indices
+            ids = numpy.zeros(self.n_users * self.n_items, dtype=numpy.int32)
+            rows_of = numpy.repeat(numpy.arange(self.n_users, dtype=numpy.int64), numpy.diff(test.indptr))
+            ids[rows_of * self.n_items + test.indices] = test.data.astype(numpy.int32)
+            slots = numpy.arange(self.n_users, dtype=numpy.int64) * (1 + fold)
+            if fold != 0:
+                ids = ids.reshape(self.n_users, self.n_items)[slots].ravel()
+            return numpy.arange(self.n_users + 1, dtype=numpy.int64) * self.n_items, ids
         rows = [numpy.asarray(self.test_indices[user * (1 + fold)]).astype(numpy.int64)
                 for user in range(self.n_users)]
         indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
@@ -204,8 +269,9 @@ class Evaluator(object):
         return indptr, ids
 
     def load_top_recommendations(self, n_recommendations, predictions, test_data, fold):
+        cand_indptr, cand_ids = self.candidate_lists(fold)
         for user in range(self.n_users):
-            cand = numpy.asarray(self.test_indices[user * (1 + fold)]).astype(numpy.int64)
+            cand = cand_ids[cand_indptr[user]:cand_indptr[user + 1]].astype(numpy.int64)
             ids, _ = top_k_stream_order(cand, numpy.asarray(predictions[user])[cand], n_recommendations)
             self.recommendation_indices[user] = ids
         self.recs_loaded = True
@@ -222,19 +288,28 @@ class Evaluator(object):
     def get_rmse(self, predicted, actual=None):
         if actual is None:
             actual = self.ratings
+        if sp.issparse(actual):
+            actual = numpy.asarray(actual.todense())
         rss = 0
         for i in range(predicted.shape[0]):
             rss += numpy.sum((predicted[i] - actual[i]) ** 2)
         return numpy.sqrt(float(rss) / numpy.size(predicted))
 
     def calculate_recall(self, ratings, predictions):
+        if sp.issparse(ratings):
+            rows, cols = ratings.nonzero()
+            return sum(numpy.asarray(predictions)[rows, cols]) / numpy.float64(ratings.sum())
         denom = sum(sum(ratings))
         return sum(predictions[ratings.nonzero()]) / denom
 
     def _hits(self, rounded_predictions):
         if self._device_hits is not None and rounded_predictions is None:
             return self._device_hits
-        return [numpy.asarray(self.ratings[user])[numpy.asarray(recs, dtype=numpy.int64)] *
+        def row(user):
+            if self.sparse:
+                return numpy.asarray(self.ratings[user].todense()).ravel()
+            return numpy.asarray(self.ratings[user])
+        return [row(user)[numpy.asarray(recs, dtype=numpy.int64)] *
                 numpy.asarray(rounded_predictions[user])[numpy.asarray(recs, dtype=numpy.int64)]
                 for user, recs in enumerate(self.recommendation_indices)]
 

@@ -160,3 +160,57 @@ def test_fold_matrices_and_csr_views_match_the_literal_construction():
     zr, zc = numpy.argwhere(train == 0)[0]
     train[zr, zc] = 1.0                                      # entry added in place
     assert ev.csr_view(train) is None
+
+
+def test_sparse_ratings_give_the_same_splits_without_dense_matrices():
+    """Evaluator(scipy sparse ratings): the k-fold and naive splits consume the random stream exactly as with the
+    dense array and hand out scipy CSR train / test matrices equal to the dense ones; candidate
+    streams are identical, including the naive split's ids-0/1 degeneration (App. A Q7)."""
+    import scipy.sparse as sp
+    from hyprec_b200 import Evaluator, synth
+    full = synth.ratings_csr("toy", n_users=60, n_items=200, positives=1500, min_degree=2, seed=3)
+    dense = numpy.asarray(full.todense())
+    for folds in (5, 1):
+        ed, es = Evaluator(dense.copy()), Evaluator(full.copy())
+        ed.set_kfolds(folds)
+        es.set_kfolds(folds)
+        if folds == 1:
+            td, sd = ed.naive_split()
+            ts, ss = es.naive_split()
+            assert sp.issparse(ts) and sp.issparse(ss)
+            assert (ts != sp.csr_matrix(td)).nnz == 0 and (ss != sp.csr_matrix(sd)).nnz == 0
+            cd, cs = ed.candidate_lists(0), es.candidate_lists(0)
+            assert numpy.array_equal(cd[0], cs[0]) and numpy.array_equal(cd[1], cs[1])
+            continue
+        ld, ls = ed.get_kfold_indices(), es.get_kfold_indices()
+        assert all(numpy.array_equal(a, b) for a, b in zip(ld, ls))
+        for f in range(folds):
+            td, sd = ed.get_fold(f, ld)
+            ts, ss = es.get_fold(f, ls)
+            assert (ts != sp.csr_matrix(td)).nnz == 0 and (ss != sp.csr_matrix(sd)).nnz == 0
+            view = es.csr_view(ts)
+            assert view is not None and numpy.array_equal(view[1], sp.csr_matrix(td).indices)
+            cd, cs = ed.candidate_lists(f), es.candidate_lists(f)
+            assert numpy.array_equal(cd[0], cs[0]) and numpy.array_equal(cd[1], cs[1])
+
+
+def test_class_runs_on_sparse_ratings_and_refuses_huge_dense_predictions(monkeypatch):
+    """The reference-facing class on scipy sparse ratings (oracle-backed stand-in for the device): the same
+    11-tuple as on the dense array; get_predictions() raises MemoryError above the dense limit."""
+    import scipy.sparse as sp
+    from grid_helpers import OracleBacked, make_recommender
+    from hyprec_b200 import collaborative_filtering as cfmod, synth
+    full = synth.ratings_csr("toy", n_users=40, n_items=90, positives=700, min_degree=2, seed=5)
+    dense = numpy.asarray(full.todense())
+    a = make_recommender(OracleBacked, dense.copy())
+    b = make_recommender(OracleBacked, sp.csr_matrix(full))
+    ra = numpy.asarray(a.train(), dtype=numpy.float64)
+    rb = numpy.asarray(b.train(), dtype=numpy.float64)
+    assert sp.issparse(b.train_data) and sp.issparse(b.test_data)
+    same = (numpy.isnan(ra) & numpy.isnan(rb)) | (numpy.abs(ra - rb) <= 1e-12 * numpy.maximum(1, numpy.abs(ra)))
+    assert numpy.all(same), (ra, rb)
+    from hyprec_b200 import CollaborativeFiltering
+    monkeypatch.setattr(cfmod, "DENSE_PREDICTIONS_LIMIT_BYTES", 1000)
+    b.predictions = None
+    with pytest.raises(MemoryError):
+        CollaborativeFiltering.get_predictions(b)

@@ -4,7 +4,9 @@ classes of this package: Evaluator(ratings) -> CollaborativeFiltering(...).train
 initialisation, n_iterations ALS epochs and the evaluation report, then the mean 11-tuple.  Wall clock of the whole call
 and of its host / device parts, one JSON line.
 
-    python tools/class_run.py [--workload citeulike-a] [--iterations 5] [--folds 5] [--factors 200]
+    python tools/class_run.py [--workload citeulike-a] [--iterations 5] [--folds 5] [--factors 200] [--sparse]
+    python tools/class_run.py --scale 0.25 --folds 1 --factors 256      # the scaled shape through the class: sparse
+        ratings, naive split, device-generated candidate lists (no dense users x items array can exist there)
 """
 import argparse
 import json
@@ -25,12 +27,25 @@ def main():
     ap.add_argument("--folds", type=int, default=5)
     ap.add_argument("--factors", type=int, default=200)
     ap.add_argument("--lambda", dest="lam", type=float, default=0.01)
+    ap.add_argument("--sparse", action="store_true", help="hand the ratings over as a scipy CSR matrix")
+    ap.add_argument("--scale", type=float, default=0.0, help="> 0: the scaled synthetic shape (sparse, hashed candidates)")
     args = ap.parse_args()
     from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer, _native, synth
-    ratings = numpy.asarray(synth.ratings_csr(args.workload).todense(), dtype=numpy.float64)
+    import scipy.sparse as sp
+    if args.scale > 0:
+        data = synth.scaled_ratings(args.scale)
+        indptr, indices = data["full"]
+        ratings = sp.csr_matrix((numpy.ones(len(indices)), indices, indptr), shape=(data["m"], data["n"]))
+        args.workload = "scaled-%g" % args.scale
+    else:
+        ratings = synth.ratings_csr(args.workload)
+        if not args.sparse:
+            ratings = numpy.asarray(ratings.todense(), dtype=numpy.float64)
     hyper = {'n_factors': args.factors, '_lambda': args.lam}
     options = {'k_folds': args.folds, 'n_iterations': args.iterations}
     evaluator = Evaluator(ratings)
+    if args.scale > 0:
+        evaluator.use_hashed_candidates(5, 20170303)
     cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), args.iterations), evaluator, hyper, options,
                                 load_matrices=False, dump_matrices=False)
     cf.device()                                   # context creation is not part of the run
@@ -48,6 +63,7 @@ def main():
         setattr(obj, name, wrapper)
 
     timed(evaluator, "get_kfold_indices", "split_indices_s")
+    timed(evaluator, "naive_split", "naive_split_s")
     timed(evaluator, "get_fold", "fold_matrices_s")
     timed(cf, "partial_train", "partial_train_s")
     timed(cf, "get_evaluation_report", "evaluation_report_s")
@@ -60,7 +76,8 @@ def main():
                       count=_native.T_COUNT, topk=_native.T_TOPK, flags=_native.T_FLAGS).items()}
     launches = h.launch_count
     cf.close()
-    print(json.dumps(dict(workload=args.workload, users=int(ratings.shape[0]), items=int(ratings.shape[1]),
+    print(json.dumps(dict(workload=args.workload, sparse_ratings=bool(sp.issparse(ratings)),
+                          precision=os.environ.get("HYPREC_PRECISION", "fp64"), users=int(ratings.shape[0]), items=int(ratings.shape[1]),
                           folds=args.folds, iterations=args.iterations, n_factors=args.factors, train_seconds=total,
                           phases_s=phases, device_kernel_ms_total=sum(device_ms.values()), device_kernel_ms=device_ms,
                           gpu_launches=int(launches), report=[float(x) for x in report])))

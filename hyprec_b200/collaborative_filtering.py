@@ -500,12 +500,32 @@ class CollaborativeFiltering(AbstractRecommender):
         else:
             cand_indptr, cand_ids = self.candidate_lists(fold)
             cp, ci = cand_indptr[lo:hi + 1] - cand_indptr[lo], cand_ids[cand_indptr[lo]:cand_indptr[hi]]
-        part = h.eval_topk(self.n_recommendations, cp, ci, lo, hi,
-                           n_train_nz=int(train_ptr[hi] - train_ptr[lo]), n_test_nz=int(test_ptr[hi] - test_ptr[lo]))
+        if hashed is not None:
+            part = self._eval_blocks(h, lo, hi, hashed[0], train_ptr, test_ptr)
+        else:
+            part = h.eval_topk(self.n_recommendations, cp, ci, lo, hi,
+                               n_train_nz=int(train_ptr[hi] - train_ptr[lo]), n_test_nz=int(test_ptr[hi] - test_ptr[lo]))
         self._cands_uploaded = None
         gathered = [None] * world
         dist.all_gather_object(gathered, part)
         return {key: numpy.concatenate([g[key] for g in gathered]) for key in part}
+
+    def _eval_blocks(self, h, lo, hi, n_folds, train_ptr=None, test_ptr=None):
+        """Device-generated candidate lists hold ~n_items / n_folds ids per user: users [lo, hi) are evaluated in
+        blocks whose lists stay below ~2 GB on the device, and the per-user outputs are concatenated."""
+        train_ptr = self._train_pattern[0] if train_ptr is None else train_ptr
+        test_ptr = self._test_pattern[0] if test_ptr is None else test_ptr
+        per_user = max(1, 4 * self.n_items // max(n_folds, 1))
+        block = int(max(128, min(hi - lo, (2 << 30) // per_user)))
+        parts = []
+        for b_lo in range(lo, hi, block):
+            b_hi = min(hi, b_lo + block)
+            parts.append(h.eval_topk(self.n_recommendations, None, None, b_lo, b_hi,
+                                     n_train_nz=int(train_ptr[b_hi] - train_ptr[b_lo]),
+                                     n_test_nz=int(test_ptr[b_hi] - test_ptr[b_lo])))
+        if len(parts) == 1:
+            return parts[0]
+        return {key: numpy.concatenate([p[key] for p in parts]) for key in parts[0]}
 
     def recall_at_cutoffs(self, cutoffs=(50, 100, 150, 200, 250, 300)):
         """recall@x for every x of ``cutoffs`` from ONE device pass (BASELINE.json configs[1]: recall@{50..300}).
@@ -527,10 +547,12 @@ class CollaborativeFiltering(AbstractRecommender):
     def _report_factors(self):
         """Hybrid recommender (``is_hybrid``): the blended scores of collaborative_filtering.py:271-279 as one
         low-rank product ``W_u W_v^T`` (hyprec_b200/hybrid.py), so that the report runs on the device like the
-        plain collaborative one instead of on three dense m x n matrices.  Opt-in (``HYPREC_HYBRID_LOWRANK=1``)
-        and only when the content model exposes the topic matrix its predictions are built from; None otherwise
-        (the dense host path of the reference is used)."""
-        if os.environ.get("HYPREC_HYBRID_LOWRANK", "0") != "1":
+        plain collaborative one instead of on three dense m x n matrices.  The default whenever the content model
+        exposes the topic matrix its predictions are built from (``document_distribution``, content_based.py:88-117;
+        checked against the dense host flow at the citeulike-a shape with k' + k = 400,
+        tests/test_gpu_bench_parity.py); ``HYPREC_HYBRID_LOWRANK=0`` or a content model without that matrix fall
+        back to the reference's dense host flow (None)."""
+        if os.environ.get("HYPREC_HYBRID_LOWRANK", "1") == "0":
             return None
         content = getattr(self, 'item_based_recommender', None)
         theta = getattr(content, 'document_distribution', None)
@@ -570,8 +592,11 @@ class CollaborativeFiltering(AbstractRecommender):
                 h.set_hashed_candidates(0, 0)
                 h.set_candidates(*self.candidate_lists(fold))        # once per fold
                 self._cands_uploaded = key
-            out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users,
-                              n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
+            if hashed is not None:
+                out = self._eval_blocks(h, 0, self.n_users, hashed[0])
+            else:
+                out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users,
+                                  n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
         else:
             out = self._eval_sharded(h, rank, world, fold)
         rmse = h.rmse()

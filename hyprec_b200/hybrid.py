@@ -1,6 +1,6 @@
 """
-Low-rank form of the hybrid recommender's scores (off by default, see
-``CollaborativeFiltering._report_factors``).
+Low-rank form of the hybrid recommender's scores (the default report path of a hybrid
+recommender whose content model exposes its topic matrix, see ``CollaborativeFiltering._report_factors``).
 
 The reference blends two dense m x n matrices: the content model's
 ``predictions = (R_train V^)(V^)^T / w`` (/root/reference/lib/content_based.py:104-117: V^ = the

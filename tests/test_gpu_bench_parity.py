@@ -263,3 +263,61 @@ def test_fused_topk_equals_exact_scoring(native, monkeypatch, precision):
                 if g_id != w_id:
                     assert abs(float(u[uid].dot(v[g_id])) - w_val) <= 1e-12 * max(abs(w_val), 1e-300) + 1e-18
         assert numpy.all(out["topk_idx"][uid][len(want):] == -1)
+
+
+def test_hybrid_report_at_citeulike_a_shape(monkeypatch):
+    """The hybrid recommender (the reference's default, config/recommender.json:7) at the citeulike-a shape with
+    k' + k = 400: the device report from the blended low-rank factors (the default) against the reference's dense
+    host flow (three users x items matrices, lib/collaborative_filtering.py:271-279, lib/linear_regression.py:56-69,
+    lib/content_based.py:88-117) -- the 11-tuple to 1e-8 and the top-200 lists (score ties apart)."""
+    from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer, hybrid, synth
+    wl = workload("citeulike-a")
+    m, n, k = wl["m"], wl["n"], wl["k"]
+    topics = synth.dirichlet_theta(n, 200, seed=23)
+    rs = numpy.random.RandomState(9)
+    user_vecs, item_vecs = rs.rand(m, k) * 0.3, rs.rand(n, k) * 0.3
+
+    class Content(object):
+        def __init__(self):
+            self.document_distribution = topics
+            self.train_data = None
+
+        def set_data(self, train, test):
+            self.train_data = train
+
+        def get_predictions(self):
+            p, a = hybrid.content_factors(self.train_data, self.document_distribution)
+            return p.dot(a.T)
+
+    hyper = {'n_factors': k, '_lambda': 0.01}
+    options = {'k_folds': 5, 'n_iterations': 1}
+    reports, lists, scores = {}, {}, {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HYPREC_HYBRID_LOWRANK", mode)
+        state = numpy.random.get_state()
+        ev = Evaluator(wl["ratings"])
+        cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), 1), ev, hyper, options, load_matrices=False,
+                                    dump_matrices=False, is_hybrid=True)
+        cf.set_item_based_recommender(Content())
+        cf.set_data(*ev.get_fold(0, ev.get_kfold_indices()))
+        numpy.random.set_state(state)
+        cf.hyperparameters['fold'] = 0
+        cf.user_vecs, cf.item_vecs = user_vecs.copy(), item_vecs.copy()
+        try:
+            reports[mode] = numpy.array([float(x) for x in cf.get_evaluation_report()])
+            lists[mode] = [list(r) for r in ev.recommendation_indices]
+            if mode == "0":
+                scores = cf.get_predictions()
+        finally:
+            cf.close()
+    assert numpy.allclose(reports["1"], reports["0"], rtol=1e-8, equal_nan=True), (reports["1"], reports["0"])
+    differing = 0
+    for uid in range(m):
+        if lists["1"][uid] != lists["0"][uid]:
+            differing += 1
+            assert len(lists["1"][uid]) == len(lists["0"][uid])
+            for a_id, b_id in zip(lists["1"][uid], lists["0"][uid]):        # only (near-)tied scores may swap
+                if a_id != b_id:
+                    sa, sb = scores[uid, a_id], scores[uid, b_id]
+                    assert abs(sa - sb) <= 1e-9 * max(abs(sa), abs(sb), 1e-300), (uid, a_id, b_id, sa, sb)
+    assert differing <= m // 50, differing

@@ -142,7 +142,7 @@ def test_lowrank_blend_matches_reference_classes_when_available():
     assert numpy.allclose(w_u.dot(w_v.T), want, rtol=1e-8, atol=1e-10)
 
 
-def test_class_hands_blended_factors_to_the_report_only_when_asked(monkeypatch):
+def test_class_hands_blended_factors_to_the_report_by_default(monkeypatch):
     from hyprec_b200 import CollaborativeFiltering, Evaluator, ModelInitializer
     train, theta, u, v = _lowrank_case(6)
     hyper = {'n_factors': u.shape[1], '_lambda': 0.01}
@@ -155,10 +155,10 @@ def test_class_hands_blended_factors_to_the_report_only_when_asked(monkeypatch):
     cf.set_item_based_recommender(Content())
     cf.set_data(train, numpy.zeros(train.shape))
     cf.user_vecs, cf.item_vecs = u, v
+    monkeypatch.setenv("HYPREC_HYBRID_LOWRANK", "0")
+    assert cf._report_factors() is None                       # switched off: the reference's dense host path
     monkeypatch.delenv("HYPREC_HYBRID_LOWRANK", raising=False)
-    assert cf._report_factors() is None                       # default: the reference's dense host path
-    monkeypatch.setenv("HYPREC_HYBRID_LOWRANK", "1")
-    w_u, w_v = cf._report_factors()
+    w_u, w_v = cf._report_factors()                           # default: blended low-rank factors for the device report
     want = LinearRegression(train, train, _dense_content(train, theta), u.dot(v.T)).train()
     assert numpy.allclose(w_u.dot(w_v.T), want, rtol=1e-8, atol=1e-10)
     assert w_u.flags.c_contiguous and w_v.flags.c_contiguous and w_u.dtype == numpy.float64

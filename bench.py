@@ -89,6 +89,7 @@ def build_workload(name):
     user_vecs = numpy.random.random((m, k))                  # drawn right after the split (App. A Q4)
     theta = synth.dirichlet_theta(n, k, seed=7)
     wl = dict(name=name, m=m, n=n, k=k, lam=lam, folds=folds, ratings=ratings, train=train, test=test,
+              evaluator=evaluator, fold_lists=lists,
               train_csr=sp.csr_matrix(train), test_csr=sp.csr_matrix(test), full_csr=ratings_csr,
               cand_indptr=cand_indptr, cand_ids=cand_ids, u0=user_vecs, v0=theta.copy(), device_init=None)
     for key in ("train_csr", "test_csr", "full_csr"):
@@ -414,6 +415,54 @@ class SingleALS(object):
         return self.h.rmse()
 
 
+def class_fold_e2e(wl, args, n_iter=5, reps=3):
+    """One fold of hyprec_b200.CollaborativeFiltering.train() (the call runnables.py makes), wall clock."""
+    from hyprec_b200 import CollaborativeFiltering, ModelInitializer
+    prev = os.environ.get("HYPREC_PRECISION")
+    os.environ["HYPREC_PRECISION"] = args.precision
+    try:
+        hyper = {'n_factors': wl["k"], '_lambda': wl["lam"]}
+        options = {'k_folds': wl["folds"], 'n_iterations': n_iter}
+        ev = wl["evaluator"]
+        cf = CollaborativeFiltering(ModelInitializer(hyper.copy(), n_iter), ev, hyper, options, load_matrices=False,
+                                    dump_matrices=False)
+        cf.fold_test_indices = wl["fold_lists"]
+        times, parts, report = [], {}, None
+
+        def timed(name, fn, *a):
+            t0 = time.perf_counter()
+            out = fn(*a)
+            parts[name] = parts.get(name, 0.0) + time.perf_counter() - t0
+            return out
+
+        for rep in range(1 + reps):
+            parts = {}
+            cf._train_uploaded = cf._eval_uploaded = cf._cands_uploaded = None      # a new fold: everything is uploaded again
+            theta = wl["v0"].copy()
+            t0 = time.perf_counter()
+            cf.set_data(wl["train"], wl["test"])
+            cf.hyperparameters['fold'] = 0
+            matrices_found = timed("init_factors_s", cf._init_fold, theta) if hasattr(cf, "_init_fold") else None
+            if matrices_found is None:
+                report = timed("train_one_fold_s", cf.train_one_fold, theta)
+            else:
+                timed("partial_train_s", cf.partial_train)
+                report = timed("evaluation_report_s", cf.get_evaluation_report)
+            if rep > 0:
+                times.append(time.perf_counter() - t0)
+        cf.close()
+        return dict(value=1e3 * float(numpy.mean(times)), unit="ms", epochs=n_iter, reps=reps,
+                    per_epoch_equivalent_ms=1e3 * float(numpy.mean(times)) / n_iter, last_rep_parts_s=parts,
+                    report=[float(x) for x in report],
+                    note="set_data + initial factors + %d epochs + evaluation report through the class, host arrays in, "
+                         "11-tuple out; train / eval CSR and candidate lists uploaded inside the timed region" % n_iter)
+    finally:
+        if prev is None:
+            os.environ.pop("HYPREC_PRECISION", None)
+        else:
+            os.environ["HYPREC_PRECISION"] = prev
+
+
 def solve_roofline(wl, precision, world, solve_ms, lowrank, fma_peak):
     """Roofline view of the row-solve kernels of one epoch on one rank: its 1/world share of the epoch's FLOPs
     (executed low-rank model, or SURVEY 8d's direct formula with HYPREC_LOWRANK=0) over their device time."""
@@ -624,6 +673,17 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
         except Exception as exc:
             recall_at = dict(error=repr(exc))
 
+    # ---- the same through the reference-facing class: ONE fold of CollaborativeFiltering.train() =
+    # set_data -> train_one_fold (random user factors, theta item factors, n_iter epochs inside hyprec_train, factors
+    # back into the host arrays) -> get_evaluation_report (device evaluation + the reference's metric arithmetic):
+    # host matrices in, the 11-tuple out, every upload of the fold inside the timed region
+    class_e2e = None
+    if has_lists and world == 1 and wl.get("evaluator") is not None and not getattr(args, "no_class", False):
+        try:
+            class_e2e = class_fold_e2e(wl, args)
+        except Exception as exc:
+            class_e2e = dict(error=repr(exc))
+
     lowrank = os.environ.get("HYPREC_LOWRANK", "1") != "0"
     fma_peak = h.probe_fma_tflops(precision)
     line = None
@@ -659,6 +719,8 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
                                    "streams at the same time, so 'prep' (whitening) and the tail of 'solve' include waiting for SMs "
                                    "those launches occupy -- the launch lists under profiles/ have the per-kernel times",
                     rmse=rmse, recall_at_200=recall200, setup_s=wl["setup_s"], upload_s=upload_s)
+        if class_e2e is not None:
+            line["e2e"]["class_fold"] = class_e2e
         if recall_at is not None:
             line["recall_at"] = recall_at
         if eval_stats is not None:
@@ -717,6 +779,7 @@ def our_arm(args, wl):
             try:
                 sub = argparse.Namespace(**vars(args))
                 sub.precision, sub.gpus, sub.steps, sub.warmup = "fp64", 1, max(3, min(args.steps, 10)), max(3, min(args.warmup, 5))
+                sub.cpu_rows = 16
                 record = run_workload(sub, build_workload("citeulike-a"), 0, 1, local, with_cpu=(world == 1))
             except Exception as exc:       # the headline must not be lost over its companion record
                 record = dict(error=repr(exc))

@@ -510,6 +510,50 @@ class CollaborativeFiltering(AbstractRecommender):
         dist.all_gather_object(gathered, part)
         return {key: numpy.concatenate([g[key] for g in gathered]) for key in part}
 
+    def _naive_lists(self, h, blended):
+        """Evaluation under the NAIVE split: ``evaluator.test_indices`` is the test MATRIX, whose rows the reference
+        walks as candidate streams of item ids 0 / 1 (evaluator.py:97, :225-228).  The lists
+        then follow from two scores per user in closed form (top_recommendations.naive_split_recommendations); the
+        device supplies thresholds, rounded counts and the flags at the positives, and no n_items-long stream is
+        built or uploaded.  Returns the eval_topk-shaped dict, or None when a test value is not 0 / 1."""
+        from hyprec_b200.top_recommendations import naive_split_recommendations
+        test_ptr, test_idx, test_val = self._host_csr(self.test_data)
+        w_u, w_v = blended if blended is not None else (self.user_vecs, self.item_vecs)
+        if self.n_items < 2:
+            return None
+        pair = numpy.asarray(w_u, dtype=numpy.float64).dot(numpy.asarray(w_v[:2], dtype=numpy.float64).T)
+        got = naive_split_recommendations(pair[:, 0], pair[:, 1], test_ptr, test_idx, test_val, self.n_items,
+                                          self.n_recommendations)
+        if got is None:
+            return None
+        ids, lengths = got
+        rank, world = self._world()
+        if world == 1:
+            out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users, want_topk=False,
+                              n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
+        else:
+            import torch.distributed as dist
+            users, _ = self._shard_bounds(world)
+            lo, hi = users[rank], users[rank + 1]
+            train_ptr = self._host_csr(self.train_data)[0]
+            part = h.eval_topk(self.n_recommendations, None, None, lo, hi, want_topk=False,
+                               n_train_nz=int(train_ptr[hi] - train_ptr[lo]), n_test_nz=int(test_ptr[hi] - test_ptr[lo]))
+            gathered = [None] * world
+            dist.all_gather_object(gathered, {k: v for k, v in part.items() if v is not None})
+            out = {key: numpy.concatenate([g[key] for g in gathered]) for key in gathered[0]}
+        full_ptr, full_idx, full_val = self._host_csr(self.ratings)
+        rated = numpy.zeros((self.n_users, 2))                     # ratings[u][0], ratings[u][1]
+        rows = numpy.repeat(numpy.arange(self.n_users), numpy.diff(full_ptr))
+        low = full_idx < 2
+        rated[rows[low], full_idx[low]] = full_val[low]
+        rounded = (pair >= numpy.asarray(out["thresholds"])[:, None]).astype(numpy.float64)
+        safe = numpy.maximum(ids, 0)
+        users = numpy.arange(self.n_users)[:, None]
+        out["topk_idx"] = ids
+        out["topk_val"] = numpy.where(ids >= 0, pair[users, safe], 0.0)
+        out["topk_hit"] = numpy.where(ids >= 0, rated[users, safe] * rounded[users, safe], 0.0)
+        return out
+
     def _eval_blocks(self, h, lo, hi, n_folds, train_ptr=None, test_ptr=None):
         """Device-generated candidate lists hold ~n_items / n_folds ids per user: users [lo, hi) are evaluated in
         blocks whose lists stay below ~2 GB on the device, and the per-user outputs are concatenated."""
@@ -580,9 +624,15 @@ class CollaborativeFiltering(AbstractRecommender):
             h.set_factors(*blended)
             self._sync_token = None         # the device no longer holds user_vecs / item_vecs
         rank, world = self._world()
-        if world == 1:
+        hashed = getattr(self.evaluator, 'hashed_candidates', None)
+        naive = None
+        if hashed is None and fold == 0 and not isinstance(self.evaluator.test_indices, list) and \
+                getattr(self.evaluator.test_indices, 'ndim', 0) == 2:
+            naive = self._naive_lists(h, blended)
+        if naive is not None:
+            out = naive
+        elif world == 1:
             key = (self.evaluator.test_indices, fold)
-            hashed = getattr(self.evaluator, 'hashed_candidates', None)
             if hashed is not None:
                 # device-generated lists (Evaluator.use_hashed_candidates): nothing to enumerate on the host
                 h.set_candidates(None, None)

@@ -86,3 +86,44 @@ def top_k_stream_order(ids, scores, capacity):
     order = numpy.lexsort((-kept, -scores[kept]))
     sel = kept[order]
     return [int(i) for i in ids[sel]], [float(v) for v in scores[sel]]
+
+
+def naive_split_recommendations(score0, score1, test_indptr, test_indices, test_values, n_items, capacity):
+    """The lists ``load_top_recommendations`` produces under the NAIVE split, in closed form.
+
+    There ``evaluator.test_indices`` is the dense test matrix (evaluator.py:97), so the "candidates" of user u are the
+    n_items VALUES of its test row cast to int (evaluator.py:225-228): item 1 wherever the row holds a 1, item 0
+    elsewhere.  Only two scores enter -- s0 = score(u, item 0), s1 = score(u, item 1) -- and the
+    streamed top-``capacity`` (util/top_recommendations.py:23-40) is determined by their order and by how many of
+    each there are:
+      s1 > s0 : every 1 (at most capacity), then 0s;     s1 < s0 : every 0 (at most capacity), then 1s;
+      s1 == s0: the first ``capacity`` stream elements, reversed (later-inserted first among equals).
+    Returns (ids int32 [n_users][capacity] padded with -1, lengths) or None when a test value does not cast to 0 or 1
+    (then the general path must stream the row)."""
+    score0 = numpy.asarray(score0, dtype=numpy.float64)
+    score1 = numpy.asarray(score1, dtype=numpy.float64)
+    n_users = len(score0)
+    casted = numpy.asarray(test_values).astype(numpy.int64)      # int(value), evaluator.py:226
+    if numpy.any((casted != 0) & (casted != 1)):
+        return None
+    total = min(int(capacity), int(n_items))
+    ids = numpy.full((n_users, capacity), -1, dtype=numpy.int32)
+    for user in range(n_users):
+        lo, hi = test_indptr[user], test_indptr[user + 1]
+        ones_at = numpy.asarray(test_indices[lo:hi])[casted[lo:hi] == 1]
+        n1 = len(ones_at)
+        n0 = n_items - n1
+        s0, s1 = score0[user], score1[user]
+        if s1 > s0:
+            head = min(total, n1)
+            ids[user, :head] = 1
+            ids[user, head:total] = 0
+        elif s1 < s0:
+            head = min(total, n0)
+            ids[user, :head] = 0
+            ids[user, head:total] = 1
+        else:
+            first = numpy.zeros(total, dtype=numpy.int32)
+            first[ones_at[ones_at < total]] = 1
+            ids[user, :total] = first[::-1]
+    return ids, numpy.full(n_users, total, dtype=numpy.int64)

@@ -214,3 +214,30 @@ def test_class_runs_on_sparse_ratings_and_refuses_huge_dense_predictions(monkeyp
     b.predictions = None
     with pytest.raises(MemoryError):
         CollaborativeFiltering.get_predictions(b)
+
+
+def test_naive_split_lists_in_closed_form():
+    """naive_split_recommendations == streaming the dense test row through TopRecommendations (App. A Q7), for
+    every order of the two scores, more / fewer ones than the capacity, ties, and rows shorter than the capacity."""
+    import scipy.sparse as sp
+    from hyprec_b200.top_recommendations import naive_split_recommendations, top_k_stream_order
+    rs = numpy.random.RandomState(0)
+    for n_items, capacity in ((60, 20), (15, 20), (40, 7)):
+        m = 30
+        test = (rs.rand(m, n_items) < rs.rand(m, 1) * 0.8).astype(numpy.float64)
+        test[3] = 0
+        test[4] = 1
+        scores = rs.randn(m, n_items)
+        scores[5:12, 1] = scores[5:12, 0]            # tied
+        scores[12] = 0.0
+        csr = sp.csr_matrix(test)
+        got = naive_split_recommendations(scores[:, 0], scores[:, 1], csr.indptr, csr.indices, csr.data, n_items, capacity)
+        assert got is not None
+        ids, lengths = got
+        for u in range(m):
+            stream = test[u].astype(numpy.int64)
+            want, _ = top_k_stream_order(stream, scores[u][stream], capacity)
+            assert list(ids[u][:lengths[u]]) == want, (n_items, capacity, u)
+            assert numpy.all(ids[u][lengths[u]:] == -1)
+    csr = sp.csr_matrix(numpy.array([[0, 2.0, 0], [1.0, 0, 0]]))
+    assert naive_split_recommendations([0, 0], [1, 1], csr.indptr, csr.indices, csr.data, 3, 2) is None

@@ -67,6 +67,15 @@ def main():
     timed(evaluator, "get_fold", "fold_matrices_s")
     timed(cf, "partial_train", "partial_train_s")
     timed(cf, "get_evaluation_report", "evaluation_report_s")
+    timed(cf, "_init_fold", "init_factors_s")
+    # inside partial_train / get_evaluation_report
+    timed(cf, "_upload_train", "  upload_train_s")
+    timed(cf, "_upload_eval", "  upload_eval_incl_train_s")
+    timed(cf, "_download_factors", "  download_factors_s")
+    timed(cf, "candidate_lists", "  candidate_lists_s")
+    handle = cf.device()
+    for name in ("set_factors", "train", "set_candidates", "eval_topk", "rmse"):
+        timed(handle, name, "  handle.%s_s" % name)
     t0 = time.perf_counter()
     report = cf.train()
     total = time.perf_counter() - t0

@@ -133,6 +133,9 @@ class CollaborativeFiltering(AbstractRecommender):
         on its own GPU even inside a process group."""
         if getattr(self, '_single_rank', False):
             return 0, 1
+        import sys
+        if 'torch.distributed' not in sys.modules:      # nobody can have initialised a group (importing torch costs ~2 s)
+            return 0, 1
         try:
             import torch.distributed as dist
         except ImportError:
@@ -154,9 +157,38 @@ class CollaborativeFiltering(AbstractRecommender):
     def _host_csr(self, matrix):
         """CSR triplet of a dense / sparse users x items matrix: the evaluator's own view when it built the
         matrix (hyprec_b200.Evaluator.csr_view, validated against the array), else a scan."""
+        return self._facts(matrix)[0]
+
+    def _facts(self, matrix):
+        """(CSR triplet, sum of all entries, row sums) of one of the API's users x items matrices, computed once per
+        matrix OBJECT: ratings / train / test are scanned by every report of the reference (test_data.sum(),
+        sum(sum(ratings)), ...), which costs more than the device work at the citeulike shape and is repeated for
+        every model of a sweep.  A cached entry is re-used only for the same object, and only while a sample of
+        its cells still reads as recorded (an in-place edit by the caller drops it)."""
+        cache = self.__dict__.setdefault('_matrix_facts', [])
+        for entry in cache:
+            if entry[0] is matrix:
+                triplet = entry[1]
+                if sp.issparse(matrix):
+                    if matrix.nnz == len(triplet[1]):
+                        return entry[1:]
+                elif len(triplet[1]) == 0 or numpy.array_equal(matrix[entry[4], triplet[1][entry[5]]], triplet[2][entry[5]]):
+                    return entry[1:4]
+                cache.remove(entry)
+                break
         view = getattr(self.evaluator, 'csr_view', None)
-        triplet = view(matrix) if view is not None and isinstance(matrix, numpy.ndarray) else None
-        return triplet if triplet is not None else _csr_triplet(matrix)
+        triplet = view(matrix) if view is not None and (isinstance(matrix, numpy.ndarray) or sp.issparse(matrix)) else None
+        if triplet is None:
+            triplet = _csr_triplet(matrix)
+        indptr, indices, values = triplet
+        rows = numpy.repeat(numpy.arange(len(indptr) - 1, dtype=numpy.int64), numpy.diff(indptr))
+        row_sums = numpy.bincount(rows, weights=values, minlength=len(indptr) - 1) if len(values) else numpy.zeros(len(indptr) - 1)
+        pick = numpy.linspace(0, max(len(indices) - 1, 0), num=min(len(indices), 4096)).astype(numpy.int64)
+        entry = (matrix, triplet, numpy.float64(values.sum()), row_sums, rows[pick], pick)
+        cache.append(entry)
+        if len(cache) > 8:
+            cache.pop(0)
+        return entry[1:4]
 
     def _upload_train(self):
         h = self.device()
@@ -585,7 +617,7 @@ class CollaborativeFiltering(AbstractRecommender):
         finally:
             self.n_recommendations, self._verbose = saved, verbose
         hits = self.last_report_details["topk_hit"]
-        test_likes = numpy.asarray(self.test_data.sum(axis=1)).ravel()
+        test_likes = self._facts(self.test_data)[2]
         return {x: metrics.recall_at_x(x, hits, test_likes) for x in cutoffs}
 
     def _report_factors(self):
@@ -659,14 +691,15 @@ class CollaborativeFiltering(AbstractRecommender):
         if hasattr(self.evaluator, "set_device_results"):
             self.evaluator.set_device_results(recs, [hits[u][:lengths[u]] for u in range(self.n_users)])
 
-        test_sum = self.test_data.sum()
-        train_sum = self.train_data.sum()
+        # (sums over the recorded non-zeros: what test_data.sum() / train_data.sum() / sum(sum(ratings)) of the
+        # reference add up, abstract_recommender.py:104-115, without three passes over dense m x n arrays)
+        _, test_sum, test_likes = self._facts(self.test_data)
+        _, train_sum, _ = self._facts(self.train_data)
         with numpy.errstate(divide='ignore', invalid='ignore'):
             # sum(rounded[ratings.nonzero()]) / sum(sum(ratings))  (evaluator.py:263-266)
             train_recall = numpy.float64(out["train_flags"].sum(dtype=numpy.int64)) / numpy.float64(train_sum)
             test_recall = numpy.float64(out["test_flags"].sum(dtype=numpy.int64)) / numpy.float64(test_sum)
-            ratio = numpy.float64(out["ones_per_row"].sum()) / _total(self.ratings)
-        test_likes = numpy.asarray(self.test_data.sum(axis=1)).ravel()
+            ratio = numpy.float64(out["ones_per_row"].sum()) / self._facts(self.ratings)[1]
         recall_at_x = metrics.recall_at_x(self.recall_cutoff, hits, test_likes)
         mrr_at_five = metrics.mrr_at(5, hits, lengths)
         ndcg_at_five = metrics.ndcg_at(5, hits, lengths)

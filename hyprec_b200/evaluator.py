@@ -272,12 +272,36 @@ class Evaluator(object):
             if fold != 0:
                 ids = ids.reshape(self.n_users, self.n_items)[slots].ravel()
             return numpy.arange(self.n_users + 1, dtype=numpy.int64) * self.n_items, ids
+        packed = self._packed_lists()
+        if packed is not None:
+            # equally long k-fold lists, kept as one int32 matrix: the fold's streams are a row gather
+            slots = numpy.arange(self.n_users, dtype=numpy.int64) * (1 + fold)
+            ids = packed[slots].ravel()
+            return numpy.arange(self.n_users + 1, dtype=numpy.int64) * packed.shape[1], ids
         rows = [numpy.asarray(self.test_indices[user * (1 + fold)]).astype(numpy.int64)
                 for user in range(self.n_users)]
         indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
         numpy.cumsum([len(r) for r in rows], out=indptr[1:])
         ids = numpy.concatenate(rows).astype(numpy.int32) if rows else numpy.zeros(0, numpy.int32)
         return indptr, ids
+
+    def _packed_lists(self):
+        """test_indices as one (slots x length) int32 matrix when it is get_kfold_indices' list of equally long
+        arrays (n_items / k_folds ids each, evaluator.py:184), else None.  Built once per list object."""
+        lists = self.test_indices
+        if not isinstance(lists, list) or not lists:
+            return None
+        cached = getattr(self, '_packed', None)
+        if cached is not None and cached[0] is lists:
+            return cached[1]
+        length = len(lists[0])
+        packed = None
+        if all(len(x) == length for x in lists):
+            packed = numpy.empty((len(lists), length), dtype=numpy.int32)
+            for i, x in enumerate(lists):
+                packed[i] = x
+        self._packed = (lists, packed)
+        return packed
 
     def load_top_recommendations(self, n_recommendations, predictions, test_data, fold):
         cand_indptr, cand_ids = self.candidate_lists(fold)

@@ -174,6 +174,7 @@ class GridSearch(object):
         if hasattr(rec.evaluator, '_device_hits'):
             rec.evaluator._device_hits = None
         rec.hyperparameters = dict(self.recommender.hyperparameters)
+        rec._matrix_facts = list(getattr(self.recommender, '_matrix_facts', []))    # entries shared, list private
         rec._handle = None
         rec._train_uploaded = rec._eval_uploaded = rec._cands_uploaded = rec._sync_token = None
         rec._train_pattern = rec._test_pattern = None

@@ -241,3 +241,24 @@ def test_naive_split_lists_in_closed_form():
             assert numpy.all(ids[u][lengths[u]:] == -1)
     csr = sp.csr_matrix(numpy.array([[0, 2.0, 0], [1.0, 0, 0]]))
     assert naive_split_recommendations([0, 0], [1, 1], csr.indptr, csr.indices, csr.data, 3, 2) is None
+
+
+def test_vectorised_metrics_equal_the_per_user_loops():
+    """metrics.recall_at_x / ndcg_at / mrr_at on the device's (m, K) zero-padded hit matrix give bit for bit the
+    float16 values of the per-user loops (the reference's arithmetic, evaluator.py:281-341)."""
+    from hyprec_b200 import metrics
+    rs = numpy.random.RandomState(1)
+    for m, cap in ((700, 200), (9000, 40), (33, 7)):
+        lengths = numpy.where(rs.rand(m) < 0.1, rs.randint(0, cap, size=m), cap)
+        hits = (rs.rand(m, cap) < 0.15).astype(numpy.float64)
+        hits[numpy.arange(cap)[None, :] >= lengths[:, None]] = 0.0
+        likes = rs.randint(0, 60, size=m).astype(numpy.float64)
+        rows = [hits[u][:lengths[u]] for u in range(m)]                 # the list form runs the loops
+        for x in (5, 50, 200, 300):
+            a, b = metrics.recall_at_x(x, hits, likes), metrics.recall_at_x(x, rows, likes)
+            assert a.dtype == numpy.float16 and (a == b or (numpy.isnan(a) and numpy.isnan(b)))
+        for n in (1, 5, 10, 250):
+            a, b = metrics.ndcg_at(n, hits, lengths), metrics.ndcg_at(n, rows, lengths)
+            assert a == b or (numpy.isnan(a) and numpy.isnan(b)), (n, a, b)
+            a, b = metrics.mrr_at(n, hits, lengths), metrics.mrr_at(n, rows, lengths)
+            assert a == b, (n, a, b)

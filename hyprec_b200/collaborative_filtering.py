@@ -166,15 +166,15 @@ class CollaborativeFiltering(AbstractRecommender):
         every model of a sweep.  A cached entry is re-used only for the same object, and only while a sample of
         its cells still reads as recorded (an in-place edit by the caller drops it)."""
         cache = self.__dict__.setdefault('_matrix_facts', [])
-        for entry in cache:
+        for at, entry in enumerate(cache):
             if entry[0] is matrix:
                 triplet = entry[1]
                 if sp.issparse(matrix):
                     if matrix.nnz == len(triplet[1]):
-                        return entry[1:]
+                        return entry[1:4]
                 elif len(triplet[1]) == 0 or numpy.array_equal(matrix[entry[4], triplet[1][entry[5]]], triplet[2][entry[5]]):
                     return entry[1:4]
-                cache.remove(entry)
+                del cache[at]             # (list.remove would compare the arrays inside the tuples)
                 break
         view = getattr(self.evaluator, 'csr_view', None)
         triplet = view(matrix) if view is not None and (isinstance(matrix, numpy.ndarray) or sp.issparse(matrix)) else None

@@ -262,3 +262,25 @@ def test_vectorised_metrics_equal_the_per_user_loops():
             assert a == b or (numpy.isnan(a) and numpy.isnan(b)), (n, a, b)
             a, b = metrics.mrr_at(n, hits, lengths), metrics.mrr_at(n, rows, lengths)
             assert a == b, (n, a, b)
+
+
+def test_matrix_facts_cache_hits_and_notices_edits():
+    """CollaborativeFiltering._facts: CSR triplet / total / row sums per matrix object, for dense and sparse matrices,
+    re-used on the second call and dropped when the caller edits the dense matrix in place."""
+    import scipy.sparse as sp
+    from grid_helpers import OracleBacked, make_recommender
+    from hyprec_b200 import synth
+    full = synth.ratings_csr("toy", n_users=30, n_items=70, positives=400, min_degree=2, seed=8)
+    dense = numpy.asarray(full.todense())
+    cf = make_recommender(OracleBacked, dense.copy())
+    for matrix in (dense.copy(), sp.csr_matrix(full)):
+        first = cf._facts(matrix)
+        again = cf._facts(matrix)
+        assert len(first) == 3 and len(again) == 3 and again[0] is first[0]
+        assert first[1] == 400.0 and numpy.array_equal(first[2], numpy.asarray(full.sum(axis=1)).ravel())
+    matrix = dense.copy()
+    before = cf._facts(matrix)
+    rows, cols = numpy.nonzero(matrix)
+    matrix[rows, cols] = 0.0                      # the caller empties the matrix in place
+    after = cf._facts(matrix)
+    assert after[1] == 0.0 and after[0] is not before[0]

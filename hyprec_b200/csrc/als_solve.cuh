@@ -113,6 +113,9 @@ struct SolveArgs {
     T* export_tiles;          // direct mode: factored tiles of the processed row (single-row launch)
     int tmem_cols;            // tensor-core launches: TMEM columns to allocate (tc::syrk_tmem_cols)
     long long* prof;          // optional: per-phase clock64() totals of block 0 (tools/solve_phases.py)
+    // optional [n_rows]: sum_j r_j (fixed_j . x) of the row -- the RMSE cross term of evaluator.py:249 as a by-product
+    // of the solve (direct: b.x = |L^-1 b|^2; low-rank: (|r|^2 - |z|^2) / 0.9); only meaningful without a prior
+    double* cross_out = nullptr;
 };
 
 // float64 dot product of two k-vectors by one warp (lane-strided partial sums, xor-shuffle tree)
@@ -299,6 +302,25 @@ __device__ __forceinline__ void trailing_update_tile(T* A, int NT, const T* ybuf
     }
 #endif
 
+// Sum over the CTA of one value per thread in a FIXED order (shuffle tree per warp, warp partials added by thread 0
+// in warp order): deterministic, unlike floating-point atomics.  red: >= 33 doubles of shared memory.  Every thread
+// returns the total.
+__device__ __forceinline__ double block_sum_fixed(double v, double* red) {
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, nwarps = (blockDim.x + 31) / 32;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += red[w];
+        red[32] = s;
+    }
+    __syncthreads();
+    return red[32];
+}
+
 // TC (float32, TS == 8, low-rank launches, sm_100a only): the rank-k accumulation runs on the tensor
 // cores (tc_syrk.cuh) instead of the SIMT rank-1 loop; everything after it is shared.
 // GA: the tiles live in per-CTA global scratch (p.a_scratch) instead of shared memory -- a separate
@@ -314,6 +336,7 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
 #endif
     long long prof_t = 0;
     __shared__ long long s_row;
+    __shared__ double s_red[33];
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid % 32, warp = tid / 32, nwarps = nthreads / 32;
     const int k = p.k;
@@ -397,6 +420,13 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
                 }
                 if (lane == 0) xvec[i] = v;
             }
+        }
+        double rr = 0.0;       // |r|^2 of the row's ratings (low-rank cross term)
+        if (p.cross_out != nullptr && lowrank) {
+            __syncthreads();
+            double part = 0.0;
+            for (int i = tid; i < dim; i += nthreads) part += (double)xvec[i] * (double)xvec[i];
+            rr = block_sum_fixed(part, s_red);
         }
 
 #ifndef HYPREC_EMU
@@ -601,6 +631,14 @@ __global__ void __launch_bounds__(kSolveThreads, TS == 4 ? 2 : 1) als_solve_rows
 
         if (!lowrank && p.export_tiles != nullptr) {
             for (int e = tid; e < (TS * TS) * NT; e += nthreads) p.export_tiles[e] = A[e];
+        }
+
+        if (p.cross_out != nullptr) {
+            // z = L^-1 b is complete: the row's share of sum_nz r (u . v)
+            double part = 0.0;
+            for (int i = tid; i < dim; i += nthreads) part += (double)zvec[i] * (double)zvec[i];
+            const double zz = block_sum_fixed(part, s_red);
+            if (tid == 0) p.cross_out[row] = lowrank ? (rr - zz) / (double)pos_scale : zz;
         }
 
         // ---- back substitution L^T x = z, one block column at a time -------------------------

@@ -20,6 +20,7 @@
 #include "comm.cuh"
 #include "gram.cuh"
 #include "score.cuh"
+#include "small_f64.cuh"
 #include "tc_score.cuh"
 #include "tc_chol.cuh"
 #include "tc_chol_multi.cuh"
@@ -163,6 +164,7 @@ struct hyprec_ctx {
     bool tc_chol_enabled = true;   // HYPREC_TC_CHOL=0: float32 systems factorise in shared-memory tiles (als_solve.cuh)
     bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
     bool split_enabled = true;     // HYPREC_SPLIT=0: rows with tens of thousands of positives stay on one CTA
+    bool small_f64_enabled = true; // HYPREC_SMALL_F64=0: float64 rows of <= 32 positives stay on the tile kernel
     int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
     bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -612,6 +614,7 @@ struct Engine : EngineBase {
         a.ymat_row0 = ymat_row0;
         a.export_tiles = export_ptr;
         a.tmem_cols = tc ? hyprec::tc::syrk_tmem_cols(max_dim) : 0;
+        a.cross_out = (cross_active && !export_ptr) ? cross.as<double>() : nullptr;
         a.prof = nullptr;
         if (h->prof_enabled && !export_ptr && slot == h->prof_slot) {
             if (prof_buf.reserve(16 * sizeof(long long)) != HYPREC_OK) return HYPREC_E_NOMEM;
@@ -671,6 +674,37 @@ struct Engine : EngineBase {
         return HYPREC_OK;
     }
 
+
+    // float64 low-rank systems of <= 32 unknowns, one warp per row, S built with FP64 MMAs (small_f64.cuh)
+    int launch_small_f64(bool user, const int32_t* list, int64_t n_list, const double* q_ptr, cudaStream_t st, int slot,
+                         int64_t out_row0) {
+        namespace hp = hyprec;
+        const Csr& rows_csr = user ? csr : csc;
+        const size_t smem = hp::small_smem_bytes();
+        HY_TRY(ensure_dynamic_smem((const void*)hp::lowrank_small_f64_kernel, (int)smem));
+        hp::SmallArgs a;
+        a.indptr = rows_csr.indptr.template as<int64_t>();
+        a.indices = rows_csr.indices.template as<int32_t>();
+        a.values = rows_csr.values.template as<double>();
+        a.fixed = q_ptr;
+        a.ymat = ymat.as<double>();
+        a.ymat_row0 = out_row0;
+        a.row_list = list;
+        a.n_list = n_list;
+        a.k = k;
+        a.work_counter = counter.as<int>() + slot;
+        a.status = counter.as<int>() + kStatusSlot;
+        a.cross_out = cross_active ? cross.as<double>() : nullptr;
+        int per_sm = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp::lowrank_small_f64_kernel, hp::kSmallWarps * 32, smem));
+        per_sm = std::max(per_sm, 1);
+        const int64_t ctas = (n_list + hp::kSmallWarps - 1) / hp::kSmallWarps;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)per_sm * h->num_sms));
+        hp::lowrank_small_f64_kernel<<<grid, hp::kSmallWarps * 32, smem, st>>>(a);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+        return HYPREC_OK;
+    }
 
     // several float32 low-rank systems of <= slot (32 / 64 / 128) unknowns per CTA pass (tc_chol_multi.cuh)
     int launch_chol_multi(bool user, double lambda, int64_t lo, int64_t hi, const int32_t* list, int64_t n_list, int slot_rows,
@@ -1525,7 +1559,7 @@ struct Engine : EngineBase {
         // the item half-step's tensor-memory kernels hand out the RMSE cross term per row (see `cross`)
         cross_valid = false;
         cross_active = false;
-        const bool cross_wanted = !user && sizeof(T) == sizeof(float) && !has_prior && h->rmse_fused_enabled;
+        const bool cross_wanted = !user && !has_prior && h->rmse_fused_enabled;
         auto begin_cross = [&]() -> int {
             HY_TRY(cross.reserve(sizeof(double) * (size_t)n));
             if (hi > lo) CU_TRY(cudaMemsetAsync(cross.as<double>() + lo, 0, sizeof(double) * (size_t)(hi - lo), h->stream));
@@ -1535,8 +1569,8 @@ struct Engine : EngineBase {
         void* peers7[7];
         const int n_peer_latent = comm ? peer_outputs(user ? cm.off_u : cm.off_v, peers7) : 0;
         // (evaluated alike on every rank: a sharded run sums the ranks' parts, so all take the same branch)
-        const bool cross_cfg = cross_wanted && chol_direct &&
-                               (!lowrank || (h->tc_solve_enabled && h->tc_chol_enabled && h->tc_multi_enabled && k % 4 == 0));
+        // (every row kernel -- the SIMT tile kernel in both precisions and the tensor-memory kernels -- hands the term out)
+        const bool cross_cfg = cross_wanted;
         if (hi == lo) {
             // (comm, empty shard) nothing to solve; still takes part in the exchange below
             if (cross_cfg) HY_TRY(begin_cross());
@@ -1636,7 +1670,14 @@ struct Engine : EngineBase {
                                                         h->aux[b], 1 + b, pl.bucket_off[b]));
                             }
                         }
-                        if (!chol && !multi)
+                        bool small64 = false;
+                        if constexpr (sizeof(T) == sizeof(double)) {
+                            small64 = h->small_f64_enabled && pl.bucket_dim[b] <= hyprec::kSmallDim && prior_ptr == nullptr;
+                            if (small64)
+                                HY_TRY(launch_small_f64(user, lists + pl.bucket_off[b], cnt, reinterpret_cast<const double*>(q_ptr),
+                                                        h->aux[b], 1 + b, pl.bucket_off[b]));
+                        }
+                        if (!chol && !multi && !small64)
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
                                            tc ? hyprec::kSolveThreads : kBucketThreads[b], q_ptr,
                                            prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
@@ -2567,6 +2608,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->tc_multi_enabled = !(tmu && tmu[0] == '0');
     const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");
     if (ps) h->prof_slot = atoi(ps);
+    const char* sm64 = getenv("HYPREC_SMALL_F64");
+    h->small_f64_enabled = !(sm64 && sm64[0] == '0');
     const char* spl = getenv("HYPREC_SPLIT");
     h->split_enabled = !(spl && spl[0] == '0');
     const char* lr = getenv("HYPREC_LOWRANK");

@@ -14,6 +14,7 @@ thread_local Block* t_block = nullptr;
 #include "../../hyprec_b200/csrc/score.cuh"
 #include "../../hyprec_b200/csrc/topk.cuh"
 #include "../../hyprec_b200/csrc/comm.cuh"
+#include "../../hyprec_b200/csrc/small_f64.cuh"
 
 using namespace hyprec;
 
@@ -29,6 +30,8 @@ static void gram_impl(const T* y, int64_t rows, int k, int nsplit, T* g) {
     emu::launch(dim3((k * k + 255) / 256), dim3(256), 0,
                 [&]() { gram_reduce_kernel<T>(partial.data(), nsplit, k, g); });
 }
+
+static double* g_cross_out = nullptr;     // emu_set_cross_out: where the row kernels put the RMSE cross term
 
 template <typename T>
 static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T* values, const T* fixed,
@@ -49,6 +52,7 @@ static int half_step_impl(const int64_t* indptr, const int32_t* indices, const T
     a.work_counter = counter; a.status = counter + 1; a.lambda = lambda; a.k = k;
     a.row_lo = row_lo; a.row_hi = row_hi; a.chunk_rows = chunk_rows;
     a.row_list = nullptr; a.n_list = 0; a.max_dim = k; a.lowrank = 0; a.ymat = nullptr; a.ymat_row0 = 0; a.export_tiles = nullptr; a.prof = nullptr;
+    a.cross_out = g_cross_out;
     if (a_in_smem) emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(a); });
     else emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8, false, true>(a); });
     return counter[1];
@@ -117,8 +121,16 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
         b.indptr = indptr; b.fixed = q.data(); b.prior = prior ? pq.data() : nullptr; b.latent = nullptr;
         b.row_list = light.data(); b.n_list = (int64_t)light.size(); b.max_dim = max_deg; b.lowrank = 1;
         b.ymat = ymat.data(); b.ymat_row0 = 0; b.export_tiles = nullptr; b.chunk_rows = 16;   // compact: list position i -> row i
+        b.cross_out = g_cross_out;
         SolveLayout l2 = solve_layout(ts, max_deg, 16, true, sizeof(T));
-        if (ts == 4) emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 4>(b); });
+        if (ts == 0) {
+            // the warp-per-row kernel (small_f64.cuh): every light row must have <= 32 positives and no prior
+            SmallArgs sa;
+            sa.indptr = indptr; sa.indices = indices; sa.values = values; sa.fixed = q.data(); sa.ymat = ymat.data();
+            sa.ymat_row0 = 0; sa.row_list = light.data(); sa.n_list = (int64_t)light.size(); sa.k = k;
+            sa.work_counter = counter; sa.status = counter + 1; sa.cross_out = g_cross_out;
+            emu::launch(dim3(grid), dim3(kSmallWarps * 32), small_smem_bytes(), [&]() { lowrank_small_f64_kernel(sa); });
+        } else if (ts == 4) emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 4>(b); });
         else emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 8>(b); });
         // 5. X = Ymat L^-1  (X[i][c] = sum_a Ymat[i][a] LinvT[c][a]) -- light rows only are meaningful
         std::vector<T> x((size_t)n_rows * k);
@@ -130,6 +142,7 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
         SolveArgs<T> d = a;
         d.indptr = indptr; d.latent = latent; d.prior = prior; d.row_list = heavy.data(); d.n_list = (int64_t)heavy.size();
         d.export_tiles = nullptr; d.chunk_rows = 8;
+        d.cross_out = g_cross_out;
         emu::launch(dim3(grid), dim3(kSolveThreads), lay.total, [&]() { als_solve_rows_kernel<T, 8>(d); });
     }
     return counter[1];
@@ -267,6 +280,8 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
 }
 
 extern "C" {
+
+void emu_set_cross_out(double* p) { g_cross_out = p; }
 
 void emu_gram_f64(const double* y, int64_t rows, int k, int nsplit, double* g) { gram_impl<double>(y, rows, k, nsplit, g); }
 void emu_gram_f32(const float* y, int64_t rows, int k, int nsplit, float* g) { gram_impl<float>(y, rows, k, nsplit, g); }

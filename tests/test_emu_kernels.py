@@ -446,3 +446,61 @@ def test_exchange_protocol_three_ranks(emu):
     # rank 2 never shows up: ranks 0 and 1 give up after the timeout and report it
     _, _, status = run([0, 1], 2 * 10 ** 8)
     assert status[0] == 2 and status[1] == 2 and status[2] is None
+
+
+@pytest.mark.parametrize("ts", [4, 8])
+@pytest.mark.parametrize("k,cap,threads", [(12, 100, 64), (16, 12, 32), (40, 20, 256)])
+def test_rmse_cross_term_from_the_row_solve(emu, k, cap, threads, ts):
+    """SolveArgs::cross_out: every row's sum_j r_j (y_j . x) -- its share of the RMSE cross term (evaluator.py:249) --
+    falls out of the solve: b.x = |L^-1 b|^2 for k x k rows, (|r|^2 - |z|^2) / 0.9 for the deg x deg rows; rows
+    without positives contribute 0.  Non-binary ratings, both tile sizes, both paths in one half-step."""
+    rs = numpy.random.RandomState(100 + k)
+    m, n = 9, 70
+    train = (rs.rand(m, n) < 0.35).astype(numpy.float64) * rs.randint(1, 3, size=(m, n))
+    train[0, :] = 0
+    csr = oals.to_csr(train)
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    want = oals.als_half_step(u0.copy(), v0, csr, 0.05)
+    out = u0.copy()
+    cross = numpy.zeros(m)
+    ip, ix = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32)
+    emu.emu_set_cross_out(_ptr(cross))
+    try:
+        status = emu.emu_half_step_lowrank_f64(_ptr(ip), _ptr(ix), _ptr(csr.data), _ptr(v0), I64(n), _ptr(out), I64(m), k,
+                                               DBL(0.05), None, cap, threads, 3, k % 2, ts)
+    finally:
+        emu.emu_set_cross_out(None)
+    assert status == 0 and numpy.allclose(out, want, rtol=1e-10, atol=1e-12)
+    expect = numpy.array([(train[r] * want[r].dot(v0.T)).sum() for r in range(m)])
+    assert numpy.allclose(cross, expect, rtol=1e-10, atol=1e-12), (cross, expect)
+    assert cross[0] == 0.0
+
+
+@pytest.mark.parametrize("k,cap", [(12, 32), (40, 9), (200, 32), (30, 20)])
+def test_small_systems_one_warp_per_row_f64(emu, k, cap):
+    """small_f64.cuh: deg x deg systems of <= 32 positives, one warp per row -- S built with (emulated) FP64 MMA
+    fragments, in-warp Cholesky, shuffle forward / shared-memory backward substitution, y = Q_r^T t -- against the
+    oracle's half-step, with the RMSE cross term as a by-product; rows above `cap` go through the k x k kernel,
+    degrees 0, 1, 8, 9, 31, 32 included, non-binary ratings, k not a multiple of 8."""
+    rs = numpy.random.RandomState(7 + k)
+    m, n = 14, 90
+    train = numpy.zeros((m, n))
+    degrees = [0, 1, 8, 9, 31, 32, 5, 17, 24, 3, 40, 12, 2, 30]
+    for u, d in enumerate(degrees):
+        train[u, rs.permutation(n)[:d]] = rs.randint(1, 3, size=d)
+    csr = oals.to_csr(train)
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    want = oals.als_half_step(u0.copy(), v0, csr, 0.05)
+    out = u0.copy()
+    cross = numpy.zeros(m)
+    ip, ix = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32)
+    emu.emu_set_cross_out(_ptr(cross))
+    try:
+        status = emu.emu_half_step_lowrank_f64(_ptr(ip), _ptr(ix), _ptr(csr.data), _ptr(v0), I64(n), _ptr(out), I64(m), k,
+                                               DBL(0.05), None, cap, 256, 2, 1, 0)
+    finally:
+        emu.emu_set_cross_out(None)
+    assert status == 0
+    assert numpy.allclose(out, want, rtol=1e-10, atol=1e-12)
+    expect = numpy.array([(train[r] * want[r].dot(v0.T)).sum() for r in range(m)])
+    assert numpy.allclose(cross, expect, rtol=1e-10, atol=1e-12)

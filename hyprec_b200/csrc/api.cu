@@ -165,6 +165,7 @@ struct hyprec_ctx {
     bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
     bool split_enabled = true;     // HYPREC_SPLIT=0: rows with tens of thousands of positives stay on one CTA
     bool small_f64_enabled = true; // HYPREC_SMALL_F64=0: float64 rows of <= 32 positives stay on the tile kernel
+    bool fused_push = true;        // HYPREC_PUSH=bulk: multi-GPU rows leave with one copy kernel per range instead of from the GEMM epilogues
     int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
     bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -1395,9 +1396,13 @@ struct Engine : EngineBase {
 
     // rows [lo, hi) or a row list of U (side 0) / V (side 1): local replica -> every other replica
     int comm_push_rows(int side, int64_t lo, int64_t n_rows, const int32_t* list) {
+        return comm_push_at(side == 0 ? cm.off_u : cm.off_v, lo, n_rows, list);
+    }
+
+    int comm_push_at(size_t off_matrix, int64_t lo, int64_t n_rows, const int32_t* list) {
         if (n_rows <= 0 || cm.world == 1) return HYPREC_OK;
         const int grid = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)h->num_sms * 8);
-        hyprec::push_rows_kernel<T><<<grid, 256, 0, h->stream>>>(cm.peers, side == 0 ? cm.off_u : cm.off_v, k, lo, n_rows, list);
+        hyprec::push_rows_kernel<T><<<grid, 256, 0, h->stream>>>(cm.peers, off_matrix, k, lo, n_rows, list);
         h->launches += 1;
         cm.bytes_pushed += (double)n_rows * k * sizeof(T) * (cm.world - 1);
         CU_TRY(cudaGetLastError());
@@ -1494,8 +1499,13 @@ struct Engine : EngineBase {
             if (hi > lo) {
                 void* peers7[7];
                 const int np = peer_outputs(cm.off_q[s] + sizeof(T) * (size_t)lo * k, peers7);
-                HY_TRY(whiten_gemm(y + lo * k, hi - lo, linv_T(), q_of(s) + lo * k, nullptr, peers7, np));
-                cm.bytes_pushed += (double)(hi - lo) * k * sizeof(T) * np;
+                if (h->fused_push) {
+                    HY_TRY(whiten_gemm(y + lo * k, hi - lo, linv_T(), q_of(s) + lo * k, nullptr, peers7, np));
+                    cm.bytes_pushed += (double)(hi - lo) * k * sizeof(T) * np;
+                } else {
+                    HY_TRY(whiten_gemm(y + lo * k, hi - lo, linv_T(), q_of(s) + lo * k, nullptr));
+                    HY_TRY(comm_push_at(cm.off_q[s], lo, hi - lo, nullptr));
+                }
             }
             cm.prep_side = s;
             cm.prep_lambda = lambda;
@@ -1691,8 +1701,13 @@ struct Engine : EngineBase {
                     // multi-GPU run, into every other rank's replica (the exchange is this GEMM's epilogue)
                     Timer t(h, HYPREC_T_PREP);
                     T* latent = user ? U.as<T>() : V.as<T>();
-                    HY_TRY(whiten_gemm(ymat.as<T>(), n_light, linv_t_T(), latent, lists, peers7, n_peer_latent));
-                    if (comm) cm.bytes_pushed += (double)n_light * k * sizeof(T) * n_peer_latent;
+                    if (h->fused_push || !comm) {
+                        HY_TRY(whiten_gemm(ymat.as<T>(), n_light, linv_t_T(), latent, lists, peers7, n_peer_latent));
+                        if (comm) cm.bytes_pushed += (double)n_light * k * sizeof(T) * n_peer_latent;
+                    } else {
+                        HY_TRY(whiten_gemm(ymat.as<T>(), n_light, linv_t_T(), latent, lists));
+                        HY_TRY(comm_push_rows(sside, 0, n_light, lists));
+                    }
                 }
             }
             if (n_heavy > 0) {
@@ -2608,6 +2623,8 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->tc_multi_enabled = !(tmu && tmu[0] == '0');
     const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");
     if (ps) h->prof_slot = atoi(ps);
+    const char* pu = getenv("HYPREC_PUSH");
+    h->fused_push = !(pu && pu[0] == 'b');
     const char* sm64 = getenv("HYPREC_SMALL_F64");
     h->small_f64_enabled = !(sm64 && sm64[0] == '0');
     const char* spl = getenv("HYPREC_SPLIT");

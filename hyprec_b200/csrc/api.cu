@@ -165,7 +165,11 @@ struct hyprec_ctx {
     bool tc_solve_enabled = true;  // HYPREC_TC_SOLVE=0: keep the row systems' rank-k accumulation on the SIMT cores
     bool split_enabled = true;     // HYPREC_SPLIT=0: rows with tens of thousands of positives stay on one CTA
     bool small_f64_enabled = true; // HYPREC_SMALL_F64=0: float64 rows of <= 32 positives stay on the tile kernel
-    bool fused_push = true;        // HYPREC_PUSH=bulk: multi-GPU rows leave with one copy kernel per range instead of from the GEMM epilogues
+    // Multi-GPU: how the solved / whitened rows reach the other replicas.  Default: one copy kernel per range over
+    // peer memory (push_rows_kernel: 512-byte warp stores).  HYPREC_PUSH=fused stores them from the GEMM epilogues
+    // instead -- one kernel fewer, but the tensor-memory epilogue owns one ROW per lane, so its peer stores are
+    // 16-byte pieces 1 KB apart: measured 111 ms against 88 ms per epoch on 8 B200s at the full scaled size.
+    bool fused_push = false;
     int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
     bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -2624,7 +2628,7 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     const char* ps = getenv("HYPREC_SOLVE_PROF_SLOT");
     if (ps) h->prof_slot = atoi(ps);
     const char* pu = getenv("HYPREC_PUSH");
-    h->fused_push = !(pu && pu[0] == 'b');
+    h->fused_push = pu && pu[0] == 'f';
     const char* sm64 = getenv("HYPREC_SMALL_F64");
     h->small_f64_enabled = !(sm64 && sm64[0] == '0');
     const char* spl = getenv("HYPREC_SPLIT");

@@ -569,7 +569,8 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
         h.set_candidates(cp, ci, elo, ehi)                    # per fold, like the train CSR
     else:
         block = int(args.eval_users) if args.eval_users > 0 else max(256, min(4096, int(2048 / max(wl.get("scale", 1.0), 1e-3))))
-        elo, ehi = ulo, min(uhi, ulo + block)
+        elo = ulo if args.eval_offset < 0 else max(ulo, min(uhi, int(args.eval_offset)))
+        ehi = min(uhi, elo + block)
         h.set_hashed_candidates(0, 5, SCALED_SEED)
     n_tr = int(tr_ptr[ehi] - tr_ptr[elo])
     n_te = int(te_ptr[ehi] - te_ptr[elo])
@@ -628,7 +629,8 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
     if dist is not None:
         per_rank = [None] * world
         dist.all_gather_object(per_rank, dict(rank=rank, users=[int(ulo), int(uhi)], epoch_ms=float(numpy.mean(epoch_ms)),
-                                              **{name: round(per_step[name], 3) for name in ("gram", "solve", "prep", "rmse", "comm")}))
+                                              eval_users=[int(elo), int(ehi)], eval_stats=eval_stats,
+                                              **{name: round(per_step[name], 3) for name in per_step}))
     # device time of the evaluation's kernels (count sweep, top-k, flags) on the slowest rank
     eval_value = reduce_max([per_step["count"] + per_step["topk"] + per_step["flags"]])[0]
 
@@ -735,7 +737,8 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
             comm_ms = per_step["comm"]
             line["comm"] = dict(bytes_per_epoch_all_ranks=comm_total, rank0_barrier_and_push_ms=comm_ms,
                                 note="bytes every rank stored into the other replicas per epoch (factor rows, whitened rows, Gram "
-                                     "mailbox); most of them leave from GEMM epilogues, so their time is inside 'prep' / 'solve'")
+                                     "mailbox); the factor rows leave with one copy kernel per range right behind the GEMM that produced them "
+                                     "(timed inside 'prep'), HYPREC_PUSH=fused stores them from the GEMM epilogues instead")
 
     # ---- CPU baseline on this box's host cores (bounded sample), rank 0, single-GPU runs only
     if rank == 0 and with_cpu and world == 1:
@@ -809,6 +812,7 @@ def main():
                     help="default: fp32 (scaled workload, as BASELINE configs[3] specifies), fp64 (citeulike workloads)")
     ap.add_argument("--cpu-rows", type=int, default=None, help="rows per side in the CPU baseline sample")
     ap.add_argument("--eval-users", type=int, default=0, help="scaled workload: users per rank in the timed evaluation block")
+    ap.add_argument("--eval-offset", type=int, default=-1, help="scaled workload: first user of the evaluation block (default: the rank's first user)")
     ap.add_argument("--no-citeulike", action="store_true", help="scaled workload: skip the citeulike-a companion record")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

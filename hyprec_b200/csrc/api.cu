@@ -680,19 +680,19 @@ struct Engine : EngineBase {
     }
 
 
-    // float64 low-rank systems of <= 32 unknowns, one warp per row, S built with FP64 MMAs (small_f64.cuh)
-    int launch_small_f64(bool user, const int32_t* list, int64_t n_list, const double* q_ptr, cudaStream_t st, int slot,
-                         int64_t out_row0) {
+    // low-rank systems of <= 32 unknowns, one warp per row, S built with FP64 MMAs (small_f64.cuh), both precisions
+    int launch_small(bool user, const int32_t* list, int64_t n_list, const T* q_ptr, cudaStream_t st, int slot, int64_t out_row0) {
         namespace hp = hyprec;
         const Csr& rows_csr = user ? csr : csc;
         const size_t smem = hp::small_smem_bytes();
-        HY_TRY(ensure_dynamic_smem((const void*)hp::lowrank_small_f64_kernel, (int)smem));
-        hp::SmallArgs a;
+        auto kern = hp::lowrank_small_kernel<T>;
+        HY_TRY(ensure_dynamic_smem((const void*)kern, (int)smem));
+        hp::SmallArgsT<T> a;
         a.indptr = rows_csr.indptr.template as<int64_t>();
         a.indices = rows_csr.indices.template as<int32_t>();
-        a.values = rows_csr.values.template as<double>();
+        a.values = rows_csr.values.template as<T>();
         a.fixed = q_ptr;
-        a.ymat = ymat.as<double>();
+        a.ymat = ymat.as<T>();
         a.ymat_row0 = out_row0;
         a.row_list = list;
         a.n_list = n_list;
@@ -701,11 +701,11 @@ struct Engine : EngineBase {
         a.status = counter.as<int>() + kStatusSlot;
         a.cross_out = cross_active ? cross.as<double>() : nullptr;
         int per_sm = 0;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp::lowrank_small_f64_kernel, hp::kSmallWarps * 32, smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, hp::kSmallWarps * 32, smem));
         per_sm = std::max(per_sm, 1);
         const int64_t ctas = (n_list + hp::kSmallWarps - 1) / hp::kSmallWarps;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)per_sm * h->num_sms));
-        hp::lowrank_small_f64_kernel<<<grid, hp::kSmallWarps * 32, smem, st>>>(a);
+        kern<<<grid, hp::kSmallWarps * 32, smem, st>>>(a);
         h->launches += 1;
         CU_TRY(cudaGetLastError());
         return HYPREC_OK;
@@ -1608,12 +1608,17 @@ struct Engine : EngineBase {
                 HY_TRY(comm_push_rows(sside, lo, hi - lo, nullptr));
             }
         } else {
-            int cap = std::min(k, kBucketDim[usable_buckets() - 1]);
+            const int cap_fits = std::min(k, kBucketDim[usable_buckets() - 1]);
+            int cap = cap_fits;
             // float64: rows of 128..191 positives cost ~350 us in low-rank form against ~165 us as direct k x k rows
             // when the k x k tiles fit shared memory (measured on B200, profiles/r02_lowrank_cap.md)
             if (sizeof(T) == sizeof(double) && hyprec::solve_layout(8, k, 8, true, sizeof(double)).total <= (size_t)h->max_smem)
                 cap = std::min(cap, 127);
-            if (h->lowrank_cap > 0) cap = std::min(cap, h->lowrank_cap);   // tuning knob, see DESIGN.md section 5
+            // float32 with the tensor-memory k x k kernel: rows of 192..255 positives are 7 % cheaper as direct rows
+            // (no second pass over the gathered rows, K = deg instead of k in the accumulation; measured 141.9 ->
+            // 139.2 ms per epoch at a quarter of the scaled shape)
+            if (chol_direct && k > 191) cap = std::min(cap, 191);
+            if (h->lowrank_cap > 0) cap = std::min(cap_fits, h->lowrank_cap);   // tuning knob (overrides the two rules above)
             HY_TRY(build_plan(user, lo, hi, cap, chol_direct && h->split_enabled));
             const RowPlan& pl = plan[user ? 0 : 1];
             const int nbk = pl.n_buckets;
@@ -1671,8 +1676,12 @@ struct Engine : EngineBase {
                         const bool f32 = sizeof(T) == sizeof(float);
                         const bool tc = h->tc_solve_enabled && f32 && kBucketTile[b] == 8 && k % 4 == 0 && pl.bucket_dim[b] <= 256;
                         const bool chol = tc && h->tc_chol_enabled && pl.bucket_dim[b] > 128;
-                        const bool multi = h->tc_chol_enabled && f32 && k % 4 == 0 && pl.bucket_dim[b] <= 128 && h->tc_multi_enabled;
-                        if constexpr (sizeof(T) == sizeof(float)) {
+                        // rows of <= 32 positives: one warp per row, float64 arithmetic in both precisions (small_f64.cuh)
+                        const bool small = h->small_f64_enabled && pl.bucket_dim[b] <= hyprec::kSmallDim && prior_ptr == nullptr;
+                        const bool multi = !small && h->tc_chol_enabled && f32 && k % 4 == 0 && pl.bucket_dim[b] <= 128 && h->tc_multi_enabled;
+                        if (small) {
+                            HY_TRY(launch_small(user, lists + pl.bucket_off[b], cnt, q_ptr, h->aux[b], 1 + b, pl.bucket_off[b]));
+                        } else if constexpr (sizeof(T) == sizeof(float)) {
                             if (multi) {
                                 const int slot_rows = pl.bucket_dim[b] <= 32 ? 32 : (pl.bucket_dim[b] <= 64 ? 64 : 128);
                                 HY_TRY(launch_chol_multi(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, slot_rows,
@@ -1684,14 +1693,7 @@ struct Engine : EngineBase {
                                                         h->aux[b], 1 + b, pl.bucket_off[b]));
                             }
                         }
-                        bool small64 = false;
-                        if constexpr (sizeof(T) == sizeof(double)) {
-                            small64 = h->small_f64_enabled && pl.bucket_dim[b] <= hyprec::kSmallDim && prior_ptr == nullptr;
-                            if (small64)
-                                HY_TRY(launch_small_f64(user, lists + pl.bucket_off[b], cnt, reinterpret_cast<const double*>(q_ptr),
-                                                        h->aux[b], 1 + b, pl.bucket_off[b]));
-                        }
-                        if (!chol && !multi && !small64)
+                        if (!chol && !multi && !small)
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
                                            tc ? hyprec::kSolveThreads : kBucketThreads[b], q_ptr,
                                            prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
@@ -2067,7 +2069,7 @@ struct Engine : EngineBase {
     int sample_cuts(int64_t lo, int64_t hi, bool have_list, int cap, int target) {
         namespace tcn = hyprec::tc;
         const int64_t nu = hi - lo;
-        int64_t n_sample = std::min<int64_t>(n, std::max<int64_t>(256, ((int64_t)32 * n + target - 1) / target));
+        const int64_t n_sample = hyprec::eval_sample_columns(n, target, 256);
         const int64_t tiles_j = (n_sample + tcn::kBN - 1) / tcn::kBN;
         const int64_t ld = tiles_j * tcn::kBN;
         const int64_t cnt = n_sample * k;
@@ -2107,7 +2109,8 @@ struct Engine : EngineBase {
         h->launches += 1;
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemsetAsync(vmax_buf.ptr, 0, 2 * sizeof(float), h->stream));
-        hyprec::max_float_kernel<<<1, 256, 0, h->stream>>>(vnorm.as<float>(), n, vmax_buf.as<float>());
+        hyprec::max_float_kernel<<<(unsigned)std::min<int64_t>((n + 2047) / 2048, h->num_sms), 256, 0, h->stream>>>(
+            vnorm.as<float>(), n, vmax_buf.as<float>());
         hyprec::SampleCutArgs c;
         c.scores = sample_scores.as<float>();
         c.scores_ld = ld;
@@ -2124,8 +2127,20 @@ struct Engine : EngineBase {
         c.err_coef = tc_margin_coef();
         c.cut = cut_buf.as<float>();
         c.cut_emit = cut_emit_buf.as<float>();
-        const int cgrid = (int)std::min<int64_t>(nu, (int64_t)8 * h->num_sms);
-        hyprec::sample_cut_kernel<<<cgrid, hyprec::kTopkThreads, 0, h->stream>>>(c);
+        // room for the sampled candidates of a user (all sampled columns when there is no list; with one, the list's
+        // share of the catalogue plus a quarter), at least 2 CTAs per SM when that is little
+        {
+            const double share = have_list ? std::min(1.0, 1.25 * (double)cand_max / (double)std::max<int64_t>(n, 1) + 0.01) : 1.0;
+            const int64_t want = std::max<int64_t>(2048, (int64_t)(share * (double)n_sample) + 64);
+            const int64_t most = ((int64_t)h->max_smem - 2048) / 4;
+            c.stage_cap = (int)std::min<int64_t>(std::min<int64_t>(want, n_sample), most);
+        }
+        const size_t cut_smem = sizeof(unsigned) * (size_t)c.stage_cap;
+        HY_TRY(ensure_dynamic_smem((const void*)hyprec::sample_cut_kernel, (int)cut_smem));
+        int cut_per_sm = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cut_per_sm, hyprec::sample_cut_kernel, hyprec::kTopkThreads, cut_smem));
+        const int cgrid = (int)std::min<int64_t>(nu, (int64_t)std::max(cut_per_sm, 1) * h->num_sms);
+        hyprec::sample_cut_kernel<<<cgrid, hyprec::kTopkThreads, cut_smem, h->stream>>>(c);
         h->launches += 2;
         CU_TRY(cudaGetLastError());
         HY_TRY(surv.reserve(sizeof(uint2) * (size_t)nu * hyprec::kSurvCap));
@@ -2329,7 +2344,7 @@ struct Engine : EngineBase {
 
         // ---- fused score -> mask -> top-k: the tensor-core sweep (needed for the rounded counts anyway) emits only
         // the candidate cells that can reach a user's top; no users x items score matrix exists (topk.cuh).
-        const int target = std::max(2 * cap, cap + 64);
+        const int target = hyprec::eval_cut_target(cap);
         const int64_t bitmap_bytes = have_list ? (int64_t)sizeof(unsigned int) * nu * ((n + 31) / 32) : 0;
         const bool fused = fused_topk_enabled && tc_usable() && want_topk && n >= 4096 && cap >= 64 &&
                            target <= (hyprec::kSurvCap * 7) / 10 && max_cand > cap && bitmap_bytes <= ((int64_t)4 << 30);

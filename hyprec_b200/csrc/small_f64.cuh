@@ -1,4 +1,4 @@
-// Small low-rank ALS systems in float64: ONE WARP per row, several rows in flight per CTA.
+// Small low-rank ALS systems, arithmetic in float64: ONE WARP per row, several rows in flight per CTA.
 //
 // The deg x deg form of a row update (als_solve.cuh: S = I + 0.9 Q_r Q_r^T on whitened factors, rhs = r,
 // y = Q_r^T t; same reference lines, /root/reference/lib/collaborative_filtering.py:83-99) for rows with at most
@@ -12,6 +12,10 @@
 //   3. forms y = Q_r^T t with lanes along the factor index (coalesced second pass over the L2-resident rows).
 // No __syncthreads anywhere: warps pull rows from an atomic counter independently.  The RMSE cross term
 // (|r|^2 - |z|^2) / 0.9 is a by-product, as in the other row kernels.
+// T = double: the float64 mode's <= 32 bucket.  T = float: the float32 mode's <= 32 bucket -- factors and ratings
+// are read and written as float32, everything in between is the same float64 arithmetic (a 32 x 32 system is too
+// small for a tensor-memory pass to pay: tc_chol_multi_kernel<32> spends ~40 us per pass of 8 rows on its serial
+// chain, 4.8 us per row and SM at the scaled shape's 240 k small item rows).
 #pragma once
 #include "common.cuh"
 
@@ -21,12 +25,13 @@ constexpr int kSmallDim = 32;            // largest system (positives of the row
 constexpr int kSmallWarps = 8;           // warps (rows in flight) per CTA
 constexpr int kSmallLd = kSmallDim + 1;  // row stride of the per-warp matrix (conflict-free column walks)
 
-struct SmallArgs {
+template <typename T>
+struct SmallArgsT {
     const int64_t* indptr;     // CSR of the side being solved, indexed by global row id
     const int32_t* indices;    // ids into `fixed`
-    const double* values;      // ratings
-    const double* fixed;       // whitened factors Q [n_fixed][k]
-    double* ymat;              // compact output: work item w writes row ymat_row0 + w
+    const T* values;           // ratings
+    const T* fixed;            // whitened factors Q [n_fixed][k]
+    T* ymat;                   // compact output: work item w writes row ymat_row0 + w
     int64_t ymat_row0;
     const int32_t* row_list;   // rows of the launch, each with 1 .. kSmallDim positives (0 positives: y = 0)
     int64_t n_list;
@@ -35,6 +40,7 @@ struct SmallArgs {
     int* status;               // set to 1 when a solution is not finite
     double* cross_out;         // optional [n_rows]: the row's share of the RMSE cross term
 };
+typedef SmallArgsT<double> SmallArgs;
 
 HYPREC_HD size_t small_smem_bytes() {
     return (size_t)kSmallWarps * (sizeof(double) * (kSmallDim * kSmallLd + 3 * kSmallDim) + sizeof(int) * kSmallDim);
@@ -63,7 +69,8 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-__global__ void __launch_bounds__(kSmallWarps * 32) lowrank_small_f64_kernel(SmallArgs p) {
+template <typename T>
+__global__ void __launch_bounds__(kSmallWarps * 32) lowrank_small_kernel(SmallArgsT<T> p) {
     HYPREC_DYN_SMEM(small_raw);
     const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     const int g = lane / 4, c = lane % 4;
@@ -84,55 +91,89 @@ __global__ void __launch_bounds__(kSmallWarps * 32) lowrank_small_f64_kernel(Sma
         const int64_t row = (int64_t)p.row_list[w];
         const int64_t lo = p.indptr[row];
         const int deg = (int)(p.indptr[row + 1] - lo);
-        double* out = p.ymat + (p.ymat_row0 + w) * k;
+        T* out = p.ymat + (p.ymat_row0 + w) * k;
         if (deg == 0) {
-            for (int a = lane; a < k; a += 32) out[a] = 0.0;
+            for (int a = lane; a < k; a += 32) out[a] = T(0);
             continue;
         }
         const int nb = (deg + 7) / 8;
         __syncwarp();
         idx[lane] = lane < deg ? p.indices[lo + lane] : -1;
-        const double r = lane < deg ? p.values[lo + lane] : 0.0;
+        const double r = lane < deg ? (double)p.values[lo + lane] : 0.0;
         __syncwarp();
 
         // ---- 1. D = Q_r Q_r^T, lower 8 x 8 blocks, by FP64 MMAs over k-steps of 4 -------------------------
         double acc[10][2];
 #pragma unroll
         for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
-        const double* rowp[4];
+        const T* rowp[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int id = b < nb ? idx[8 * b + g] : -1;
             rowp[b] = id >= 0 ? p.fixed + (int64_t)id * k : nullptr;
         }
-        for (int k0 = 0; k0 < k; k0 += 8) {                  // two k-steps per iteration: their loads go out together
-            double f[2][4];
+        // (warp-uniform conditions below: nb is the same on every lane)
+        auto mma_blocks = [&](const double (&f)[4]) {
+            dmma_8x8x4(acc[0][0], acc[0][1], f[0], f[0]);
+            if (nb > 1) {
+                dmma_8x8x4(acc[1][0], acc[1][1], f[1], f[0]);
+                dmma_8x8x4(acc[2][0], acc[2][1], f[1], f[1]);
+            }
+            if (nb > 2) {
+                dmma_8x8x4(acc[3][0], acc[3][1], f[2], f[0]);
+                dmma_8x8x4(acc[4][0], acc[4][1], f[2], f[1]);
+                dmma_8x8x4(acc[5][0], acc[5][1], f[2], f[2]);
+            }
+            if (nb > 3) {
+                dmma_8x8x4(acc[6][0], acc[6][1], f[3], f[0]);
+                dmma_8x8x4(acc[7][0], acc[7][1], f[3], f[1]);
+                dmma_8x8x4(acc[8][0], acc[8][1], f[3], f[2]);
+                dmma_8x8x4(acc[9][0], acc[9][1], f[3], f[3]);
+            }
+        };
+        constexpr int kVec = 16 / (int)sizeof(T);            // factor entries per 16-byte load
+        if (k % kVec == 0) {
+            // One 16-byte load per lane, row block and group of kVec k-steps: lane (g, c) fetches columns
+            // col .. col + kVec - 1 of row g, col = k0 + 4 kVec h + kVec c, and k-step s of the group multiplies entry s
+            // of every lane's vector -- the four lanes of a row then cover columns {col(c) + s}, a different set of
+            // four per step, the same one in the A and the B fragment (a sum over k does not care about its order).
+            // Two groups per iteration: 8 x 16 bytes in flight per lane, a quarter (float) / half (double) of the
+            // round trips of the entry-wise loop below -- the rows come from HBM at the scaled shapes.
+            struct __align__(16) Vec { T v[kVec]; };
+            for (int k0 = 0; k0 < k; k0 += 8 * kVec) {
+                Vec ld[2][4];
 #pragma unroll
-            for (int s = 0; s < 2; ++s)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int colk = k0 + 4 * s + c;
-                    f[s][b] = (rowp[b] != nullptr && colk < k) ? rowp[b][colk] : 0.0;
-                }
+                    for (int b = 0; b < 4; ++b) {
+                        const int colk = k0 + 4 * kVec * h + kVec * c;
+                        if (rowp[b] != nullptr && colk < k) {
+                            ld[h][b] = *reinterpret_cast<const Vec*>(rowp[b] + colk);
+                        } else {
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                // (warp-uniform conditions: nb is the same on every lane)
-                dmma_8x8x4(acc[0][0], acc[0][1], f[s][0], f[s][0]);
-                if (nb > 1) {
-                    dmma_8x8x4(acc[1][0], acc[1][1], f[s][1], f[s][0]);
-                    dmma_8x8x4(acc[2][0], acc[2][1], f[s][1], f[s][1]);
-                }
-                if (nb > 2) {
-                    dmma_8x8x4(acc[3][0], acc[3][1], f[s][2], f[s][0]);
-                    dmma_8x8x4(acc[4][0], acc[4][1], f[s][2], f[s][1]);
-                    dmma_8x8x4(acc[5][0], acc[5][1], f[s][2], f[s][2]);
-                }
-                if (nb > 3) {
-                    dmma_8x8x4(acc[6][0], acc[6][1], f[s][3], f[s][0]);
-                    dmma_8x8x4(acc[7][0], acc[7][1], f[s][3], f[s][1]);
-                    dmma_8x8x4(acc[8][0], acc[8][1], f[s][3], f[s][2]);
-                    dmma_8x8x4(acc[9][0], acc[9][1], f[s][3], f[s][3]);
-                }
+                            for (int s = 0; s < kVec; ++s) ld[h][b].v[s] = T(0);
+                        }
+                    }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int s = 0; s < kVec; ++s) {
+                        const double f[4] = {(double)ld[h][0].v[s], (double)ld[h][1].v[s], (double)ld[h][2].v[s], (double)ld[h][3].v[s]};
+                        mma_blocks(f);
+                    }
+            }
+        } else {
+            for (int k0 = 0; k0 < k; k0 += 8) {              // two k-steps per iteration: their loads go out together
+                double f[2][4];
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int colk = k0 + 4 * s + c;
+                        f[s][b] = (rowp[b] != nullptr && colk < k) ? (double)rowp[b][colk] : 0.0;
+                    }
+#pragma unroll
+                for (int s = 0; s < 2; ++s) mma_blocks(f[s]);
             }
         }
         // S = I + 0.9 D into shared memory: tile (bi, bj) entry (row g, columns 2c, 2c+1)
@@ -204,22 +245,54 @@ __global__ void __launch_bounds__(kSmallWarps * 32) lowrank_small_f64_kernel(Sma
         tvec[lane] = lane < deg ? tmine : 0.0;
         __syncwarp();
 
-        // ---- 4. y = Q_r^T t: lanes along the factor index, four rows in flight --------------------------------
+        // ---- 4. y = Q_r^T t: lanes along the factor index -----------------------------------------------------
         bool finite = true;
-        for (int col0 = lane; col0 < k; col0 += 32) {
-            double s = 0.0;
-            int i = 0;
-            for (; i + 4 <= deg; i += 4) {
-                const double q0 = p.fixed[(int64_t)idx[i] * k + col0], q1 = p.fixed[(int64_t)idx[i + 1] * k + col0];
-                const double q2 = p.fixed[(int64_t)idx[i + 2] * k + col0], q3 = p.fixed[(int64_t)idx[i + 3] * k + col0];
-                s += q0 * tvec[i];
-                s += q1 * tvec[i + 1];
-                s += q2 * tvec[i + 2];
-                s += q3 * tvec[i + 3];
+        if (k % kVec == 0) {
+            // 16-byte loads, eight rows in flight per lane: the rows are L2-resident after step 1, so a row costs one
+            // round trip per 32 kVec columns and eight of them overlap
+            struct __align__(16) Vec { T v[kVec]; };
+            for (int col0 = kVec * lane; col0 < k; col0 += 32 * kVec) {
+                double s[kVec];
+#pragma unroll
+                for (int e = 0; e < kVec; ++e) s[e] = 0.0;
+                for (int i0 = 0; i0 < deg; i0 += 8) {
+                    Vec q[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u < deg ? i0 + u : deg - 1;       // (the repeats get weight 0 below)
+                        q[u] = *reinterpret_cast<const Vec*>(p.fixed + (int64_t)idx[i] * k + col0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double w = i0 + u < deg ? tvec[i0 + u] : 0.0;
+#pragma unroll
+                        for (int e = 0; e < kVec; ++e) s[e] += (double)q[u].v[e] * w;
+                    }
+                }
+                Vec o;
+#pragma unroll
+                for (int e = 0; e < kVec; ++e) {
+                    finite = finite && (s[e] - s[e] == 0.0);
+                    o.v[e] = (T)s[e];
+                }
+                *reinterpret_cast<Vec*>(out + col0) = o;
             }
-            for (; i < deg; ++i) s += p.fixed[(int64_t)idx[i] * k + col0] * tvec[i];
-            finite = finite && (s - s == 0.0);
-            out[col0] = s;
+        } else {
+            for (int col0 = lane; col0 < k; col0 += 32) {
+                double s = 0.0;
+                int i = 0;
+                for (; i + 4 <= deg; i += 4) {
+                    const double q0 = (double)p.fixed[(int64_t)idx[i] * k + col0], q1 = (double)p.fixed[(int64_t)idx[i + 1] * k + col0];
+                    const double q2 = (double)p.fixed[(int64_t)idx[i + 2] * k + col0], q3 = (double)p.fixed[(int64_t)idx[i + 3] * k + col0];
+                    s += q0 * tvec[i];
+                    s += q1 * tvec[i + 1];
+                    s += q2 * tvec[i + 2];
+                    s += q3 * tvec[i + 3];
+                }
+                for (; i < deg; ++i) s += (double)p.fixed[(int64_t)idx[i] * k + col0] * tvec[i];
+                finite = finite && (s - s == 0.0);
+                out[col0] = (T)s;
+            }
         }
         if (!finite) *p.status = 1;
     }

@@ -522,21 +522,42 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_rows_kernel(CholRowsA
                 out[tid] = v;
             }
         } else {
-            // y = Q_r^T t + p  (second, L2-resident pass over the row's Q rows; coalesced along a)
-            for (int a = tid; a < k; a += kCholThreads) {
-                float s = prior_row ? p.lambda * prior_row[a] : 0.f;
-                int i = 0;
-#pragma unroll 2
-                for (; i + 8 <= dim; i += 8) {   // eight (sixteen after unrolling) loads in flight per thread
-                    float q[8];
+            // y = Q_r^T t + p  (second, L2-resident pass over the row's Q rows).  Four thread groups of 64 take every
+            // fourth row each, a thread its 4 columns with 16-byte loads, eight rows in flight; the groups' partial
+            // sums meet in shared memory (l11 is free after the back substitution).
+            // (k may exceed 256 -- only the system is limited to 256 unknowns: 256 columns per round)
+            const int grp = tid >> 6;
+            for (int cb = 0; cb < k; cb += 256) {
+                const int c4 = cb + (tid & 63) * 4;
+                float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c4 < k) {
+                    for (int i0 = grp; i0 < dim; i0 += 32) {
+                        float4 q[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) q[u] = __ldg(p.fixed + (int64_t)idxs[i + u] * k + a);
+                        for (int u = 0; u < 8; ++u) {
+                            const int i = i0 + 4 * u < dim ? i0 + 4 * u : i0;     // (the repeats get weight 0 below)
+                            q[u] = __ldg(reinterpret_cast<const float4*>(p.fixed + (int64_t)idxs[i] * k + c4));
+                        }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) s = fmaf(q[u], xs[i + u], s);
+                        for (int u = 0; u < 8; ++u) {
+                            const float w = i0 + 4 * u < dim ? xs[i0 + 4 * u] : 0.f;
+                            acc4.x = fmaf(q[u].x, w, acc4.x);
+                            acc4.y = fmaf(q[u].y, w, acc4.y);
+                            acc4.z = fmaf(q[u].z, w, acc4.z);
+                            acc4.w = fmaf(q[u].w, w, acc4.w);
+                        }
+                    }
                 }
-                for (; i < dim; ++i) s += p.fixed[(int64_t)idxs[i] * k + a] * xs[i];
-                if (!(s - s == 0.f)) *p.status = 1;
-                out[a] = s;
+                __syncthreads();                           // (l11: its last readers -- back substitution, previous round -- are done)
+                if (c4 < k) *reinterpret_cast<float4*>(l11 + grp * 256 + (c4 - cb)) = acc4;
+                __syncthreads();
+                const int a = cb + tid;
+                if (a < k) {
+                    float s = prior_row ? p.lambda * prior_row[a] : 0.f;
+                    s += (l11[tid] + l11[256 + tid]) + (l11[512 + tid] + l11[768 + tid]);
+                    if (!(s - s == 0.f)) *p.status = 1;
+                    out[a] = s;
+                }
             }
         }
         HYPREC_TCPROF(10)

@@ -617,9 +617,9 @@ __global__ void __launch_bounds__(kTopkThreads) hashed_candidates_kernel(HashedC
 // ---------------------------------------------------------------------------------------------------
 // Fused score -> mask -> top-k without a users x items score matrix (BASELINE north_star kernel (d)).
 //   1. cand_bitmap_kernel: one bit per (user, item) of the user's candidate stream (once per fold);
-//   2. a small tensor-core pass scores every user against J = ~32 n / target sampled item columns; per user,
-//      sample_cut_kernel takes the r-th largest sampled CANDIDATE score (r ~ 32) as `cut`: about `target`
-//      (~2 x capacity) of the user's candidates are expected above it;
+//   2. a small tensor-core pass scores every user against J = ~44 n / target sampled item columns; per user,
+//      sample_cut_kernel takes the r-th largest sampled CANDIDATE score (r ~ 44) as `cut`: about `target`
+//      (2.8 x capacity) of the user's candidates are expected above it (eval_cut_target below);
 //   3. the full tensor-core sweep (needed anyway for the rounded counts) emits from its epilogue only the candidate
 //      cells with s~ >= cut - 2E (tc_score.cuh);
 //   4. eval_topk_kernel above looks the emitted cells up while streaming the candidate list, re-scores the
@@ -652,6 +652,29 @@ __global__ void cand_bitmap_kernel(const int64_t* __restrict__ cand_indptr, cons
     }
 }
 
+// How many of a user's candidates the cut aims to keep, and how many item columns are sampled for it.
+// The r-th largest sampled candidate score is the cut, r = target * (sampled candidates) / (list length) ~ 44
+// when the list is longer than the sample is sparse; the number of list elements above it then spreads like
+// target * Gamma(r) / r.  With target = 2.8 x capacity and r ~ 44 both accidents -- fewer than `capacity` elements
+// above the cut, more than kSurvCap cells emitted -- are > 4 sigma away (~1e-7 per user).  With r ~ 32 and
+// 2 x capacity (the first version) one user in ~5 000 came up short and went through its whole stream on ONE
+// CTA: 40 ms for a 100 000-element stream, 130 ms for 400 000 -- longer than everything else of the evaluation.
+// Capacities above 255 cannot have 2.8 x: the target stays at 0.7 kSurvCap down to 2 x capacity (more users redone
+// through their streams: overflow at 2.9 sigma for capacity 300), beyond that the fused path is not used.
+HYPREC_HD int eval_cut_target(int capacity) {
+    const int a = (14 * capacity) / 5, b = capacity + 64, limit = (kSurvCap * 7) / 10;
+    const int want = a > b ? a : b;
+    int least = 2 * capacity > b ? 2 * capacity : b;
+    if (least < limit) least = limit;
+    return want < least ? want : least;
+}
+constexpr int kCutRank = 44;
+HYPREC_HD int64_t eval_sample_columns(int64_t n_items, int target, int64_t at_least) {
+    int64_t j = ((int64_t)kCutRank * n_items + target - 1) / target;
+    if (j < at_least) j = at_least;
+    return j < n_items ? j : n_items;
+}
+
 // item id of sampled column j: evenly spread over [0, n)
 HYPREC_HD int64_t sample_item(int64_t j, int64_t n_sample, int64_t n_items) {
     return (2 * j + 1) * n_items / (2 * n_sample);
@@ -671,16 +694,18 @@ struct SampleCutArgs {
     float err_coef;
     float* cut;                    // [n_local_users]
     float* cut_emit;               // [n_local_users] = cut - 2E, rounded down
+    int stage_cap;                 // entries of dynamic shared memory (4 bytes each) for a user's sampled candidate keys
 };
 
-constexpr int kCutStaged = 8192;          // sampled columns whose keys are kept in shared memory between the passes
-
+// The keys of a user's sampled CANDIDATES are compacted into shared memory by the first pass (stage_cap entries
+// of dynamic shared memory, 4 bytes each); the radix passes then touch neither the score row nor the bitmap again.
+// A user with more sampled candidates than that re-reads them in every pass.
 __global__ void __launch_bounds__(kTopkThreads) sample_cut_kernel(SampleCutArgs p) {
+    HYPREC_DYN_SMEM(cut_raw);
+    unsigned* staged = (unsigned*)cut_raw;
     __shared__ unsigned hist[256];
-    __shared__ unsigned staged[kCutStaged];
     __shared__ int s_digit, s_need, s_count, s_total;
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
-    const bool stage = p.n_sample <= kCutStaged;       // (else every pass re-reads the scores and the bitmap)
     for (int64_t ul = blockIdx.x; ul < p.n_users; ul += gridDim.x) {
         const float* row = p.scores + ul * p.scores_ld;
         const unsigned int* bits = p.cand_bits ? p.cand_bits + ul * p.bits_ld : nullptr;
@@ -691,19 +716,27 @@ __global__ void __launch_bounds__(kTopkThreads) sample_cut_kernel(SampleCutArgs 
             }
             return float_key(row[j]);
         };
-        auto key_of = [&](int64_t j) -> unsigned int { return stage ? staged[j] : key_raw(j); };
         __syncthreads();
         if (tid == 0) s_total = 0;
         __syncthreads();
-        int mine = 0;
-        for (int64_t j = tid; j < p.n_sample; j += kTopkThreads) {
-            const unsigned int key = key_raw(j);
-            if (stage) staged[j] = key;
-            mine += key != 0u ? 1 : 0;
+        // (whole warps stay in the loop: the slots of a warp's candidates are reserved with one atomic)
+        for (int64_t j0 = 32 * warp; j0 < p.n_sample; j0 += kTopkThreads) {
+            const int64_t j = j0 + lane;
+            const unsigned int key = j < p.n_sample ? key_raw(j) : 0u;
+            const unsigned int have = __ballot_sync(0xffffffffu, key != 0u);
+            int base = 0;
+            if (lane == 0 && have != 0u) base = atomicAdd(&s_total, __popc(have));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (key != 0u) {
+                const int slot = base + __popc(have & ((1u << lane) - 1u));
+                if (slot < p.stage_cap) staged[slot] = key;
+            }
         }
-        if (mine) atomicAdd(&s_total, mine);
         __syncthreads();
         const int n_sc = s_total;
+        const bool stage = n_sc <= p.stage_cap;
+        const int64_t n_keys = stage ? (int64_t)n_sc : p.n_sample;
+        auto key_of = [&](int64_t j) -> unsigned int { return stage ? staged[j] : key_raw(j); };
         const int64_t list_len = p.cand_indptr ? p.cand_indptr[ul + 1] - p.cand_indptr[ul] : p.n_items;
         float cut = -3.0e38f;
         if (n_sc > 0 && list_len > (int64_t)p.target) {
@@ -711,13 +744,13 @@ __global__ void __launch_bounds__(kTopkThreads) sample_cut_kernel(SampleCutArgs 
             int64_t r = ((int64_t)p.target * n_sc + list_len - 1) / list_len;
             if (r < 1) r = 1;
             if (r <= n_sc) {
-                // most-significant-digit radix select of the r-th largest key, keys recomputed per pass
+                // most-significant-digit radix select of the r-th largest key
                 unsigned int prefix = 0, mask = 0;
                 int need = (int)r;
                 for (int shift = 24; shift >= 0; shift -= 8) {
                     hist[tid] = 0;
                     __syncthreads();
-                    for (int64_t j = tid; j < p.n_sample; j += kTopkThreads) {
+                    for (int64_t j = tid; j < n_keys; j += kTopkThreads) {
                         const unsigned int key = key_of(j);
                         if (key != 0u && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
                     }
@@ -780,18 +813,19 @@ __global__ void gather_rows_cast_kernel(const T* __restrict__ v, int64_t n_sampl
     out[i] = (float)v[sample_item(j, n_sample, n_items) * k + c];
 }
 
-// max of a float array (single block), for the uniform error bound of the pre-filter
+// max of a non-negative float array (any grid; *out zeroed by the caller): non-negative floats order like their
+// bit patterns, so the blocks combine with an integer atomicMax -- order-independent, hence deterministic
 __global__ void max_float_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
     __shared__ float red[256];
     float s = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = in[i] > s ? in[i] : s;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = in[i] > s ? in[i] : s;
     red[threadIdx.x] = s;
     __syncthreads();
     for (int w = blockDim.x / 2; w > 0; w >>= 1) {
         if ((int)threadIdx.x < w) red[threadIdx.x] = red[threadIdx.x + w] > red[threadIdx.x] ? red[threadIdx.x + w] : red[threadIdx.x];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = red[0];
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(red[0]));
 }
 
 }  // namespace hyprec

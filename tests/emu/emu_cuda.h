@@ -147,6 +147,11 @@ inline unsigned atomicCAS(unsigned* p, unsigned compare, unsigned val) {
     return compare;
 }
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 inline float __uint_as_float(unsigned v) { float r; memcpy(&r, &v, 4); return r; }
 inline unsigned __float_as_uint(float v) { unsigned r; memcpy(&r, &v, 4); return r; }
 struct uint2 { unsigned x, y; };

@@ -129,7 +129,7 @@ static int half_step_lowrank_impl(const int64_t* indptr, const int32_t* indices,
             sa.indptr = indptr; sa.indices = indices; sa.values = values; sa.fixed = q.data(); sa.ymat = ymat.data();
             sa.ymat_row0 = 0; sa.row_list = light.data(); sa.n_list = (int64_t)light.size(); sa.k = k;
             sa.work_counter = counter; sa.status = counter + 1; sa.cross_out = g_cross_out;
-            emu::launch(dim3(grid), dim3(kSmallWarps * 32), small_smem_bytes(), [&]() { lowrank_small_f64_kernel(sa); });
+            emu::launch(dim3(grid), dim3(kSmallWarps * 32), small_smem_bytes(), [&]() { lowrank_small_kernel<double>(sa); });
         } else if (ts == 4) emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 4>(b); });
         else emu::launch(dim3(grid), dim3(threads), l2.total, [&]() { als_solve_rows_kernel<T, 8>(b); });
         // 5. X = Ymat L^-1  (X[i][c] = sum_a Ymat[i][a] LinvT[c][a]) -- light rows only are meaningful
@@ -215,8 +215,8 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
             distinct.assign(nu, 0);
             emu::launch(dim3(3), dim3(64), 0, [&]() { cand_bitmap_kernel(cp, ci, nu, words, bits.data(), distinct.data()); });
         }
-        const int target = std::max(2 * cap, cap + 64);
-        int64_t n_sample = std::min<int64_t>(n, std::max<int64_t>(16, (32 * n + target - 1) / target));
+        const int target = eval_cut_target(cap);
+        const int64_t n_sample = eval_sample_columns(n, target, 16);
         sample.assign((size_t)nu * n_sample, 0.f);
         for (int64_t u = 0; u < nu; ++u)
             for (int64_t j = 0; j < n_sample; ++j) sample[(size_t)u * n_sample + j] = approx[(size_t)u * ld + sample_item(j, n_sample, n)];
@@ -227,7 +227,9 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
         sc.cand_bits = ci ? bits.data() : nullptr; sc.bits_ld = words; sc.cand_indptr = ci ? cp : nullptr; sc.n_users = nu;
         sc.capacity = cap; sc.target = target; sc.unorm = unorm_v.data(); sc.vmax = vmax; sc.err_coef = (float)prefilter_coef;
         sc.cut = cut.data(); sc.cut_emit = cut_emit.data();
-        emu::launch(dim3(2), dim3(kTopkThreads), 0, [&]() { sample_cut_kernel(sc); });
+        // (room for about half of the sampled columns: users with longer lists take the re-reading path)
+        sc.stage_cap = (int)std::max<int64_t>(8, n_sample / 2);
+        emu::launch(dim3(2), dim3(kTopkThreads), sizeof(unsigned) * (size_t)sc.stage_cap, [&]() { sample_cut_kernel(sc); });
         surv.assign((size_t)nu * kSurvCap, make_uint2(0u, 0u));
         surv_cnt.assign(nu, 0u);
         for (int64_t u = 0; u < nu; ++u)
@@ -282,6 +284,18 @@ static void eval_impl(const T* U, const T* V, int64_t m, int64_t n, int k, int64
 extern "C" {
 
 void emu_set_cross_out(double* p) { g_cross_out = p; }
+
+// the warp-per-row kernel on float32 factors (float64 arithmetic inside): rows `list` of the CSR against whitened
+// factors q, compact output ymat[i] for list position i, cross[row] = (|r|^2 - |z|^2) / 0.9
+int emu_small_rows_f32(const int64_t* indptr, const int32_t* indices, const float* values, const float* q, int k,
+                       const int32_t* list, int64_t n_list, float* ymat, double* cross, int grid) {
+    int counter[2] = {0, 0};
+    SmallArgsT<float> sa;
+    sa.indptr = indptr; sa.indices = indices; sa.values = values; sa.fixed = q; sa.ymat = ymat; sa.ymat_row0 = 0;
+    sa.row_list = list; sa.n_list = n_list; sa.k = k; sa.work_counter = counter; sa.status = counter + 1; sa.cross_out = cross;
+    emu::launch(dim3(grid), dim3(kSmallWarps * 32), small_smem_bytes(), [&]() { lowrank_small_kernel<float>(sa); });
+    return counter[1];
+}
 
 void emu_gram_f64(const double* y, int64_t rows, int k, int nsplit, double* g) { gram_impl<double>(y, rows, k, nsplit, g); }
 void emu_gram_f32(const float* y, int64_t rows, int k, int nsplit, float* g) { gram_impl<float>(y, rows, k, nsplit, g); }

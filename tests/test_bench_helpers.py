@@ -116,6 +116,7 @@ def test_bench_line_python_flow_with_a_stand_in_handle(monkeypatch, capsys):
     class Args(object):
         gpus, steps, warmup, impl, workload, scale, precision, cpu_rows, eval_users = 1, 2, 1, "ours", "small", 0.1, None, 2, 0
         no_citeulike = False
+        eval_offset = -1
 
     args = Args()
     bench.our_arm(args, bench.make_workload(args))

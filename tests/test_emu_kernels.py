@@ -476,7 +476,7 @@ def test_rmse_cross_term_from_the_row_solve(emu, k, cap, threads, ts):
     assert cross[0] == 0.0
 
 
-@pytest.mark.parametrize("k,cap", [(12, 32), (40, 9), (200, 32), (30, 20)])
+@pytest.mark.parametrize("k,cap", [(12, 32), (40, 9), (200, 32), (30, 20), (15, 32)])
 def test_small_systems_one_warp_per_row_f64(emu, k, cap):
     """small_f64.cuh: deg x deg systems of <= 32 positives, one warp per row -- S built with (emulated) FP64 MMA
     fragments, in-warp Cholesky, shuffle forward / shared-memory backward substitution, y = Q_r^T t -- against the
@@ -504,3 +504,38 @@ def test_small_systems_one_warp_per_row_f64(emu, k, cap):
     assert numpy.allclose(out, want, rtol=1e-10, atol=1e-12)
     expect = numpy.array([(train[r] * want[r].dot(v0.T)).sum() for r in range(m)])
     assert numpy.allclose(cross, expect, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("k", [12, 30, 40, 256])
+def test_small_systems_one_warp_per_row_f32_factors(emu, k):
+    """The float32 instantiation of small_f64.cuh (the float32 mode's <= 32 bucket): float32 whitened factors and
+    ratings in, float64 arithmetic inside, float32 y = Q_r^T (I + 0.9 Q_r Q_r^T)^-1 r out, with the row's share of
+    the RMSE cross term (|r|^2 - |z|^2) / 0.9 -- against the same formulas in numpy float64 on the float32 inputs
+    (tolerance: one float32 rounding of the result)."""
+    rs = numpy.random.RandomState(70 + k)
+    m, n = 13, 80
+    degrees = [0, 1, 8, 9, 31, 32, 5, 17, 24, 3, 12, 2, 30]
+    train = numpy.zeros((m, n))
+    for u, d in enumerate(degrees):
+        train[u, rs.permutation(n)[:d]] = rs.randint(1, 3, size=d)
+    csr = oals.to_csr(train)
+    q = (rs.rand(n, k) / numpy.sqrt(k)).astype(numpy.float32)
+    ip, ix, vals = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float32)
+    rows = numpy.arange(m, dtype=numpy.int32)[::-1].copy()          # any order: output row i belongs to list position i
+    ymat = numpy.full((m, k), -7.0, dtype=numpy.float32)
+    cross = numpy.zeros(m)
+    status = emu.emu_small_rows_f32(_ptr(ip), _ptr(ix), _ptr(vals), _ptr(q), k, _ptr(rows), I64(m), _ptr(ymat), _ptr(cross), 2)
+    assert status == 0
+    for at, r in enumerate(rows):
+        cols = ix[ip[r]:ip[r + 1]]
+        qr = q[cols].astype(numpy.float64)
+        rv = vals[ip[r]:ip[r + 1]].astype(numpy.float64)
+        s = numpy.eye(len(cols)) + 0.9 * qr.dot(qr.T)
+        t = numpy.linalg.solve(s, rv) if len(cols) else rv
+        want = qr.T.dot(t) if len(cols) else numpy.zeros(k)
+        assert numpy.allclose(ymat[at], want, rtol=2e-7, atol=1e-9), (r, numpy.abs(ymat[at] - want).max())
+        if len(cols):
+            z = numpy.linalg.solve(numpy.linalg.cholesky(s), rv)
+            assert numpy.isclose(cross[r], (rv.dot(rv) - z.dot(z)) / 0.9, rtol=1e-10, atol=1e-12)
+        else:
+            assert cross[r] == 0.0

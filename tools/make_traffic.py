@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-SOLVE = ("als_solve_rows_kernel", "lowrank_small_f64_kernel", "tc_chol_rows_kernel", "tc_chol_multi_kernel", "split_partial_kernel")
+SOLVE = ("als_solve_rows_kernel", "lowrank_small_kernel", "tc_chol_rows_kernel", "tc_chol_multi_kernel", "split_partial_kernel")
 
 
 def launches(path):

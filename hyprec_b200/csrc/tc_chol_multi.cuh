@@ -268,26 +268,60 @@ __global__ void __launch_bounds__(kCholThreads, 1) tc_chol_multi_kernel(CholRows
         }
 
         // ---- 4. y = Q_r^T t + p for every system ------------------------------------------------
-        for (int e = tid; e < NSYS * k; e += kCholThreads) {
-            const int s = e / k, a = e % k;
-            const long long row = sys_row[s];
-            if (row < 0) continue;
-            const int d = (int)sys_dim[s];
-            const int* ids = idxs + s * SLOT;
-            const float* t = xs + s * SLOT;
-            float acc = p.prior ? p.lambda * p.prior[row * k + a] : 0.f;
-            int i = 0;
-#pragma unroll 2
-            for (; i + 8 <= d; i += 8) {
-                float q[8];
+        // 16-byte loads: a unit is (system, 4 columns, row group) -- 256 columns per round, eight rows in flight per
+        // thread.  Two systems per pass leave room for two row groups each (their halves meet in shared memory; the
+        // L11 area is free after the back substitution); with 4 / 8 systems a thread walks all rows of its unit.
+        constexpr int RG = NSYS == 2 ? 2 : 1;
+        constexpr int UNITS = NSYS * 64 * RG;                // per round of 256 columns: 256, 256, 512
+        float4* halves = reinterpret_cast<float4*>(l11_all);
+        for (int cb = 0; cb < k; cb += 256) {
+            for (int u0 = 0; u0 < UNITS; u0 += kCholThreads) {
+                const int u = u0 + tid;
+                const int s = u / (64 * RG), rem = u % (64 * RG), g = rem / 64, c4 = cb + 4 * (rem % 64);
+                const long long row = sys_row[s];
+                const bool live = row >= 0 && c4 < k;
+                float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    const int d = (int)sys_dim[s];
+                    const int* ids = idxs + s * SLOT;
+                    const float* t = xs + s * SLOT;
+                    for (int i0 = g; i0 < d; i0 += 8 * RG) {
+                        float4 q[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) q[u] = __ldg(p.fixed + (int64_t)ids[i + u] * k + a);
+                        for (int v = 0; v < 8; ++v) {
+                            const int i = i0 + RG * v < d ? i0 + RG * v : i0;      // (the repeats get weight 0 below)
+                            q[v] = __ldg(reinterpret_cast<const float4*>(p.fixed + (int64_t)ids[i] * k + c4));
+                        }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc = fmaf(q[u], t[i + u], acc);
+                        for (int v = 0; v < 8; ++v) {
+                            const float w = i0 + RG * v < d ? t[i0 + RG * v] : 0.f;
+                            acc4.x = fmaf(q[v].x, w, acc4.x);
+                            acc4.y = fmaf(q[v].y, w, acc4.y);
+                            acc4.z = fmaf(q[v].z, w, acc4.z);
+                            acc4.w = fmaf(q[v].w, w, acc4.w);
+                        }
+                    }
+                }
+                if (RG == 2) {
+                    __syncthreads();                       // (the area's last readers -- back substitution, previous round -- are done)
+                    if (g == 1) halves[tid] = acc4;
+                    __syncthreads();
+                    if (g == 0) {
+                        const float4 o = halves[tid + 64];
+                        acc4.x += o.x; acc4.y += o.y; acc4.z += o.z; acc4.w += o.w;
+                    }
+                }
+                if (live && g == 0) {
+                    if (p.prior) {
+                        const float4 pr = *reinterpret_cast<const float4*>(p.prior + row * k + c4);
+                        acc4.x = fmaf(p.lambda, pr.x, acc4.x); acc4.y = fmaf(p.lambda, pr.y, acc4.y);
+                        acc4.z = fmaf(p.lambda, pr.z, acc4.z); acc4.w = fmaf(p.lambda, pr.w, acc4.w);
+                    }
+                    const float chk = (acc4.x + acc4.y) + (acc4.z + acc4.w);
+                    if (!(chk - chk == 0.f)) *p.status = 1;
+                    *reinterpret_cast<float4*>(p.out + (p.out_row0 + s_first + s) * k + c4) = acc4;
+                }
             }
-            for (; i < d; ++i) acc = fmaf(__ldg(p.fixed + (int64_t)ids[i] * k + a), t[i], acc);
-            if (!(acc - acc == 0.f)) *p.status = 1;
-            p.out[(p.out_row0 + s_first + s) * k + a] = acc;
         }
         HYPREC_TCPROF(10)
         tc_fence_before();

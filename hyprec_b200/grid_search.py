@@ -133,18 +133,21 @@ class GridSearch(object):
         best_error = numpy.inf
         best_params = dict()
         all_results = [list(HEADER)]
+        # under torchrun every rank holds the whole table; the reference writes it once: rank 0 does
+        rank = self.recommender._world()[0] if hasattr(self.recommender, '_world') else 0
         for hyperparameters, (report, train_recall, test_recall) in zip(combos, outcomes):
             all_results.append([hyperparameters['n_factors'], hyperparameters['_lambda']] + list(report))
-            if self._verbose:
+            if self._verbose and rank == 0:
                 print('Train error: %f, Test error: %f' % (train_recall, test_recall))
             if 1 - test_recall < best_error:
                 best_params = hyperparameters
                 best_error = 1 - test_recall
             key = self.get_key(hyperparameters)
             self.all_errors[key] = dict(train_recall=train_recall, test_recall=test_recall)
-        self.dump_csv(all_results)
-        if self._verbose:
-            print("Best config: %s" % best_params)
+        if rank == 0:
+            self.dump_csv(all_results)
+            if self._verbose:
+                print("Best config: %s" % best_params)
         return best_params, all_results
 
     def _sweep_sequential(self, combos):
@@ -277,6 +280,21 @@ class GridSearch(object):
             dist.all_gather_object(gathered, {i: tuple(results[i]) for i in results})
             for part in gathered:
                 results.update(part)
+            # every rank leaves train() holding the last configuration's model, as the reference's loop does: its
+            # owner hands the factors and the report details round (the split is the same on every rank)
+            if combos:
+                src = (len(combos) - 1) % world
+                payload = [(rec0.user_vecs, rec0.item_vecs, rec0.last_report_details, rec0.evaluator.recommendation_indices,
+                            rec0.evaluator.recs_loaded) if rank == src else None]
+                dist.broadcast_object_list(payload, src=src)
+                if rank != src:
+                    (rec0.user_vecs, rec0.item_vecs, rec0.last_report_details, rec0.evaluator.recommendation_indices,
+                     rec0.evaluator.recs_loaded) = payload[0]
+                    if shared['split'] is not None:
+                        rec0.hyperparameters['fold'] = 0
+                        rec0.document_distribution = None
+                        rec0.set_data(shared['split'][0], shared['split'][1])
+                        rec0.evaluator.test_indices = shared['split'][1]
         return [results[i] for i in range(len(combos))]
 
     def _adopt(self, worker, combos, shared):

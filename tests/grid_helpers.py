@@ -54,8 +54,11 @@ def sweep_under_gloo(rank, world, port, ratings, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         search = GridSearch(make_recommender(OracleBacked, ratings), GRID, verbose=False, workers=2)
-        search.dump_csv = lambda rows: None
+        dumps = []
+        search.dump_csv = lambda rows: dumps.append(len(rows))
         best, rows = search.train()
-        out[rank] = (best, [[float(x) for x in row] for row in rows[1:]])
+        rec = search.recommender
+        out[rank] = (best, [[float(x) for x in row] for row in rows[1:]], len(dumps),
+                     (numpy.asarray(rec.user_vecs).copy(), numpy.asarray(rec.item_vecs).copy()))
     finally:
         dist.destroy_process_group()

@@ -136,6 +136,9 @@ def test_configurations_are_dealt_to_ranks_gloo(golden):
         p.join(timeout=240)
         assert p.exitcode == 0
     for r in range(world):
-        best, rows = out[r]
+        best, rows, n_dumps, (uv, iv) = out[r]
         check_rows([list(golden["header"])] + rows, golden)
         assert [best['_lambda'], best['n_factors']] == list(golden["best"])
+        assert n_dumps == (1 if r == 0 else 0)                    # the table is written once, by rank 0
+        # every rank leaves train() holding the LAST configuration's model (its owner broadcasts it)
+        assert numpy.array_equal(uv, out[0][3][0]) and numpy.array_equal(iv, out[0][3][1])

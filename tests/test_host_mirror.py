@@ -284,3 +284,23 @@ def test_matrix_facts_cache_hits_and_notices_edits():
     matrix[rows, cols] = 0.0                      # the caller empties the matrix in place
     after = cf._facts(matrix)
     assert after[1] == 0.0 and after[0] is not before[0]
+
+
+def test_factor_fingerprint_sees_every_element():
+    """collaborative_filtering._fingerprint decides whether the device factors are stale: an in-place edit of ANY
+    element (here far from where a strided sample would look) must change it; equal contents must not."""
+    from hyprec_b200.collaborative_filtering import CollaborativeFiltering
+    rs = numpy.random.RandomState(5)
+    u, v = rs.rand(700, 33), rs.rand(1900, 33)
+    token = CollaborativeFiltering._fingerprint(u, v)
+    assert CollaborativeFiltering._fingerprint(u.copy(), v.copy()) == token
+    for arr, pos in ((u, (123, 7)), (v, (1777, 31)), (v, (0, 1))):
+        old = arr[pos]
+        arr[pos] = numpy.nextafter(old, 2.0)
+        assert CollaborativeFiltering._fingerprint(u, v) != token
+        arr[pos] = old
+    assert CollaborativeFiltering._fingerprint(u, v) == token
+    swapped = v.copy()
+    swapped[[3, 4]] = swapped[[4, 3]]                # a permutation keeps the xor: the CRC must see it
+    assert CollaborativeFiltering._fingerprint(u, swapped) != token
+    assert CollaborativeFiltering._fingerprint(u.astype(numpy.float32), v) != token

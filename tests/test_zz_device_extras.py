@@ -54,8 +54,13 @@ def test_recall_at_cutoffs_from_one_pass(als_cases):
     cf.user_vecs, cf.item_vecs = fold["u"].copy(), fold["v"].copy()
     cutoffs = (1, 3, 5, 10, 24, 300)
     try:
+        cf.get_evaluation_report()
+        lists_before, details_before = ev.recommendation_indices, cf.last_report_details
         got = cf.recall_at_cutoffs(cutoffs)
         assert cf.n_recommendations == 200
+        # the 300-long lists were the call's own: the evaluator and the report details hold the last report's again
+        assert ev.recommendation_indices is lists_before and cf.last_report_details is details_before
+        assert max(len(r) for r in ev.recommendation_indices) <= 200
     finally:
         cf.close()
     host = Evaluator(g["ratings"])

@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-SOLVE = ("als_solve_rows_kernel", "lowrank_small_kernel", "tc_chol_rows_kernel", "tc_chol_multi_kernel", "split_partial_kernel")
+SOLVE = ("als_solve_rows_kernel", "lowrank_small_kernel", "tc_chol_rows_kernel", "tc_chol_multi_kernel", "split_partial_kernel",
+         "split_reduce_kernel")
 
 
 def launches(path):
@@ -46,6 +47,14 @@ def main():
     last_flag = max(i for i, d in enumerate(epoch) if "nz_flags_kernel" in d["name"])
     epoch = epoch[last_flag + 1:]
     evaluation = ls[evals[-1]:]
+    flags_after = [i for i, d in enumerate(evaluation) if "nz_flags_kernel" in d["name"]]
+    tail_markers = [i for i, d in enumerate(evaluation) if i > 0 and ("build_base_tiles" in d["name"] or "fma_probe" in d["name"])]
+    if tail_markers:                       # a bench.py capture goes on after its last evaluation (end-to-end steps, probes)
+        flags_after = [i for i in flags_after if i < tail_markers[0]]
+    if flags_after:
+        evaluation = evaluation[:flags_after[-1] + 1]
+    elif tail_markers:
+        evaluation = evaluation[:tail_markers[0]]
 
     def dram(group):
         return sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for d in group)

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "comm.cuh"
 #include "gram.cuh"
+#include "host_split.cuh"
 #include "score.cuh"
 #include "small_f64.cuh"
 #include "tc_score.cuh"
@@ -2919,6 +2920,27 @@ int hyprec_flush_l2(hyprec_t* h) {
     }
     CU_TRY(cudaMemsetAsync(h->flush_buf, 0x5a, h->flush_bytes, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    return HYPREC_OK;
+}
+
+int hyprec_host_kfold_lists(uint32_t* mt_key, int* mt_pos, int64_t n_users, int64_t n_items, int k_folds,
+                            const int64_t* indptr, const int32_t* indices, int64_t capacity, int64_t* slot_ptr,
+                            int64_t* slot_positives, int64_t* ids64, int32_t* ids32) {
+    if (!mt_key || !mt_pos || !indptr || !slot_ptr || !slot_positives || (!ids64 && !ids32))
+        return fail(HYPREC_E_INVALID, "host_kfold_lists: null argument");
+    if (n_users < 0 || n_items <= 0 || n_items >= ((int64_t)1 << 31) || k_folds < 1 || *mt_pos < 0 || *mt_pos > 624)
+        return fail(HYPREC_E_INVALID, "host_kfold_lists: bad sizes or generator position");
+    for (int64_t u = 0; u < n_users; ++u) {
+        if (indptr[u + 1] < indptr[u]) return fail(HYPREC_E_INVALID, "host_kfold_lists: indptr not monotone");
+        for (int64_t e = indptr[u]; e < indptr[u + 1]; ++e)
+            if (indices[e] < 0 || indices[e] >= n_items) return fail(HYPREC_E_INVALID, "host_kfold_lists: item id out of range");
+    }
+    const int rc = hyprec_host::kfold_lists(mt_key, mt_pos, n_users, n_items, k_folds, indptr, indices, capacity,
+                                            slot_ptr, slot_positives, ids64, ids32);
+    if (rc == 1)
+        return fail(HYPREC_E_UNSUPPORTED, "host_kfold_lists: a fold's share of a user's positives exceeds n_items / k_folds "
+                                          "(negative slice bounds in evaluator.py:184-189); generator state untouched");
+    if (rc == 2) return fail(HYPREC_E_INVALID, "host_kfold_lists: capacity too small");
     return HYPREC_OK;
 }
 

@@ -23,6 +23,8 @@ What differs is how the work is done, not what comes out:
   lists cannot be enumerated (the k-fold lists hold n_items / k_folds ids per user, the naive split's lists
   n_items), ``use_hashed_candidates`` switches the evaluation to device-generated lists.
 """
+import os
+
 import numpy
 import scipy.sparse as sp
 
@@ -126,13 +128,17 @@ class Evaluator(object):
 
     # ------------------------------------------------------------------ k-fold (:120-213)
     def get_kfold_indices(self):
-        """Flat list of n_users * k_folds int64 arrays; slot ``u * k_folds + f`` holds user u's
+        """Flat list of n_users * k_folds id arrays; slot ``u * k_folds + f`` holds user u's
         fold-f candidates: its share of shuffled positives followed by shuffled non-rated items,
-        int(n_items / k_folds) long (evaluator.py:176-192)."""
+        int(n_items / k_folds) long (evaluator.py:176-192).  Normally produced by the library's host code
+        (``_native_kfold_lists``: int32 views of one buffer); the loop below is the same thing step by step."""
         if self.random_seed is False:
             numpy.random.seed(42)
         csr = self.ratings_csr()
         n, k = self.n_items, self.k_folds
+        native = self._native_kfold_lists(csr)
+        if native is not None:
+            return native
         all_items = numpy.arange(n)
         out = []
         n_positives = []        # per slot: how many entries at the head of the list are rated cells
@@ -158,6 +164,34 @@ class Evaluator(object):
                 n_positives.append(len(positives))
         self.test_indices = out
         self._slot_positives = (out, numpy.asarray(n_positives, dtype=numpy.int64))
+        return out
+
+    def _native_kfold_lists(self, csr):
+        """The same lists from the library's host code (csrc/host_split.cuh: numpy's MT19937 stream and legacy shuffle
+        restated in C++, ~4x faster than 2 x n_users numpy.random.shuffle calls plus the Python slicing).  None when
+        it does not apply (HYPREC_NATIVE_SPLIT=0, library not built, a user whose lists need negative slice bounds):
+        the loop below then runs, from the same generator state."""
+        if os.environ.get("HYPREC_NATIVE_SPLIT", "1") == "0" or self.n_items >= (1 << 31):
+            return None
+        try:
+            from hyprec_b200 import _native
+            got = _native.host_kfold_lists(csr.indptr, csr.indices, self.n_users, self.n_items, self.k_folds)
+        except (RuntimeError, OSError, AttributeError):
+            return None
+        if got is None:
+            return None
+        slot_ptr, n_positives, ids = got
+        lengths = numpy.diff(slot_ptr)
+        if len(lengths) and (lengths == lengths[0]).all() and lengths[0] > 0:
+            packed = ids[:len(lengths) * int(lengths[0])].reshape(len(lengths), int(lengths[0]))
+            out = list(packed)                      # row views: one buffer behind all lists
+        else:
+            out = [ids[slot_ptr[s]:slot_ptr[s + 1]] for s in range(len(lengths))]
+            packed = None
+        self.test_indices = out
+        self._slot_positives = (out, n_positives)
+        self._packed = (out, packed)
+        self._flat = (out, slot_ptr, ids)
         return out
 
     def get_fold(self, fold_num, fold_test_indices):
@@ -278,6 +312,15 @@ class Evaluator(object):
             slots = numpy.arange(self.n_users, dtype=numpy.int64) * (1 + fold)
             ids = packed[slots].ravel()
             return numpy.arange(self.n_users + 1, dtype=numpy.int64) * packed.shape[1], ids
+        flat = getattr(self, '_flat', None)
+        if flat is not None and flat[0] is self.test_indices:
+            # ragged lists from the native split, still one buffer: gather the fold's slots by range
+            slots = numpy.arange(self.n_users, dtype=numpy.int64) * (1 + fold)
+            starts, lens = flat[1][slots], flat[1][slots + 1] - flat[1][slots]
+            indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)
+            numpy.cumsum(lens, out=indptr[1:])
+            where = numpy.repeat(starts - indptr[:-1], lens) + numpy.arange(indptr[-1], dtype=numpy.int64)
+            return indptr, flat[2][where]
         rows = [numpy.asarray(self.test_indices[user * (1 + fold)]).astype(numpy.int64)
                 for user in range(self.n_users)]
         indptr = numpy.zeros(self.n_users + 1, dtype=numpy.int64)

@@ -240,6 +240,21 @@ int hyprec_host_free(hyprec_t* h, void* ptr);
 /* Overwrite a buffer 3x the size of L2 so the next kernel starts cold (benchmark hygiene). */
 int hyprec_flush_l2(hyprec_t* h);
 
+/* ---- host-side split (no device involved) ------------------------------------------------------------------
+ * The k-fold candidate lists of Evaluator.get_kfold_indices (lib/evaluator.py:136-195): per user, in user order,
+ * one legacy numpy.random.shuffle of its rated items and one of its non-rated items, dealt into k_folds lists of
+ * int(n_items / k_folds) ids (the fold's share of the positives first).  mt_key[624] / mt_pos are numpy's global
+ * MT19937 state (numpy.random.get_state()[1:3]), advanced exactly as the reference's calls advance it, so the lists
+ * and everything drawn afterwards (the initial factors, collaborative_filtering.py:173-176) are bit-identical.
+ * Slot u * k_folds + f occupies ids[slot_ptr[slot] .. slot_ptr[slot + 1]); slot_positives[slot] of its leading
+ * entries are rated cells.  ids64 and / or ids32 receive the lists (either may be NULL); capacity = entries they
+ * hold (n_users * k_folds * (n_items / k_folds) always suffices).  HYPREC_E_UNSUPPORTED, with the generator state
+ * untouched, when a list would need the reference's negative slice bounds (a fold's positives outnumber
+ * n_items / k_folds): the caller then runs the reference's loop. */
+int hyprec_host_kfold_lists(uint32_t* mt_key, int* mt_pos, int64_t n_users, int64_t n_items, int k_folds,
+                            const int64_t* indptr, const int32_t* indices, int64_t capacity, int64_t* slot_ptr,
+                            int64_t* slot_positives, int64_t* ids64, int32_t* ids32);
+
 #ifdef __cplusplus
 }
 #endif

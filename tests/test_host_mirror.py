@@ -304,3 +304,57 @@ def test_factor_fingerprint_sees_every_element():
     swapped[[3, 4]] = swapped[[4, 3]]                # a permutation keeps the xor: the CRC must see it
     assert CollaborativeFiltering._fingerprint(u, swapped) != token
     assert CollaborativeFiltering._fingerprint(u.astype(numpy.float32), v) != token
+
+
+def _kfold_both_ways(ratings, k_folds, monkeypatch):
+    got = []
+    for native in ("0", "1"):
+        monkeypatch.setenv("HYPREC_NATIVE_SPLIT", native)
+        ev = Evaluator(ratings.copy())
+        ev.set_kfolds(k_folds)
+        lists = ev.get_kfold_indices()
+        after = numpy.random.random(4)                  # the stream right behind the split (initial factors come next)
+        folds = [ev.candidate_lists(f) for f in range(k_folds)]
+        got.append((lists, ev._slot_positives[1], after, folds, ev))
+    return got
+
+
+def test_native_kfold_lists_equal_the_numpy_loop(monkeypatch):
+    """hyprec_host_kfold_lists (csrc/host_split.cuh: MT19937 + legacy shuffle restated in C++) against the loop of
+    numpy.random.shuffle calls it replaces (evaluator.py:144-192): same lists, same number of leading positives, and
+    the global stream left at the same position -- on random small shapes (ragged lists, empty users, k_folds = 1,
+    more folds than positives), incl. shapes where a fold's positives outnumber n_items / k_folds and the native call
+    must refuse without drawing anything."""
+    rs = numpy.random.RandomState(11)
+    native_used = refused = 0
+    for trial in range(150):
+        m, n, k = rs.randint(1, 7), rs.randint(1, 60), rs.randint(1, 8)
+        ratings = (rs.rand(m, n) < rs.rand()).astype(float)
+        py, nat = _kfold_both_ways(ratings, k, monkeypatch)
+        assert len(py[0]) == len(nat[0]) == m * k
+        for a, b in zip(py[0], nat[0]):
+            assert numpy.array_equal(numpy.asarray(a, dtype=numpy.int64), numpy.asarray(b, dtype=numpy.int64))
+        assert numpy.array_equal(py[1], nat[1])
+        assert numpy.array_equal(py[2], nat[2])
+        for (pa, ia), (pb, ib) in zip(py[3], nat[3]):
+            assert numpy.array_equal(pa, pb) and numpy.array_equal(ia, ib)
+        if getattr(nat[4], '_flat', None) is not None and nat[4]._flat[0] is nat[0]:
+            native_used += 1
+        else:
+            refused += 1
+    assert native_used > 50 and refused > 0
+
+
+def test_native_kfold_lists_at_a_long_row(monkeypatch):
+    """Rows long enough to cross several refills of the 624-word generator state and several mask widths."""
+    rs = numpy.random.RandomState(5)
+    ratings = (rs.rand(7, 5000) < 0.01).astype(float)
+    ratings[3] = 0.0                                    # a user without ratings
+    py, nat = _kfold_both_ways(ratings, 5, monkeypatch)
+    assert nat[4]._flat[0] is nat[0] and nat[0][0].dtype == numpy.int32
+    for a, b in zip(py[0], nat[0]):
+        assert numpy.array_equal(a, b)
+    assert numpy.array_equal(py[2], nat[2])
+    train_py, test_py = py[4].get_fold(2, py[0])
+    train_nat, test_nat = nat[4].get_fold(2, nat[0])
+    assert numpy.array_equal(train_py, train_nat) and numpy.array_equal(test_py, test_nat)

@@ -642,8 +642,9 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
     if has_lists and ehi > elo:
         nu = ehi - elo
         eval_out = dict(thresholds=h.pinned_empty(nu), ones_per_row=h.pinned_empty(nu, numpy.int64),
-                        topk_idx=h.pinned_empty((nu, 200), numpy.int32), topk_val=h.pinned_empty((nu, 200)),
-                        topk_hit=h.pinned_empty((nu, 200)), train_flags=h.pinned_empty(max(n_tr, 1), numpy.uint8),
+                        topk_idx=h.pinned_empty((nu, 200), numpy.int32), topk_val=None,     # the class's report call:
+                        topk_hit=h.pinned_empty((nu, 200), numpy.uint8),                      # hyprec_eval_topk_u8
+                        train_flags=h.pinned_empty(max(n_tr, 1), numpy.uint8),
                         test_flags=h.pinned_empty(max(n_te, 1), numpy.uint8))
     e2e_epoch, e2e_eval = [], []
     for step in range(1 + e2e_steps):
@@ -662,7 +663,7 @@ def run_workload(args, wl, rank, world, local, with_cpu=True, quiet=False):
     e2e_epoch_ms = 1e3 * float(numpy.mean(reduce_max(e2e_epoch)))
     e2e_eval_ms = 1e3 * float(numpy.mean(reduce_max(e2e_eval)))
     factor_bytes = (m + n) * k * 8
-    eval_d2h = (ehi - elo) * 200 * (4 + 8 + 8) + (ehi - elo) * 16 + n_tr + n_te if eval_out is not None else 0
+    eval_d2h = (ehi - elo) * 200 * (4 + 1) + (ehi - elo) * 16 + n_tr + n_te if eval_out is not None else 0
 
     # ---- metrics of the final model (reported, not timed)
     recall200, recall_at = None, None

@@ -17,11 +17,11 @@ EXPORTS = [
     "hyprec_create", "hyprec_destroy", "hyprec_last_error", "hyprec_abi_version", "hyprec_launch_count",
     "hyprec_set_train_csr", "hyprec_set_shard", "hyprec_set_factors", "hyprec_get_factors",
     "hyprec_device_factors", "hyprec_set_item_prior", "hyprec_als_half_step", "hyprec_rmse", "hyprec_rmse_terms", "hyprec_train",
-    "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_set_hashed_candidates", "hyprec_eval_topk", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
+    "hyprec_predict_dense", "hyprec_score_dense_f32", "hyprec_set_eval_csr", "hyprec_set_candidates", "hyprec_set_hashed_candidates", "hyprec_eval_topk", "hyprec_eval_topk_u8", "hyprec_kernel_ms", "hyprec_reset_kernel_ms",
     "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles", "hyprec_host_alloc", "hyprec_host_free",
     "hyprec_comm_blob_bytes", "hyprec_comm_export", "hyprec_comm_attach", "hyprec_comm_detach", "hyprec_comm_stats",
     "hyprec_init_factors_uniform", "hyprec_get_factor_rows", "hyprec_mark", "hyprec_elapsed_ms",
-    "hyprec_comm_arena", "hyprec_comm_attach_local", "hyprec_eval_stats", "hyprec_host_kfold_lists",
+    "hyprec_comm_arena", "hyprec_comm_attach_local", "hyprec_eval_stats", "hyprec_host_kfold_lists", "hyprec_host_count_nonzero",
 ]
 
 EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
@@ -73,9 +73,12 @@ def load_library(rebuild=False):
     lib.hyprec_set_candidates.argtypes = [vp, c_i64, c_i64, vp, vp]
     lib.hyprec_set_hashed_candidates.argtypes = [vp, c_int, c_int, ctypes.c_uint64]
     lib.hyprec_eval_topk.argtypes = [vp, c_i64, c_i64, vp, vp, c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.hyprec_eval_topk_u8.argtypes = [vp, c_i64, c_i64, vp, vp, c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.hyprec_kernel_ms.argtypes = [vp, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]
     lib.hyprec_reset_kernel_ms.argtypes = [vp]
     lib.hyprec_flush_l2.argtypes = [vp]
+    lib.hyprec_host_count_nonzero.argtypes = [vp, c_i64]
+    lib.hyprec_host_count_nonzero.restype = c_i64
     lib.hyprec_host_kfold_lists.argtypes = [vp, ctypes.POINTER(c_int), c_i64, c_i64, c_int, vp, vp, c_i64, vp, vp, vp, vp]
     lib.hyprec_host_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
     lib.hyprec_host_free.argtypes = [vp, vp]
@@ -104,6 +107,11 @@ def _as(array, dtype):
     if array is None:
         return None
     return numpy.ascontiguousarray(array, dtype=dtype)
+
+
+def host_count_nonzero(block):
+    """Non-zeros of a C-contiguous float64 array through the library (the call releases the GIL)."""
+    return load_library().hyprec_host_count_nonzero(_ptr(block), int(block.size))
 
 
 def host_kfold_lists(indptr, indices, n_users, n_items, k_folds):
@@ -314,31 +322,32 @@ class Handle(object):
         return out
 
     def eval_topk(self, capacity, cand_indptr=None, cand_ids=None, user_lo=0, user_hi=None, want_counts=True,
-                  want_topk=True, n_train_nz=None, n_test_nz=None, out=None):
+                  want_topk=True, n_train_nz=None, n_test_nz=None, out=None, compact=False):
         """Returns dict(thresholds, ones_per_row, topk_idx, topk_val, topk_hit, train_flags, test_flags).
-        `out`: a dict returned by an earlier identical call, to reuse its (possibly pinned) arrays."""
+        `out`: a dict returned by an earlier identical call, to reuse its (possibly pinned) arrays.
+        `compact`: hit values as uint8 and no score array (hyprec_eval_topk_u8; a tenth of the device -> host bytes);
+        a reused `out` whose topk_hit is uint8 selects the same call."""
         user_hi = self.m if user_hi is None else user_hi
         nu = user_hi - user_lo
         cand_indptr, cand_ids = _as(cand_indptr, numpy.int64), _as(cand_ids, numpy.int32)
-        if out is not None:
-            self._check(self._lib.hyprec_eval_topk(
-                self._h, user_lo, user_hi, _ptr(cand_indptr), _ptr(cand_ids), int(capacity), _ptr(out["thresholds"]),
-                _ptr(out["ones_per_row"]), _ptr(out["topk_idx"]), _ptr(out["topk_val"]), _ptr(out["topk_hit"]),
-                _ptr(out["train_flags"]), _ptr(out["test_flags"])))
-            return out
-        out = dict(thresholds=numpy.empty(nu))
-        out["ones_per_row"] = numpy.zeros(nu, dtype=numpy.int64) if want_counts else None
-        if want_topk:
-            out["topk_idx"] = numpy.empty((nu, capacity), dtype=numpy.int32)
-            out["topk_val"] = numpy.empty((nu, capacity))
-            out["topk_hit"] = numpy.empty((nu, capacity))
-        else:
+        if out is None:
+            out = dict(thresholds=numpy.empty(nu))
+            out["ones_per_row"] = numpy.zeros(nu, dtype=numpy.int64) if want_counts else None
             out["topk_idx"] = out["topk_val"] = out["topk_hit"] = None
-        out["train_flags"] = numpy.zeros(n_train_nz, dtype=numpy.uint8) if n_train_nz is not None else None
-        out["test_flags"] = numpy.zeros(n_test_nz, dtype=numpy.uint8) if n_test_nz is not None else None
-        self._check(self._lib.hyprec_eval_topk(
+            if want_topk:
+                out["topk_idx"] = numpy.empty((nu, capacity), dtype=numpy.int32)
+                if compact:
+                    out["topk_hit"] = numpy.empty((nu, capacity), dtype=numpy.uint8)
+                else:
+                    out["topk_val"] = numpy.empty((nu, capacity))
+                    out["topk_hit"] = numpy.empty((nu, capacity))
+            out["train_flags"] = numpy.zeros(n_train_nz, dtype=numpy.uint8) if n_train_nz is not None else None
+            out["test_flags"] = numpy.zeros(n_test_nz, dtype=numpy.uint8) if n_test_nz is not None else None
+        hit = out["topk_hit"]
+        call = self._lib.hyprec_eval_topk_u8 if hit is not None and hit.dtype == numpy.uint8 else self._lib.hyprec_eval_topk
+        self._check(call(
             self._h, user_lo, user_hi, _ptr(cand_indptr), _ptr(cand_ids), int(capacity), _ptr(out["thresholds"]),
-            _ptr(out["ones_per_row"]), _ptr(out["topk_idx"]), _ptr(out["topk_val"]), _ptr(out["topk_hit"]),
+            _ptr(out["ones_per_row"]), _ptr(out["topk_idx"]), _ptr(out["topk_val"]), _ptr(hit),
             _ptr(out["train_flags"]), _ptr(out["test_flags"])))
         return out
 

@@ -28,6 +28,7 @@ gathers the per-user integers, and every rank ends up with identical factors and
 """
 import os
 import time
+import zlib
 
 import numpy
 import scipy.sparse as sp
@@ -64,6 +65,11 @@ def _csr_triplet(matrix):
     csr.eliminate_zeros()
     csr.sort_indices()
     return csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
+
+
+def _crc_pool():
+    from hyprec_b200.evaluator import host_pool
+    return host_pool()
 
 
 class CollaborativeFiltering(AbstractRecommender):
@@ -149,6 +155,10 @@ class CollaborativeFiltering(AbstractRecommender):
             self._handle.close()
             self._handle = None
             self._train_uploaded = self._eval_uploaded = self._sync_token = self._cands_uploaded = None
+        pool = self.__dict__.pop('_ahead_pool', None)
+        if pool is not None:
+            pool.shutdown(wait=True)
+        self._cands_ready = None
 
     def set_data(self, train_data, test_data):
         AbstractRecommender.set_data(self, train_data, test_data)
@@ -210,6 +220,11 @@ class CollaborativeFiltering(AbstractRecommender):
             full = self._host_csr(self.ratings)
             test = self._host_csr(self.test_data)
             h.set_eval_csr(full, test)
+            # hit values (rating x rounded prediction) fit one byte when the ratings are small integers -- the
+            # reference's data is 0 / 1 -- and then travel that way (hyprec_eval_topk_u8)
+            values = full[2]
+            self._hits_u8 = bool(len(values) == 0 or (values.min() >= 0 and values.max() <= 255 and
+                                                      numpy.array_equal(values, numpy.floor(values))))
             self._test_nnz = len(test[1])
             self._test_pattern = (test[0], test[1])      # order of the device's test flags
             self._eval_uploaded = key
@@ -217,22 +232,25 @@ class CollaborativeFiltering(AbstractRecommender):
 
     @staticmethod
     def _fingerprint(user_vecs, item_vecs):
-        """Witness that the host factor arrays still hold what the device holds: a CRC-32 of the whole buffer
-        (position-sensitive) plus the xor of all 64-bit patterns, so an in-place edit anywhere -- an external als_step
-        loop, SDAE writing rows, a row permutation -- is noticed and the factors are uploaded again (~10 ms for 36 MB;
-        the sampled witness of round 1 missed edits between its ~500 probes)."""
-        import zlib
-
-        def full(a):
+        """Witness that the host factor arrays still hold what the device holds: CRC-32s of the whole buffer in 4 MB
+        pieces (position-sensitive), so an in-place edit anywhere -- an external als_step loop, SDAE writing rows, a row
+        permutation -- is noticed and the factors are uploaded again (the sampled witness of round 1 missed edits
+        between its ~500 probes).  The pieces are checksummed on a few threads (zlib releases the GIL): ~2 ms for the
+        36 MB of the citeulike-a factors instead of ~9."""
+        def pieces(a):
             a = numpy.asarray(a)
             if not a.flags.c_contiguous:
                 a = numpy.ascontiguousarray(a)
-            if a.size == 0:
-                return 0, 0, a.shape, a.dtype.str
-            raw = a.reshape(-1).view(numpy.uint8)
-            fold = a.reshape(-1).view(numpy.uint64) if a.dtype.itemsize == 8 else raw
-            return zlib.crc32(memoryview(raw)), int(numpy.bitwise_xor.reduce(fold)), a.shape, a.dtype.str
-        return full(user_vecs), full(item_vecs)
+            raw = memoryview(a.reshape(-1).view(numpy.uint8)) if a.size else memoryview(b"")
+            step = 4 << 20
+            return (a.shape, a.dtype.str), [raw[at:at + step] for at in range(0, len(raw), step)]
+        (head_u, chunks_u), (head_v, chunks_v) = pieces(user_vecs), pieces(item_vecs)
+        chunks = chunks_u + chunks_v
+        if len(chunks) > 2:
+            sums = list(_crc_pool().map(zlib.crc32, chunks))
+        else:
+            sums = [zlib.crc32(c) for c in chunks]
+        return head_u, head_v, tuple(sums)
 
     def _upload_factors(self, force=False):
         h = self._upload_train()
@@ -308,12 +326,40 @@ class CollaborativeFiltering(AbstractRecommender):
     def train_k_fold(self, item_vecs=None):
         """collaborative_filtering.py:147-161."""
         all_errors = []
+        ahead = None
         for current_k in range(self.k_folds):
-            self.set_data(*self.evaluator.get_fold(current_k, self.fold_test_indices))
+            data = ahead.result() if ahead is not None else self.evaluator.get_fold(current_k, self.fold_test_indices)
+            ahead = self._prepare_ahead(current_k + 1) if current_k + 1 < self.k_folds else None
+            self.set_data(*data)
             self.hyperparameters['fold'] = current_k
             all_errors.append(self.train_one_fold(item_vecs))
             self.predictions = None
         return numpy.mean(all_errors, axis=0)
+
+    def _prepare_ahead(self, fold):
+        """Host work of fold ``fold`` that depends on nothing the current fold computes -- its train / test matrices
+        (evaluator.py:120-134, 197-213) and the candidate streams its report will rank -- done on a host thread while
+        the current fold's epochs and report run on the device (the library calls release the GIL).  Nothing here
+        touches the numpy.random stream: the initial draws stay on the caller's thread, in the reference's order.
+        Returns a future of get_fold's (train, test), or None when prefetching is off (HYPREC_PREFETCH=0) or the
+        evaluator is not this package's."""
+        if os.environ.get("HYPREC_PREFETCH", "1") == "0" or not hasattr(self.evaluator, 'candidate_lists') \
+                or getattr(self.evaluator, 'hashed_candidates', None) is not None:
+            return None
+        if not sp.issparse(self.ratings) and 16 * self.n_users * self.n_items > (4 << 30):
+            return None                     # two more dense users x items matrices alive at once: not worth the memory
+        lists = self.fold_test_indices
+
+        def work():
+            data = self.evaluator.get_fold(fold, lists)
+            if self.evaluator.test_indices is lists and self._world()[1] == 1:
+                self._cands_ready = (lists, fold, self.evaluator.candidate_lists(fold))
+            return data
+        from concurrent.futures import ThreadPoolExecutor
+        pool = self.__dict__.get('_ahead_pool')
+        if pool is None:
+            pool = self._ahead_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="hyprec-fold")
+        return pool.submit(work)
 
     def train_one_fold(self, item_vecs=None):
         """collaborative_filtering.py:164-212: initialise (random / theta / checkpoint), train,
@@ -519,6 +565,10 @@ class CollaborativeFiltering(AbstractRecommender):
         ``evaluator.test_indices[user * (1 + fold)]`` cast to int (evaluator.py:225-228; SURVEY.md
         App. A Q6 / Q7 describe what that slot holds for k-fold and naive splits)."""
         if hasattr(self.evaluator, 'candidate_lists'):         # hyprec_b200.Evaluator (dense or sparse test_indices)
+            ready = self.__dict__.get('_cands_ready')
+            if ready is not None and ready[0] is self.evaluator.test_indices and ready[1] == fold:
+                self._cands_ready = None                        # gathered while the previous fold was on the device
+                return ready[2]
             return self.evaluator.candidate_lists(fold)
         rows = [numpy.asarray(self.evaluator.test_indices[user * (1 + fold)]).astype(numpy.int64)
                 for user in range(self.n_users)]
@@ -695,10 +745,13 @@ class CollaborativeFiltering(AbstractRecommender):
                 out = self._eval_blocks(h, 0, self.n_users, hashed[0])
             else:
                 out = h.eval_topk(self.n_recommendations, None, None, 0, self.n_users,
-                                  n_train_nz=self._train_nnz, n_test_nz=self._test_nnz)
+                                  n_train_nz=self._train_nnz, n_test_nz=self._test_nnz,
+                                  compact=getattr(self, '_hits_u8', False))
         else:
             out = self._eval_sharded(h, rank, world, fold)
         rmse = h.rmse()
+        if out["topk_hit"].dtype != numpy.float64:      # one byte per hit on the wire; the metric arithmetic is float64
+            out["topk_hit"] = out["topk_hit"].astype(numpy.float64)
 
         lengths = (out["topk_idx"] >= 0).sum(axis=1)
         recs = [row[:n].tolist() for row, n in zip(out["topk_idx"], lengths)]

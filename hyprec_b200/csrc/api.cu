@@ -122,7 +122,8 @@ struct EngineBase {
     virtual int rmse_terms(double* out3, bool shard_only) = 0;
     virtual int predict_dense(double* out) = 0;
     virtual int eval_topk(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci, int cap, double* thr,
-                          int64_t* ones, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) = 0;
+                          int64_t* ones, int32_t* tidx, double* tval, double* thit, uint8_t* thit8, uint8_t* trf,
+                          uint8_t* tef) = 0;
     virtual int device_factors(void** u, void** v, int* elem) = 0;
     virtual int set_candidates(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci) = 0;
     virtual int set_hashed_candidates(int fold, int n_folds, unsigned long long seed) = 0;
@@ -257,13 +258,15 @@ struct Engine : EngineBase {
     DevBuf a_scratch_slot[8];
     static constexpr int kStatusSlot = 15;
     static constexpr int kHeavyStream = 6;   // aux streams 0..5: degree buckets, 6: rows above the cap
+    bool hits_u8_exact = true;     // every rating an integer in 0..255: hit values fit one byte (hyprec_eval_topk_u8)
+    DevBuf out_hit8;
     DevBuf cand_ptr, cand_ids, out_idx, out_val, out_hit, counts, flags, dense_blk, topk_spill, rows_idx, rows_out;
 
     explicit Engine(hyprec_ctx* ctx) : h(ctx) {}
     ~Engine() override {
         DevBuf* all[] = {&U, &V, &prior, &gram[0], &gram[1], &gram_partial, &base, &colsum, &colsum_partial,
                          &thresholds, &row_s1, &row_s2, &scalars, &counter, &cand_ptr,
-                         &cand_ids, &out_idx, &out_val, &out_hit, &counts, &flags, &dense_blk, &tiles, &linv,
+                         &cand_ids, &out_idx, &out_val, &out_hit, &out_hit8, &counts, &flags, &dense_blk, &tiles, &linv,
                          &linv_t, &qmat, &pq, &ymat, &dummy_ptr, &dummy_out, &prof_buf, &bdense, &lfac, &blk_tmp, &blk_base, &fixed_d, &gram_partial_d, &gram_dbuf, &linv_f, &linv_t_f, &stage_d, &w_hi, &w_lo, &l_hi, &l_lo, &cross, &plan[0].lists, &plan[1].lists,
                          &a_scratch_slot[0], &a_scratch_slot[1], &a_scratch_slot[2], &a_scratch_slot[3],
                          &a_scratch_slot[4], &a_scratch_slot[5], &a_scratch_slot[6], &a_scratch_slot[7],
@@ -353,7 +356,11 @@ struct Engine : EngineBase {
         if (full.nnz > 0) {
             HY_TRY(full.values.reserve(sizeof(double) * full.nnz));
             std::vector<double> vals(full.nnz);
-            for (int64_t e = 0; e < full.nnz; ++e) vals[e] = fv ? fv[e] : 1.0;
+            hits_u8_exact = true;
+            for (int64_t e = 0; e < full.nnz; ++e) {
+                vals[e] = fv ? fv[e] : 1.0;
+                if (!(vals[e] >= 0.0 && vals[e] <= 255.0 && vals[e] == (double)(uint8_t)vals[e])) hits_u8_exact = false;
+            }
             CU_TRY(cudaMemcpyAsync(full.values.ptr, vals.data(), sizeof(double) * full.nnz, cudaMemcpyHostToDevice, h->stream));
             CU_TRY(cudaStreamSynchronize(h->stream));
         }
@@ -2301,11 +2308,15 @@ struct Engine : EngineBase {
     }
 
     int eval_topk(int64_t lo, int64_t hi, const int64_t* cp, const int32_t* ci, int cap, double* thr_out,
-                  int64_t* ones_out, int32_t* tidx, double* tval, double* thit, uint8_t* trf, uint8_t* tef) override {
+                  int64_t* ones_out, int32_t* tidx, double* tval, double* thit, uint8_t* thit8, uint8_t* trf,
+                  uint8_t* tef) override {
         if (k == 0) return fail(HYPREC_E_INVALID, "eval_topk before set_factors");
         if (lo < 0 || hi > m || lo > hi) return fail(HYPREC_E_INVALID, "eval_topk: user range outside the matrix");
         const int64_t nu = hi - lo;
-        const bool want_topk = tidx || tval || thit;
+        const bool want_topk = tidx || tval || thit || thit8;
+        if (thit8 && !hits_u8_exact)
+            return fail(HYPREC_E_UNSUPPORTED, "eval_topk: one-byte hit values need ratings that are integers in 0..255 "
+                                              "(hit = rating x rounded prediction, evaluator.py:287-288); ask for the float64 hits");
         if (want_topk && (cap <= 0 || cap > 4096)) return fail(HYPREC_E_UNSUPPORTED, "capacity must be in [1, 4096]");
         if (ci && !cp) return fail(HYPREC_E_INVALID, "eval_topk: candidate ids without indptr");
         if (cp && !ci) return fail(HYPREC_E_INVALID, "eval_topk: candidate indptr without ids");
@@ -2508,6 +2519,16 @@ struct Engine : EngineBase {
             if (tidx) CU_TRY(cudaMemcpyAsync(tidx, out_idx.ptr, sizeof(int32_t) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
             if (tval) CU_TRY(cudaMemcpyAsync(tval, out_val.ptr, sizeof(double) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
             if (thit) CU_TRY(cudaMemcpyAsync(thit, out_hit.ptr, sizeof(double) * (size_t)nu * cap, cudaMemcpyDeviceToHost, h->stream));
+            if (thit8) {
+                // the same hit values, one byte each: 1/8 of the device -> host bytes of the float64 form
+                const size_t count = (size_t)nu * cap;
+                HY_TRY(out_hit8.reserve(count));
+                hyprec::cast_kernel<double, uint8_t><<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(
+                    out_hit.as<double>(), (int64_t)count, out_hit8.as<uint8_t>());
+                h->launches += 1;
+                CU_TRY(cudaGetLastError());
+                CU_TRY(cudaMemcpyAsync(thit8, out_hit8.ptr, count, cudaMemcpyDeviceToHost, h->stream));
+            }
         }
 
         // rounded predictions at train / test non-zeros
@@ -2794,7 +2815,16 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
                      uint8_t* test_flags) {
     HY_TRY(check(h));
     return h->engine->eval_topk(user_lo, user_hi, cand_indptr, cand_ids, capacity, thresholds, ones_per_row,
-                                topk_idx, topk_val, topk_hit, train_flags, test_flags);
+                                topk_idx, topk_val, topk_hit, nullptr, train_flags, test_flags);
+}
+
+int hyprec_eval_topk_u8(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
+                        const int32_t* cand_ids, int capacity, double* thresholds, int64_t* ones_per_row,
+                        int32_t* topk_idx, double* topk_val, uint8_t* topk_hit, uint8_t* train_flags,
+                        uint8_t* test_flags) {
+    HY_TRY(check(h));
+    return h->engine->eval_topk(user_lo, user_hi, cand_indptr, cand_ids, capacity, thresholds, ones_per_row,
+                                topk_idx, topk_val, nullptr, topk_hit, train_flags, test_flags);
 }
 
 int hyprec_kernel_ms(hyprec_t* h, int which, double* total_ms, int64_t* calls, double* last_ms) {
@@ -2921,6 +2951,13 @@ int hyprec_flush_l2(hyprec_t* h) {
     CU_TRY(cudaMemsetAsync(h->flush_buf, 0x5a, h->flush_bytes, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     return HYPREC_OK;
+}
+
+int64_t hyprec_host_count_nonzero(const double* x, int64_t count) {
+    int64_t c = 0;
+    if (x)
+        for (int64_t i = 0; i < count; ++i) c += (x[i] != 0.0);
+    return c;
 }
 
 int hyprec_host_kfold_lists(uint32_t* mt_key, int* mt_pos, int64_t n_users, int64_t n_items, int k_folds,

@@ -198,6 +198,14 @@ int hyprec_eval_topk(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_
                      const int32_t* cand_ids, int capacity, double* thresholds,
                      int64_t* ones_per_row, int32_t* topk_idx, double* topk_val, double* topk_hit,
                      uint8_t* train_flags, uint8_t* test_flags);
+/* The same call with the hit values as ONE byte per list entry instead of a float64: for a top-200 report at the
+ * citeulike-a shape the results shrink from 58.5 MB (ids + float64 scores + float64 hits) to 5.6 MB when topk_val is
+ * NULL as well, and the device -> host copy is most of the end-to-end evaluation time.  Exact when every rating is an
+ * integer in 0..255 (the reference's data is 0 / 1, util/data_parser.py:111-115); HYPREC_E_UNSUPPORTED otherwise. */
+int hyprec_eval_topk_u8(hyprec_t* h, int64_t user_lo, int64_t user_hi, const int64_t* cand_indptr,
+                        const int32_t* cand_ids, int capacity, double* thresholds,
+                        int64_t* ones_per_row, int32_t* topk_idx, double* topk_val, uint8_t* topk_hit,
+                        uint8_t* train_flags, uint8_t* test_flags);
 
 /* Diagnostics of the most recent hyprec_eval_topk: out8 = { top-k fed by sweep survivors (1) or by exact scoring of
  * every candidate (0), users of that call that fell back to exact scoring, cells the rounded-count sweep re-checked
@@ -251,6 +259,9 @@ int hyprec_flush_l2(hyprec_t* h);
  * hold (n_users * k_folds * (n_items / k_folds) always suffices).  HYPREC_E_UNSUPPORTED, with the generator state
  * untouched, when a list would need the reference's negative slice bounds (a fold's positives outnumber
  * n_items / k_folds): the caller then runs the reference's loop. */
+/* Number of non-zero entries of a float64 buffer (no device involved; callers scan row blocks of a dense users x items
+ * matrix on several host threads -- the check that a fold matrix still holds exactly the recorded ratings). */
+int64_t hyprec_host_count_nonzero(const double* x, int64_t count);
 int hyprec_host_kfold_lists(uint32_t* mt_key, int* mt_pos, int64_t n_users, int64_t n_items, int k_folds,
                             const int64_t* indptr, const int32_t* indices, int64_t capacity, int64_t* slot_ptr,
                             int64_t* slot_positives, int64_t* ids64, int32_t* ids32);

@@ -211,3 +211,44 @@ def test_hashed_candidates_equal_explicit_lists():
         assert not numpy.array_equal(everything["topk_idx"], want["topk_idx"])
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_one_byte_hits_equal_the_float64_hits(precision):
+    """hyprec_eval_topk_u8: the hit values as one byte each (and no score array) are the float64 call's, for both the
+    fused top-k and a reused output dict; ratings that do not fit a byte are refused, not truncated."""
+    from hyprec_b200 import _native as native
+    from test_gpu_parity import make_handle, synthetic
+    m, n, k = 70, 900, 24
+    full, train, test, u0, v0, cands = synthetic(m, n, k, 6000, seed=8)
+    cp = numpy.zeros(m + 1, numpy.int64)
+    cp[1:] = numpy.cumsum([len(c) for c in cands])
+    ids = numpy.concatenate(cands).astype(numpy.int32)
+    h, _ = make_handle(native, train, precision)
+    try:
+        h.set_eval_csr((full.indptr, full.indices, full.data), (test.indptr, test.indices, test.data))
+        h.set_factors(u0, v0)
+        h.als_half_step(native.SIDE_USER, 0.01)
+        h.als_half_step(native.SIDE_ITEM, 0.01)
+        want = h.eval_topk(40, cp, ids, n_train_nz=train.nnz, n_test_nz=test.nnz)
+        got = h.eval_topk(40, cp, ids, n_train_nz=train.nnz, n_test_nz=test.nnz, compact=True)
+        assert got["topk_val"] is None and got["topk_hit"].dtype == numpy.uint8
+        assert want["topk_hit"].max() == 1.0
+        for key in ("topk_idx", "thresholds", "ones_per_row", "train_flags", "test_flags"):
+            assert numpy.array_equal(got[key], want[key]), key
+        assert numpy.array_equal(got["topk_hit"].astype(numpy.float64), want["topk_hit"])
+        got["topk_hit"][...] = 7
+        again = h.eval_topk(40, cp, ids, out=got)                               # reused arrays keep the compact call
+        assert again is got and numpy.array_equal(got["topk_hit"].astype(numpy.float64), want["topk_hit"])
+        part = h.eval_topk(40, cp[11:31] - cp[11], ids[cp[11]:cp[30]], 11, 30, want_counts=False, compact=True)
+        assert numpy.array_equal(part["topk_hit"], got["topk_hit"][11:30])
+        odd = full.data.copy()
+        odd[3] = 2.5
+        h.set_eval_csr((full.indptr, full.indices, odd), (test.indptr, test.indices, test.data))
+        with pytest.raises(native.HyprecError) as err:
+            h.eval_topk(40, cp, ids, compact=True)
+        assert err.value.code == -4
+        exact = h.eval_topk(40, cp, ids)                                          # the float64 form still serves them
+        assert exact["topk_hit"].max() in (1.0, 2.5)
+    finally:
+        h.close()

@@ -21,7 +21,7 @@ EXPORTS = [
     "hyprec_flush_l2", "hyprec_probe_fma_tflops", "hyprec_solve_phase_cycles", "hyprec_host_alloc", "hyprec_host_free",
     "hyprec_comm_blob_bytes", "hyprec_comm_export", "hyprec_comm_attach", "hyprec_comm_detach", "hyprec_comm_stats",
     "hyprec_init_factors_uniform", "hyprec_get_factor_rows", "hyprec_mark", "hyprec_elapsed_ms",
-    "hyprec_comm_arena", "hyprec_comm_attach_local", "hyprec_eval_stats", "hyprec_host_kfold_lists", "hyprec_host_count_nonzero",
+    "hyprec_comm_arena", "hyprec_comm_attach_local", "hyprec_eval_stats", "hyprec_host_kfold_lists", "hyprec_host_count_nonzero", "hyprec_host_naive_picks", "hyprec_host_row_counts", "hyprec_host_dense_to_csr",
 ]
 
 EPOCH_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
@@ -77,6 +77,9 @@ def load_library(rebuild=False):
     lib.hyprec_kernel_ms.argtypes = [vp, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]
     lib.hyprec_reset_kernel_ms.argtypes = [vp]
     lib.hyprec_flush_l2.argtypes = [vp]
+    lib.hyprec_host_naive_picks.argtypes = [vp, ctypes.POINTER(c_int), c_i64, vp, vp, vp]
+    lib.hyprec_host_row_counts.argtypes = [vp, c_i64, c_i64, vp]
+    lib.hyprec_host_dense_to_csr.argtypes = [vp, c_i64, c_i64, vp, vp, vp]
     lib.hyprec_host_count_nonzero.argtypes = [vp, c_i64]
     lib.hyprec_host_count_nonzero.restype = c_i64
     lib.hyprec_host_kfold_lists.argtypes = [vp, ctypes.POINTER(c_int), c_i64, c_i64, c_int, vp, vp, c_i64, vp, vp, vp, vp]
@@ -112,6 +115,52 @@ def _as(array, dtype):
 def host_count_nonzero(block):
     """Non-zeros of a C-contiguous float64 array through the library (the call releases the GIL)."""
     return load_library().hyprec_host_count_nonzero(_ptr(block), int(block.size))
+
+
+def host_dense_to_csr(matrix, pool):
+    """(indptr int64, indices int32, values float64) of a C-contiguous float64 matrix: row blocks scanned by the
+    library's host code on the threads of `pool` (the calls release the GIL)."""
+    lib = load_library()
+    rows, cols = matrix.shape
+    step = max(1, -(-rows // 32))
+    blocks = [(at, min(rows, at + step)) for at in range(0, rows, step)]
+    counts = numpy.zeros(rows, dtype=numpy.int64)
+
+    def count(block):
+        return lib.hyprec_host_row_counts(_ptr(matrix[block[0]:block[1]]), block[1] - block[0], cols, _ptr(counts[block[0]:block[1]]))
+    if any(code != 0 for code in pool.map(count, blocks)):
+        raise HyprecError(-1, lib.hyprec_last_error().decode("utf-8", "replace"))
+    indptr = numpy.zeros(rows + 1, dtype=numpy.int64)
+    numpy.cumsum(counts, out=indptr[1:])
+    indices = numpy.empty(int(indptr[-1]), dtype=numpy.int32)
+    values = numpy.empty(int(indptr[-1]), dtype=numpy.float64)
+
+    def fill(block):
+        return lib.hyprec_host_dense_to_csr(_ptr(matrix[block[0]:block[1]]), block[1] - block[0], cols,
+                                            _ptr(indptr[block[0]:block[1] + 1]), _ptr(indices), _ptr(values))
+    if any(code != 0 for code in pool.map(fill, blocks)):
+        raise HyprecError(-1, lib.hyprec_last_error().decode("utf-8", "replace"))
+    return indptr, indices, values
+
+
+def host_naive_picks(indptr, sizes):
+    """CSR entry numbers Evaluator.naive_split_users samples (lib/evaluator.py:92-93: one numpy.random.choice with
+    replacement per user), drawn from -- and advancing -- numpy's global legacy stream.  None when that stream is not
+    MT19937."""
+    lib = load_library()
+    state = numpy.random.get_state()
+    if state[0] != 'MT19937':
+        return None
+    key = numpy.ascontiguousarray(state[1], dtype=numpy.uint32).copy()
+    pos = ctypes.c_int(int(state[2]))
+    indptr = numpy.ascontiguousarray(indptr, dtype=numpy.int64)
+    sizes = numpy.ascontiguousarray(sizes, dtype=numpy.int64)
+    picks = numpy.empty(int(sizes.sum()), dtype=numpy.int64)
+    code = lib.hyprec_host_naive_picks(_ptr(key), ctypes.byref(pos), len(indptr) - 1, _ptr(indptr), _ptr(sizes), _ptr(picks))
+    if code != 0:
+        raise HyprecError(code, lib.hyprec_last_error().decode("utf-8", "replace"))
+    numpy.random.set_state((state[0], key, int(pos.value), state[3], state[4]))
+    return picks
 
 
 def host_kfold_lists(indptr, indices, n_users, n_items, k_folds):

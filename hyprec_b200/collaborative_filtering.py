@@ -60,10 +60,13 @@ DENSE_PREDICTIONS_LIMIT_BYTES = int(os.environ.get("HYPREC_DENSE_LIMIT_BYTES", 8
 def _csr_triplet(matrix):
     """(indptr int64, indices int32, values float64) of a dense or scipy-sparse matrix, zeros
     dropped, column ids sorted."""
-    csr = matrix if sp.issparse(matrix) else sp.csr_matrix(numpy.asarray(matrix, dtype=numpy.float64))
-    csr = sp.csr_matrix(csr, dtype=numpy.float64)
-    csr.eliminate_zeros()
-    csr.sort_indices()
+    if sp.issparse(matrix):
+        csr = sp.csr_matrix(matrix, dtype=numpy.float64)
+        csr.eliminate_zeros()
+        csr.sort_indices()
+    else:
+        from hyprec_b200.evaluator import dense_to_csr
+        csr = dense_to_csr(numpy.asarray(matrix, dtype=numpy.float64))
     return csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32), csr.data.astype(numpy.float64)
 
 

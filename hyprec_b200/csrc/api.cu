@@ -2953,6 +2953,50 @@ int hyprec_flush_l2(hyprec_t* h) {
     return HYPREC_OK;
 }
 
+int hyprec_host_naive_picks(uint32_t* mt_key, int* mt_pos, int64_t n_users, const int64_t* indptr, const int64_t* sizes,
+                            int64_t* picks) {
+    if (!mt_key || !mt_pos || !indptr || !sizes || !picks) return fail(HYPREC_E_INVALID, "host_naive_picks: null argument");
+    if (n_users < 0 || *mt_pos < 0 || *mt_pos > 624) return fail(HYPREC_E_INVALID, "host_naive_picks: bad sizes or generator position");
+    for (int64_t u = 0; u < n_users; ++u) {
+        const int64_t len = indptr[u + 1] - indptr[u];
+        if (len < 0 || len >= ((int64_t)1 << 32) || sizes[u] < 0 || (len == 0 && sizes[u] != 0))
+            return fail(HYPREC_E_INVALID, "host_naive_picks: bad row length or sample size");
+    }
+    hyprec_host::naive_picks(mt_key, mt_pos, n_users, indptr, sizes, picks);
+    return HYPREC_OK;
+}
+
+int hyprec_host_dense_to_csr(const double* x, int64_t rows, int64_t cols, const int64_t* indptr, int32_t* indices,
+                             double* values) {
+    if (!x || !indptr || !indices || !values || rows < 0 || cols < 0 || cols >= ((int64_t)1 << 31))
+        return fail(HYPREC_E_INVALID, "host_dense_to_csr: bad argument");
+    for (int64_t r = 0; r < rows; ++r) {
+        const double* row = x + r * cols;
+        int64_t at = indptr[r];
+        const int64_t end = indptr[r + 1];
+        for (int64_t c = 0; c < cols; ++c)
+            if (row[c] != 0.0) {
+                if (at >= end) return fail(HYPREC_E_INVALID, "host_dense_to_csr: more non-zeros than indptr allows");
+                indices[at] = (int32_t)c;
+                values[at] = row[c];
+                ++at;
+            }
+        if (at != end) return fail(HYPREC_E_INVALID, "host_dense_to_csr: fewer non-zeros than indptr says");
+    }
+    return HYPREC_OK;
+}
+
+int hyprec_host_row_counts(const double* x, int64_t rows, int64_t cols, int64_t* counts) {
+    if (!x || !counts || rows < 0 || cols < 0) return fail(HYPREC_E_INVALID, "host_row_counts: bad argument");
+    for (int64_t r = 0; r < rows; ++r) {
+        const double* row = x + r * cols;
+        int64_t c = 0;
+        for (int64_t j = 0; j < cols; ++j) c += (row[j] != 0.0);
+        counts[r] = c;
+    }
+    return HYPREC_OK;
+}
+
 int64_t hyprec_host_count_nonzero(const double* x, int64_t count) {
     int64_t c = 0;
     if (x)

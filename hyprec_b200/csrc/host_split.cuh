@@ -171,4 +171,20 @@ static int kfold_lists(uint32_t* key, int* pos_io, int64_t n_users, int64_t n_it
     return 0;
 }
 
+// The draws of Evaluator.naive_split_users (evaluator.py:92-93): per user, in user order,
+// numpy.random.choice(non_zeros, size) = `size` legacy randint(0, len) values, i.e. masked rejection draws below
+// len - 1 (no draw at all when the user has a single rating).  picks[] receives the CSR entry numbers drawn
+// (with repeats: the reference samples with replacement), user after user; sizes[u] entries each.
+static void naive_picks(uint32_t* key, int* pos_io, int64_t n_users, const int64_t* indptr, const int64_t* sizes,
+                        int64_t* picks) {
+    Mt19937 rng{key, *pos_io};
+    int64_t at = 0;
+    for (int64_t user = 0; user < n_users; ++user) {
+        const int64_t len = indptr[user + 1] - indptr[user];
+        for (int64_t i = 0; i < sizes[user]; ++i)
+            picks[at++] = indptr[user] + (len > 1 ? (int64_t)rng.interval((uint32_t)(len - 1)) : 0);
+    }
+    *pos_io = rng.pos;
+}
+
 }  // namespace hyprec_host

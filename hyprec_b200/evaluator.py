@@ -59,6 +59,23 @@ def count_nonzero(matrix):
     return int(sum(host_pool().map(_native.host_count_nonzero, [matrix[at:at + step] for at in range(0, rows, step)])))
 
 
+def dense_to_csr(matrix):
+    """scipy CSR (float64, no stored zeros, sorted column ids) of a dense users x items array.  Large float64 arrays
+    are scanned by the library's host code on the host threads (numpy's nonzero(): 0.42 s per citeulike-a matrix)."""
+    matrix = numpy.asarray(matrix)
+    if matrix.ndim == 2 and matrix.size >= (1 << 22) and matrix.dtype == numpy.float64 and matrix.flags.c_contiguous:
+        try:
+            from hyprec_b200 import _native
+            indptr, indices, values = _native.host_dense_to_csr(matrix, host_pool())
+            return sp.csr_matrix((values, indices, indptr), shape=matrix.shape)
+        except (RuntimeError, OSError, AttributeError):
+            pass
+    csr = sp.csr_matrix(matrix, dtype=numpy.float64)
+    csr.eliminate_zeros()
+    csr.sort_indices()
+    return csr
+
+
 class Evaluator(object):
     def __init__(self, ratings, abstracts_preprocessor=None, random_seed=False, verbose=False):
         self.sparse = sp.issparse(ratings)
@@ -101,10 +118,7 @@ class Evaluator(object):
         if self.sparse:
             return self.ratings
         if self._ratings_csr is None:
-            csr = sp.csr_matrix(self.ratings, dtype=numpy.float64)
-            csr.eliminate_zeros()
-            csr.sort_indices()
-            self._ratings_csr = csr
+            self._ratings_csr = dense_to_csr(self.ratings)
         return self._ratings_csr
 
     def set_kfolds(self, kfolds):
@@ -121,6 +135,23 @@ class Evaluator(object):
         if self.random_seed is False:
             numpy.random.seed(42)
         csr = self.ratings_csr()
+        picks = self._native_naive_picks(csr)
+        if picks is not None:
+            # every draw of the loop below, made by the library's host code; the cells follow by indexing
+            rows_of = numpy.repeat(numpy.arange(self.n_users, dtype=numpy.int64), numpy.diff(csr.indptr))
+            test_keys = rows_of[picks] * self.n_items + csr.indices[picks].astype(numpy.int64)
+            if self.sparse:
+                train, test = self._split_sparse(test_keys)
+                self.test_indices = test
+                return train, test
+            rows, cols = rows_of[picks], csr.indices[picks]
+            test = numpy.zeros(self.ratings.shape)
+            train = self.ratings.copy()
+            train[rows, cols] = 0.
+            test[rows, cols] = csr.data[picks]
+            self.test_indices = test
+            self._remember_csr(train, test, test_keys)
+            return train, test
         keys = []
         if self.sparse:
             for user in range(self.n_users):
@@ -142,6 +173,21 @@ class Evaluator(object):
         self.test_indices = test
         self._remember_csr(train, test, numpy.concatenate(keys) if keys else numpy.zeros(0, dtype=numpy.int64))
         return train, test
+
+    def _native_naive_picks(self, csr):
+        """CSR entry numbers of every cell the naive split samples (csrc/host_split.cuh: the per-user
+        numpy.random.choice calls of evaluator.py:92-93 restated in C++, same stream, same draws), or None when it does
+        not apply (HYPREC_NATIVE_SPLIT=0, library not built)."""
+        if os.environ.get("HYPREC_NATIVE_SPLIT", "1") == "0" or self.n_users == 0:
+            return None
+        lengths = numpy.diff(csr.indptr).astype(numpy.int64)
+        sizes = numpy.array([int(self.test_percentage * int(n)) for n in numpy.unique(lengths)], dtype=numpy.int64)
+        sizes = sizes[numpy.searchsorted(numpy.unique(lengths), lengths)]        # int(p * len), evaluator.py:93
+        try:
+            from hyprec_b200 import _native
+            return _native.host_naive_picks(csr.indptr, sizes)
+        except (RuntimeError, OSError, AttributeError):
+            return None
 
     def naive_split_items(self):
         if self.random_seed is False:

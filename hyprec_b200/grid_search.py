@@ -47,9 +47,20 @@ def _cell_keys(indptr, indices, n_items):
 
 class CellSet(object):
     """The non-zero cells of a users x items matrix as sorted ``row * n_items + col`` keys, with the denominator
-    ``sum(sum(matrix))`` of evaluator.py:266.  Built once per sweep for the matrices every model is judged on."""
+    ``sum(sum(matrix))`` of evaluator.py:266.  Built once per sweep for the matrices every model is judged on --
+    from the evaluator's CSR view of the matrix when it has one (``triplet``: no scan of the dense array)."""
 
-    def __init__(self, matrix):
+    def __init__(self, matrix, triplet=None):
+        self._lookup = None                       # ((pattern arrays), positions) of the latest flags_at
+        if triplet is not None:
+            indptr, indices, values = triplet
+            self.n_items = matrix.shape[1]
+            self.keys = _cell_keys(indptr, indices, self.n_items)
+            # sum(sum(matrix)): column sums accumulated row by row, then added up column by column, in float64 --
+            # bincount adds a column's entries in CSR (= row) order, and the zeros of the dense rows add nothing
+            column_sums = numpy.bincount(numpy.asarray(indices, dtype=numpy.int64), weights=values, minlength=self.n_items)
+            self.total = sum(column_sums) if len(indices) else sum(numpy.zeros(self.n_items))
+            return
         matrix = numpy.asarray(matrix)
         self.n_items = matrix.shape[1]
         rows, cols = numpy.nonzero(matrix)
@@ -59,22 +70,31 @@ class CellSet(object):
 
 def flags_at(cells, train_pattern, train_flags, test_pattern, test_flags):
     """Rounded predictions (0/1) at the cells of ``cells`` (a CellSet or a matrix), looked up among the cells the
-    device reported (the train and the test positives).  Returns None when some cell was not reported."""
+    device reported (the train and the test positives).  Returns None when some cell was not reported.
+    Where a CellSet's cells sit among the reported ones depends on the two patterns only, which every model of a
+    sweep shares: the positions are computed once per CellSet and pattern pair."""
     if not isinstance(cells, CellSet):
         cells = CellSet(cells)
-    keys = numpy.concatenate([_cell_keys(train_pattern[0], train_pattern[1], cells.n_items),
-                              _cell_keys(test_pattern[0], test_pattern[1], cells.n_items)])
     flags = numpy.concatenate([numpy.asarray(train_flags, dtype=numpy.uint8),
                                numpy.asarray(test_flags, dtype=numpy.uint8)])
+    known = cells._lookup
+    arrays = (train_pattern[0], train_pattern[1], test_pattern[0], test_pattern[1])
+    if known is not None and all(a is b for a, b in zip(known[0], arrays)):
+        return None if known[1] is None else flags[known[1]]
+    keys = numpy.concatenate([_cell_keys(train_pattern[0], train_pattern[1], cells.n_items),
+                              _cell_keys(test_pattern[0], test_pattern[1], cells.n_items)])
     order = numpy.argsort(keys, kind='stable')
-    keys, flags = keys[order], flags[order]
+    keys = keys[order]
     wanted = cells.keys
     if len(wanted) == 0:
         return numpy.zeros(0, dtype=numpy.uint8)
     pos = numpy.searchsorted(keys, wanted)
     if len(keys) == 0 or pos.max() >= len(keys) or not numpy.array_equal(keys[pos], wanted):
+        cells._lookup = (arrays, None)
         return None
-    return flags[pos]
+    where = order[pos]
+    cells._lookup = (arrays, where)
+    return flags[where]
 
 
 def recall_from_flags(cells, flags):
@@ -229,7 +249,9 @@ class GridSearch(object):
         rank, world = rec0._world() if hasattr(rec0, '_world') else (0, 1)
         with _RNG_LOCK:
             naive_train, naive_test = rec0.evaluator.naive_split(rec0._split_type)       # :59
-            shared = dict(split=None, last_state={}, cells=(CellSet(naive_test), CellSet(rec0.get_ratings())))
+            view = getattr(rec0.evaluator, 'csr_view', lambda matrix: None)
+            shared = dict(split=None, last_state={},
+                          cells=(CellSet(naive_test, view(naive_test)), CellSet(rec0.get_ratings(), view(rec0.get_ratings()))))
             if rec0.evaluator.random_seed is False:
                 shared['split'] = (naive_train, naive_test, numpy.random.get_state())
         mine = list(range(rank, len(combos), world))

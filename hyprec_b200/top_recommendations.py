@@ -108,22 +108,18 @@ def naive_split_recommendations(score0, score1, test_indptr, test_indices, test_
         return None
     total = min(int(capacity), int(n_items))
     ids = numpy.full((n_users, capacity), -1, dtype=numpy.int32)
-    for user in range(n_users):
+    test_indptr = numpy.asarray(test_indptr, dtype=numpy.int64)
+    rows = numpy.repeat(numpy.arange(n_users, dtype=numpy.int64), numpy.diff(test_indptr))
+    n1 = numpy.bincount(rows[casted == 1], minlength=n_users).astype(numpy.int64)     # ones in the user's test row
+    n0 = n_items - n1
+    slot = numpy.arange(total, dtype=numpy.int64)[None, :]
+    ones_first = (slot < numpy.minimum(total, n1)[:, None]).astype(numpy.int32)        # 1 ... 1 0 ... 0
+    zeros_first = (slot >= numpy.minimum(total, n0)[:, None]).astype(numpy.int32)      # 0 ... 0 1 ... 1
+    ids[:, :total] = numpy.where((score1 > score0)[:, None], ones_first, zeros_first)
+    for user in numpy.nonzero(~(score1 > score0) & ~(score1 < score0))[0]:    # (rare: e.g. all-zero factor rows)
         lo, hi = test_indptr[user], test_indptr[user + 1]
         ones_at = numpy.asarray(test_indices[lo:hi])[casted[lo:hi] == 1]
-        n1 = len(ones_at)
-        n0 = n_items - n1
-        s0, s1 = score0[user], score1[user]
-        if s1 > s0:
-            head = min(total, n1)
-            ids[user, :head] = 1
-            ids[user, head:total] = 0
-        elif s1 < s0:
-            head = min(total, n0)
-            ids[user, :head] = 0
-            ids[user, head:total] = 1
-        else:
-            first = numpy.zeros(total, dtype=numpy.int32)
-            first[ones_at[ones_at < total]] = 1
-            ids[user, :total] = first[::-1]
+        first = numpy.zeros(total, dtype=numpy.int32)
+        first[ones_at[ones_at < total]] = 1
+        ids[user, :total] = first[::-1]
     return ids, numpy.full(n_users, total, dtype=numpy.int64)

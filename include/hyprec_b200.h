@@ -259,6 +259,19 @@ int hyprec_flush_l2(hyprec_t* h);
  * hold (n_users * k_folds * (n_items / k_folds) always suffices).  HYPREC_E_UNSUPPORTED, with the generator state
  * untouched, when a list would need the reference's negative slice bounds (a fold's positives outnumber
  * n_items / k_folds): the caller then runs the reference's loop. */
+/* The draws of Evaluator.naive_split_users (lib/evaluator.py:92-93) from numpy's global MT19937 state (as above):
+ * per user, in user order, sizes[u] = int(test_percentage * len_u) samples WITH replacement among the user's len_u
+ * ratings (numpy.random.choice -> legacy randint: masked rejection draws; none when len_u == 1).  picks receives
+ * sum(sizes) CSR entry numbers (indptr[u] + position), user after user. */
+int hyprec_host_naive_picks(uint32_t* mt_key, int* mt_pos, int64_t n_users, const int64_t* indptr, const int64_t* sizes,
+                            int64_t* picks);
+/* CSR form of a dense row-major float64 users x items block without numpy's nonzero() scan (0.42 s per 754 MB
+ * matrix): hyprec_host_row_counts counts the non-zeros of every row, the caller turns the counts into indptr, and
+ * hyprec_host_dense_to_csr fills indices / values of rows [0, rows) at indptr[r] (indptr is the block's own slice of
+ * the matrix-wide array; indices / values are the matrix-wide arrays).  Callers run row blocks on several threads. */
+int hyprec_host_row_counts(const double* x, int64_t rows, int64_t cols, int64_t* counts);
+int hyprec_host_dense_to_csr(const double* x, int64_t rows, int64_t cols, const int64_t* indptr, int32_t* indices,
+                             double* values);
 /* Number of non-zero entries of a float64 buffer (no device involved; callers scan row blocks of a dense users x items
  * matrix on several host threads -- the check that a fold matrix still holds exactly the recorded ratings). */
 int64_t hyprec_host_count_nonzero(const double* x, int64_t count);

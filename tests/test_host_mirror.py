@@ -358,3 +358,34 @@ def test_native_kfold_lists_at_a_long_row(monkeypatch):
     train_py, test_py = py[4].get_fold(2, py[0])
     train_nat, test_nat = nat[4].get_fold(2, nat[0])
     assert numpy.array_equal(train_py, train_nat) and numpy.array_equal(test_py, test_nat)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_native_naive_split_equals_the_numpy_loop(monkeypatch, sparse):
+    """hyprec_host_naive_picks against the per-user numpy.random.choice calls it replaces (evaluator.py:92-93): same
+    train / test matrices and the same stream position, for several test percentages, users with one rating (no draw)
+    and users without any."""
+    import scipy.sparse as sp
+    rs = numpy.random.RandomState(3)
+    for trial in range(40):
+        m, n, k = rs.randint(1, 9), rs.randint(2, 70), rs.randint(1, 6)
+        dense = (rs.rand(m, n) < rs.rand() * 0.6).astype(float) * rs.randint(1, 4, size=(m, n))
+        if trial % 3 == 0:
+            dense[rs.randint(m)] = 0.0
+        if trial % 4 == 0:
+            dense[rs.randint(m)] = 0.0
+            dense[rs.randint(m), rs.randint(n)] = 1.0
+        got = []
+        for native in ("0", "1"):
+            monkeypatch.setenv("HYPREC_NATIVE_SPLIT", native)
+            ev = Evaluator(sp.csr_matrix(dense) if sparse else dense.copy())
+            ev.set_kfolds(k)
+            train, test = ev.naive_split()
+            after = numpy.random.random(3)
+            as_dense = (lambda x: numpy.asarray(x.todense())) if sparse else (lambda x: x)
+            got.append((as_dense(train), as_dense(test), after, ev.csr_view(train), ev.csr_view(test)))
+        py, nat = got
+        assert numpy.array_equal(py[0], nat[0]) and numpy.array_equal(py[1], nat[1])
+        assert numpy.array_equal(py[2], nat[2])
+        for a, b in zip(py[3] + py[4], nat[3] + nat[4]):
+            assert numpy.array_equal(a, b)

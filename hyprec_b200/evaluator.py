@@ -59,6 +59,18 @@ def count_nonzero(matrix):
     return int(sum(host_pool().map(_native.host_count_nonzero, [matrix[at:at + step] for at in range(0, rows, step)])))
 
 
+def dense_copy(matrix):
+    """numpy.array(matrix, dtype=float64) with the row blocks copied (and their fresh pages faulted in) on the host
+    threads: 0.21 s -> 0.035 s for a citeulike-a fold matrix."""
+    matrix = numpy.asarray(matrix)
+    if matrix.ndim != 2 or matrix.size < (1 << 22):
+        return numpy.array(matrix, dtype=numpy.float64)
+    out = numpy.empty(matrix.shape, dtype=numpy.float64)
+    step = -(-matrix.shape[0] // 16)
+    list(host_pool().map(lambda at: numpy.copyto(out[at:at + step], matrix[at:at + step]), range(0, matrix.shape[0], step)))
+    return out
+
+
 def dense_to_csr(matrix):
     """scipy CSR (float64, no stored zeros, sorted column ids) of a dense users x items array.  Large float64 arrays
     are scanned by the library's host code on the host threads (numpy's nonzero(): 0.42 s per citeulike-a matrix)."""
@@ -146,7 +158,7 @@ class Evaluator(object):
                 return train, test
             rows, cols = rows_of[picks], csr.indices[picks]
             test = numpy.zeros(self.ratings.shape)
-            train = self.ratings.copy()
+            train = dense_copy(self.ratings) if self.ratings.dtype == numpy.float64 else self.ratings.copy()
             train[rows, cols] = 0.
             test[rows, cols] = csr.data[picks]
             self.test_indices = test
@@ -295,7 +307,7 @@ class Evaluator(object):
         values = ratings[rows, cols]
         rated = values != 0
         rows, cols, values = rows[rated], cols[rated], values[rated]
-        train = numpy.array(ratings, dtype=numpy.float64)
+        train = dense_copy(ratings)
         test = numpy.zeros(ratings.shape)
         test[rows, cols] = values
         train[rows, cols] = 0

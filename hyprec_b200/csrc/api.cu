@@ -172,6 +172,11 @@ struct hyprec_ctx {
     // instead -- one kernel fewer, but the tensor-memory epilogue owns one ROW per lane, so its peer stores are
     // 16-byte pieces 1 KB apart: measured 111 ms against 88 ms per epoch on 8 B200s at the full scaled size.
     bool fused_push = false;
+    // Low-rank degree buckets: threads per CTA and tile edge (4 or 8) of the shared-memory tile kernel, per bucket
+    // (<= 31 / 63 / 127 / 191 / 255 / 319 unknowns).  HYPREC_BUCKET_THREADS / HYPREC_BUCKET_TILE = six comma-separated
+    // numbers override them (A/B tests, tools/ab_epoch.py).
+    int bucket_threads[6] = {64, 128, 128, 256, 256, 256};
+    int bucket_tile[6] = {4, 4, 8, 8, 8, 8};
     int prof_slot = 0;             // HYPREC_SOLVE_PROF_SLOT: which launch class (0 direct, 1..6 buckets, 7 heavy)
     bool prof_enabled = false;     // HYPREC_SOLVE_PROF=1: per-phase clock64() totals of the direct solve
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -871,8 +876,6 @@ struct Engine : EngineBase {
     // Degree buckets of the low-rank path: upper dimension, threads per CTA, tile edge.
     static constexpr int kMaxBuckets = 6;
     static constexpr int kBucketDim[kMaxBuckets] = {31, 63, 127, 191, 255, 319};
-    static constexpr int kBucketThreads[kMaxBuckets] = {64, 128, 128, 256, 256, 256};
-    static constexpr int kBucketTile[kMaxBuckets] = {4, 4, 8, 8, 8, 8};
     static constexpr int kSplitCounterSlot = 8;
     static constexpr int64_t kSplitMinWork = 4096;
 
@@ -880,7 +883,7 @@ struct Engine : EngineBase {
     int usable_buckets() const {
         int nbk = 0;
         for (int b = 0; b < kMaxBuckets; ++b)
-            if (hyprec::solve_layout(kBucketTile[b], kBucketDim[b], 8, true, sizeof(T)).total <= (size_t)h->max_smem) nbk = b + 1;
+            if (hyprec::solve_layout(h->bucket_tile[b], kBucketDim[b], 8, true, sizeof(T)).total <= (size_t)h->max_smem) nbk = b + 1;
         return nbk;
     }
 
@@ -1682,7 +1685,7 @@ struct Engine : EngineBase {
                         // HYPREC_TC_CHOL (default) every bucket up to 256 rows also factorises in tensor
                         // memory -- the small ones several per CTA pass (tc_chol_multi.cuh)
                         const bool f32 = sizeof(T) == sizeof(float);
-                        const bool tc = h->tc_solve_enabled && f32 && kBucketTile[b] == 8 && k % 4 == 0 && pl.bucket_dim[b] <= 256;
+                        const bool tc = h->tc_solve_enabled && f32 && h->bucket_tile[b] == 8 && k % 4 == 0 && pl.bucket_dim[b] <= 256;
                         const bool chol = tc && h->tc_chol_enabled && pl.bucket_dim[b] > 128;
                         // rows of <= 32 positives: one warp per row, float64 arithmetic in both precisions (small_f64.cuh)
                         const bool small = h->small_f64_enabled && pl.bucket_dim[b] <= hyprec::kSmallDim && prior_ptr == nullptr;
@@ -1703,9 +1706,9 @@ struct Engine : EngineBase {
                         }
                         if (!chol && !multi && !small)
                         HY_TRY(launch_rows(user, lambda, lo, hi, lists + pl.bucket_off[b], cnt, true, pl.bucket_dim[b],
-                                           tc ? hyprec::kSolveThreads : kBucketThreads[b], q_ptr,
+                                           tc ? hyprec::kSolveThreads : h->bucket_threads[b], q_ptr,
                                            prior_ptr ? pq.as<T>() : nullptr, nullptr, nullptr, cnt, h->aux[b], 1 + b,
-                                           kBucketTile[b], tc, pl.bucket_off[b]));
+                                           h->bucket_tile[b], tc, pl.bucket_off[b]));
                         CU_TRY(cudaEventRecord(h->ev_join[b], h->aux[b]));
                         CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
                     }
@@ -2672,6 +2675,29 @@ int hyprec_create(hyprec_t** out, int device_id, int precision) {
     h->split_enabled = !(spl && spl[0] == '0');
     const char* lr = getenv("HYPREC_LOWRANK");
     h->lowrank_enabled = !(lr && lr[0] == '0');
+    auto six = [](const char* name, int* out, int lo, int hi, int multiple) {
+        const char* v = getenv(name);
+        if (!v) return;
+        int got[6], n = 0;
+        while (n < 6 && *v) {
+            char* end = nullptr;
+            const long x = strtol(v, &end, 10);
+            if (end == v || x < lo || x > hi || x % multiple != 0) return;      // malformed: keep the defaults
+            got[n++] = (int)x;
+            v = (*end == ',') ? end + 1 : end;
+            if (*end != ',' && *end != 0) return;
+        }
+        if (n == 6) for (int i = 0; i < 6; ++i) out[i] = got[i];
+    };
+    if (precision == HYPREC_F64) {
+        // float64: systems of up to 127 unknowns on 4 x 4 tiles (no register spills, twice the threads per system):
+        // 1.90 -> 1.74 ms per citeulike-a epoch, 3.45 -> 3.15 ms at the citeulike-t shape (tools/ab_epoch.py,
+        // profiles/r02_ab_*.jsonl).  float32 keeps 8 x 8 tiles there: its <= 127 bucket runs in tensor memory.
+        const int threads64[6] = {64, 96, 256, 256, 256, 256}, tile64[6] = {4, 4, 4, 8, 8, 8};
+        for (int i = 0; i < 6; ++i) { h->bucket_threads[i] = threads64[i]; h->bucket_tile[i] = tile64[i]; }
+    }
+    six("HYPREC_BUCKET_THREADS", h->bucket_threads, 32, 1024, 32);
+    six("HYPREC_BUCKET_TILE", h->bucket_tile, 4, 8, 4);
     const char* lc = getenv("HYPREC_LOWRANK_CAP");
     if (lc) h->lowrank_cap = std::max(0, atoi(lc));
     if (precision == HYPREC_F64) h->engine = new Engine<double>(h);

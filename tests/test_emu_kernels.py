@@ -539,3 +539,22 @@ def test_small_systems_one_warp_per_row_f32_factors(emu, k):
             assert numpy.isclose(cross[r], (rv.dot(rv) - z.dot(z)) / 0.9, rtol=1e-10, atol=1e-12)
         else:
             assert cross[r] == 0.0
+
+
+@pytest.mark.parametrize("ts,threads", [(4, 512), (4, 256), (8, 256)])
+def test_lowrank_rows_of_a_hundred_positives_with_many_threads(emu, ts, threads):
+    """The <= 127 bucket with other launch shapes than the default 8 x 8 tiles on 128 threads (HYPREC_BUCKET_TILE /
+    HYPREC_BUCKET_THREADS, tools/ab_epoch.py): systems of ~100 unknowns on 4 x 4 tiles and up to 512 threads."""
+    rs = numpy.random.RandomState(ts + threads)
+    m, n, k = 3, 250, 20
+    train = (rs.rand(m, n) < 0.42).astype(numpy.float64)
+    csr = oals.to_csr(train)
+    assert numpy.diff(csr.indptr).max() > 95
+    u0, v0 = rs.rand(m, k), rs.rand(n, k)
+    want = oals.als_half_step(u0.copy(), v0, csr, 0.05)
+    out = u0.copy()
+    ip, ix = csr.indptr.astype(numpy.int64), csr.indices.astype(numpy.int32)
+    status = emu.emu_half_step_lowrank_f64(_ptr(ip), _ptr(ix), _ptr(csr.data), _ptr(v0), I64(n), _ptr(out), I64(m), k,
+                                           DBL(0.05), None, 1000, threads, 2, 0, ts)
+    assert status == 0
+    assert numpy.allclose(out, want, rtol=1e-10, atol=1e-12)

@@ -155,10 +155,13 @@ def measured_peaks():
 
 
 def csrc_fingerprint():
-    """sha256 over the kernel sources: recorded ncu traffic figures only apply to the kernels they were taken from."""
+    """sha256 over the kernel sources: recorded ncu traffic figures only apply to the kernels they were taken from.
+    (host_*.cuh hold host-only code -- the split's random stream -- and launch nothing.)"""
     sha = hashlib.sha256()
     base = os.path.join(ROOT, "hyprec_b200", "csrc")
     for name in sorted(os.listdir(base)):
+        if name.startswith("host_"):
+            continue
         with open(os.path.join(base, name), "rb") as f:
             sha.update(f.read())
     return sha.hexdigest()[:16]

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libhyprec_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "host_split.cuh", "comm.cuh", "small_f64.cuh", "gram.cuh", "als_solve.cuh", "score.cuh", "topk.cuh", "tc_score.cuh", "tc_syrk.cuh", "tc_chol.cuh", "tc_chol_multi.cuh"]
+HEADERS = ["common.cuh", "host_split.cuh", "host_api.cuh", "comm.cuh", "small_f64.cuh", "gram.cuh", "als_solve.cuh", "score.cuh", "topk.cuh", "tc_score.cuh", "tc_syrk.cuh", "tc_chol.cuh", "tc_chol_multi.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -258,7 +258,9 @@ int hyprec_flush_l2(hyprec_t* h);
  * entries are rated cells.  ids64 and / or ids32 receive the lists (either may be NULL); capacity = entries they
  * hold (n_users * k_folds * (n_items / k_folds) always suffices).  HYPREC_E_UNSUPPORTED, with the generator state
  * untouched, when a list would need the reference's negative slice bounds (a fold's positives outnumber
- * n_items / k_folds): the caller then runs the reference's loop. */
+ * n_items / k_folds): the caller then runs the reference's loop.  indices must be strictly increasing within a row.
+ * The stream is walked sequentially (which draws a shuffle consumes does not depend on the data shuffled); the
+ * shuffles themselves run on up to 16 host threads (HYPREC_HOST_THREADS). */
 /* The draws of Evaluator.naive_split_users (lib/evaluator.py:92-93) from numpy's global MT19937 state (as above):
  * per user, in user order, sizes[u] = int(test_percentage * len_u) samples WITH replacement among the user's len_u
  * ratings (numpy.random.choice -> legacy randint: masked rejection draws; none when len_u == 1).  picks receives

@@ -389,3 +389,21 @@ def test_native_naive_split_equals_the_numpy_loop(monkeypatch, sparse):
         assert numpy.array_equal(py[2], nat[2])
         for a, b in zip(py[3] + py[4], nat[3] + nat[4]):
             assert numpy.array_equal(a, b)
+
+
+def test_native_kfold_lists_do_not_depend_on_the_thread_count(monkeypatch):
+    """The stream is walked once sequentially and the shuffles run on host threads from recorded generator states
+    (csrc/host_split.cuh): one thread, three threads and more threads than users give the same lists and leave the
+    global generator at the same position."""
+    rs = numpy.random.RandomState(9)
+    ratings = (rs.rand(23, 400) < 0.05).astype(float)
+    got = []
+    for threads in ("1", "3", "64"):
+        monkeypatch.setenv("HYPREC_HOST_THREADS", threads)
+        ev = Evaluator(ratings.copy())
+        ev.set_kfolds(4)
+        lists = ev.get_kfold_indices()
+        assert ev._flat[0] is lists
+        got.append((numpy.concatenate(lists), numpy.random.random(3)))
+    for other in got[1:]:
+        assert numpy.array_equal(got[0][0], other[0]) and numpy.array_equal(got[0][1], other[1])

@@ -362,7 +362,11 @@ class CollaborativeFiltering(AbstractRecommender):
         pool = self.__dict__.get('_ahead_pool')
         if pool is None:
             pool = self._ahead_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="hyprec-fold")
-        return pool.submit(work)
+        try:
+            return pool.submit(work)
+        except RuntimeError:                # shut down by close() of a shallow copy of this object
+            pool = self._ahead_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="hyprec-fold")
+            return pool.submit(work)
 
     def train_one_fold(self, item_vecs=None):
         """collaborative_filtering.py:164-212: initialise (random / theta / checkpoint), train,

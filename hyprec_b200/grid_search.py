@@ -204,6 +204,8 @@ class GridSearch(object):
         rec.last_report_details = None
         rec.predictions = None
         rec._single_rank = True
+        rec.__dict__.pop('_ahead_pool', None)          # (a k-fold run's host thread belongs to the caller's object)
+        rec._cands_ready = None
         return rec
 
     def _prepare(self, rec, hyperparameters, shared):

@@ -339,7 +339,10 @@ class Evaluator(object):
 
     def _remember_csr(self, train, test, test_keys):
         views = self._split_triplets(test_keys, only_rated=False)
-        self._csr_views = (getattr(self, '_csr_views', []) + [(train, views[0]), (test, views[1])])[-4:]
+        # (the views of the latest TWO folds are kept, the class prepares fold f + 1 while fold f is on the device --
+        # unless two more dense users x items matrices alive would be felt, where it does not prefetch either)
+        keep = 4 if 16 * self.n_users * self.n_items <= (4 << 30) else 2
+        self._csr_views = (getattr(self, '_csr_views', []) + [(train, views[0]), (test, views[1])])[-keep:]
 
     def _split_sparse(self, test_keys):
         """train / test as scipy CSR matrices, straight from the index lists (sparse ``ratings``)."""
